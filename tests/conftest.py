@@ -1,0 +1,50 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+
+
+def rel_rms(a, b) -> float:
+    """relative RMS error ||a-b|| / ||b|| (b = oracle)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    den = float(np.sqrt(np.mean(np.abs(b.astype(np.complex128)) ** 2)))
+    num = float(np.sqrt(np.mean(np.abs(a.astype(np.complex128) - b.astype(np.complex128)) ** 2)))
+    return num / den if den > 0 else num
+
+
+def wrap_rel_rms(a, b, period) -> float:
+    """rel-RMS for phase-like outputs: differences are wrapped into (-period/2, period/2]
+    (an angle of -pi+eps and +pi-eps are the same discriminator value up to rounding)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    d = a - b
+    d = d - period * np.round(d / period)
+    den = float(np.sqrt(np.mean(b ** 2)))
+    return float(np.sqrt(np.mean(d ** 2))) / den if den > 0 else float(np.sqrt(np.mean(d ** 2)))
+
+
+@pytest.fixture(scope="session")
+def native():
+    """The ctypes library on an initialised B200; GPU tests fail loudly if it is missing."""
+    import wavecap_sdr_b200._native as N
+
+    N.init(0)
+    return N
+
+
+def golden_path(name: str) -> str:
+    return os.path.join(GOLDEN, name)

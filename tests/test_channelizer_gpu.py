@@ -1,0 +1,159 @@
+"""GPU parity: csrc/channelizer.cu vs the oracle restatement of wavecapsdr/dsp/channelizer.py.
+
+Tolerance (BASELINE.json north_star): float outputs within 1e-4 relative RMS of the reference."""
+import numpy as np
+import pytest
+
+from conftest import rel_rms, wrap_rel_rms, golden_path
+from oracle.channelizer import ChannelizerOracle, channelize_fm
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _iq(n, seed, scale=0.5):
+    rng = np.random.default_rng(seed)
+    return ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * scale).astype(np.complex64)
+
+
+def _chan(native, fs, bw, t=9):
+    from wavecap_sdr_b200.dsp.channelizer import PolyphaseChannelizer
+
+    return PolyphaseChannelizer(fs, bw, t)
+
+
+def test_attrs_match_reference_design(native):
+    ch = _chan(native, 125_000_000, 488281)
+    o = ChannelizerOracle(125_000_000, 488281)
+    assert ch.channel_count == 256 and ch.taps_per_channel == 9
+    assert ch.channel_sample_rate == o.channel_sample_rate
+    assert ch.arms.shape == (256, 9) and ch.arms.dtype == np.float64
+    assert np.abs(ch.arms - o.arms).max() < 1e-12  # in-library firwin/kaiser vs scipy
+
+
+@pytest.mark.parametrize("n", [255, 256, 383, 384, 1279, 2048, 40000, 123457])
+def test_c5_complex_frames_single_call(native, n):
+    ch = _chan(native, 125_000_000, 488281)
+    o = ChannelizerOracle(125_000_000, 488281)
+    x = _iq(n, 5)
+    got = ch.process(x)
+    exp = o.process(x)
+    assert isinstance(got, list) and len(got) == exp.shape[0]
+    if exp.shape[0]:
+        got = np.stack(got)
+        assert got.dtype == np.complex64
+        assert rel_rms(got, exp) < TOL
+        assert rel_rms(ch.arm_history, o.arm_history) == 0.0
+
+
+def test_c5_state_carries_across_calls_and_reset(native):
+    ch = _chan(native, 125_000_000, 488281)
+    o = ChannelizerOracle(125_000_000, 488281)
+    x = _iq(60000, 6)
+    cuts = [0, 5120, 10240, 10240 + 300, 10240 + 300 + 777, 40001, 60000]  # ragged, incl. < 9 frames
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        got = ch.process_array(x[a:b])
+        exp = o.process_vectorized(x[a:b])
+        assert got.shape == exp.shape
+        if exp.size:
+            assert rel_rms(got, exp) < TOL
+        assert np.array_equal(ch.arm_history, o.arm_history)
+    ch.reset(); o.reset()
+    assert not ch.arm_history.any()
+    assert rel_rms(ch.process_array(x[:4096]), o.process(x[:4096])) < TOL
+
+
+def test_c5_two_short_calls_drop_the_straddling_frame(native):
+    # two 5120-sample calls give 78 frames, one 10240-sample call gives 79
+    ch = _chan(native, 125_000_000, 488281)
+    x = _iq(10240, 7)
+    assert len(ch.process(x)) == 79
+    ch.reset()
+    assert len(ch.process(x[:5120])) + len(ch.process(x[5120:])) == 78
+
+
+def test_c5_fused_fm_discriminator(native):
+    ch = _chan(native, 125_000_000, 488281)
+    o = ChannelizerOracle(125_000_000, 488281)
+    x = _iq(256 + 128 * 700, 8)
+    rate = int(ch.channel_sample_rate)
+    for part in (x[:50000], x[50000:]):
+        got = ch.process_fm(part, rate)
+        exp = channelize_fm(o.process_vectorized(part), rate)
+        assert got.dtype == np.float32 and got.shape == exp.shape
+        assert not got[0].any()
+        period = 2 * np.pi * float(np.float32(rate / (2.0 * np.pi * 75000.0)))
+        assert wrap_rel_rms(got, exp, period) < TOL
+
+
+def test_c5_batched_chunks_equal_sequential_calls(native):
+    ch = _chan(native, 125_000_000, 488281)
+    o = ChannelizerOracle(125_000_000, 488281)
+    n, b = 30000, 4
+    x = _iq(n * b, 9)
+    exp = np.concatenate([o.process_vectorized(x[i * n:(i + 1) * n]) for i in range(b)])
+    got = ch.process_batch(x, b)
+    assert rel_rms(got, exp) < TOL
+    assert np.array_equal(ch.arm_history, o.arm_history)
+    ch.reset(); o.reset()
+    rate = int(ch.channel_sample_rate)
+    expf = np.concatenate([channelize_fm(o.process_vectorized(x[i * n:(i + 1) * n]), rate) for i in range(b)])
+    gotf = ch.process_batch(x, b, fm=True, demod_sample_rate=rate)
+    period = 2 * np.pi * float(np.float32(rate / (2.0 * np.pi * 75000.0)))
+    assert wrap_rel_rms(gotf, expf, period) < TOL
+
+
+def test_generic_channel_counts(native):
+    # benchmark_dsp.py:117-123 workload: 8 MS/s, 25 kHz -> 320 channels (not a power of two)
+    for fs, bw, t in ((8_000_000, 25000, 9), (2_400_000, 200000, 5), (1_000_000, 12500, 9)):
+        ch = _chan(native, fs, bw, t)
+        o = ChannelizerOracle(fs, bw, t)
+        assert ch.channel_count == o.channel_count
+        x = _iq(o.channel_count * 40 + 17, 10)
+        for part in (x[: x.size // 3], x[x.size // 3:]):
+            got, exp = ch.process_array(part), o.process_vectorized(part)
+            assert rel_rms(got, exp) < TOL
+        assert np.array_equal(ch.arm_history, o.arm_history)
+
+
+def test_golden_channelizer_fixture(native):
+    g = np.load(golden_path("channelizer_c5.npz"))
+    ch = _chan(native, float(g["fs"]), int(g["bw"]))
+    x = g["x"]
+    got1 = ch.process_array(x[: int(g["cut"])])
+    got2 = ch.process_array(x[int(g["cut"]):])
+    assert rel_rms(got1, g["frames1"]) < TOL and rel_rms(got2, g["frames2"]) < TOL
+
+
+def test_device_tensor_path(native):
+    import torch
+
+    ch = _chan(native, 125_000_000, 488281)
+    o = ChannelizerOracle(125_000_000, 488281)
+    x = _iq(70000, 11)
+    xd = torch.from_numpy(x).cuda()
+    got = ch.process_array(xd)
+    assert got.is_cuda and got.dtype == torch.complex64
+    assert rel_rms(got.cpu().numpy(), o.process_vectorized(x)) < TOL
+
+
+def test_full_size_properties(native):
+    """BASELINE config 5 size (6.25 M samples): linearity + shift-consistency, no oracle needed."""
+    import torch
+
+    ch = _chan(native, 125_000_000, 488281)
+    n = 6_250_000
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.view_as_complex(torch.randn((n, 2), generator=g, device="cuda") * 0.5)
+    b = torch.view_as_complex(torch.randn((n, 2), generator=g, device="cuda") * 0.5)
+    ya = ch.process_array(a); ch.reset()
+    yb = ch.process_array(b); ch.reset()
+    yab = ch.process_array(2.0 * a - 0.5 * b); ch.reset()
+    assert ya.shape == (48827, 256)
+    err = (yab - (2.0 * ya - 0.5 * yb)).abs().pow(2).mean().sqrt() / yab.abs().pow(2).mean().sqrt()
+    assert float(err) < 1e-5
+    # frame b of x[128*s:] equals frame b+s of x once the 9-block history is filled
+    s = 16
+    ys = ch.process_array(a[128 * s:].contiguous()); ch.reset()
+    err2 = (ys[9:1000] - ya[9 + s:1000 + s]).abs().max()
+    assert float(err2) < 1e-4 * float(ya.abs().max())

@@ -1,0 +1,138 @@
+"""ctypes binding of libwcsdr_b200.so (the C-ABI declared in include/wcsdr_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or no B200 is present, every compute
+entry point raises. Only `tests/`, `bench.py --impl reference` and `smoke()` may touch `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libwcsdr_b200.so"
+
+_lib = None
+_lock = threading.Lock()
+_inited_device: int | None = None
+
+
+class NativeError(RuntimeError):
+    """Raised when the CUDA library reports an error (or is not built)."""
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once). Raises NativeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise NativeError(
+                f"{LIB_PATH} not found — build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "wavecap_sdr_b200 has no CPU fallback."
+            )
+        l = C.CDLL(str(LIB_PATH))
+        _declare(l)
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().wc_last_error().decode("utf-8", "replace")
+        raise NativeError(f"wcsdr_b200 error {rc}: {msg}")
+
+
+def init(device: int | None = None) -> None:
+    """Select the CUDA device (default: LOCAL_RANK or 0) and verify it is sm_100."""
+    global _inited_device
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _inited_device == device:
+        return
+    check(lib().wc_init(device))
+    _inited_device = device
+
+
+def ensure_init() -> None:
+    if _inited_device is None:
+        init()
+
+
+# ---- pointer helpers -------------------------------------------------------------------------------
+
+def np_ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def is_torch_cuda(x) -> bool:
+    return hasattr(x, "is_cuda") and bool(getattr(x, "is_cuda"))
+
+
+def torch_stream_ptr() -> C.c_void_p:
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array backed by CUDA pinned host memory (torch is only the allocator)."""
+    import torch
+
+    tdt = {np.dtype(np.complex64): torch.complex64, np.dtype(np.float32): torch.float32,
+           np.dtype(np.int16): torch.int16, np.dtype(np.uint8): torch.uint8,
+           np.dtype(np.float64): torch.float64, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+    t = torch.empty(shape, dtype=tdt, pin_memory=True)
+    a = t.numpy()
+    _keepalive[id(a)] = t
+    return a
+
+
+_keepalive: dict[int, object] = {}
+
+
+# ---- prototypes ------------------------------------------------------------------------------------
+
+def _declare(l: C.CDLL) -> None:
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+    P = C.POINTER
+
+    def fn(name, res, *args):
+        f = getattr(l, name)
+        f.restype = res
+        f.argtypes = list(args)
+
+    fn("wc_init", i32, i32)
+    fn("wc_last_error", C.c_char_p)
+    fn("wc_version", C.c_char_p)
+    fn("wc_device_info", i32, P(i32), P(i32), P(i32), P(i64))
+    # channelizer
+    fn("wc_chan_create", i32, f64, i32, i32, P(vp))
+    fn("wc_chan_destroy", None, vp)
+    fn("wc_chan_info", i32, vp, P(i32), P(f64), P(i32))
+    fn("wc_chan_get_arms", i32, vp, vp)
+    fn("wc_chan_get_history", i32, vp, vp)
+    fn("wc_chan_frames_for", i64, vp, i64)
+    fn("wc_chan_reset", i32, vp)
+    fn("wc_chan_process", i32, vp, vp, i64, i32, i64, i32, f32, vp, vp)
+    fn("wc_chan_process_host", i32, vp, vp, i64, i32, i32, f32, vp)
+    for extra in _EXTRA_DECLS:
+        extra(l, fn)
+
+
+_EXTRA_DECLS: list = []
+
+
+def exported_symbols() -> list[str]:
+    """Every `wc_*` function declared in include/wcsdr_b200.h (parsed from the header)."""
+    import re
+
+    hdr = (_PKG.parent / "include" / "wcsdr_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(wc_[a-z0-9_]+)\s*\(", hdr)))

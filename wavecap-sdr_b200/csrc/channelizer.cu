@@ -1,0 +1,621 @@
+// Polyphase channelizer (NMDPFB, 2x oversampled) — B200-native.
+//
+// Replaces the per-frame Python loop of wavecapsdr/dsp/channelizer.py:91-137
+// (np.roll + einsum + np.fft.fft per frame) with one grid-wide pass:
+//
+//   u_b[k] = sum_{j=0..T-1} h[k + j*M] * blk_{b-j}[k],   blk_i[k] = x[i*M/2 + k]
+//   y_b    = FFT_M(u_b)                                  (forward, unnormalised, FFT bin order)
+//   fused FM: d_b[k] = angle(y_b[k] * conj(y_{b-1}[k])) * scale, d_0 = 0   (dsp/fm.py:65-97)
+//
+// Fast path (M = 256, T = 9 — the 125 MS/s / 256-channel workload): each CTA owns a contiguous
+// run of frames. Per sub-tile of 8 frames:
+//   phase 1  FIR: thread r keeps a 10-sample sliding window x[q*128 + r] in registers (both
+//            u_b[r] and u_b[r+128] come from the same residue class), new rows arrive in shared
+//            memory through a double-buffered 1-D bulk async copy (TMA engine) so every input
+//            sample is read from HBM exactly once per run.
+//   phase 2  256-point FFT as 16 x 16: 16 threads per frame, two in-register radix-16 passes,
+//            one padded shared-memory exchange.
+//   phase 3  (FM mode) per-bin discriminator with the previous frame's bin kept in registers,
+//            coalesced float2 stores.
+// Generic path (any even M): FIR kernel + direct O(M^2) DFT kernel; correct, not tuned.
+#include <math.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "../../include/wcsdr_b200.h"
+#include "common.cuh"
+
+namespace wc {
+
+constexpr int CH_M = 256;
+constexpr int CH_H = 128;
+constexpr int CH_T = 9;
+constexpr int CH_S = 8;          // frames per sub-tile
+constexpr int CH_THREADS = 128;  // one thread per residue class
+constexpr int CH_REGION = 272;   // complex words per frame region (16 x 17 padded exchange)
+
+struct ChanArgs {
+    const float2* x;       // [n_chunks][chunk_stride] complex64
+    long long chunk_stride;
+    int F;                 // frames per chunk
+    int R;                 // frames per CTA run (multiple of 8, >= 16)
+    const float* taps;     // [M*T] prototype, h[k + j*M], zero padded
+    const float2* carried; // [9][256] blk_{-9..-1} for chunk 0
+    void* out;             // MODE 0: float2 [n_chunks*F][256]; MODE 1: float [n_chunks*F][256]
+    float scale;           // FM discriminator scale
+};
+
+struct __align__(128) ChanSmem {
+    float2 stage[2][CH_S * CH_H];  // TMA landing buffers: 8 rows of 128 samples each
+    float2 u[CH_S * CH_REGION];    // FIR output -> FFT exchange -> FFT output (in place)
+    float2 tw[16 * 16];            // tw[k1*16 + t] = exp(-2*pi*i*k1*t/256)
+    uint64_t full[2];
+};
+
+// forward 4-point DFT in place: (a,b,c,d) -> (X0,X1,X2,X3)
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
+    const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
+    a = cadd(t0, t2);
+    c = csub(t0, t2);
+    b = make_float2(t1.x + t3.y, t1.y - t3.x);
+    d = make_float2(t1.x - t3.y, t1.y + t3.x);
+}
+
+// forward 16-point DFT in registers. Input natural order; X[k] ends up in v[4*(k&3) + (k>>2)].
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+    // twiddles W16^(n2*k1) on v[4*k1 + n2]
+    float2 t;
+    // k1 = 1: W^1, W^2, W^3
+    t = v[5];  v[5]  = make_float2(fmaf(t.x, C1, t.y * S1), fmaf(t.y, C1, -t.x * S1));
+    t = v[6];  v[6]  = make_float2((t.x + t.y) * R2, (t.y - t.x) * R2);
+    t = v[7];  v[7]  = make_float2(fmaf(t.x, S1, t.y * C1), fmaf(t.y, S1, -t.x * C1));
+    // k1 = 2: W^2, W^4, W^6
+    t = v[9];  v[9]  = make_float2((t.x + t.y) * R2, (t.y - t.x) * R2);
+    t = v[10]; v[10] = make_float2(t.y, -t.x);
+    t = v[11]; v[11] = make_float2((t.y - t.x) * R2, -(t.x + t.y) * R2);
+    // k1 = 3: W^3, W^6, W^9
+    t = v[13]; v[13] = make_float2(fmaf(t.x, S1, t.y * C1), fmaf(t.y, S1, -t.x * C1));
+    t = v[14]; v[14] = make_float2((t.y - t.x) * R2, -(t.x + t.y) * R2);
+    t = v[15]; v[15] = make_float2(fmaf(-t.x, C1, -t.y * S1), fmaf(-t.y, C1, t.x * S1));
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+}
+
+__device__ __forceinline__ constexpr int rev4(int o) { return ((o & 3) << 2) | (o >> 2); }
+
+// block value for the slow prologue path: blk_i[k] of chunk c, i may be negative (history)
+__device__ __forceinline__ float2 blk_fetch(const ChanArgs& a, const float2* xc, int c, int i, int k) {
+    if (i >= 0) return xc[(long long)i * CH_H + k];
+    if (c > 0) return (xc - a.chunk_stride)[(long long)(a.F + i) * CH_H + k];
+    return a.carried[(i + CH_T) * CH_M + k];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CH_THREADS, 4) chan256_kernel(const ChanArgs a) {
+    __shared__ ChanSmem sm;
+    const int tid = threadIdx.x;
+    const int r = tid;
+    const int c = blockIdx.y;
+    // run i emits frames [f0, f1); in FM mode runs i > 0 also compute frame f0-1 (needs y_{f0-1}),
+    // so they emit R-1 frames and every run computes a multiple of 8 frames.
+    const int step = (MODE == 1) ? a.R - 1 : a.R;
+    const int f0 = (blockIdx.x == 0) ? 0 : a.R + (blockIdx.x - 1) * step;
+    if (f0 >= a.F) return;
+    const int f1 = min(a.F, (blockIdx.x == 0) ? a.R : f0 + step);
+    const float2* __restrict__ xc = a.x + (long long)c * a.chunk_stride;
+    const long long out_base = (long long)c * a.F;
+
+    // one warm-up frame so the discriminator has y_{f0-1}
+    const int fe = (MODE == 1 && f0 > 0) ? f0 - 1 : f0;
+    const int fast_start = (f0 == 0) ? 8 : fe;
+    const int n_fast = (fast_start < f1) ? (f1 - fast_start + CH_S - 1) / CH_S : 0;
+
+    if (tid == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < 256; i += CH_THREADS) {
+        float s, co;
+        sincospif(-(float)((i >> 4) * (i & 15)) * (1.0f / 128.0f), &s, &co);
+        sm.tw[i] = make_float2(co, s);
+    }
+    __syncthreads();
+
+    auto issue = [&](int n) {
+        const int fs = fast_start + CH_S * n;
+        const int nrows = min(CH_S, a.F - fs);  // rows fs+1 .. fs+nrows (row F is the last one)
+        const uint32_t bytes = (uint32_t)nrows * CH_H * sizeof(float2);
+        mbar_expect_tx(&sm.full[n & 1], bytes);
+        bulk_g2s(sm.stage[n & 1], xc + (long long)(fs + 1) * CH_H, bytes, &sm.full[n & 1]);
+    };
+    if (tid == 0) {
+        if (n_fast > 0) issue(0);
+        if (n_fast > 1) issue(1);
+    }
+
+    float hlo[CH_T], hhi[CH_T];
+#pragma unroll
+    for (int j = 0; j < CH_T; ++j) {
+        hlo[j] = __ldg(a.taps + r + CH_M * j);
+        hhi[j] = __ldg(a.taps + r + CH_H + CH_M * j);
+    }
+
+    float2 prev0 = make_float2(0.f, 0.f), prev1 = make_float2(0.f, 0.f);
+
+    // phases 2 + 3 for the sub-tile whose FIR outputs sit in sm.u (frames fs .. fs+nv-1)
+    auto fft_and_emit = [&](int fs, int nv) {
+        {
+            const int g = tid >> 4, t = tid & 15;
+            float2* reg = sm.u + g * CH_REGION;
+            float2 v[16];
+            if (g < nv) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = reg[t + 16 * i];
+            }
+            __syncwarp();
+            if (g < nv) {
+                fft16(v);
+#pragma unroll
+                for (int k1 = 0; k1 < 16; ++k1) {
+                    float2 w = v[rev4(k1)];
+                    if (k1 > 0) w = cmul(w, sm.tw[k1 * 16 + t]);
+                    reg[t * 17 + k1] = w;
+                }
+            }
+            __syncwarp();
+            if (g < nv) {
+#pragma unroll
+                for (int n2 = 0; n2 < 16; ++n2) v[n2] = reg[n2 * 17 + t];
+            }
+            __syncwarp();
+            if (g < nv) {
+                fft16(v);
+                if (MODE == 0) {
+                    const int b = fs + g;
+                    if (b >= f0) {
+                        float2* o = reinterpret_cast<float2*>(a.out) + (out_base + b) * CH_M + t;
+#pragma unroll
+                        for (int k2 = 0; k2 < 16; ++k2) o[16 * k2] = v[rev4(k2)];
+                    }
+                } else {
+#pragma unroll
+                    for (int k2 = 0; k2 < 16; ++k2) reg[t + 16 * k2] = v[rev4(k2)];
+                }
+            }
+        }
+        __syncthreads();
+        if (MODE == 1) {
+            float* o = reinterpret_cast<float*>(a.out);
+            for (int i = 0; i < nv; ++i) {
+                const int b = fs + i;
+                const float4 y = *reinterpret_cast<const float4*>(sm.u + i * CH_REGION + 2 * tid);
+                const float2 y0 = make_float2(y.x, y.y), y1 = make_float2(y.z, y.w);
+                if (b >= f0) {
+                    float2 d;
+                    if (b == 0) {
+                        d = make_float2(0.f, 0.f);
+                    } else {
+                        const float2 p0 = cmulc(y0, prev0), p1 = cmulc(y1, prev1);
+                        d.x = fast_atan2f(p0.y, p0.x) * a.scale;
+                        d.y = fast_atan2f(p1.y, p1.x) * a.scale;
+                    }
+                    *reinterpret_cast<float2*>(o + (out_base + b) * CH_M + 2 * tid) = d;
+                }
+                prev0 = y0;
+                prev1 = y1;
+            }
+            __syncthreads();
+        }
+    };
+
+    // ---- prologue sub-tile: frames 0..7 of a chunk reach into the previous call/chunk ----
+    if (f0 == 0) {
+        const int nv = min(CH_S, f1);
+        for (int b = 0; b < nv; ++b) {
+            float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < CH_T; ++j) {
+                const float2 vl = blk_fetch(a, xc, c, b - j, r);
+                const float2 vh = blk_fetch(a, xc, c, b - j, r + CH_H);
+                lo.x = fmaf(hlo[j], vl.x, lo.x);
+                lo.y = fmaf(hlo[j], vl.y, lo.y);
+                hi.x = fmaf(hhi[j], vh.x, hi.x);
+                hi.y = fmaf(hhi[j], vh.y, hi.y);
+            }
+            sm.u[b * CH_REGION + r] = lo;
+            sm.u[b * CH_REGION + r + CH_H] = hi;
+        }
+        __syncthreads();
+        fft_and_emit(0, nv);
+    }
+    if (n_fast == 0) return;
+
+    // ---- fast path: sliding window over rows fast_start-8 .. ----
+    float2 w[10];
+#pragma unroll
+    for (int m = 0; m < 9; ++m) w[m] = __ldg(xc + (long long)(fast_start - 8 + m) * CH_H + r);
+
+    for (int n = 0; n < n_fast; ++n) {
+        const int fs = fast_start + CH_S * n;
+        const int nv = min(CH_S, f1 - fs);
+        mbar_wait(&sm.full[n & 1], (n >> 1) & 1);
+        const float2* st = sm.stage[n & 1];
+#pragma unroll
+        for (int i = 0; i < CH_S; ++i) {
+            w[9] = st[i * CH_H + r];
+            float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < CH_T; ++j) {
+                lo.x = fmaf(hlo[j], w[8 - j].x, lo.x);
+                lo.y = fmaf(hlo[j], w[8 - j].y, lo.y);
+                hi.x = fmaf(hhi[j], w[9 - j].x, hi.x);
+                hi.y = fmaf(hhi[j], w[9 - j].y, hi.y);
+            }
+            sm.u[i * CH_REGION + r] = lo;
+            sm.u[i * CH_REGION + r + CH_H] = hi;
+#pragma unroll
+            for (int m = 0; m < 9; ++m) w[m] = w[m + 1];
+        }
+        __syncthreads();
+        if (tid == 0 && n + 2 < n_fast) issue(n + 2);
+        fft_and_emit(fs, nv);
+    }
+}
+
+// ---- carried-history update: blk_{-8..-1} for the next call (double buffered) ----
+__global__ void chan_carry_kernel(const float2* x_last, int F, int M, int T1, const float2* old_c, float2* new_c) {
+    // new_c[m][k], m = 0..T1-1 <-> block index F + m - T1 of the last chunk (or older history); T1 = T
+    const int m = blockIdx.x;
+    const int H = M / 2;
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+        const int i = F + m - T1;
+        float2 v;
+        if (i >= 0) v = x_last[(long long)i * H + k];
+        else v = old_c[(i + T1) * M + k];
+        new_c[m * M + k] = v;
+    }
+}
+
+// ---- generic path (any even M): FIR then direct DFT ----
+struct GenArgs {
+    const float2* x;
+    long long chunk_stride;
+    int F, M, T;
+    const float* taps;      // [M*T]
+    const float2* carried;  // [T][M] blk_{-T..-1}
+    float2* u;              // [n_chunks*F][M] workspace
+};
+
+__global__ void chan_generic_fir_kernel(const GenArgs a) {
+    const int c = blockIdx.z;
+    const int b = blockIdx.x;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (k >= a.M) return;
+    const int H = a.M / 2, T1 = a.T;
+    const float2* xc = a.x + (long long)c * a.chunk_stride;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int j = 0; j < a.T; ++j) {
+        const int i = b - j;
+        float2 v;
+        if (i >= 0) v = xc[(long long)i * H + k];
+        else if (c > 0) v = (xc - a.chunk_stride)[(long long)(a.F + i) * H + k];
+        else v = a.carried[(i + T1) * a.M + k];
+        const float h = a.taps[k + j * a.M];
+        acc.x = fmaf(h, v.x, acc.x);
+        acc.y = fmaf(h, v.y, acc.y);
+    }
+    a.u[((long long)c * a.F + b) * a.M + k] = acc;
+}
+
+// one CTA per frame; smem = u[M] + twiddle[M]
+__global__ void chan_generic_dft_kernel(const float2* __restrict__ u, float2* __restrict__ y, int M) {
+    extern __shared__ float2 gsm[];
+    float2* su = gsm;
+    float2* sw = gsm + M;
+    const long long fr = blockIdx.x;
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+        su[k] = u[fr * M + k];
+        double s, co;
+        sincospi(-2.0 * (double)k / (double)M, &s, &co);
+        sw[k] = make_float2((float)co, (float)s);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < M; q += blockDim.x) {
+        float2 acc = make_float2(0.f, 0.f);
+        int idx = 0;
+        for (int k = 0; k < M; ++k) {
+            const float2 p = cmul(su[k], sw[idx]);
+            acc.x += p.x;
+            acc.y += p.y;
+            idx += q;
+            if (idx >= M) idx -= M;
+        }
+        y[fr * M + q] = acc;
+    }
+}
+
+// discriminator over frames for the generic path: y [n_chunks][F][M] -> d
+__global__ void chan_generic_disc_kernel(const float2* __restrict__ y, float* __restrict__ d, int F, int M, float scale) {
+    const int c = blockIdx.z;
+    const int b = blockIdx.x;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const long long o = ((long long)c * F + b) * M + k;
+    if (b == 0) {
+        d[o] = 0.f;
+        return;
+    }
+    const float2 p = cmulc(y[o], y[o - M]);
+    d[o] = fast_atan2f(p.y, p.x) * scale;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+
+static double bessel_i0(double x) {
+    // power series; converges quickly for the beta values used by Kaiser windows
+    double sum = 1.0, term = 1.0;
+    const double q = x * x / 4.0;
+    for (int k = 1; k < 200; ++k) {
+        term *= q / ((double)k * (double)k);
+        sum += term;
+        if (term < 1e-18 * sum) break;
+    }
+    return sum;
+}
+
+// scipy.signal.firwin(numtaps, cutoff, window=("kaiser", beta)) for a single low-pass band,
+// cutoff normalised to Nyquist, scaled to unit DC gain.
+void firwin_kaiser_lowpass(int numtaps, double cutoff, double beta, std::vector<double>& h) {
+    h.resize(numtaps);
+    const double alpha = 0.5 * (numtaps - 1);
+    const double i0b = bessel_i0(beta);
+    double s = 0.0;
+    for (int n = 0; n < numtaps; ++n) {
+        const double m = n - alpha;
+        const double xx = cutoff * m;
+        const double sinc = (xx == 0.0) ? 1.0 : sin(M_PI * xx) / (M_PI * xx);
+        double rr = (numtaps > 1) ? (2.0 * n / (numtaps - 1) - 1.0) : 0.0;
+        double arg = 1.0 - rr * rr;
+        if (arg < 0) arg = 0;
+        const double win = bessel_i0(beta * sqrt(arg)) / i0b;
+        h[n] = cutoff * sinc * win;
+        s += h[n];
+    }
+    for (int n = 0; n < numtaps; ++n) h[n] /= s;
+}
+
+}  // namespace wc
+
+using namespace wc;
+
+struct wc_chan {
+    double sample_rate;
+    int channel_bandwidth;
+    int T;
+    int M;
+    std::vector<double> arms;  // [M][T] float64, as the reference exposes
+    float* d_taps = nullptr;   // [T][M] float32: h[k + j*M]
+    float2* d_carried[2] = {nullptr, nullptr};
+    int cur = 0;
+    // workspaces
+    float2* d_ws = nullptr;   size_t ws_bytes = 0;     // generic path u / y
+    void* d_in = nullptr;     size_t in_bytes = 0;     // host API staging
+    void* d_out = nullptr;    size_t out_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+static int ensure(void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    WC_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+extern "C" {
+
+int wc_chan_create(double sample_rate, int channel_bandwidth, int taps_per_channel, wc_chan** out) {
+    WC_REQUIRE(out != nullptr, "wc_chan_create: out is null");
+    WC_REQUIRE(sample_rate > 0 && channel_bandwidth > 0 && taps_per_channel >= 1 && taps_per_channel <= 64,
+               "wc_chan_create: bad parameters");
+    int M = (int)(sample_rate / (double)channel_bandwidth);  // channelizer.py:53-55
+    if (M % 2 != 0) M -= 1;
+    WC_REQUIRE(M >= 2 && M <= 8192, "wc_chan_create: channel count %d out of range [2, 8192]", M);
+    wc_chan* h = new wc_chan();
+    h->sample_rate = sample_rate;
+    h->channel_bandwidth = channel_bandwidth;
+    h->T = taps_per_channel;
+    h->M = M;
+    // channelizer.py:69-89 prototype + polyphase split
+    std::vector<double> proto;
+    const int L = M * taps_per_channel - 1;
+    const double cutoff = ((double)channel_bandwidth * 0.9) / (sample_rate / 2.0);
+    firwin_kaiser_lowpass(L, cutoff, 8.0, proto);
+    h->arms.assign((size_t)M * taps_per_channel, 0.0);
+    std::vector<float> taps((size_t)M * taps_per_channel, 0.f);
+    for (int k = 0; k < M; ++k)
+        for (int j = 0; j < taps_per_channel; ++j) {
+            const int idx = k + j * M;
+            const double v = idx < L ? proto[idx] : 0.0;
+            h->arms[(size_t)k * taps_per_channel + j] = v;
+            taps[(size_t)j * M + k] = (float)v;
+        }
+    const size_t carry_bytes = sizeof(float2) * (size_t)M * (size_t)taps_per_channel;
+    if (cudaMalloc(&h->d_taps, taps.size() * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&h->d_carried[0], carry_bytes) != cudaSuccess ||
+        cudaMalloc(&h->d_carried[1], carry_bytes) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("wc_chan_create: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return -2;
+    }
+    cudaMemcpy(h->d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemset(h->d_carried[0], 0, carry_bytes);
+    cudaMemset(h->d_carried[1], 0, carry_bytes);
+    *out = h;
+    return 0;
+}
+
+void wc_chan_destroy(wc_chan* h) {
+    if (!h) return;
+    cudaFree(h->d_taps);
+    cudaFree(h->d_carried[0]);
+    cudaFree(h->d_carried[1]);
+    if (h->d_ws) cudaFree(h->d_ws);
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int wc_chan_info(const wc_chan* h, int* channel_count, double* channel_sample_rate, int* taps_per_channel) {
+    WC_REQUIRE(h != nullptr, "wc_chan_info: null handle");
+    if (channel_count) *channel_count = h->M;
+    if (channel_sample_rate) *channel_sample_rate = (h->sample_rate / h->M) * 2.0;  // channelizer.py:58
+    if (taps_per_channel) *taps_per_channel = h->T;
+    return 0;
+}
+
+int wc_chan_get_arms(const wc_chan* h, double* arms) {
+    WC_REQUIRE(h && arms, "wc_chan_get_arms: null argument");
+    for (size_t i = 0; i < h->arms.size(); ++i) arms[i] = h->arms[i];
+    return 0;
+}
+
+long long wc_chan_frames_for(const wc_chan* h, long long n_samples) {
+    if (!h || n_samples < h->M) return 0;
+    return (n_samples - h->M) / (h->M / 2) + 1;  // range(0, len - M + 1, M/2), channelizer.py:114
+}
+
+int wc_chan_reset(wc_chan* h) {
+    WC_REQUIRE(h != nullptr, "wc_chan_reset: null handle");
+    const size_t carry_bytes = sizeof(float2) * (size_t)h->M * (size_t)h->T;
+    WC_CUDA(cudaMemsetAsync(h->d_carried[0], 0, carry_bytes, h->stream));
+    WC_CUDA(cudaMemsetAsync(h->d_carried[1], 0, carry_bytes, h->stream));
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    h->cur = 0;
+    return 0;
+}
+
+// arm_history[k][j] = blk_{last-j}[k] (channelizer.py:64,122-126), complex64 [M][T].
+int wc_chan_get_history(wc_chan* h, void* arm_history_host) {
+    WC_REQUIRE(h && arm_history_host, "wc_chan_get_history: null argument");
+    const int T = h->T;
+    std::vector<float2> c((size_t)h->M * T);
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    WC_CUDA(cudaMemcpy(c.data(), h->d_carried[h->cur], c.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+    float2* o = reinterpret_cast<float2*>(arm_history_host);
+    for (int k = 0; k < h->M; ++k)
+        for (int j = 0; j < T; ++j) o[(size_t)k * T + j] = c[(size_t)(T - 1 - j) * h->M + k];
+    return 0;
+}
+
+int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_chunks, long long chunk_stride,
+                    int mode, float fm_scale, void* out_dev, void* stream_v) {
+    WC_REQUIRE(h && iq_dev && out_dev, "wc_chan_process: null argument");
+    WC_REQUIRE(mode == WC_CHAN_OUT_COMPLEX || mode == WC_CHAN_OUT_FM, "wc_chan_process: bad mode %d", mode);
+    WC_REQUIRE(n_chunks >= 1, "wc_chan_process: n_chunks must be >= 1");
+    cudaStream_t stream = (cudaStream_t)stream_v;  // taken literally: NULL = the CUDA default stream
+    const long long F = wc_chan_frames_for(h, n_samples);
+    if (F == 0) return 0;
+    WC_REQUIRE(F < (1LL << 30), "wc_chan_process: chunk too long");
+    const int T1 = h->T;
+    WC_REQUIRE(n_chunks == 1 || F >= T1, "wc_chan_process: batched chunks need >= %d frames each", T1);
+    WC_REQUIRE(n_chunks == 1 || chunk_stride >= n_samples, "wc_chan_process: chunk_stride < n_samples");
+    const float2* x = reinterpret_cast<const float2*>(iq_dev);
+
+    const bool fast = (h->M == CH_M && h->T == CH_T && ((uintptr_t)iq_dev % 16 == 0) &&
+                       (n_chunks == 1 || chunk_stride % 2 == 0));
+    if (fast) {
+        ChanArgs a;
+        a.x = x;
+        a.chunk_stride = chunk_stride;
+        a.F = (int)F;
+        a.taps = h->d_taps;
+        a.carried = h->d_carried[h->cur];
+        a.out = out_dev;
+        a.scale = fm_scale;
+        int R;
+        if (const char* e = getenv("WC_CHAN_R")) {
+            R = atoi(e);
+        } else {
+            const long long total = F * n_chunks;
+            const long long target = (long long)sm_count() * 4 * 6;
+            R = (int)((total + target - 1) / target);
+        }
+        R = ((R + 7) / 8) * 8;
+        if (R < 16) R = 16;
+        if (R > 256) R = 256;
+        a.R = R;
+        const int step = (mode == WC_CHAN_OUT_FM) ? R - 1 : R;
+        const unsigned runs = (F > R) ? 1u + (unsigned)((F - R + step - 1) / step) : 1u;
+        dim3 grid(runs, (unsigned)n_chunks);
+        if (mode == WC_CHAN_OUT_COMPLEX) chan256_kernel<0><<<grid, CH_THREADS, 0, stream>>>(a);
+        else chan256_kernel<1><<<grid, CH_THREADS, 0, stream>>>(a);
+        WC_CUDA(cudaGetLastError());
+    } else {
+        const size_t need = sizeof(float2) * (size_t)F * n_chunks * h->M * (mode == WC_CHAN_OUT_FM ? 2 : 1);
+        if (ensure((void**)&h->d_ws, &h->ws_bytes, need)) return -2;
+        GenArgs g;
+        g.x = x;
+        g.chunk_stride = chunk_stride;
+        g.F = (int)F;
+        g.M = h->M;
+        g.T = h->T;
+        g.taps = h->d_taps;
+        g.carried = h->d_carried[h->cur];
+        g.u = h->d_ws;
+        dim3 fgrid((unsigned)F, (h->M + 127) / 128, (unsigned)n_chunks);
+        chan_generic_fir_kernel<<<fgrid, 128, 0, stream>>>(g);
+        float2* y = (mode == WC_CHAN_OUT_FM) ? h->d_ws + (size_t)F * n_chunks * h->M
+                                             : reinterpret_cast<float2*>(out_dev);
+        const size_t smem = sizeof(float2) * 2 * h->M;
+        if (smem > 48 * 1024)
+            WC_CUDA(cudaFuncSetAttribute(chan_generic_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chan_generic_dft_kernel<<<(unsigned)(F * n_chunks), 256, smem, stream>>>(h->d_ws, y, h->M);
+        if (mode == WC_CHAN_OUT_FM)
+            chan_generic_disc_kernel<<<fgrid, 128, 0, stream>>>(y, reinterpret_cast<float*>(out_dev), (int)F, h->M, fm_scale);
+        WC_CUDA(cudaGetLastError());
+    }
+    {
+        const float2* x_last = x + (long long)(n_chunks - 1) * chunk_stride;
+        chan_carry_kernel<<<T1, 256, 0, stream>>>(x_last, (int)F, h->M, T1, h->d_carried[h->cur], h->d_carried[h->cur ^ 1]);
+        WC_CUDA(cudaGetLastError());
+        h->cur ^= 1;
+    }
+    return 0;
+}
+
+int wc_chan_process_host(wc_chan* h, const void* iq_host, long long n_samples, int n_chunks, int mode,
+                         float fm_scale, void* out_host) {
+    WC_REQUIRE(h && iq_host && out_host, "wc_chan_process_host: null argument");
+    const long long F = wc_chan_frames_for(h, n_samples);
+    if (F == 0) return 0;
+    const long long stride = (n_samples + 1) & ~1LL;  // keep chunk bases 16-byte aligned
+    const size_t in_need = sizeof(float2) * (size_t)stride * n_chunks;
+    const size_t esz = (mode == WC_CHAN_OUT_FM) ? sizeof(float) : sizeof(float2);
+    const size_t out_need = esz * (size_t)F * n_chunks * h->M;
+    if (ensure(&h->d_in, &h->in_bytes, in_need)) return -2;
+    if (ensure(&h->d_out, &h->out_bytes, out_need)) return -2;
+    if (stride == n_samples) {
+        WC_CUDA(cudaMemcpyAsync(h->d_in, iq_host, sizeof(float2) * (size_t)n_samples * n_chunks, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        WC_CUDA(cudaMemcpy2DAsync(h->d_in, sizeof(float2) * stride, iq_host, sizeof(float2) * n_samples,
+                                  sizeof(float2) * n_samples, n_chunks, cudaMemcpyHostToDevice, h->stream));
+    }
+    int rc = wc_chan_process(h, h->d_in, n_samples, n_chunks, stride, mode, fm_scale, h->d_out, h->stream);
+    if (rc) return rc;
+    WC_CUDA(cudaMemcpyAsync(out_host, h->d_out, out_need, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // extern "C"

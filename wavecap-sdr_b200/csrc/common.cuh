@@ -1,0 +1,116 @@
+// Shared helpers for the wcsdr_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace wc {
+
+// ---- error plumbing: every C-ABI entry returns 0 or a negative code and leaves a message ----
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define WC_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            ::wc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,               \
+                            cudaGetErrorString(_e));                                    \
+            return -2;                                                                  \
+        }                                                                               \
+    } while (0)
+
+#define WC_REQUIRE(cond, ...)                                                           \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            ::wc::set_error(__VA_ARGS__);                                               \
+            return -1;                                                                  \
+        }                                                                               \
+    } while (0)
+
+int sm_count();
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) — global -> shared.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WC_DONE_%=;\n"
+        "bra WC_WAIT_%=;\n"
+        "WC_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- small complex helpers on float2 ----
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+
+// atan2 with a degree-13 odd minimax polynomial (relative error <= 6.5e-7, fitted offline with
+// tools/fit_atan.py). No divergence, one MUFU.RCP. atan2(0,0)=0 like numpy.
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = __fdividef(mn, fmaxf(mx, 1e-37f));
+    const float s = t * t;
+    float p = 0.008007131516933441f;
+    p = fmaf(p, s, -0.037443727254867554f);
+    p = fmaf(p, s, 0.08435501158237457f);
+    p = fmaf(p, s, -0.13512229919433594f);
+    p = fmaf(p, s, 0.198873370885849f);
+    p = fmaf(p, s, -0.3332701623439789f);
+    p = fmaf(p, s, 0.9999994039535522f);
+    float a = p * t;
+    a = (ay > ax) ? (1.57079632679489662f - a) : a;
+    a = (x < 0.0f) ? (3.14159265358979324f - a) : a;
+    return copysignf(a, y);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace wc

@@ -1,0 +1,160 @@
+"""GPU polyphase channelizer with the call surface of `wavecapsdr.dsp.channelizer`.
+
+Mirrors (names, argument meaning, return contracts) wavecapsdr/dsp/channelizer.py:
+`PolyphaseChannelizer` (:28-158), `ChannelCalculator` (:161-231), `channelize_samples` (:234-268).
+All arithmetic runs in csrc/channelizer.cu through the C ABI (`wc_chan_*`).
+
+Extra, GPU-only entry points (not in the reference): `process_array`, `process_fm`,
+`process_batch` and device-tensor inputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from .. import _native as N
+
+DEFAULT_CHANNEL_BANDWIDTH = 25000
+DEFAULT_TAPS_PER_CHANNEL = 9
+PERFECT_RECONSTRUCTION_GAIN = 0.5
+
+OUT_COMPLEX = 0
+OUT_FM = 1
+
+
+def fm_scale(sample_rate: int) -> float:
+    """Discriminator scale of dsp/fm.py:94: float32(fs / (2*pi*75000))."""
+    return float(np.float32(sample_rate / (2.0 * np.pi * 75000.0)))
+
+
+class PolyphaseChannelizer:
+    """2x-oversampled polyphase filter bank; state carries across `process()` calls."""
+
+    def __init__(self, sample_rate: float, channel_bandwidth: int = DEFAULT_CHANNEL_BANDWIDTH,
+                 taps_per_channel: int = DEFAULT_TAPS_PER_CHANNEL):
+        N.ensure_init()
+        self.sample_rate = sample_rate
+        self.channel_bandwidth = channel_bandwidth
+        self.taps_per_channel = taps_per_channel
+        h = C.c_void_p()
+        N.check(N.lib().wc_chan_create(float(sample_rate), int(channel_bandwidth), int(taps_per_channel),
+                                       C.byref(h)))
+        self._h = h
+        m, rate, t = C.c_int(), C.c_double(), C.c_int()
+        N.check(N.lib().wc_chan_info(self._h, C.byref(m), C.byref(rate), C.byref(t)))
+        self.channel_count = m.value
+        self.channel_sample_rate = rate.value
+        self.block_counter = 0  # unused by the reference as well (channelizer.py:67)
+        arms = np.empty((self.channel_count, self.taps_per_channel), dtype=np.float64)
+        N.check(N.lib().wc_chan_get_arms(self._h, N.np_ptr(arms)))
+        self.arms = arms
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                N.lib().wc_chan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- reference attribute ---------------------------------------------------------------------
+    @property
+    def arm_history(self) -> np.ndarray:
+        """complex64 [channel_count, taps_per_channel]; column j = block fed j frames ago."""
+        out = np.empty((self.channel_count, self.taps_per_channel), dtype=np.complex64)
+        N.check(N.lib().wc_chan_get_history(self._h, N.np_ptr(out)))
+        return out
+
+    def frames_for(self, n_samples: int) -> int:
+        return int(N.lib().wc_chan_frames_for(self._h, int(n_samples)))
+
+    # -- core ------------------------------------------------------------------------------------
+    def _run(self, samples, mode: int, n_chunks: int = 1, scale: float = 0.0):
+        m = self.channel_count
+        if N.is_torch_cuda(samples):
+            import torch
+
+            x = samples
+            if x.dtype != torch.complex64:
+                x = x.to(torch.complex64)
+            x = x.contiguous()
+            n = x.numel() // n_chunks
+            frames = self.frames_for(n)
+            out = torch.empty((frames * n_chunks, m), device=x.device,
+                              dtype=torch.float32 if mode == OUT_FM else torch.complex64)
+            if frames:
+                N.check(N.lib().wc_chan_process(self._h, C.c_void_p(x.data_ptr()), n, n_chunks, n, mode,
+                                                scale, C.c_void_p(out.data_ptr()), N.torch_stream_ptr()))
+            return out
+        x = np.ascontiguousarray(samples, dtype=np.complex64)
+        n = x.size // n_chunks
+        frames = self.frames_for(n)
+        out = np.empty((frames * n_chunks, m), dtype=np.float32 if mode == OUT_FM else np.complex64)
+        if frames:
+            N.check(N.lib().wc_chan_process_host(self._h, N.np_ptr(x), n, n_chunks, mode, scale, N.np_ptr(out)))
+        return out
+
+    def process(self, samples) -> list:
+        """One array of `channel_count` complex64 values per output frame (channelizer.py:91-137)."""
+        return list(self.process_array(samples))
+
+    def process_array(self, samples):
+        """Same result as `process()` as one [frames, channel_count] array (numpy in -> numpy out,
+        CUDA tensor in -> CUDA tensor out)."""
+        return self._run(samples, OUT_COMPLEX)
+
+    def process_fm(self, samples, demod_sample_rate: int | None = None):
+        """Fused `quadrature_demod(extract_channel(process(samples), k), rate)` for every k:
+        float32 [frames, channel_count]; row 0 is zero (dsp/fm.py:90-91)."""
+        rate = int(self.channel_sample_rate) if demod_sample_rate is None else int(demod_sample_rate)
+        return self._run(samples, OUT_FM, scale=fm_scale(rate))
+
+    def process_batch(self, samples, n_chunks: int, fm: bool = False, demod_sample_rate: int | None = None):
+        """`n_chunks` back-to-back `process()` calls of equal length in one launch."""
+        rate = int(self.channel_sample_rate) if demod_sample_rate is None else int(demod_sample_rate)
+        return self._run(samples, OUT_FM if fm else OUT_COMPLEX, n_chunks=n_chunks,
+                         scale=fm_scale(rate) if fm else 0.0)
+
+    def reset(self) -> None:
+        N.check(N.lib().wc_chan_reset(self._h))
+        self.block_counter = 0
+
+    def extract_channel(self, channel_results, channel_index: int):
+        """Samples of one channel across frames (channelizer.py:144-158)."""
+        if isinstance(channel_results, np.ndarray):
+            return np.ascontiguousarray(channel_results[:, channel_index], dtype=np.complex64)
+        if N.is_torch_cuda(channel_results):
+            return channel_results[:, channel_index].contiguous()
+        return np.array([fr[channel_index] for fr in channel_results], dtype=np.complex64)
+
+
+class ChannelCalculator:
+    """Frequency <-> FFT-bin bookkeeping (channelizer.py:161-231); pure host arithmetic."""
+
+    def __init__(self, center_frequency: float, sample_rate: float,
+                 channel_bandwidth: int = DEFAULT_CHANNEL_BANDWIDTH):
+        self.center_frequency = center_frequency
+        self.sample_rate = sample_rate
+        self.channel_bandwidth = channel_bandwidth
+        count = int(sample_rate / channel_bandwidth)
+        self.channel_count = count - (count % 2)
+
+    def get_channel_index(self, target_frequency: float) -> int:
+        steps = int(round((target_frequency - self.center_frequency) / self.channel_bandwidth))
+        return self.channel_count + steps if steps < 0 else steps % self.channel_count
+
+    def get_channel_center_frequency(self, channel_index: int) -> float:
+        signed = channel_index if channel_index < self.channel_count // 2 else channel_index - self.channel_count
+        return self.center_frequency + signed * self.channel_bandwidth
+
+
+def channelize_samples(samples, sample_rate: float, target_frequency: float, center_frequency: float,
+                       channel_bandwidth: int = DEFAULT_CHANNEL_BANDWIDTH):
+    """Extract one channel from wideband IQ (channelizer.py:234-268)."""
+    chan = PolyphaseChannelizer(sample_rate, channel_bandwidth)
+    idx = ChannelCalculator(center_frequency, sample_rate, channel_bandwidth).get_channel_index(target_frequency)
+    frames = chan.process_array(samples)
+    return chan.extract_channel(frames, idx), chan.channel_sample_rate
