@@ -50,6 +50,68 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
 int wc_chan_process_host(wc_chan* h, const void* iq_host, long long n_samples, int n_chunks, int mode,
                          float fm_scale, void* out_host);
 
+/* ---- analog demod chain: wavecapsdr/capture.py:298-439, dsp/fm.py, dsp/am.py, dsp/agc.py, dsp/filters.py ----
+ * Stage-level operators on device buffers; the Python host (wavecap_sdr_b200/capture.py, dsp/*.py) chains
+ * them exactly as the reference chains numpy/scipy calls. Sequences are channel-major:
+ * seq = channel*n_chunks + chunk, each `seq_stride` floats apart. */
+#define WC_MODE_NONE 0 /* p25/dmr/...: only RSSI power (capture.py:422-428) */
+#define WC_MODE_WBFM 1
+#define WC_MODE_NBFM 2
+#define WC_MODE_AM 3
+#define WC_MODE_SSB 4
+#define WC_MODE_RAW 5
+#define WC_FMT_CF32 0
+#define WC_FMT_CS16 1 /* interleaved int16 I,Q scaled by 1/32768 (cli.py:449-453) */
+
+/* capture.freq_shift (capture.py:166-193; float32 phase, restarted per chunk, offset rounded to int Hz,
+ * untouched when offset == 0) + RSSI power sum (capture.py:331-334) + demod front end
+ * (FM: dsp/fm.py:65-97; AM: |x| dsp/am.py:99; SSB: Re(x*exp(+j2pi*bfo*t)) dsp/am.py:23-42,223) for every
+ * channel of every chunk in ONE launch; the IQ tile is staged in shared memory once for all channels.
+ * modes/offsets_hz/bfo_hz are host arrays [n_ch]; out_dev float32 [n_ch][n_chunks][n] (float2 for RAW);
+ * base_out_dev optional complex64 [n_ch][n_chunks][n]; power_dev float64 [n_ch][n_chunks] (sum |x|^2);
+ * nonfinite_dev int32 [n_chunks] (validation.py:37-38); chan_scratch_dev >= wc_front_chan_scratch_bytes. */
+int wc_front_chan_scratch_bytes(int n_ch);
+int wc_front_run(const void* iq_dev, int fmt, int n, int n_chunks, long long chunk_stride, int n_ch,
+                 const int* modes, const double* offsets_hz, const double* bfo_hz, int sample_rate,
+                 float* out_dev, void* base_out_dev, double* power_dev, int* nonfinite_dev, void* chan_scratch_dev,
+                 void* stream);
+
+/* scipy.signal.lfilter(b, a, x), zero initial state, float64 DF2T, order <= 10, as a block scan
+ * (dsp/fm.py:123,178; dsp/filters.py:124,170,217,260; dsp/agc.py:93,100). */
+typedef struct wc_iir wc_iir;
+int wc_iir_create(const double* b, int nb, const double* a, int na, wc_iir** out);
+void wc_iir_destroy(wc_iir* h);
+int wc_iir_lfilter(wc_iir* h, const float* x_dev, float* y_dev, int n, long long seq_stride, int n_seq,
+                   int abs_input, void* stream);
+
+/* sum(x**2) per sequence -> float64 (dsp/fm.py:58 rms_normalize, capture.py:436 signal power) */
+int wc_sumsq(const float* x_dev, int n, long long seq_stride, int n_seq, double* out_dev, void* stream);
+/* op 0: dsp.fm.soft_clip (fm.py:26-39); 1: dsp.agc.soft_clip (agc.py:58-70); 2: y = x * p0 */
+int wc_elementwise(const float* x_dev, float* y_dev, long long total, int op, float p0, void* stream);
+/* apply_agc tail (dsp/agc.py:228-242) given the two envelope-filter outputs */
+int wc_agc_apply(const float* x_dev, const float* env_attack_dev, const float* env_release_dev, float* y_dev,
+                 long long total, float target_linear, float max_gain_linear, void* stream);
+
+/* scipy.signal.resample_poly(x.astype(f64), up, down) -> float32 (dsp/fm.py:184-221): zero-extended upfirdn,
+ * only kept outputs computed, float64 accumulation. `taps` = firwin(2*10*max(up,down)+1, 1/max(up,down),
+ * ("kaiser", 5.0)) * up, designed by the host like the reference does. */
+typedef struct wc_resampler wc_resampler;
+#define WC_EPI_NONE 0
+#define WC_EPI_RMS_CLIP 1 /* rms_normalize (fm.py:42-62) then fm soft_clip: the wbfm/nbfm tail */
+#define WC_EPI_CLIP 2     /* fm soft_clip only */
+#define WC_EPI_RMS 3      /* rms_normalize only */
+#define WC_EPI_CLIP_AGC 4 /* dsp.agc.soft_clip (am/ssb without AGC, am.py:139-141) */
+int wc_resampler_create(int up, int down, const double* taps, int ntaps, wc_resampler** out);
+void wc_resampler_destroy(wc_resampler* h);
+long long wc_resampler_out_len(const wc_resampler* h, long long n_in);
+int wc_resampler_run(wc_resampler* h, const float* x_dev, int n_in, long long seq_stride, int n_seq, float* out_dev,
+                     int epilogue, const double* sumsq_dev, float target_rms, float min_rms, double* power_dev,
+                     int* invalid_dev, float max_abs, void* stream);
+/* RSSI dB per sequence + squelch select (capture.py:331-334, 2918-2921) */
+int wc_finalize(float* audio_dev, int n_out, int n_chunks, int n_seq, const double* power_iq_dev, int n_in,
+                const float* squelch_db_dev, const int* has_squelch_dev, float* rssi_db_dev,
+                unsigned char* squelched_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

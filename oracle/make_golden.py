@@ -43,7 +43,61 @@ def gen_channelizer_c5():
                         demod_rate=rate)
 
 
-GENERATORS = {"channelizer_c5": gen_channelizer_c5}
+def gen_analog():
+    """C1 (WBFM, 2.4 MS/s cf32), C2 (16 NBFM from one 10 MS/s int16 capture) and 48 kS/s AM/SSB/AGC
+    through the reference's own capture._process_channel_dsp_stateless / dsp functions. Inputs are
+    regenerated from seeds by oracle.analog.synth_*; only outputs are stored."""
+    import wavecapsdr.capture as rc
+    from wavecapsdr.dsp import agc as ragc
+    from wavecapsdr.dsp import am as ram
+    from wavecapsdr.dsp import fm as rfm
+    from oracle import analog as oa
+
+    out = {}
+    # C1: two consecutive chunks (per-chunk restarts)
+    for i in range(2):
+        x = oa.synth_c1(seed=1, n=120_000, t0=i * 120_000)
+        cfg = rc.ChannelConfig(id="c1", capture_id="c", mode="wbfm", offset_hz=200000.0)
+        a, m = rc._process_channel_dsp_stateless(x, 2_400_000, cfg)
+        out[f"c1_audio{i}"] = a
+        out[f"c1_metrics{i}"] = np.array([m["rssi_db"], m["signal_power_db"]])
+    # C2: one chunk, 16 channels, carriers 3 and 12 keyed off
+    q, offs = oa.synth_c2(seed=2, n=500_000, keyed_off=(3, 12))
+    xc = oa.cs16_to_cf32(q)
+    aud, met = [], []
+    for off in offs:
+        cfg = rc.ChannelConfig(id="c2", capture_id="c", mode="nbfm", offset_hz=float(off))
+        rc.CaptureManager._apply_mode_defaults(None, "nbfm", cfg)
+        a, m = rc._process_channel_dsp_stateless(xc, 10_000_000, cfg)
+        aud.append(a)
+        met.append([m["rssi_db"], m["signal_power_db"]])
+    out["c2_audio"] = np.stack(aud)
+    out["c2_metrics"] = np.array(met)
+    out["c2_offsets"] = np.array(offs, dtype=np.float64)
+    # stage functions at 48 kS/s (AM/SSB/AGC are unstable at MS/s rates, SURVEY App. A.6)
+    rng = np.random.default_rng(3)
+    n, fs = 9600, 48000
+    t = np.arange(n) / fs
+    xa = ((1 + 0.5 * np.sin(2 * np.pi * 700 * t)) * 0.3 * np.exp(1j * 0.3)
+          + 0.01 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    out["am_x"] = xa
+    out["am_audio"] = ram.am_demod(xa, fs, 16000)
+    out["am_audio_noagc"] = ram.am_demod(xa, fs, 16000, enable_agc=False)
+    out["ssb_audio"] = ram.ssb_demod(xa, fs, 16000)
+    out["ssb_audio_lsb"] = ram.ssb_demod(xa, fs, 16000, mode="lsb", enable_agc=False)
+    f = np.real(xa).astype(np.float32)
+    out["agc"] = ragc.apply_agc(f, fs)
+    out["deemph"] = rfm.deemphasis_filter(f, fs)
+    out["lpf"] = rfm.lpf_audio(f, fs, 5000)
+    out["resamp_3_10"] = rfm.resample_poly(f, 48000, 14400)
+    out["resamp_up"] = rfm.resample_poly(f[:1000], 8000, 48000)
+    out["quad"] = rfm.quadrature_demod(xa, fs)
+    out["fshift"] = rc.freq_shift(xa, 1234.4, fs)
+    out["am_fshift"] = ram.freq_shift(xa, 1500.0, fs)
+    np.savez_compressed(os.path.join(OUT, "analog.npz"), **out)
+
+
+GENERATORS = {"channelizer_c5": gen_channelizer_c5, "analog": gen_analog}
 
 
 def main(argv):

@@ -122,6 +122,20 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_chan_reset", i32, vp)
     fn("wc_chan_process", i32, vp, vp, i64, i32, i64, i32, f32, vp, vp)
     fn("wc_chan_process_host", i32, vp, vp, i64, i32, i32, f32, vp)
+    # analog chain stages
+    fn("wc_front_chan_scratch_bytes", i32, i32)
+    fn("wc_front_run", i32, vp, i32, i32, i32, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp)
+    fn("wc_iir_create", i32, vp, i32, vp, i32, P(vp))
+    fn("wc_iir_destroy", None, vp)
+    fn("wc_iir_lfilter", i32, vp, vp, vp, i32, i64, i32, i32, vp)
+    fn("wc_sumsq", i32, vp, i32, i64, i32, vp, vp)
+    fn("wc_elementwise", i32, vp, vp, i64, i32, f32, vp)
+    fn("wc_agc_apply", i32, vp, vp, vp, vp, i64, f32, f32, vp)
+    fn("wc_resampler_create", i32, i32, i32, vp, i32, P(vp))
+    fn("wc_resampler_destroy", None, vp)
+    fn("wc_resampler_out_len", i64, vp, i64)
+    fn("wc_resampler_run", i32, vp, vp, i32, i64, i32, vp, i32, vp, f32, f32, vp, vp, f32, vp)
+    fn("wc_finalize", i32, vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp)
     for extra in _EXTRA_DECLS:
         extra(l, fn)
 

@@ -1,0 +1,271 @@
+"""GPU versions of the DSP entry points of `wavecapsdr.capture` (capture.py).
+
+Mirrors: `ChannelConfig` (:442-501), `freq_shift` (:180-193), `decimate_iq_for_p25` (:203-295),
+`_process_channel_dsp_stateless` (:298-439), `_validate_audio_output` (:147-162) and the squelch rule
+of `_apply_stateful_processing` (:2918-2921). The threads / watchdogs / subscribers of the reference's
+Capture class stay in the reference (out of scope).
+
+GPU-only addition: `process_channels_batch` runs B chunks x C channels in a handful of launches,
+reading each IQ chunk from HBM once for all channels (the reference submits one Python task per
+channel to a 3-thread pool, capture.py:2489-2597).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+
+from . import _native as N
+from .dsp import _stages as S
+from .dsp import am as AM
+from .dsp import fm as FM
+
+AUDIO_MAX_ABS = 1.2  # validation.py:9
+
+
+@dataclass
+class ChannelConfig:
+    """Per-channel parameter block; same fields and defaults as capture.py:442-501."""
+    id: str
+    capture_id: str
+    mode: str
+    offset_hz: float = 0.0
+    audio_rate: int = 48_000
+    squelch_db: float | None = None
+    name: str | None = None
+    auto_name: str | None = None
+    enable_deemphasis: bool = True
+    deemphasis_tau_us: float = 75.0
+    enable_mpx_filter: bool = True
+    mpx_cutoff_hz: float = 15_000
+    enable_fm_highpass: bool = False
+    fm_highpass_hz: float = 100
+    enable_fm_lowpass: bool = False
+    fm_lowpass_hz: float = 3_000
+    enable_am_highpass: bool = True
+    am_highpass_hz: float = 100
+    enable_am_lowpass: bool = True
+    am_lowpass_hz: float = 5_000
+    enable_ssb_bandpass: bool = True
+    ssb_bandpass_low_hz: float = 300
+    ssb_bandpass_high_hz: float = 3_000
+    ssb_mode: str = "usb"
+    ssb_bfo_offset_hz: float = 1500.0
+    sam_sideband: str = "dsb"
+    sam_pll_bandwidth_hz: float = 50.0
+    enable_agc: bool = False
+    agc_target_db: float = -20.0
+    agc_attack_ms: float = 5.0
+    agc_release_ms: float = 50.0
+    enable_noise_blanker: bool = False
+    noise_blanker_threshold_db: float = 10.0
+    notch_frequencies: list[float] = field(default_factory=list)
+    enable_noise_reduction: bool = False
+    noise_reduction_db: float = 12.0
+    enable_rds: bool = True
+    enable_pocsag: bool = False
+    pocsag_baud: int = 1200
+
+
+def apply_mode_defaults(mode: str, cfg: ChannelConfig) -> ChannelConfig:
+    """Mode defaults of CaptureManager._apply_mode_defaults (capture.py:3425-3470)."""
+    if mode == "wbfm":
+        cfg.enable_deemphasis, cfg.deemphasis_tau_us = True, 75.0
+        cfg.enable_mpx_filter, cfg.mpx_cutoff_hz = True, 15_000
+        cfg.enable_fm_highpass = cfg.enable_fm_lowpass = cfg.enable_agc = False
+    elif mode == "nbfm":
+        cfg.enable_deemphasis = cfg.enable_mpx_filter = False
+        cfg.enable_fm_highpass, cfg.fm_highpass_hz = False, 300
+        cfg.enable_fm_lowpass, cfg.fm_lowpass_hz = False, 3_000
+        cfg.enable_agc = False
+    elif mode == "am":
+        cfg.enable_am_highpass, cfg.am_highpass_hz = True, 100
+        cfg.enable_am_lowpass, cfg.am_lowpass_hz = True, 5_000
+        cfg.enable_agc = True
+    elif mode == "ssb":
+        cfg.enable_ssb_bandpass, cfg.ssb_bandpass_low_hz, cfg.ssb_bandpass_high_hz = True, 300, 3_000
+        cfg.enable_agc = True
+    return cfg
+
+
+def _n(x) -> int:
+    return int(x.numel()) if hasattr(x, "numel") else int(np.asarray(x).size)
+
+
+def freq_shift(iq, offset_hz: float, sample_rate: int):
+    """Mix with exp(-j 2 pi round(offset)/fs n), float32 phase restarted at n=0 (capture.py:166-193).
+    Returns the input itself when offset is 0 or the input is empty."""
+    if offset_hz == 0.0 or _n(iq) == 0:
+        return iq
+    x = S.to_device(iq, np.complex64).reshape(-1)
+    _, base, _, _ = S.front(x, S.FMT_CF32, x.numel(), 1, [S.MODE_NONE], [float(offset_hz)], None, int(sample_rate),
+                            want_out=False, want_base=True)
+    return S.like_input(base.reshape(-1), iq)
+
+
+def decimate_iq_for_p25(iq, sample_rate: int):
+    """To ~48 kHz for P25 (capture.py:203-295): plain subsampling when down > 50, else polyphase
+    resampling of I and Q."""
+    target = 48000
+    if sample_rate <= target or _n(iq) == 0:
+        return iq, sample_rate
+    g = math.gcd(sample_rate, target)
+    up, down = target // g, sample_rate // g
+    if down > 50:
+        factor = sample_rate // target
+        x = S.to_device(iq, np.complex64).reshape(-1)
+        return S.like_input(x[::factor].contiguous(), iq), sample_rate // factor
+    import torch
+
+    x = S.to_device(iq, np.complex64).reshape(-1)
+    ri = torch.view_as_real(x)
+    rows = torch.stack([ri[:, 0], ri[:, 1]]).contiguous()
+    y = S.resample(rows, up, down)
+    out = torch.complex(y[0], y[1]).to(torch.complex64)
+    return S.like_input(out, iq), (sample_rate * up) // down
+
+
+_MODE_CODE = {"wbfm": S.MODE_WBFM, "nbfm": S.MODE_NBFM, "am": S.MODE_AM, "ssb": S.MODE_SSB, "raw": S.MODE_RAW}
+_DIGITAL = ("p25", "dmr", "nxdn", "dstar", "ysf")
+
+
+def _chain_signature(cfg: ChannelConfig, sample_rate: int):
+    """(kind, iir stages, agc?, target, audio_rate) — channels with equal signatures share launches."""
+    notch = tuple(cfg.notch_frequencies) if cfg.notch_frequencies else ()
+    if cfg.enable_noise_reduction:
+        FM.F.spectral_noise_reduction(None, sample_rate)
+    if cfg.mode == "wbfm":
+        st = FM.fm_post_chain(sample_rate, wide=True, enable_deemphasis=cfg.enable_deemphasis,
+                              deemphasis_tau=cfg.deemphasis_tau_us * 1e-6, enable_mpx_filter=cfg.enable_mpx_filter,
+                              mpx_cutoff_hz=cfg.mpx_cutoff_hz, enable_highpass=cfg.enable_fm_highpass,
+                              highpass_hz=cfg.fm_highpass_hz, notch_frequencies=notch)
+        return ("fm", tuple(st), False, 0.0, int(cfg.audio_rate))
+    if cfg.mode == "nbfm":
+        st = FM.fm_post_chain(sample_rate, wide=False, enable_deemphasis=cfg.enable_deemphasis,
+                              deemphasis_tau=cfg.deemphasis_tau_us * 1e-6, enable_highpass=cfg.enable_fm_highpass,
+                              highpass_hz=cfg.fm_highpass_hz, enable_lowpass=cfg.enable_fm_lowpass,
+                              lowpass_hz=cfg.fm_lowpass_hz, notch_frequencies=notch)
+        return ("fm", tuple(st), False, 0.0, int(cfg.audio_rate))
+    if cfg.mode == "am":
+        st = AM.am_post_chain(sample_rate, cfg.enable_am_highpass, cfg.am_highpass_hz, cfg.enable_am_lowpass,
+                              cfg.am_lowpass_hz, notch)
+        return ("am", tuple(st), bool(cfg.enable_agc), float(cfg.agc_target_db), int(cfg.audio_rate))
+    if cfg.mode == "ssb":
+        st = AM.ssb_post_chain(sample_rate, cfg.enable_ssb_bandpass, cfg.ssb_bandpass_low_hz,
+                               cfg.ssb_bandpass_high_hz, notch)
+        return ("am", tuple(st), bool(cfg.enable_agc), float(cfg.agc_target_db), int(cfg.audio_rate))
+    if cfg.mode == "raw":
+        return ("raw",)
+    if cfg.mode in _DIGITAL:
+        return ("digital",)
+    if cfg.mode == "sam":
+        raise NotImplementedError("sam_demod_simple (dsp/sam.py) is outside the accelerated hot path (SURVEY §8a)")
+    return ("unknown",)
+
+
+def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig], *, n_chunks: int = 1,
+                           in_fmt: str = "cf32", apply_squelch: bool = False, return_device: bool = False):
+    """`_process_channel_dsp_stateless` for every (chunk, channel) pair of a batch.
+
+    samples: complex64 [n_chunks*N] / [n_chunks, N] (in_fmt="cf32") or interleaved int16 I,Q
+    [n_chunks, N, 2] (in_fmt="cs16", scaled by 1/32768 like cli.py:449-453); numpy or CUDA tensor.
+    Returns results[chunk][channel] = (audio float32 | None, metrics dict) with the reference's keys
+    (`rssi_db`, `signal_power_db`). With apply_squelch, audio of channels whose rssi_db is below
+    cfg.squelch_db is zeroed (capture.py:2918-2921).
+    """
+    import torch
+
+    N.ensure_init()
+    n_ch = len(cfgs)
+    if in_fmt == "cs16":
+        x = S.to_device(samples, np.int16).reshape(n_chunks, -1, 2)
+        n, fmt = x.shape[1], S.FMT_CS16
+    else:
+        x = S.to_device(samples, np.complex64).reshape(n_chunks, -1)
+        n, fmt = x.shape[1], S.FMT_CF32
+    results = [[(None, {}) for _ in range(n_ch)] for _ in range(n_chunks)]
+    if n == 0 or n_ch == 0:
+        return results
+
+    sigs = [_chain_signature(c, sample_rate) for c in cfgs]
+    modes = [_MODE_CODE.get(c.mode, S.MODE_NONE) for c in cfgs]
+    bfo = [(c.ssb_bfo_offset_hz if c.ssb_mode.lower() == "usb" else -c.ssb_bfo_offset_hz) if c.mode == "ssb" else 0.0
+           for c in cfgs]
+    want_base = any(s[0] == "raw" for s in sigs)
+    out, base, power, nonfinite = S.front(x, fmt, n, n_chunks, modes, [float(c.offset_hz) for c in cfgs], bfo,
+                                          int(sample_rate), want_out=True, want_base=want_base)
+
+    audio = [None] * n_ch          # per channel: CUDA [n_chunks, n_audio]
+    apower = [None] * n_ch
+    invalid = [None] * n_ch
+    c = 0
+    while c < n_ch:                 # runs of adjacent channels with identical chains share launches
+        e = c + 1
+        while e < n_ch and sigs[e] == sigs[c]:
+            e += 1
+        sig = sigs[c]
+        if sig[0] in ("fm", "am"):
+            rows = out[c:e].reshape((e - c) * n_chunks, n)
+            if sig[0] == "fm":
+                a, p, inv = FM.fm_tail(rows, int(sample_rate), sig[4], sig[1], want_stats=True)
+            else:
+                a, p, inv = AM.am_tail(rows, int(sample_rate), sig[4], sig[1], sig[2], sig[3], want_stats=True)
+            a = a.reshape(e - c, n_chunks, -1)
+            p = p.reshape(e - c, n_chunks)
+            inv = inv.reshape(e - c, n_chunks)
+            for i in range(c, e):
+                audio[i], apower[i], invalid[i] = a[i - c], p[i - c], inv[i - c]
+        elif sig[0] == "raw":
+            for i in range(c, e):
+                audio[i] = torch.view_as_real(base[i]).reshape(n_chunks, 2 * n)   # interleaved I,Q (capture.py:415-420)
+                apower[i] = (audio[i].double() ** 2).sum(dim=1)
+                invalid[i] = ((~torch.isfinite(audio[i]).all(dim=1)) | (audio[i].abs().amax(dim=1) > AUDIO_MAX_ABS)).int()
+        c = e
+
+    power_h = power.cpu().numpy()
+    nonfinite_h = nonfinite.cpu().numpy()
+    for ci, cfg in enumerate(cfgs):
+        a_h = p_h = inv_h = None
+        if audio[ci] is not None:
+            inv_h = invalid[ci].cpu().numpy()
+            p_h = apower[ci].cpu().numpy()
+            a_h = audio[ci] if return_device else audio[ci].cpu().numpy()
+        for b in range(n_chunks):
+            if nonfinite_h[b]:
+                continue            # non-finite IQ: chunk dropped, empty metrics (capture.py:323-325)
+            rssi = float(np.float32(10.0) * np.log10(np.float32(power_h[ci, b] / n) + np.float32(1e-10)))
+            metrics: dict[str, Any] = {"rssi_db": rssi}
+            if sigs[ci][0] == "digital":
+                metrics["signal_power_db"] = rssi   # same power of the shifted IQ (capture.py:426-428)
+                results[b][ci] = (None, metrics)
+                continue
+            if a_h is None:
+                results[b][ci] = (None, metrics)
+                continue
+            if inv_h[b]:
+                results[b][ci] = (None, metrics)    # _validate_audio_output failed (capture.py:433-435)
+                continue
+            au = a_h[b]
+            n_a = au.shape[-1]
+            metrics["signal_power_db"] = float(10.0 * np.log10(np.float32(p_h[b] / max(n_a, 1)) + np.float32(1e-10)))
+            if apply_squelch and cfg.squelch_db is not None and rssi < cfg.squelch_db:
+                au = torch.zeros_like(au) if return_device else np.zeros_like(au)
+            results[b][ci] = (au, metrics)
+    return results
+
+
+def _process_channel_dsp_stateless(samples, sample_rate: int, cfg: ChannelConfig):
+    """Stateless per-channel DSP (capture.py:298-439): (audio | None, {rssi_db, signal_power_db})."""
+    if _n(samples) == 0:
+        return None, {}
+    return process_channels_batch(samples, sample_rate, [cfg], n_chunks=1)[0][0]
+
+
+def _validate_audio_output(audio, context: str = "") -> bool:
+    """finite and max|x| <= 1.2 (capture.py:147-162, validation.py:41-52)."""
+    a = audio.cpu().numpy() if hasattr(audio, "is_cuda") else np.asarray(audio)
+    if a.size == 0:
+        return True
+    return bool(np.isfinite(a).all() and float(np.max(np.abs(a))) <= AUDIO_MAX_ABS)

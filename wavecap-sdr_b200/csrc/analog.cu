@@ -1,0 +1,820 @@
+// Analog demod chain (configs C1/C2): the per-(chunk, channel) work of
+// wavecapsdr/capture.py:298-439 (_process_channel_dsp_stateless) as batched GPU stages.
+//
+//   front   capture.freq_shift (capture.py:166-193, float32-phase NCO restarted per chunk)
+//           + RSSI power (capture.py:331-334) + demod front end:
+//             FM  : dsp/fm.py:65-97 quadrature_demod
+//             AM  : |base|                    (dsp/am.py:99)
+//             SSB : Re(base * exp(+j*2*pi*bfo*t)), float64 phase (dsp/am.py:23-42,219-223)
+//           One CTA stages a tile of IQ (cf32 or cs16) in shared memory ONCE and loops over all
+//           channels, so HBM sees each IQ byte once per chunk no matter how many channels.
+//   iir     scipy.signal.lfilter(b, a, x) with zero initial state, float64 direct-form-II-transposed
+//           (dsp/fm.py:123,178; dsp/filters.py:124,170,217,260; dsp/agc.py:93,100) as a two-level
+//           block scan: 64-sample segments run in parallel from zero state, segment end states are
+//           chained with the exact transition matrix A^64, then every segment is re-run from its
+//           true start state. Linear recurrences compose exactly, so this equals the sequential
+//           recursion up to float64 rounding.
+//   rms     dsp/fm.py:42-62 (sum of squares per sequence)
+//   resamp  scipy.signal.resample_poly index math (upfirdn with zero extension), float64
+//           accumulation, only kept outputs are computed; epilogue fuses the RMS scale, tanh soft
+//           clip (dsp/fm.py:26-39), the finite/|x|<=1.2 validity gate (validation.py:41-52) and the
+//           audio power reduction (capture.py:436-437).
+//   agc     dsp/agc.py:169-242 (two one-pole envelopes via `iir`, then gain + tanh).
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/wcsdr_b200.h"
+#include "common.cuh"
+
+namespace wc {
+
+// ---------------------------------------------------------------------------------------------
+// front end
+// ---------------------------------------------------------------------------------------------
+constexpr int FR_TILE = 4096;
+constexpr int FR_THREADS = 256;
+
+struct FrontChan {
+    float k32;        // float32(-2*pi*round(offset)/fs); 0 => no shift (capture.py:185-186)
+    int shift;        // 0: offset == 0 (samples pass through untouched)
+    int mode;         // WC_MODE_*
+    double bfo_turns; // SSB: +-bfo/fs in turns per sample
+    float disc_scale; // float32(fs/(2*pi*75000))
+};
+
+struct FrontArgs {
+    const void* iq;        // [n_chunks][chunk_stride] cf32 or cs16 pairs
+    long long chunk_stride;
+    int n;                 // samples per chunk
+    int fmt;               // 0 cf32, 1 cs16 (scaled by 1/32768, cli.py:449-453)
+    int n_ch;
+    const FrontChan* ch;   // [n_ch]
+    float* out;            // [n_ch][n_chunks][n] demod front-end output
+    float2* base_out;      // optional [n_ch][n_chunks][n] shifted IQ (freq_shift result), may be null
+    double* power;         // [n_ch][n_chunks] sum |base|^2
+    int n_chunks;
+    int* nonfinite;        // [n_chunks] set to 1 if any input sample is not finite
+};
+
+__device__ __forceinline__ void nco_f32(float k32, int n, float& c, float& s) {
+    // theta = fl32(k32 * fl32(n)) exactly as numpy computes it; then an accurate cos/sin of that
+    // float32 angle: reduce in double (theta < 2^24 rad is exact in double), evaluate in float.
+    const float th = __fmul_rn(k32, (float)n);
+    const double t = (double)th * 0.15915494309189535;  // turns
+    const double fr = t - rint(t);                       // [-0.5, 0.5]
+    sincospif((float)(2.0 * fr), &s, &c);
+}
+
+__global__ void __launch_bounds__(FR_THREADS) front_kernel(const FrontArgs a) {
+    __shared__ float2 tile[FR_TILE + 1];
+    __shared__ double red[FR_THREADS / 32];
+    const int chunk = blockIdx.y;
+    const int t0 = blockIdx.x * FR_TILE;
+    const int cnt = min(FR_TILE, a.n - t0);
+    const int tid = threadIdx.x;
+    // stage tile (+1 halo sample in front) as cf32
+    bool bad = false;
+    for (int i = tid; i < cnt + 1; i += FR_THREADS) {
+        const int n = t0 - 1 + i;
+        float2 v = make_float2(0.f, 0.f);
+        if (n >= 0) {
+            if (a.fmt == 0) {
+                v = reinterpret_cast<const float2*>(a.iq)[(long long)chunk * a.chunk_stride + n];
+            } else {
+                const short2 q = reinterpret_cast<const short2*>(a.iq)[(long long)chunk * a.chunk_stride + n];
+                v = make_float2((float)q.x / 32768.0f, (float)q.y / 32768.0f);
+            }
+            if (i > 0 && !(isfinite(v.x) && isfinite(v.y))) bad = true;
+        }
+        tile[i] = v;
+    }
+    if (__syncthreads_or(bad) && tid == 0) atomicExch(a.nonfinite + chunk, 1);
+
+    for (int c = 0; c < a.n_ch; ++c) {
+        const FrontChan ch = a.ch[c];
+        const long long obase = ((long long)c * a.n_chunks + chunk) * a.n;
+        double psum = 0.0;
+        for (int i = tid; i < cnt; i += FR_THREADS) {
+            const int n = t0 + i;
+            float2 x1 = tile[i + 1];
+            float2 x0 = tile[i];
+            float2 b1 = x1, b0 = x0;
+            if (ch.shift) {
+                float c1, s1, c0, s0;
+                nco_f32(ch.k32, n, c1, s1);
+                b1 = make_float2(x1.x * c1 - x1.y * s1, x1.x * s1 + x1.y * c1);
+                if (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM) {
+                    nco_f32(ch.k32, n - 1, c0, s0);
+                    b0 = make_float2(x0.x * c0 - x0.y * s0, x0.x * s0 + x0.y * c0);
+                }
+            }
+            const float mag = sqrtf(b1.x * b1.x + b1.y * b1.y);  // np.abs(base)
+            psum += (double)(mag * mag);
+            float o;
+            if (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM) {
+                // angle(x[n] * conj(x[n-1])) * scale, out[0] = 0
+                const float pr = b1.x * b0.x + b1.y * b0.y;
+                const float pi = b1.y * b0.x - b1.x * b0.y;
+                o = (n == 0) ? 0.0f : atan2f(pi, pr) * ch.disc_scale;
+            } else if (ch.mode == WC_MODE_AM) {
+                o = mag;
+            } else if (ch.mode == WC_MODE_SSB) {
+                // t = n / fs in float64; shift = complex64(exp(2j*pi*f*t)); real(iq * shift)
+                double s, co;
+                const double ph = ch.bfo_turns * (double)n;
+                sincospi(2.0 * (ph - rint(ph)), &s, &co);
+                o = b1.x * (float)co - b1.y * (float)s;
+            } else {
+                o = 0.f;
+            }
+            // RAW (capture.py:415-420) is served by base_out; NONE only needs the power sum
+            if (ch.mode != WC_MODE_NONE && ch.mode != WC_MODE_RAW) a.out[obase + n] = o;
+            if (a.base_out) a.base_out[obase + n] = b1;
+        }
+        psum = warp_sum(psum);
+        if ((tid & 31) == 0) red[tid >> 5] = psum;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < FR_THREADS / 32; ++w) s += red[w];
+            atomicAdd(a.power + (long long)c * a.n_chunks + chunk, s);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// IIR block scan (float64 DF2T segments, double-double chaining)
+// ---------------------------------------------------------------------------------------------
+// tf-form Butterworth filters with poles clustered near z=1 (100 Hz high-pass at 48 kS/s, order-10
+// band-pass) have transition matrices A^64 with entries ~1e6..1e9 and massive cancellation in
+// P*s + z. Chaining segment states in plain float64 amplifies rounding twice and produces garbage;
+// with the transition powers and the chained state in double-double the scan reproduces the
+// sequential float64 recursion to its own rounding level (validated with exact rationals,
+// DESIGN.md "IIR scan").
+constexpr int IIR_L = 64;    // samples per segment
+constexpr int IIR_T = 128;   // segments per tile (one per thread)
+constexpr int IIR_TILE = IIR_L * IIR_T;
+constexpr int IIR_KMAX = 10;
+constexpr int IIR_LOG_T = 7;
+
+struct dd {
+    double hi, lo;
+};
+__host__ __device__ __forceinline__ dd dd_two_sum(double a, double b) {
+    const double s = a + b;
+    const double bb = s - a;
+    return dd{s, (a - (s - bb)) + (b - bb)};
+}
+__host__ __device__ __forceinline__ dd dd_quick(double a, double b) {
+    const double s = a + b;
+    return dd{s, b - (s - a)};
+}
+__host__ __device__ __forceinline__ dd dd_add(dd a, dd b) {
+    dd s = dd_two_sum(a.hi, b.hi);
+    const dd t = dd_two_sum(a.lo, b.lo);
+    s.lo += t.hi;
+    s = dd_quick(s.hi, s.lo);
+    s.lo += t.lo;
+    return dd_quick(s.hi, s.lo);
+}
+__host__ __device__ __forceinline__ dd dd_mul(dd a, dd b) {
+    const double p = a.hi * b.hi;
+    double e = fma(a.hi, b.hi, -p);
+    e = fma(a.hi, b.lo, e);
+    e = fma(a.lo, b.hi, e);
+    return dd_quick(p, e);
+}
+
+struct IirCoef {
+    int K;                                   // order
+    double b0;
+    double a[IIR_KMAX];                      // a[i+1]
+    double b[IIR_KMAX];                      // b[i+1]
+    dd Ppow[IIR_LOG_T][IIR_KMAX * IIR_KMAX]; // A^(L*2^k), k = 0..6 (segment transition powers)
+    dd PT[IIR_KMAX * IIR_KMAX];              // A^(L*T)    (tile transition)
+};
+
+template <int K>
+__device__ __forceinline__ double df2t_step(const double b0, const double (&cb)[K], const double (&ca)[K],
+                                            double (&z)[K], double x) {
+    const double y = fma(b0, x, z[0]);
+#pragma unroll
+    for (int i = 0; i < K - 1; ++i) z[i] = fma(cb[i], x, fma(-ca[i], y, z[i + 1]));
+    z[K - 1] = fma(cb[K - 1], x, -ca[K - 1] * y);
+    return y;
+}
+
+// o = M * s + o   (row-major K x K double-double)
+template <int K>
+__device__ __forceinline__ void dd_matvec_acc(const dd* __restrict__ M, const dd* s, dd* o) {
+    for (int r = 0; r < K; ++r) {
+        dd acc = o[r];
+        for (int c = 0; c < K; ++c) acc = dd_add(acc, dd_mul(M[r * K + c], s[c]));
+        o[r] = acc;
+    }
+}
+
+// Dynamic shared memory layout: float sx[T*(L+1)] | dd vb[2][T][K]
+template <int K>
+constexpr size_t iir_smem_bytes() {
+    return sizeof(float) * IIR_T * (IIR_L + 1) + sizeof(dd) * 2 * IIR_T * K + 16;
+}
+
+// FINAL = 0 (pass 1): zero-state run of every 64-sample segment -> z_i (global), inclusive scan
+//   -> tile aggregate Z_c (double-double).
+// FINAL = 1 (pass 3): scan again with the true tile-start state S_c folded into segment 0, then
+//   re-run every segment from its true start state and write y.
+template <int K, int FINAL, typename TIn>
+__global__ void __launch_bounds__(IIR_T) iir_kernel(const IirCoef* __restrict__ cf, const TIn* __restrict__ x,
+                                                    float* __restrict__ y, int n, long long seq_stride,
+                                                    double* __restrict__ zseg, dd* __restrict__ ztile,
+                                                    const dd* __restrict__ stile, int tiles, int absin) {
+    extern __shared__ __align__(16) unsigned char iir_smem[];
+    float* sx = reinterpret_cast<float*>(iir_smem);
+    dd* vb = reinterpret_cast<dd*>(iir_smem + ((sizeof(float) * IIR_T * (IIR_L + 1) + 15) & ~size_t(15)));
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x, seq = blockIdx.y;
+    const int t0 = tile * IIR_TILE;
+    const int cnt = min(IIR_TILE, n - t0);
+    const TIn* xs = x + (long long)seq * seq_stride + t0;
+    for (int e = tid; e < IIR_TILE; e += IIR_T) {
+        float v = 0.f;
+        if (e < cnt) {
+            v = (float)xs[e];
+            if (absin) v = fabsf(v);
+        }
+        sx[(e >> 6) * (IIR_L + 1) + (e & 63)] = v;
+    }
+    double cb[K], ca[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        cb[i] = cf->b[i];
+        ca[i] = cf->a[i];
+    }
+    const double b0 = cf->b0;
+    __syncthreads();
+    const int nseg = (cnt + IIR_L - 1) / IIR_L;
+    const long long tix = (long long)seq * tiles + tile;
+    const long long zoff = tix * IIR_T * K;
+    float* row = sx + tid * (IIR_L + 1);
+    double z[K];
+    dd v[K];
+    if (!FINAL) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) z[i] = 0.0;
+        if (tid < nseg) {
+#pragma unroll 4
+            for (int j = 0; j < IIR_L; ++j) df2t_step<K>(b0, cb, ca, z, (double)row[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) zseg[zoff + (long long)tid * K + i] = z[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < K; ++i) z[i] = zseg[zoff + (long long)tid * K + i];
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) v[i] = dd{z[i], 0.0};
+    dd sc[K];
+    if (FINAL) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) sc[i] = stile[tix * K + i];
+        if (tid == 0) dd_matvec_acc<K>(cf->Ppow[0], sc, v);  // end(seg 0) = P*S_c + z_0
+    }
+    // Kogge-Stone inclusive scan: v_i <- v_i + P^(2^k) * v_{i-2^k}
+    int cur = 0;
+#pragma unroll 1
+    for (int k = 0; k < IIR_LOG_T; ++k) {
+        dd* buf = vb + (size_t)cur * IIR_T * K;
+#pragma unroll
+        for (int i = 0; i < K; ++i) buf[tid * K + i] = v[i];
+        __syncthreads();
+        const int d = 1 << k;
+        if (tid >= d) dd_matvec_acc<K>(cf->Ppow[k], buf + (tid - d) * K, v);
+        cur ^= 1;
+    }
+    if (!FINAL) {
+        if (tid == IIR_T - 1) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) ztile[tix * K + i] = v[i];
+        }
+        return;
+    }
+    // exclusive: start state of segment i is the (true) end state of segment i-1
+    dd* buf = vb + (size_t)cur * IIR_T * K;
+#pragma unroll
+    for (int i = 0; i < K; ++i) buf[tid * K + i] = v[i];
+    __syncthreads();
+    if (tid < nseg) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) z[i] = (tid == 0) ? sc[i].hi : buf[(tid - 1) * K + i].hi;
+#pragma unroll 4
+        for (int j = 0; j < IIR_L; ++j) row[j] = (float)df2t_step<K>(b0, cb, ca, z, (double)row[j]);
+    }
+    __syncthreads();
+    float* ys = y + (long long)seq * seq_stride + t0;
+    for (int e = tid; e < cnt; e += IIR_T) ys[e] = sx[(e >> 6) * (IIR_L + 1) + (e & 63)];
+}
+
+// pass 2: chain tile aggregates in double-double: S_0 = 0, S_{c+1} = PT * S_c + Z_c.
+// One warp per sequence, lane r computes row r.
+template <int K>
+__global__ void iir_chain_kernel(const IirCoef* __restrict__ cf, const dd* __restrict__ ztile,
+                                 dd* __restrict__ stile, int tiles, int n_seq) {
+    __shared__ dd s_sh[4][IIR_KMAX];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seq = blockIdx.x * 4 + w;
+    if (seq >= n_seq) return;
+    dd s = dd{0.0, 0.0};
+    for (int c = 0; c < tiles; ++c) {
+        const long long off = ((long long)seq * tiles + c) * K;
+        if (lane < K) {
+            stile[off + lane] = s;
+            s_sh[w][lane] = s;
+        }
+        __syncwarp();
+        if (lane < K) {
+            dd acc = ztile[off + lane];
+            for (int j = 0; j < K; ++j) acc = dd_add(acc, dd_mul(cf->PT[lane * K + j], s_sh[w][j]));
+            s = acc;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions / elementwise
+// ---------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ x, int n, long long seq_stride, double* __restrict__ out) {
+    __shared__ double red[8];
+    const int seq = blockIdx.y;
+    const float* xs = x + (long long)seq * seq_stride;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float v = xs[i];
+        acc += (double)(v * v);  // x**2 is float32 in the reference
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        atomicAdd(out + seq, s);
+    }
+}
+
+__device__ __forceinline__ float soft_clip_fm(float x) {  // dsp/fm.py:26-39
+    return tanhf(x * 1.5f) * 1.1047914f * 0.95f;           // float32(1/tanh(1.5)) = 1.1047914
+}
+__device__ __forceinline__ float soft_clip_agc(float x) {  // dsp/agc.py:58-70
+    return tanhf(x * 1.5f) * 1.1047914f;
+}
+
+// apply_agc tail (dsp/agc.py:228-242): gain = min(target / max(max(env_a, env_r), 1e-6), max_gain)
+__global__ void agc_apply_kernel(const float* __restrict__ x, const float* __restrict__ env_a,
+                                 const float* __restrict__ env_r, float* __restrict__ y, long long total,
+                                 float target_lin, float max_gain) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float env = fmaxf(env_a[i], env_r[i]);
+        const float g = fminf(target_lin / fmaxf(env, 1e-6f), max_gain);
+        y[i] = soft_clip_agc(x[i] * g);
+    }
+}
+
+__global__ void elementwise_kernel(const float* __restrict__ x, float* __restrict__ y, long long total, int op,
+                                   float p0) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        float o = v;
+        if (op == 0) o = soft_clip_fm(v);
+        else if (op == 1) o = soft_clip_agc(v);
+        else if (op == 2) o = v * p0;
+        y[i] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// polyphase resampler (scipy.signal.resample_poly / upfirdn index math)
+// ---------------------------------------------------------------------------------------------
+struct ResampArgs {
+    const float* x;          // [n_seq][seq_stride]
+    long long seq_stride;
+    int n_in, n_out;
+    int up, down;
+    long long q0;            // Q(m) = (m + n_pre_remove)*down - n_pre_pad = q0 + m*down
+    int ntaps;               // len(h) (unpadded)
+    int tpp;                 // taps per phase (ceil(ntaps/up))
+    const double* hp;        // [up][tpp] polyphase taps: hp[phi][i] = h[phi + up*i] (0 past the end)
+    float* out;              // [n_seq][n_out]
+    // epilogue
+    int epi;                 // 0 none, 1 rms-scale + fm soft clip, 2 fm soft clip, 3 rms-scale only, 4 agc soft clip
+    const double* sumsq;     // [n_seq] for epi 1/3 (rms = sqrt(sumsq / n_in))
+    float target_rms, min_rms;
+    double* power;           // optional [n_seq]: sum out^2
+    int* invalid;            // optional [n_seq]: set when an output is non-finite or |x| > max_abs
+    float max_abs;
+};
+
+constexpr int RS_WARPS = 8;
+
+__global__ void __launch_bounds__(RS_WARPS * 32) resample_kernel(const ResampArgs a) {
+    const int seq = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* xs = a.x + (long long)seq * a.seq_stride;
+    float scale = 1.0f;
+    if (a.epi == 1 || a.epi == 3) {
+        const float rms = (float)sqrt(a.sumsq[seq] / (double)a.n_in);
+        if (rms > a.min_rms) scale = (float)((double)a.target_rms / (double)rms);
+    }
+    double pw = 0.0;
+    bool bad = false;
+    for (int m = blockIdx.x * RS_WARPS + warp; m < a.n_out; m += gridDim.x * RS_WARPS) {
+        const long long Q = a.q0 + (long long)m * a.down;
+        // taps t = Q - n*up in [0, ntaps); phase phi = Q mod up; n = nmax - i with i = (t - phi)/up
+        long long phi = Q % a.up;
+        if (phi < 0) phi += a.up;
+        const long long nmax = (Q - phi) / a.up;
+        const double* h = a.hp + phi * a.tpp;
+        // valid i: 0 <= i < tpp_phi, 0 <= nmax - i < n_in
+        int i_lo = (nmax >= a.n_in) ? (int)(nmax - a.n_in + 1) : 0;
+        long long i_hi_ll = nmax;  // inclusive upper bound from n >= 0
+        int i_hi = (i_hi_ll >= a.tpp) ? a.tpp - 1 : (int)i_hi_ll;
+        double acc = 0.0;
+        for (int i = i_lo + lane; i <= i_hi; i += 32) acc = fma(h[i], (double)xs[nmax - i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            float v = (float)acc;  // resample_poly(...).astype(float32)
+            if (a.epi == 1) v = soft_clip_fm((float)(acc * (double)scale));
+            else if (a.epi == 2) v = soft_clip_fm(v);
+            else if (a.epi == 3) v = (float)(acc * (double)scale);
+            else if (a.epi == 4) v = soft_clip_agc(v);
+            a.out[(long long)seq * a.n_out + m] = v;
+            pw += (double)(v * v);
+            if (!isfinite(v) || fabsf(v) > a.max_abs) bad = true;
+        }
+    }
+    if (lane == 0) {
+        if (a.power && pw != 0.0) atomicAdd(a.power + seq, pw);
+        if (a.invalid && bad) atomicExch(a.invalid + seq, 1);
+    }
+}
+
+// squelch / validity select (capture.py:2918-2921, 147-162): zero or flag audio per sequence
+__global__ void finalize_kernel(float* __restrict__ audio, int n_out, int n_chunks, const double* __restrict__ power_iq,
+                                int n_in, const float* __restrict__ squelch_db, const int* __restrict__ has_squelch,
+                                float* __restrict__ rssi_db, unsigned char* __restrict__ squelched) {
+    const int seq = blockIdx.y;
+    const int c = seq / n_chunks;  // sequences are channel-major: seq = c*n_chunks + chunk
+    const float rssi = (float)(10.0 * log10(power_iq[seq] / (double)n_in + 1e-10));
+    const bool sq = has_squelch[c] && (rssi < squelch_db[c]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rssi_db[seq] = rssi;
+        squelched[seq] = sq ? 1 : 0;
+    }
+    if (sq)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x)
+            audio[(long long)seq * n_out + i] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------
+static void dd_matmul(const dd* A, const dd* B, dd* C, int K) {
+    std::vector<dd> t((size_t)K * K);
+    for (int r = 0; r < K; ++r)
+        for (int c = 0; c < K; ++c) {
+            dd acc = dd{0.0, 0.0};
+            for (int k = 0; k < K; ++k) acc = dd_add(acc, dd_mul(A[r * K + k], B[k * K + c]));
+            t[r * K + c] = acc;
+        }
+    for (int i = 0; i < K * K; ++i) C[i] = t[i];
+}
+
+// Normalise (b, a) like scipy.signal.lfilter (divide by a[0], pad to equal length), build the DF2T
+// state matrix A (z' = A z + B x) and its powers A^(64*2^k) in double-double by repeated squaring.
+static int make_iir_coef(const double* b, int nb, const double* a, int na, IirCoef* out) {
+    if (na < 1 || nb < 1 || a[0] == 0.0) return -1;
+    int K = (nb > na ? nb : na) - 1;
+    if (K > IIR_KMAX) return -1;
+    memset(out, 0, sizeof(*out));
+    std::vector<double> bn(K + 1, 0.0), an(K + 1, 0.0);
+    for (int i = 0; i < nb; ++i) bn[i] = b[i] / a[0];
+    for (int i = 0; i < na; ++i) an[i] = a[i] / a[0];
+    out->b0 = bn[0];
+    out->K = K;
+    if (K == 0) return 0;
+    for (int i = 0; i < K; ++i) {
+        out->a[i] = an[i + 1];
+        out->b[i] = bn[i + 1];
+    }
+    std::vector<dd> P((size_t)K * K, dd{0.0, 0.0});
+    for (int i = 0; i < K; ++i) {
+        P[i * K + 0] = dd{-an[i + 1], 0.0};
+        if (i + 1 < K) P[i * K + i + 1] = dd_add(P[i * K + i + 1], dd{1.0, 0.0});
+    }
+    for (int s = 0; s < 6; ++s) dd_matmul(P.data(), P.data(), P.data(), K);  // A^64
+    for (int k = 0; k < IIR_LOG_T; ++k) {
+        for (int i = 0; i < K * K; ++i) out->Ppow[k][i] = P[i];
+        dd_matmul(P.data(), P.data(), P.data(), K);
+    }
+    for (int i = 0; i < K * K; ++i) out->PT[i] = P[i];  // A^(64*128)
+    return 0;
+}
+
+struct Workspace {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t need) {
+        if (cap >= need) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        WC_CUDA(cudaMalloc(&p, need));
+        cap = need;
+        return 0;
+    }
+    ~Workspace() {
+        if (p) cudaFree(p);
+    }
+};
+
+template <int K, typename TIn>
+static int launch_iir_k(const IirCoef* d_cf, const TIn* x, float* y, int n, long long seq_stride, int n_seq,
+                        int absin, double* zseg, dd* ztile, dd* stile, int tiles, cudaStream_t st) {
+    const size_t smem = iir_smem_bytes<K>();
+    static bool configured = false;
+    if (!configured) {
+        WC_CUDA(cudaFuncSetAttribute(iir_kernel<K, 0, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WC_CUDA(cudaFuncSetAttribute(iir_kernel<K, 1, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(tiles, n_seq);
+    iir_kernel<K, 0, TIn><<<grid, IIR_T, smem, st>>>(d_cf, x, y, n, seq_stride, zseg, ztile, stile, tiles, absin);
+    iir_chain_kernel<K><<<(n_seq + 3) / 4, 128, 0, st>>>(d_cf, ztile, stile, tiles, n_seq);
+    iir_kernel<K, 1, TIn><<<grid, IIR_T, smem, st>>>(d_cf, x, y, n, seq_stride, zseg, ztile, stile, tiles, absin);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename TIn>
+static int launch_iir_typed(const IirCoef* d_cf, int K, const TIn* x, float* y, int n, long long seq_stride,
+                            int n_seq, int absin, double* zseg, dd* ztile, dd* stile, int tiles, cudaStream_t st) {
+#define WC_IIR_CASE(KK) \
+    case KK:            \
+        return launch_iir_k<KK, TIn>(d_cf, x, y, n, seq_stride, n_seq, absin, zseg, ztile, stile, tiles, st);
+    switch (K) {
+        WC_IIR_CASE(1) WC_IIR_CASE(2) WC_IIR_CASE(3) WC_IIR_CASE(4) WC_IIR_CASE(5) WC_IIR_CASE(6) WC_IIR_CASE(7)
+        WC_IIR_CASE(8) WC_IIR_CASE(9) WC_IIR_CASE(10)
+        default:
+            set_error("iir: unsupported order %d", K);
+            return -1;
+    }
+#undef WC_IIR_CASE
+}
+
+}  // namespace wc
+
+using namespace wc;
+
+// ---------------------------------------------------------------------------------------------
+// C ABI: stage-level operators (device pointers)
+// ---------------------------------------------------------------------------------------------
+struct wc_iir {
+    IirCoef h_cf;
+    IirCoef* d_cf = nullptr;
+    Workspace ws;
+};
+
+extern "C" {
+
+int wc_iir_create(const double* b, int nb, const double* a, int na, wc_iir** out) {
+    WC_REQUIRE(b && a && out, "wc_iir_create: null argument");
+    wc_iir* h = new wc_iir();
+    if (make_iir_coef(b, nb, a, na, &h->h_cf)) {
+        delete h;
+        set_error("wc_iir_create: unsupported filter (order must be 0..%d, a[0] != 0)", IIR_KMAX);
+        return -1;
+    }
+    if (cudaMalloc(&h->d_cf, sizeof(IirCoef)) != cudaSuccess) {
+        delete h;
+        set_error("wc_iir_create: cudaMalloc failed");
+        return -2;
+    }
+    cudaMemcpy(h->d_cf, &h->h_cf, sizeof(IirCoef), cudaMemcpyHostToDevice);
+    *out = h;
+    return 0;
+}
+
+void wc_iir_destroy(wc_iir* h) {
+    if (!h) return;
+    if (h->d_cf) cudaFree(h->d_cf);
+    delete h;
+}
+
+// y = lfilter(b, a, x) per sequence, zero initial state; x float32 [n_seq][seq_stride], y may alias x.
+// abs_input != 0 filters |x| (AGC envelope, dsp/agc.py:83).
+int wc_iir_lfilter(wc_iir* h, const float* x_dev, float* y_dev, int n, long long seq_stride, int n_seq,
+                   int abs_input, void* stream) {
+    WC_REQUIRE(h && x_dev && y_dev, "wc_iir_lfilter: null argument");
+    if (n <= 0 || n_seq <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = h->h_cf.K;
+    if (K == 0) {
+        const long long total = (long long)n;
+        for (int s = 0; s < n_seq; ++s)
+            elementwise_kernel<<<(unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256), 256, 0, st>>>(
+                x_dev + s * seq_stride, y_dev + s * seq_stride, total, 2, (float)h->h_cf.b0);
+        WC_CUDA(cudaGetLastError());
+        return 0;
+    }
+    const int tiles = (n + IIR_TILE - 1) / IIR_TILE;
+    const size_t nz = (size_t)n_seq * tiles;
+    const size_t need = sizeof(double) * nz * IIR_T * K + sizeof(dd) * 2 * nz * K;
+    if (h->ws.reserve(need)) return -2;
+    double* zseg = reinterpret_cast<double*>(h->ws.p);
+    dd* ztile = reinterpret_cast<dd*>(zseg + nz * IIR_T * K);
+    dd* stile = ztile + nz * K;
+    return launch_iir_typed<float>(h->d_cf, K, x_dev, y_dev, n, seq_stride, n_seq, abs_input, zseg, ztile, stile,
+                                   tiles, st);
+}
+
+// sum of squares per sequence (float64 accumulators); out_dev[n_seq] is overwritten.
+int wc_sumsq(const float* x_dev, int n, long long seq_stride, int n_seq, double* out_dev, void* stream) {
+    WC_REQUIRE(x_dev && out_dev, "wc_sumsq: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    WC_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * n_seq, st));
+    if (n <= 0) return 0;
+    int bx = (n + 255) / 256;
+    if (bx > 64) bx = 64;
+    sumsq_kernel<<<dim3(bx, n_seq), 256, 0, st>>>(x_dev, n, seq_stride, out_dev);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wc_elementwise(const float* x_dev, float* y_dev, long long total, int op, float p0, void* stream) {
+    WC_REQUIRE(x_dev && y_dev, "wc_elementwise: null argument");
+    if (total <= 0) return 0;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    elementwise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, y_dev, total, op, p0);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wc_agc_apply(const float* x_dev, const float* env_attack_dev, const float* env_release_dev, float* y_dev,
+                 long long total, float target_linear, float max_gain_linear, void* stream) {
+    WC_REQUIRE(x_dev && env_attack_dev && env_release_dev && y_dev, "wc_agc_apply: null argument");
+    if (total <= 0) return 0;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    agc_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, env_attack_dev, env_release_dev, y_dev,
+                                                                        total, target_linear, max_gain_linear);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- resampler handle -------------------------------------------------------------------------
+struct wc_resampler {
+    int up, down, ntaps, tpp, half_len;
+    long long n_pre_pad, n_pre_remove;
+    double* d_hp = nullptr;
+};
+
+extern "C" {
+
+// taps = the FIR scipy.signal.resample_poly would use: firwin(2*half_len+1, 1/max(up,down),
+// window=("kaiser", 5.0)) * up with half_len = 10*max(up,down). Passing the taps keeps filter design
+// on the host (as in the reference); the index math (pre-pad / pre-remove / zero extension) is here.
+int wc_resampler_create(int up, int down, const double* taps, int ntaps, wc_resampler** out) {
+    WC_REQUIRE(out && taps && up >= 1 && down >= 1 && ntaps >= 1 && (ntaps & 1), "wc_resampler_create: bad arguments");
+    wc_resampler* h = new wc_resampler();
+    h->up = up;
+    h->down = down;
+    h->ntaps = ntaps;
+    h->half_len = (ntaps - 1) / 2;
+    h->n_pre_pad = down - h->half_len % down;                   // scipy: n_pre_pad = down - half_len % down
+    h->n_pre_remove = (h->half_len + h->n_pre_pad) / down;      // scipy: (half_len + n_pre_pad) // down
+    h->tpp = (ntaps + up - 1) / up;
+    std::vector<double> hp((size_t)up * h->tpp, 0.0);
+    for (int t = 0; t < ntaps; ++t) hp[(size_t)(t % up) * h->tpp + t / up] = taps[t];
+    if (cudaMalloc(&h->d_hp, hp.size() * sizeof(double)) != cudaSuccess) {
+        delete h;
+        set_error("wc_resampler_create: cudaMalloc failed");
+        return -2;
+    }
+    cudaMemcpy(h->d_hp, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice);
+    *out = h;
+    return 0;
+}
+
+void wc_resampler_destroy(wc_resampler* h) {
+    if (!h) return;
+    if (h->d_hp) cudaFree(h->d_hp);
+    delete h;
+}
+
+long long wc_resampler_out_len(const wc_resampler* h, long long n_in) {
+    if (!h || n_in <= 0) return 0;
+    return (n_in * h->up + h->down - 1) / h->down;  // ceil(n_in*up/down)
+}
+
+// epilogue: WC_EPI_NONE / WC_EPI_RMS_CLIP / WC_EPI_CLIP / WC_EPI_RMS (see header)
+int wc_resampler_run(wc_resampler* h, const float* x_dev, int n_in, long long seq_stride, int n_seq, float* out_dev,
+                     int epilogue, const double* sumsq_dev, float target_rms, float min_rms, double* power_dev,
+                     int* invalid_dev, float max_abs, void* stream) {
+    WC_REQUIRE(h && x_dev && out_dev, "wc_resampler_run: null argument");
+    WC_REQUIRE(!((epilogue == 1 || epilogue == 3) && !sumsq_dev), "wc_resampler_run: epilogue needs sumsq");
+    const long long n_out = wc_resampler_out_len(h, n_in);
+    if (n_out <= 0 || n_seq <= 0) return 0;
+    ResampArgs a;
+    a.x = x_dev;
+    a.seq_stride = seq_stride;
+    a.n_in = n_in;
+    a.n_out = (int)n_out;
+    a.up = h->up;
+    a.down = h->down;
+    a.q0 = h->n_pre_remove * h->down - h->n_pre_pad;
+    a.ntaps = h->ntaps;
+    a.tpp = h->tpp;
+    a.hp = h->d_hp;
+    a.out = out_dev;
+    a.epi = epilogue;
+    a.sumsq = sumsq_dev;
+    a.target_rms = target_rms;
+    a.min_rms = min_rms;
+    a.power = power_dev;
+    a.invalid = invalid_dev;
+    a.max_abs = max_abs;
+    int bx = (int)((n_out + RS_WARPS - 1) / RS_WARPS);
+    if (bx > 148 * 8) bx = 148 * 8;
+    resample_kernel<<<dim3(bx, n_seq), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- front end ----------------------------------------------------------------------------------
+// One launch for all channels of all chunks; see FrontArgs. chan arrays are host pointers [n_ch].
+int wc_front_run(const void* iq_dev, int fmt, int n, int n_chunks, long long chunk_stride, int n_ch,
+                 const int* modes, const double* offsets_hz, const double* bfo_hz, int sample_rate,
+                 float* out_dev, void* base_out_dev, double* power_dev, int* nonfinite_dev, void* chan_scratch_dev,
+                 void* stream) {
+    WC_REQUIRE(iq_dev && modes && offsets_hz && power_dev && nonfinite_dev && chan_scratch_dev,
+               "wc_front_run: null argument");
+    WC_REQUIRE(n_ch >= 1 && n_ch <= 4096, "wc_front_run: n_ch out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<FrontChan> ch(n_ch);
+    for (int c = 0; c < n_ch; ++c) {
+        FrontChan& f = ch[c];
+        f.mode = modes[c];
+        f.shift = (offsets_hz[c] != 0.0) ? 1 : 0;  // capture.py:185 / :328
+        // numpy: complex64(-1j*2*pi*(round(off)/fs)) * float32(n)  ->  k32 = float32(2*pi*round(off)/fs)
+        const double off = nearbyint(offsets_hz[c]);  // Python round() = banker's rounding
+        f.k32 = (float)(-(2.0 * M_PI * (off / (double)sample_rate)));
+        f.bfo_turns = bfo_hz ? bfo_hz[c] / (double)sample_rate : 0.0;
+        f.disc_scale = (float)((double)sample_rate / (2.0 * M_PI * 75000.0));
+    }
+    WC_CUDA(cudaMemcpyAsync(chan_scratch_dev, ch.data(), sizeof(FrontChan) * n_ch, cudaMemcpyHostToDevice, st));
+    WC_CUDA(cudaMemsetAsync(power_dev, 0, sizeof(double) * (size_t)n_chunks * n_ch, st));
+    WC_CUDA(cudaMemsetAsync(nonfinite_dev, 0, sizeof(int) * (size_t)n_chunks, st));
+    if (n <= 0) return 0;
+    FrontArgs a;
+    a.iq = iq_dev;
+    a.chunk_stride = chunk_stride;
+    a.n = n;
+    a.fmt = fmt;
+    a.n_ch = n_ch;
+    a.n_chunks = n_chunks;
+    a.ch = reinterpret_cast<const FrontChan*>(chan_scratch_dev);
+    a.out = out_dev;
+    a.base_out = reinterpret_cast<float2*>(base_out_dev);
+    a.power = power_dev;
+    a.nonfinite = nonfinite_dev;
+    front_kernel<<<dim3((n + FR_TILE - 1) / FR_TILE, n_chunks), FR_THREADS, 0, st>>>(a);
+    WC_CUDA(cudaGetLastError());
+    // the pageable host vector must outlive the async copy
+    WC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int wc_front_chan_scratch_bytes(int n_ch) { return (int)(sizeof(FrontChan) * (size_t)n_ch); }
+
+int wc_finalize(float* audio_dev, int n_out, int n_chunks, int n_seq, const double* power_iq_dev, int n_in,
+                const float* squelch_db_dev, const int* has_squelch_dev, float* rssi_db_dev,
+                unsigned char* squelched_dev, void* stream) {
+    WC_REQUIRE(audio_dev && power_iq_dev && squelch_db_dev && has_squelch_dev && rssi_db_dev && squelched_dev,
+               "wc_finalize: null argument");
+    if (n_seq <= 0) return 0;
+    int bx = n_out > 0 ? (n_out + 255) / 256 : 1;
+    if (bx > 16) bx = 16;
+    finalize_kernel<<<dim3(bx, n_seq), 256, 0, (cudaStream_t)stream>>>(audio_dev, n_out, n_chunks, power_iq_dev, n_in,
+                                                                       squelch_db_dev, has_squelch_dev, rssi_db_dev,
+                                                                       squelched_dev);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

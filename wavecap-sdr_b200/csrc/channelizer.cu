@@ -32,7 +32,7 @@ constexpr int CH_H = 128;
 constexpr int CH_T = 9;
 constexpr int CH_S = 8;          // frames per sub-tile
 constexpr int CH_THREADS = 128;  // one thread per residue class
-constexpr int CH_REGION = 272;   // complex words per frame region (16 x 17 padded exchange)
+constexpr int CH_REGION = 280;   // complex words per frame region (16 x 17 padded exchange + bank offset)
 
 struct ChanArgs {
     const float2* x;       // [n_chunks][chunk_stride] complex64
@@ -45,41 +45,52 @@ struct ChanArgs {
     float scale;           // FM discriminator scale
 };
 
+constexpr int CH_REGION_W = 2 * CH_REGION;  // 32-bit words per frame region
+static_assert(CH_REGION_W % 32 == 16, "frame regions must be offset by 16 banks (planar Y stores)");
+constexpr int CH_YIM = 272;                 // word offset of the Im plane inside a frame region
+
 struct __align__(128) ChanSmem {
-    float2 stage[2][CH_S * CH_H];  // TMA landing buffers: 8 rows of 128 samples each
-    float2 u[CH_S * CH_REGION];    // FIR output -> FFT exchange -> FFT output (in place)
-    float2 tw[16 * 16];            // tw[k1*16 + t] = exp(-2*pi*i*k1*t/256)
+    u64 stage[2][CH_S * CH_H];   // TMA landing buffers: 8 rows of 128 cf32 samples each
+    u64 u[CH_S * CH_REGION];     // FIR output -> FFT exchange -> planar FFT output (in place)
+    float2 tw[16 * 16];          // tw[k1*16 + t] = exp(-2*pi*i*k1*t/256)
     uint64_t full[2];
 };
 
-// forward 4-point DFT in place: (a,b,c,d) -> (X0,X1,X2,X3)
-__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
-    const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
-    a = cadd(t0, t2);
-    c = csub(t0, t2);
-    b = make_float2(t1.x + t3.y, t1.y - t3.x);
-    d = make_float2(t1.x - t3.y, t1.y + t3.x);
+// Complex values live in one 64-bit register pair (re = lo, im = hi) so that complex add/sub and
+// real-scalar multiplies issue as single FADD2/FFMA2 instructions.
+
+// forward 4-point DFT in place: (a,b,c,d) -> (X0,X1,X2,X3); 6 packed + 4 scalar adds
+__device__ __forceinline__ void dft4(u64& a, u64& b, u64& c, u64& d) {
+    const u64 t0 = add2(a, c), t1 = sub2(a, c), t2 = add2(b, d), t3 = sub2(b, d);
+    a = add2(t0, t2);
+    c = sub2(t0, t2);
+    const float t1x = lo2(t1), t1y = hi2(t1), t3x = lo2(t3), t3y = hi2(t3);
+    b = pk2(t1x + t3y, t1y - t3x);  // t1 - j*t3
+    d = pk2(t1x - t3y, t1y + t3x);  // t1 + j*t3
+}
+
+// v * (c - j*s)
+__device__ __forceinline__ u64 twid(u64 v, float c, float s) {
+    const float x = lo2(v), y = hi2(v);
+    return pk2(fmaf(x, c, y * s), fmaf(y, c, -x * s));
 }
 
 // forward 16-point DFT in registers. Input natural order; X[k] ends up in v[4*(k&3) + (k>>2)].
-__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+__device__ __forceinline__ void fft16(u64 (&v)[16]) {
     constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
     // twiddles W16^(n2*k1) on v[4*k1 + n2]
-    float2 t;
-    // k1 = 1: W^1, W^2, W^3
-    t = v[5];  v[5]  = make_float2(fmaf(t.x, C1, t.y * S1), fmaf(t.y, C1, -t.x * S1));
-    t = v[6];  v[6]  = make_float2((t.x + t.y) * R2, (t.y - t.x) * R2);
-    t = v[7];  v[7]  = make_float2(fmaf(t.x, S1, t.y * C1), fmaf(t.y, S1, -t.x * C1));
-    // k1 = 2: W^2, W^4, W^6
-    t = v[9];  v[9]  = make_float2((t.x + t.y) * R2, (t.y - t.x) * R2);
-    t = v[10]; v[10] = make_float2(t.y, -t.x);
-    t = v[11]; v[11] = make_float2((t.y - t.x) * R2, -(t.x + t.y) * R2);
-    // k1 = 3: W^3, W^6, W^9
-    t = v[13]; v[13] = make_float2(fmaf(t.x, S1, t.y * C1), fmaf(t.y, S1, -t.x * C1));
-    t = v[14]; v[14] = make_float2((t.y - t.x) * R2, -(t.x + t.y) * R2);
-    t = v[15]; v[15] = make_float2(fmaf(-t.x, C1, -t.y * S1), fmaf(-t.y, C1, t.x * S1));
+    float x, y;
+    v[5] = twid(v[5], C1, S1);                                                              // W^1
+    x = lo2(v[6]);  y = hi2(v[6]);  v[6]  = mul2(pk2(x + y, y - x), bc2(R2));               // W^2
+    v[7] = twid(v[7], S1, C1);                                                              // W^3
+    x = lo2(v[9]);  y = hi2(v[9]);  v[9]  = mul2(pk2(x + y, y - x), bc2(R2));               // W^2
+    x = lo2(v[10]); y = hi2(v[10]); v[10] = pk2(y, -x);                                     // W^4
+    x = lo2(v[11]); y = hi2(v[11]); v[11] = mul2(pk2(y - x, -(x + y)), bc2(R2));            // W^6
+    v[13] = twid(v[13], S1, C1);                                                            // W^3
+    x = lo2(v[14]); y = hi2(v[14]); v[14] = mul2(pk2(y - x, -(x + y)), bc2(R2));            // W^6
+    v[15] = twid(v[15], -C1, -S1);                                                          // W^9
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
 }
@@ -144,14 +155,16 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256_kernel(const ChanArgs a
         hhi[j] = __ldg(a.taps + r + CH_H + CH_M * j);
     }
 
-    float2 prev0 = make_float2(0.f, 0.f), prev1 = make_float2(0.f, 0.f);
+    // discriminator state: previous frame's bins 2*tid, 2*tid+1 as (re0,re1) / (im0,im1) pairs
+    u64 pre = 0ull, pim = 0ull;
+    float* const sw = reinterpret_cast<float*>(sm.u);
 
     // phases 2 + 3 for the sub-tile whose FIR outputs sit in sm.u (frames fs .. fs+nv-1)
     auto fft_and_emit = [&](int fs, int nv) {
         {
             const int g = tid >> 4, t = tid & 15;
-            float2* reg = sm.u + g * CH_REGION;
-            float2 v[16];
+            u64* reg = sm.u + g * CH_REGION;
+            u64 v[16];
             if (g < nv) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = reg[t + 16 * i];
@@ -161,8 +174,11 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256_kernel(const ChanArgs a
                 fft16(v);
 #pragma unroll
                 for (int k1 = 0; k1 < 16; ++k1) {
-                    float2 w = v[rev4(k1)];
-                    if (k1 > 0) w = cmul(w, sm.tw[k1 * 16 + t]);
+                    u64 w = v[rev4(k1)];
+                    if (k1 > 0) {
+                        const float2 tw = sm.tw[k1 * 16 + t];
+                        w = twid(w, tw.x, -tw.y);
+                    }
                     reg[t * 17 + k1] = w;
                 }
             }
@@ -177,36 +193,42 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256_kernel(const ChanArgs a
                 if (MODE == 0) {
                     const int b = fs + g;
                     if (b >= f0) {
-                        float2* o = reinterpret_cast<float2*>(a.out) + (out_base + b) * CH_M + t;
+                        u64* o = reinterpret_cast<u64*>(a.out) + (out_base + b) * CH_M + t;
 #pragma unroll
                         for (int k2 = 0; k2 < 16; ++k2) o[16 * k2] = v[rev4(k2)];
                     }
                 } else {
+                    // planar: Re plane at words [0,256), Im plane at [CH_YIM, CH_YIM+256)
+                    float* w = sw + g * CH_REGION_W + t;
 #pragma unroll
-                    for (int k2 = 0; k2 < 16; ++k2) reg[t + 16 * k2] = v[rev4(k2)];
+                    for (int k2 = 0; k2 < 16; ++k2) {
+                        w[16 * k2] = lo2(v[rev4(k2)]);
+                        w[CH_YIM + 16 * k2] = hi2(v[rev4(k2)]);
+                    }
                 }
             }
         }
         __syncthreads();
         if (MODE == 1) {
-            float* o = reinterpret_cast<float*>(a.out);
-            for (int i = 0; i < nv; ++i) {
-                const int b = fs + i;
-                const float4 y = *reinterpret_cast<const float4*>(sm.u + i * CH_REGION + 2 * tid);
-                const float2 y0 = make_float2(y.x, y.y), y1 = make_float2(y.z, y.w);
-                if (b >= f0) {
-                    float2 d;
-                    if (b == 0) {
-                        d = make_float2(0.f, 0.f);
-                    } else {
-                        const float2 p0 = cmulc(y0, prev0), p1 = cmulc(y1, prev1);
-                        d.x = fast_atan2f(p0.y, p0.x) * a.scale;
-                        d.y = fast_atan2f(p1.y, p1.x) * a.scale;
-                    }
-                    *reinterpret_cast<float2*>(o + (out_base + b) * CH_M + 2 * tid) = d;
-                }
-                prev0 = y0;
-                prev1 = y1;
+            float* o = reinterpret_cast<float*>(a.out) + (out_base + fs) * CH_M + 2 * tid;
+            const u64 sc = bc2(a.scale);
+            auto one = [&](int i) {
+                const float* w = sw + i * CH_REGION_W + 2 * tid;
+                const u64 yre = *reinterpret_cast<const u64*>(w);
+                const u64 yim = *reinterpret_cast<const u64*>(w + CH_YIM);
+                // p = y * conj(prev)
+                const u64 px = fma2(yre, pre, mul2(yim, pim));
+                const u64 py = sub2(mul2(yim, pre), mul2(yre, pim));
+                const u64 d = mul2(fast_atan2f_x2(py, px), sc);
+                if (fs + i >= f0) *reinterpret_cast<u64*>(o + (long long)i * CH_M) = d;
+                pre = yre;
+                pim = yim;
+            };
+            if (nv == CH_S) {
+#pragma unroll
+                for (int i = 0; i < CH_S; ++i) one(i);
+            } else {
+                for (int i = 0; i < nv; ++i) one(i);
             }
             __syncthreads();
         }
@@ -226,8 +248,8 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256_kernel(const ChanArgs a
                 hi.x = fmaf(hhi[j], vh.x, hi.x);
                 hi.y = fmaf(hhi[j], vh.y, hi.y);
             }
-            sm.u[b * CH_REGION + r] = lo;
-            sm.u[b * CH_REGION + r + CH_H] = hi;
+            sm.u[b * CH_REGION + r] = pk2(lo.x, lo.y);
+            sm.u[b * CH_REGION + r + CH_H] = pk2(hi.x, hi.y);
         }
         __syncthreads();
         fft_and_emit(0, nv);
@@ -235,25 +257,26 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256_kernel(const ChanArgs a
     if (n_fast == 0) return;
 
     // ---- fast path: sliding window over rows fast_start-8 .. ----
-    float2 w[10];
+    u64 w[10];
+    {
+        const u64* xr = reinterpret_cast<const u64*>(xc);
 #pragma unroll
-    for (int m = 0; m < 9; ++m) w[m] = __ldg(xc + (long long)(fast_start - 8 + m) * CH_H + r);
+        for (int m = 0; m < 9; ++m) w[m] = __ldg(xr + (long long)(fast_start - 8 + m) * CH_H + r);
+    }
 
     for (int n = 0; n < n_fast; ++n) {
         const int fs = fast_start + CH_S * n;
         const int nv = min(CH_S, f1 - fs);
         mbar_wait(&sm.full[n & 1], (n >> 1) & 1);
-        const float2* st = sm.stage[n & 1];
+        const u64* st = sm.stage[n & 1];
 #pragma unroll
         for (int i = 0; i < CH_S; ++i) {
             w[9] = st[i * CH_H + r];
-            float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+            u64 lo = mul2(w[8], bc2(hlo[0])), hi = mul2(w[9], bc2(hhi[0]));
 #pragma unroll
-            for (int j = 0; j < CH_T; ++j) {
-                lo.x = fmaf(hlo[j], w[8 - j].x, lo.x);
-                lo.y = fmaf(hlo[j], w[8 - j].y, lo.y);
-                hi.x = fmaf(hhi[j], w[9 - j].x, hi.x);
-                hi.y = fmaf(hhi[j], w[9 - j].y, hi.y);
+            for (int j = 1; j < CH_T; ++j) {
+                lo = fma2(w[8 - j], bc2(hlo[j]), lo);
+                hi = fma2(w[9 - j], bc2(hhi[j]), hi);
             }
             sm.u[i * CH_REGION + r] = lo;
             sm.u[i * CH_REGION + r + CH_H] = hi;
@@ -407,7 +430,9 @@ struct wc_chan {
     float2* d_ws = nullptr;   size_t ws_bytes = 0;     // generic path u / y
     void* d_in = nullptr;     size_t in_bytes = 0;     // host API staging
     void* d_out = nullptr;    size_t out_bytes = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                     // compute stream of the *_host entry points
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;     // copy streams of the pipelined host path
+    cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
 };
 
 static int ensure(void** p, size_t* cap, size_t need) {
@@ -473,6 +498,15 @@ void wc_chan_destroy(wc_chan* h) {
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->s_h2d) {
+        cudaStreamDestroy(h->s_h2d);
+        cudaStreamDestroy(h->s_d2h);
+        for (int i = 0; i < 2; ++i) {
+            cudaEventDestroy(h->ev_in[i]);
+            cudaEventDestroy(h->ev_comp[i]);
+            cudaEventDestroy(h->ev_out[i]);
+        }
+    }
     delete h;
 }
 
@@ -597,23 +631,58 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
 int wc_chan_process_host(wc_chan* h, const void* iq_host, long long n_samples, int n_chunks, int mode,
                          float fm_scale, void* out_host) {
     WC_REQUIRE(h && iq_host && out_host, "wc_chan_process_host: null argument");
+    WC_REQUIRE(n_chunks >= 1, "wc_chan_process_host: n_chunks must be >= 1");
     const long long F = wc_chan_frames_for(h, n_samples);
     if (F == 0) return 0;
-    const long long stride = (n_samples + 1) & ~1LL;  // keep chunk bases 16-byte aligned
-    const size_t in_need = sizeof(float2) * (size_t)stride * n_chunks;
+    WC_REQUIRE(n_chunks == 1 || F >= h->T, "wc_chan_process_host: batched chunks need >= %d frames each", h->T);
+    // Software pipeline over sub-batches of g chunks: H2D (copy stream) | kernels (compute stream) |
+    // D2H (copy stream), double-buffered on the device. Chunk bases stay 16-byte aligned.
+    const long long stride = (n_samples + 1) & ~1LL;
+    int g = (int)((4LL << 20) / n_samples);
+    if (g < 1) g = 1;
+    if (g > n_chunks) g = n_chunks;
     const size_t esz = (mode == WC_CHAN_OUT_FM) ? sizeof(float) : sizeof(float2);
-    const size_t out_need = esz * (size_t)F * n_chunks * h->M;
-    if (ensure(&h->d_in, &h->in_bytes, in_need)) return -2;
-    if (ensure(&h->d_out, &h->out_bytes, out_need)) return -2;
-    if (stride == n_samples) {
-        WC_CUDA(cudaMemcpyAsync(h->d_in, iq_host, sizeof(float2) * (size_t)n_samples * n_chunks, cudaMemcpyHostToDevice, h->stream));
-    } else {
-        WC_CUDA(cudaMemcpy2DAsync(h->d_in, sizeof(float2) * stride, iq_host, sizeof(float2) * n_samples,
-                                  sizeof(float2) * n_samples, n_chunks, cudaMemcpyHostToDevice, h->stream));
+    const size_t in_sub = sizeof(float2) * (size_t)stride * g;
+    const size_t out_sub = esz * (size_t)F * g * h->M;
+    if (ensure(&h->d_in, &h->in_bytes, 2 * in_sub)) return -2;
+    if (ensure(&h->d_out, &h->out_bytes, 2 * out_sub)) return -2;
+    if (!h->s_h2d) {
+        WC_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        WC_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            WC_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            WC_CUDA(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+            WC_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
     }
-    int rc = wc_chan_process(h, h->d_in, n_samples, n_chunks, stride, mode, fm_scale, h->d_out, h->stream);
-    if (rc) return rc;
-    WC_CUDA(cudaMemcpyAsync(out_host, h->d_out, out_need, cudaMemcpyDeviceToHost, h->stream));
+    const char* src = reinterpret_cast<const char*>(iq_host);
+    char* dst = reinterpret_cast<char*>(out_host);
+    int it = 0;
+    for (int c0 = 0; c0 < n_chunks; c0 += g, ++it) {
+        const int gc = (n_chunks - c0 < g) ? (n_chunks - c0) : g;
+        const int b = it & 1;
+        char* din = reinterpret_cast<char*>(h->d_in) + (size_t)b * in_sub;
+        char* dout = reinterpret_cast<char*>(h->d_out) + (size_t)b * out_sub;
+        if (it >= 2) WC_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));  // d_in[b] free again
+        const char* hs = src + sizeof(float2) * (size_t)n_samples * c0;
+        if (stride == n_samples) {
+            WC_CUDA(cudaMemcpyAsync(din, hs, sizeof(float2) * (size_t)n_samples * gc, cudaMemcpyHostToDevice, h->s_h2d));
+        } else {
+            WC_CUDA(cudaMemcpy2DAsync(din, sizeof(float2) * stride, hs, sizeof(float2) * n_samples,
+                                      sizeof(float2) * n_samples, gc, cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        WC_CUDA(cudaEventRecord(h->ev_in[b], h->s_h2d));
+        WC_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+        if (it >= 2) WC_CUDA(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));  // d_out[b] drained
+        int rc = wc_chan_process(h, din, n_samples, gc, stride, mode, fm_scale, dout, h->stream);
+        if (rc) return rc;
+        WC_CUDA(cudaEventRecord(h->ev_comp[b], h->stream));
+        WC_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
+        const size_t obytes = esz * (size_t)F * gc * h->M;
+        WC_CUDA(cudaMemcpyAsync(dst + esz * (size_t)F * c0 * h->M, dout, obytes, cudaMemcpyDeviceToHost, h->s_d2h));
+        WC_CUDA(cudaEventRecord(h->ev_out[b], h->s_d2h));
+    }
+    WC_CUDA(cudaStreamSynchronize(h->s_d2h));
     WC_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }

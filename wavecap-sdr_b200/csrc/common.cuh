@@ -80,6 +80,45 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
 
+// ---- packed FP32 pairs (sm_100 FFMA2/FADD2/FMUL2: one issue slot, two lanes of the FMA pipe) ----
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(u64 v) {
+    float a;
+    asm("{ .reg .b32 t; mov.b64 {%0, t}, %1; }" : "=f"(a) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi2(u64 v) {
+    float b;
+    asm("{ .reg .b32 t; mov.b64 {t, %0}, %1; }" : "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ u64 bc2(float v) { return pk2(v, v); }  // folds into a .F32 broadcast operand
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // atan2 with a degree-13 odd minimax polynomial (relative error <= 6.5e-7, fitted offline with
 // tools/fit_atan.py). No divergence, one MUFU.RCP. atan2(0,0)=0 like numpy.
 __device__ __forceinline__ float fast_atan2f(float y, float x) {
@@ -98,6 +137,37 @@ __device__ __forceinline__ float fast_atan2f(float y, float x) {
     a = (ay > ax) ? (1.57079632679489662f - a) : a;
     a = (x < 0.0f) ? (3.14159265358979324f - a) : a;
     return copysignf(a, y);
+}
+
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// two atan2's at once: the polynomial and the products run packed, the quadrant fix-ups scalar.
+// y/x = (lo, hi) pairs. Same polynomial as fast_atan2f.
+__device__ __forceinline__ u64 fast_atan2f_x2(u64 y, u64 x) {
+    const float x0 = lo2(x), x1 = hi2(x), y0 = lo2(y), y1 = hi2(y);
+    const float ax0 = fabsf(x0), ay0 = fabsf(y0), ax1 = fabsf(x1), ay1 = fabsf(y1);
+    const float mx0 = fmaxf(fmaxf(ax0, ay0), 1e-37f), mn0 = fminf(ax0, ay0);
+    const float mx1 = fmaxf(fmaxf(ax1, ay1), 1e-37f), mn1 = fminf(ax1, ay1);
+    const u64 t = mul2(pk2(mn0, mn1), pk2(rcp_approx(mx0), rcp_approx(mx1)));
+    const u64 s = mul2(t, t);
+    u64 p = bc2(0.008007131516933441f);
+    p = fma2(p, s, bc2(-0.037443727254867554f));
+    p = fma2(p, s, bc2(0.08435501158237457f));
+    p = fma2(p, s, bc2(-0.13512229919433594f));
+    p = fma2(p, s, bc2(0.198873370885849f));
+    p = fma2(p, s, bc2(-0.3332701623439789f));
+    p = fma2(p, s, bc2(0.9999994039535522f));
+    const u64 a = mul2(p, t);
+    float a0 = lo2(a), a1 = hi2(a);
+    a0 = (ay0 > ax0) ? (1.57079632679489662f - a0) : a0;
+    a1 = (ay1 > ax1) ? (1.57079632679489662f - a1) : a1;
+    a0 = (x0 < 0.0f) ? (3.14159265358979324f - a0) : a0;
+    a1 = (x1 < 0.0f) ? (3.14159265358979324f - a1) : a1;
+    return pk2(copysignf(a0, y0), copysignf(a1, y1));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
