@@ -112,6 +112,20 @@ int wc_finalize(float* audio_dev, int n_out, int n_chunks, int n_seq, const doub
                 const float* squelch_db_dev, const int* has_squelch_dev, float* rssi_db_dev,
                 unsigned char* squelched_dev, void* stream);
 
+/* ---- spectrum / waterfall: wavecapsdr/dsp/fft/base.py:31-77 (FFTBackend), scipy_backend.py:38-79 ----
+ * power_db = float32(20*log10(|fftshift(fft(iq[:N] * float32(hanning(N))))| + 1e-10)); consecutive groups of
+ * `avg` frames are averaged in dB (the frontend's spectrum averaging, SpectrumAnalyzer.react.tsx:309-327).
+ * fft_size must be a power of two. This is the kernel the "cuda" slot of the FFT registry
+ * (dsp/fft/registry.py:167-174, today CuPy -> cuFFT) binds to. */
+typedef struct wc_spectrum wc_spectrum;
+int wc_spectrum_create(int fft_size, wc_spectrum** out);
+void wc_spectrum_destroy(wc_spectrum* h);
+int wc_spectrum_window(const wc_spectrum* h, float* window_host /* [fft_size], FFTBackend.window */);
+int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stride, int n_frames, int avg,
+                        float* power_db_dev /* [ceil(n_frames/avg)][fft_size] */, void* stream);
+int wc_spectrum_execute_host(wc_spectrum* h, const void* iq_host, long long frame_stride, int n_frames, int avg,
+                             float* power_db_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,7 +97,35 @@ def gen_analog():
     np.savez_compressed(os.path.join(OUT, "analog.npz"), **out)
 
 
-GENERATORS = {"channelizer_c5": gen_channelizer_c5, "analog": gen_analog}
+def gen_spectrum():
+    """ScipyFFTBackend.execute (the reference's default backend) on seeded C3 input; 65536-point
+    frames are stored every 16th bin (plus the argmax neighbourhood) to keep the fixture small."""
+    from wavecapsdr.dsp.fft.scipy_backend import ScipyFFTBackend
+    from oracle import spectrum as osp
+
+    out = {}
+    fs = 61_440_000
+    be = ScipyFFTBackend(65536)
+    frames = []
+    for i in range(4):
+        r = be.execute(osp.synth_c3(seed=3, n=65536, t0=i * 65536), fs)
+        frames.append(r.power_db)
+    frames = np.stack(frames)
+    out["c3_frame0"] = frames[0]
+    out["c3_frames_dec16"] = frames[:, ::16]
+    out["c3_freqs_dec16"] = r.freqs[::16]
+    out["c3_bin_hz"] = np.float64(r.bin_hz)
+    out["c3_window_dec16"] = be.window[::16]
+    be2 = ScipyFFTBackend(2048)
+    r2 = be2.execute(osp.synth_c3(seed=4, n=5000, fs=2_400_000), 2_400_000)
+    out["s2048_power"] = r2.power_db
+    out["s2048_freqs"] = r2.freqs
+    r3 = ScipyFFTBackend(512).execute(osp.synth_c3(seed=5, n=100), 48000)   # too few samples -> zeros
+    out["short_power"] = r3.power_db
+    np.savez_compressed(os.path.join(OUT, "spectrum.npz"), **out)
+
+
+GENERATORS = {"channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

@@ -136,6 +136,12 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_resampler_out_len", i64, vp, i64)
     fn("wc_resampler_run", i32, vp, vp, i32, i64, i32, vp, i32, vp, f32, f32, vp, vp, f32, vp)
     fn("wc_finalize", i32, vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp)
+    # spectrum
+    fn("wc_spectrum_create", i32, i32, P(vp))
+    fn("wc_spectrum_destroy", None, vp)
+    fn("wc_spectrum_window", i32, vp, vp)
+    fn("wc_spectrum_execute", i32, vp, vp, i64, i32, i32, vp, vp)
+    fn("wc_spectrum_execute_host", i32, vp, vp, i64, i32, i32, vp)
     for extra in _EXTRA_DECLS:
         extra(l, fn)
 
