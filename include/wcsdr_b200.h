@@ -126,6 +126,29 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
 int wc_spectrum_execute_host(wc_spectrum* h, const void* iq_host, long long frame_stride, int n_frames, int avg,
                              float* power_db_host);
 
+/* ---- P25 Phase-1 C4FM symbol recovery: wavecapsdr/dsp/p25/c4fm.py:2379-2807 (C4FMDemodulator) ----
+ * One handle = n_channels independent stateful demodulators advanced by the same call (the reference runs one
+ * Python object per control/voice channel). Filters: pass the float32 designs of design_baseband_lpf
+ * (c4fm.py:95-132) and design_rrc_filter (:135-183), or NULL/0 to have them designed inside the library.
+ * demod(): iq complex64 [n_channels][chan_stride] (first n_samples used) -> dibits uint8 / soft float32
+ * [n_channels][max_sym], n_sym int32 [n_channels]; max_sym >= wc_c4fm_max_symbols(h, n_samples). Output depends on
+ * the call (chunk) sequence exactly like the reference. */
+typedef struct wc_c4fm wc_c4fm;
+int wc_c4fm_create(int n_channels, int sample_rate, int symbol_rate, int wide_pulse, const float* lpf_taps, int n_lpf,
+                   const float* rrc_taps, int n_rrc, wc_c4fm** out);
+void wc_c4fm_destroy(wc_c4fm* h);
+int wc_c4fm_info(const wc_c4fm* h, int* n_channels, double* samples_per_symbol, int* n_lpf, int* n_rrc);
+int wc_c4fm_get_taps(const wc_c4fm* h, float* lpf, float* rrc);
+int wc_c4fm_max_symbols(const wc_c4fm* h, int n_samples);
+int wc_c4fm_reset(wc_c4fm* h, int channel /* -1 = all; C4FMDemodulator.reset(), c4fm.py:2505 */);
+int wc_c4fm_demod(wc_c4fm* h, const void* iq_dev, long long chan_stride, int n_samples, unsigned char* dibits_dev,
+                  float* soft_dev, int* n_sym_dev, int max_sym, void* stream);
+int wc_c4fm_demod_host(wc_c4fm* h, const void* iq_host /* [n_channels][n_samples] */, int n_samples,
+                       unsigned char* dibits_host, float* soft_host, int* n_sym_host, int max_sym);
+/* state8 = {pll (get_timing_offset, c4fm.py:2809), gain, sample_point, buffer_pointer, fine_sync, symbols_since_sync,
+ * sync_count, sync events accepted during the last call} */
+int wc_c4fm_get_state(wc_c4fm* h, int channel, double* state8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -432,24 +432,28 @@ def random_frames(rng, n_frames=6, payload=150, gap=40):
 
 
 def modulate_c4fm(dibits, sample_rate=48000, snr_db=25.0, cfo_hz=60.0, timing=0.3, seed=0, amp=0.5):
-    """RRC-shaped 4-level FM: deviation +-600/+-1800 Hz (phase step +-pi/4, +-3pi/4 per symbol)."""
+    """Recipe of the reference's scripts/generate_p25_test_signal.py:84-168 `modulate_dibits(use_rrc=True)`:
+    rectangular +-1/+-3 frequency pulses (one symbol long), RRC(alpha 0.2, 8 symbols) shaping of the
+    frequency, pi/4 of phase per unit level per symbol — plus a fractional timing offset, a carrier
+    frequency offset and complex AWGN."""
     rng = np.random.default_rng(seed)
     sps = sample_rate / 4800.0
     level = {0: 1.0, 1: 3.0, 2: -1.0, 3: -3.0}
-    n = int(np.ceil((len(dibits) + 4) * sps))
-    imp = np.zeros(n)
+    n = int(np.ceil((len(dibits) + 2) * sps))
+    freq = np.zeros(n, dtype=np.float64)
     for k, d in enumerate(dibits):
-        imp[int(round((k + 1 + timing) * sps))] += level[int(d)]
-    span = 8
-    t = np.arange(-span * sps, span * sps + 1) / sps
-    alpha = 0.2
+        freq[int((k + timing) * sps):int((k + 1 + timing) * sps)] = level[int(d)]
+    alpha, span = 0.2, 8
+    n_taps = int(span * sps) | 1
+    t = np.arange(-(n_taps - 1) // 2, (n_taps + 1) // 2) / sps
     with np.errstate(divide="ignore", invalid="ignore"):
         h = (np.sin(np.pi * t * (1 - alpha)) + 4 * alpha * t * np.cos(np.pi * t * (1 + alpha))) / (
             np.pi * t * (1 - (4 * alpha * t) ** 2))
-    h[np.isnan(h) | np.isinf(h)] = 1 - alpha + 4 * alpha / np.pi
+    h[t == 0] = 1 + alpha * (4 / np.pi - 1)
+    h[~np.isfinite(h)] = 0.0
     h /= h.sum()
-    freq = np.convolve(imp, h * sps, mode="same") * (np.pi / 4) / sps     # rad/sample so a symbol integrates to level*pi/4
-    phase = np.cumsum(freq) + 2 * np.pi * cfo_hz / sample_rate * np.arange(n)
+    freq = signal.lfilter(h, 1.0, freq)
+    phase = np.cumsum(freq * (np.pi / 4) / sps) + 2 * np.pi * cfo_hz / sample_rate * np.arange(n)
     x = amp * np.exp(1j * phase)
     sigma = amp * 10 ** (-snr_db / 20) / np.sqrt(2)
     x = x + sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n))

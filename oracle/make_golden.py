@@ -125,7 +125,45 @@ def gen_spectrum():
     np.savez_compressed(os.path.join(OUT, "spectrum.npz"), **out)
 
 
-GENERATORS = {"channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+def c4fm_cases():
+    """(name, sample_rate, chunk, n_frames, snr_db, cfo_hz, timing, seed) — shared with the tests."""
+    return [
+        ("c4fm_48k_2400", 48000, 2400, 8, 25.0, 120.0, 0.30, 41),      # generic path, 50 ms chunks
+        ("c4fm_50k_2500", 50000, 2500, 8, 22.0, -150.0, 0.65, 42),     # fractional sps (10.4167)
+        ("c4fm_48k_72000", 48000, 72000, 44, 28.0, 60.0, 0.10, 43),    # control-channel path: chunk > buffer half
+        ("c4fm_48k_ragged", 48000, 1777, 6, 30.0, 0.0, 0.80, 44),      # chunk not a multiple of sps
+    ]
+
+
+def gen_p25_c4fm():
+    """C4FMDemodulator.demodulate of the reference on seeded C4FM signals, replaying fixed chunk
+    sequences (the output is chunking dependent). Inputs are stored (complex64) because they come
+    out of float64 transcendental code whose last bit may differ between CPUs."""
+    from wavecapsdr.dsp.p25.c4fm import C4FMDemodulator
+    from oracle import c4fm as oc
+
+    out = {}
+    for name, fs, chunk, nfr, snr, cfo, timing, seed in c4fm_cases():
+        rng = np.random.default_rng(seed)
+        dib = oc.random_frames(rng, n_frames=nfr, payload=150, gap=40)
+        x = oc.modulate_c4fm(dib, fs, snr_db=snr, cfo_hz=cfo, timing=timing, seed=seed)
+        d = C4FMDemodulator(sample_rate=fs)
+        ds, ss, cnt = [], [], []
+        for s in range(0, len(x), chunk):
+            a, b = d.demodulate(x[s:s + chunk])
+            ds.append(a)
+            ss.append(b)
+            cnt.append(len(a))
+        out[name + "_x"] = x
+        out[name + "_dibits"] = np.concatenate(ds).astype(np.uint8)
+        out[name + "_soft"] = np.concatenate(ss).astype(np.float32)
+        out[name + "_counts"] = np.array(cnt, dtype=np.int32)
+        out[name + "_sync_count"] = np.int32(d._sync_count)
+        out[name + "_tx"] = dib
+    np.savez_compressed(os.path.join(OUT, "p25_c4fm.npz"), **out)
+
+
+GENERATORS = {"p25_c4fm": gen_p25_c4fm, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

@@ -1,0 +1,120 @@
+"""GPU parity (through the C ABI): batched C4FM symbol recovery vs the oracle and the reference goldens.
+Bar: dibits, symbol counts and sync-event counts identical; soft symbols within 2e-6 absolute (the
+reference's float32 arctan2 is a SIMD approximation that is not correctly rounded; ours is)."""
+import numpy as np
+import pytest
+
+from conftest import golden_path
+from oracle.c4fm import C4FMOracle, modulate_c4fm, random_frames
+from oracle.make_golden import c4fm_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def run_bank(bank, xs, chunk):
+    """xs: [C][n]; replay the chunk sequence; returns per-channel (dibits, soft, counts)."""
+    C = xs.shape[0]
+    ds, ss, cs = [[] for _ in range(C)], [[] for _ in range(C)], [[] for _ in range(C)]
+    for s in range(0, xs.shape[1], chunk):
+        d, so, cnt = bank.demodulate(xs[:, s:s + chunk])
+        for c in range(C):
+            n = int(cnt[c])
+            ds[c].append(d[c, :n].copy())
+            ss[c].append(so[c, :n].copy())
+            cs[c].append(n)
+    return [np.concatenate(v) for v in ds], [np.concatenate(v) for v in ss], [np.array(v, np.int32) for v in cs]
+
+
+def run_oracle(fs, x, chunk):
+    o = C4FMOracle(sample_rate=fs)
+    ds, ss, cs = [], [], []
+    for s in range(0, len(x), chunk):
+        d, so = o.demodulate(x[s:s + chunk])
+        ds.append(d)
+        ss.append(so)
+        cs.append(len(d))
+    return np.concatenate(ds), np.concatenate(ss), np.array(cs, np.int32), o
+
+
+@pytest.mark.parametrize("case", c4fm_cases(), ids=lambda c: c[0])
+def test_matches_reference_golden(native, case):
+    from wavecap_sdr_b200.dsp.p25.c4fm import C4FMDemodulator
+
+    name, fs, chunk = case[0], case[1], case[2]
+    g = np.load(golden_path("p25_c4fm.npz"))
+    x = g[name + "_x"]
+    dm = C4FMDemodulator(sample_rate=fs)
+    ds, ss, cs = [], [], []
+    for s in range(0, len(x), chunk):
+        d, so = dm.demodulate(x[s:s + chunk])
+        assert d.dtype == np.uint8 and so.dtype == np.float32
+        ds.append(d)
+        ss.append(so)
+        cs.append(len(d))
+    assert np.array_equal(np.array(cs, np.int32), g[name + "_counts"])
+    d, so = np.concatenate(ds), np.concatenate(ss)
+    assert np.array_equal(d, g[name + "_dibits"]), f"{int((d != g[name + '_dibits']).sum())} dibit mismatches"
+    assert np.max(np.abs(so - g[name + "_soft"])) <= 2e-6
+    assert dm._sync_count == int(g[name + "_sync_count"])
+
+
+@pytest.mark.parametrize("fs,chunk", [(48000, 2400), (50000, 2500), (48000, 72000)])
+def test_bank_matches_oracle(native, fs, chunk):
+    """8 channels with different CFO / timing / SNR / content advanced together."""
+    from wavecap_sdr_b200.dsp.p25.c4fm import C4FMBank
+
+    C = 8
+    nfr = 5 if chunk < 10000 else 30
+    xs = []
+    for c in range(C):
+        rng = np.random.default_rng(400 + c)
+        dib = random_frames(rng, n_frames=nfr, payload=150, gap=40)
+        xs.append(modulate_c4fm(dib, fs, snr_db=20.0 + 1.5 * c, cfo_hz=-200.0 + 57.0 * c, timing=0.11 * c, seed=400 + c))
+    n = min(len(x) for x in xs)
+    xs = np.stack([x[:n] for x in xs])
+    bank = C4FMBank(C, sample_rate=fs)
+    gd, gs, gc = run_bank(bank, xs, chunk)
+    worst = 0.0
+    for c in range(C):
+        d, so, cnt, o = run_oracle(fs, xs[c], chunk)
+        assert np.array_equal(gc[c], cnt), f"channel {c}: symbol counts differ"
+        assert np.array_equal(gd[c], d), f"channel {c}: {int((gd[c] != d).sum())} dibit mismatches of {len(d)}"
+        worst = max(worst, float(np.max(np.abs(gs[c] - so))))
+        st = bank.state(c)
+        assert st["sync_count"] == o.sync_count and st["fine_sync"] == o.fine
+        assert abs(st["pll"] - o.pll) < 1e-6 and abs(st["gain"] - o.gain) < 1e-6
+        assert abs(st["sample_point"] - o.sample_point) < 1e-6 and st["buffer_pointer"] == o.buf_ptr
+    assert worst <= 2e-6, worst
+
+
+def test_reset_and_empty(native):
+    from wavecap_sdr_b200.dsp.p25.c4fm import C4FMDemodulator
+
+    rng = np.random.default_rng(9)
+    x = modulate_c4fm(random_frames(rng, n_frames=3), 48000, seed=9)
+    dm = C4FMDemodulator(sample_rate=48000)
+    d0, s0 = dm.demodulate(x)
+    e, es = dm.demodulate(np.zeros(0, np.complex64))
+    assert e.size == 0 and es.size == 0 and e.dtype == np.uint8 and es.dtype == np.float32
+    dm.reset()
+    d1, s1 = dm.demodulate(x)
+    assert np.array_equal(d0, d1) and np.array_equal(s0, s1)
+    o = C4FMOracle(sample_rate=48000)
+    d2, _ = o.demodulate(x)
+    assert np.array_equal(d0, d2)
+
+
+def test_noise_only_and_short_chunks(native):
+    """pure noise (no sync) and chunks shorter than the filter history / one symbol."""
+    from wavecap_sdr_b200.dsp.p25.c4fm import C4FMDemodulator
+
+    rng = np.random.default_rng(11)
+    x = ((rng.standard_normal(6000) + 1j * rng.standard_normal(6000)) * 0.1).astype(np.complex64)
+    dm, o = C4FMDemodulator(sample_rate=48000), C4FMOracle(sample_rate=48000)
+    for chunk in (7, 130, 3, 500, 1, 2000, 3359):
+        if len(x) < chunk:
+            break
+        c, x = x[:chunk], x[chunk:]
+        d, s = dm.demodulate(c)
+        do, so = o.demodulate(c)
+        assert np.array_equal(d, do) and (len(s) == 0 or np.max(np.abs(s - so)) <= 2e-6)

@@ -1,0 +1,65 @@
+"""CPU: the oracle restatement of dsp/p25/c4fm.py is pinned to outputs of the reference itself
+(tests/golden/p25_c4fm.npz, made by oracle/make_golden.py) and, when /root/reference is present,
+to the live reference. Dibits and symbol counts must be identical; soft symbols are compared with a
+2e-6 absolute allowance because numpy's float32 arctan2 (SIMD) is not correctly rounded and may
+differ in the last bit between CPUs."""
+import numpy as np
+import pytest
+
+from conftest import golden_path
+from oracle import refenv
+from oracle.c4fm import C4FMOracle, modulate_c4fm, random_frames, design_rrc_filter, sync_symbols
+from oracle.make_golden import c4fm_cases
+
+
+def replay(demod, x, chunk):
+    ds, ss, cnt = [], [], []
+    for s in range(0, len(x), chunk):
+        a, b = demod.demodulate(x[s:s + chunk])
+        ds.append(a)
+        ss.append(b)
+        cnt.append(len(a))
+    return np.concatenate(ds), np.concatenate(ss), np.array(cnt, dtype=np.int32)
+
+
+@pytest.mark.parametrize("case", c4fm_cases(), ids=lambda c: c[0])
+def test_oracle_matches_golden(case):
+    name, fs, chunk = case[0], case[1], case[2]
+    g = np.load(golden_path("p25_c4fm.npz"))
+    o = C4FMOracle(sample_rate=fs)
+    d, s, c = replay(o, g[name + "_x"], chunk)
+    assert np.array_equal(c, g[name + "_counts"])
+    assert np.array_equal(d, g[name + "_dibits"])
+    assert np.max(np.abs(s - g[name + "_soft"])) <= 2e-6
+    assert o.sync_count == int(g[name + "_sync_count"])
+
+
+def test_golden_signals_exercise_the_sync_path():
+    """every fixture makes the reference lock (sync events -> timing optimiser, PLL/gain correction and
+    message re-slicing all run); agreement with the transmitted dibits is NOT asserted — the reference's
+    chunked fixed-rate slicer recovers only 50-80 % of them on its own generator recipe."""
+    g = np.load(golden_path("p25_c4fm.npz"))
+    for case in c4fm_cases():
+        assert int(g[case[0] + "_sync_count"]) >= 5
+
+
+def test_empty_and_constants():
+    o = C4FMOracle(sample_rate=48000)
+    d, s = o.demodulate(np.zeros(0, np.complex64))
+    assert d.dtype == np.uint8 and s.dtype == np.float32 and d.size == 0 and s.size == 0
+    assert len(design_rrc_filter(10.0, 161)) == 161 and abs(float(design_rrc_filter(10.0, 161).sum()) - 1.0) < 1e-6
+    assert sync_symbols().tolist().count(3.0) + sync_symbols().tolist().count(-3.0) == 24
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refenv.available(), reason="/root/reference not present")
+def test_oracle_matches_live_reference():
+    refenv.load()
+    from wavecapsdr.dsp.p25.c4fm import C4FMDemodulator
+
+    rng = np.random.default_rng(7)
+    x = modulate_c4fm(random_frames(rng, n_frames=5), 50000, snr_db=24, cfo_hz=90, timing=0.4, seed=7)
+    r, o = C4FMDemodulator(sample_rate=50000), C4FMOracle(sample_rate=50000)
+    d1, s1, c1 = replay(r, x, 3100)
+    d2, s2, c2 = replay(o, x, 3100)
+    assert np.array_equal(c1, c2) and np.array_equal(d1, d2) and np.array_equal(s1, s2)

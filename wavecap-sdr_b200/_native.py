@@ -142,6 +142,17 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_spectrum_window", i32, vp, vp)
     fn("wc_spectrum_execute", i32, vp, vp, i64, i32, i32, vp, vp)
     fn("wc_spectrum_execute_host", i32, vp, vp, i64, i32, i32, vp)
+    # P25 C4FM
+    u8p = vp
+    fn("wc_c4fm_create", i32, i32, i32, i32, i32, vp, i32, vp, i32, P(vp))
+    fn("wc_c4fm_destroy", None, vp)
+    fn("wc_c4fm_info", i32, vp, P(i32), P(f64), P(i32), P(i32))
+    fn("wc_c4fm_get_taps", i32, vp, vp, vp)
+    fn("wc_c4fm_max_symbols", i32, vp, i32)
+    fn("wc_c4fm_reset", i32, vp, i32)
+    fn("wc_c4fm_demod", i32, vp, vp, i64, i32, u8p, vp, vp, i32, vp)
+    fn("wc_c4fm_demod_host", i32, vp, vp, i32, u8p, vp, vp, i32)
+    fn("wc_c4fm_get_state", i32, vp, i32, vp)
     for extra in _EXTRA_DECLS:
         extra(l, fn)
 

@@ -22,6 +22,9 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3", "--expt-relaxed-constexpr",
          "-Xptxas", "-v"]
+# per-file extras: the P25 kernels replay the reference's float32/float64 operation order, so the
+# compiler must not contract a*b+c into one fused multiply-add there (explicit fma() calls stay fused)
+EXTRA = {"p25.cu": ["-fmad=false"], "cqpsk.cu": ["-fmad=false"]}
 
 
 def _newer(a: Path, b: Path) -> bool:
@@ -31,13 +34,13 @@ def _newer(a: Path, b: Path) -> bool:
 def build(verbose: bool = False, force: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     srcs = sorted(CSRC.glob("*.cu"))
-    hdrs = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((ROOT / "include").glob("*.h"))
+    hdrs = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc")) + list((ROOT / "include").glob("*.h"))
     newest_hdr = max((h.stat().st_mtime for h in hdrs), default=0.0)
 
     def compile_one(src: Path) -> tuple[Path, str]:
         obj = OBJ / (src.stem + ".o")
         if force or _newer(src, obj) or obj.stat().st_mtime < newest_hdr:
-            cmd = [NVCC, *ARCH, *FLAGS, "-c", str(src), "-o", str(obj)]
+            cmd = [NVCC, *ARCH, *FLAGS, *EXTRA.get(src.name, []), "-c", str(src), "-o", str(obj)]
             p = subprocess.run(cmd, capture_output=True, text=True)
             if p.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src.name}:\n{p.stdout}\n{p.stderr}")

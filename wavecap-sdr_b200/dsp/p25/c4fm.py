@@ -1,0 +1,161 @@
+"""GPU C4FM demodulator with the call surface of `wavecapsdr.dsp.p25.c4fm`.
+
+Mirrors wavecapsdr/dsp/p25/c4fm.py: `C4FMDemodulator` (:2379-2807: `demodulate`, `reset`,
+`get_timing_offset`), `design_baseband_lpf` (:95-132), `design_rrc_filter` (:135-183). All signal
+arithmetic runs in csrc/p25.cu through the C ABI (`wc_c4fm_*`); filters are designed on the host at
+construction, like the reference does (scipy at plan creation, never on the data path).
+
+GPU-only addition: `C4FMBank` — C independent stateful demodulators advanced by one call (what the
+reference does with one Python object per control/voice channel).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ... import _native as N
+
+NUMBA_AVAILABLE = False  # name kept for benchmark_dsp.py:19; nothing here is JIT-compiled Python
+
+EQUALIZER_LOOP_GAIN = 0.15
+MAXIMUM_PLL = np.pi / 3.0
+MAXIMUM_GAIN = 1.25
+INITIAL_GAIN = 1.219
+
+
+def design_baseband_lpf(sample_rate: float, passband_hz: float = 5200.0, stopband_hz: float = 6500.0,
+                        num_taps: int = 63) -> np.ndarray:
+    """c4fm.py:95-132 — remez with the legacy `Hz=` keyword inside try/except, windowed-sinc fallback
+    (with scipy >= 1.15 the fallback is what runs, in the reference as here)."""
+    from scipy import signal
+
+    try:
+        h = signal.remez(num_taps, [0, passband_hz, stopband_hz, sample_rate / 2.0], [1, 0], Hz=sample_rate)
+    except Exception:
+        h = signal.firwin(num_taps, passband_hz, fs=sample_rate, window="hamming")
+    return np.asarray(h, dtype=np.float32)
+
+
+def design_rrc_filter(samples_per_symbol: float, num_taps: int = 101, alpha: float = 0.2) -> np.ndarray:
+    """c4fm.py:135-183 — root raised cosine, normalised to unit sum, float32."""
+    if num_taps % 2 == 0:
+        num_taps += 1
+    t = (np.arange(num_taps) - (num_taps - 1) / 2) / samples_per_symbol
+    h = np.zeros(num_taps, dtype=np.float64)
+    for i, ti in enumerate(t):
+        if ti == 0:
+            h[i] = 1 - alpha + 4 * alpha / np.pi
+        elif abs(ti) == 1 / (4 * alpha):
+            h[i] = (alpha / np.sqrt(2)) * ((1 + 2 / np.pi) * np.sin(np.pi / (4 * alpha))
+                                           + (1 - 2 / np.pi) * np.cos(np.pi / (4 * alpha)))
+        else:
+            h[i] = (np.sin(np.pi * ti * (1 - alpha)) + 4 * alpha * ti * np.cos(np.pi * ti * (1 + alpha))) / (
+                np.pi * ti * (1 - (4 * alpha * ti) ** 2))
+    return (h / np.sum(h)).astype(np.float32)
+
+
+class C4FMBank:
+    """`n_channels` C4FM demodulators with persistent per-channel state, one launch sequence per call."""
+
+    def __init__(self, n_channels: int, sample_rate: int = 19200, symbol_rate: int = 4800, wide_pulse: bool = False):
+        N.ensure_init()
+        self.n_channels = int(n_channels)
+        self.sample_rate = sample_rate
+        self.symbol_rate = symbol_rate
+        self.samples_per_symbol = sample_rate / symbol_rate
+        self.wide_pulse = wide_pulse
+        pb, sb, alpha = (10000.0, 12000.0, 0.5) if wide_pulse else (5200.0, 6500.0, 0.2)
+        self._baseband_lpf = design_baseband_lpf(sample_rate, passband_hz=pb, stopband_hz=sb)
+        self._rrc_filter = design_rrc_filter(self.samples_per_symbol,
+                                             num_taps=int(16 * self.samples_per_symbol) + 1, alpha=alpha)
+        h = C.c_void_p()
+        N.check(N.lib().wc_c4fm_create(self.n_channels, int(sample_rate), int(symbol_rate), int(bool(wide_pulse)),
+                                       N.np_ptr(self._baseband_lpf), int(self._baseband_lpf.size),
+                                       N.np_ptr(self._rrc_filter), int(self._rrc_filter.size), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                N.lib().wc_c4fm_destroy(h)
+            except Exception:
+                pass
+
+    def max_symbols(self, n_samples: int) -> int:
+        return int(N.lib().wc_c4fm_max_symbols(self._h, int(n_samples)))
+
+    def reset(self, channel: int = -1) -> None:
+        N.check(N.lib().wc_c4fm_reset(self._h, int(channel)))
+
+    def state(self, channel: int = 0) -> dict:
+        s = np.zeros(8, dtype=np.float64)
+        N.check(N.lib().wc_c4fm_get_state(self._h, int(channel), N.np_ptr(s)))
+        return {"pll": s[0], "gain": s[1], "sample_point": s[2], "buffer_pointer": int(s[3]), "fine_sync": bool(s[4]),
+                "symbols_since_sync": int(s[5]), "sync_count": int(s[6]), "events_last_call": int(s[7])}
+
+    def demodulate(self, iq):
+        """iq: complex64 [n_channels][n] (numpy, or a torch CUDA tensor) ->
+        (dibits uint8 [C][max_sym], soft float32 [C][max_sym], counts int32 [C]); row c is valid up to counts[c]."""
+        if N.is_torch_cuda(iq):
+            import torch
+
+            x = iq.to(torch.complex64).contiguous()
+            assert x.dim() == 2 and x.shape[0] == self.n_channels, x.shape
+            n = int(x.shape[1])
+            ms = max(1, self.max_symbols(n))
+            dib = torch.zeros((self.n_channels, ms), dtype=torch.uint8, device=x.device)
+            soft = torch.zeros((self.n_channels, ms), dtype=torch.float32, device=x.device)
+            cnt = torch.zeros((self.n_channels,), dtype=torch.int32, device=x.device)
+            if n:
+                N.check(N.lib().wc_c4fm_demod(self._h, C.c_void_p(x.data_ptr()), n, n, C.c_void_p(dib.data_ptr()),
+                                              C.c_void_p(soft.data_ptr()), C.c_void_p(cnt.data_ptr()), ms,
+                                              N.torch_stream_ptr()))
+            return dib, soft, cnt
+        x = np.ascontiguousarray(iq, dtype=np.complex64)
+        assert x.ndim == 2 and x.shape[0] == self.n_channels, x.shape
+        n = int(x.shape[1])
+        ms = max(1, self.max_symbols(n))
+        dib = np.zeros((self.n_channels, ms), dtype=np.uint8)
+        soft = np.zeros((self.n_channels, ms), dtype=np.float32)
+        cnt = np.zeros((self.n_channels,), dtype=np.int32)
+        if n:
+            N.check(N.lib().wc_c4fm_demod_host(self._h, N.np_ptr(x), n, N.np_ptr(dib), N.np_ptr(soft), N.np_ptr(cnt), ms))
+        return dib, soft, cnt
+
+
+class C4FMDemodulator:
+    """Drop-in for wavecapsdr.dsp.p25.c4fm.C4FMDemodulator (one channel)."""
+
+    def __init__(self, sample_rate: int = 19200, symbol_rate: int = 4800, wide_pulse: bool = False, **kwargs):
+        self._bank = C4FMBank(1, sample_rate, symbol_rate, wide_pulse)
+        self.sample_rate = sample_rate
+        self.symbol_rate = symbol_rate
+        self.samples_per_symbol = sample_rate / symbol_rate
+        self.wide_pulse = wide_pulse
+        self._baseband_lpf = self._bank._baseband_lpf
+        self._rrc_filter = self._bank._rrc_filter
+
+    def reset(self) -> None:
+        self._bank.reset(0)
+
+    def demodulate(self, iq):
+        """c4fm.py:2528-2807: complex IQ -> (dibits uint8, soft symbols float32)."""
+        iq = np.asarray(iq)
+        if iq.size == 0:
+            return np.array([], dtype=np.uint8), np.array([], dtype=np.float32)
+        dib, soft, cnt = self._bank.demodulate(iq.reshape(1, -1))
+        n = int(cnt[0])
+        return dib[0, :n].copy(), soft[0, :n].copy()
+
+    def get_timing_offset(self) -> float:
+        return float(self._bank.state(0)["pll"])
+
+    @property
+    def _sync_count(self) -> int:
+        return self._bank.state(0)["sync_count"]
+
+    @property
+    def _fine_sync(self) -> bool:
+        return self._bank.state(0)["fine_sync"]
