@@ -149,6 +149,23 @@ int wc_c4fm_demod_host(wc_c4fm* h, const void* iq_host /* [n_channels][n_samples
  * sync_count, sync events accepted during the last call} */
 int wc_c4fm_get_state(wc_c4fm* h, int channel, double* state8);
 
+/* ---- P25 CQPSK / LSM symbol recovery: wavecapsdr/decoders/p25.py:190-669 (CQPSKDemodulator) ----
+ * n_channels independent stateful demodulators advanced by one call. lpf_taps63 = _design_baseband_filter
+ * (:375-388, float32[63]) and mmse_taps_129x8 = _generate_mmse_taps (:289-323, float32[129*8]); NULL = built inside.
+ * demod(): iq complex64 [n_channels][chan_stride] -> dibits uint8 [n_channels][max_sym], n_sym int32 [n_channels]. */
+typedef struct wc_cqpsk wc_cqpsk;
+int wc_cqpsk_create(int n_channels, int sample_rate, int symbol_rate, const float* lpf_taps63, const float* mmse_taps_129x8,
+                    wc_cqpsk** out);
+void wc_cqpsk_destroy(wc_cqpsk* h);
+int wc_cqpsk_max_symbols(const wc_cqpsk* h, int n_samples);
+int wc_cqpsk_reset(wc_cqpsk* h, int channel /* -1 = all */);
+int wc_cqpsk_demod(wc_cqpsk* h, const void* iq_dev, long long chan_stride, int n_samples, unsigned char* dibits_dev,
+                   int* n_sym_dev, int max_sym, void* stream);
+int wc_cqpsk_demod_host(wc_cqpsk* h, const void* iq_host, int n_samples, unsigned char* dibits_host, int* n_sym_host,
+                        int max_sym);
+/* state6 = {_freq_offset, _phase_acc, _symbol_clock, _symbol_time, _agc_gain, _omega} */
+int wc_cqpsk_get_state(wc_cqpsk* h, int channel, double* state6);
+
 #ifdef __cplusplus
 }
 #endif

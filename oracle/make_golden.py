@@ -163,7 +163,47 @@ def gen_p25_c4fm():
     np.savez_compressed(os.path.join(OUT, "p25_c4fm.npz"), **out)
 
 
-GENERATORS = {"p25_c4fm": gen_p25_c4fm, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+def cqpsk_cases():
+    """(name, sample_rate, symbol_rate, chunk, n_dibits, snr_db, cfo_hz, timing, seed)."""
+    return [
+        ("cqpsk_48k_2400", 48000, 4800, 2400, 2400, 25.0, 40.0, 0.30, 51),
+        ("cqpsk_50k_2500", 50000, 4800, 2500, 2400, 22.0, -60.0, 0.70, 52),
+        ("cqpsk_48k_72000", 48000, 4800, 72000, 9000, 28.0, 25.0, 0.10, 53),
+        ("cqpsk_48k_6000baud_ragged", 48000, 6000, 1777, 2400, 30.0, 0.0, 0.55, 54),
+        ("cqpsk_48k_tiny", 48000, 4800, 50, 300, 25.0, 30.0, 0.20, 55),     # chunks shorter than the 63-tap filter
+    ]
+
+
+def gen_p25_cqpsk():
+    """decoders.p25.CQPSKDemodulator.demodulate of the reference on seeded pi/4-DQPSK signals, fixed chunk
+    sequences. Inputs are stored (complex64), see gen_p25_c4fm."""
+    import warnings
+
+    from wavecapsdr.decoders.p25 import CQPSKDemodulator
+    from oracle import cqpsk as oq
+
+    warnings.filterwarnings("ignore")
+    out = {}
+    for name, fs, sr, chunk, nd, snr, cfo, timing, seed in cqpsk_cases():
+        rng = np.random.default_rng(seed)
+        tx = rng.integers(0, 4, nd).astype(np.uint8)
+        x = oq.modulate_cqpsk(tx, fs, sr, snr_db=snr, cfo_hz=cfo, timing=timing, seed=seed)
+        d = CQPSKDemodulator(sample_rate=fs, symbol_rate=sr)
+        ds, cnt = [], []
+        for s in range(0, len(x), chunk):
+            a = d.demodulate(x[s:s + chunk])
+            ds.append(a)
+            cnt.append(len(a))
+        out[name + "_x"] = x
+        out[name + "_dibits"] = np.concatenate(ds).astype(np.uint8)
+        out[name + "_counts"] = np.array(cnt, dtype=np.int32)
+        out[name + "_state"] = np.array([float(d._freq_offset), float(d._phase_acc), float(d._symbol_clock),
+                                         float(d._symbol_time), float(d._agc_gain)], dtype=np.float64)
+        out[name + "_tx"] = tx
+    np.savez_compressed(os.path.join(OUT, "p25_cqpsk.npz"), **out)
+
+
+GENERATORS = {"p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

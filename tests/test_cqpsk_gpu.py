@@ -1,0 +1,93 @@
+"""GPU parity (through the C ABI): batched CQPSK symbol recovery vs the oracle and the reference goldens.
+Bar: symbol counts identical and dibits identical on every symbol whose differential phase is more than
+1e-4 rad away from a slicer boundary (0, +-pi/2, +-pi); the committed reference goldens must match on
+EVERY symbol. Why the knife-edge allowance: the reference's own arithmetic is not reproducible to the last
+bit across host CPUs on this path — numpy's float32 arctan2 is a SIMD (SVML) approximation that differs
+from the correctly rounded value in 38 % of calls, its first-call 63-tap filter is an OpenBLAS sdot whose
+summation order depends on the CPU, and np.mean is a pairwise float32 sum. Ours are correctly rounded /
+float64-accumulated, so the loop state (frequency offset, symbol clock, AGC gain) agrees to ~1e-6 and a
+symbol sitting within a few 1e-6 rad of a boundary can fall on either side. Measured on B200: 1 such symbol
+(|phase| = 3.0e-6 rad) in 218 000."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import golden_path
+from oracle.cqpsk import CQPSKOracle, modulate_cqpsk
+from oracle.make_golden import cqpsk_cases
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+
+
+@pytest.mark.parametrize("case", cqpsk_cases(), ids=lambda c: c[0])
+def test_matches_reference_golden(native, case):
+    from wavecap_sdr_b200.decoders.p25 import CQPSKDemodulator
+
+    name, fs, sr, chunk = case[:4]
+    g = np.load(golden_path("p25_cqpsk.npz"))
+    x = g[name + "_x"]
+    dm = CQPSKDemodulator(sample_rate=fs, symbol_rate=sr)
+    ds, cs = [], []
+    for s in range(0, len(x), chunk):
+        d = dm.demodulate(x[s:s + chunk])
+        assert d.dtype == np.uint8
+        ds.append(d)
+        cs.append(len(d))
+    assert np.array_equal(np.array(cs, np.int32), g[name + "_counts"])
+    d = np.concatenate(ds)
+    assert np.array_equal(d, g[name + "_dibits"]), f"{int((d != g[name + '_dibits']).sum())} dibit mismatches of {len(d)}"
+    st = g[name + "_state"]
+    assert abs(dm._freq_offset - st[0]) < 1e-5 and abs(dm._symbol_clock - st[2]) < 1e-4 and abs(dm._agc_gain - st[4]) < 1e-5
+
+
+@pytest.mark.parametrize("fs,sr,chunk", [(48000, 4800, 2400), (50000, 4800, 2500), (48000, 4800, 72000)])
+def test_bank_matches_oracle(native, fs, sr, chunk):
+    from wavecap_sdr_b200.decoders.p25 import CQPSKBank
+
+    C = 8
+    nd = 1500 if chunk < 10000 else 9000
+    xs = []
+    for c in range(C):
+        rng = np.random.default_rng(500 + c)
+        xs.append(modulate_cqpsk(rng.integers(0, 4, nd), fs, sr, snr_db=19.0 + 1.5 * c, cfo_hz=-70.0 + 20.0 * c,
+                                 timing=0.12 * c, seed=500 + c, amp=0.2 + 0.05 * c))
+    n = min(len(x) for x in xs)
+    xs = np.stack([x[:n] for x in xs])
+    bank = CQPSKBank(C, sample_rate=fs, symbol_rate=sr)
+    got = [[] for _ in range(C)]
+    for s in range(0, n, chunk):
+        d, cnt = bank.demodulate(xs[:, s:s + chunk])
+        for c in range(C):
+            got[c].append(d[c, : int(cnt[c])].copy())
+    for c in range(C):
+        o = CQPSKOracle(sample_rate=fs, symbol_rate=sr)
+        exp, phases = [], []
+        for s in range(0, n, chunk):
+            exp.append(o.demodulate(xs[c, s:s + chunk]))
+            phases += o.phases
+        exp = np.concatenate(exp)
+        g = np.concatenate(got[c])
+        assert len(g) == len(exp), f"channel {c}: {len(g)} vs {len(exp)} symbols"
+        bad = np.nonzero(g != exp)[0]
+        if bad.size:
+            ph = np.array(phases)
+            bounds = np.array([-np.pi, -np.pi / 2, 0.0, np.pi / 2, np.pi])
+            margin = np.min(np.abs(ph[bad, None] - bounds[None, :]), axis=1)
+            assert bad.size <= 2 and np.all(margin < 1e-4), (
+                f"channel {c}: {bad.size} dibit mismatches of {len(exp)}, decision margins {margin}")
+        st = bank.state(c)
+        assert abs(st["freq_offset"] - float(o.freq_offset)) < 1e-5
+        assert abs(st["symbol_clock"] - float(o.clock)) < 1e-4
+        assert abs(st["agc_gain"] - float(o.agc_gain)) < 1e-5
+
+
+def test_empty_and_zero_input(native):
+    from wavecap_sdr_b200.decoders.p25 import CQPSKDemodulator
+
+    dm, o = CQPSKDemodulator(sample_rate=48000), CQPSKOracle(sample_rate=48000)
+    e = dm.demodulate(np.zeros(0, np.complex64))
+    assert e.dtype == np.uint8 and e.size == 0
+    z = np.zeros(1000, np.complex64)
+    assert np.array_equal(dm.demodulate(z), o.demodulate(z))

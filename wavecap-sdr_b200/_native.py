@@ -153,6 +153,14 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_c4fm_demod", i32, vp, vp, i64, i32, u8p, vp, vp, i32, vp)
     fn("wc_c4fm_demod_host", i32, vp, vp, i32, u8p, vp, vp, i32)
     fn("wc_c4fm_get_state", i32, vp, i32, vp)
+    # P25 CQPSK
+    fn("wc_cqpsk_create", i32, i32, i32, i32, vp, vp, P(vp))
+    fn("wc_cqpsk_destroy", None, vp)
+    fn("wc_cqpsk_max_symbols", i32, vp, i32)
+    fn("wc_cqpsk_reset", i32, vp, i32)
+    fn("wc_cqpsk_demod", i32, vp, vp, i64, i32, vp, vp, i32, vp)
+    fn("wc_cqpsk_demod_host", i32, vp, vp, i32, vp, vp, i32)
+    fn("wc_cqpsk_get_state", i32, vp, i32, vp)
     for extra in _EXTRA_DECLS:
         extra(l, fn)
 
