@@ -166,6 +166,31 @@ int wc_cqpsk_demod_host(wc_cqpsk* h, const void* iq_host, int n_samples, unsigne
 /* state6 = {_freq_offset, _phase_acc, _symbol_clock, _symbol_time, _agc_gain, _omega} */
 int wc_cqpsk_get_state(wc_cqpsk* h, int channel, double* state6);
 
+/* ---- streaming complex FIR: wavecapsdr/dsp/filters.py:558-668 (fir_filter_complex, fir_decimate) ----
+ * y = (taps (*) [zi | x])[::decim] as complex64 (only kept outputs are computed), zi_out = last n_taps-1 entries of
+ * [zi | x] as complex128. zi_host NULL = zeros. x_dev/y_dev are device pointers, the rest host; synchronises. */
+int wc_fir_complex(const void* x_dev, int n, const double* taps_host, int n_taps, int decim, const void* zi_host,
+                   void* y_dev, void* zi_out_host, void* stream);
+
+/* ---- trunking fan-out: phase-continuous NCO + two-stage FIR decimation for K channels of one wideband chunk ----
+ * TrunkingSystem.on_raw_iq_callback (trunking/system.py:1434-1466 NCO, :1392-1406 filters, :1753-1779 stages) with
+ * init_mode 1 / keep_f64 0, and VoiceRecorder.process_iq (:561-656) with init_mode 2 / keep_f64 1.
+ * taps NULL = firwin(157, 0.8/decim1, kaiser 7.857) / firwin(73, 0.8/decim2, kaiser 7.857) designed inside; decim2 = 1
+ * disables stage 2. init_mode: first-call filter state 0 = zeros, 1 = lfilter_zi(taps)*x[0] taken as previous INPUTS
+ * (what fir_decimate does with the zi it is handed), 2 = scipy lfilter steady state (previous inputs = x[0]).
+ * Output per call: [K][out_stride] complex64 (keep_f64 0) or complex128 (1), wc_ddc_out_len(h, n) valid per row;
+ * decimation restarts at sample 0 of every call, exactly like `filtered[::D]` per chunk. */
+typedef struct wc_ddc wc_ddc;
+int wc_ddc_create(int n_channels, int sample_rate, const double* taps1, int n_taps1, int decim1, const double* taps2,
+                  int n_taps2, int decim2, int init_mode, int keep_f64, wc_ddc** out);
+void wc_ddc_destroy(wc_ddc* h);
+int wc_ddc_get_taps(const wc_ddc* h, double* taps1, double* taps2, int* n1, int* n2);
+int wc_ddc_set_offsets(wc_ddc* h, const double* offsets_hz /* [K] */);
+int wc_ddc_reset(wc_ddc* h, int channel /* -1 = all */);
+int wc_ddc_out_len(const wc_ddc* h, int n_samples);
+int wc_ddc_process(wc_ddc* h, const void* iq_dev, int n_samples, void* out_dev, long long out_stride, void* stream);
+int wc_ddc_process_host(wc_ddc* h, const void* iq_host, int n_samples, void* out_host /* [K][out_len] */);
+
 #ifdef __cplusplus
 }
 #endif

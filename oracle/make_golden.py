@@ -203,7 +203,31 @@ def gen_p25_cqpsk():
     np.savez_compressed(os.path.join(OUT, "p25_cqpsk.npz"), **out)
 
 
-GENERATORS = {"p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+def gen_ddc():
+    """wavecapsdr.dsp.filters.fir_filter_complex / fir_decimate (numba kernels) of the reference on seeded input,
+    streamed over three calls with carried state."""
+    from wavecapsdr.dsp.filters import fir_decimate, fir_filter_complex
+    from scipy import signal as sg
+
+    rng = np.random.default_rng(6)
+    x = ((rng.standard_normal(30000) + 1j * rng.standard_normal(30000)) * 0.3).astype(np.complex64)
+    taps = sg.firwin(157, 0.8 / 30, window=("kaiser", 7.857))
+    out = {"x": x, "taps": taps}
+    zi = sg.lfilter_zi(taps, 1.0).astype(np.complex128) * x[0]
+    ys, cuts = [], [0, 12000, 12077, 30000]          # 12000 > 10000 takes the prange kernel, 77 < 156 taps
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        y, zi = fir_decimate(x[a:b], taps, 30, zi=zi)
+        ys.append(np.asarray(y))
+    out["dec30"] = np.concatenate(ys)
+    out["dec30_counts"] = np.array([len(y) for y in ys])
+    out["dec30_zi"] = zi
+    y, z = fir_filter_complex(x[:5000], taps[:73].copy(), None)
+    out["filt73"] = np.asarray(y)
+    out["filt73_zi"] = z
+    np.savez_compressed(os.path.join(OUT, "ddc.npz"), **out)
+
+
+GENERATORS = {"ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

@@ -161,6 +161,16 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_cqpsk_demod", i32, vp, vp, i64, i32, vp, vp, i32, vp)
     fn("wc_cqpsk_demod_host", i32, vp, vp, i32, vp, vp, i32)
     fn("wc_cqpsk_get_state", i32, vp, i32, vp)
+    # streaming FIR / trunking fan-out
+    fn("wc_fir_complex", i32, vp, i32, vp, i32, i32, vp, vp, vp, vp)
+    fn("wc_ddc_create", i32, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, P(vp))
+    fn("wc_ddc_destroy", None, vp)
+    fn("wc_ddc_get_taps", i32, vp, vp, vp, P(i32), P(i32))
+    fn("wc_ddc_set_offsets", i32, vp, vp)
+    fn("wc_ddc_reset", i32, vp, i32)
+    fn("wc_ddc_out_len", i32, vp, i32)
+    fn("wc_ddc_process", i32, vp, vp, i32, vp, i64, vp)
+    fn("wc_ddc_process_host", i32, vp, vp, i32, vp)
     for extra in _EXTRA_DECLS:
         extra(l, fn)
 
