@@ -46,6 +46,9 @@ int wc_chan_reset(wc_chan* h);                                       /* reset(),
  * Output: [n_chunks*F][M] complex64 (mode 0) or float32 (mode 1, scaled by fm_scale). */
 int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_chunks, long long chunk_stride,
                     int mode, float fm_scale, void* out_dev, void* stream);
+/* advance the carried history (arm_history) as if process() had been called on iq_dev[0..n_samples) without
+ * computing outputs — for time-sharded multi-GPU runs where another rank emitted the tail of the call. */
+int wc_chan_carry_from(wc_chan* h, const void* iq_dev, long long n_samples, void* stream);
 /* same, host buffers: H2D copy + kernels + D2H copy + sync (the reference-facing call). */
 int wc_chan_process_host(wc_chan* h, const void* iq_host, long long n_samples, int n_chunks, int mode,
                          float fm_scale, void* out_host);

@@ -91,7 +91,8 @@ def interp8(window_f32: np.ndarray, row: int) -> np.ndarray:
 class DiffDemodOracle:
     """_FMDemodulator (c4fm.py:276-395)."""
 
-    def __init__(self, samples_per_symbol: float):
+    def __init__(self, samples_per_symbol: float, portable: bool = False):
+        self.portable = portable
         self.mu = samples_per_symbol % 1.0
         self.interp_offset = max(0, int(np.floor(samples_per_symbol)) - 4)
         self.overlap = int(np.floor(samples_per_symbol)) + 4
@@ -123,6 +124,8 @@ class DiffDemodOracle:
         q_prev_conj = -bq[:n]
         diff_i = (i_prev * i_curr) - (q_prev_conj * q_curr)
         diff_q = (i_prev * q_curr) + (i_curr * q_prev_conj)
+        if self.portable:   # correctly rounded float32 arctan2 (numpy's float32 SIMD arctan2 depends on the host CPU)
+            return np.arctan2(diff_q.astype(F64), diff_i.astype(F64)).astype(F32)
         return np.arctan2(diff_q, diff_i).astype(F32)
 
 
@@ -242,13 +245,15 @@ class SoftSyncOracle:
 class C4FMOracle:
     """C4FMDemodulator (c4fm.py:2379-2807)."""
 
-    def __init__(self, sample_rate=19200, symbol_rate=4800, wide_pulse=False):
+    def __init__(self, sample_rate=19200, symbol_rate=4800, wide_pulse=False, portable=False):
+        """portable=True replaces numpy's host-CPU-dependent float32 arctan2 by its correctly rounded value (what
+        the CUDA path computes); everything else is identical. The reference goldens pin both modes."""
         self.sample_rate, self.symbol_rate = sample_rate, symbol_rate
         self.sps = sample_rate / symbol_rate
         pb, sb, alpha = (10000.0, 12000.0, 0.5) if wide_pulse else (5200.0, 6500.0, 0.2)
         self.lpf = design_baseband_lpf(sample_rate, pb, sb)
         self.rrc = design_rrc_filter(self.sps, num_taps=int(16 * self.sps) + 1, alpha=alpha)
-        self.fm = DiffDemodOracle(self.sps)
+        self.fm = DiffDemodOracle(self.sps, portable)
         self.det, self.det_lag = SoftSyncOracle(), SoftSyncOracle()
         self.lag_offset = self.sps / 2.0
         self.max_fine_adj = self.sps * 0.2

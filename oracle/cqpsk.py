@@ -52,8 +52,21 @@ def baseband_taps(sample_rate, cutoff_hz=7250, num_taps=63):
     return np.asarray(signal.firwin(num_taps, norm, window="hamming"), dtype=F32)
 
 
+def _angle32(z):
+    """np.angle for a complex64 scalar with a CORRECTLY ROUNDED float32 result (float64 atan2, then cast).
+    numpy's own float32 arctan2 is a SIMD approximation whose last bit depends on the host CPU."""
+    return np.float32(np.arctan2(np.float64(z.imag), np.float64(z.real)))
+
+
 class CQPSKOracle:
-    def __init__(self, sample_rate=19200, symbol_rate=4800):
+    """portable=False: literally the reference's numpy calls (pins the restatement to the reference on THIS host).
+    portable=True: the three host-CPU-dependent calls are replaced by their correctly rounded values — float32
+    arctan2 (SVML), the first-call float32 np.convolve (OpenBLAS sdot order) and the pairwise float32 np.mean —
+    so that the expected output does not depend on which CPU the test runs on. That is also what the CUDA path
+    computes; GPU parity tests use this mode, the reference goldens pin both modes."""
+
+    def __init__(self, sample_rate=19200, symbol_rate=4800, portable=False):
+        self.portable = portable
         self.sample_rate, self.symbol_rate = sample_rate, symbol_rate
         self.sps = sample_rate / symbol_rate
         self.half_pi, self.quarter_pi, self.three_quarter_pi = np.pi / 2, np.pi / 4, 3 * np.pi / 4
@@ -84,7 +97,7 @@ class CQPSKOracle:
         """AGC + NCO + low-pass of one call (decoders/p25.py:413-471) -> complex64 chunk."""
         x = iq.astype(C64, copy=False)
         mags = np.abs(x)
-        mean_mag = np.mean(mags)
+        mean_mag = np.float32(np.mean(mags, dtype=np.float64)) if self.portable else np.mean(mags)
         if mean_mag > 1e-8:
             tg = self.agc_target / mean_mag
             self.agc_gain = self.agc_gain * (1 - self.agc_alpha) + tg * self.agc_alpha
@@ -96,8 +109,9 @@ class CQPSKOracle:
             self.phase_acc += self.freq_offset * len(x)
             self.phase_acc = np.angle(np.exp(1j * self.phase_acc))
         if len(x) >= len(self.taps):
-            xi = np.convolve(x.real, self.taps, mode="same")
-            xq = np.convolve(x.imag, self.taps, mode="same")
+            t = self.taps.astype(np.float64) if self.portable else self.taps
+            xi = np.convolve(x.real.astype(np.float64) if self.portable else x.real, t, mode="same")
+            xq = np.convolve(x.imag.astype(np.float64) if self.portable else x.imag, t, mode="same")
             x = (xi + 1j * xq).astype(C64)
         return x
 
@@ -125,7 +139,7 @@ class CQPSKOracle:
                     diff = (curr / cm) * np.conj(self.prev_symbol / pm)
                 else:
                     diff = curr * np.conj(self.prev_symbol)
-                phase = np.angle(diff)
+                phase = _angle32(diff) if (self.portable and diff.dtype == C64) else np.angle(diff)
                 self.phases.append(float(phase))
                 if phase >= self.half_pi:
                     dibit, expected = 1, self.three_quarter_pi

@@ -48,3 +48,28 @@ def native():
 
 def golden_path(name: str) -> str:
     return os.path.join(GOLDEN, name)
+
+
+# The reference's P25 paths call three numpy routines whose float32 results depend on the host CPU's SIMD
+# path: np.arctan2 (SVML), np.convolve on float32 (OpenBLAS sdot) and np.mean (pairwise). The goldens were
+# generated on a host with this fingerprint; the LITERAL oracle mode can only be compared bit for bit with them
+# on a host that computes the same bits (the portable mode is host independent and is always checked).
+GOLDEN_HOST_FINGERPRINT = "6a1bb319817b8d0e"
+
+
+def host_simd_fingerprint() -> str:
+    import hashlib
+
+    rng = np.random.default_rng(123)
+    y = rng.standard_normal(4096).astype(np.float32)
+    x = rng.standard_normal(4096).astype(np.float32)
+    a = np.arctan2(y, x)
+    t = rng.standard_normal(63).astype(np.float32)
+    c = np.convolve(x, t, mode="same")
+    m = np.float32(np.mean(np.abs(x)))
+    return hashlib.sha1(a.tobytes() + c.tobytes() + m.tobytes()).hexdigest()[:16]
+
+
+def require_golden_host():
+    if host_simd_fingerprint() != GOLDEN_HOST_FINGERPRINT:
+        pytest.skip("host CPU computes float32 arctan2/convolve/mean with different last bits than the golden host")

@@ -26,7 +26,7 @@ def run_bank(bank, xs, chunk):
 
 
 def run_oracle(fs, x, chunk):
-    o = C4FMOracle(sample_rate=fs)
+    o = C4FMOracle(sample_rate=fs, portable=True)
     ds, ss, cs = [], [], []
     for s in range(0, len(x), chunk):
         d, so = o.demodulate(x[s:s + chunk])
@@ -99,7 +99,7 @@ def test_reset_and_empty(native):
     dm.reset()
     d1, s1 = dm.demodulate(x)
     assert np.array_equal(d0, d1) and np.array_equal(s0, s1)
-    o = C4FMOracle(sample_rate=48000)
+    o = C4FMOracle(sample_rate=48000, portable=True)
     d2, _ = o.demodulate(x)
     assert np.array_equal(d0, d2)
 
@@ -110,7 +110,7 @@ def test_noise_only_and_short_chunks(native):
 
     rng = np.random.default_rng(11)
     x = ((rng.standard_normal(6000) + 1j * rng.standard_normal(6000)) * 0.1).astype(np.complex64)
-    dm, o = C4FMDemodulator(sample_rate=48000), C4FMOracle(sample_rate=48000)
+    dm, o = C4FMDemodulator(sample_rate=48000), C4FMOracle(sample_rate=48000, portable=True)
     for chunk in (7, 130, 3, 500, 1, 2000, 3359):
         if len(x) < chunk:
             break

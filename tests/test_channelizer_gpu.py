@@ -157,3 +157,29 @@ def test_full_size_properties(native):
     ys = ch.process_array(a[128 * s:].contiguous()); ch.reset()
     err2 = (ys[9:1000] - ya[9 + s:1000 + s]).abs().max()
     assert float(err2) < 1e-4 * float(ya.abs().max())
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_time_slabs_equal_the_unsharded_call(native, world):
+    """multi-GPU time sharding emulated in one process: every rank's slab (9-frame halo) reproduces the rows of the
+    unsharded process() call bit for bit, over two consecutive calls (history carried from the true block tail)."""
+    import torch
+
+    n = 256 + 128 * 1234 + 17
+    blocks = [torch.from_numpy(_iq(n, 60 + i)).cuda() for i in range(2)]
+    for fm in (False, True):
+        whole = _chan(native, 125_000_000, 488281)
+        ranks = [_chan(native, 125_000_000, 488281) for _ in range(world)]
+        for blk in blocks:
+            exp = whole.process_fm(blk) if fm else whole.process_array(blk)
+            got = torch.zeros_like(exp)
+            for r in range(world):
+                rows, f0 = ranks[r].process_slab(blk, world, r, fm=fm)
+                got[f0:f0 + rows.shape[0]] = rows
+            torch.cuda.synchronize()
+            if fm:
+                # a slab's first emitted row is computed like any other row (not the call's zero row), except at f0 = 0
+                assert torch.equal(got, exp)
+            else:
+                assert torch.equal(got, exp)
+            assert np.array_equal(ranks[-1].arm_history, whole.arm_history)

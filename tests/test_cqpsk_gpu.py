@@ -62,7 +62,7 @@ def test_bank_matches_oracle(native, fs, sr, chunk):
         for c in range(C):
             got[c].append(d[c, : int(cnt[c])].copy())
     for c in range(C):
-        o = CQPSKOracle(sample_rate=fs, symbol_rate=sr)
+        o = CQPSKOracle(sample_rate=fs, symbol_rate=sr, portable=True)
         exp, phases = [], []
         for s in range(0, n, chunk):
             exp.append(o.demodulate(xs[c, s:s + chunk]))
@@ -86,7 +86,7 @@ def test_bank_matches_oracle(native, fs, sr, chunk):
 def test_empty_and_zero_input(native):
     from wavecap_sdr_b200.decoders.p25 import CQPSKDemodulator
 
-    dm, o = CQPSKDemodulator(sample_rate=48000), CQPSKOracle(sample_rate=48000)
+    dm, o = CQPSKDemodulator(sample_rate=48000), CQPSKOracle(sample_rate=48000, portable=True)
     e = dm.demodulate(np.zeros(0, np.complex64))
     assert e.dtype == np.uint8 and e.size == 0
     z = np.zeros(1000, np.complex64)

@@ -6,7 +6,7 @@ differ in the last bit between CPUs."""
 import numpy as np
 import pytest
 
-from conftest import golden_path
+from conftest import golden_path, require_golden_host
 from oracle import refenv
 from oracle.c4fm import C4FMOracle, modulate_c4fm, random_frames, design_rrc_filter, sync_symbols
 from oracle.make_golden import c4fm_cases
@@ -22,11 +22,14 @@ def replay(demod, x, chunk):
     return np.concatenate(ds), np.concatenate(ss), np.array(cnt, dtype=np.int32)
 
 
+@pytest.mark.parametrize("portable", [False, True], ids=["literal", "portable"])
 @pytest.mark.parametrize("case", c4fm_cases(), ids=lambda c: c[0])
-def test_oracle_matches_golden(case):
+def test_oracle_matches_golden(case, portable):
     name, fs, chunk = case[0], case[1], case[2]
+    if not portable:
+        require_golden_host()
     g = np.load(golden_path("p25_c4fm.npz"))
-    o = C4FMOracle(sample_rate=fs)
+    o = C4FMOracle(sample_rate=fs, portable=portable)
     d, s, c = replay(o, g[name + "_x"], chunk)
     assert np.array_equal(c, g[name + "_counts"])
     assert np.array_equal(d, g[name + "_dibits"])

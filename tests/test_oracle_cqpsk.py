@@ -6,7 +6,7 @@ import warnings
 import numpy as np
 import pytest
 
-from conftest import golden_path
+from conftest import golden_path, require_golden_host
 from oracle import refenv
 from oracle.cqpsk import CQPSKOracle, mmse_table, modulate_cqpsk
 from oracle.make_golden import cqpsk_cases
@@ -23,11 +23,14 @@ def replay(demod, x, chunk):
     return np.concatenate(ds), np.array(cnt, dtype=np.int32)
 
 
+@pytest.mark.parametrize("portable", [False, True], ids=["literal", "portable"])
 @pytest.mark.parametrize("case", cqpsk_cases(), ids=lambda c: c[0])
-def test_oracle_matches_golden(case):
+def test_oracle_matches_golden(case, portable):
     name, fs, sr, chunk = case[:4]
+    if not portable:
+        require_golden_host()
     g = np.load(golden_path("p25_cqpsk.npz"))
-    o = CQPSKOracle(sample_rate=fs, symbol_rate=sr)
+    o = CQPSKOracle(sample_rate=fs, symbol_rate=sr, portable=portable)
     d, c = replay(o, g[name + "_x"], chunk)
     assert np.array_equal(c, g[name + "_counts"])
     assert np.array_equal(d, g[name + "_dibits"])

@@ -121,6 +121,7 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_chan_frames_for", i64, vp, i64)
     fn("wc_chan_reset", i32, vp)
     fn("wc_chan_process", i32, vp, vp, i64, i32, i64, i32, f32, vp, vp)
+    fn("wc_chan_carry_from", i32, vp, vp, i64, vp)
     fn("wc_chan_process_host", i32, vp, vp, i64, i32, i32, f32, vp)
     # analog chain stages
     fn("wc_front_chan_scratch_bytes", i32, i32)

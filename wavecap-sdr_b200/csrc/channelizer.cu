@@ -588,6 +588,20 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
     return 0;
 }
 
+// Advance the carried history as if process() had just been called on these n_samples, without computing
+// any output: used by time-sharded runs where another rank emitted the tail of the call.
+int wc_chan_carry_from(wc_chan* h, const void* iq_dev, long long n_samples, void* stream_v) {
+    WC_REQUIRE(h && iq_dev, "wc_chan_carry_from: null argument");
+    const long long F = wc_chan_frames_for(h, n_samples);
+    if (F == 0) return 0;
+    WC_REQUIRE(F < (1LL << 30), "wc_chan_carry_from: chunk too long");
+    chan_carry_kernel<<<h->T, 256, 0, (cudaStream_t)stream_v>>>(reinterpret_cast<const float2*>(iq_dev), (int)F, h->M, h->T,
+                                                               h->d_carried[h->cur], h->d_carried[h->cur ^ 1]);
+    WC_CUDA(cudaGetLastError());
+    h->cur ^= 1;
+    return 0;
+}
+
 int wc_chan_process_host(wc_chan* h, const void* iq_host, long long n_samples, int n_chunks, int mode,
                          float fm_scale, void* out_host) {
     WC_REQUIRE(h && iq_host && out_host, "wc_chan_process_host: null argument");
