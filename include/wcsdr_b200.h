@@ -148,6 +148,13 @@ int wc_c4fm_demod(wc_c4fm* h, const void* iq_dev, long long chan_stride, int n_s
                   float* soft_dev, int* n_sym_dev, int max_sym, void* stream);
 int wc_c4fm_demod_host(wc_c4fm* h, const void* iq_host /* [n_channels][n_samples] */, int n_samples,
                        unsigned char* dibits_host, float* soft_host, int* n_sym_host, int max_sym);
+/* stand-alone stages behind the helper classes backend/benchmark_dsp.py:17-114 times:
+ * _FMDemodulator.demodulate (c4fm.py:324-395), _Interpolator.filter (:2204-2253), _SoftSyncDetector.process (:2306-2329) */
+int wc_c4fm_diffdemod(wc_c4fm* h, const void* iq_pairs_dev /* float2 [C][n] */, int n_samples, float* phases_dev, void* stream);
+int wc_c4fm_interp(const float* samples_dev, int n, const int* offsets_dev, const double* mus_dev, int count, double* out_dev,
+                   void* stream);
+int wc_c4fm_sync_scores(const float* soft_dev, int n, const float* hist24_dev, double* scores_dev, float* new_hist24_dev,
+                        void* stream);
 /* state8 = {pll (get_timing_offset, c4fm.py:2809), gain, sample_point, buffer_pointer, fine_sync, symbols_since_sync,
  * sync_count, sync events accepted during the last call} */
 int wc_c4fm_get_state(wc_c4fm* h, int channel, double* state8);

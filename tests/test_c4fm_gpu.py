@@ -118,3 +118,41 @@ def test_noise_only_and_short_chunks(native):
         d, s = dm.demodulate(c)
         do, so = o.demodulate(c)
         assert np.array_equal(d, do) and (len(s) == 0 or np.max(np.abs(s - so)) <= 2e-6)
+
+
+def test_benchmark_helper_classes(native):
+    """_FMDemodulator / _Interpolator / _SoftSyncDetector (the names backend/benchmark_dsp.py:17-114 times) vs the oracle."""
+    from oracle.c4fm import DiffDemodOracle, SoftSyncOracle, TAPS, tap_row
+    from wavecap_sdr_b200.dsp.p25.c4fm import _FMDemodulator, _Interpolator, _SoftSyncDetector
+
+    rng = np.random.default_rng(21)
+    i = (rng.standard_normal(5000) * 0.5).astype(np.float32)
+    q = (rng.standard_normal(5000) * 0.5).astype(np.float32)
+    for kw in ({"symbol_delay": 10}, {"samples_per_symbol": 50000 / 4800}):
+        d = _FMDemodulator(**kw)
+        o = DiffDemodOracle(list(kw.values())[0], portable=True)
+        for a, b in ((0, 1000), (1000, 1007), (1007, 5000)):
+            got, exp = d.demodulate(i[a:b], q[a:b]), o.demodulate(i[a:b], q[a:b])
+            assert got.dtype == np.float32 and np.max(np.abs(got - exp)) <= 5e-7
+        d.reset()
+        o.reset()
+        assert np.max(np.abs(d.demodulate(i[:100], q[:100]) - o.demodulate(i[:100], q[:100]))) <= 5e-7
+    s = rng.standard_normal(600).astype(np.float32)
+    it = _Interpolator()
+    offs = rng.integers(-3, 598, 200)
+    mus = rng.random(200)
+    got = it.filter_batch(s, offs, mus)
+    for k in range(200):
+        row = tap_row(float(mus[k]))
+        exp = 0.0
+        for t in range(8):
+            j = int(offs[k]) + t
+            if 0 <= j < len(s):
+                exp += float(np.float32(s[j] * TAPS[row][t]))
+        assert abs(got[k] - exp) < 1e-12
+    assert abs(it.filter(s, 5, 0.0) - float(s[8])) < 1e-6 and abs(it.filter(s, 5, 1.0) - float(s[9])) < 1e-6
+    det, od = _SoftSyncDetector(), SoftSyncOracle()
+    soft = (rng.standard_normal(300) * 3).astype(np.float32)
+    got = np.concatenate([det.process_block(soft[:7]), det.process_block(soft[7:250]), [det.process(float(v)) for v in soft[250:]]])
+    exp = np.array([od.process(v) for v in soft])
+    assert np.max(np.abs(got - exp)) < 1e-9

@@ -1,0 +1,142 @@
+#!/usr/bin/env python
+"""Throughput of the non-headline configs (BASELINE.json configs[0..3] + the trunking fan-out) on one B200.
+Not the bench.py contract — a measurement aid whose JSON lines are kept under profiles/.
+
+Each line: config, what one "step" is, ms per step (CUDA events, after warm-up, inputs resident in HBM), the
+metric in the unit natural to the config, algorithmic HBM bytes per step and the HBM fraction they imply
+(SURVEY §8d says which configs are HBM-bound and which are compute/latency-bound by construction).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import wavecap_sdr_b200._native as N  # noqa: E402
+
+N.init(0)
+PEAK = 6550.1
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, warm=3, iters=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def emit(**kw):
+    if "alg_bytes" in kw and kw.get("ms"):
+        kw["alg_gbs"] = round(kw["alg_bytes"] / (kw["ms"] * 1e-3) / 1e9, 1)
+        kw["hbm_frac"] = round(kw["alg_gbs"] / PEAK, 4)
+    print(json.dumps(kw), flush=True)
+
+
+def c1_c2():
+    from wavecap_sdr_b200.capture import ChannelConfig, apply_mode_defaults, process_channels_batch
+
+    # C1: one WBFM channel, 2.4 MS/s cf32, B chunks of 120 000 per call
+    fs, n, B = 2_400_000, 120_000, 64
+    x = torch.view_as_complex(torch.randn((B * n, 2), device="cuda") * 0.3)
+    cfg = apply_mode_defaults("wbfm", ChannelConfig(id="a", capture_id="c", mode="wbfm", offset_hz=200000.0))
+    ms = timeit(lambda: process_channels_batch(x, fs, [cfg], n_chunks=B, return_device=True), iters=5)
+    emit(config="C1 WBFM 1 ch, 2.4 MS/s cf32", step=f"{B} chunks x {n} samples, full wbfm chain incl. host result assembly",
+         ms=round(ms, 3), msps=round(B * n / ms / 1e3, 1), realtime_x=round(B * n / fs / (ms * 1e-3), 1),
+         alg_bytes=B * n * 8 + B * 2400 * 4)
+    # C2: 16 NBFM channels, 10 MS/s int16, B chunks of 500 000
+    fs, n, B = 10_000_000, 500_000, 8
+    q = torch.randint(-2000, 2000, (B, n, 2), device="cuda", dtype=torch.int16)
+    cfgs = []
+    for i in range(16):
+        c = apply_mode_defaults("nbfm", ChannelConfig(id=str(i), capture_id="c", mode="nbfm", offset_hz=-3.75e6 + 5e5 * i))
+        c.squelch_db = -45.0
+        cfgs.append(c)
+    ms = timeit(lambda: process_channels_batch(q, fs, cfgs, n_chunks=B, in_fmt="cs16", apply_squelch=True,
+                                               return_device=True), iters=5)
+    emit(config="C2 16 NBFM ch + squelch, 10 MS/s cs16", step=f"{B} chunks x {n} samples x 16 channels",
+         ms=round(ms, 3), input_msps=round(B * n / ms / 1e3, 1), channel_msps=round(16 * B * n / ms / 1e3, 1),
+         realtime_x=round(B * n / fs / (ms * 1e-3), 1), alg_bytes=B * n * 4 + 16 * B * 2400 * 4)
+
+
+def c3():
+    from wavecap_sdr_b200.dsp.fft.cuda_backend import CudaFFTBackend
+
+    be = CudaFFTBackend(65536)
+    for frames in (46 * 8, 4096):
+        x = torch.view_as_complex(torch.randn((frames * 65536, 2), device="cuda") * 0.2)
+        out = be.execute_frames(x, frames, 65536, 4)
+        ms = timeit(lambda: be.execute_frames(x, frames, 65536, 4))
+        emit(config="C3 65536-pt spectrum, Hann, dB, fftshift, K=4 mean, 61.44 MS/s", step=f"{frames} contiguous frames",
+             ms=round(ms, 3), msps=round(frames * 65536 / ms / 1e3, 1), frames_per_s=round(frames / (ms * 1e-3)),
+             realtime_x=round(frames * 65536 / 61.44e6 / (ms * 1e-3), 1), alg_bytes=frames * 65536 * 8 + frames // 4 * 65536 * 4)
+        del x, out
+
+
+def c4():
+    from wavecap_sdr_b200.decoders.p25 import CQPSKBank
+    from wavecap_sdr_b200.dsp.p25.c4fm import C4FMBank
+    from oracle.c4fm import modulate_c4fm, random_frames
+    from oracle.cqpsk import modulate_cqpsk
+
+    fs = 48000
+    for C in (64, 1024):
+        for n in (2400, 72000):
+            rng = np.random.default_rng(1)
+            base = modulate_c4fm(random_frames(rng, n_frames=(n // 2140) + 2, payload=150, gap=40), fs, seed=1)[:n]
+            x = torch.from_numpy(np.ascontiguousarray(np.tile(base, (C, 1)))).cuda()
+            x = x * torch.exp(1j * torch.rand((C, 1), device="cuda") * 6.28).to(torch.complex64)
+            bank = C4FMBank(C, fs)
+            ms = timeit(lambda: bank.demodulate(x), warm=2, iters=5)
+            emit(config=f"C4 C4FM bank, {C} ch, 48 kS/s", step=f"one demodulate() of {n} samples/channel ({n / fs * 1e3:.0f} ms of signal)",
+                 ms=round(ms, 3), channel_msps=round(C * n / ms / 1e3, 2), realtime_x_per_channel=round(n / fs / (ms * 1e-3), 1),
+                 channels_x_realtime=round(C * n / fs / (ms * 1e-3)), alg_bytes=C * n * 8 + C * (n // 10) * 5)
+            cb = modulate_cqpsk(rng.integers(0, 4, n // 10 + 8), fs, 4800, seed=2)[:n]
+            xq = torch.from_numpy(np.ascontiguousarray(np.tile(cb, (C, 1)))).cuda()
+            qb = CQPSKBank(C, fs)
+            ms = timeit(lambda: qb.demodulate(xq), warm=2, iters=5)
+            emit(config=f"C4 CQPSK bank, {C} ch, 48 kS/s", step=f"one demodulate() of {n} samples/channel",
+                 ms=round(ms, 3), channel_msps=round(C * n / ms / 1e3, 2), realtime_x_per_channel=round(n / fs / (ms * 1e-3), 1),
+                 channels_x_realtime=round(C * n / fs / (ms * 1e-3)), alg_bytes=C * n * 8 + C * (n // 10))
+
+
+def ddc():
+    from wavecap_sdr_b200.trunking import DDCBank
+
+    fs, n = 6_000_000, 300_000
+    x = torch.view_as_complex(torch.randn((n, 2), device="cuda") * 0.1)
+    for K in (1, 24, 96):
+        b = DDCBank(K, fs, 30, 4)
+        b.set_offsets(np.linspace(-2.9e6, 2.9e6, K))
+        ms = timeit(lambda: b.process(x))
+        emit(config=f"trunking fan-out, {K} ch from 6 MS/s (NCO + 157-tap /30 + 73-tap /4)", step=f"one {n}-sample chunk (50 ms)",
+             ms=round(ms, 3), input_msps=round(n / ms / 1e3, 1), channel_msps=round(K * n / ms / 1e3, 1),
+             realtime_x=round(n / fs / (ms * 1e-3), 1), alg_bytes=n * 8 + K * (n // 120) * 8)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c1c2", "c3", "c4", "ddc"]
+    t0 = time.time()
+    if "c1c2" in which:
+        c1_c2()
+    if "c3" in which:
+        c3()
+    if "c4" in which:
+        c4()
+    if "ddc" in which:
+        ddc()
+    print(json.dumps({"wall_s": round(time.time() - t0, 1), "hbm_peak_gbs": PEAK}), flush=True)

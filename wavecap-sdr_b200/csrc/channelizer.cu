@@ -44,6 +44,7 @@ struct ChanArgs {
     const float2* carried; // [9][256] blk_{-9..-1} for chunk 0
     void* out;             // MODE 0: float2 [n_chunks*F][256]; MODE 1: float [n_chunks*F][256]
     float scale;           // FM discriminator scale
+    AtanScaled at;         // scale folded into the atan2 polynomial (fused FM mode)
 };
 
 constexpr int CH_REGION_W = 2 * CH_REGION;  // 32-bit words per frame region
@@ -64,8 +65,8 @@ __device__ __forceinline__ float2 blk_fetch(const ChanArgs& a, const float2* xc,
     return a.carried[(i + CH_T) * CH_M + k];
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(CH_THREADS, 4) chan256_kernel(const ChanArgs a) {
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArgs a) {
     __shared__ ChanSmem sm;
     const int tid = threadIdx.x;
     const int r = tid;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256_kernel(const ChanArgs a
         __syncthreads();
         if (MODE == 1) {
             float* o = reinterpret_cast<float*>(a.out) + (out_base + fs) * CH_M + 2 * tid;
-            const u64 sc = bc2(a.scale);
+            const AtanScaled at = a.at;
             auto one = [&](int i) {
                 const float* w = sw + i * CH_REGION_W + 2 * tid;
                 const u64 yre = *reinterpret_cast<const u64*>(w);
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256_kernel(const ChanArgs a
                 // p = y * conj(prev)
                 const u64 px = fma2(yre, pre, mul2(yim, pim));
                 const u64 py = sub2(mul2(yim, pre), mul2(yre, pim));
-                const u64 d = mul2(fast_atan2f_x2(py, px), sc);
+                const u64 d = scaled_atan2f_x2(py, px, at);
                 if (fs + i >= f0) *reinterpret_cast<u64*>(o + (long long)i * CH_M) = d;
                 pre = yre;
                 pim = yim;
@@ -538,11 +539,14 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
         a.out = out_dev;
         a.scale = fm_scale;
         int R;
+        int occ = 4;  // resident CTAs per SM of the fused-FM kernel; measured on B200: 4 -> 181 GS/s, 5 -> 165, 6 -> 159 (profiles/r01_chan_sweep2.jsonl)
+        if (const char* e = getenv("WC_CHAN_OCC")) occ = atoi(e);
+        if (mode == WC_CHAN_OUT_COMPLEX) occ = 4;
         if (const char* e = getenv("WC_CHAN_R")) {
             R = atoi(e);
         } else {
             const long long total = F * n_chunks;
-            const long long target = (long long)sm_count() * 4 * 6;
+            const long long target = (long long)sm_count() * occ * 6;
             R = (int)((total + target - 1) / target);
         }
         R = ((R + 7) / 8) * 8;
@@ -552,8 +556,21 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
         const int step = (mode == WC_CHAN_OUT_FM) ? R - 1 : R;
         const unsigned runs = (F > R) ? 1u + (unsigned)((F - R + step - 1) / step) : 1u;
         dim3 grid(runs, (unsigned)n_chunks);
-        if (mode == WC_CHAN_OUT_COMPLEX) chan256_kernel<0><<<grid, CH_THREADS, 0, stream>>>(a);
-        else chan256_kernel<1><<<grid, CH_THREADS, 0, stream>>>(a);
+        {
+            // scale * (degree-9 minimax coefficients of atan(t)/t in t^2), tools/fit_atan.py
+            const double c[5] = {0.999970019, -0.331700921, 0.185215309, -0.0919253752, 0.0238626394};
+            a.at.k0 = (float)(c[0] * fm_scale);
+            a.at.k1 = (float)(c[1] * fm_scale);
+            a.at.k2 = (float)(c[2] * fm_scale);
+            a.at.k3 = (float)(c[3] * fm_scale);
+            a.at.k4 = (float)(c[4] * fm_scale);
+            a.at.hp = (float)(1.5707963267948966 * fm_scale);
+            a.at.pi = (float)(3.141592653589793 * fm_scale);
+        }
+        if (mode == WC_CHAN_OUT_COMPLEX) chan256_kernel<0, 4><<<grid, CH_THREADS, 0, stream>>>(a);
+        else if (occ == 4) chan256_kernel<1, 4><<<grid, CH_THREADS, 0, stream>>>(a);
+        else if (occ == 6) chan256_kernel<1, 6><<<grid, CH_THREADS, 0, stream>>>(a);
+        else chan256_kernel<1, 5><<<grid, CH_THREADS, 0, stream>>>(a);
         WC_CUDA(cudaGetLastError());
     } else {
         const size_t need = sizeof(float2) * (size_t)F * n_chunks * h->M * (mode == WC_CHAN_OUT_FM ? 2 : 1);

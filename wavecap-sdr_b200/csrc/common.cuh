@@ -170,6 +170,34 @@ __device__ __forceinline__ u64 fast_atan2f_x2(u64 y, u64 x) {
     return pk2(copysignf(a0, y0), copysignf(a1, y1));
 }
 
+// Discriminator flavour of the above: returns scale * atan2(y, x) for two (y, x) pairs with the output scale folded
+// into the polynomial coefficients and the quadrant constants (k[0..4] = scale * c_i, hp = scale*pi/2, pi = scale*pi).
+// Degree-9 odd minimax polynomial in t = min/max (tools/fit_atan.py: max relative error 3.0e-5, i.e. <= 3e-5
+// relative on every output sample, inside the 1e-4 relative-RMS budget of the FM path).
+struct AtanScaled {
+    float k0, k1, k2, k3, k4, hp, pi;
+};
+__device__ __forceinline__ u64 scaled_atan2f_x2(u64 y, u64 x, const AtanScaled& c) {
+    const float x0 = lo2(x), x1 = hi2(x), y0 = lo2(y), y1 = hi2(y);
+    const float ax0 = fabsf(x0), ay0 = fabsf(y0), ax1 = fabsf(x1), ay1 = fabsf(y1);
+    const float mx0 = fmaxf(fmaxf(ax0, ay0), 1e-37f), mn0 = fminf(ax0, ay0);
+    const float mx1 = fmaxf(fmaxf(ax1, ay1), 1e-37f), mn1 = fminf(ax1, ay1);
+    const u64 t = mul2(pk2(mn0, mn1), pk2(rcp_approx(mx0), rcp_approx(mx1)));
+    const u64 s = mul2(t, t);
+    u64 p = bc2(c.k4);
+    p = fma2(p, s, bc2(c.k3));
+    p = fma2(p, s, bc2(c.k2));
+    p = fma2(p, s, bc2(c.k1));
+    p = fma2(p, s, bc2(c.k0));
+    const u64 a = mul2(p, t);
+    float a0 = lo2(a), a1 = hi2(a);
+    a0 = (ay0 > ax0) ? (c.hp - a0) : a0;
+    a1 = (ay1 > ax1) ? (c.hp - a1) : a1;
+    a0 = (x0 < 0.0f) ? (c.pi - a0) : a0;
+    a1 = (x1 < 0.0f) ? (c.pi - a1) : a1;
+    return pk2(copysignf(a0, y0), copysignf(a1, y1));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

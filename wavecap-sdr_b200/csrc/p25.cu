@@ -612,6 +612,45 @@ __global__ void c4fm_reset_kernel(C4State* st, float* ring, float2* hist0, float
     }
 }
 
+// ---- stand-alone stages for the helper classes benchmark_dsp.py times (_Interpolator, _SoftSyncDetector) ----
+// _Interpolator.filter (c4fm.py:2204-2253): 8-tap dot product at row clamp(int((1-mu)*128+0.5)); taps outside the
+// array contribute nothing (the reference's slow path); float32 products, float64 sum.
+__global__ void c4fm_interp_kernel(const float* __restrict__ x, int n, const int* __restrict__ offs, const double* __restrict__ mus,
+                                   int count, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int row = (int)((1.0 - mus[i]) * 128 + 0.5);
+    row = min(max(row, 0), 128);
+    const int o = offs[i];
+    double acc = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int j = o + t;
+        if (j >= 0 && j < n) acc += (double)__fmul_rn(x[j], c_interp[row][t]);
+    }
+    out[i] = acc;
+}
+
+// _SoftSyncDetector.process for a block of symbols (c4fm.py:2306-2329): score[k] = sum_i sync[i] * s[k-23+i] with the
+// 24 symbols before the block in hist (oldest first); new_hist = last 24 of [hist | s].
+__global__ void c4fm_sync_score_kernel(const float* __restrict__ s, int n, const float* __restrict__ hist, double* __restrict__ score,
+                                       float* __restrict__ new_hist) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < 24) {
+        const int t = n - 24 + k;
+        new_hist[k] = (t >= 0) ? s[t] : hist[24 + t];
+    }
+    if (k >= n) return;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+        const int t = k - 23 + i;
+        const float v = (t >= 0) ? s[t] : hist[24 + t];
+        acc += (double)__fmul_rn(c_sync[i], v);
+    }
+    score[k] = acc;
+}
+
 // ---- host-side filter design (used when the caller passes no taps) ----
 // scipy.signal.firwin(numtaps, cutoff_hz, fs=fs, window="hamming"): the branch design_baseband_lpf
 // (c4fm.py:95-132) ends up in with scipy >= 1.15, where remez(..., Hz=) raises.
@@ -916,6 +955,53 @@ int wc_c4fm_demod_host(wc_c4fm* h, const void* iq_host, int n_samples, unsigned 
     WC_CUDA(cudaMemcpyAsync(soft_host, h->d_soft, sizeof(float) * (size_t)C * max_sym, cudaMemcpyDeviceToHost, h->stream));
     WC_CUDA(cudaMemcpyAsync(n_sym_host, h->d_nsym, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
     WC_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+/* _FMDemodulator.demodulate (c4fm.py:324-395) on its own: filtered (i, q) pairs [C][n] -> phases float32 [C][n], with the
+ * overlap carried in the handle like the reference object does. A handle used this way should not also be used for
+ * wc_c4fm_demod (both advance the same overlap state). */
+int wc_c4fm_diffdemod(wc_c4fm* h, const void* iq_pairs_dev, int n_samples, float* phases_dev, void* stream_v) {
+    WC_REQUIRE(h && iq_pairs_dev && phases_dev, "wc_c4fm_diffdemod: null argument");
+    if (n_samples <= 0) return 0;
+    PhaseArgs p;
+    p.filt = reinterpret_cast<const float2*>(iq_pairs_dev);
+    p.tail = h->d_tail[h->cur];
+    p.new_tail = h->d_tail[h->cur ^ 1];
+    p.n = n_samples;
+    p.k = h->k;
+    p.st = h->d_state;
+    p.ph = phases_dev;
+    p.ring = h->d_ring;
+    const int pn = n_samples > h->k.ov ? n_samples : h->k.ov;
+    c4fm_phase_kernel<<<dim3((pn + 255) / 256, h->C), 256, 0, (cudaStream_t)stream_v>>>(p);
+    WC_CUDA(cudaGetLastError());
+    h->cur ^= 1;
+    return 0;
+}
+
+/* _Interpolator.filter for `count` (offset, mu) pairs over one float32 sample array (c4fm.py:2204-2253) -> float64 */
+int wc_c4fm_interp(const float* samples_dev, int n, const int* offsets_dev, const double* mus_dev, int count, double* out_dev,
+                   void* stream_v) {
+    WC_REQUIRE(samples_dev && offsets_dev && mus_dev && out_dev, "wc_c4fm_interp: null argument");
+    if (count <= 0) return 0;
+    c4fm_interp_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(samples_dev, n, offsets_dev, mus_dev, count, out_dev);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* _SoftSyncDetector.process over a block (c4fm.py:2268-2329): scores float64 [n]; hist24 in/out are device float32[24] */
+int wc_c4fm_sync_scores(const float* soft_dev, int n, const float* hist24_dev, double* scores_dev, float* new_hist24_dev,
+                        void* stream_v) {
+    WC_REQUIRE(soft_dev && hist24_dev && scores_dev && new_hist24_dev, "wc_c4fm_sync_scores: null argument");
+    if (n <= 0) return 0;
+    float sync[24];
+    const unsigned long long pat = 0x5575F5FF77FFull;
+    for (int i = 0; i < 24; ++i) sync[i] = (((pat >> ((23 - i) * 2)) & 3ull) == 1ull) ? 3.0f : -3.0f;
+    WC_CUDA(cudaMemcpyToSymbolAsync(c_sync, sync, sizeof(sync), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream_v));
+    const int m = n > 24 ? n : 24;
+    c4fm_sync_score_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(soft_dev, n, hist24_dev, scores_dev, new_hist24_dev);
+    WC_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -13,6 +13,7 @@
 //   HBM traffic per input sample: 8 B in + 4/K B out (the 16 B of scratch traffic stays in L2).
 // Any other power of two: windowed radix-2 Stockham passes in global memory (correct, untuned).
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "../../include/wcsdr_b200.h"
@@ -45,9 +46,8 @@ __device__ __forceinline__ void sp_tables(SpSmem& sm, int tid) {
 
 // 256-point FFT of the shared row `reg` by the 16 threads of one half-warp (t = lane & 15).
 // On return thread t holds X[t + 16*k2] in v[rev4(k2)].
-__device__ __forceinline__ void fft256_row(u64* reg, const float2* tw, int t, u64 (&v)[16]) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = reg[t + 16 * i];
+// fft256_core: same, with the row already in registers (v[i] = x[t + 16*i]); `reg` is only the exchange area.
+__device__ __forceinline__ void fft256_core(u64* reg, const float2* tw, int t, u64 (&v)[16]) {
     __syncwarp();
     fft16(v);
 #pragma unroll
@@ -65,9 +65,27 @@ __device__ __forceinline__ void fft256_row(u64* reg, const float2* tw, int t, u6
     __syncwarp();
     fft16(v);
 }
+__device__ __forceinline__ void fft256_row(u64* reg, const float2* tw, int t, u64 (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = reg[t + 16 * i];
+    fft256_core(reg, tw, t, v);
+}
+
+// ---- Ampere-style async copies (LDGSTS): global -> shared without staging in registers ----
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // pass A: grid (N2/16, n_frames)
-__global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_a(const float2* __restrict__ iq, long long frame_stride,
+__global__ void __launch_bounds__(SP_THREADS, 4) spectrum_pass_a(const float2* __restrict__ iq, long long frame_stride,
                                                                  const float* __restrict__ window,
                                                                  u64* __restrict__ scratch) {
     __shared__ SpSmem sm;
@@ -113,7 +131,7 @@ __global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_a(const float2* _
 }
 
 // pass B: grid (N1/16, n_groups); each CTA accumulates `avg` frames.
-__global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_b(const u64* __restrict__ scratch, int avg, int n_frames,
+__global__ void __launch_bounds__(SP_THREADS, 4) spectrum_pass_b(const u64* __restrict__ scratch, int avg, int n_frames,
                                                                  float* __restrict__ out) {
     __shared__ SpSmem sm;
     const int tid = threadIdx.x;
@@ -144,6 +162,305 @@ __global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_b(const u64* __re
     // stage as [k2][16 rows] so that the 16 adjacent k1 of one k2 leave as one 64-byte run
     __syncthreads();
     float* so = reinterpret_cast<float*>(sm.tile);
+    const float inv = 1.0f / (float)cnt;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) so[(t + 16 * q) * 17 + g] = acc[q] * inv;
+    __syncthreads();
+    float* o = out + (long long)grp * SP_N;
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+        const int id = tid + SP_THREADS * j;
+        const int k2 = id >> 4, row = id & 15;
+        const int k = (r0 + row) + SP_N1 * k2;
+        o[k ^ (SP_N / 2)] = so[k2 * 17 + row];  // fftshift
+    }
+}
+
+// ---- pipelined, persistent versions (the ones the 65536-point path launches) ------------------------
+// Both passes are streaming kernels whose only problem is latency, so each CTA keeps TWO tiles in shared
+// memory: while the 256-point FFTs of tile k run, the LDGSTS copies of tile k+1 are in flight.
+constexpr int SPB_STRIDE = 274;   // pass-B row stride in complex words: even (16-byte copies), >= 272 exchange area
+
+struct SpSmemA {
+    u64 tile[2][SP_COLS * SP_STRIDE];
+    float2 tw[256], wa[256], wb[256];
+};
+struct SpSmemB {
+    u64 tile[2][SP_COLS * SPB_STRIDE];
+    float2 tw[256];
+};
+
+// pass A: CTA b owns column tile (b & 15) for frames (b >> 4), (b >> 4) + G, ...; the Hann window of its 16
+// columns lives in registers for the whole kernel.
+__global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_a2(const float2* __restrict__ iq, long long frame_stride,
+                                                                  const float* __restrict__ window, u64* __restrict__ scratch,
+                                                                  int n_frames) {
+    extern __shared__ __align__(16) unsigned char sp_raw[];
+    SpSmemA& sm = *reinterpret_cast<SpSmemA*>(sp_raw);
+    const int tid = threadIdx.x;
+    const int c0 = (blockIdx.x & 15) * SP_COLS;
+    const int G = gridDim.x >> 4;
+    {
+        float sn, cs;
+        sincospif(-(float)((tid >> 4) * (tid & 15)) * (1.0f / 128.0f), &sn, &cs);
+        sm.tw[tid] = make_float2(cs, sn);
+        sincospif(-(float)tid * (1.0f / 32768.0f), &sn, &cs);
+        sm.wa[tid] = make_float2(cs, sn);
+        sincospif(-(float)tid * (1.0f / 128.0f), &sn, &cs);
+        sm.wb[tid] = make_float2(cs, sn);
+    }
+    const int g = tid >> 4, t = tid & 15;
+    float wv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wv[i] = __ldg(window + (t + 16 * i) * SP_N2 + c0 + g);
+
+    auto issue = [&](int f, int buf) {
+        const float2* x = iq + (long long)f * frame_stride;
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) {
+            const int id = tid + SP_THREADS * j;
+            const int n1 = id >> 4, col = id & 15;
+            cp_async8(&sm.tile[buf][col * SP_STRIDE + n1], x + n1 * SP_N2 + c0 + col);
+        }
+        cp_async_commit();
+    };
+    int f = blockIdx.x >> 4;
+    if (f < n_frames) issue(f, 0);
+    int buf = 0;
+    for (; f < n_frames; f += G, buf ^= 1) {
+        const bool more = f + G < n_frames;
+        if (more) issue(f + G, buf ^ 1);
+        if (more) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncthreads();
+        u64* reg = sm.tile[buf] + g * SP_STRIDE;
+        u64 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = mul2(reg[t + 16 * i], bc2(wv[i]));
+        fft256_core(reg, sm.tw, t, v);
+        __syncwarp();
+        const int n2 = c0 + g;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int k1 = t + 16 * q;
+            const int m = n2 * k1;  // < 65536
+            const float2 a = sm.wa[m & 255], b = sm.wb[m >> 8];
+            const float2 wq = cmul(a, b);  // exp(-2 pi i m / 65536)
+            reg[k1] = twid(v[rev4(q)], wq.x, -wq.y);
+        }
+        __syncthreads();
+        u64* T = scratch + (long long)f * SP_N;
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) {
+            const int id = tid + SP_THREADS * j;
+            const int k1 = id >> 4, col = id & 15;
+            T[k1 * SP_N2 + c0 + col] = sm.tile[buf][col * SP_STRIDE + k1];
+        }
+        __syncthreads();  // tile[buf] is the target of the copies issued at the top of the next iteration but one
+    }
+}
+
+// pass B: work item = (16 rows, averaging group); a CTA walks items blockIdx.x, +gridDim.x, ... and inside an
+// item the frames of the group, always with the next tile's copies in flight.
+__global__ void __launch_bounds__(SP_THREADS, 3) spectrum_pass_b2(const u64* __restrict__ scratch, int avg, int n_frames,
+                                                                  int n_groups, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sp_raw[];
+    SpSmemB& sm = *reinterpret_cast<SpSmemB*>(sp_raw);
+    const int tid = threadIdx.x;
+    {
+        float sn, cs;
+        sincospif(-(float)((tid >> 4) * (tid & 15)) * (1.0f / 128.0f), &sn, &cs);
+        sm.tw[tid] = make_float2(cs, sn);
+    }
+    const int g = tid >> 4, t = tid & 15;
+    const int n_items = n_groups * 16;
+    auto frames_in = [&](int item) { return min(avg, n_frames - (item >> 4) * avg); };
+    auto issue = [&](int item, int fr, int buf) {
+        const u64* T = scratch + (long long)((item >> 4) * avg + fr) * SP_N + (long long)(item & 15) * SP_COLS * SP_N2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int id = tid + SP_THREADS * j;   // 16-byte chunk: 128 per row
+            const int row = id >> 7, cc = id & 127;
+            cp_async16(&sm.tile[buf][row * SPB_STRIDE + 2 * cc], T + row * SP_N2 + 2 * cc);
+        }
+        cp_async_commit();
+    };
+    int item = blockIdx.x, fr = 0, buf = 0;
+    if (item < n_items) issue(item, 0, 0);
+    float acc[16];
+    while (item < n_items) {
+        const int cnt = frames_in(item);
+        if (fr == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        }
+        // next tile in this CTA's sequence
+        int nitem = item, nfr = fr + 1;
+        if (nfr >= cnt) {
+            nitem = item + gridDim.x;
+            nfr = 0;
+        }
+        const bool more = nitem < n_items;
+        if (more) issue(nitem, nfr, buf ^ 1);
+        if (more) cp_async_wait<1>();
+        else cp_async_wait<0>();
+        __syncthreads();
+        u64 v[16];
+        fft256_row(sm.tile[buf] + g * SPB_STRIDE, sm.tw, t, v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float re = lo2(v[rev4(q)]), im = hi2(v[rev4(q)]);
+            const float mag = sqrtf(fmaf(re, re, im * im));
+            acc[q] += 6.02059991327962f * __log2f(mag + 1e-10f);  // 20*log10(x) = 20*log10(2)*log2(x)
+        }
+        __syncthreads();  // all exchange traffic in tile[buf] done
+        if (fr + 1 >= cnt) {
+            // stage as [k2][16 rows] so that the 16 adjacent k1 of one k2 leave as one 64-byte run
+            float* so = reinterpret_cast<float*>(sm.tile[buf]);
+            const float inv = 1.0f / (float)cnt;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) so[(t + 16 * q) * 17 + g] = acc[q] * inv;
+            __syncthreads();
+            float* o = out + (long long)(item >> 4) * SP_N;
+            const int r0 = (item & 15) * SP_COLS;
+#pragma unroll 4
+            for (int j = 0; j < 16; ++j) {
+                const int id = tid + SP_THREADS * j;
+                const int k2 = id >> 4, row = id & 15;
+                const int k = (r0 + row) + SP_N1 * k2;
+                o[k ^ (SP_N / 2)] = so[k2 * 17 + row];  // fftshift
+            }
+            __syncthreads();
+        }
+        item = nitem;
+        fr = nfr;
+        buf ^= 1;
+    }
+}
+
+// ---- register-direct versions: no staging through shared memory -------------------------------------
+// ncu on the staged kernels shows them bound by shared-memory wavefronts (stage in, FFT read, exchange, stage out),
+// not by DRAM. Here every thread loads its 16 FFT inputs straight from global memory into registers with lanes
+// running along the contiguous direction (128-byte segments), and shared memory carries only the one 16x16
+// exchange in the middle of each 256-point FFT.
+//
+// pass A3: thread (t = tid >> 4, col = tid & 15) owns column c0+col, rows n1 = t + 16 i. The 16 threads of one
+// column sit in 16 different half-warps, so the exchange is CTA-wide (__syncthreads).
+struct SpSmemA3 {
+    u64 ex[SP_COLS * SP_STRIDE];   // per column: 16 x 17 exchange area (stride 273: columns land on distinct banks)
+    float2 tw[256];
+};
+
+__global__ void __launch_bounds__(SP_THREADS, 3) spectrum_pass_a3(const float2* __restrict__ iq, long long frame_stride,
+                                                                  const float* __restrict__ window, u64* __restrict__ scratch,
+                                                                  int n_frames) {
+    __shared__ SpSmemA3 sm;
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * SP_COLS;
+    {
+        float sn, cs;
+        sincospif(-(float)((tid >> 4) * (tid & 15)) * (1.0f / 128.0f), &sn, &cs);
+        sm.tw[tid] = make_float2(cs, sn);
+    }
+    const int t = tid >> 4, col = tid & 15;
+    const int n2 = c0 + col;
+    // four-step twiddle W_65536^(n2 * k1), k1 = t + 16 kb: base * step^kb
+    float2 base, step;
+    {
+        float sn, cs;
+        sincospif(-(float)(n2 * t) * (1.0f / 32768.0f), &sn, &cs);
+        base = make_float2(cs, sn);
+        sincospif(-(float)(n2 * 16) * (1.0f / 32768.0f), &sn, &cs);
+        step = make_float2(cs, sn);
+    }
+    u64* ex = sm.ex + col * SP_STRIDE;
+    const u64* xw = reinterpret_cast<const u64*>(iq);
+    for (int f = blockIdx.y; f < n_frames; f += gridDim.y) {
+        const u64* x = xw + (long long)f * frame_stride;
+        u64 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int n = (t + 16 * i) * SP_N2 + n2;
+            v[i] = mul2(__ldg(x + n), bc2(__ldg(window + n)));
+        }
+        fft16(v);
+        __syncthreads();   // previous frame's exchange reads are done
+#pragma unroll
+        for (int ka = 0; ka < 16; ++ka) {
+            u64 w = v[rev4(ka)];
+            if (ka > 0) {
+                const float2 q = sm.tw[ka * 16 + t];
+                w = twid(w, q.x, -q.y);
+            }
+            ex[t * 17 + ka] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = ex[m * 17 + t];   // thread t now plays ka = t
+        fft16(v);
+        u64* T = scratch + (long long)f * SP_N;
+        float2 w = base;
+#pragma unroll
+        for (int kb = 0; kb < 16; ++kb) {
+            const int k1 = t + 16 * kb;
+            T[k1 * SP_N2 + n2] = twid(v[rev4(kb)], w.x, -w.y);
+            w = cmul(w, step);
+        }
+    }
+}
+
+// pass B3: thread (g = tid >> 4 row, t = tid & 15); the next frame's row is prefetched into registers while the
+// current one is transformed; exchange is half-warp local.
+struct SpSmemB3 {
+    u64 ex[SP_COLS * SP_STRIDE];
+    float2 tw[256];
+};
+
+__global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_b3(const u64* __restrict__ scratch, int avg, int n_frames,
+                                                                  float* __restrict__ out) {
+    __shared__ SpSmemB3 sm;
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * SP_COLS;
+    const int grp = blockIdx.y;
+    {
+        float sn, cs;
+        sincospif(-(float)((tid >> 4) * (tid & 15)) * (1.0f / 128.0f), &sn, &cs);
+        sm.tw[tid] = make_float2(cs, sn);
+    }
+    __syncthreads();
+    const int g = tid >> 4, t = tid & 15;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    const int f0 = grp * avg;
+    const int cnt = min(avg, n_frames - f0);
+    u64* ex = sm.ex + g * SP_STRIDE;
+    u64 nx[16];
+    {
+        const u64* T = scratch + (long long)f0 * SP_N + (long long)(r0 + g) * SP_N2;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nx[i] = __ldg(T + t + 16 * i);
+    }
+    for (int f = 0; f < cnt; ++f) {
+        u64 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = nx[i];
+        if (f + 1 < cnt) {
+            const u64* T = scratch + (long long)(f0 + f + 1) * SP_N + (long long)(r0 + g) * SP_N2;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) nx[i] = __ldg(T + t + 16 * i);
+        }
+        fft256_core(ex, sm.tw, t, v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float re = lo2(v[rev4(q)]), im = hi2(v[rev4(q)]);
+            const float mag = sqrtf(fmaf(re, re, im * im));
+            acc[q] += 6.02059991327962f * __log2f(mag + 1e-10f);  // 20*log10(x) = 20*log10(2)*log2(x)
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    float* so = reinterpret_cast<float*>(sm.ex);
     const float inv = 1.0f / (float)cnt;
 #pragma unroll
     for (int q = 0; q < 16; ++q) so[(t + 16 * q) * 17 + g] = acc[q] * inv;
@@ -248,6 +565,16 @@ int wc_spectrum_create(int fft_size, wc_spectrum** out) {
         return -2;
     }
     cudaMemcpy(h->d_window, h->h_window.data(), sizeof(float) * fft_size, cudaMemcpyHostToDevice);
+    // both passes are latency-bound streaming kernels: 4 resident CTAs per SM (64 registers, 41 KB of shared memory
+    // each) need the large shared-memory carve-out
+    cudaFuncSetAttribute(spectrum_pass_a, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(spectrum_pass_b, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(spectrum_pass_a2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSmemA));
+    cudaFuncSetAttribute(spectrum_pass_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSmemB));
+    cudaFuncSetAttribute(spectrum_pass_a2, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(spectrum_pass_a3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(spectrum_pass_b3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(spectrum_pass_b2, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     *out = h;
     return 0;
 }
@@ -277,8 +604,12 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
     cudaStream_t st = (cudaStream_t)stream_v;
     const int n = h->n;
     const float2* iq = reinterpret_cast<const float2*>(iq_dev);
-    // process in slabs whose scratch stays L2-resident (<= 64 MB)
-    int slab = (int)((64ull << 20) / (sizeof(float2) * (size_t)n));
+    // process in slabs of <= 512 MB of scratch. Measured on B200 (profiles/r01_spectrum_notes.md): the scratch does not
+    // stay L2-resident at any useful slab size (ncu: pass A writes it to DRAM), small slabs only starve the grid
+    // (16 MB: 79 GS/s, 64 MB: 124, 512 MB: 150), so slabs are sized for parallelism.
+    size_t slab_bytes = 512ull << 20;
+    if (const char* e = getenv("WC_SPECTRUM_SLAB_MB")) slab_bytes = (size_t)atoi(e) << 20;
+    int slab = (int)(slab_bytes / (sizeof(float2) * (size_t)n));
     if (slab < avg) slab = avg;
     slab -= slab % avg;
     if (slab > n_frames) slab = ((n_frames + avg - 1) / avg) * avg;
@@ -291,8 +622,27 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
         const float2* x = iq + (long long)f0 * frame_stride;
         if (n == SP_N) {
             u64* T = reinterpret_cast<u64*>(h->d_scratch);
-            spectrum_pass_a<<<dim3(SP_N2 / SP_COLS, cnt), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T);
-            spectrum_pass_b<<<dim3(SP_N1 / SP_COLS, groups), SP_THREADS, 0, st>>>(T, avg, cnt, o);
+            const char* var = getenv("WC_SPECTRUM_VARIANT");
+            const int variant = var ? atoi(var) : 3;
+            if (variant == 3) {
+                int fy = (6 * sm_count()) / 16;   // frames in flight: ~6 CTAs per SM over the 16 column tiles
+                if (fy > cnt) fy = cnt;
+                if (fy < 1) fy = 1;
+                spectrum_pass_a3<<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
+                spectrum_pass_b3<<<dim3(SP_N1 / SP_COLS, groups), SP_THREADS, 0, st>>>(T, avg, cnt, o);
+            } else if (variant == 1) {
+                spectrum_pass_a<<<dim3(SP_N2 / SP_COLS, cnt), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T);
+                spectrum_pass_b<<<dim3(SP_N1 / SP_COLS, groups), SP_THREADS, 0, st>>>(T, avg, cnt, o);
+            } else {
+                // persistent grids: 2 (pass A) / 3 (pass B) CTAs per SM, each double-buffering its tiles
+                int ga = (2 * sm_count()) / 16;
+                if (ga > cnt) ga = cnt;
+                if (ga < 1) ga = 1;
+                spectrum_pass_a2<<<16 * ga, SP_THREADS, sizeof(SpSmemA), st>>>(x, frame_stride, h->d_window, T, cnt);
+                int gb = 3 * sm_count();
+                if (gb > groups * 16) gb = groups * 16;
+                spectrum_pass_b2<<<gb, SP_THREADS, sizeof(SpSmemB), st>>>(T, avg, cnt, groups, o);
+            }
         } else {
             float2* A = reinterpret_cast<float2*>(h->d_scratch);
             float2* B = A + (size_t)n * slab;

@@ -159,3 +159,91 @@ class C4FMDemodulator:
     @property
     def _fine_sync(self) -> bool:
         return self._bank.state(0)["fine_sync"]
+
+
+# ---- helper classes timed by backend/benchmark_dsp.py:17-114 (same names and call shapes) -----------------------
+
+class _FMDemodulator:
+    """Symbol-spaced differential demodulator (c4fm.py:276-395) on the GPU. `symbol_delay` is accepted as an alias of
+    `samples_per_symbol` — benchmark_dsp.py:27 still passes the old keyword, which raises TypeError in the reference."""
+
+    def __init__(self, samples_per_symbol: float = 10.0, symbol_delay: float | None = None):
+        if symbol_delay is not None:
+            samples_per_symbol = float(symbol_delay)
+        self.samples_per_symbol = float(samples_per_symbol)
+        self._bank = C4FMBank(1, int(round(self.samples_per_symbol * 4800)), 4800)
+        sps = C.c_double()
+        N.check(N.lib().wc_c4fm_info(self._bank._h, None, C.byref(sps), None, None))
+        assert abs(sps.value - self.samples_per_symbol) < 1e-9, "samples_per_symbol must be sample_rate / 4800 for an integer rate"
+
+    def reset(self) -> None:
+        self._bank.reset(0)
+
+    def demodulate(self, i, q):
+        import torch
+
+        i = np.asarray(i, dtype=np.float32)
+        q = np.asarray(q, dtype=np.float32)
+        n = len(i)
+        if n == 0:
+            return np.array([], dtype=np.float32)
+        pairs = torch.from_numpy(np.ascontiguousarray(np.stack([i, q], axis=1))).cuda()
+        out = torch.empty((n,), dtype=torch.float32, device="cuda")
+        N.check(N.lib().wc_c4fm_diffdemod(self._bank._h, C.c_void_p(pairs.data_ptr()), n, C.c_void_p(out.data_ptr()),
+                                          N.torch_stream_ptr()))
+        return out.cpu().numpy()
+
+
+class _Interpolator:
+    """8-tap, 128-step fractional interpolator (c4fm.py:891-2253); `filter_batch` evaluates many positions per launch."""
+
+    NTAPS = 8
+    NSTEPS = 128
+
+    def filter_batch(self, samples, offsets, mus) -> np.ndarray:
+        import torch
+
+        N.ensure_init()
+        x = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float32)).cuda()
+        o = torch.from_numpy(np.ascontiguousarray(offsets, dtype=np.int32)).cuda()
+        m = torch.from_numpy(np.ascontiguousarray(mus, dtype=np.float64)).cuda()
+        out = torch.empty((o.numel(),), dtype=torch.float64, device="cuda")
+        N.check(N.lib().wc_c4fm_interp(C.c_void_p(x.data_ptr()), int(x.numel()), C.c_void_p(o.data_ptr()),
+                                       C.c_void_p(m.data_ptr()), int(o.numel()), C.c_void_p(out.data_ptr()),
+                                       N.torch_stream_ptr()))
+        return out.cpu().numpy()
+
+    def filter(self, samples, offset: int, mu: float) -> float:
+        return float(self.filter_batch(samples, [int(offset)], [float(mu)])[0])
+
+
+class _SoftSyncDetector:
+    """24-symbol soft sync correlator (c4fm.py:2268-2329); `process_block` scores a whole block per launch."""
+
+    SYNC_PATTERN = 0x5575F5FF77FF
+    SYNC_THRESHOLD = 130.0
+
+    def __init__(self) -> None:
+        N.ensure_init()
+        self.reset()
+
+    def reset(self) -> None:
+        self._hist = np.zeros(24, dtype=np.float32)
+
+    def process_block(self, soft) -> np.ndarray:
+        import torch
+
+        s = torch.from_numpy(np.ascontiguousarray(soft, dtype=np.float32).reshape(-1)).cuda()
+        n = int(s.numel())
+        if n == 0:
+            return np.zeros(0, dtype=np.float64)
+        h = torch.from_numpy(self._hist).cuda()
+        nh = torch.empty_like(h)
+        sc = torch.empty((n,), dtype=torch.float64, device="cuda")
+        N.check(N.lib().wc_c4fm_sync_scores(C.c_void_p(s.data_ptr()), n, C.c_void_p(h.data_ptr()), C.c_void_p(sc.data_ptr()),
+                                            C.c_void_p(nh.data_ptr()), N.torch_stream_ptr()))
+        self._hist = nh.cpu().numpy()
+        return sc.cpu().numpy()
+
+    def process(self, soft_symbol: float) -> float:
+        return float(self.process_block([soft_symbol])[0])

@@ -1,0 +1,59 @@
+"""Rebind the reference's hot-path names to the GPU implementations.
+
+    import wavecap_sdr_b200.install as b200
+    b200.install()             # needs an importable `wavecapsdr`, libwcsdr_b200.so and a B200
+
+Every right-hand side has the reference's signature and array contracts. `uninstall()` restores the originals.
+"""
+from __future__ import annotations
+
+import importlib
+
+from . import _native as N
+
+# (reference module, attribute) -> (our module, attribute)
+REBIND = [
+    ("wavecapsdr.dsp.channelizer", "PolyphaseChannelizer", "wavecap_sdr_b200.dsp.channelizer", "PolyphaseChannelizer"),
+    ("wavecapsdr.dsp.channelizer", "channelize_samples", "wavecap_sdr_b200.dsp.channelizer", "channelize_samples"),
+    *[("wavecapsdr.dsp.fm", n, "wavecap_sdr_b200.dsp.fm", n) for n in
+      ("quadrature_demod", "deemphasis_filter", "lpf_audio", "resample_poly", "rms_normalize", "soft_clip", "wbfm_demod",
+       "nbfm_demod")],
+    *[("wavecapsdr.dsp.am", n, "wavecap_sdr_b200.dsp.am", n) for n in ("freq_shift", "am_demod", "ssb_demod")],
+    *[("wavecapsdr.dsp.agc", n, "wavecap_sdr_b200.dsp.agc", n) for n in ("apply_agc", "apply_simple_agc", "soft_clip")],
+    *[("wavecapsdr.dsp.filters", n, "wavecap_sdr_b200.dsp.filters", n) for n in
+      ("highpass_filter", "lowpass_filter", "bandpass_filter", "notch_filter", "fir_filter_complex", "fir_decimate")],
+    *[("wavecapsdr.capture", n, "wavecap_sdr_b200.capture", n) for n in
+      ("freq_shift", "decimate_iq_for_p25", "_process_channel_dsp_stateless")],
+    ("wavecapsdr.dsp.p25.c4fm", "C4FMDemodulator", "wavecap_sdr_b200.dsp.p25.c4fm", "C4FMDemodulator"),
+    ("wavecapsdr.decoders.p25", "CQPSKDemodulator", "wavecap_sdr_b200.decoders.p25", "CQPSKDemodulator"),
+]
+
+_saved: list[tuple[object, str, object]] = []
+
+
+def install(device: int | None = None) -> list[str]:
+    """Returns the list of rebound names; raises NativeError when the library or a B200 is missing."""
+    N.init(device)
+    done = []
+    for ref_mod, ref_attr, our_mod, our_attr in REBIND:
+        rm = importlib.import_module(ref_mod)
+        om = importlib.import_module(our_mod)
+        _saved.append((rm, ref_attr, getattr(rm, ref_attr)))
+        setattr(rm, ref_attr, getattr(om, our_attr))
+        done.append(f"{ref_mod}.{ref_attr}")
+    # FFT registry: take the "cuda" slot (dsp/fft/registry.py:167-174)
+    try:
+        reg = importlib.import_module("wavecapsdr.dsp.fft.registry")
+        from .dsp.fft.cuda_backend import CudaFFTBackend
+
+        reg.register("cuda")(CudaFFTBackend)
+        done.append("wavecapsdr.dsp.fft.registry['cuda']")
+    except Exception:  # registry shape differs: leave the reference's backends alone
+        pass
+    return done
+
+
+def uninstall() -> None:
+    while _saved:
+        mod, attr, val = _saved.pop()
+        setattr(mod, attr, val)
