@@ -475,6 +475,161 @@ __global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_b3(const u64* __r
     }
 }
 
+// ---- fused persistent version: both passes in ONE kernel, scratch is a small L2-resident ring --------
+// The two-pass design moves 8 (in) + 8 (scratch write) + 8 (scratch read) + 4/K (out) bytes per sample through
+// HBM because a slab's scratch does not survive in L2 between two launches. Here a single persistent grid pulls
+// work items from an in-order ticket counter:
+//     step s:  A items (column tile x frame) of averaging group s,  then  B items (row tile) of group s - LAG
+// so pass B of a frame runs a few dozen microseconds after its pass A, while the frame's 512 KB are still in L2,
+// and the scratch is a ring of R frames that is re-dirtied in place instead of being written back. Dependencies
+// are per-frame / per-group completion counters in global memory: a B item spins until the 16 column tiles of its
+// frames are done, an A item spins until the previous tenant of its ring slot has been consumed. Tickets are
+// handed out in dependency order and a CTA only takes a ticket when it is running, so every awaited item is
+// either finished or owned by a resident CTA: no co-residency requirement, no deadlock.
+// Ring data is read with ld.global.cg (L2 only): L1 is not coherent across SMs and ring slots are reused.
+struct SpFusedArgs {
+    const u64* iq;
+    long long frame_stride;
+    const float* window;
+    u64* ring;           // [R][65536]
+    int R;               // ring frames
+    int avg, n_frames, n_groups, lag;   // lag in groups
+    float* out;
+    int* ctrl;           // [0] ticket, [1 .. 1+n_frames) a_done per frame, then b_done per group
+};
+
+__device__ __forceinline__ void sp_spin_until(const int* ctr, int target) {
+    const volatile int* v = ctr;
+    while (*v < target) __nanosleep(64);
+    __threadfence();
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 3) spectrum_fused_kernel(const SpFusedArgs a) {
+    __shared__ SpSmemA3 sm;
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x;
+    {
+        float sn, cs;
+        sincospif(-(float)((tid >> 4) * (tid & 15)) * (1.0f / 128.0f), &sn, &cs);
+        sm.tw[tid] = make_float2(cs, sn);
+    }
+    int* a_done = a.ctrl + 1;
+    int* b_done = a.ctrl + 1 + a.n_frames;
+    const int per_step = a.avg * 16 + 16;
+    const int n_steps = a.n_groups + a.lag;
+    if (tid == 0) s_ticket = atomicAdd(a.ctrl, 1);
+    for (;;) {
+        __syncthreads();                 // s_ticket visible; previous item's shared-memory traffic finished
+        const int ticket = s_ticket;
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(a.ctrl, 1);   // next ticket is fetched while this item runs
+        const int step = ticket / per_step, slot = ticket - step * per_step;
+        if (step >= n_steps) break;
+        if (slot < a.avg * 16) {
+            // ---------------- pass A item: frame fr, column tile ct ----------------
+            const int fr = step * a.avg + (slot >> 4);
+            if (step >= a.n_groups || fr >= a.n_frames) continue;
+            const int c0 = (slot & 15) * SP_COLS;
+            if (fr >= a.R) {
+                if (tid == 0) sp_spin_until(b_done + (fr - a.R) / a.avg, 16);
+                __syncthreads();
+            }
+            const int t = tid >> 4, col = tid & 15;
+            const int n2 = c0 + col;
+            float2 base, stp;
+            {
+                float sn, cs;
+                sincospif(-(float)(n2 * t) * (1.0f / 32768.0f), &sn, &cs);
+                base = make_float2(cs, sn);
+                sincospif(-(float)(n2 * 16) * (1.0f / 32768.0f), &sn, &cs);
+                stp = make_float2(cs, sn);
+            }
+            u64* ex = sm.ex + col * SP_STRIDE;
+            const u64* x = a.iq + (long long)fr * a.frame_stride;
+            u64 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int n = (t + 16 * i) * SP_N2 + n2;
+                v[i] = mul2(__ldcs(x + n), bc2(__ldg(a.window + n)));   // input is streamed once: evict-first
+            }
+            fft16(v);
+#pragma unroll
+            for (int ka = 0; ka < 16; ++ka) {
+                u64 w = v[rev4(ka)];
+                if (ka > 0) {
+                    const float2 q = sm.tw[ka * 16 + t];
+                    w = twid(w, q.x, -q.y);
+                }
+                ex[t * 17 + ka] = w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = ex[m * 17 + t];
+            fft16(v);
+            u64* T = a.ring + (long long)(fr % a.R) * SP_N;
+            float2 w = base;
+#pragma unroll
+            for (int kb = 0; kb < 16; ++kb) {
+                const int k1 = t + 16 * kb;
+                T[k1 * SP_N2 + n2] = twid(v[rev4(kb)], w.x, -w.y);
+                w = cmul(w, stp);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();         // cumulative: orders the whole CTA's ring stores (observed via the barrier)
+                atomicAdd(a_done + fr, 1);
+            }
+        } else {
+            // ---------------- pass B item: group grp, row tile rt ----------------
+            const int grp = step - a.lag;
+            if (grp < 0 || grp >= a.n_groups) continue;
+            const int r0 = (slot - a.avg * 16) * SP_COLS;
+            const int f0 = grp * a.avg;
+            const int cnt = min(a.avg, a.n_frames - f0);
+            const int g = tid >> 4, t = tid & 15;
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            u64* ex = sm.ex + g * SP_STRIDE;
+            for (int f = 0; f < cnt; ++f) {
+                if (tid == 0) sp_spin_until(a_done + f0 + f, 16);
+                __syncthreads();
+                const u64* T = a.ring + (long long)((f0 + f) % a.R) * SP_N + (long long)(r0 + g) * SP_N2;
+                u64 v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __ldcg(T + t + 16 * i);
+                fft256_core(ex, sm.tw, t, v);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float re = lo2(v[rev4(q)]), im = hi2(v[rev4(q)]);
+                    const float mag = sqrtf(fmaf(re, re, im * im));
+                    acc[q] += 6.02059991327962f * __log2f(mag + 1e-10f);
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            float* so = reinterpret_cast<float*>(sm.ex);
+            const float inv = 1.0f / (float)cnt;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) so[(t + 16 * q) * 17 + g] = acc[q] * inv;
+            __syncthreads();
+            float* o = a.out + (long long)grp * SP_N;
+#pragma unroll 4
+            for (int j = 0; j < 16; ++j) {
+                const int id = tid + SP_THREADS * j;
+                const int k2 = id >> 4, row = id & 15;
+                const int k = (r0 + row) + SP_N1 * k2;
+                o[k ^ (SP_N / 2)] = so[k2 * 17 + row];  // fftshift
+            }
+            __syncthreads();   // ring reads of this item are complete (they were consumed into registers above)
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(b_done + grp, 1);
+            }
+        }
+    }
+}
+
 // ---- generic power-of-two path: Stockham autosort radix-2 in global memory --------------------
 __global__ void sp_window_kernel(const float2* __restrict__ iq, long long frame_stride, const float* __restrict__ window,
                                  float2* __restrict__ dst, int n) {
@@ -527,6 +682,10 @@ struct wc_spectrum {
     std::vector<float> h_window;
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    void* d_ring = nullptr;
+    size_t ring_bytes = 0;
+    void* d_ctrl = nullptr;
+    size_t ctrl_bytes = 0;
     void* d_in = nullptr;
     size_t in_bytes = 0;
     void* d_out = nullptr;
@@ -573,6 +732,7 @@ int wc_spectrum_create(int fft_size, wc_spectrum** out) {
     cudaFuncSetAttribute(spectrum_pass_b2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSmemB));
     cudaFuncSetAttribute(spectrum_pass_a2, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(spectrum_pass_a3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(spectrum_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(spectrum_pass_b3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(spectrum_pass_b2, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     *out = h;
@@ -583,6 +743,8 @@ void wc_spectrum_destroy(wc_spectrum* h) {
     if (!h) return;
     cudaFree(h->d_window);
     if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->d_ring) cudaFree(h->d_ring);
+    if (h->d_ctrl) cudaFree(h->d_ctrl);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -612,9 +774,15 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
     int slab = (int)(slab_bytes / (sizeof(float2) * (size_t)n));
     if (slab < avg) slab = avg;
     slab -= slab % avg;
+    const char* var = getenv("WC_SPECTRUM_VARIANT");
+    const int variant = var ? atoi(var) : 3;   // 3 = two register-direct passes (fastest measured), 4 = fused ring kernel
+    const bool fused = (n == SP_N && variant == 4);
+    if (fused) slab = 1 << 20;   // the fused kernel's scratch is a ring: no slab limit (ctrl is 4 bytes per frame)
     if (slab > n_frames) slab = ((n_frames + avg - 1) / avg) * avg;
-    const size_t need = sizeof(float2) * (size_t)n * slab * (n == SP_N ? 1 : 2);
-    if (sp_ensure(&h->d_scratch, &h->scratch_bytes, need)) return -2;
+    if (!fused) {
+        const size_t need = sizeof(float2) * (size_t)n * slab * (n == SP_N ? 1 : 2);
+        if (sp_ensure(&h->d_scratch, &h->scratch_bytes, need)) return -2;
+    }
     for (int f0 = 0; f0 < n_frames; f0 += slab) {
         const int cnt = (n_frames - f0 < slab) ? n_frames - f0 : slab;
         const int groups = (cnt + avg - 1) / avg;
@@ -622,9 +790,34 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
         const float2* x = iq + (long long)f0 * frame_stride;
         if (n == SP_N) {
             u64* T = reinterpret_cast<u64*>(h->d_scratch);
-            const char* var = getenv("WC_SPECTRUM_VARIANT");
-            const int variant = var ? atoi(var) : 3;
-            if (variant == 3) {
+            if (variant == 4) {
+                // fused persistent kernel: ring of R frames, pass B lags pass A by `lag` groups
+                int lagf = 32;
+                if (const char* e = getenv("WC_SPECTRUM_LAG")) lagf = atoi(e);
+                int lag = lagf / avg;
+                if (lag < 1) lag = 1;
+                int R = 2 * (lag + 1) * avg;
+                if (R < 64) R = 64;
+                if (const char* e = getenv("WC_SPECTRUM_RING")) R = atoi(e);
+                if (R < (lag + 2) * avg) R = (lag + 2) * avg;
+                if (sp_ensure(&h->d_ring, &h->ring_bytes, sizeof(float2) * (size_t)n * R)) return -2;
+                const size_t ctrl_need = sizeof(int) * (size_t)(1 + cnt + groups);
+                if (sp_ensure(&h->d_ctrl, &h->ctrl_bytes, ctrl_need)) return -2;
+                WC_CUDA(cudaMemsetAsync(h->d_ctrl, 0, ctrl_need, st));
+                SpFusedArgs fa;
+                fa.iq = reinterpret_cast<const u64*>(x);
+                fa.frame_stride = frame_stride;
+                fa.window = h->d_window;
+                fa.ring = reinterpret_cast<u64*>(h->d_ring);
+                fa.R = R;
+                fa.avg = avg;
+                fa.n_frames = cnt;
+                fa.n_groups = groups;
+                fa.lag = lag;
+                fa.out = o;
+                fa.ctrl = reinterpret_cast<int*>(h->d_ctrl);
+                spectrum_fused_kernel<<<3 * sm_count(), SP_THREADS, 0, st>>>(fa);
+            } else if (variant == 3) {
                 int fy = (6 * sm_count()) / 16;   // frames in flight: ~6 CTAs per SM over the 16 column tiles
                 if (fy > cnt) fy = cnt;
                 if (fy < 1) fy = 1;
