@@ -338,6 +338,31 @@ def main():
     value = world * samples_per_step / (ms * 1e-3) / 1e6
     checksum = float(out[:: max(1, out.shape[0] // 997)].double().abs().sum().item())
 
+    # secondary, informational: the channelizer alone (mode 0 = what PolyphaseChannelizer.process() returns,
+    # complex64 frames, 24 algorithmic bytes per input sample) on a sub-batch that fits beside the FM buffers
+    from wavecap_sdr_b200.dsp.channelizer import OUT_COMPLEX
+
+    nb0 = max(1, min(nb, 16))
+    del out
+    outc = torch.empty((nb0 * frames, 256), dtype=torch.complex64, device="cuda")
+
+    def step0():
+        N.check(lib.wc_chan_process(ch._h, C.c_void_p(x.data_ptr()), CHUNK, nb0, CHUNK, OUT_COMPLEX, 0.0,
+                                    C.c_void_p(outc.data_ptr()), stream))
+
+    for _ in range(3):
+        step0()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    c0.record()
+    for _ in range(5):
+        step0()
+    c1.record()
+    torch.cuda.synchronize()
+    ms0 = c0.elapsed_time(c1) / 5
+    chan_only_msps = nb0 * CHUNK / (ms0 * 1e-3) / 1e6
+    del outc
+
     # ---- e2e leg: host buffers through the reference-facing C-ABI call -------------------------
     eb = args.e2e_chunks
     e_steps = args.e2e_steps or min(args.steps, 5)
@@ -393,7 +418,13 @@ def main():
             "roofline": {
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "kernel": "wc::chan256_kernel<1>", "alg_bytes_per_sample": ALG_BYTES_PER_SAMPLE,
+                "kernel": "wc::chan256_kernel<1,4>", "alg_bytes_per_sample": ALG_BYTES_PER_SAMPLE,
+                "channelizer_only": {"kernel": "wc::chan256_kernel<0,4>", "alg_bytes_per_sample": 24,
+                                     "msps_per_gpu": round(chan_only_msps, 1),
+                                     "achieved": round(24 * chan_only_msps / 1e3, 1),
+                                     "frac": round(24 * chan_only_msps / 1e3 / peak, 4),
+                                     "note": "mode 0 = complex64 frames exactly as PolyphaseChannelizer.process() "
+                                             "returns them, no discriminator; informational"},
             },
             "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_value, 1), "unit": "MS/s", "ms_per_step": round(e_ms, 3),

@@ -201,6 +201,17 @@ int wc_ddc_out_len(const wc_ddc* h, int n_samples);
 int wc_ddc_process(wc_ddc* h, const void* iq_dev, int n_samples, void* out_dev, long long out_stride, void* stream);
 int wc_ddc_process_host(wc_ddc* h, const void* iq_host, int n_samples, void* out_host /* [K][out_len] */);
 
+/* ---- optional audio clean-up of the FM chains (off by default in the reference) ----
+ * dsp/filters.py:267-343 noise_blanker: y = x with every sample within +-blanking_width of a sample whose |x| exceeds
+ * median(|x|) * 10^(threshold_db/20) set to 0 (untouched when the median is < 1e-10); rows are seq_stride apart.
+ * dsp/filters.py:346-459 spectral_noise_reduction with its default geometry (fft 1024, hop 512, periodic Hann):
+ * out rows hold wc_spectral_nr_out_len(n) samples (what whole STFT frames cover; n itself when n < 1024). */
+int wc_noise_blanker(const float* x_dev, float* y_dev, int n, long long seq_stride, int n_seq, float threshold_db,
+                     int blanking_width, void* stream);
+int wc_spectral_nr_out_len(int n);
+int wc_spectral_nr(const float* x_dev, int n, long long seq_stride, int n_seq, float reduction_db, float* y_dev,
+                   long long y_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

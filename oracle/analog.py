@@ -355,3 +355,52 @@ def cs16_to_cf32(q):
     """cli.py:449-453: int16 pairs / 32768 -> complex64."""
     f = q.astype(F32) / F32(32768.0)
     return (f[..., 0] + 1j * f[..., 1]).astype(np.complex64)
+
+
+# ---- optional clean-up stages (dsp/filters.py:267-459), restated with the same numpy/scipy calls ----
+
+def noise_blanker(x, threshold_db=10.0, blanking_width=3):
+    """dsp/filters.py:267-343."""
+    from scipy.ndimage import binary_dilation
+
+    if x.size == 0:
+        return x.astype(np.float32, copy=False)
+    mag = np.abs(x)
+    med = np.median(mag)
+    if med < 1e-10:
+        return x.astype(np.float32, copy=False)
+    mask = mag > med * (10 ** (threshold_db / 20.0))
+    if not np.any(mask):
+        return x.astype(np.float32, copy=False)
+    if blanking_width > 0:
+        mask = binary_dilation(mask, structure=np.ones(2 * blanking_width + 1, dtype=bool))
+    y = x.copy()
+    y[mask] = 0
+    return y.astype(np.float32)
+
+
+def spectral_noise_reduction(x, sample_rate, reduction_db=12.0, fft_size=1024, overlap=0.5):
+    """dsp/filters.py:346-459."""
+    from scipy import signal as sg
+
+    if x.size == 0 or x.size < fft_size:
+        return x.astype(np.float32, copy=False)
+    hop = int(fft_size * (1 - overlap))
+    window = sg.windows.hann(fft_size, sym=False).astype(np.float32)
+    n_frames = (len(x) - fft_size) // hop + 1
+    padded = (n_frames - 1) * hop + fft_size
+    stft = np.zeros((n_frames, fft_size // 2 + 1), dtype=np.complex64)
+    for i in range(n_frames):
+        stft[i] = np.fft.rfft(x[i * hop:i * hop + fft_size] * window)
+    mag, phase = np.abs(stft), np.angle(stft)
+    noise = np.percentile(mag, 10, axis=0) * (10 ** (reduction_db / 20.0))
+    gain = np.maximum(np.maximum(0.0, 1.0 - (noise / np.maximum(mag, 1e-10)) ** 2), 0.1)
+    clean = mag * gain * np.exp(1j * phase)
+    out = np.zeros(padded, dtype=np.float32)
+    wsum = np.zeros(padded, dtype=np.float32)
+    for i in range(n_frames):
+        fr = np.fft.irfft(clean[i], n=fft_size).astype(np.float32)
+        out[i * hop:i * hop + fft_size] += fr * window
+        wsum[i * hop:i * hop + fft_size] += window ** 2
+    out /= np.maximum(wsum, 1e-10)
+    return out[:len(x)].astype(np.float32)

@@ -227,7 +227,33 @@ def gen_ddc():
     np.savez_compressed(os.path.join(OUT, "ddc.npz"), **out)
 
 
-GENERATORS = {"ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+def gen_audiofx():
+    """dsp.filters.noise_blanker / spectral_noise_reduction and the FM chains with those flags on."""
+    from wavecapsdr.dsp import filters as rf
+    from wavecapsdr.dsp import fm as rfm
+    from oracle import analog as oa
+
+    rng = np.random.default_rng(12)
+    x = (rng.standard_normal(20000) * 0.1 + 0.3 * np.sin(2 * np.pi * 700 / 48000 * np.arange(20000))).astype(np.float32)
+    x[[100, 101, 5000, 19999]] = [3, -4, 2.5, 5]
+    out = {"x": x}
+    out["nb"] = rf.noise_blanker(x, 10.0, 3)
+    out["nb_w0"] = rf.noise_blanker(x[:4001], 6.0, 0)
+    out["nr"] = rf.spectral_noise_reduction(x, 48000, 12.0)
+    out["nr18"] = rf.spectral_noise_reduction(x[:3000], 48000, 18.0)
+    iq = oa.synth_c1(seed=1, n=120_000)
+    out["wbfm_nb_nr"] = rfm.wbfm_demod(oa_shift(iq), 2_400_000, 48000, enable_noise_blanker=True, enable_noise_reduction=True)
+    np.savez_compressed(os.path.join(OUT, "audiofx.npz"), **out)
+
+
+def oa_shift(iq):
+    """the C1 carrier sits at +200 kHz: bring it to baseband like capture.freq_shift does"""
+    import wavecapsdr.capture as rc
+
+    return rc.freq_shift(iq, 200000.0, 2_400_000)
+
+
+GENERATORS = {"audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

@@ -175,6 +175,10 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_ddc_out_len", i32, vp, i32)
     fn("wc_ddc_process", i32, vp, vp, i32, vp, i64, vp)
     fn("wc_ddc_process_host", i32, vp, vp, i32, vp)
+    # optional audio clean-up stages
+    fn("wc_noise_blanker", i32, vp, vp, i32, i64, i32, f32, i32, vp)
+    fn("wc_spectral_nr_out_len", i32, i32)
+    fn("wc_spectral_nr", i32, vp, i32, i64, i32, f32, vp, i64, vp)
     for extra in _EXTRA_DECLS:
         extra(l, fn)
 

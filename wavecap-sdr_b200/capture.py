@@ -134,20 +134,20 @@ _DIGITAL = ("p25", "dmr", "nxdn", "dstar", "ysf")
 def _chain_signature(cfg: ChannelConfig, sample_rate: int):
     """(kind, iir stages, agc?, target, audio_rate) — channels with equal signatures share launches."""
     notch = tuple(cfg.notch_frequencies) if cfg.notch_frequencies else ()
-    if cfg.enable_noise_reduction:
-        FM.F.spectral_noise_reduction(None, sample_rate)
+    nb = None  # the reference's capture path never forwards the blanker flags to wbfm/nbfm_demod (capture.py:340-369)
+    nr = float(cfg.noise_reduction_db) if cfg.enable_noise_reduction else None
     if cfg.mode == "wbfm":
         st = FM.fm_post_chain(sample_rate, wide=True, enable_deemphasis=cfg.enable_deemphasis,
                               deemphasis_tau=cfg.deemphasis_tau_us * 1e-6, enable_mpx_filter=cfg.enable_mpx_filter,
                               mpx_cutoff_hz=cfg.mpx_cutoff_hz, enable_highpass=cfg.enable_fm_highpass,
                               highpass_hz=cfg.fm_highpass_hz, notch_frequencies=notch)
-        return ("fm", tuple(st), False, 0.0, int(cfg.audio_rate))
+        return ("fm", tuple(st), False, 0.0, int(cfg.audio_rate), nb, nr)
     if cfg.mode == "nbfm":
         st = FM.fm_post_chain(sample_rate, wide=False, enable_deemphasis=cfg.enable_deemphasis,
                               deemphasis_tau=cfg.deemphasis_tau_us * 1e-6, enable_highpass=cfg.enable_fm_highpass,
                               highpass_hz=cfg.fm_highpass_hz, enable_lowpass=cfg.enable_fm_lowpass,
                               lowpass_hz=cfg.fm_lowpass_hz, notch_frequencies=notch)
-        return ("fm", tuple(st), False, 0.0, int(cfg.audio_rate))
+        return ("fm", tuple(st), False, 0.0, int(cfg.audio_rate), nb, nr)
     if cfg.mode == "am":
         st = AM.am_post_chain(sample_rate, cfg.enable_am_highpass, cfg.am_highpass_hz, cfg.enable_am_lowpass,
                               cfg.am_lowpass_hz, notch)
@@ -209,7 +209,7 @@ def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig],
         if sig[0] in ("fm", "am"):
             rows = out[c:e].reshape((e - c) * n_chunks, n)
             if sig[0] == "fm":
-                a, p, inv = FM.fm_tail(rows, int(sample_rate), sig[4], sig[1], want_stats=True)
+                a, p, inv = FM.fm_tail(rows, int(sample_rate), sig[4], sig[1], want_stats=True, blanker_db=sig[5], nr_db=sig[6])
             else:
                 a, p, inv = AM.am_tail(rows, int(sample_rate), sig[4], sig[1], sig[2], sig[3], want_stats=True)
             a = a.reshape(e - c, n_chunks, -1)

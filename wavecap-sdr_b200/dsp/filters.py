@@ -4,8 +4,8 @@ IIR section (:41-264): Butterworth order-5 high/low/band-pass and iirnotch, exec
 block-scan `lfilter` in csrc/analog.cu. Coefficients are designed on the host with scipy exactly as the
 reference does (:59-61, :82) and cached. Invalid cut-offs return the input unchanged as float32.
 Streaming FIR section (:471-668): `fir_filter_complex`, `fir_decimate` — csrc/firdec.cu.
-`noise_blanker` / `spectral_noise_reduction` (:267-459, optional flags, off by default) are not built
-in this round and raise NotImplementedError (no silent CPU fallback).
+`noise_blanker` (:267-343) and `spectral_noise_reduction` (:346-459) — csrc/audiofx.cu (real float32 input; the
+default fft_size=1024 / overlap=0.5 of the reference are the only STFT geometry built).
 """
 from __future__ import annotations
 
@@ -13,6 +13,7 @@ from functools import lru_cache
 
 import numpy as np
 
+from .. import _native as N
 from . import _stages as S
 
 NUMBA_AVAILABLE = False  # the reference's flag; nothing here uses numba
@@ -105,13 +106,48 @@ def notch_filter(x, sample_rate: int, freq: float, q: float = 30.0):
     return _run_iir(x, notch_coeffs(sample_rate, freq, q))
 
 
+def noise_blanker_rows(rows, threshold_db: float = 10.0, blanking_width: int = 3):
+    """rows: CUDA float32 [n_seq, n] -> blanked rows (one median + one masked copy per sequence)."""
+    import torch
+
+    rows = rows.contiguous()
+    out = torch.empty_like(rows)
+    N.check(N.lib().wc_noise_blanker(S.ptr(rows), S.ptr(out), int(rows.shape[1]), int(rows.shape[1]), int(rows.shape[0]),
+                                     float(threshold_db), int(blanking_width), S.stream()))
+    return out
+
+
 def noise_blanker(x, threshold_db: float = 10.0, blanking_width: int = 3):
-    raise NotImplementedError("noise_blanker (dsp/filters.py:267-343) has no GPU kernel yet; there is no CPU fallback")
+    """dsp/filters.py:267-343: zero every sample within `blanking_width` of a sample whose magnitude exceeds the
+    median magnitude by `threshold_db`."""
+    if _size(x) == 0:
+        return _f32_passthrough(x)
+    if (hasattr(x, "is_complex") and x.is_complex()) or (isinstance(x, np.ndarray) and np.iscomplexobj(x)):
+        raise NotImplementedError("noise_blanker: only the real (post-discriminator) path of the FM chains is built")
+    y = noise_blanker_rows(_as_rows(x), threshold_db, blanking_width).reshape(_shape(x))
+    return S.like_input(y, x)
 
 
-def spectral_noise_reduction(x, sample_rate: int, reduction_db: float = 12.0, **kw):
-    raise NotImplementedError(
-        "spectral_noise_reduction (dsp/filters.py:346-459) has no GPU kernel yet; there is no CPU fallback")
+def spectral_nr_rows(rows, reduction_db: float = 12.0):
+    """rows: CUDA float32 [n_seq, n] -> [n_seq, out_len] (out_len = samples covered by whole STFT frames)."""
+    import torch
+
+    rows = rows.contiguous()
+    n = int(rows.shape[1])
+    m = int(N.lib().wc_spectral_nr_out_len(n))
+    out = torch.empty((rows.shape[0], m), dtype=torch.float32, device=rows.device)
+    N.check(N.lib().wc_spectral_nr(S.ptr(rows), n, n, int(rows.shape[0]), float(reduction_db), S.ptr(out), m, S.stream()))
+    return out
+
+
+def spectral_noise_reduction(x, sample_rate: int, reduction_db: float = 12.0, fft_size: int = 1024, overlap: float = 0.5):
+    """dsp/filters.py:346-459 (Wiener-style spectral gain against the per-bin 10th-percentile noise floor)."""
+    if fft_size != 1024 or overlap != 0.5:
+        raise NotImplementedError("spectral_noise_reduction: only fft_size=1024, overlap=0.5 (the reference defaults) are built")
+    if _size(x) == 0 or _size(x) < fft_size:
+        return _f32_passthrough(x)
+    y = spectral_nr_rows(_as_rows(x), reduction_db)
+    return S.like_input(y.reshape(-1) if len(_shape(x)) == 1 else y, x)
 
 
 def __getattr__(name):

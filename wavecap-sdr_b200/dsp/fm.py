@@ -115,11 +115,16 @@ def fm_post_chain(sample_rate: int, *, wide: bool, enable_deemphasis: bool, deem
     return [s for s in stages if s is not None]
 
 
-def fm_tail(fm_rows, sample_rate: int, audio_rate: int, stages, want_stats: bool = False):
-    """IIR stages -> RMS -> resample with fused scale + soft clip. fm_rows: CUDA [n_seq, n] float32."""
+def fm_tail(fm_rows, sample_rate: int, audio_rate: int, stages, want_stats: bool = False, blanker_db=None, nr_db=None):
+    """[noise blanker] -> IIR stages -> [spectral noise reduction] -> RMS -> resample with fused scale + soft clip
+    (dsp/fm.py:277-314, :368-406). fm_rows: CUDA [n_seq, n] float32."""
     y = fm_rows
+    if blanker_db is not None:
+        y = F.noise_blanker_rows(y, blanker_db, 3)
     for b, a in stages:
         y = S.lfilter(b, a, y)
+    if nr_db is not None:
+        y = F.spectral_nr_rows(y, nr_db)
     ss = S.sumsq(y)
     if sample_rate == audio_rate:
         # resample_linear returns its input; scale and clip elementwise
@@ -135,16 +140,12 @@ def fm_tail(fm_rows, sample_rate: int, audio_rate: int, stages, want_stats: bool
     return S.resample(y, up, down, S.EPI_RMS_CLIP, ss, 0.18, 1e-4, want_stats=want_stats)
 
 
-def _fm_demod(iq, sample_rate, audio_rate, stages, enable_noise_blanker, enable_noise_reduction):
-    if enable_noise_blanker:
-        F.noise_blanker(None)
-    if enable_noise_reduction:
-        F.spectral_noise_reduction(None, sample_rate)
+def _fm_demod(iq, sample_rate, audio_rate, stages, blanker_db, nr_db):
     if _n(iq) == 0:
         return np.empty(0, dtype=np.float32)
     x = S.to_device(iq, np.complex64).reshape(-1)
     fm, _, _, _ = S.front(x, S.FMT_CF32, x.numel(), 1, [S.MODE_NBFM], [0.0], None, int(sample_rate))
-    audio = fm_tail(fm.reshape(1, -1), int(sample_rate), int(audio_rate), stages)
+    audio = fm_tail(fm.reshape(1, -1), int(sample_rate), int(audio_rate), stages, blanker_db=blanker_db, nr_db=nr_db)
     return S.like_input(audio.reshape(-1), iq)
 
 
@@ -158,7 +159,8 @@ def wbfm_demod(iq, sample_rate: int, audio_rate: int = 48_000, enable_deemphasis
                            deemphasis_tau=deemphasis_tau, enable_mpx_filter=enable_mpx_filter,
                            mpx_cutoff_hz=mpx_cutoff_hz, enable_highpass=enable_highpass, highpass_hz=highpass_hz,
                            notch_frequencies=notch_frequencies)
-    return _fm_demod(iq, sample_rate, audio_rate, stages, enable_noise_blanker, enable_noise_reduction)
+    return _fm_demod(iq, sample_rate, audio_rate, stages, noise_blanker_threshold_db if enable_noise_blanker else None,
+                     noise_reduction_db if enable_noise_reduction else None)
 
 
 def nbfm_demod(iq, sample_rate: int, audio_rate: int = 48_000, enable_deemphasis: bool = False,
@@ -171,4 +173,5 @@ def nbfm_demod(iq, sample_rate: int, audio_rate: int = 48_000, enable_deemphasis
                            deemphasis_tau=deemphasis_tau, enable_highpass=enable_highpass, highpass_hz=highpass_hz,
                            enable_lowpass=enable_lowpass, lowpass_hz=lowpass_hz,
                            notch_frequencies=notch_frequencies)
-    return _fm_demod(iq, sample_rate, audio_rate, stages, enable_noise_blanker, enable_noise_reduction)
+    return _fm_demod(iq, sample_rate, audio_rate, stages, noise_blanker_threshold_db if enable_noise_blanker else None,
+                     noise_reduction_db if enable_noise_reduction else None)
