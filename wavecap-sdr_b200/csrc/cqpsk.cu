@@ -174,7 +174,10 @@ struct CqSyncArgs {
 struct CqView {
     const float2* tail;   // 32 carried samples
     const float2* x;      // this call's filtered samples
+    const float* mmse;    // shared-memory copy of the 129 x 8 table, rows padded to 9 floats: every thread (channel)
+                          // indexes its own row, which would serialise on the constant cache
 };
+constexpr int CQ_ROW = 9;
 
 // sample `back` positions before sample index m of this call (m - back may reach into the tail)
 __device__ __forceinline__ float2 cq_hist(const CqView& v, int m, int back) {
@@ -191,7 +194,7 @@ __device__ __forceinline__ float2 cq_interp(const CqView& v, int m, int back, in
         const int off = back + (tap - 3);
         if (off >= 0 && off < CQ_HIST) {
             const float2 h = cq_hist(v, m, off);
-            const float t = c_mmse[imu][tap];
+            const float t = v.mmse[imu * CQ_ROW + tap];
             const float pr = __fmul_rn(t, h.x), pi = __fmul_rn(t, h.y);
             if (!any) {
                 rr = pr;
@@ -211,10 +214,14 @@ __device__ __forceinline__ float cq_abs(float2 z) {
 }
 
 __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
+    __shared__ float s_mmse[129 * CQ_ROW];
+    for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) s_mmse[(i >> 3) * CQ_ROW + (i & 7)] = c_mmse[i >> 3][i & 7];
+    __syncthreads();
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= a.C) return;
     CqState S = a.st[ch];
     CqView v;
+    v.mmse = s_mmse;
     v.tail = a.st[ch].tail;
     v.x = a.filt + (long long)ch * a.n;
     unsigned char* out = a.dibits + (long long)ch * a.max_sym;
@@ -223,16 +230,24 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
     const double PI_D = 3.141592653589793;
     const float omega_lo = (float)(a.k.sps * 0.95), omega_hi = (float)(a.k.sps * 1.05);
     int nsym = 0;
-    for (int m = 0; m < a.n; ++m) {
-        bool fire;
-        if (S.clock_is_f32) {
-            S.clock_f = __fadd_rn(S.clock_f, S.sym_time_f);
-            fire = S.clock_f >= 1.0f;
-        } else {
-            S.clock_d += a.k.sym_time0;
-            fire = S.clock_d >= 1.0;
+    // Symbol-driven loop: every lane (channel) first advances its own sample clock to its next firing sample (a
+    // 9-11 iteration inner loop), then all lanes of the warp run the expensive symbol body together. A plain
+    // per-sample loop would execute the body at almost every sample index because the channels' clocks are not aligned.
+    int m = -1;
+    for (;;) {
+        bool fire = false;
+        while (m + 1 < a.n) {
+            ++m;
+            if (S.clock_is_f32) {
+                S.clock_f = __fadd_rn(S.clock_f, S.sym_time_f);
+                fire = S.clock_f >= 1.0f;
+            } else {
+                S.clock_d += a.k.sym_time0;
+                fire = S.clock_d >= 1.0;
+            }
+            if (fire) break;
         }
-        if (!fire) continue;
+        if (!fire) break;
         int imu;
         if (S.clock_is_f32) {
             S.clock_f = __fsub_rn(S.clock_f, 1.0f);

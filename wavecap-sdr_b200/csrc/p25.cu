@@ -222,9 +222,13 @@ struct SyncArgs {
 
 struct SyncCtx {
     const float* ring;
+    const float* taps;    // shared-memory copy of the 129 x 8 interpolator table, rows padded to 9 floats (the lanes of
+                          // a score evaluation index 24 different rows: that would serialise on the constant cache)
     int ptr, shift_mod;
     double sps, pll, gain;
+    float my_sync;        // c_sync[lane]
 };
+constexpr int C4_ROW = 9;
 
 __device__ __forceinline__ float c4_buf(const SyncCtx& c, int v) {
     if (v < 0 || v > c.ptr) return 0.0f;
@@ -254,7 +258,7 @@ __device__ __forceinline__ bool c4_sync_sample(const SyncCtx& c, double offset, 
     row = min(max(row, 0), 128);
     double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc += (double)__fmul_rn(c4_buf(c, io + j), c_interp[row][j]);
+    for (int j = 0; j < 8; ++j) acc += (double)__fmul_rn(c4_buf(c, io + j), c.taps[row * C4_ROW + j]);
     soft = (acc + c.pll) * c.gain;
     return true;
 }
@@ -264,7 +268,7 @@ __device__ double c4_score(const SyncCtx& c, double offset, int lane, double* st
     double soft = 0.0;
     const bool ok = c4_sync_sample(c, offset, lane, soft);
     const unsigned vm = __ballot_sync(0xffffffffu, ok);
-    if (lane < 24) sterm[lane] = ok ? soft * (double)c_sync[lane] : 0.0;
+    if (lane < 24) sterm[lane] = ok ? soft * (double)c.my_sync : 0.0;
     __syncwarp();
     double score = 0.0;
     if (lane == 0) {
@@ -315,6 +319,9 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
     __shared__ float lagbuf[24 + 32];
     __shared__ int pos_n[32];
     __shared__ double pos_mu[32];
+    __shared__ float s_taps[129 * C4_ROW];
+    for (int i = threadIdx.x; i < 129 * 8; i += 32) s_taps[(i >> 3) * C4_ROW + (i & 7)] = c_interp[i >> 3][i & 7];
+    __syncwarp();
     const int ch = blockIdx.x;
     const int lane = threadIdx.x;
     C4State& S = a.st[ch];
@@ -400,6 +407,8 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
     c.sps = sps;
     c.pll = pll0;
     c.gain = gain0;
+    c.taps = s_taps;
+    c.my_sync = (lane < 24) ? c_sync[lane] : 0.f;
     int fine = S.fine, since = S.since_sync, eq_init = S.eq_init, sync_count = S.sync_count, n_events = 0;
     double sample_point = S.sample_point;
 
