@@ -152,6 +152,11 @@ class C4FMDemodulator:
     def get_timing_offset(self) -> float:
         return float(self._bank.state(0)["pll"])
 
+    def demodulate_discriminator(self, disc_audio):
+        """c4fm.py:2817-2992 — the discriminator-audio entry used only by the native IMBE voice decoder
+        (decoders/imbe_native.py:289), i.e. the voice path SURVEY §8f lists as "next". Not built: no CPU fallback."""
+        raise NotImplementedError("C4FMDemodulator.demodulate_discriminator (voice path, SURVEY §8f) is not built on the GPU")
+
     @property
     def _sync_count(self) -> int:
         return self._bank.state(0)["sync_count"]
@@ -159,6 +164,12 @@ class C4FMDemodulator:
     @property
     def _fine_sync(self) -> bool:
         return self._bank.state(0)["fine_sync"]
+
+
+def c4fm_demod_simple(iq, sample_rate: int = 19200, symbol_rate: int = 4800):
+    """Stateless single-shot form (c4fm.py:2995-3015): dibits of one fresh demodulator."""
+    dibits, _ = C4FMDemodulator(sample_rate=sample_rate, symbol_rate=symbol_rate).demodulate(iq)
+    return dibits
 
 
 # ---- helper classes timed by backend/benchmark_dsp.py:17-114 (same names and call shapes) -----------------------

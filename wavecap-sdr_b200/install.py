@@ -24,7 +24,8 @@ REBIND = [
       ("highpass_filter", "lowpass_filter", "bandpass_filter", "notch_filter", "fir_filter_complex", "fir_decimate")],
     *[("wavecapsdr.capture", n, "wavecap_sdr_b200.capture", n) for n in
       ("freq_shift", "decimate_iq_for_p25", "_process_channel_dsp_stateless")],
-    ("wavecapsdr.dsp.p25.c4fm", "C4FMDemodulator", "wavecap_sdr_b200.dsp.p25.c4fm", "C4FMDemodulator"),
+    *[("wavecapsdr.dsp.p25.c4fm", n, "wavecap_sdr_b200.dsp.p25.c4fm", n) for n in
+      ("C4FMDemodulator", "c4fm_demod_simple", "_FMDemodulator", "_Interpolator", "_SoftSyncDetector")],
     ("wavecapsdr.decoders.p25", "CQPSKDemodulator", "wavecap_sdr_b200.decoders.p25", "CQPSKDemodulator"),
 ]
 
