@@ -212,6 +212,12 @@ int wc_spectral_nr_out_len(int n);
 int wc_spectral_nr(const float* x_dev, int n, long long seq_stride, int n_seq, float reduction_db, float* y_dev,
                    long long y_stride, void* stream);
 
+/* ---- output stage: capture.pack_iq16 / pack_pcm16 / pack_f32 (capture.py:102-144) and
+ * Channel._update_audio_metrics (capture.py:633-661: sum of squares, peak |x|, count of |x| > 0.95 per sequence) ---- */
+int wc_pack(const float* x_dev, void* y_dev, long long total_floats, int fmt /* 0 int16, 1 clipped float32 */, void* stream);
+int wc_audio_levels(const float* x_dev, int n, long long seq_stride, int n_seq, double* sumsq_dev, float* peak_dev,
+                    int* clip_count_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,6 +179,8 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_noise_blanker", i32, vp, vp, i32, i64, i32, f32, i32, vp)
     fn("wc_spectral_nr_out_len", i32, i32)
     fn("wc_spectral_nr", i32, vp, i32, i64, i32, f32, vp, i64, vp)
+    fn("wc_pack", i32, vp, vp, i64, i32, vp)
+    fn("wc_audio_levels", i32, vp, i32, i64, i32, vp, vp, vp, vp)
     for extra in _EXTRA_DECLS:
         extra(l, fn)
 

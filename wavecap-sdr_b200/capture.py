@@ -269,3 +269,60 @@ def _validate_audio_output(audio, context: str = "") -> bool:
     if a.size == 0:
         return True
     return bool(np.isfinite(a).all() and float(np.max(np.abs(a))) <= AUDIO_MAX_ABS)
+
+
+# ---- output stage: wire packers and audio level metering (capture.py:102-144, 633-661) ----------------------------
+
+def _pack(samples, fmt: int, np_dtype):
+    import torch
+
+    if _n(samples) == 0:
+        return b""
+    if N.is_torch_cuda(samples):
+        x = samples.contiguous()
+        x = torch.view_as_real(x.to(torch.complex64)).reshape(-1) if x.is_complex() else x.to(torch.float32).reshape(-1)
+    else:
+        a = np.asarray(samples)
+        a = a.astype(np.complex64, copy=False).view(np.float32) if np.iscomplexobj(a) else np.ascontiguousarray(a, dtype=np.float32)
+        x = torch.from_numpy(np.ascontiguousarray(a).reshape(-1)).cuda()
+    N.ensure_init()
+    out = torch.empty((x.numel(),), dtype=torch.int16 if fmt == 0 else torch.float32, device=x.device)
+    N.check(N.lib().wc_pack(S.ptr(x), S.ptr(out), int(x.numel()), fmt, S.stream()))
+    return out.cpu().numpy().astype(np_dtype, copy=False).tobytes()
+
+
+def pack_iq16(samples) -> bytes:
+    """Interleaved int16 I,Q: clip to [-1, 1], x 32767, truncate (capture.py:102-115). Unlike the reference, the
+    caller's array is not clipped in place."""
+    return _pack(samples, 0, np.int16)
+
+
+def pack_pcm16(samples) -> bytes:
+    """16-bit PCM (capture.py:118-130)."""
+    return _pack(samples, 0, np.int16)
+
+
+def pack_f32(samples) -> bytes:
+    """Clipped float32 (capture.py:133-144)."""
+    return _pack(samples, 1, np.float32)
+
+
+def audio_levels(audio_rows):
+    """Channel._update_audio_metrics (capture.py:633-661) for a batch: audio_rows CUDA/numpy float32 [n_seq, n] ->
+    (rms_db [n_seq], peak_db [n_seq], clipping_count [n_seq]) with the reference's -100 dB floor."""
+    import torch
+
+    N.ensure_init()
+    x = S.to_device(audio_rows, np.float32)
+    x = x.reshape(1, -1) if x.dim() == 1 else x.contiguous()
+    n_seq, n = int(x.shape[0]), int(x.shape[1])
+    ss = torch.empty((n_seq,), dtype=torch.float64, device=x.device)
+    pk = torch.empty((n_seq,), dtype=torch.float32, device=x.device)
+    cc = torch.empty((n_seq,), dtype=torch.int32, device=x.device)
+    N.check(N.lib().wc_audio_levels(S.ptr(x), n, n, n_seq, S.ptr(ss), S.ptr(pk), S.ptr(cc), S.stream()))
+    rms = np.sqrt((ss.cpu().numpy() / n).astype(np.float32)).astype(np.float64)
+    peak = pk.cpu().numpy().astype(np.float64)
+    with np.errstate(divide="ignore"):
+        rms_db = np.where(rms > 1e-10, 20.0 * np.log10(np.maximum(rms, 1e-300)), -100.0)
+        peak_db = np.where(peak > 1e-10, 20.0 * np.log10(np.maximum(peak, 1e-300)), -100.0)
+    return rms_db, peak_db, cc.cpu().numpy()

@@ -274,3 +274,97 @@ int wc_spectral_nr(const float* x_dev, int n, long long seq_stride, int n_seq, f
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// wire packers + audio level metering: the output stage of the analog chain
+//   capture.pack_iq16 / pack_pcm16 / pack_f32 (capture.py:102-144): clip to [-1, 1], scale by 32767, truncate to
+//   int16 (numpy astype truncates toward zero); Channel._update_audio_metrics (capture.py:633-661): RMS, peak and
+//   the count of |x| > 0.95 per sequence — fused so that audio leaves the GPU already as PCM16 with its levels.
+// ---------------------------------------------------------------------------------------------
+namespace wc {
+
+__global__ void pack16_kernel(const float* __restrict__ x, short* __restrict__ y, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float v = fminf(fmaxf(x[i], -1.0f), 1.0f);
+    y[i] = (short)(int)__fmul_rn(v, 32767.0f);   // float -> int conversion truncates toward zero like astype(int16)
+}
+
+__global__ void clip_f32_kernel(const float* __restrict__ x, float* __restrict__ y, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    y[i] = fminf(fmaxf(x[i], -1.0f), 1.0f);
+}
+
+// per sequence: sum x^2 (float64), max |x|, count(|x| > 0.95)
+__global__ void __launch_bounds__(256) audio_levels_kernel(const float* __restrict__ x, int n, long long stride,
+                                                           double* __restrict__ sumsq, float* __restrict__ peak,
+                                                           int* __restrict__ clip_count) {
+    __shared__ double rs[8];
+    __shared__ float rp[8];
+    __shared__ int rc[8];
+    const float* xs = x + (long long)blockIdx.x * stride;
+    double s = 0.0;
+    float p = 0.f;
+    int c = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = xs[i], a = fabsf(v);
+        s += (double)v * (double)v;
+        p = fmaxf(p, a);
+        c += a > 0.95f;
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        p = fmaxf(p, __shfl_xor_sync(0xffffffffu, p, o));
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        rs[threadIdx.x >> 5] = s;
+        rp[threadIdx.x >> 5] = p;
+        rc[threadIdx.x >> 5] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0;
+        float tp = 0.f;
+        int tc = 0;
+        for (int w = 0; w < 8; ++w) {
+            ts += rs[w];
+            tp = fmaxf(tp, rp[w]);
+            tc += rc[w];
+        }
+        sumsq[blockIdx.x] = ts;
+        peak[blockIdx.x] = tp;
+        clip_count[blockIdx.x] = tc;
+    }
+}
+
+}  // namespace wc
+
+extern "C" {
+
+/* fmt 0: int16 PCM / interleaved IQ16 (pack_pcm16, pack_iq16 — complex64 input is just 2*total floats);
+ * fmt 1: clipped float32 (pack_f32) */
+int wc_pack(const float* x_dev, void* y_dev, long long total_floats, int fmt, void* stream_v) {
+    WC_REQUIRE(x_dev && y_dev, "wc_pack: null argument");
+    WC_REQUIRE(fmt == 0 || fmt == 1, "wc_pack: fmt must be 0 (int16) or 1 (float32)");
+    if (total_floats <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    const unsigned blocks = (unsigned)((total_floats + 255) / 256);
+    if (fmt == 0) wc::pack16_kernel<<<blocks, 256, 0, s>>>(x_dev, reinterpret_cast<short*>(y_dev), total_floats);
+    else wc::clip_f32_kernel<<<blocks, 256, 0, s>>>(x_dev, reinterpret_cast<float*>(y_dev), total_floats);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wc_audio_levels(const float* x_dev, int n, long long seq_stride, int n_seq, double* sumsq_dev, float* peak_dev,
+                    int* clip_count_dev, void* stream_v) {
+    WC_REQUIRE(x_dev && sumsq_dev && peak_dev && clip_count_dev, "wc_audio_levels: null argument");
+    WC_REQUIRE(n >= 1 && n_seq >= 1, "wc_audio_levels: bad sizes");
+    wc::audio_levels_kernel<<<n_seq, 256, 0, (cudaStream_t)stream_v>>>(x_dev, n, seq_stride, sumsq_dev, peak_dev, clip_count_dev);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -375,14 +375,16 @@ __global__ void __launch_bounds__(SP_THREADS, 3) spectrum_pass_a3(const float2* 
     }
     u64* ex = sm.ex + col * SP_STRIDE;
     const u64* xw = reinterpret_cast<const u64*>(iq);
+    float wv[16];   // this thread's 16 Hann coefficients: the column tile is fixed, so they are loaded once per CTA
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wv[i] = __ldg(window + (t + 16 * i) * SP_N2 + n2);
     for (int f = blockIdx.y; f < n_frames; f += gridDim.y) {
         const u64* x = xw + (long long)f * frame_stride;
         u64 v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int n = (t + 16 * i) * SP_N2 + n2;
-            v[i] = mul2(__ldg(x + n), bc2(__ldg(window + n)));
-        }
+        for (int i = 0; i < 16; ++i) v[i] = __ldcs(x + (t + 16 * i) * SP_N2 + n2);   // streamed once: evict-first
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = mul2(v[i], bc2(wv[i]));
         fft16(v);
         __syncthreads();   // previous frame's exchange reads are done
 #pragma unroll
