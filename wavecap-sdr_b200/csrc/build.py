@@ -21,7 +21,7 @@ OBJ = CSRC / "build"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3", "--expt-relaxed-constexpr",
-         "-Xptxas", "-v"]
+         "-Xptxas", "-v"] + (["-DWC_DEV_ABLATE"] if os.environ.get("WC_DEV_ABLATE") else [])
 # per-file extras: the P25 kernels replay the reference's float32/float64 operation order, so the
 # compiler must not contract a*b+c into one fused multiply-add there (explicit fma() calls stay fused)
 EXTRA = {"p25.cu": ["-fmad=false"], "cqpsk.cu": ["-fmad=false"]}

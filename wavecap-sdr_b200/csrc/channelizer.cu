@@ -65,7 +65,8 @@ __device__ __forceinline__ float2 blk_fetch(const ChanArgs& a, const float2* xc,
     return a.carried[(i + CH_T) * CH_M + k];
 }
 
-template <int MODE, int MINB>
+// ABL (dev builds only, -DWC_DEV_ABLATE): timing ablations that skip one phase; results are then wrong by design.
+template <int MODE, int MINB, int ABL = 0>
 __global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArgs a) {
     __shared__ ChanSmem sm;
     const int tid = threadIdx.x;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArg
 
     // phases 2 + 3 for the sub-tile whose FIR outputs sit in sm.u (frames fs .. fs+nv-1)
     auto fft_and_emit = [&](int fs, int nv) {
-        {
+        if (ABL != 2) {
             const int g = tid >> 4, t = tid & 15;
             u64* reg = sm.u + g * CH_REGION;
             u64 v[16];
@@ -180,8 +181,10 @@ __global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArg
                 // p = y * conj(prev)
                 const u64 px = fma2(yre, pre, mul2(yim, pim));
                 const u64 py = sub2(mul2(yim, pre), mul2(yre, pim));
-                const u64 d = scaled_atan2f_x2(py, px, at);
-                if (fs + i >= f0) *reinterpret_cast<u64*>(o + (long long)i * CH_M) = d;
+                const u64 d = (ABL == 3) ? add2(py, px) : scaled_atan2f_x2(py, px, at);
+                if (ABL == 4) {
+                    if (lo2(d) == 123.456f) *reinterpret_cast<u64*>(o + (long long)i * CH_M) = d;
+                } else if (fs + i >= f0) *reinterpret_cast<u64*>(o + (long long)i * CH_M) = d;
                 pre = yre;
                 pim = yim;
             };
@@ -234,10 +237,12 @@ __global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArg
         for (int i = 0; i < CH_S; ++i) {
             w[9] = st[i * CH_H + r];
             u64 lo = mul2(w[8], bc2(hlo[0])), hi = mul2(w[9], bc2(hhi[0]));
+            if (ABL != 1) {
 #pragma unroll
-            for (int j = 1; j < CH_T; ++j) {
-                lo = fma2(w[8 - j], bc2(hlo[j]), lo);
-                hi = fma2(w[9 - j], bc2(hhi[j]), hi);
+                for (int j = 1; j < CH_T; ++j) {
+                    lo = fma2(w[8 - j], bc2(hlo[j]), lo);
+                    hi = fma2(w[9 - j], bc2(hhi[j]), hi);
+                }
             }
             sm.u[i * CH_REGION + r] = lo;
             sm.u[i * CH_REGION + r + CH_H] = hi;
@@ -247,6 +252,302 @@ __global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArg
         __syncthreads();
         if (tid == 0 && n + 2 < n_fast) issue(n + 2);
         fft_and_emit(fs, nv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Software-pipelined variant ("P"): the FIR of sub-tile n+1 is issued inside the FFT of sub-tile n.
+//
+// Why: in chan256_kernel the FIR phase is a burst of FFMA2 (FMA-pipe bound, issue slots idle) and the FFT
+// phase is bound by shared-memory latency (short-scoreboard stalls, FMA pipe idle) — ncu attributes 30 % /
+// 46 % of the warp samples to them (profiles/r02_chan_fm_phases.md). Both live in the same 128 threads, so
+// placing them in ONE instruction stream lets every warp fill its LDS/exchange latency with independent
+// FFMA2 work instead of relying on the 4 resident CTAs being in different phases. The FIR output buffer is
+// double-buffered (u[2]); one CTA-wide barrier per sub-tile disappears.
+//
+//   pre-loop : FIR(0) -> u[0]
+//   iter n   : wait stage[n+1] | FFT(n) in u[n&1]  ++  FIR(n+1) -> u[(n+1)&1] | barrier | TMA issue(n+3)
+//              | discriminator(n) from u[n&1] | barrier
+// ---------------------------------------------------------------------------------------------
+struct __align__(128) ChanSmemP {
+    u64 stage[2][CH_S * CH_H];       // TMA landing buffers: 8 rows of 128 cf32 samples each
+    u64 u[2][CH_S * CH_REGION];      // FIR output -> FFT exchange -> planar FFT output (in place), double buffered
+    float2 tw[16 * 16];
+    uint64_t full[2];
+    uint64_t drained;                // split barrier: all discriminator reads of a sub-tile's u[] are done
+};
+
+// per-thread FIR state: sliding window of residue class r (9 history rows + up to 2 new rows), taps of u[r] and u[r+128]
+struct FirState {
+    u64 w[11];
+    float hlo[CH_T], hhi[CH_T];
+};
+
+// FIR rows [I0, I1) of one sub-tile: new row from the staged tile, two packed accumulations, window shift
+template <int I0, int I1>
+__device__ __forceinline__ void fir_rows(FirState& f, const u64* __restrict__ st, u64* __restrict__ ub, int r) {
+#pragma unroll
+    for (int i = I0; i < I1; ++i) {
+        f.w[9] = st[i * CH_H + r];
+        u64 lo = mul2(f.w[8], bc2(f.hlo[0])), hi = mul2(f.w[9], bc2(f.hhi[0]));
+#pragma unroll
+        for (int j = 1; j < CH_T; ++j) {
+            lo = fma2(f.w[8 - j], bc2(f.hlo[j]), lo);
+            hi = fma2(f.w[9 - j], bc2(f.hhi[j]), hi);
+        }
+        ub[i * CH_REGION + r] = lo;
+        ub[i * CH_REGION + r + CH_H] = hi;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) f.w[m] = f.w[m + 1];
+    }
+}
+
+// The same two rows split into load / math / store so that the caller can keep every shared-memory load of a
+// segment ahead of every shared-memory store (ptxas cannot prove that the stage, exchange and twiddle regions do
+// not alias, so it never moves an LDS above an earlier STS).
+template <int I>
+__device__ __forceinline__ void fir2_load(FirState& f, const u64* __restrict__ st, int r) {
+    f.w[9] = st[I * CH_H + r];
+    f.w[10] = st[(I + 1) * CH_H + r];
+}
+__device__ __forceinline__ void fir2_math(FirState& f, u64 (&o)[4]) {
+    o[0] = mul2(f.w[8], bc2(f.hlo[0]));
+    o[1] = mul2(f.w[9], bc2(f.hhi[0]));
+    o[2] = mul2(f.w[9], bc2(f.hlo[0]));
+    o[3] = mul2(f.w[10], bc2(f.hhi[0]));
+#pragma unroll
+    for (int j = 1; j < CH_T; ++j) {
+        o[0] = fma2(f.w[8 - j], bc2(f.hlo[j]), o[0]);
+        o[1] = fma2(f.w[9 - j], bc2(f.hhi[j]), o[1]);
+        o[2] = fma2(f.w[9 - j], bc2(f.hlo[j]), o[2]);
+        o[3] = fma2(f.w[10 - j], bc2(f.hhi[j]), o[3]);
+    }
+#pragma unroll
+    for (int m = 0; m < 9; ++m) f.w[m] = f.w[m + 2];
+}
+template <int I>
+__device__ __forceinline__ void fir2_store(const u64 (&o)[4], u64* __restrict__ ub, int r) {
+    ub[I * CH_REGION + r] = o[0];
+    ub[I * CH_REGION + r + CH_H] = o[1];
+    ub[(I + 1) * CH_REGION + r] = o[2];
+    ub[(I + 1) * CH_REGION + r + CH_H] = o[3];
+}
+
+// FFT-256 of the sub-tile in `uc` (16 threads per frame), optionally with the FIR of the next sub-tile
+// (stage tile `st` -> `un`) interleaved two rows per segment. FULL: all 8 frames valid (no guards).
+// Every segment (between warp barriers) is written loads -> math -> stores.
+template <int MODE, bool FULL, bool FIR>
+__device__ __forceinline__ void fft_fir_phase(const ChanArgs& a, u64* __restrict__ uc, const float2* __restrict__ tws,
+                                              FirState& f, const u64* __restrict__ st, u64* __restrict__ un,
+                                              int tid, int fs, int nv, int f0, long long out_base,
+                                              uint64_t* drained, int drained_parity) {
+    const int g = tid >> 4, t = tid & 15;
+    u64* reg = uc + g * CH_REGION;
+    const bool on = FULL || (g < nv);
+    u64 v[16];
+    u64 o[4];
+    // segment 1: pass-1 operands + FIR rows 0,1
+    if (on) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = reg[t + 16 * i];
+    }
+    if (FIR) {
+        fir2_load<0>(f, st, tid);
+        fir2_math(f, o);
+        // `un` was read by the discriminator of the sub-tile before last: wait (late) for every thread's reads
+        if (drained_parity >= 0) mbar_wait(drained, (uint32_t)drained_parity);
+        fir2_store<0>(o, un, tid);
+    }
+    __syncwarp();
+    // segment 2: radix-16 pass 1, four-step twiddle in place, exchange store + FIR rows 2,3
+    if (FIR) fir2_load<2>(f, st, tid);
+    if (on) {
+        fft16(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 16; ++k1) {
+            const float2 tw = tws[k1 * 16 + t];
+            v[rev4(k1)] = twid(v[rev4(k1)], tw.x, -tw.y);
+        }
+    }
+    if (FIR) fir2_math(f, o);
+    if (on) {
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) reg[t * 17 + k1] = v[rev4(k1)];
+    }
+    if (FIR) fir2_store<2>(o, un, tid);
+    __syncwarp();
+    // segment 3: pass-2 operands + FIR rows 4,5
+    if (on) {
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) v[n2] = reg[n2 * 17 + t];
+    }
+    if (FIR) {
+        fir2_load<4>(f, st, tid);
+        fir2_math(f, o);
+        fir2_store<4>(o, un, tid);
+    }
+    __syncwarp();
+    // segment 4: radix-16 pass 2, output + FIR rows 6,7
+    if (FIR) fir2_load<6>(f, st, tid);
+    if (on) fft16(v);
+    if (FIR) fir2_math(f, o);
+    if (on) {
+        if (MODE == 0) {
+            const int b = fs + g;
+            if (b >= f0) {
+                u64* og = reinterpret_cast<u64*>(a.out) + (out_base + b) * CH_M + t;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) og[16 * k2] = v[rev4(k2)];
+            }
+        } else {
+            float* w = reinterpret_cast<float*>(uc) + g * CH_REGION_W + t;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                w[16 * k2] = lo2(v[rev4(k2)]);
+                w[CH_YIM + 16 * k2] = hi2(v[rev4(k2)]);
+            }
+        }
+    }
+    if (FIR) fir2_store<6>(o, un, tid);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs a) {
+    extern __shared__ __align__(128) unsigned char chan_smem_raw[];
+    ChanSmemP& sm = *reinterpret_cast<ChanSmemP*>(chan_smem_raw);
+    const int tid = threadIdx.x;
+    const int r = tid;
+    const int c = blockIdx.y;
+    const int step = (MODE == 1) ? a.R - 1 : a.R;
+    const int f0 = (blockIdx.x == 0) ? 0 : a.R + (blockIdx.x - 1) * step;
+    if (f0 >= a.F) return;
+    const int f1 = min(a.F, (blockIdx.x == 0) ? a.R : f0 + step);
+    const float2* __restrict__ xc = a.x + (long long)c * a.chunk_stride;
+    const long long out_base = (long long)c * a.F;
+
+    const int fe = (MODE == 1 && f0 > 0) ? f0 - 1 : f0;
+    const int fast_start = (f0 == 0) ? 8 : fe;
+    const int n_fast = (fast_start < f1) ? (f1 - fast_start + CH_S - 1) / CH_S : 0;
+
+    if (tid == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        mbar_init(&sm.drained, CH_THREADS);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < 256; i += CH_THREADS) {
+        float s, co;
+        sincospif(-(float)((i >> 4) * (i & 15)) * (1.0f / 128.0f), &s, &co);
+        sm.tw[i] = make_float2(co, s);
+    }
+    __syncthreads();
+
+    auto issue = [&](int n) {
+        const int fs = fast_start + CH_S * n;
+        const int nrows = min(CH_S, a.F - fs);
+        const uint32_t bytes = (uint32_t)nrows * CH_H * sizeof(float2);
+        mbar_expect_tx(&sm.full[n & 1], bytes);
+        bulk_g2s(sm.stage[n & 1], xc + (long long)(fs + 1) * CH_H, bytes, &sm.full[n & 1]);
+    };
+    if (tid == 0) {
+        if (n_fast > 0) issue(0);
+        if (n_fast > 1) issue(1);
+    }
+
+    FirState f;
+#pragma unroll
+    for (int j = 0; j < CH_T; ++j) {
+        f.hlo[j] = __ldg(a.taps + r + CH_M * j);
+        f.hhi[j] = __ldg(a.taps + r + CH_H + CH_M * j);
+    }
+
+    u64 pre = 0ull, pim = 0ull;
+
+    // discriminator of the sub-tile whose planar FFT output sits in `ub` (frames fs .. fs+nv-1)
+    auto disc = [&](const u64* ub, int fs, int nv) {
+        const float* sw = reinterpret_cast<const float*>(ub);
+        float* o = reinterpret_cast<float*>(a.out) + (out_base + fs) * CH_M + 2 * tid;
+        const AtanScaled at = a.at;
+        auto one = [&](int i, bool guard) {
+            const float* w = sw + i * CH_REGION_W + 2 * tid;
+            const u64 yre = *reinterpret_cast<const u64*>(w);
+            const u64 yim = *reinterpret_cast<const u64*>(w + CH_YIM);
+            const u64 px = fma2(yre, pre, mul2(yim, pim));
+            const u64 py = sub2(mul2(yim, pre), mul2(yre, pim));
+            const u64 d = scaled_atan2f_x2(py, px, at);
+            if (!guard || fs + i >= f0) *reinterpret_cast<u64*>(o + (long long)i * CH_M) = d;
+            pre = yre;
+            pim = yim;
+        };
+        if (nv == CH_S && fs >= f0) {
+#pragma unroll
+            for (int i = 0; i < CH_S; ++i) one(i, false);
+        } else if (nv == CH_S) {
+#pragma unroll
+            for (int i = 0; i < CH_S; ++i) one(i, true);
+        } else {
+            for (int i = 0; i < nv; ++i) one(i, true);
+        }
+    };
+
+    // ---- prologue sub-tile: frames 0..7 of a chunk reach into the previous call/chunk ----
+    if (f0 == 0) {
+        const int nv = min(CH_S, f1);
+        for (int b = 0; b < nv; ++b) {
+            float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < CH_T; ++j) {
+                const float2 vl = blk_fetch(a, xc, c, b - j, r);
+                const float2 vh = blk_fetch(a, xc, c, b - j, r + CH_H);
+                lo.x = fmaf(f.hlo[j], vl.x, lo.x);
+                lo.y = fmaf(f.hlo[j], vl.y, lo.y);
+                hi.x = fmaf(f.hhi[j], vh.x, hi.x);
+                hi.y = fmaf(f.hhi[j], vh.y, hi.y);
+            }
+            sm.u[0][b * CH_REGION + r] = pk2(lo.x, lo.y);
+            sm.u[0][b * CH_REGION + r + CH_H] = pk2(hi.x, hi.y);
+        }
+        __syncthreads();
+        fft_fir_phase<MODE, false, false>(a, sm.u[0], sm.tw, f, nullptr, nullptr, tid, 0, nv, f0, out_base, nullptr, -1);
+        __syncthreads();
+        if (MODE == 1) {
+            disc(sm.u[0], 0, nv);
+            __syncthreads();
+        }
+    }
+    if (n_fast == 0) return;
+
+    {
+        const u64* xr = reinterpret_cast<const u64*>(xc);
+#pragma unroll
+        for (int m = 0; m < 9; ++m) f.w[m] = __ldg(xr + (long long)(fast_start - 8 + m) * CH_H + r);
+    }
+    // pre-loop: FIR of fast sub-tile 0
+    mbar_wait(&sm.full[0], 0);
+    fir_rows<0, 8>(f, sm.stage[0], sm.u[0], r);
+    __syncthreads();
+    if (tid == 0 && 2 < n_fast) issue(2);
+
+    for (int n = 0; n < n_fast; ++n) {
+        const int fs = fast_start + CH_S * n;
+        const int nv = min(CH_S, f1 - fs);
+        u64* uc = sm.u[n & 1];
+        if (n + 1 < n_fast) {
+            // nv == 8 here: only the last sub-tile of a run can be ragged
+            mbar_wait(&sm.full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+            fft_fir_phase<MODE, true, true>(a, uc, sm.tw, f, sm.stage[(n + 1) & 1], sm.u[(n + 1) & 1], tid, fs, nv, f0,
+                                            out_base, &sm.drained, (MODE == 1 && n > 0) ? ((n - 1) & 1) : -1);
+        } else {
+            fft_fir_phase<MODE, false, false>(a, uc, sm.tw, f, nullptr, nullptr, tid, fs, nv, f0, out_base, nullptr, -1);
+        }
+        __syncthreads();
+        if (tid == 0 && n + 3 < n_fast) issue(n + 3);
+        if (MODE == 1) {
+            disc(uc, fs, nv);
+            // split barrier instead of __syncthreads: u[n&1] is next written by the FIR stores of iteration n+1,
+            // which wait on this phase (parity n&1) only after their own loads and math
+            mbar_arrive(&sm.drained);
+        }
     }
 }
 
@@ -567,7 +868,25 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
             a.at.hp = (float)(1.5707963267948966 * fm_scale);
             a.at.pi = (float)(3.141592653589793 * fm_scale);
         }
+        int var = 1;  // 1 = software-pipelined kernel (FIR of sub-tile n+1 inside the FFT of sub-tile n); 0 = phase-serial
+        if (const char* e = getenv("WC_CHAN_VAR")) var = atoi(e);
+        if (var == 1) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                WC_CUDA(cudaFuncSetAttribute(chan256p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChanSmemP)));
+                WC_CUDA(cudaFuncSetAttribute(chan256p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChanSmemP)));
+                attr_done = true;
+            }
+            if (mode == WC_CHAN_OUT_COMPLEX) chan256p_kernel<0><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);
+            else chan256p_kernel<1><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);
+        } else
         if (mode == WC_CHAN_OUT_COMPLEX) chan256_kernel<0, 4><<<grid, CH_THREADS, 0, stream>>>(a);
+#ifdef WC_DEV_ABLATE
+        else if (getenv("WC_CHAN_ABL") && atoi(getenv("WC_CHAN_ABL")) == 1) chan256_kernel<1, 4, 1><<<grid, CH_THREADS, 0, stream>>>(a);
+        else if (getenv("WC_CHAN_ABL") && atoi(getenv("WC_CHAN_ABL")) == 2) chan256_kernel<1, 4, 2><<<grid, CH_THREADS, 0, stream>>>(a);
+        else if (getenv("WC_CHAN_ABL") && atoi(getenv("WC_CHAN_ABL")) == 3) chan256_kernel<1, 4, 3><<<grid, CH_THREADS, 0, stream>>>(a);
+        else if (getenv("WC_CHAN_ABL") && atoi(getenv("WC_CHAN_ABL")) == 4) chan256_kernel<1, 4, 4><<<grid, CH_THREADS, 0, stream>>>(a);
+#endif
         else if (occ == 4) chan256_kernel<1, 4><<<grid, CH_THREADS, 0, stream>>>(a);
         else if (occ == 6) chan256_kernel<1, 6><<<grid, CH_THREADS, 0, stream>>>(a);
         else chan256_kernel<1, 5><<<grid, CH_THREADS, 0, stream>>>(a);
