@@ -418,8 +418,8 @@ def main():
             "roofline": {
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "kernel": "wc::chan256_kernel<1,4>", "alg_bytes_per_sample": ALG_BYTES_PER_SAMPLE,
-                "channelizer_only": {"kernel": "wc::chan256_kernel<0,4>", "alg_bytes_per_sample": 24,
+                "kernel": "wc::chan256p_kernel<1>", "alg_bytes_per_sample": ALG_BYTES_PER_SAMPLE,
+                "channelizer_only": {"kernel": "wc::chan256p_kernel<0>", "alg_bytes_per_sample": 24,
                                      "msps_per_gpu": round(chan_only_msps, 1),
                                      "achieved": round(24 * chan_only_msps / 1e3, 1),
                                      "frac": round(24 * chan_only_msps / 1e3 / peak, 4),

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArg
 //
 // Why: in chan256_kernel the FIR phase is a burst of FFMA2 (FMA-pipe bound, issue slots idle) and the FFT
 // phase is bound by shared-memory latency (short-scoreboard stalls, FMA pipe idle) — ncu attributes 30 % /
-// 46 % of the warp samples to them (profiles/r02_chan_fm_phases.md). Both live in the same 128 threads, so
+// 46 % of the warp samples to them (profiles/r01_chan_fm_notes.md). Both live in the same 128 threads, so
 // placing them in ONE instruction stream lets every warp fill its LDS/exchange latency with independent
 // FFMA2 work instead of relying on the 4 resident CTAs being in different phases. The FIR output buffer is
 // double-buffered (u[2]); one CTA-wide barrier per sub-tile disappears.
