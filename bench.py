@@ -120,14 +120,19 @@ class ClockSampler:
         }
 
 
+WORKLOAD = ("C5: 256-ch polyphase channelizer (M=256, 9 taps/arm, hop 128) + FM discriminator "
+            "of every channel, 125 MS/s cf32, 50 ms chunks (6.25 M samples)")
+
+
 def cpu_baseline(samples_per_worker: int, workers: int) -> dict:
     from oracle.cpu_baseline import channelizer_fm_cpu
 
-    r = channelizer_fm_cpu(samples_per_worker, workers, faithful=True)
+    # bounded sample: ~10 s of CPU work per core (12 passes over the per-worker slice)
+    r = channelizer_fm_cpu(samples_per_worker, workers, faithful=True, reps=12)
     v = channelizer_fm_cpu(samples_per_worker * 4, workers, faithful=False)
     return {
         "value": round(r["msps"], 3), "unit": "MS/s", "cores": workers, "kind": "port",
-        "sample": f"{workers} processes x {samples_per_worker} cf32 samples each: oracle restatement of "
+        "sample": f"{workers} processes x 12 passes x {samples_per_worker} cf32 samples each: oracle restatement of "
                   f"PolyphaseChannelizer.process (per-frame loop, channelizer.py:114-135) + quadrature_demod "
                   f"of all 256 channels; {r['seconds']:.1f} s",
         "vectorized_port_msps": round(v["msps"], 3),
@@ -142,7 +147,7 @@ def run_reference(args, rank):
     workers = os.cpu_count() or 1
     from oracle.cpu_baseline import channelizer_fm_cpu
 
-    per_worker = max(256 + 128 * 64, min(args.cpu_samples, 1_500_000))
+    per_worker = max(256 + 128 * 64, min(2 * args.cpu_samples, 6_000_000))
     for _ in range(max(0, min(args.warmup, 1))):
         channelizer_fm_cpu(per_worker // 4, workers, faithful=True)
     times, total = [], 0
@@ -157,7 +162,7 @@ def run_reference(args, rank):
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(1e3 * sum(times) / steps, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (numpy)",
         "data": "synthetic",
-        "config": {"workload": "C5 256-ch polyphase channelizer + FM discriminator, 125 MS/s cf32",
+        "config": {"workload": WORKLOAD,
                    "step": f"{workers} x {per_worker} samples (bounded sample of the 50 ms chunk)"},
         "cpu_baseline": {"value": round(msps, 3), "unit": "MS/s", "cores": workers, "kind": "port",
                          "sample": f"{steps} steps of {workers} processes x {per_worker} samples"},
@@ -407,8 +412,7 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": round(ms, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "C5: 256-ch polyphase channelizer (M=256, 9 taps/arm, hop 128) + FM discriminator "
-                            "of every channel, 125 MS/s cf32, 50 ms chunks (6.25 M samples)",
+                "workload": WORKLOAD,
                 "chunks_per_step": nb, "samples_per_step_per_gpu": samples_per_step,
                 "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed"
                       % ((8 + 8) * samples_per_step / 1e9),

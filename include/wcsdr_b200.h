@@ -218,6 +218,42 @@ int wc_pack(const float* x_dev, void* y_dev, long long total_floats, int fmt /* 
 int wc_audio_levels(const float* x_dev, int n, long long seq_stride, int n_seq, double* sumsq_dev, float* peak_dev,
                     int* clip_count_dev, void* stream);
 
+/* ---- P25 Phase 1 framing --------------------------------------------------------------------
+ * wc_bch_decode: dsp/fec/bch.py:644-658 bch_decode / BCH_63_16_23.decode (:533-641) for `count` codewords at once.
+ * bits63 uint8 [count][63] (codeword[0] first, 16 data bits then 47 parity), tracked_nac int32 [count] or NULL
+ * (<= 0 = none) -> data int32 [count] (16-bit NAC|DUID, 0 when uncorrectable), errors int32 [count] (-1 = uncorrectable). */
+int wc_bch_decode(const unsigned char* bits63_dev, const int* tracked_nac_dev, int count, int* data_dev, int* errors_dev,
+                  void* stream);
+int wc_bch_decode_host(const unsigned char* bits63_host, const int* tracked_nac_host, int count, int* data_host,
+                       int* errors_host);
+/* wc_p25framer_*: decoders/p25_framer.py:363-849 P25P1MessageFramer, one stateful framer per channel advanced by one
+ * call (soft sync correlation :193-231 with threshold 60, status-symbol stripping, NID BCH decode with the NAC tracker
+ * :320-349, message assembly :234-318 and dispatch :690-827). mode 0 = process_batch (:471-509), 1 =
+ * process_with_soft_sync per symbol (:438-457), 2 = process (:459-469). dispatch_enabled = started and a listener is
+ * set. Inputs: soft float32 / dibits uint8 [C][chan_stride], n_sym int32 [C] or NULL (= n_symbols for every channel).
+ * Outputs (device, per channel c): msg_hdr int32 [C][max_msgs][6] = {duid, nac, nbits, corrected_bit_count, offset
+ * into the channel's bit pool, 0}; msg_sym int64 [C][max_msgs] = symbols processed when the message was dispatched
+ * (timestamp = ref + 1000*that/4800 on the host); msg_bits uint8 [C][pool_bytes] one byte per bit; summary int32
+ * [C][8] = {n_msgs, valid NIDs, error code, symbol index of the error (-1), err_a, err_b, err_duid, pool bytes used}.
+ * Error codes mirror the AssertionErrors the reference raises out of the batch (the channel stops at that symbol with
+ * the reference's partial state): 1 placeholder dispatch, 2 below minimum length (a = length, b = minimum), 3 not
+ * aligned to 196-bit blocks, 4 length mismatch, 5 invalid dibit (a = dibit), 6 output buffers full (never with the
+ * sizes below). scores (optional, float32 [C][n_symbols]) receives the soft sync scores. */
+typedef struct wc_p25framer wc_p25framer;
+int wc_p25framer_create(int n_channels, wc_p25framer** out);
+void wc_p25framer_destroy(wc_p25framer* h);
+int wc_p25framer_reset(wc_p25framer* h, int channel /* -1 = all */, int full /* 1 = also NAC tracker + symbol clock */);
+int wc_p25framer_max_msgs(int n_symbols);
+int wc_p25framer_pool_bytes(int n_symbols);
+int wc_p25framer_process(wc_p25framer* h, const float* soft_dev, const unsigned char* dibits_dev, long long chan_stride,
+                         const int* n_sym_dev, int n_symbols, int mode, int dispatch_enabled, float* scores_dev,
+                         int* msg_hdr_dev, long long* msg_sym_dev, unsigned char* msg_bits_dev, int* summary_dev,
+                         void* stream);
+int wc_p25framer_process_host(wc_p25framer* h, const float* soft_host, const unsigned char* dibits_host, int n_symbols,
+                              const int* n_sym_host, int mode, int dispatch_enabled, float* scores_host, int* msg_hdr_host,
+                              long long* msg_sym_host, unsigned char* msg_bits_host, int* summary_host);
+int wc_p25framer_get_state(wc_p25framer* h, int channel, int* state12);
+
 #ifdef __cplusplus
 }
 #endif

@@ -253,7 +253,163 @@ def oa_shift(iq):
     return rc.freq_shift(iq, 200000.0, 2_400_000)
 
 
-GENERATORS = {"audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+
+def framer_streams():
+    """(name, dibits uint8, soft float32, chunk) — symbol streams with valid NIDs (oracle.bch.bch_encode), shared with the
+    tests: contiguous 3-TSBK TSDUs, a voice call, single TSBKs with gaps, mixed/unknown DUIDs with uncorrectable NIDs,
+    noise. Soft symbols = ideal levels + seeded Gaussian noise."""
+    from oracle import p25_framer as of
+
+    out = []
+    rng = np.random.default_rng(11)
+    s = list(rng.integers(0, 4, 70))
+    for k in range(8):
+        s += of.frame_dibits(rng, 0x293, 0x7, 588, nid_errors=k % 5)
+    s += list(rng.integers(0, 4, 100))
+    out.append(("tsdu3", s, 720))
+    s = list(rng.integers(0, 4, 40))
+    for duid, nb in [(0x0, 648), (0x5, 1568), (0xA, 1568), (0x5, 1568), (0xA, 1568), (0xF, 168), (0x3, 28), (0x3, 28)]:
+        s += of.frame_dibits(rng, 0x4A1, duid, nb, nid_errors=int(rng.integers(0, 8)))
+        while len(s) % 36 != 40 % 36:
+            s.append(int(rng.integers(0, 4)))
+    s += list(rng.integers(0, 4, 120))
+    out.append(("voice", s, 500))
+    s = list(rng.integers(0, 4, 60))
+    for k in range(6):
+        s += of.frame_dibits(rng, 0x293, 0x7, 196)
+        s += list(rng.integers(0, 4, int(rng.integers(0, 30))))
+    s += list(rng.integers(0, 4, 80))
+    out.append(("tsbk1_gaps", s, 300))
+    s = list(rng.integers(0, 4, 30))
+    for k in range(14):
+        duid = [0xC, 0x9, 0x7, 0x3, 0xE, 0xD, 0x5][k % 7]
+        nac = [0x293, 0x293, 0x111, 0x293][k % 4]
+        nb = {0xC: 196 * 3, 0x9: 300, 0x7: 588, 0x3: 28, 0xE: 100, 0xD: 400, 0x5: 1568}[duid]
+        s += of.frame_dibits(rng, nac, duid, nb, nid_errors=[0, 3, 12, 11, 13][k % 5])
+        s += list(rng.integers(0, 4, int(rng.integers(0, 50))))
+    out.append(("mixed", s, 777))
+    out.append(("noise", list(rng.integers(0, 4, 6000)), 1000))
+    res = []
+    for name, s, chunk in out:
+        dib = np.array(s, dtype=np.uint8)
+        soft = (of.dibits_to_soft(dib) + np.random.default_rng(5).normal(0, 0.3, len(dib))).astype(np.float32)
+        res.append((name, dib, soft, chunk))
+    return res
+
+
+def framer_e2e_signal():
+    """48 kS/s C4FM signal carrying a train of valid 3-TSBK TSDUs (the SURVEY §8d C4 control-channel recipe)."""
+    from oracle import c4fm as oc, p25_framer as of
+
+    rng = np.random.default_rng(77)
+    s = list(rng.integers(0, 4, 90))
+    for k in range(10):
+        s += of.frame_dibits(rng, 0x293, 0x7, 588, nid_errors=k % 3)
+    s += list(rng.integers(0, 4, 150))
+    dib = np.array(s, dtype=np.uint8)
+    return dib, oc.modulate_c4fm(dib, 48000, snr_db=26.0, cfo_hz=40.0, timing=0.35, seed=9)
+
+
+def _pack_msgs(msgs):
+    meta = np.array([[int(m.duid), int(m.nac), int(m.timestamp), int(m.corrected_bit_count), len(m.bits)] for m in msgs],
+                    dtype=np.int64).reshape(-1, 5)
+    bits = np.concatenate([np.asarray(m.bits, dtype=np.uint8) for m in msgs]) if msgs else np.zeros(0, np.uint8)
+    return meta, bits
+
+
+def gen_p25_framer():
+    """bch_decode and P25P1MessageFramer of the live reference: (a) 1200 codewords with 0-15 flipped bits / random words,
+    with and without a tracked NAC; (b) the framer_streams() through process_batch (chunked; AssertionErrors recorded where
+    the reference raises them) and through process_with_soft_sync symbol by symbol; (c) C4FMDemodulator.demodulate ->
+    process_batch / process_with_soft_sync on a C4FM signal with valid TSDUs."""
+    import json
+
+    from wavecapsdr.decoders.p25_framer import P25P1MessageFramer
+    from wavecapsdr.dsp.fec.bch import bch_decode
+    from wavecapsdr.dsp.p25.c4fm import C4FMDemodulator
+    from oracle import bch as ob
+
+    out = {}
+    rng = np.random.default_rng(21)
+    cws, trs, ds, es = [], [], [], []
+    for t in range(1200):
+        if t % 4 == 3:
+            c = rng.integers(0, 2, 63).astype(np.uint8)
+            d = 0
+        else:
+            d = int(rng.integers(0, 65536))
+            c = ob.bch_encode(d).copy()
+            c[rng.choice(63, int(rng.integers(0, 16)), replace=False)] ^= 1
+        tr = [0, 0x293, d >> 4][t % 3]
+        a = bch_decode(c, tr if tr else None)
+        cws.append(c); trs.append(tr); ds.append(int(a[0])); es.append(int(a[1]))
+    out["bch_cw"] = np.array(cws, dtype=np.uint8)
+    out["bch_tracked"] = np.array(trs, dtype=np.int32)
+    out["bch_data"] = np.array(ds, dtype=np.int32)
+    out["bch_errors"] = np.array(es, dtype=np.int32)
+
+    TS = 1_700_000_000_000
+
+    def run_batch(chunks):
+        fr = P25P1MessageFramer(); msgs = []
+        fr.set_listener(msgs.append); fr.start(); fr.set_timestamp(TS)
+        log = []
+        for soft, dib in chunks:
+            try:
+                log.append(int(fr.process_batch(soft, dib)))
+            except AssertionError as e:
+                log.append(str(e))
+        return msgs, log
+
+    def run_stream(soft, dib, max_errors=40):
+        fr = P25P1MessageFramer(); msgs = []
+        fr.set_listener(msgs.append); fr.start(); fr.set_timestamp(TS)
+        log = []
+        for i in range(len(dib)):
+            try:
+                if fr.process_with_soft_sync(float(soft[i]), int(dib[i])):
+                    log.append(i)
+            except AssertionError as e:
+                log.append([i, str(e)])
+                if len(log) > max_errors:
+                    break
+        return msgs, log
+
+    names = []
+    for name, dib, soft, chunk in framer_streams():
+        names.append(name)
+        out[f"{name}_dibits"] = dib
+        out[f"{name}_soft"] = soft
+        out[f"{name}_chunk"] = np.int32(chunk)
+        m, log = run_batch([(soft[s:s + chunk], dib[s:s + chunk]) for s in range(0, len(dib), chunk)])
+        out[f"{name}_batch_meta"], out[f"{name}_batch_bits"] = _pack_msgs(m)
+        out[f"{name}_batch_log"] = np.array(json.dumps(log))
+        m, log = run_stream(soft, dib)
+        out[f"{name}_stream_meta"], out[f"{name}_stream_bits"] = _pack_msgs(m)
+        out[f"{name}_stream_log"] = np.array(json.dumps(log))
+    out["stream_names"] = np.array(json.dumps(names))
+
+    tx, x = framer_e2e_signal()
+    d = C4FMDemodulator(sample_rate=48000)
+    chunks = []
+    for s in range(0, len(x), 2400):
+        a, b = d.demodulate(x[s:s + 2400])
+        chunks.append((np.asarray(b, dtype=np.float32), np.asarray(a, dtype=np.uint8)))
+    out["e2e_x"] = x
+    out["e2e_tx"] = tx
+    out["e2e_counts"] = np.array([len(c[1]) for c in chunks], dtype=np.int32)
+    out["e2e_dibits"] = np.concatenate([c[1] for c in chunks])
+    out["e2e_soft"] = np.concatenate([c[0] for c in chunks])
+    m, log = run_batch(chunks)
+    out["e2e_batch_meta"], out["e2e_batch_bits"] = _pack_msgs(m)
+    out["e2e_batch_log"] = np.array(json.dumps(log))
+    m, log = run_stream(out["e2e_soft"], out["e2e_dibits"])
+    out["e2e_stream_meta"], out["e2e_stream_bits"] = _pack_msgs(m)
+    out["e2e_stream_log"] = np.array(json.dumps(log))
+    np.savez_compressed(os.path.join(OUT, "p25_framer.npz"), **out)
+
+
+GENERATORS = {"p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

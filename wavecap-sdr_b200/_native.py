@@ -181,6 +181,17 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_spectral_nr", i32, vp, i32, i64, i32, f32, vp, i64, vp)
     fn("wc_pack", i32, vp, vp, i64, i32, vp)
     fn("wc_audio_levels", i32, vp, i32, i64, i32, vp, vp, vp, vp)
+    # P25 framing
+    fn("wc_bch_decode", i32, vp, vp, i32, vp, vp, vp)
+    fn("wc_bch_decode_host", i32, vp, vp, i32, vp, vp)
+    fn("wc_p25framer_create", i32, i32, P(vp))
+    fn("wc_p25framer_destroy", None, vp)
+    fn("wc_p25framer_reset", i32, vp, i32, i32)
+    fn("wc_p25framer_max_msgs", i32, i32)
+    fn("wc_p25framer_pool_bytes", i32, i32)
+    fn("wc_p25framer_process", i32, vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp)
+    fn("wc_p25framer_process_host", i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp)
+    fn("wc_p25framer_get_state", i32, vp, i32, vp)
     for extra in _EXTRA_DECLS:
         extra(l, fn)
 

@@ -1,0 +1,799 @@
+// P25 Phase 1 framing on the GPU, batched over channels:
+//   * BCH(63,16,23) decoding of the Network ID      — dsp/fec/bch.py:52-222 (syndromes, Berlekamp-Massey, Chien),
+//                                                      :533-641 (two-pass decode with the tracked NAC)
+//   * soft sync correlation over a block of symbols  — decoders/p25_framer.py:193-231
+//   * the message framer state machine               — decoders/p25_framer.py:363-849 (P25P1MessageFramer),
+//                                                      :234-318 (assembler), trunking NAC tracker :320-349
+//
+// Layout. One handle owns C channels; all state lives in device memory (FramerState[C]). A call consumes
+// soft/dibit rows [C][stride] (n_sym[c] valid symbols per row — exactly what the C4FM bank leaves on the device),
+// runs (1) a grid-wide score kernel (one thread per symbol, 24-tap correlation, previous 24 symbols carried),
+// (2) the sequential per-channel machine, one thread per channel: status-symbol stripping, NID collection,
+// in-thread BCH decode, message assembly. Assembled messages go to a per-channel header list + bit pool that
+// the host turns into P25P1Message objects. The reference raises AssertionError out of the middle of a batch in
+// some flows; the machine stops that channel at the same symbol with the same partial state and reports a code.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/wcsdr_b200.h"
+#include "common.cuh"
+
+namespace wc {
+
+// ---- GF(2^6), primitive polynomial x^6 + x + 1 (bch.py:246,255-271) ----
+__constant__ unsigned char c_gf_pow[64];
+__constant__ unsigned char c_gf_log[64];
+__constant__ float c_fsync[24];
+
+constexpr int BCH_N = 63, BCH_T = 11;
+
+__device__ __forceinline__ int gf_mul(int a, int b) {
+    if (a == 0 || b == 0) return 0;
+    int s = c_gf_log[a] + c_gf_log[b];
+    if (s >= BCH_N) s -= BCH_N;
+    return c_gf_pow[s];
+}
+
+// syndromes S_j = r(alpha^j), j = 1..22, r(x) = sum_i cw[i] x^(62-i) (bch.py:195-222); w holds cw[i] in bit (62-i)
+__device__ void bch_syndromes(unsigned long long w, unsigned char* S) {
+#pragma unroll 1
+    for (int j = 0; j < 2 * BCH_T; ++j) S[j] = 0;
+    while (w) {
+        const int p = 63 - __clzll((long long)w);  // degree of the highest set term
+        w &= ~(1ull << p);
+        int e = p % BCH_N;  // exponent of alpha^(p*(j+1)), advanced by p each syndrome
+        int acc = e;
+#pragma unroll 1
+        for (int j = 0; j < 2 * BCH_T; ++j) {
+            S[j] ^= c_gf_pow[acc];
+            acc += e;
+            if (acc >= BCH_N) acc -= BCH_N;
+        }
+    }
+}
+
+// One decoding attempt (bch.py:575-641). Returns the number of corrected bits or -1; *data = first 16 bits.
+__device__ int bch_decode_once(unsigned long long w, int* data) {
+    unsigned char S[2 * BCH_T];
+    bch_syndromes(w, S);
+    int any = 0;
+    for (int j = 0; j < 2 * BCH_T; ++j) any |= S[j];
+    if (!any) {
+        *data = (int)(w >> 47) & 0xFFFF;
+        return 0;
+    }
+    // Berlekamp-Massey over GF(64), locator truncated to degree T like the reference (bch.py:52-127)
+    unsigned char Cp[BCH_T + 1], Bp[BCH_T + 1], Tp[BCH_T + 1];
+    for (int i = 0; i <= BCH_T; ++i) Cp[i] = Bp[i] = 0;
+    Cp[0] = Bp[0] = 1;
+    int L = 0, m = 1, log_b = 0;
+    for (int n = 0; n < 2 * BCH_T; ++n) {
+        int d = S[n];
+        const int upper = (L + 1 > BCH_T + 1) ? BCH_T + 1 : L + 1;
+        for (int i = 1; i < upper; ++i)
+            if (n >= i) d ^= gf_mul(Cp[i], S[n - i]);
+        if (d == 0) {
+            ++m;
+        } else {
+            for (int i = 0; i <= BCH_T; ++i) Tp[i] = Cp[i];
+            const int log_d = c_gf_log[d];
+            int log_db = log_d + BCH_N - log_b;
+            if (log_db >= BCH_N) log_db -= BCH_N;
+            for (int i = 0; i + m <= BCH_T; ++i) {
+                const int bv = Bp[i];
+                if (bv) {
+                    int s = c_gf_log[bv] + log_db;
+                    if (s >= BCH_N) s -= BCH_N;
+                    Cp[i + m] ^= c_gf_pow[s];
+                }
+            }
+            if (n >= 2 * L) {
+                L = n + 1 - L;
+                for (int i = 0; i <= BCH_T; ++i) Bp[i] = Tp[i];
+                log_b = log_d;
+                m = 1;
+            } else {
+                ++m;
+            }
+        }
+    }
+    if (L == 0 || L > BCH_T) return -1;
+    // Chien search (bch.py:131-191): root alpha^i <-> error term x^((63-i)%63) <-> cw index 62 - that
+    int found = 0;
+    unsigned long long flips = 0ull;
+    for (int i = 0; i < BCH_N && found < L; ++i) {
+        int val = 0;
+        for (int k = 0; k <= L; ++k) {
+            const int ck = Cp[k];
+            if (ck) val ^= c_gf_pow[(c_gf_log[ck] + i * k) % BCH_N];
+        }
+        if (val == 0) {
+            const int deg = (BCH_N - i) % BCH_N;
+            flips ^= (1ull << deg);
+            ++found;
+        }
+    }
+    if (found != L) return -1;
+    const unsigned long long fixed = w ^ flips;
+    bch_syndromes(fixed, S);
+    any = 0;
+    for (int j = 0; j < 2 * BCH_T; ++j) any |= S[j];
+    if (any) return -1;
+    *data = (int)(fixed >> 47) & 0xFFFF;
+    return L;
+}
+
+// BCH_63_16_23.decode (bch.py:533-573): second attempt with the NAC field overwritten by the tracked NAC
+__device__ int bch_decode_nid(unsigned long long w, int tracked_nac, int* data) {
+    int e = bch_decode_once(w, data);
+    if (e >= 0) return e;
+    if (tracked_nac > 0) {
+        const int cur = (int)(w >> 51) & 0xFFF;
+        if (cur != tracked_nac) {
+            const unsigned long long w2 = (w & ((1ull << 51) - 1ull)) | ((unsigned long long)(tracked_nac & 0xFFF) << 51);
+            return bch_decode_once(w2, data);
+        }
+    }
+    *data = 0;
+    return -1;
+}
+
+__global__ void bch_batch_kernel(const unsigned char* __restrict__ bits, const int* __restrict__ tracked, int B,
+                                 int* __restrict__ data, int* __restrict__ errors) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    unsigned long long w = 0ull;
+    for (int k = 0; k < BCH_N; ++k) w |= (unsigned long long)(bits[(size_t)i * BCH_N + k] & 1) << (62 - k);
+    int d = 0;
+    const int e = bch_decode_nid(w, tracked ? tracked[i] : 0, &d);
+    data[i] = (e >= 0) ? d : 0;
+    errors[i] = e;
+}
+
+// ---- framer state (one per channel) ----
+constexpr int DUID_HDU = 0x0, DUID_TDU = 0x3, DUID_LDU1 = 0x5, DUID_TSBK1 = 0x7, DUID_LDU2 = 0xA, DUID_PDU = 0xC,
+              DUID_TDULC = 0xF, DUID_UNKNOWN = 0xE, DUID_PLACEHOLDER = 0xD, DUID_TSBK2 = 0x17, DUID_TSBK3 = 0x27;
+constexpr int MAX_MSG_BITS = 2000;
+
+struct FramerState {
+    float hist[24];            // last 24 soft symbols (oldest first)
+    long long symbols_total;   // every symbol ever processed (timestamps are derived from it on the host)
+    int sync_detected, nid_pointer;
+    int dibit_counter, status_counter;
+    int asm_active, asm_nac, asm_duid, asm_nbits, asm_target, asm_forced;
+    int assembly_required, previous_duid, detected_duid, detected_nac, detected_errs;
+    int tracked_nac;
+    unsigned char nid_buf[36];
+    unsigned char asm_bits[MAX_MSG_BITS];
+    unsigned char nac_seen[4096];  // observation counts, saturating (NACTracker, p25_framer.py:320-349)
+};
+
+__device__ __forceinline__ int duid_from_value(int v) {  // P25P1DataUnitID.from_value, p25_framer.py:57-63
+    switch (v) {
+        case DUID_HDU: case DUID_TDU: case DUID_LDU1: case DUID_TSBK1: case DUID_LDU2: case DUID_PDU: case DUID_TDULC:
+        case DUID_UNKNOWN: case DUID_PLACEHOLDER:
+            return v;
+        default:
+            return DUID_UNKNOWN;
+    }
+}
+__device__ __forceinline__ int duid_length(int d) {  // get_message_length, p25_framer.py:65-84
+    switch (d) {
+        case DUID_HDU: return 648;
+        case DUID_TDU: return 28;
+        case DUID_LDU1: case DUID_LDU2: return 1568;
+        case DUID_TSBK1: return 196;
+        case DUID_TSBK2: return 392;
+        case DUID_TSBK3: return 588;
+        case DUID_PDU: return 196;
+        case 0x1C: return 392;
+        case 0x2C: return 588;
+        case 0x3C: return 784;
+        case 0x4C: return 980;
+        case 0x5C: return 1176;
+        case DUID_TDULC: return 168;
+        case DUID_PLACEHOLDER: return 2000;
+        default: return 196;
+    }
+}
+__device__ __forceinline__ bool duid_is_tsbk(int d) { return d == DUID_TSBK1 || d == DUID_TSBK2 || d == DUID_TSBK3; }
+__device__ __forceinline__ bool duid_is_pdu(int d) {
+    return d == DUID_PDU || d == 0x1C || d == 0x2C || d == 0x3C || d == 0x4C || d == 0x5C;
+}
+
+// per-call output cursor of one channel
+struct FramerOut {
+    int* hdr;               // [max_msgs][6]: duid, nac, nbits, corrected, bit_offset, (symbols_total at dispatch) low 31 bits
+    long long* hdr_sym;     // [max_msgs] symbols_total at dispatch
+    unsigned char* pool;    // message bits, one byte per bit
+    int max_msgs, pool_cap;
+    int n_msgs, pool_used;
+    int err_code, err_a, err_b, err_duid;
+    int dispatch_enabled;
+};
+
+enum { ERR_NONE = 0, ERR_PLACEHOLDER = 1, ERR_BELOW_MIN = 2, ERR_NOT_ALIGNED = 3, ERR_LENGTH = 4, ERR_BAD_DIBIT = 5,
+       ERR_OUTPUT_FULL = 6 };
+
+__device__ void emit_msg(FramerState& s, FramerOut& o, int duid, int first, int count, int corrected) {
+    if (!o.dispatch_enabled) return;  // _broadcast: running and a listener are required (p25_framer.py:829-835)
+    if (o.n_msgs >= o.max_msgs || o.pool_used + count > o.pool_cap) {
+        if (!o.err_code) o.err_code = ERR_OUTPUT_FULL;
+        return;
+    }
+    int* h = o.hdr + (size_t)o.n_msgs * 6;
+    h[0] = duid;
+    h[1] = s.asm_nac;
+    h[2] = count;
+    h[3] = corrected;
+    h[4] = o.pool_used;
+    h[5] = 0;
+    o.hdr_sym[o.n_msgs] = s.symbols_total;
+    for (int i = 0; i < count; ++i) o.pool[o.pool_used + i] = s.asm_bits[first + i];
+    o.pool_used += count;
+    ++o.n_msgs;
+}
+
+// _assert_message_length (p25_framer.py:651-688); true = raise
+__device__ bool length_check_fails(FramerOut& o, int nbits, int duid, bool allow_truncated) {
+    if (duid == DUID_PLACEHOLDER) {
+        o.err_code = ERR_PLACEHOLDER;
+        o.err_duid = duid;
+        return true;
+    }
+    const int expected = duid_length(duid);
+    if (allow_truncated && nbits < expected) return false;
+    if (duid_is_tsbk(duid) || duid_is_pdu(duid)) {
+        if (nbits < expected) {
+            o.err_code = ERR_BELOW_MIN; o.err_a = nbits; o.err_b = expected; o.err_duid = duid;
+            return true;
+        }
+        if (nbits % 196 != 0) {
+            o.err_code = ERR_NOT_ALIGNED; o.err_a = nbits; o.err_b = expected; o.err_duid = duid;
+            return true;
+        }
+        return false;
+    }
+    if (nbits != expected) {
+        o.err_code = ERR_LENGTH; o.err_a = nbits; o.err_b = expected; o.err_duid = duid;
+        return true;
+    }
+    return false;
+}
+
+// _dispatch_message and its three flavours (p25_framer.py:690-827); true = raised
+__device__ bool dispatch_message(FramerState& s, FramerOut& o) {
+    if (!s.asm_active) return false;
+    s.previous_duid = s.asm_duid;
+    if (!o.dispatch_enabled) {
+        s.asm_active = 0;
+        return false;
+    }
+    const bool allow = s.asm_forced != 0;
+    int duid = s.asm_duid;
+    if (duid_is_tsbk(duid)) {
+        // _dispatch_tsbk recurses block by block; every level re-checks the length
+        for (;;) {
+            duid = s.asm_duid;
+            if (length_check_fails(o, s.asm_nbits, duid, allow)) return true;
+            if (duid == DUID_TSBK1) {
+                if (s.asm_nbits >= 196) {
+                    emit_msg(s, o, duid, 0, 196, s.detected_errs);
+                    s.asm_duid = DUID_TSBK2;
+                    s.asm_target = duid_length(DUID_TSBK2);
+                    if (s.asm_nbits >= 392) continue;
+                }
+                return false;
+            }
+            if (duid == DUID_TSBK2) {
+                if (s.asm_nbits >= 392) {
+                    emit_msg(s, o, duid, 196, 196, 0);
+                    s.asm_duid = DUID_TSBK3;
+                    s.asm_target = duid_length(DUID_TSBK3);
+                    if (s.asm_nbits >= 588) continue;
+                }
+                return false;
+            }
+            if (s.asm_nbits >= 588) emit_msg(s, o, duid, 392, 196, 0);
+            s.asm_active = 0;
+            return false;
+        }
+    }
+    if (duid == DUID_PLACEHOLDER && !duid_is_pdu(duid)) {
+        s.asm_active = 0;
+        return false;
+    }
+    // PDU flavours and everything else: whole message, then the assembler is dropped
+    if (length_check_fails(o, s.asm_nbits, duid, allow)) return true;
+    emit_msg(s, o, duid, 0, s.asm_nbits, s.detected_errs);
+    s.asm_active = 0;
+    return false;
+}
+
+__device__ __forceinline__ void asm_start(FramerState& s, int nac, int duid) {
+    s.asm_active = 1;
+    s.asm_nac = nac;
+    s.asm_duid = duid;
+    s.asm_nbits = 0;
+    s.asm_target = duid_length(duid);
+    s.asm_forced = 0;
+}
+__device__ __forceinline__ void asm_receive(FramerState& s, int dibit) {  // p25_framer.py:251-259
+    if (s.asm_nbits < s.asm_target) {
+        s.asm_bits[s.asm_nbits++] = (unsigned char)((dibit >> 1) & 1);
+        if (s.asm_nbits < s.asm_target) s.asm_bits[s.asm_nbits++] = (unsigned char)(dibit & 1);
+    }
+}
+// force_completion (p25_framer.py:287-317)
+__device__ void asm_force_completion(FramerState& s, int next_duid) {
+    const int size = s.asm_nbits;
+    s.asm_forced = 1;
+    if (s.asm_duid == DUID_PLACEHOLDER) {
+        if (size <= 28) s.asm_duid = DUID_TDU;
+        else if (next_duid == DUID_LDU1) {
+            if (size <= 770) s.asm_duid = DUID_HDU;
+            else if (size >= 1500) s.asm_duid = DUID_LDU2;
+        } else if (next_duid == DUID_LDU2) {
+            if (size >= 1500) s.asm_duid = DUID_LDU1;
+        } else if (next_duid == DUID_TSBK1) {
+            if (size >= 195) s.asm_duid = DUID_TSBK1;
+        }
+    }
+    if (s.asm_duid == DUID_PLACEHOLDER) s.asm_duid = DUID_TDU;
+    s.asm_target = duid_length(s.asm_duid);
+}
+
+// _check_nid + _nid_detected (p25_framer.py:581-649); returns 1 valid NID, 0 none, -1 raised
+__device__ int check_nid(FramerState& s, FramerOut& o) {
+    unsigned long long w = 0ull;
+    int k = 0;
+    for (int i = 0; i < 33 && k < 32; ++i) {
+        if (i == 11) continue;  // status symbol inside the NID
+        const int d = s.nid_buf[i] & 3;
+        const int b0 = (d >> 1) & 1, b1 = d & 1;
+        if (2 * k < BCH_N) w |= (unsigned long long)b0 << (62 - 2 * k);
+        if (2 * k + 1 < BCH_N) w |= (unsigned long long)b1 << (62 - (2 * k + 1));
+        ++k;
+    }
+    int decoded = 0;
+    const int errs = bch_decode_nid(w, s.tracked_nac, &decoded);
+    if (errs < 0) return 0;
+    const int nac = (decoded >> 4) & 0xFFF;
+    const int duid = duid_from_value(decoded & 0xF);
+    if (nac >= 0x001 && nac <= 0xFFE) {
+        unsigned char& cnt = s.nac_seen[nac];
+        if (cnt < 255) ++cnt;
+        if (cnt >= 3) s.tracked_nac = nac;
+    }
+    s.detected_duid = (duid == DUID_UNKNOWN) ? DUID_PLACEHOLDER : duid;
+    s.detected_nac = nac;
+    s.detected_errs = errs;
+    if (s.asm_active) {
+        if (s.asm_nbits >= s.asm_target) {
+            if (s.asm_duid != DUID_PLACEHOLDER && dispatch_message(s, o)) return -1;
+        } else {
+            asm_force_completion(s, s.detected_duid);
+            if (dispatch_message(s, o)) return -1;
+        }
+    }
+    s.assembly_required = 1;
+    s.dibit_counter = 57;
+    s.status_counter = 21;
+    return 1;
+}
+
+// _process (p25_framer.py:517-579); returns 1 valid NID, 0, -1 raised
+__device__ int process_symbol(FramerState& s, FramerOut& o, int dibit) {
+    int valid = 0;
+    ++s.symbols_total;
+    ++s.status_counter;
+    if (s.sync_detected) {
+        if (s.nid_pointer < 36) s.nid_buf[s.nid_pointer] = (unsigned char)dibit;
+        ++s.nid_pointer;
+        if (s.nid_pointer >= 33) {
+            const int r = check_nid(s, o);
+            if (r < 0) return -1;  // raised inside: _sync_detected stays set, like the reference
+            valid = r;
+            s.sync_detected = 0;
+        }
+    }
+    if (s.status_counter == 36) {
+        s.status_counter = 0;
+        ++s.dibit_counter;
+        return 0;
+    }
+    if (s.asm_active) {
+        if (s.asm_nbits >= s.asm_target) {
+            if (dispatch_message(s, o)) return -1;
+            if (s.asm_active) {
+                if (dibit > 3) { o.err_code = ERR_BAD_DIBIT; o.err_a = dibit; o.err_duid = s.asm_duid; return -1; }
+                asm_receive(s, dibit);
+            }
+        } else {
+            if (dibit > 3) { o.err_code = ERR_BAD_DIBIT; o.err_a = dibit; o.err_duid = s.asm_duid; return -1; }
+            asm_receive(s, dibit);
+        }
+    } else if (s.dibit_counter == 57) {
+        if (s.assembly_required) {
+            asm_start(s, s.detected_nac, s.detected_duid);
+            s.assembly_required = 0;
+        } else if (s.detected_nac > 0) {
+            s.detected_duid = DUID_PLACEHOLDER;
+            asm_start(s, s.detected_nac, DUID_PLACEHOLDER);
+        }
+    } else if (s.dibit_counter >= 4800) {
+        s.dibit_counter -= 4800;
+    }
+    ++s.dibit_counter;
+    return valid;
+}
+
+// scores[c][k] = sum_i sync[i] * s[k-23+i] (float32 result), previous 24 symbols from the carried history
+__global__ void framer_score_kernel(const float* __restrict__ soft, long long stride, const int* __restrict__ n_sym, int n_fixed,
+                                    const FramerState* __restrict__ st, float* __restrict__ scores, long long score_stride) {
+    const int c = blockIdx.y;
+    const int n = n_sym ? n_sym[c] : n_fixed;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float* s = soft + (size_t)c * stride;
+    const float* hist = st[c].hist;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+        const int t = k - 23 + i;
+        const float v = (t >= 0) ? s[t] : hist[24 + t];
+        acc += (double)__fmul_rn(c_fsync[i], v);
+    }
+    scores[(size_t)c * score_stride + k] = (float)acc;
+}
+
+struct FramerArgs {
+    FramerState* st;
+    const float* soft;
+    const unsigned char* dibits;
+    long long stride;
+    const int* n_sym;
+    int n_fixed;
+    const float* scores;
+    long long score_stride;
+    int mode;              // 0 = process_batch order (sync callback before the symbol), 1 = process_with_soft_sync order,
+                           // 2 = process(): no sync detection
+    int dispatch_enabled;
+    int C;
+    int* hdr;              // [C][max_msgs][6]
+    long long* hdr_sym;    // [C][max_msgs]
+    unsigned char* pool;   // [C][pool_cap]
+    int max_msgs, pool_cap;
+    int* summary;          // [C][8]: n_msgs, nid_count, err_code, err_pos, err_a, err_b, err_duid, pool_used
+};
+
+__global__ void framer_machine_kernel(const FramerArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.C) return;
+    FramerState& s = a.st[c];
+    const int n = a.n_sym ? a.n_sym[c] : a.n_fixed;
+    FramerOut o;
+    o.hdr = a.hdr + (size_t)c * a.max_msgs * 6;
+    o.hdr_sym = a.hdr_sym + (size_t)c * a.max_msgs;
+    o.pool = a.pool + (size_t)c * a.pool_cap;
+    o.max_msgs = a.max_msgs;
+    o.pool_cap = a.pool_cap;
+    o.n_msgs = 0;
+    o.pool_used = 0;
+    o.err_code = 0;
+    o.err_a = o.err_b = o.err_duid = 0;
+    o.dispatch_enabled = a.dispatch_enabled;
+    const unsigned char* d = a.dibits + (size_t)c * a.stride;
+    const float* sc = a.scores + (size_t)c * a.score_stride;
+    int nid_count = 0, err_pos = -1;
+    for (int i = 0; i < n; ++i) {
+        const bool hit = (a.mode != 2) && (sc[i] > 60.0f);
+        if (a.mode == 0 && hit) {  // _sync_detected_callback (p25_framer.py:511-515)
+            s.sync_detected = 1;
+            s.nid_pointer = 0;
+        }
+        const int r = process_symbol(s, o, d[i]);
+        if (r < 0) {
+            err_pos = i;
+            break;
+        }
+        nid_count += r;
+        if (a.mode == 1 && hit) {
+            s.sync_detected = 1;
+            s.nid_pointer = 0;
+        }
+    }
+    // batch order: the detector consumed the whole block before the machine ran (p25_framer.py:485-486).
+    // per-symbol order: a symbol whose _process raised never reaches the detector (:448-455). process() never feeds it.
+    if (a.mode != 2) {
+        const int nh_sym = (a.mode == 1 && err_pos >= 0) ? err_pos : n;
+        const float* sf = a.soft + (size_t)c * a.stride;
+        float nh[24];
+        for (int k = 0; k < 24; ++k) {
+            const int t = nh_sym - 24 + k;
+            nh[k] = (t >= 0) ? sf[t] : s.hist[24 + t];
+        }
+        for (int k = 0; k < 24; ++k) s.hist[k] = nh[k];
+    }
+    int* sm = a.summary + (size_t)c * 8;
+    sm[0] = o.n_msgs;
+    sm[1] = nid_count;
+    sm[2] = o.err_code;
+    sm[3] = err_pos;
+    sm[4] = o.err_a;
+    sm[5] = o.err_b;
+    sm[6] = o.err_duid;
+    sm[7] = o.pool_used;
+}
+
+__global__ void framer_reset_kernel(FramerState* st, int C, int channel, int keep_tracker) {
+    const int c = blockIdx.x;
+    if (c >= C || (channel >= 0 && c != channel)) return;
+    FramerState& s = st[c];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 24; ++i) s.hist[i] = 0.f;
+        s.sync_detected = 0;
+        s.nid_pointer = 0;
+        s.dibit_counter = 58;
+        s.status_counter = 36;
+        s.asm_active = 0;
+        s.asm_nac = s.asm_duid = s.asm_nbits = s.asm_target = s.asm_forced = 0;
+        s.assembly_required = 0;
+        s.previous_duid = DUID_PLACEHOLDER;
+        s.detected_duid = DUID_PLACEHOLDER;
+        s.detected_nac = 0;
+        if (!keep_tracker) {
+            s.symbols_total = 0;
+            s.detected_errs = 0;
+            s.tracked_nac = 0;
+        }
+    }
+    if (!keep_tracker)
+        for (int i = threadIdx.x; i < 4096; i += blockDim.x) s.nac_seen[i] = 0;
+}
+
+static bool g_tables_ready = false;
+static int ensure_tables() {
+    if (g_tables_ready) return 0;
+    unsigned char pw[64], lg[64];
+    memset(pw, 0, sizeof(pw));
+    memset(lg, 0, sizeof(lg));
+    int x = 1;
+    for (int i = 0; i < 63; ++i) {
+        pw[i] = (unsigned char)x;
+        lg[x] = (unsigned char)i;
+        x <<= 1;
+        if (x & 64) x ^= 0x43;
+    }
+    pw[63] = 1;
+    float sync[24];
+    const unsigned long long pat = 0x5575F5FF77FFull;
+    for (int i = 0; i < 24; ++i) sync[i] = (((pat >> ((23 - i) * 2)) & 3ull) == 1ull) ? 3.0f : -3.0f;
+    WC_CUDA(cudaMemcpyToSymbol(c_gf_pow, pw, sizeof(pw)));
+    WC_CUDA(cudaMemcpyToSymbol(c_gf_log, lg, sizeof(lg)));
+    WC_CUDA(cudaMemcpyToSymbol(c_fsync, sync, sizeof(sync)));
+    g_tables_ready = true;
+    return 0;
+}
+
+}  // namespace wc
+
+using namespace wc;
+
+struct wc_p25framer {
+    int C = 0;
+    FramerState* d_state = nullptr;
+    float* d_scores = nullptr;   size_t scores_cap = 0;   // [C][n]
+    // host-call staging
+    void* d_soft = nullptr;      size_t soft_cap = 0;
+    void* d_dibits = nullptr;    size_t dib_cap = 0;
+    void* d_hdr = nullptr;       size_t hdr_cap = 0;
+    void* d_hsym = nullptr;      size_t hsym_cap = 0;
+    void* d_pool = nullptr;      size_t pool_cap_b = 0;
+    int* d_summary = nullptr;
+    int* d_nsym = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+static int grow(void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    WC_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+extern "C" {
+
+int wc_bch_decode(const unsigned char* bits63_dev, const int* tracked_nac_dev, int count, int* data_dev, int* errors_dev,
+                  void* stream_v) {
+    WC_REQUIRE(bits63_dev && data_dev && errors_dev, "wc_bch_decode: null argument");
+    if (count <= 0) return 0;
+    if (ensure_tables()) return -2;
+    bch_batch_kernel<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(bits63_dev, tracked_nac_dev, count, data_dev,
+                                                                             errors_dev);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wc_bch_decode_host(const unsigned char* bits63_host, const int* tracked_nac_host, int count, int* data_host,
+                       int* errors_host) {
+    WC_REQUIRE(bits63_host && data_host && errors_host, "wc_bch_decode_host: null argument");
+    if (count <= 0) return 0;
+    unsigned char* d_bits = nullptr;
+    int *d_tr = nullptr, *d_data = nullptr, *d_err = nullptr;
+    WC_CUDA(cudaMalloc(&d_bits, (size_t)count * 63));
+    WC_CUDA(cudaMalloc(&d_data, sizeof(int) * (size_t)count));
+    WC_CUDA(cudaMalloc(&d_err, sizeof(int) * (size_t)count));
+    if (tracked_nac_host) WC_CUDA(cudaMalloc(&d_tr, sizeof(int) * (size_t)count));
+    int rc = 0;
+    cudaMemcpy(d_bits, bits63_host, (size_t)count * 63, cudaMemcpyHostToDevice);
+    if (d_tr) cudaMemcpy(d_tr, tracked_nac_host, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice);
+    rc = wc_bch_decode(d_bits, d_tr, count, d_data, d_err, nullptr);
+    if (!rc) {
+        cudaMemcpy(data_host, d_data, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost);
+        if (cudaMemcpy(errors_host, d_err, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("wc_bch_decode_host: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = -2;
+        }
+    }
+    cudaFree(d_bits);
+    cudaFree(d_data);
+    cudaFree(d_err);
+    if (d_tr) cudaFree(d_tr);
+    return rc;
+}
+
+int wc_p25framer_create(int n_channels, wc_p25framer** out) {
+    WC_REQUIRE(out != nullptr, "wc_p25framer_create: out is null");
+    WC_REQUIRE(n_channels >= 1 && n_channels <= 65536, "wc_p25framer_create: n_channels %d out of range", n_channels);
+    if (ensure_tables()) return -2;
+    wc_p25framer* h = new wc_p25framer();
+    h->C = n_channels;
+    if (cudaMalloc(&h->d_state, sizeof(FramerState) * (size_t)n_channels) != cudaSuccess ||
+        cudaMalloc(&h->d_summary, sizeof(int) * 8 * (size_t)n_channels) != cudaSuccess ||
+        cudaMalloc(&h->d_nsym, sizeof(int) * (size_t)n_channels) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("wc_p25framer_create: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return -2;
+    }
+    cudaMemset(h->d_state, 0, sizeof(FramerState) * (size_t)n_channels);
+    framer_reset_kernel<<<n_channels, 128, 0, h->stream>>>(h->d_state, n_channels, -1, 0);
+    cudaStreamSynchronize(h->stream);
+    *out = h;
+    return 0;
+}
+
+void wc_p25framer_destroy(wc_p25framer* h) {
+    if (!h) return;
+    cudaFree(h->d_state);
+    cudaFree(h->d_summary);
+    cudaFree(h->d_nsym);
+    if (h->d_scores) cudaFree(h->d_scores);
+    if (h->d_soft) cudaFree(h->d_soft);
+    if (h->d_dibits) cudaFree(h->d_dibits);
+    if (h->d_hdr) cudaFree(h->d_hdr);
+    if (h->d_hsym) cudaFree(h->d_hsym);
+    if (h->d_pool) cudaFree(h->d_pool);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+/* P25P1MessageFramer.reset (p25_framer.py:837-849) keeps the NAC tracker and the symbol clock; full = 1 also clears those */
+int wc_p25framer_reset(wc_p25framer* h, int channel, int full) {
+    WC_REQUIRE(h != nullptr, "wc_p25framer_reset: null handle");
+    WC_REQUIRE(channel >= -1 && channel < h->C, "wc_p25framer_reset: channel %d out of range", channel);
+    framer_reset_kernel<<<h->C, 128, 0, h->stream>>>(h->d_state, h->C, channel, full ? 0 : 1);
+    WC_CUDA(cudaGetLastError());
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int wc_p25framer_max_msgs(int n_symbols) { return n_symbols / 57 + 8; }
+int wc_p25framer_pool_bytes(int n_symbols) { return 2 * n_symbols + 2 * MAX_MSG_BITS; }
+
+int wc_p25framer_process(wc_p25framer* h, const float* soft_dev, const unsigned char* dibits_dev, long long chan_stride,
+                         const int* n_sym_dev, int n_symbols, int mode, int dispatch_enabled, float* scores_dev,
+                         int* msg_hdr_dev, long long* msg_sym_dev, unsigned char* msg_bits_dev, int* summary_dev,
+                         void* stream_v) {
+    WC_REQUIRE(h && soft_dev && dibits_dev && msg_hdr_dev && msg_sym_dev && msg_bits_dev && summary_dev,
+               "wc_p25framer_process: null argument");
+    WC_REQUIRE(n_symbols >= 0 && chan_stride >= n_symbols, "wc_p25framer_process: bad n_symbols / chan_stride");
+    WC_REQUIRE(mode >= 0 && mode <= 2, "wc_p25framer_process: bad mode %d", mode);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    const int nmax = n_symbols > 0 ? n_symbols : 1;
+    float* scores = scores_dev;
+    if (!scores) {
+        if (grow((void**)&h->d_scores, &h->scores_cap, sizeof(float) * (size_t)h->C * nmax)) return -2;
+        scores = h->d_scores;
+    }
+    if (n_symbols > 0) {
+        dim3 grid((n_symbols + 127) / 128, h->C);
+        framer_score_kernel<<<grid, 128, 0, stream>>>(soft_dev, chan_stride, n_sym_dev, n_symbols, h->d_state, scores, nmax);
+    }
+    FramerArgs a;
+    a.st = h->d_state;
+    a.soft = soft_dev;
+    a.dibits = dibits_dev;
+    a.stride = chan_stride;
+    a.n_sym = n_sym_dev;
+    a.n_fixed = n_symbols;
+    a.scores = scores;
+    a.score_stride = nmax;
+    a.mode = mode;
+    a.dispatch_enabled = dispatch_enabled;
+    a.C = h->C;
+    a.hdr = msg_hdr_dev;
+    a.hdr_sym = msg_sym_dev;
+    a.pool = msg_bits_dev;
+    a.max_msgs = wc_p25framer_max_msgs(n_symbols);
+    a.pool_cap = wc_p25framer_pool_bytes(n_symbols);
+    a.summary = summary_dev;
+    framer_machine_kernel<<<(h->C + 31) / 32, 32, 0, stream>>>(a);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wc_p25framer_process_host(wc_p25framer* h, const float* soft_host, const unsigned char* dibits_host, int n_symbols,
+                              const int* n_sym_host, int mode, int dispatch_enabled, float* scores_host, int* msg_hdr_host,
+                              long long* msg_sym_host, unsigned char* msg_bits_host, int* summary_host) {
+    WC_REQUIRE(h && soft_host && dibits_host && msg_hdr_host && msg_sym_host && msg_bits_host && summary_host,
+               "wc_p25framer_process_host: null argument");
+    WC_REQUIRE(n_symbols >= 0, "wc_p25framer_process_host: negative n_symbols");
+    const int C = h->C;
+    const int nmax = n_symbols > 0 ? n_symbols : 1;
+    const int mm = wc_p25framer_max_msgs(n_symbols), pc = wc_p25framer_pool_bytes(n_symbols);
+    if (grow(&h->d_soft, &h->soft_cap, sizeof(float) * (size_t)C * nmax)) return -2;
+    if (grow(&h->d_dibits, &h->dib_cap, (size_t)C * nmax)) return -2;
+    if (grow(&h->d_hdr, &h->hdr_cap, sizeof(int) * 6 * (size_t)C * mm)) return -2;
+    if (grow(&h->d_hsym, &h->hsym_cap, sizeof(long long) * (size_t)C * mm)) return -2;
+    if (grow(&h->d_pool, &h->pool_cap_b, (size_t)C * pc)) return -2;
+    if (grow((void**)&h->d_scores, &h->scores_cap, sizeof(float) * (size_t)C * nmax)) return -2;
+    cudaStream_t s = h->stream;
+    if (n_symbols > 0) {
+        WC_CUDA(cudaMemcpyAsync(h->d_soft, soft_host, sizeof(float) * (size_t)C * n_symbols, cudaMemcpyHostToDevice, s));
+        WC_CUDA(cudaMemcpyAsync(h->d_dibits, dibits_host, (size_t)C * n_symbols, cudaMemcpyHostToDevice, s));
+    }
+    if (n_sym_host) WC_CUDA(cudaMemcpyAsync(h->d_nsym, n_sym_host, sizeof(int) * (size_t)C, cudaMemcpyHostToDevice, s));
+    int rc = wc_p25framer_process(h, (const float*)h->d_soft, (const unsigned char*)h->d_dibits, nmax,
+                                  n_sym_host ? h->d_nsym : nullptr, n_symbols, mode, dispatch_enabled, h->d_scores,
+                                  (int*)h->d_hdr, (long long*)h->d_hsym, (unsigned char*)h->d_pool, h->d_summary, s);
+    if (rc) return rc;
+    WC_CUDA(cudaMemcpyAsync(summary_host, h->d_summary, sizeof(int) * 8 * (size_t)C, cudaMemcpyDeviceToHost, s));
+    WC_CUDA(cudaMemcpyAsync(msg_hdr_host, h->d_hdr, sizeof(int) * 6 * (size_t)C * mm, cudaMemcpyDeviceToHost, s));
+    WC_CUDA(cudaMemcpyAsync(msg_sym_host, h->d_hsym, sizeof(long long) * (size_t)C * mm, cudaMemcpyDeviceToHost, s));
+    WC_CUDA(cudaMemcpyAsync(msg_bits_host, h->d_pool, (size_t)C * pc, cudaMemcpyDeviceToHost, s));
+    if (scores_host && n_symbols > 0)
+        WC_CUDA(cudaMemcpyAsync(scores_host, h->d_scores, sizeof(float) * (size_t)C * n_symbols, cudaMemcpyDeviceToHost, s));
+    WC_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+/* state12 = {sync_detected, nid_pointer, dibit_counter, status_counter, asm_active, asm_duid, asm_nbits, detected_nac,
+ * detected_duid, tracked_nac, previous_duid, symbols_total (low 31 bits)} */
+int wc_p25framer_get_state(wc_p25framer* h, int channel, int* state12) {
+    WC_REQUIRE(h && state12, "wc_p25framer_get_state: null argument");
+    WC_REQUIRE(channel >= 0 && channel < h->C, "wc_p25framer_get_state: channel %d out of range", channel);
+    static FramerState tmp;  // ~6 KB: keep it off the stack
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    WC_CUDA(cudaMemcpy(&tmp, h->d_state + channel, sizeof(FramerState), cudaMemcpyDeviceToHost));
+    state12[0] = tmp.sync_detected;
+    state12[1] = tmp.nid_pointer;
+    state12[2] = tmp.dibit_counter;
+    state12[3] = tmp.status_counter;
+    state12[4] = tmp.asm_active;
+    state12[5] = tmp.asm_duid;
+    state12[6] = tmp.asm_nbits;
+    state12[7] = tmp.detected_nac;
+    state12[8] = tmp.detected_duid;
+    state12[9] = tmp.tracked_nac;
+    state12[10] = tmp.previous_duid;
+    state12[11] = (int)(tmp.symbols_total & 0x7fffffff);
+    return 0;
+}
+
+}  // extern "C"
