@@ -22,117 +22,145 @@
 namespace wc {
 
 // ---- GF(2^6), primitive polynomial x^6 + x + 1 (bch.py:246,255-271) ----
-__constant__ unsigned char c_gf_pow[64];
-__constant__ unsigned char c_gf_log[64];
+// pw is doubled (alpha^i for i < 126) so that a product is pw[lg[a] + lg[b]] without a modulo. The tables are copied
+// into shared memory by every kernel that decodes: lanes look up different elements, which a constant bank serialises.
+__constant__ unsigned char c_gf_pw[128];
+__constant__ unsigned char c_gf_lg[64];
 __constant__ float c_fsync[24];
+// syndrome table: g_syn[b][v] = XOR over the set bits p = 8b+k of byte value v of the packed odd syndromes
+// (alpha^p, alpha^3p, ..., alpha^21p): .x/.y = S1..S19 in 6-bit fields, .z = S21. 8 x 256 x 16 B = 32 KB, L1/L2 resident.
+__device__ uint4 g_syn[8 * 256];
 
 constexpr int BCH_N = 63, BCH_T = 11;
 
-__device__ __forceinline__ int gf_mul(int a, int b) {
-    if (a == 0 || b == 0) return 0;
-    int s = c_gf_log[a] + c_gf_log[b];
-    if (s >= BCH_N) s -= BCH_N;
-    return c_gf_pow[s];
+struct Gf {
+    const unsigned char* pw;
+    const unsigned char* lg;
+    __device__ __forceinline__ int mul(int a, int b) const { return (a && b) ? pw[lg[a] + lg[b]] : 0; }
+    __device__ __forceinline__ int mul_log(int a, int log_b) const { return a ? pw[lg[a] + log_b] : 0; }
+    __device__ __forceinline__ int sqr(int a) const { return a ? pw[2 * lg[a]] : 0; }
+};
+
+__device__ __forceinline__ void gf_load_shared(unsigned char* s_pw, unsigned char* s_lg) {
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_pw[i] = c_gf_pw[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_lg[i] = c_gf_lg[i];
 }
 
-// syndromes S_j = r(alpha^j), j = 1..22, r(x) = sum_i cw[i] x^(62-i) (bch.py:195-222); w holds cw[i] in bit (62-i)
-__device__ void bch_syndromes(unsigned long long w, unsigned char* S) {
-#pragma unroll 1
-    for (int j = 0; j < 2 * BCH_T; ++j) S[j] = 0;
-    while (w) {
-        const int p = 63 - __clzll((long long)w);  // degree of the highest set term
-        w &= ~(1ull << p);
-        int e = p % BCH_N;  // exponent of alpha^(p*(j+1)), advanced by p each syndrome
-        int acc = e;
-#pragma unroll 1
-        for (int j = 0; j < 2 * BCH_T; ++j) {
-            S[j] ^= c_gf_pow[acc];
-            acc += e;
-            if (acc >= BCH_N) acc -= BCH_N;
-        }
+// odd syndromes S1, S3, ..., S21 of r(x) = sum_i cw[i] x^(62-i) (bch.py:195-222); w holds cw[i] in bit (62-i)
+__device__ __forceinline__ uint4 bch_odd_syndromes(unsigned long long w) {
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const uint4 t = g_syn[b * 256 + (int)((w >> (8 * b)) & 255ull)];
+        acc.x ^= t.x;
+        acc.y ^= t.y;
+        acc.z ^= t.z;
     }
+    return acc;
 }
 
 // One decoding attempt (bch.py:575-641). Returns the number of corrected bits or -1; *data = first 16 bits.
-__device__ int bch_decode_once(unsigned long long w, int* data) {
-    unsigned char S[2 * BCH_T];
-    bch_syndromes(w, S);
-    int any = 0;
-    for (int j = 0; j < 2 * BCH_T; ++j) any |= S[j];
-    if (!any) {
+// Every array below is indexed with compile-time constants (loops fully unrolled), so it lives in registers:
+// the locator update keeps x^m * B(x) instead of B(x) and m, which turns C[i+m] ^= q * B[i] into C[i] ^= q * Bx[i].
+__device__ int bch_decode_once(const Gf gf, unsigned long long w, int* data) {
+    const uint4 odd = bch_odd_syndromes(w);
+    if ((odd.x | odd.y | odd.z) == 0u) {
         *data = (int)(w >> 47) & 0xFFFF;
         return 0;
     }
-    // Berlekamp-Massey over GF(64), locator truncated to degree T like the reference (bch.py:52-127)
-    unsigned char Cp[BCH_T + 1], Bp[BCH_T + 1], Tp[BCH_T + 1];
-    for (int i = 0; i <= BCH_T; ++i) Cp[i] = Bp[i] = 0;
-    Cp[0] = Bp[0] = 1;
-    int L = 0, m = 1, log_b = 0;
+    // S[k] = S_(k+1): odd ones from the table, even ones by squaring (S_2j = S_j^2 in characteristic 2)
+    int S[2 * BCH_T];
+    {
+        const unsigned long long lo = ((unsigned long long)odd.y << 32) | odd.x;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) S[2 * j] = (int)((lo >> (6 * j)) & 63ull);
+        S[20] = (int)(odd.z & 63u);
+#pragma unroll
+        for (int k = 2; k <= 2 * BCH_T; k += 2) S[k - 1] = gf.sqr(S[k / 2 - 1]);
+    }
+    // Berlekamp-Massey (bch.py:52-127), locator truncated to degree T like the reference
+    int Cp[BCH_T + 1], Bx[BCH_T + 1], Sw[BCH_T + 1];  // Sw[i] = S[n - i] (0 when n < i)
+#pragma unroll
+    for (int i = 0; i <= BCH_T; ++i) Cp[i] = Bx[i] = Sw[i] = 0;
+    Cp[0] = 1;
+    Bx[1] = 1;  // x^1 * B(x), B = 1
+    int L = 0, log_b = 0;
+#pragma unroll
     for (int n = 0; n < 2 * BCH_T; ++n) {
-        int d = S[n];
-        const int upper = (L + 1 > BCH_T + 1) ? BCH_T + 1 : L + 1;
-        for (int i = 1; i < upper; ++i)
-            if (n >= i) d ^= gf_mul(Cp[i], S[n - i]);
+#pragma unroll
+        for (int i = BCH_T; i > 0; --i) Sw[i] = Sw[i - 1];
+        Sw[0] = S[n];
+        int d = Sw[0];
+#pragma unroll
+        for (int i = 1; i <= BCH_T; ++i)
+            if (i <= L) d ^= gf.mul(Cp[i], Sw[i]);
         if (d == 0) {
-            ++m;
+#pragma unroll
+            for (int i = BCH_T; i > 0; --i) Bx[i] = Bx[i - 1];
+            Bx[0] = 0;
         } else {
-            for (int i = 0; i <= BCH_T; ++i) Tp[i] = Cp[i];
-            const int log_d = c_gf_log[d];
-            int log_db = log_d + BCH_N - log_b;
-            if (log_db >= BCH_N) log_db -= BCH_N;
-            for (int i = 0; i + m <= BCH_T; ++i) {
-                const int bv = Bp[i];
-                if (bv) {
-                    int s = c_gf_log[bv] + log_db;
-                    if (s >= BCH_N) s -= BCH_N;
-                    Cp[i + m] ^= c_gf_pow[s];
-                }
+            const int log_d = gf.lg[d];
+            const int log_q = log_d + BCH_N - log_b;  // < 126
+            const bool grow = n >= 2 * L;
+            int old[BCH_T + 1];
+#pragma unroll
+            for (int i = 0; i <= BCH_T; ++i) {
+                old[i] = Cp[i];
+                Cp[i] ^= gf.mul_log(Bx[i], log_q >= BCH_N ? log_q - BCH_N : log_q);
             }
-            if (n >= 2 * L) {
+            if (grow) {
                 L = n + 1 - L;
-                for (int i = 0; i <= BCH_T; ++i) Bp[i] = Tp[i];
                 log_b = log_d;
-                m = 1;
+#pragma unroll
+                for (int i = BCH_T; i > 0; --i) Bx[i] = old[i - 1];
             } else {
-                ++m;
+#pragma unroll
+                for (int i = BCH_T; i > 0; --i) Bx[i] = Bx[i - 1];
             }
+            Bx[0] = 0;
         }
     }
     if (L == 0 || L > BCH_T) return -1;
-    // Chien search (bch.py:131-191): root alpha^i <-> error term x^((63-i)%63) <-> cw index 62 - that
+    // Chien search (bch.py:131-191): root alpha^i <-> error term x^((63-i)%63). term[k] = C[k] * alpha^(i*k) is
+    // advanced by a constant factor per step.
+    int term[BCH_T + 1];
+#pragma unroll
+    for (int k = 0; k <= BCH_T; ++k) term[k] = (k <= L) ? Cp[k] : 0;
     int found = 0;
     unsigned long long flips = 0ull;
     for (int i = 0; i < BCH_N && found < L; ++i) {
         int val = 0;
-        for (int k = 0; k <= L; ++k) {
-            const int ck = Cp[k];
-            if (ck) val ^= c_gf_pow[(c_gf_log[ck] + i * k) % BCH_N];
+#pragma unroll
+        for (int k = 0; k <= BCH_T; ++k) {
+            val ^= term[k];
+            term[k] = gf.mul_log(term[k], k);
         }
         if (val == 0) {
-            const int deg = (BCH_N - i) % BCH_N;
-            flips ^= (1ull << deg);
+            flips ^= 1ull << ((BCH_N - i) % BCH_N);
             ++found;
         }
     }
     if (found != L) return -1;
     const unsigned long long fixed = w ^ flips;
-    bch_syndromes(fixed, S);
-    any = 0;
-    for (int j = 0; j < 2 * BCH_T; ++j) any |= S[j];
-    if (any) return -1;
+    const uint4 chk = bch_odd_syndromes(fixed);
+    if ((chk.x | chk.y | chk.z) != 0u) return -1;
     *data = (int)(fixed >> 47) & 0xFFFF;
     return L;
 }
 
 // BCH_63_16_23.decode (bch.py:533-573): second attempt with the NAC field overwritten by the tracked NAC
-__device__ int bch_decode_nid(unsigned long long w, int tracked_nac, int* data) {
-    int e = bch_decode_once(w, data);
+__device__ __noinline__ int bch_decode_nid(const unsigned char* s_pw, const unsigned char* s_lg, unsigned long long w,
+                                           int tracked_nac, int* data) {
+    Gf gf;
+    gf.pw = s_pw;
+    gf.lg = s_lg;
+    int e = bch_decode_once(gf, w, data);
     if (e >= 0) return e;
     if (tracked_nac > 0) {
         const int cur = (int)(w >> 51) & 0xFFF;
         if (cur != tracked_nac) {
             const unsigned long long w2 = (w & ((1ull << 51) - 1ull)) | ((unsigned long long)(tracked_nac & 0xFFF) << 51);
-            return bch_decode_once(w2, data);
+            return bch_decode_once(gf, w2, data);
         }
     }
     *data = 0;
@@ -141,12 +169,15 @@ __device__ int bch_decode_nid(unsigned long long w, int tracked_nac, int* data) 
 
 __global__ void bch_batch_kernel(const unsigned char* __restrict__ bits, const int* __restrict__ tracked, int B,
                                  int* __restrict__ data, int* __restrict__ errors) {
+    __shared__ unsigned char s_pw[128], s_lg[64];
+    gf_load_shared(s_pw, s_lg);
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     unsigned long long w = 0ull;
     for (int k = 0; k < BCH_N; ++k) w |= (unsigned long long)(bits[(size_t)i * BCH_N + k] & 1) << (62 - k);
     int d = 0;
-    const int e = bch_decode_nid(w, tracked ? tracked[i] : 0, &d);
+    const int e = bch_decode_nid(s_pw, s_lg, w, tracked ? tracked[i] : 0, &d);
     data[i] = (e >= 0) ? d : 0;
     errors[i] = e;
 }
@@ -156,16 +187,20 @@ constexpr int DUID_HDU = 0x0, DUID_TDU = 0x3, DUID_LDU1 = 0x5, DUID_TSBK1 = 0x7,
               DUID_TDULC = 0xF, DUID_UNKNOWN = 0xE, DUID_PLACEHOLDER = 0xD, DUID_TSBK2 = 0x17, DUID_TSBK3 = 0x27;
 constexpr int MAX_MSG_BITS = 2000;
 
-struct FramerState {
-    float hist[24];            // last 24 soft symbols (oldest first)
+// scalars + NID buffer: copied into registers / local memory for the duration of a call
+struct FramerCore {
     long long symbols_total;   // every symbol ever processed (timestamps are derived from it on the host)
     int sync_detected, nid_pointer;
     int dibit_counter, status_counter;
     int asm_active, asm_nac, asm_duid, asm_nbits, asm_target, asm_forced;
     int assembly_required, previous_duid, detected_duid, detected_nac, detected_errs;
     int tracked_nac;
-    unsigned char nid_buf[36];
-    unsigned char asm_bits[MAX_MSG_BITS];
+};
+struct __align__(16) FramerState {
+    FramerCore core;
+    float hist[24];                // last 24 soft symbols (oldest first)
+    unsigned char nid_buf[40];     // dibits collected after a sync hit
+    __align__(16) unsigned char asm_bits[MAX_MSG_BITS];
     unsigned char nac_seen[4096];  // observation counts, saturating (NACTracker, p25_framer.py:320-349)
 };
 
@@ -211,14 +246,20 @@ struct FramerOut {
     int n_msgs, pool_used;
     int err_code, err_a, err_b, err_duid;
     int dispatch_enabled;
+    unsigned char* asm_bits;   // the channel's assembler bits, NID dibits and NAC observation counts stay in global memory
+    unsigned char* nac_seen;
+    unsigned char* nid_buf;
+    const unsigned char* gf_pw;  // GF(64) tables in shared memory
+    const unsigned char* gf_lg;
 };
 
 enum { ERR_NONE = 0, ERR_PLACEHOLDER = 1, ERR_BELOW_MIN = 2, ERR_NOT_ALIGNED = 3, ERR_LENGTH = 4, ERR_BAD_DIBIT = 5,
        ERR_OUTPUT_FULL = 6 };
 
-__device__ void emit_msg(FramerState& s, FramerOut& o, int duid, int first, int count, int corrected) {
+__device__ __forceinline__ void emit_msg(FramerCore& s, FramerOut& o, int duid, int first, int count, int corrected) {
     if (!o.dispatch_enabled) return;  // _broadcast: running and a listener are required (p25_framer.py:829-835)
-    if (o.n_msgs >= o.max_msgs || o.pool_used + count > o.pool_cap) {
+    const int padded = (count + 3) & ~3;
+    if (o.n_msgs >= o.max_msgs || o.pool_used + padded > o.pool_cap) {
         if (!o.err_code) o.err_code = ERR_OUTPUT_FULL;
         return;
     }
@@ -230,13 +271,17 @@ __device__ void emit_msg(FramerState& s, FramerOut& o, int duid, int first, int 
     h[4] = o.pool_used;
     h[5] = 0;
     o.hdr_sym[o.n_msgs] = s.symbols_total;
-    for (int i = 0; i < count; ++i) o.pool[o.pool_used + i] = s.asm_bits[first + i];
-    o.pool_used += count;
+    // word copies: `first` is 0 / 196 / 392 and the pool cursor stays 4-byte aligned, both buffers are padded to words
+    const unsigned int* __restrict__ src = reinterpret_cast<const unsigned int*>(o.asm_bits + first);
+    unsigned int* __restrict__ dst = reinterpret_cast<unsigned int*>(o.pool + o.pool_used);
+#pragma unroll 8
+    for (int i = 0; i < padded / 4; ++i) dst[i] = src[i];
+    o.pool_used += padded;
     ++o.n_msgs;
 }
 
 // _assert_message_length (p25_framer.py:651-688); true = raise
-__device__ bool length_check_fails(FramerOut& o, int nbits, int duid, bool allow_truncated) {
+__device__ __forceinline__ bool length_check_fails(FramerOut& o, int nbits, int duid, bool allow_truncated) {
     if (duid == DUID_PLACEHOLDER) {
         o.err_code = ERR_PLACEHOLDER;
         o.err_duid = duid;
@@ -263,7 +308,7 @@ __device__ bool length_check_fails(FramerOut& o, int nbits, int duid, bool allow
 }
 
 // _dispatch_message and its three flavours (p25_framer.py:690-827); true = raised
-__device__ bool dispatch_message(FramerState& s, FramerOut& o) {
+__device__ __forceinline__ bool dispatch_message(FramerCore& s, FramerOut& o) {
     if (!s.asm_active) return false;
     s.previous_duid = s.asm_duid;
     if (!o.dispatch_enabled) {
@@ -311,7 +356,7 @@ __device__ bool dispatch_message(FramerState& s, FramerOut& o) {
     return false;
 }
 
-__device__ __forceinline__ void asm_start(FramerState& s, int nac, int duid) {
+__device__ __forceinline__ void asm_start(FramerCore& s, int nac, int duid) {
     s.asm_active = 1;
     s.asm_nac = nac;
     s.asm_duid = duid;
@@ -319,14 +364,14 @@ __device__ __forceinline__ void asm_start(FramerState& s, int nac, int duid) {
     s.asm_target = duid_length(duid);
     s.asm_forced = 0;
 }
-__device__ __forceinline__ void asm_receive(FramerState& s, int dibit) {  // p25_framer.py:251-259
+__device__ __forceinline__ void asm_receive(FramerCore& s, FramerOut& o, int dibit) {  // p25_framer.py:251-259
     if (s.asm_nbits < s.asm_target) {
-        s.asm_bits[s.asm_nbits++] = (unsigned char)((dibit >> 1) & 1);
-        if (s.asm_nbits < s.asm_target) s.asm_bits[s.asm_nbits++] = (unsigned char)(dibit & 1);
+        o.asm_bits[s.asm_nbits++] = (unsigned char)((dibit >> 1) & 1);
+        if (s.asm_nbits < s.asm_target) o.asm_bits[s.asm_nbits++] = (unsigned char)(dibit & 1);
     }
 }
 // force_completion (p25_framer.py:287-317)
-__device__ void asm_force_completion(FramerState& s, int next_duid) {
+__device__ __forceinline__ void asm_force_completion(FramerCore& s, int next_duid) {
     const int size = s.asm_nbits;
     s.asm_forced = 1;
     if (s.asm_duid == DUID_PLACEHOLDER) {
@@ -345,24 +390,24 @@ __device__ void asm_force_completion(FramerState& s, int next_duid) {
 }
 
 // _check_nid + _nid_detected (p25_framer.py:581-649); returns 1 valid NID, 0 none, -1 raised
-__device__ int check_nid(FramerState& s, FramerOut& o) {
+__device__ __forceinline__ int check_nid(FramerCore& s, FramerOut& o) {
     unsigned long long w = 0ull;
     int k = 0;
     for (int i = 0; i < 33 && k < 32; ++i) {
         if (i == 11) continue;  // status symbol inside the NID
-        const int d = s.nid_buf[i] & 3;
+        const int d = o.nid_buf[i] & 3;
         const int b0 = (d >> 1) & 1, b1 = d & 1;
         if (2 * k < BCH_N) w |= (unsigned long long)b0 << (62 - 2 * k);
         if (2 * k + 1 < BCH_N) w |= (unsigned long long)b1 << (62 - (2 * k + 1));
         ++k;
     }
     int decoded = 0;
-    const int errs = bch_decode_nid(w, s.tracked_nac, &decoded);
+    const int errs = bch_decode_nid(o.gf_pw, o.gf_lg, w, s.tracked_nac, &decoded);
     if (errs < 0) return 0;
     const int nac = (decoded >> 4) & 0xFFF;
     const int duid = duid_from_value(decoded & 0xF);
     if (nac >= 0x001 && nac <= 0xFFE) {
-        unsigned char& cnt = s.nac_seen[nac];
+        unsigned char& cnt = o.nac_seen[nac];
         if (cnt < 255) ++cnt;
         if (cnt >= 3) s.tracked_nac = nac;
     }
@@ -384,12 +429,12 @@ __device__ int check_nid(FramerState& s, FramerOut& o) {
 }
 
 // _process (p25_framer.py:517-579); returns 1 valid NID, 0, -1 raised
-__device__ int process_symbol(FramerState& s, FramerOut& o, int dibit) {
+__device__ __forceinline__ int process_symbol(FramerCore& s, FramerOut& o, int dibit) {
     int valid = 0;
     ++s.symbols_total;
     ++s.status_counter;
     if (s.sync_detected) {
-        if (s.nid_pointer < 36) s.nid_buf[s.nid_pointer] = (unsigned char)dibit;
+        if (s.nid_pointer < 36) o.nid_buf[s.nid_pointer] = (unsigned char)dibit;
         ++s.nid_pointer;
         if (s.nid_pointer >= 33) {
             const int r = check_nid(s, o);
@@ -408,11 +453,11 @@ __device__ int process_symbol(FramerState& s, FramerOut& o, int dibit) {
             if (dispatch_message(s, o)) return -1;
             if (s.asm_active) {
                 if (dibit > 3) { o.err_code = ERR_BAD_DIBIT; o.err_a = dibit; o.err_duid = s.asm_duid; return -1; }
-                asm_receive(s, dibit);
+                asm_receive(s, o, dibit);
             }
         } else {
             if (dibit > 3) { o.err_code = ERR_BAD_DIBIT; o.err_a = dibit; o.err_duid = s.asm_duid; return -1; }
-            asm_receive(s, dibit);
+            asm_receive(s, o, dibit);
         }
     } else if (s.dibit_counter == 57) {
         if (s.assembly_required) {
@@ -429,9 +474,11 @@ __device__ int process_symbol(FramerState& s, FramerOut& o, int dibit) {
     return valid;
 }
 
-// scores[c][k] = sum_i sync[i] * s[k-23+i] (float32 result), previous 24 symbols from the carried history
+// score[c][k] = sum_i sync[i] * s[k-23+i] (float32 result), previous 24 symbols from the carried history;
+// hits[c][k] = score > 60 (SYNC_DETECTION_THRESHOLD). One thread per symbol, whole bank in one grid.
 __global__ void framer_score_kernel(const float* __restrict__ soft, long long stride, const int* __restrict__ n_sym, int n_fixed,
-                                    const FramerState* __restrict__ st, float* __restrict__ scores, long long score_stride) {
+                                    const FramerState* __restrict__ st, unsigned char* __restrict__ hits,
+                                    float* __restrict__ scores, long long score_stride) {
     const int c = blockIdx.y;
     const int n = n_sym ? n_sym[c] : n_fixed;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,7 +492,9 @@ __global__ void framer_score_kernel(const float* __restrict__ soft, long long st
         const float v = (t >= 0) ? s[t] : hist[24 + t];
         acc += (double)__fmul_rn(c_fsync[i], v);
     }
-    scores[(size_t)c * score_stride + k] = (float)acc;
+    const float sc = (float)acc;
+    hits[(size_t)c * score_stride + k] = sc > 60.0f ? 1 : 0;
+    if (scores) scores[(size_t)c * score_stride + k] = sc;
 }
 
 struct FramerArgs {
@@ -455,8 +504,8 @@ struct FramerArgs {
     long long stride;
     const int* n_sym;
     int n_fixed;
-    const float* scores;
-    long long score_stride;
+    const unsigned char* hits;
+    long long hit_stride;
     int mode;              // 0 = process_batch order (sync callback before the symbol), 1 = process_with_soft_sync order,
                            // 2 = process(): no sync detection
     int dispatch_enabled;
@@ -468,15 +517,40 @@ struct FramerArgs {
     int* summary;          // [C][8]: n_msgs, nid_count, err_code, err_pos, err_a, err_b, err_duid, pool_used
 };
 
-__global__ void framer_machine_kernel(const FramerArgs a) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.C) return;
-    FramerState& s = a.st[c];
-    const int n = a.n_sym ? a.n_sym[c] : a.n_fixed;
+constexpr int FR_TILE = 256;          // symbols staged per step
+constexpr int FR_ROW = FR_TILE + 4;   // row pitch in bytes: 65 words, so the 32 channel rows sit in 32 different banks
+
+// One warp = 32 channels. Dibits and sync hits are staged tile by tile into shared memory with coalesced loads
+// (lanes along the symbol axis), then every lane walks its own channel's row; the scalar machine state lives in
+// registers for the whole call, only the assembler's bit buffer and the NAC counts are touched in global memory.
+__global__ void __launch_bounds__(32) framer_machine_kernel(const FramerArgs a) {
+    __shared__ unsigned char sd[32][FR_ROW];
+    __shared__ unsigned char sh[32][FR_ROW];
+    __shared__ unsigned char s_pw[128], s_lg[64];
+    gf_load_shared(s_pw, s_lg);
+    __syncwarp();
+    const int lane = threadIdx.x;
+    const int c0 = blockIdx.x * 32;
+    const int c = c0 + lane;
+    const bool live = c < a.C;
+    const int n = live ? (a.n_sym ? a.n_sym[c] : a.n_fixed) : 0;
+    int n_max = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, o));
+
+    FramerCore s;
     FramerOut o;
-    o.hdr = a.hdr + (size_t)c * a.max_msgs * 6;
-    o.hdr_sym = a.hdr_sym + (size_t)c * a.max_msgs;
-    o.pool = a.pool + (size_t)c * a.pool_cap;
+    if (live) {
+        s = a.st[c].core;
+        o.hdr = a.hdr + (size_t)c * a.max_msgs * 6;
+        o.hdr_sym = a.hdr_sym + (size_t)c * a.max_msgs;
+        o.pool = a.pool + (size_t)c * a.pool_cap;
+        o.asm_bits = a.st[c].asm_bits;
+        o.nac_seen = a.st[c].nac_seen;
+        o.nid_buf = a.st[c].nid_buf;
+    }
+    o.gf_pw = s_pw;
+    o.gf_lg = s_lg;
     o.max_msgs = a.max_msgs;
     o.pool_cap = a.pool_cap;
     o.n_msgs = 0;
@@ -484,37 +558,64 @@ __global__ void framer_machine_kernel(const FramerArgs a) {
     o.err_code = 0;
     o.err_a = o.err_b = o.err_duid = 0;
     o.dispatch_enabled = a.dispatch_enabled;
-    const unsigned char* d = a.dibits + (size_t)c * a.stride;
-    const float* sc = a.scores + (size_t)c * a.score_stride;
     int nid_count = 0, err_pos = -1;
-    for (int i = 0; i < n; ++i) {
-        const bool hit = (a.mode != 2) && (sc[i] > 60.0f);
-        if (a.mode == 0 && hit) {  // _sync_detected_callback (p25_framer.py:511-515)
-            s.sync_detected = 1;
-            s.nid_pointer = 0;
+    bool stopped = !live;
+
+    for (int base = 0; base < n_max; base += FR_TILE) {
+        __syncwarp();
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const int cr = c0 + r;
+            if (cr >= a.C) break;
+            const unsigned char* dr = a.dibits + (size_t)cr * a.stride + base;
+            const unsigned char* hr = a.hits + (size_t)cr * a.hit_stride + base;
+            const int nr = min(FR_TILE, (a.n_sym ? a.n_sym[cr] : a.n_fixed) - base);
+#pragma unroll
+            for (int k = 0; k < FR_TILE / 32; ++k) {
+                const int i = lane + 32 * k;
+                if (i < nr) {
+                    sd[r][i] = dr[i];
+                    sh[r][i] = (a.mode != 2) ? hr[i] : 0;
+                }
+            }
         }
-        const int r = process_symbol(s, o, d[i]);
-        if (r < 0) {
-            err_pos = i;
-            break;
-        }
-        nid_count += r;
-        if (a.mode == 1 && hit) {
-            s.sync_detected = 1;
-            s.nid_pointer = 0;
+        __syncwarp();
+        if (!stopped) {
+            const int lim = min(FR_TILE, n - base);
+            for (int i = 0; i < lim; ++i) {
+                const bool hit = sh[lane][i] != 0;
+                if (a.mode == 0 && hit) {  // _sync_detected_callback (p25_framer.py:511-515)
+                    s.sync_detected = 1;
+                    s.nid_pointer = 0;
+                }
+                const int r = process_symbol(s, o, sd[lane][i]);
+                if (r < 0) {
+                    err_pos = base + i;
+                    stopped = true;
+                    break;
+                }
+                nid_count += r;
+                if (a.mode == 1 && hit) {
+                    s.sync_detected = 1;
+                    s.nid_pointer = 0;
+                }
+            }
         }
     }
+    if (!live) return;
+    a.st[c].core = s;
     // batch order: the detector consumed the whole block before the machine ran (p25_framer.py:485-486).
     // per-symbol order: a symbol whose _process raised never reaches the detector (:448-455). process() never feeds it.
     if (a.mode != 2) {
         const int nh_sym = (a.mode == 1 && err_pos >= 0) ? err_pos : n;
         const float* sf = a.soft + (size_t)c * a.stride;
+        float* hist = a.st[c].hist;
         float nh[24];
         for (int k = 0; k < 24; ++k) {
             const int t = nh_sym - 24 + k;
-            nh[k] = (t >= 0) ? sf[t] : s.hist[24 + t];
+            nh[k] = (t >= 0) ? sf[t] : hist[24 + t];
         }
-        for (int k = 0; k < 24; ++k) s.hist[k] = nh[k];
+        for (int k = 0; k < 24; ++k) hist[k] = nh[k];
     }
     int* sm = a.summary + (size_t)c * 8;
     sm[0] = o.n_msgs;
@@ -530,9 +631,10 @@ __global__ void framer_machine_kernel(const FramerArgs a) {
 __global__ void framer_reset_kernel(FramerState* st, int C, int channel, int keep_tracker) {
     const int c = blockIdx.x;
     if (c >= C || (channel >= 0 && c != channel)) return;
-    FramerState& s = st[c];
+    FramerState& f = st[c];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 24; ++i) s.hist[i] = 0.f;
+        FramerCore& s = f.core;
+        for (int i = 0; i < 24; ++i) f.hist[i] = 0.f;
         s.sync_detected = 0;
         s.nid_pointer = 0;
         s.dibit_counter = 58;
@@ -550,13 +652,13 @@ __global__ void framer_reset_kernel(FramerState* st, int C, int channel, int kee
         }
     }
     if (!keep_tracker)
-        for (int i = threadIdx.x; i < 4096; i += blockDim.x) s.nac_seen[i] = 0;
+        for (int i = threadIdx.x; i < 4096; i += blockDim.x) f.nac_seen[i] = 0;
 }
 
 static bool g_tables_ready = false;
 static int ensure_tables() {
     if (g_tables_ready) return 0;
-    unsigned char pw[64], lg[64];
+    unsigned char pw[128], lg[64];
     memset(pw, 0, sizeof(pw));
     memset(lg, 0, sizeof(lg));
     int x = 1;
@@ -566,13 +668,31 @@ static int ensure_tables() {
         x <<= 1;
         if (x & 64) x ^= 0x43;
     }
-    pw[63] = 1;
+    for (int i = 63; i < 128; ++i) pw[i] = pw[i - 63];
     float sync[24];
     const unsigned long long pat = 0x5575F5FF77FFull;
     for (int i = 0; i < 24; ++i) sync[i] = (((pat >> ((23 - i) * 2)) & 3ull) == 1ull) ? 3.0f : -3.0f;
-    WC_CUDA(cudaMemcpyToSymbol(c_gf_pow, pw, sizeof(pw)));
-    WC_CUDA(cudaMemcpyToSymbol(c_gf_log, lg, sizeof(lg)));
+    // packed odd syndromes of every single bit, then of every byte value at every byte position
+    std::vector<uint4> tab(8 * 256);
+    for (int b = 0; b < 8; ++b)
+        for (int v = 0; v < 256; ++v) {
+            unsigned long long lo = 0ull;
+            unsigned int hi = 0u;
+            for (int k = 0; k < 8; ++k) {
+                if (!((v >> k) & 1)) continue;
+                const int p = 8 * b + k;  // bit 63 never occurs in a 63-bit word; its row stays consistent anyway
+                for (int j = 0; j < 11; ++j) {
+                    const unsigned long long e = pw[((2 * j + 1) * p) % 63];
+                    if (j < 10) lo ^= e << (6 * j);
+                    else hi ^= (unsigned int)e;
+                }
+            }
+            tab[b * 256 + v] = make_uint4((unsigned int)(lo & 0xffffffffull), (unsigned int)(lo >> 32), hi, 0u);
+        }
+    WC_CUDA(cudaMemcpyToSymbol(c_gf_pw, pw, sizeof(pw)));
+    WC_CUDA(cudaMemcpyToSymbol(c_gf_lg, lg, sizeof(lg)));
     WC_CUDA(cudaMemcpyToSymbol(c_fsync, sync, sizeof(sync)));
+    WC_CUDA(cudaMemcpyToSymbol(g_syn, tab.data(), sizeof(uint4) * tab.size()));
     g_tables_ready = true;
     return 0;
 }
@@ -584,7 +704,8 @@ using namespace wc;
 struct wc_p25framer {
     int C = 0;
     FramerState* d_state = nullptr;
-    float* d_scores = nullptr;   size_t scores_cap = 0;   // [C][n]
+    float* d_scores = nullptr;   size_t scores_cap = 0;   // [C][n] (host-call staging of the optional score output)
+    unsigned char* d_hits = nullptr; size_t hits_cap = 0;  // [C][n] score > 60
     // host-call staging
     void* d_soft = nullptr;      size_t soft_cap = 0;
     void* d_dibits = nullptr;    size_t dib_cap = 0;
@@ -674,6 +795,7 @@ void wc_p25framer_destroy(wc_p25framer* h) {
     cudaFree(h->d_summary);
     cudaFree(h->d_nsym);
     if (h->d_scores) cudaFree(h->d_scores);
+    if (h->d_hits) cudaFree(h->d_hits);
     if (h->d_soft) cudaFree(h->d_soft);
     if (h->d_dibits) cudaFree(h->d_dibits);
     if (h->d_hdr) cudaFree(h->d_hdr);
@@ -694,7 +816,7 @@ int wc_p25framer_reset(wc_p25framer* h, int channel, int full) {
 }
 
 int wc_p25framer_max_msgs(int n_symbols) { return n_symbols / 57 + 8; }
-int wc_p25framer_pool_bytes(int n_symbols) { return 2 * n_symbols + 2 * MAX_MSG_BITS; }
+int wc_p25framer_pool_bytes(int n_symbols) { return 2 * n_symbols + 2 * MAX_MSG_BITS + 4 * wc_p25framer_max_msgs(n_symbols); }
 
 int wc_p25framer_process(wc_p25framer* h, const float* soft_dev, const unsigned char* dibits_dev, long long chan_stride,
                          const int* n_sym_dev, int n_symbols, int mode, int dispatch_enabled, float* scores_dev,
@@ -706,14 +828,11 @@ int wc_p25framer_process(wc_p25framer* h, const float* soft_dev, const unsigned 
     WC_REQUIRE(mode >= 0 && mode <= 2, "wc_p25framer_process: bad mode %d", mode);
     cudaStream_t stream = (cudaStream_t)stream_v;
     const int nmax = n_symbols > 0 ? n_symbols : 1;
-    float* scores = scores_dev;
-    if (!scores) {
-        if (grow((void**)&h->d_scores, &h->scores_cap, sizeof(float) * (size_t)h->C * nmax)) return -2;
-        scores = h->d_scores;
-    }
-    if (n_symbols > 0) {
+    if (grow((void**)&h->d_hits, &h->hits_cap, (size_t)h->C * nmax)) return -2;
+    if (n_symbols > 0 && mode != 2) {
         dim3 grid((n_symbols + 127) / 128, h->C);
-        framer_score_kernel<<<grid, 128, 0, stream>>>(soft_dev, chan_stride, n_sym_dev, n_symbols, h->d_state, scores, nmax);
+        framer_score_kernel<<<grid, 128, 0, stream>>>(soft_dev, chan_stride, n_sym_dev, n_symbols, h->d_state, h->d_hits,
+                                                      scores_dev, nmax);
     }
     FramerArgs a;
     a.st = h->d_state;
@@ -722,8 +841,8 @@ int wc_p25framer_process(wc_p25framer* h, const float* soft_dev, const unsigned 
     a.stride = chan_stride;
     a.n_sym = n_sym_dev;
     a.n_fixed = n_symbols;
-    a.scores = scores;
-    a.score_stride = nmax;
+    a.hits = h->d_hits;
+    a.hit_stride = nmax;
     a.mode = mode;
     a.dispatch_enabled = dispatch_enabled;
     a.C = h->C;
@@ -760,7 +879,8 @@ int wc_p25framer_process_host(wc_p25framer* h, const float* soft_host, const uns
     }
     if (n_sym_host) WC_CUDA(cudaMemcpyAsync(h->d_nsym, n_sym_host, sizeof(int) * (size_t)C, cudaMemcpyHostToDevice, s));
     int rc = wc_p25framer_process(h, (const float*)h->d_soft, (const unsigned char*)h->d_dibits, nmax,
-                                  n_sym_host ? h->d_nsym : nullptr, n_symbols, mode, dispatch_enabled, h->d_scores,
+                                  n_sym_host ? h->d_nsym : nullptr, n_symbols, mode, dispatch_enabled,
+                                  scores_host ? h->d_scores : nullptr,
                                   (int*)h->d_hdr, (long long*)h->d_hsym, (unsigned char*)h->d_pool, h->d_summary, s);
     if (rc) return rc;
     WC_CUDA(cudaMemcpyAsync(summary_host, h->d_summary, sizeof(int) * 8 * (size_t)C, cudaMemcpyDeviceToHost, s));
@@ -781,18 +901,19 @@ int wc_p25framer_get_state(wc_p25framer* h, int channel, int* state12) {
     static FramerState tmp;  // ~6 KB: keep it off the stack
     WC_CUDA(cudaStreamSynchronize(h->stream));
     WC_CUDA(cudaMemcpy(&tmp, h->d_state + channel, sizeof(FramerState), cudaMemcpyDeviceToHost));
-    state12[0] = tmp.sync_detected;
-    state12[1] = tmp.nid_pointer;
-    state12[2] = tmp.dibit_counter;
-    state12[3] = tmp.status_counter;
-    state12[4] = tmp.asm_active;
-    state12[5] = tmp.asm_duid;
-    state12[6] = tmp.asm_nbits;
-    state12[7] = tmp.detected_nac;
-    state12[8] = tmp.detected_duid;
-    state12[9] = tmp.tracked_nac;
-    state12[10] = tmp.previous_duid;
-    state12[11] = (int)(tmp.symbols_total & 0x7fffffff);
+    const FramerCore& k = tmp.core;
+    state12[0] = k.sync_detected;
+    state12[1] = k.nid_pointer;
+    state12[2] = k.dibit_counter;
+    state12[3] = k.status_counter;
+    state12[4] = k.asm_active;
+    state12[5] = k.asm_duid;
+    state12[6] = k.asm_nbits;
+    state12[7] = k.detected_nac;
+    state12[8] = k.detected_duid;
+    state12[9] = k.tracked_nac;
+    state12[10] = k.previous_duid;
+    state12[11] = (int)(k.symbols_total & 0x7fffffff);
     return 0;
 }
 
