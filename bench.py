@@ -120,6 +120,25 @@ class ClockSampler:
         }
 
 
+def init_nccl(local_rank: int) -> None:
+    """NCCL prints its version banner on fd 1 when the communicator is created; the contract is ONE JSON line on
+    stdout, so fd 1 points at stderr until the first collective has run."""
+    import torch
+    import torch.distributed as dist
+
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        init_nccl(local_rank)
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 WORKLOAD = ("C5: 256-ch polyphase channelizer (M=256, 9 taps/arm, hop 128) + FM discriminator "
             "of every channel, 125 MS/s cf32, 50 ms chunks (6.25 M samples)")
 
@@ -188,7 +207,7 @@ def run_broadcast(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     N.init(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl(local_rank)
     n = args.bcast_chunks * CHUNK
     ch = PolyphaseChannelizer(FS, BW)
     bufs = [torch.empty((n,), dtype=torch.complex64, device="cuda") for _ in range(2)]
@@ -297,7 +316,7 @@ def main():
     torch.cuda.set_device(local_rank)
     N.init(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl(local_rank)
 
     def barrier():
         if world > 1:

@@ -148,6 +148,13 @@ int wc_c4fm_demod(wc_c4fm* h, const void* iq_dev, long long chan_stride, int n_s
                   float* soft_dev, int* n_sym_dev, int max_sym, void* stream);
 int wc_c4fm_demod_host(wc_c4fm* h, const void* iq_host /* [n_channels][n_samples] */, int n_samples,
                        unsigned char* dibits_host, float* soft_host, int* n_sym_host, int max_sym);
+/* C4FMDemodulator.demodulate_discriminator (c4fm.py:2817-2992): discriminator audio (radians/sample, float32)
+ * [C][chan_stride] -> dibits / soft / n_sym as above. first_host float64 [C] = audio[0] per channel in the caller's own
+ * precision (scales lfilter_zi on a channel's first call; may be NULL afterwards). Same object state as wc_c4fm_demod. */
+int wc_c4fm_demod_disc(wc_c4fm* h, const float* audio_dev, long long chan_stride, int n_samples, const double* first_host,
+                       unsigned char* dibits_dev, float* soft_dev, int* n_sym_dev, int max_sym, void* stream);
+int wc_c4fm_demod_disc_host(wc_c4fm* h, const float* audio_host, int n_samples, const double* first_host,
+                            unsigned char* dibits_host, float* soft_host, int* n_sym_host, int max_sym);
 /* stand-alone stages behind the helper classes backend/benchmark_dsp.py:17-114 times:
  * _FMDemodulator.demodulate (c4fm.py:324-395), _Interpolator.filter (:2204-2253), _SoftSyncDetector.process (:2306-2329) */
 int wc_c4fm_diffdemod(wc_c4fm* h, const void* iq_pairs_dev /* float2 [C][n] */, int n_samples, float* phases_dev, void* stream);

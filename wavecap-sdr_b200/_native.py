@@ -154,6 +154,8 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_c4fm_demod", i32, vp, vp, i64, i32, u8p, vp, vp, i32, vp)
     fn("wc_c4fm_demod_host", i32, vp, vp, i32, u8p, vp, vp, i32)
     fn("wc_c4fm_get_state", i32, vp, i32, vp)
+    fn("wc_c4fm_demod_disc", i32, vp, vp, i64, i32, vp, u8p, vp, vp, i32, vp)
+    fn("wc_c4fm_demod_disc_host", i32, vp, vp, i32, vp, u8p, vp, vp, i32)
     fn("wc_c4fm_diffdemod", i32, vp, vp, i32, vp, vp)
     fn("wc_c4fm_interp", i32, vp, i32, vp, vp, i32, vp, vp)
     fn("wc_c4fm_sync_scores", i32, vp, i32, vp, vp, vp, vp)

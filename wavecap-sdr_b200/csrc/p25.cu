@@ -205,6 +205,67 @@ __global__ void __launch_bounds__(256) c4fm_phase_kernel(const PhaseArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2': discriminator-audio front end of demodulate_discriminator (c4fm.py:2855-2874): RRC FIR in float64 with the
+// state scipy's lfilter carries (first call: zi = lfilter_zi(rrc) * audio[0], i.e. the filter behaves as if audio[0]
+// had been its input forever), phases = filtered * samples_per_symbol -> float32, into the scratch row and the ring.
+// ---------------------------------------------------------------------------------------------
+struct DiscArgs {
+    const float* x;        // [C][stride] discriminator audio (float32, as the reference casts it)
+    long long stride;
+    int n;
+    const double* hist;    // [C][hl] previous inputs, oldest first
+    double* new_hist;
+    const double* taps;    // [nt] float32 design promoted to float64
+    int nt;
+    int* init;             // [C] 0 until the first call
+    const double* first;   // [C] audio[0] of the first call (float64: the caller's own dtype)
+    double sps;
+    const C4State* st;
+    float* ph;             // [C][n]
+    float* ring;           // [C][65536]
+};
+
+__global__ void __launch_bounds__(256) disc_fir_kernel(const DiscArgs a) {
+    const int ch = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.n) return;
+    const int hl = a.nt - 1;
+    const float* xc = a.x + (long long)ch * a.stride;
+    const double* hc = a.hist + (long long)ch * hl;
+    const bool warm = a.init[ch] != 0;
+    const double x0 = a.first[ch];
+    double acc = 0.0;
+    for (int t = 0; t < a.nt; ++t) {
+        const int j = x - t;
+        const double v = (j >= 0) ? (double)xc[j] : (warm ? hc[hl + j] : x0);
+        acc = fma(a.taps[t], v, acc);
+    }
+    const float phase = (float)(acc * a.sps);
+    a.ph[(long long)ch * a.n + x] = phase;
+    if (x >= a.n - C4_RING) {
+        const C4State& s = a.st[ch];
+        const int slot = (s.ptr + s.shift_mod + 1 + x) & (C4_RING - 1);
+        a.ring[(long long)ch * C4_RING + slot] = phase;
+    }
+}
+
+// runs after disc_fir_kernel on the same stream
+__global__ void disc_hist_kernel(const DiscArgs a) {
+    const int ch = blockIdx.x;
+    const int hl = a.nt - 1;
+    const bool warm = a.init[ch] != 0;
+    for (int i = threadIdx.x; i < hl; i += blockDim.x) {
+        const int g = a.n - hl + i;
+        double v;
+        if (g >= 0) v = (double)a.x[(long long)ch * a.stride + g];
+        else v = warm ? a.hist[(long long)ch * hl + (hl + g)] : a.first[ch];
+        a.new_hist[(long long)ch * hl + i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) a.init[ch] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3: symbol extraction + sync loop, one warp per channel
 // ---------------------------------------------------------------------------------------------
 struct SyncArgs {
@@ -314,6 +375,10 @@ __device__ void c4_correction(const SyncCtx& c, double offset, int lane, double*
     gain_acc = shfl_d(ga, 0);
 }
 
+// DISC = true: the sync loop of C4FMDemodulator.demodulate_discriminator (c4fm.py:2896-2966) instead of demodulate's
+// (:2596-2807): same detectors and lagging path, but an accepted sync only re-times the sample point — no PLL / gain
+// correction, no re-slicing, no sync counter — and the optimiser is handed the sample point as its buffer offset.
+template <bool DISC>
 __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
     __shared__ double sterm[24];
     __shared__ float lagbuf[24 + 32];
@@ -492,7 +557,12 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
         k0 = ke + 1;
         if (idxe < 0) continue;  // shifted out of the buffer: the reference `continue`s (:2663-2664)
         const double extra = ul ? -a.k.lag_offset : 0.0;
-        const double off = ((double)idxe + 0.5) + extra;
+        if (DISC) {
+            since = 0;
+            if (fine) continue;  // since == 0: the 3600-symbol check below cannot fire either
+        }
+        // demodulate: buffer offset of the sync symbol; demodulate_discriminator passes self._sample_point (:2947-2949)
+        const double off = DISC ? sample_point : ((double)idxe + 0.5) + extra;
         // _timing_optimize_jit (:543-644)
         double step = fine ? sps / 16.0 : sps / 8.0;
         const double step_min = sps / 200.0;
@@ -519,6 +589,18 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
                     sR = c4_score(c, (off + adj) + step, lane, sterm);
                 }
             }
+        }
+        if (DISC) {
+            const double total = adj + extra;  // :2950-2958
+            if (fabs(total) >= 0.1) {
+                sample_point += total;
+                if (sample_point >= sps) sample_point -= sps;
+                else if (sample_point < 0.0) sample_point += sps;
+                fine = 1;
+                c.gain = 1.0;
+                ++n_events;
+            }
+            continue;
         }
         double pa, ga;
         c4_correction(c, off + adj, lane, sterm, pa, ga);
@@ -723,6 +805,12 @@ struct wc_c4fm {
     unsigned char* d_dib = nullptr; size_t dib_cap = 0;
     float* d_soft = nullptr;   size_t soft_cap = 0;
     int* d_nsym = nullptr;
+    // discriminator-audio entry (demodulate_discriminator): its own RRC state, untouched by reset() like the reference's
+    double* d_rrc64 = nullptr;
+    double* d_dhist[2] = {nullptr, nullptr};
+    int* d_dinit = nullptr;
+    double* d_dfirst = nullptr;
+    int dcur = 0;
     cudaStream_t stream = nullptr;
 };
 
@@ -841,6 +929,11 @@ void wc_c4fm_destroy(wc_c4fm* h) {
         cudaFree(h->d_tail[i]);
     }
     cudaFree(h->d_nsym);
+    if (h->d_rrc64) cudaFree(h->d_rrc64);
+    if (h->d_dhist[0]) cudaFree(h->d_dhist[0]);
+    if (h->d_dhist[1]) cudaFree(h->d_dhist[1]);
+    if (h->d_dinit) cudaFree(h->d_dinit);
+    if (h->d_dfirst) cudaFree(h->d_dfirst);
     if (h->d_filt) cudaFree(h->d_filt);
     if (h->d_ph) cudaFree(h->d_ph);
     if (h->d_idx) cudaFree(h->d_idx);
@@ -933,7 +1026,7 @@ int wc_c4fm_demod(wc_c4fm* h, const void* iq_dev, long long chan_stride, int n_s
     y.soft = soft_dev;
     y.idx = h->d_idx;
     y.n_sym = n_sym_dev;
-    c4fm_sync_kernel<<<C, 32, 0, s>>>(y);
+    c4fm_sync_kernel<false><<<C, 32, 0, s>>>(y);
     WC_CUDA(cudaGetLastError());
     h->cur ^= 1;
     return 0;
@@ -959,6 +1052,100 @@ int wc_c4fm_demod_host(wc_c4fm* h, const void* iq_host, int n_samples, unsigned 
     if (ensure_buf(&h->d_soft, &h->soft_cap, (size_t)C * max_sym)) return -2;
     WC_CUDA(cudaMemcpyAsync(h->d_in, iq_host, in_bytes, cudaMemcpyHostToDevice, h->stream));
     int rc = wc_c4fm_demod(h, h->d_in, n_samples, n_samples, h->d_dib, h->d_soft, h->d_nsym, max_sym, h->stream);
+    if (rc) return rc;
+    WC_CUDA(cudaMemcpyAsync(dibits_host, h->d_dib, (size_t)C * max_sym, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaMemcpyAsync(soft_host, h->d_soft, sizeof(float) * (size_t)C * max_sym, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaMemcpyAsync(n_sym_host, h->d_nsym, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+/* C4FMDemodulator.demodulate_discriminator (c4fm.py:2817-2992): discriminator audio float32 [C][chan_stride] ->
+ * dibits / soft / n_sym like wc_c4fm_demod. first_host: float64 [C], audio[0] of each channel in the caller's own
+ * precision — only read on a channel's first call (it scales lfilter_zi). Shares the phase buffer, sample point,
+ * equaliser and sync detectors with wc_c4fm_demod exactly like the two methods share one Python object. */
+int wc_c4fm_demod_disc(wc_c4fm* h, const float* audio_dev, long long chan_stride, int n_samples, const double* first_host,
+                       unsigned char* dibits_dev, float* soft_dev, int* n_sym_dev, int max_sym, void* stream_v) {
+    WC_REQUIRE(h && audio_dev && dibits_dev && soft_dev && n_sym_dev, "wc_c4fm_demod_disc: null argument");
+    WC_REQUIRE(n_samples >= 0 && chan_stride >= n_samples, "wc_c4fm_demod_disc: bad sizes");
+    cudaStream_t s = (cudaStream_t)stream_v;
+    const int C = h->C;
+    if (n_samples == 0) {
+        WC_CUDA(cudaMemsetAsync(n_sym_dev, 0, sizeof(int) * C, s));
+        return 0;
+    }
+    WC_REQUIRE(max_sym >= wc_c4fm_max_symbols(h, n_samples), "wc_c4fm_demod_disc: max_sym %d < %d", max_sym,
+               wc_c4fm_max_symbols(h, n_samples));
+    const int hl = h->n_rrc - 1;
+    if (!h->d_rrc64) {
+        std::vector<double> t(h->rrc.begin(), h->rrc.end());
+        WC_CUDA(cudaMalloc(&h->d_rrc64, sizeof(double) * h->n_rrc));
+        WC_CUDA(cudaMalloc(&h->d_dhist[0], sizeof(double) * (size_t)C * (hl > 0 ? hl : 1)));
+        WC_CUDA(cudaMalloc(&h->d_dhist[1], sizeof(double) * (size_t)C * (hl > 0 ? hl : 1)));
+        WC_CUDA(cudaMalloc(&h->d_dinit, sizeof(int) * (size_t)C));
+        WC_CUDA(cudaMalloc(&h->d_dfirst, sizeof(double) * (size_t)C));
+        WC_CUDA(cudaMemcpy(h->d_rrc64, t.data(), sizeof(double) * h->n_rrc, cudaMemcpyHostToDevice));
+        WC_CUDA(cudaMemset(h->d_dinit, 0, sizeof(int) * (size_t)C));
+        WC_CUDA(cudaMemset(h->d_dfirst, 0, sizeof(double) * (size_t)C));
+    }
+    if (first_host) WC_CUDA(cudaMemcpyAsync(h->d_dfirst, first_host, sizeof(double) * (size_t)C, cudaMemcpyHostToDevice, s));
+    if (ensure_buf(&h->d_ph, &h->ph_cap, (size_t)C * n_samples)) return -2;
+    if (ensure_buf(&h->d_idx, &h->idx_cap, (size_t)C * max_sym)) return -2;
+    DiscArgs d;
+    d.x = audio_dev;
+    d.stride = chan_stride;
+    d.n = n_samples;
+    d.hist = h->d_dhist[h->dcur];
+    d.new_hist = h->d_dhist[h->dcur ^ 1];
+    d.taps = h->d_rrc64;
+    d.nt = h->n_rrc;
+    d.init = h->d_dinit;
+    d.first = h->d_dfirst;
+    d.sps = h->k.sps;
+    d.st = h->d_state;
+    d.ph = h->d_ph;
+    d.ring = h->d_ring;
+    dim3 g((n_samples + 255) / 256, C);
+    disc_fir_kernel<<<g, 256, 0, s>>>(d);
+    disc_hist_kernel<<<C, 128, 0, s>>>(d);
+    h->dcur ^= 1;
+    SyncArgs y;
+    y.n = n_samples;
+    y.max_sym = max_sym;
+    y.k = h->k;
+    y.st = h->d_state;
+    y.ph = h->d_ph;
+    y.ring = h->d_ring;
+    y.dibits = dibits_dev;
+    y.soft = soft_dev;
+    y.idx = h->d_idx;
+    y.n_sym = n_sym_dev;
+    c4fm_sync_kernel<true><<<C, 32, 0, s>>>(y);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wc_c4fm_demod_disc_host(wc_c4fm* h, const float* audio_host, int n_samples, const double* first_host,
+                            unsigned char* dibits_host, float* soft_host, int* n_sym_host, int max_sym) {
+    WC_REQUIRE(h && audio_host && dibits_host && soft_host && n_sym_host, "wc_c4fm_demod_disc_host: null argument");
+    const int C = h->C;
+    if (n_samples <= 0) {
+        for (int c = 0; c < C; ++c) n_sym_host[c] = 0;
+        return 0;
+    }
+    const size_t in_bytes = sizeof(float) * (size_t)C * n_samples;
+    if (h->in_cap < in_bytes) {
+        if (h->d_in) cudaFree(h->d_in);
+        h->d_in = nullptr;
+        h->in_cap = 0;
+        WC_CUDA(cudaMalloc(&h->d_in, in_bytes));
+        h->in_cap = in_bytes;
+    }
+    if (ensure_buf(&h->d_dib, &h->dib_cap, (size_t)C * max_sym)) return -2;
+    if (ensure_buf(&h->d_soft, &h->soft_cap, (size_t)C * max_sym)) return -2;
+    WC_CUDA(cudaMemcpyAsync(h->d_in, audio_host, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    int rc = wc_c4fm_demod_disc(h, (const float*)h->d_in, n_samples, n_samples, first_host, h->d_dib, h->d_soft, h->d_nsym,
+                                max_sym, h->stream);
     if (rc) return rc;
     WC_CUDA(cudaMemcpyAsync(dibits_host, h->d_dib, (size_t)C * max_sym, cudaMemcpyDeviceToHost, h->stream));
     WC_CUDA(cudaMemcpyAsync(soft_host, h->d_soft, sizeof(float) * (size_t)C * max_sym, cudaMemcpyDeviceToHost, h->stream));

@@ -125,6 +125,24 @@ class C4FMBank:
         return dib, soft, cnt
 
 
+    def demodulate_discriminator(self, audio):
+        """audio: [n_channels][n] discriminator audio (any float dtype; cast to float32 like the reference, audio[:, 0]
+        kept in float64 for the first-call filter state) -> (dibits, soft, counts) as `demodulate`."""
+        a = np.asarray(audio)
+        assert a.ndim == 2 and a.shape[0] == self.n_channels, a.shape
+        n = int(a.shape[1])
+        ms = max(1, self.max_symbols(n))
+        dib = np.zeros((self.n_channels, ms), dtype=np.uint8)
+        soft = np.zeros((self.n_channels, ms), dtype=np.float32)
+        cnt = np.zeros((self.n_channels,), dtype=np.int32)
+        if n:
+            first = np.ascontiguousarray(a[:, 0].astype(np.float64))
+            x = np.ascontiguousarray(a.astype(np.float32))
+            N.check(N.lib().wc_c4fm_demod_disc_host(self._h, N.np_ptr(x), n, N.np_ptr(first), N.np_ptr(dib), N.np_ptr(soft),
+                                                    N.np_ptr(cnt), ms))
+        return dib, soft, cnt
+
+
 class C4FMDemodulator:
     """Drop-in for wavecapsdr.dsp.p25.c4fm.C4FMDemodulator (one channel)."""
 
@@ -153,9 +171,17 @@ class C4FMDemodulator:
         return float(self._bank.state(0)["pll"])
 
     def demodulate_discriminator(self, disc_audio):
-        """c4fm.py:2817-2992 — the discriminator-audio entry used only by the native IMBE voice decoder
-        (decoders/imbe_native.py:289), i.e. the voice path SURVEY §8f lists as "next". Not built: no CPU fallback."""
-        raise NotImplementedError("C4FMDemodulator.demodulate_discriminator (voice path, SURVEY §8f) is not built on the GPU")
+        """c4fm.py:2817-2992: discriminator audio (radians/sample) -> (dibits uint8, soft symbols float32). RRC in
+        float64 with scipy's carried state (first call: lfilter_zi * audio[0]), phases = filtered * sps, the shared
+        symbol recovery, and the discriminator flavour of the sync loop (csrc/p25.cu c4fm_sync_kernel<true>)."""
+        a = np.asarray(disc_audio)
+        if a.size == 0:
+            return np.array([], dtype=np.uint8), np.array([], dtype=np.float32)
+        if a.ndim > 1:  # "take first channel if stereo"
+            a = a[:, 0]
+        dib, soft, cnt = self._bank.demodulate_discriminator(a.reshape(1, -1))
+        n = int(cnt[0])
+        return dib[0, :n].copy(), soft[0, :n].copy()
 
     @property
     def _sync_count(self) -> int:
