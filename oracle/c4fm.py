@@ -424,6 +424,69 @@ class C4FMOracle:
         return dib, soft
 
 
+def _demodulate_discriminator(self, disc_audio):
+    """C4FMDemodulator.demodulate_discriminator (c4fm.py:2817-2992). The RRC state `rrc_state_disc` is created on the
+    first call as lfilter_zi(rrc) * audio[0] and is NOT touched by reset() (the reference only creates it via hasattr)."""
+    a = np.asarray(disc_audio)
+    if len(a) == 0:
+        return np.array([], dtype=np.uint8), np.array([], dtype=F32)
+    if a.ndim > 1:
+        a = a[:, 0]
+    if getattr(self, "rrc_state_disc", None) is None:
+        self.rrc_state_disc = signal.lfilter_zi(self.rrc, 1.0) * a[0]
+    y, self.rrc_state_disc = signal.lfilter(self.rrc, 1.0, a.astype(F32), zi=self.rrc_state_disc)
+    ph = y * self.sps
+    dib, soft, idxs = self.symbol_recovery(ph.astype(F32))
+    blen = len(self.buf)
+    for k in range(len(soft)):
+        self.since_sync += 1
+        sp = self.det.process(soft[k])
+        use_lag, extra = False, 0.0
+        if self.fine or idxs[k] < 0:
+            score = sp
+        else:
+            lag_pos = int(idxs[k]) - int(self.lag_offset)
+            sl = 0.0
+            if lag_pos >= 4:
+                lag_mu = 1.0 - (self.lag_offset - int(self.lag_offset))
+                lo = lag_pos - 4
+                if lo >= 0 and lag_pos < blen:
+                    v = self.lag_symbol(lo, lag_mu)
+                    sl = self.det_lag.process(v * F32(4.0 / np.pi))
+            if sl > sp and sl >= THRESH_DETECT:
+                score, use_lag, extra = sl, True, -self.lag_offset
+            else:
+                score = sp
+        if score >= THRESH_DETECT:
+            if idxs[k] < 0:
+                continue
+            self.since_sync = 0
+            if not self.fine:
+                # the optimiser is handed the sample point, not a buffer index (:2947-2949)
+                adj, _osc, _pa, _ga = timing_optimize(self.buf, self.sample_point, self.pll, self.gain, self.sps, False)
+                total = adj + extra
+                if abs(total) >= 0.1:
+                    self.sample_point += total
+                    if self.sample_point >= self.sps:
+                        self.sample_point -= self.sps
+                    elif self.sample_point < 0:
+                        self.sample_point += self.sps
+                    self.fine = True
+                    self.gain = 1.0
+        if self.since_sync > 3600:
+            self.fine = False
+            self.since_sync = 0
+    return dib, soft
+
+
+C4FMOracle.demodulate_discriminator = _demodulate_discriminator
+
+
+def discriminator_audio(iq):
+    """What the reference's callers feed demodulate_discriminator: np.diff(np.unwrap(np.angle(iq))) (float64)."""
+    return np.diff(np.unwrap(np.angle(np.asarray(iq, dtype=np.complex128))))
+
+
 # ---- synthetic C4FM source (SURVEY §8d C4; recipe of scripts/generate_p25_test_signal.py:84-168) ----
 
 def random_frames(rng, n_frames=6, payload=150, gap=40):

@@ -409,7 +409,43 @@ def gen_p25_framer():
     np.savez_compressed(os.path.join(OUT, "p25_framer.npz"), **out)
 
 
-GENERATORS = {"p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+
+def c4fm_disc_cases():
+    """(name, sample_rate, chunk, seed, audio dtype) — discriminator-audio entry, shared with the tests."""
+    return [("disc_48k_2400", 48000, 2400, 51, "float64"), ("disc_48k_7000", 48000, 7000, 52, "float32"),
+            ("disc_50k_2500", 50000, 2500, 53, "float64"), ("disc_48k_ragged", 48000, 1777, 54, "float64")]
+
+
+def gen_p25_c4fm_disc():
+    """C4FMDemodulator.demodulate_discriminator of the reference (c4fm.py:2817-2992) on np.diff(np.unwrap(np.angle(iq)))
+    of seeded C4FM signals, replaying fixed chunk sequences; the last case also calls reset() half way (which leaves the
+    discriminator RRC state alone in the reference)."""
+    from wavecapsdr.dsp.p25.c4fm import C4FMDemodulator
+    from oracle import c4fm as oc
+
+    out = {}
+    for name, fs, chunk, seed, dt in c4fm_disc_cases():
+        rng = np.random.default_rng(seed)
+        dib = oc.random_frames(rng, n_frames=10, payload=150, gap=40)
+        x = oc.modulate_c4fm(dib, fs, snr_db=25.0, cfo_hz=50.0, timing=0.4, seed=seed)
+        au = oc.discriminator_audio(x).astype(dt)
+        d = C4FMDemodulator(sample_rate=fs)
+        ds, ss, cnt = [], [], []
+        starts = list(range(0, len(au), chunk))
+        for j, s0 in enumerate(starts):
+            if name.endswith("ragged") and j == len(starts) // 2:
+                d.reset()
+            a, b = d.demodulate_discriminator(au[s0:s0 + chunk])
+            ds.append(a); ss.append(b); cnt.append(len(a))
+        out[name + "_audio"] = au
+        out[name + "_dibits"] = np.concatenate(ds).astype(np.uint8)
+        out[name + "_soft"] = np.concatenate(ss).astype(np.float32)
+        out[name + "_counts"] = np.array(cnt, dtype=np.int32)
+        out[name + "_state"] = np.array([float(d._fine_sync), d._sample_point, d._equalizer.gain, d._equalizer.pll])
+    np.savez_compressed(os.path.join(OUT, "p25_c4fm_disc.npz"), **out)
+
+
+GENERATORS = {"p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

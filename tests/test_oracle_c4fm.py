@@ -66,3 +66,26 @@ def test_oracle_matches_live_reference():
     d1, s1, c1 = replay(r, x, 3100)
     d2, s2, c2 = replay(o, x, 3100)
     assert np.array_equal(c1, c2) and np.array_equal(d1, d2) and np.array_equal(s1, s2)
+
+
+def test_discriminator_entry_matches_reference_golden():
+    """C4FMOracle.demodulate_discriminator vs the live reference's demodulate_discriminator (c4fm.py:2817-2992)."""
+    from oracle.make_golden import c4fm_disc_cases
+
+    g = np.load(golden_path("p25_c4fm_disc.npz"))
+    for name, fs, chunk, seed, dt in c4fm_disc_cases():
+        au = g[name + "_audio"]
+        assert au.dtype == np.dtype(dt)
+        o = C4FMOracle(sample_rate=fs)
+        ds, ss, cnt = [], [], []
+        starts = list(range(0, len(au), chunk))
+        for j, s0 in enumerate(starts):
+            if name.endswith("ragged") and j == len(starts) // 2:
+                o.reset()
+            a, b = o.demodulate_discriminator(au[s0:s0 + chunk])
+            ds.append(a); ss.append(b); cnt.append(len(a))
+        assert np.array_equal(np.array(cnt, np.int32), g[name + "_counts"]), name
+        assert np.array_equal(np.concatenate(ds), g[name + "_dibits"]), name
+        assert np.array_equal(np.concatenate(ss), g[name + "_soft"]), name
+        st = g[name + "_state"]
+        assert bool(st[0]) == bool(o.fine) and st[1] == o.sample_point and st[2] == o.gain and st[3] == o.pll, name
