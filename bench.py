@@ -149,7 +149,7 @@ def init_nccl(local_rank: int) -> None:
     saved = os.dup(1)
     os.dup2(2, 1)
     try:
-        init_nccl(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist.barrier()
         torch.cuda.synchronize()
     finally:
