@@ -334,7 +334,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     N.init(local_rank)
-    numa = bind_to_gpu_numa(local_rank) if world > 1 else "single rank: not bound"
+    numa = bind_to_gpu_numa(local_rank)  # after the cpu_baseline leg, which uses every host core
     if world > 1:
         init_nccl(local_rank)
 
