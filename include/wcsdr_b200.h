@@ -261,6 +261,29 @@ int wc_p25framer_process_host(wc_p25framer* h, const float* soft_host, const uns
                               long long* msg_sym_host, unsigned char* msg_bits_host, int* summary_host);
 int wc_p25framer_get_state(wc_p25framer* h, int channel, int* state12);
 
+/* ---- voice-channel discriminator path -----------------------------------------------------------
+ * wc_fm_discriminator: trunking/system.py:708-717 (VoiceRecorder.process_iq) np.diff(np.unwrap([last | np.angle(iq)])):
+ * iq complex64 (is_f64 0) / complex128 (1) [C][chan_stride] -> out float64 [C][n_samples]; last_phase float64 [C] in/out.
+ * wc_discdemod_*: decoders/p25.py:1105-1345 DiscriminatorDemodulator, one stateful demodulator per channel advanced by
+ * one call: audio float32 [C][chan_stride] -> dibits uint8 [C][max_sym] (+ the slicer input `output` as soft float32
+ * [C][max_sym], optional), n_sym int32 [C]. mmse_taps_129x8 / lpf_taps65: the reference's float32 tables
+ * (_generate_mmse_taps :1165-1186, _design_baseband_filter :1188-1195); NULL mmse taps = built inside. reset()
+ * (:1335-1345) keeps the input gain. */
+int wc_fm_discriminator(const void* iq_dev, int is_f64, long long chan_stride, int n_samples, int n_channels,
+                        double* last_phase_dev, double* out_dev, void* stream);
+typedef struct wc_discdemod wc_discdemod;
+int wc_discdemod_create(int n_channels, int sample_rate, int symbol_rate, const float* mmse_taps_129x8,
+                        const float* lpf_taps65, wc_discdemod** out);
+void wc_discdemod_destroy(wc_discdemod* h);
+int wc_discdemod_reset(wc_discdemod* h, int channel /* -1 = all */);
+int wc_discdemod_max_symbols(const wc_discdemod* h, int n_samples);
+int wc_discdemod_get_taps(const wc_discdemod* h, float* mmse_taps_129x8);
+int wc_discdemod_demod(wc_discdemod* h, const float* audio_dev, long long chan_stride, int n_samples,
+                       unsigned char* dibits_dev, float* soft_dev, int* n_sym_dev, int max_sym, void* stream);
+int wc_discdemod_demod_host(wc_discdemod* h, const float* audio_host, int n_samples, unsigned char* dibits_host,
+                            float* soft_host, int* n_sym_host, int max_sym);
+int wc_discdemod_get_state(wc_discdemod* h, int channel, double* state8);
+
 #ifdef __cplusplus
 }
 #endif

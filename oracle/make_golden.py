@@ -445,7 +445,49 @@ def gen_p25_c4fm_disc():
     np.savez_compressed(os.path.join(OUT, "p25_c4fm_disc.npz"), **out)
 
 
-GENERATORS = {"p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+
+def discriminator_cases():
+    """(name, chunk, seed, snr_db, cfo_hz) — 48 kS/s voice-channel IQ -> discriminator audio -> dibits; shared with the tests."""
+    return [("disc_2400", 2400, 61, 24.0, 80.0), ("disc_7000", 7000, 62, 20.0, -120.0), ("disc_999", 999, 63, 26.0, 30.0),
+            ("disc_60", 60, 64, 24.0, 0.0)]
+
+
+def gen_p25_discriminator():
+    """VoiceRecorder's discriminator (trunking/system.py:708-717, restated inline exactly as the reference writes it) and
+    decoders.p25.DiscriminatorDemodulator.demodulate of the live reference, replaying fixed chunk sequences; disc_999 also
+    calls reset() half way."""
+    from wavecapsdr.decoders.p25 import DiscriminatorDemodulator
+    from oracle import c4fm as oc
+
+    out = {}
+    for name, chunk, seed, snr, cfo in discriminator_cases():
+        rng = np.random.default_rng(seed)
+        dib = oc.random_frames(rng, n_frames=12, payload=150, gap=40)
+        x = oc.modulate_c4fm(dib, 48000, snr_db=snr, cfo_hz=cfo, timing=0.3, seed=seed)
+        d = DiscriminatorDemodulator(sample_rate=48000)
+        last = 0.0
+        aud, ds, cnt = [], [], []
+        starts = list(range(0, len(x), chunk))
+        for j, s0 in enumerate(starts):
+            iq = x[s0:s0 + chunk]
+            phase = np.angle(iq)
+            up = np.unwrap(np.concatenate([[last], phase]))
+            last = up[-1] if len(up) > 1 else last
+            au = np.diff(up)
+            if name == "disc_999" and j == len(starts) // 2:
+                d.reset()
+            a = d.demodulate(au.astype(np.float32))
+            aud.append(au); ds.append(a); cnt.append(len(a))
+        out[name + "_x"] = x
+        out[name + "_audio"] = np.concatenate(aud)
+        out[name + "_dibits"] = np.concatenate(ds).astype(np.uint8)
+        out[name + "_counts"] = np.array(cnt, dtype=np.int32)
+        out[name + "_state"] = np.array([float(d._input_gain), float(d._dc_estimate), float(d._symbol_clock),
+                                         float(d._symbol_spread), float(d._fine_freq_correction)])
+    np.savez_compressed(os.path.join(OUT, "p25_discriminator.npz"), **out)
+
+
+GENERATORS = {"p25_discriminator": gen_p25_discriminator, "p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

@@ -159,6 +159,27 @@ def framer():
          ms=round(ms, 3), mwords_per_s=round(65536 / ms / 1e3, 2))
 
 
+def voice():
+    """voice-channel FM discriminator + DiscriminatorDemodulator bank on device-resident IQ."""
+    from oracle.c4fm import modulate_c4fm, random_frames
+    from wavecap_sdr_b200.decoders.p25 import DiscriminatorBank
+    from wavecap_sdr_b200.trunking import VoiceDiscriminator
+
+    fs, n = 48000, 72000
+    rng = np.random.default_rng(2)
+    base = modulate_c4fm(random_frames(rng, n_frames=(n // 2140) + 2, payload=150, gap=40), fs, seed=2)[:n]
+    for Cn in (64, 1024):
+        x = torch.from_numpy(np.ascontiguousarray(np.tile(base, (Cn, 1)))).cuda()
+        disc, bank = VoiceDiscriminator(Cn), DiscriminatorBank(Cn, fs)
+        au = disc.process(x).to(torch.float32)
+        ms_a = timeit(lambda: disc.process(x), warm=2, iters=5)
+        ms_b = timeit(lambda: bank.demodulate(au), warm=2, iters=5)
+        emit(config=f"voice path, {Cn} ch, 48 kS/s: FM discriminator + DiscriminatorDemodulator", step=f"one call of {n} samples/channel (1.5 s)",
+             ms=round(ms_a + ms_b, 3), ms_discriminator=round(ms_a, 3), ms_demodulator=round(ms_b, 3),
+             channel_msps=round(Cn * n / (ms_a + ms_b) / 1e3, 2), channels_x_realtime=round(Cn * 1.5 / ((ms_a + ms_b) * 1e-3)),
+             alg_bytes=Cn * n * 8 + Cn * (n // 10))
+
+
 def ddc():
     from wavecap_sdr_b200.trunking import DDCBank
 
@@ -174,7 +195,7 @@ def ddc():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c1c2", "c3", "c4", "ddc", "framer"]
+    which = sys.argv[1:] or ["c1c2", "c3", "c4", "ddc", "framer", "voice"]
     t0 = time.time()
     if "c1c2" in which:
         c1_c2()
@@ -186,4 +207,6 @@ if __name__ == "__main__":
         ddc()
     if "framer" in which:
         framer()
+    if "voice" in which:
+        voice()
     print(json.dumps({"wall_s": round(time.time() - t0, 1), "hbm_peak_gbs": PEAK}), flush=True)

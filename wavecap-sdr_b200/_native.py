@@ -194,6 +194,16 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_p25framer_process", i32, vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp)
     fn("wc_p25framer_process_host", i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp)
     fn("wc_p25framer_get_state", i32, vp, i32, vp)
+    # voice-channel discriminator path
+    fn("wc_fm_discriminator", i32, vp, i32, i64, i32, i32, vp, vp, vp)
+    fn("wc_discdemod_create", i32, i32, i32, i32, vp, vp, P(vp))
+    fn("wc_discdemod_destroy", None, vp)
+    fn("wc_discdemod_reset", i32, vp, i32)
+    fn("wc_discdemod_max_symbols", i32, vp, i32)
+    fn("wc_discdemod_get_taps", i32, vp, vp)
+    fn("wc_discdemod_demod", i32, vp, vp, i64, i32, vp, vp, vp, i32, vp)
+    fn("wc_discdemod_demod_host", i32, vp, vp, i32, vp, vp, vp, i32)
+    fn("wc_discdemod_get_state", i32, vp, i32, vp)
     for extra in _EXTRA_DECLS:
         extra(l, fn)
 

@@ -24,7 +24,7 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3", "--expt-re
          "-Xptxas", "-v"] + (["-DWC_DEV_ABLATE"] if os.environ.get("WC_DEV_ABLATE") else [])
 # per-file extras: the P25 kernels replay the reference's float32/float64 operation order, so the
 # compiler must not contract a*b+c into one fused multiply-add there (explicit fma() calls stay fused)
-EXTRA = {"p25.cu": ["-fmad=false"], "cqpsk.cu": ["-fmad=false"]}
+EXTRA = {"p25.cu": ["-fmad=false"], "cqpsk.cu": ["-fmad=false"], "discdemod.cu": ["-fmad=false"]}
 
 
 def _newer(a: Path, b: Path) -> bool:

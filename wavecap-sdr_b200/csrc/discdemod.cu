@@ -1,0 +1,532 @@
+// Voice-channel discriminator path, batched over channels:
+//   wc_fm_discriminator   trunking/system.py:708-717   np.diff(np.unwrap([last_phase | np.angle(iq)])), last phase carried
+//   wc_discdemod_*        decoders/p25.py:1105-1345    DiscriminatorDemodulator.demodulate: auto gain, DC tracker,
+//                                                      65-tap low-pass (np.convolve 'same' per call), MMSE interpolation
+//                                                      with timing / spread / frequency loops, 4-level slicer
+//
+// The reference mixes Python floats with np.float32 values; under the NumPy >= 2 promotion rules every state variable
+// that has met a float32 IS a float32 (oracle/discriminator.py documents the flow and reports it via state_dtypes()).
+// Two variables keep a Python-float phase that matters numerically and is modelled explicitly:
+//   clock   a Python float (float64 accumulation of symbol_time) from construction / reset() until the first symbol,
+//           float32 afterwards;
+//   spread  the literal 1.6 / 2.4 whenever max(1.6, min(2.4, spread)) clamps — then `1.5 * spread` is a float64 product
+//           rounded once instead of a float32 product.
+// Compiled with -fmad=false: every float32 operation of the reference rounds on its own.
+//
+// Kernels: peak (parallel), gain + DC tracker (sequential per channel, 32 channels per warp, tiles staged through
+// shared memory), low-pass (parallel, float64 accumulation, rounded once), MMSE loop (sequential per channel, staged).
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/wcsdr_b200.h"
+#include "common.cuh"
+
+namespace wc {
+
+constexpr int DD_TAPS = 8, DD_STEPS = 128, DD_LPF = 65;
+constexpr int DD_TILE = 128;          // samples staged per step
+constexpr int DD_ROW = DD_TILE + 1;   // row pitch in floats: 32 channel rows in 32 different banks
+
+struct DDState {
+    double clock_d;     // valid while clock_py
+    float clock_f;
+    int clock_py;
+    float spread;       // float32 value (1.6f / 2.4f while spread_py)
+    int spread_py;      // 0 = float32, 1 = literal 1.6, 2 = literal 2.4
+    float fine, coarse, dc, gain;
+    float hist[DD_TAPS];
+    int hidx;
+    long long symbols;
+};
+
+struct DDConst {
+    double symbol_time;    // symbol_rate / sample_rate
+    float symbol_time_f;
+};
+
+__global__ void dd_peak_kernel(const float* __restrict__ x, long long stride, int n, float* __restrict__ peak) {
+    __shared__ float red[32];
+    const int ch = blockIdx.x;
+    const float* xc = x + (long long)ch * stride;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(xc[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) peak[ch] = m;
+    }
+}
+
+// auto gain (p25.py:1213-1222) and DC removal (:1224-1229); y = x*gain - dc, float32 throughout
+__global__ void __launch_bounds__(32) dd_dc_kernel(const float* __restrict__ x, long long stride, int n, int C,
+                                                   const float* __restrict__ peak, DDState* __restrict__ st, float* __restrict__ y) {
+    __shared__ float tile[32][DD_ROW];
+    const int lane = threadIdx.x;
+    const int c0 = blockIdx.x * 32;
+    const int c = c0 + lane;
+    const bool live = c < C;
+    float gain = 1.f, dc = 0.f;
+    if (live) {
+        gain = st[c].gain;
+        dc = st[c].dc;
+        const float pk = peak[c];
+        if (n > 100 && pk > 0.01f)
+            gain = __fadd_rn(__fmul_rn(gain, 0.9f), __fmul_rn(__fdiv_rn(3.0f, pk), 0.1f));
+    }
+    for (int base = 0; base < n; base += DD_TILE) {
+        const int lim = min(DD_TILE, n - base);
+        __syncwarp();
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            if (c0 + r >= C) break;
+            const float* xr = x + (long long)(c0 + r) * stride + base;
+            for (int i = lane; i < lim; i += 32) tile[r][i] = xr[i];
+        }
+        __syncwarp();
+        if (live) {
+            for (int i = 0; i < lim; ++i) {
+                const float v = __fmul_rn(tile[lane][i], gain);
+                dc = __fadd_rn(__fmul_rn(dc, 0.999f), __fmul_rn(v, 0.001f));
+                tile[lane][i] = __fsub_rn(v, dc);
+            }
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            if (c0 + r >= C) break;
+            float* yr = y + (long long)(c0 + r) * n + base;
+            for (int i = lane; i < lim; i += 32) yr[i] = tile[r][i];
+        }
+    }
+    if (live) {
+        st[c].gain = gain;
+        st[c].dc = dc;
+    }
+}
+
+// np.convolve(x, h, 'same') for the odd-length kernel: out[i] = sum_k h[k] x[i + 32 - k], zero outside the call;
+// skipped (copy) when the call is shorter than the filter (p25.py:1231-1233)
+__global__ void __launch_bounds__(256) dd_lpf_kernel(const float* __restrict__ x, int n, const double* __restrict__ h,
+                                                     float* __restrict__ y) {
+    __shared__ double sh[DD_LPF];
+    if (threadIdx.x < DD_LPF) sh[threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+    const int ch = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* xc = x + (long long)ch * n;
+    if (n < DD_LPF) {
+        y[(long long)ch * n + i] = xc[i];
+        return;
+    }
+    double acc = 0.0;
+#pragma unroll 5
+    for (int k = 0; k < DD_LPF; ++k) {
+        const int j = i + 32 - k;
+        if (j >= 0 && j < n) acc += sh[k] * (double)xc[j];
+    }
+    y[(long long)ch * n + i] = (float)acc;
+}
+
+__device__ __forceinline__ float dd_interp(const float* __restrict__ taps, const float* hist, int hidx, int imu) {
+    // p25.py:1238-1248: float32 products summed in order into a float32 accumulator (0.0 + first product = that product)
+    float acc = __fmul_rn(taps[imu * DD_TAPS], hist[hidx & 7]);
+#pragma unroll
+    for (int i = 1; i < DD_TAPS; ++i) acc = __fadd_rn(acc, __fmul_rn(taps[imu * DD_TAPS + i], hist[(hidx + i) & 7]));
+    return acc;
+}
+
+// _mmse_timing_recovery (p25.py:1250-1333)
+__global__ void __launch_bounds__(32) dd_mmse_kernel(const float* __restrict__ x, int n, int C, DDConst k,
+                                                     const float* __restrict__ taps_g, DDState* __restrict__ st,
+                                                     unsigned char* __restrict__ dibits, float* __restrict__ soft_out,
+                                                     int max_sym, int* __restrict__ n_sym) {
+    __shared__ float tile[32][DD_ROW];
+    __shared__ float taps[(DD_STEPS + 1) * DD_TAPS];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < (DD_STEPS + 1) * DD_TAPS; i += 32) taps[i] = taps_g[i];
+    const int c0 = blockIdx.x * 32;
+    const int c = c0 + lane;
+    const bool live = c < C;
+    DDState s;
+    float hist[DD_TAPS];
+    if (live) {
+        s = st[c];
+#pragma unroll
+        for (int i = 0; i < DD_TAPS; ++i) hist[i] = s.hist[i];
+    } else {
+        memset(&s, 0, sizeof(s));
+#pragma unroll
+        for (int i = 0; i < DD_TAPS; ++i) hist[i] = 0.f;
+    }
+    int hidx = s.hidx;
+    int count = 0;
+    unsigned char* dout = dibits + (long long)c * max_sym;
+    float* sout = soft_out ? soft_out + (long long)c * max_sym : nullptr;
+    for (int base = 0; base < n; base += DD_TILE) {
+        const int lim = min(DD_TILE, n - base);
+        __syncwarp();
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            if (c0 + r >= C) break;
+            const float* xr = x + (long long)(c0 + r) * n + base;
+            for (int i = lane; i < lim; i += 32) tile[r][i] = xr[i];
+        }
+        __syncwarp();
+        if (!live) continue;
+        for (int i = 0; i < lim; ++i) {
+            // history ring with a compile-time-indexable copy: rotate instead of indexing dynamically
+            hist[hidx & 7] = tile[lane][i];
+            hidx = (hidx + 1) & 7;
+            bool tick;
+            if (s.clock_py) {
+                s.clock_d += k.symbol_time;
+                tick = s.clock_d > 1.0;
+            } else {
+                s.clock_f = __fadd_rn(s.clock_f, k.symbol_time_f);
+                tick = s.clock_f > 1.0f;
+            }
+            if (!tick) continue;
+            int imu, imu1;
+            if (s.clock_py) {
+                s.clock_d -= 1.0;
+                double mu = s.clock_d / k.symbol_time;
+                if (1.0 < mu) mu = 1.0;
+                imu = min((int)rint(mu * 128.0), DD_STEPS);
+                double m1 = mu + 0.0078125;
+                if (1.0 < m1) m1 = 1.0;
+                imu1 = min((int)rint(m1 * 128.0), DD_STEPS);
+            } else {
+                s.clock_f = __fsub_rn(s.clock_f, 1.0f);
+                const float mu = __fdiv_rn(s.clock_f, k.symbol_time_f);
+                if (1.0f < mu) {
+                    imu = DD_STEPS;   // min() returned the Python float 1.0
+                    imu1 = DD_STEPS;
+                } else {
+                    imu = min((int)rintf(__fmul_rn(mu, 128.0f)), DD_STEPS);
+                    const float m1 = __fadd_rn(mu, 0.0078125f);
+                    imu1 = (1.0f < m1) ? DD_STEPS : min((int)rintf(__fmul_rn(m1, 128.0f)), DD_STEPS);
+                }
+            }
+            float y = dd_interp(taps, hist, hidx, imu);
+            float y1 = dd_interp(taps, hist, hidx, imu1);
+            y = __fsub_rn(y, s.fine);
+            y1 = __fsub_rn(y1, s.fine);
+            const float sp = s.spread;
+            const float soft = __fdiv_rn(__fmul_rn(2.0f, y), sp);
+            const float c15 = (s.spread_py == 1) ? (float)(1.5 * 1.6) : (s.spread_py == 2) ? (float)(1.5 * 2.4) : __fmul_rn(1.5f, sp);
+            const float c05 = __fmul_rn(0.5f, sp);
+            float err;
+            if (y < -sp) err = __fadd_rn(y, c15);
+            else if (y < 0.0f) err = __fadd_rn(y, c05);
+            else if (y < sp) err = __fsub_rn(y, c05);
+            else err = __fsub_rn(y, c15);
+            float ns;
+            if (y < -sp || y >= sp) ns = __fsub_rn(sp, __fmul_rn(__fmul_rn(err, 0.5f), 0.01f));
+            else if (y < 0.0f) ns = __fsub_rn(sp, __fmul_rn(err, 0.01f));
+            else ns = __fadd_rn(sp, __fmul_rn(err, 0.01f));
+            // max(1.6, min(2.4, spread)): the literals win when the float32 value reaches them
+            if (!(ns < 2.4f)) {
+                s.spread = 2.4f;
+                s.spread_py = 2;
+            } else if (!(ns > 1.6f)) {
+                s.spread = 1.6f;
+                s.spread_py = 1;
+            } else {
+                s.spread = ns;
+                s.spread_py = 0;
+            }
+            const float cf = s.clock_py ? (float)s.clock_d : s.clock_f;
+            const float tadj = __fmul_rn(err, 0.025f);
+            s.clock_f = (y1 < y) ? __fadd_rn(cf, tadj) : __fsub_rn(cf, tadj);
+            s.clock_py = 0;
+            s.coarse = __fadd_rn(s.coarse, __fmul_rn(__fsub_rn(s.fine, s.coarse), 0.00125f));
+            s.fine = __fadd_rn(s.fine, __fmul_rn(err, 0.125f));
+            if (count < max_sym) {
+                dout[count] = (soft < -2.0f) ? 3 : (soft < 0.0f) ? 2 : (soft < 2.0f) ? 0 : 1;
+                if (sout) sout[count] = soft;
+            }
+            ++count;
+        }
+    }
+    if (live) {
+        s.hidx = hidx;
+        s.symbols += count;
+#pragma unroll
+        for (int i = 0; i < DD_TAPS; ++i) s.hist[i] = hist[i];
+        st[c] = s;
+        n_sym[c] = min(count, max_sym);
+    }
+}
+
+__global__ void dd_reset_kernel(DDState* st, int C, int channel, int keep_gain) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C || (channel >= 0 && c != channel)) return;
+    DDState& s = st[c];
+    s.clock_d = 0.0;
+    s.clock_f = 0.f;
+    s.clock_py = 1;
+    s.spread = 2.0f;
+    s.spread_py = 0;
+    s.fine = s.coarse = s.dc = 0.f;
+    if (!keep_gain) s.gain = 1.0f;   // reset() leaves _input_gain alone (p25.py:1335-1345)
+    for (int i = 0; i < DD_TAPS; ++i) s.hist[i] = 0.f;
+    s.hidx = 0;
+    s.symbols = 0;
+}
+
+// np.diff(np.unwrap([last | angle(iq)])): wrapped phase step per sample, float64 (trunking/system.py:708-717)
+template <typename T2>
+__global__ void fm_disc_kernel(const T2* __restrict__ iq, long long stride, int n, double* __restrict__ last, double* __restrict__ out,
+                               double* __restrict__ new_last) {
+    const int ch = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T2* x = iq + (long long)ch * stride;
+    // np.angle of complex64 is float32 (correctly rounded here; numpy's SIMD arctan2 may be 1 ulp off), of complex128 float64
+    const bool f32 = sizeof(x[0].x) == 4;
+    double cur = atan2((double)x[i].y, (double)x[i].x);
+    if (f32) cur = (double)(float)cur;
+    double prev = last[ch];
+    if (i > 0) {
+        prev = atan2((double)x[i - 1].y, (double)x[i - 1].x);
+        if (f32) prev = (double)(float)prev;
+    }
+    const double dd = cur - prev;
+    // numpy.unwrap (period 2 pi, discont pi): ddmod = mod(dd + pi, 2 pi) - pi, with -pi -> +pi for positive steps;
+    // the correction only applies where |dd| >= pi
+    const double PI = 3.141592653589793, TWO_PI = 6.283185307179586;
+    double r = fmod(dd + PI, TWO_PI);
+    if (r < 0.0) r += TWO_PI;   // Python's mod has the sign of the divisor
+    double ddmod = r - PI;
+    if (ddmod == -PI && dd > 0.0) ddmod = PI;
+    out[(long long)ch * n + i] = (fabs(dd) < PI) ? dd : ddmod;
+    if (i == n - 1) new_last[ch] = cur;
+}
+
+// MMSE interpolation table of the reference (p25.py:1165-1186), float32
+static void dd_build_taps(std::vector<float>& taps) {
+    taps.assign((DD_STEPS + 1) * DD_TAPS, 0.f);
+    for (int step = 0; step <= DD_STEPS; ++step) {
+        const double mu = (double)step / DD_STEPS;
+        for (int tap = 0; tap < DD_TAPS; ++tap) {
+            const double t = tap - 3 - mu;
+            float v;
+            if (fabs(t) < 1e-6) v = 1.0f;
+            else {
+                const double sinc = sin(M_PI * t) / (M_PI * t);
+                const double win = (fabs(t) < 4) ? 0.5 * (1 + cos(M_PI * t / 4)) : 0.0;
+                v = (float)(sinc * win);
+            }
+            taps[step * DD_TAPS + tap] = v;
+        }
+        // np.sum of 8 float32 values (pairwise == sequential below 8 elements is NOT guaranteed; numpy adds the 8-element
+        // row with its unrolled pairwise kernel: ((a0+a1)+(a2+a3)) + ((a4+a5)+(a6+a7)))
+        const float* r = &taps[step * DD_TAPS];
+        const float tot = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        if (tot > 0)
+            for (int tap = 0; tap < DD_TAPS; ++tap) taps[step * DD_TAPS + tap] /= tot;
+    }
+}
+
+}  // namespace wc
+
+using namespace wc;
+
+struct wc_discdemod {
+    int C = 0;
+    int sample_rate = 0, symbol_rate = 0;
+    DDConst k;
+    DDState* d_state = nullptr;
+    float* d_taps = nullptr;
+    double* d_lpf = nullptr;
+    float* d_peak = nullptr;
+    float* d_a = nullptr;  size_t a_cap = 0;   // [C][n] after DC removal
+    float* d_b = nullptr;  size_t b_cap = 0;   // [C][n] after the low-pass
+    // host-call staging
+    float* d_in = nullptr; size_t in_cap = 0;
+    unsigned char* d_dib = nullptr; size_t dib_cap = 0;
+    float* d_soft = nullptr; size_t soft_cap = 0;
+    int* d_nsym = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+template <typename T>
+static int dd_ensure(T** p, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    WC_CUDA(cudaMalloc((void**)p, need * sizeof(T)));
+    *cap = need;
+    return 0;
+}
+
+extern "C" {
+
+int wc_discdemod_create(int n_channels, int sample_rate, int symbol_rate, const float* mmse_taps_129x8,
+                        const float* lpf_taps65, wc_discdemod** out) {
+    WC_REQUIRE(out != nullptr, "wc_discdemod_create: out is null");
+    WC_REQUIRE(n_channels >= 1 && sample_rate > 0 && symbol_rate > 0 && symbol_rate < sample_rate,
+               "wc_discdemod_create: bad parameters");
+    WC_REQUIRE(lpf_taps65 != nullptr, "wc_discdemod_create: the 65-tap low-pass design is required (scipy firwin on the host)");
+    wc_discdemod* h = new wc_discdemod();
+    h->C = n_channels;
+    h->sample_rate = sample_rate;
+    h->symbol_rate = symbol_rate;
+    h->k.symbol_time = (double)symbol_rate / (double)sample_rate;
+    h->k.symbol_time_f = (float)h->k.symbol_time;
+    std::vector<float> taps;
+    if (mmse_taps_129x8) taps.assign(mmse_taps_129x8, mmse_taps_129x8 + (DD_STEPS + 1) * DD_TAPS);
+    else dd_build_taps(taps);
+    std::vector<double> lpf(DD_LPF);
+    for (int i = 0; i < DD_LPF; ++i) lpf[i] = (double)lpf_taps65[i];
+    const size_t C = (size_t)n_channels;
+    bool ok = cudaMalloc(&h->d_state, sizeof(DDState) * C) == cudaSuccess &&
+              cudaMalloc(&h->d_taps, sizeof(float) * taps.size()) == cudaSuccess &&
+              cudaMalloc(&h->d_lpf, sizeof(double) * DD_LPF) == cudaSuccess &&
+              cudaMalloc(&h->d_peak, sizeof(float) * C) == cudaSuccess &&
+              cudaMalloc(&h->d_nsym, sizeof(int) * C) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMemcpy(h->d_taps, taps.data(), sizeof(float) * taps.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(h->d_lpf, lpf.data(), sizeof(double) * DD_LPF, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        set_error("wc_discdemod_create: CUDA allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return -2;
+    }
+    cudaMemset(h->d_state, 0, sizeof(DDState) * C);
+    dd_reset_kernel<<<(n_channels + 127) / 128, 128, 0, h->stream>>>(h->d_state, n_channels, -1, 0);
+    cudaStreamSynchronize(h->stream);
+    *out = h;
+    return 0;
+}
+
+void wc_discdemod_destroy(wc_discdemod* h) {
+    if (!h) return;
+    cudaFree(h->d_state);
+    cudaFree(h->d_taps);
+    cudaFree(h->d_lpf);
+    cudaFree(h->d_peak);
+    cudaFree(h->d_nsym);
+    if (h->d_a) cudaFree(h->d_a);
+    if (h->d_b) cudaFree(h->d_b);
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->d_dib) cudaFree(h->d_dib);
+    if (h->d_soft) cudaFree(h->d_soft);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int wc_discdemod_reset(wc_discdemod* h, int channel) {
+    WC_REQUIRE(h != nullptr, "wc_discdemod_reset: null handle");
+    WC_REQUIRE(channel >= -1 && channel < h->C, "wc_discdemod_reset: channel %d out of range", channel);
+    dd_reset_kernel<<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->d_state, h->C, channel, 1);
+    WC_CUDA(cudaGetLastError());
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int wc_discdemod_max_symbols(const wc_discdemod* h, int n_samples) {
+    if (!h || n_samples <= 0) return 0;
+    // the timing loop moves the clock by at most 0.025 * 3.6 per symbol: 1.2x the nominal rate is a safe bound
+    return (int)(1.2 * (double)n_samples * h->k.symbol_time) + 8;
+}
+
+int wc_discdemod_get_taps(const wc_discdemod* h, float* mmse_taps_129x8) {
+    WC_REQUIRE(h && mmse_taps_129x8, "wc_discdemod_get_taps: null argument");
+    WC_CUDA(cudaMemcpy(mmse_taps_129x8, h->d_taps, sizeof(float) * (DD_STEPS + 1) * DD_TAPS, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int wc_discdemod_demod(wc_discdemod* h, const float* audio_dev, long long chan_stride, int n_samples,
+                       unsigned char* dibits_dev, float* soft_dev, int* n_sym_dev, int max_sym, void* stream_v) {
+    WC_REQUIRE(h && audio_dev && dibits_dev && n_sym_dev, "wc_discdemod_demod: null argument");
+    WC_REQUIRE(n_samples >= 0 && chan_stride >= n_samples, "wc_discdemod_demod: bad sizes");
+    cudaStream_t s = (cudaStream_t)stream_v;
+    const int C = h->C;
+    if (n_samples == 0) {
+        WC_CUDA(cudaMemsetAsync(n_sym_dev, 0, sizeof(int) * C, s));
+        return 0;
+    }
+    WC_REQUIRE(max_sym >= wc_discdemod_max_symbols(h, n_samples), "wc_discdemod_demod: max_sym %d < %d", max_sym,
+               wc_discdemod_max_symbols(h, n_samples));
+    if (dd_ensure(&h->d_a, &h->a_cap, (size_t)C * n_samples)) return -2;
+    if (dd_ensure(&h->d_b, &h->b_cap, (size_t)C * n_samples)) return -2;
+    dd_peak_kernel<<<C, 256, 0, s>>>(audio_dev, chan_stride, n_samples, h->d_peak);
+    dd_dc_kernel<<<(C + 31) / 32, 32, 0, s>>>(audio_dev, chan_stride, n_samples, C, h->d_peak, h->d_state, h->d_a);
+    dim3 lg((n_samples + 255) / 256, C);
+    dd_lpf_kernel<<<lg, 256, 0, s>>>(h->d_a, n_samples, h->d_lpf, h->d_b);
+    dd_mmse_kernel<<<(C + 31) / 32, 32, 0, s>>>(h->d_b, n_samples, C, h->k, h->d_taps, h->d_state, dibits_dev, soft_dev,
+                                                max_sym, n_sym_dev);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wc_discdemod_demod_host(wc_discdemod* h, const float* audio_host, int n_samples, unsigned char* dibits_host,
+                            float* soft_host, int* n_sym_host, int max_sym) {
+    WC_REQUIRE(h && audio_host && dibits_host && n_sym_host, "wc_discdemod_demod_host: null argument");
+    const int C = h->C;
+    if (n_samples <= 0) {
+        for (int c = 0; c < C; ++c) n_sym_host[c] = 0;
+        return 0;
+    }
+    if (dd_ensure(&h->d_in, &h->in_cap, (size_t)C * n_samples)) return -2;
+    if (dd_ensure(&h->d_dib, &h->dib_cap, (size_t)C * max_sym)) return -2;
+    if (dd_ensure(&h->d_soft, &h->soft_cap, (size_t)C * max_sym)) return -2;
+    WC_CUDA(cudaMemcpyAsync(h->d_in, audio_host, sizeof(float) * (size_t)C * n_samples, cudaMemcpyHostToDevice, h->stream));
+    int rc = wc_discdemod_demod(h, h->d_in, n_samples, n_samples, h->d_dib, h->d_soft, h->d_nsym, max_sym, h->stream);
+    if (rc) return rc;
+    WC_CUDA(cudaMemcpyAsync(dibits_host, h->d_dib, (size_t)C * max_sym, cudaMemcpyDeviceToHost, h->stream));
+    if (soft_host)
+        WC_CUDA(cudaMemcpyAsync(soft_host, h->d_soft, sizeof(float) * (size_t)C * max_sym, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaMemcpyAsync(n_sym_host, h->d_nsym, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+/* state8 = {input gain, dc estimate, symbol clock, symbol spread, fine freq correction, coarse, clock is still the
+ * Python float (1/0), symbols produced since reset} */
+int wc_discdemod_get_state(wc_discdemod* h, int channel, double* state8) {
+    WC_REQUIRE(h && state8, "wc_discdemod_get_state: null argument");
+    WC_REQUIRE(channel >= 0 && channel < h->C, "wc_discdemod_get_state: channel %d out of range", channel);
+    DDState s;
+    WC_CUDA(cudaStreamSynchronize(h->stream));
+    WC_CUDA(cudaMemcpy(&s, h->d_state + channel, sizeof(DDState), cudaMemcpyDeviceToHost));
+    state8[0] = s.gain;
+    state8[1] = s.dc;
+    state8[2] = s.clock_py ? s.clock_d : (double)s.clock_f;
+    state8[3] = (s.spread_py == 1) ? 1.6 : (s.spread_py == 2) ? 2.4 : (double)s.spread;
+    state8[4] = s.fine;
+    state8[5] = s.coarse;
+    state8[6] = s.clock_py;
+    state8[7] = (double)s.symbols;
+    return 0;
+}
+
+/* trunking/system.py:708-717. iq complex64 (is_f64 = 0) or complex128 (1) [C][chan_stride]; last_phase_dev float64 [C] in/out
+ * (0.0 initially); out float64 [C][n_samples]. */
+int wc_fm_discriminator(const void* iq_dev, int is_f64, long long chan_stride, int n_samples, int n_channels,
+                        double* last_phase_dev, double* out_dev, void* stream_v) {
+    WC_REQUIRE(iq_dev && last_phase_dev && out_dev, "wc_fm_discriminator: null argument");
+    WC_REQUIRE(n_channels >= 1 && n_samples >= 0 && chan_stride >= n_samples, "wc_fm_discriminator: bad sizes");
+    if (n_samples == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    double* tmp = nullptr;
+    WC_CUDA(cudaMallocAsync((void**)&tmp, sizeof(double) * n_channels, s));
+    dim3 g((n_samples + 255) / 256, n_channels);
+    if (is_f64) fm_disc_kernel<double2><<<g, 256, 0, s>>>((const double2*)iq_dev, chan_stride, n_samples, last_phase_dev, out_dev, tmp);
+    else fm_disc_kernel<float2><<<g, 256, 0, s>>>((const float2*)iq_dev, chan_stride, n_samples, last_phase_dev, out_dev, tmp);
+    WC_CUDA(cudaGetLastError());
+    WC_CUDA(cudaMemcpyAsync(last_phase_dev, tmp, sizeof(double) * n_channels, cudaMemcpyDeviceToDevice, s));
+    WC_CUDA(cudaFreeAsync(tmp, s));
+    return 0;
+}
+
+}  // extern "C"

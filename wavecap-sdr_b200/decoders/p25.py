@@ -144,3 +144,121 @@ class CQPSKDemodulator:
     @property
     def _symbol_clock(self) -> float:
         return float(self._bank.state(0)["symbol_clock"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# DiscriminatorDemodulator (decoders/p25.py:1105-1345) on the GPU: csrc/discdemod.cu
+# ---------------------------------------------------------------------------------------------------
+def _discriminator_lpf(sample_rate: int) -> np.ndarray:
+    """_design_baseband_filter (decoders/p25.py:1188-1195): firwin(65, 5200 Hz, hamming), float32."""
+    from scipy import signal
+
+    cutoff = min(5200 / (sample_rate / 2), 0.99)
+    return np.asarray(signal.firwin(65, cutoff, window="hamming"), dtype=np.float32)
+
+
+class DiscriminatorBank:
+    """C stateful discriminator-audio demodulators advanced by one call: audio [C][n] -> (dibits uint8 [C][max_sym],
+    soft float32 [C][max_sym] (the slicer input), counts int32 [C])."""
+
+    def __init__(self, n_channels: int, sample_rate: int = 48000, symbol_rate: int = 4800):
+        N.ensure_init()
+        self.n_channels, self.sample_rate, self.symbol_rate = int(n_channels), int(sample_rate), int(symbol_rate)
+        self._mmse_taps = np.ascontiguousarray(_mmse_taps())
+        self._baseband_taps = np.ascontiguousarray(_discriminator_lpf(sample_rate))
+        h = C.c_void_p()
+        N.check(N.lib().wc_discdemod_create(self.n_channels, self.sample_rate, self.symbol_rate, N.np_ptr(self._mmse_taps),
+                                            N.np_ptr(self._baseband_taps), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                N.lib().wc_discdemod_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def max_symbols(self, n_samples: int) -> int:
+        return int(N.lib().wc_discdemod_max_symbols(self._h, int(n_samples)))
+
+    def reset(self, channel: int = -1) -> None:
+        N.check(N.lib().wc_discdemod_reset(self._h, int(channel)))
+
+    def state(self, channel: int = 0) -> dict:
+        s = np.zeros(8, dtype=np.float64)
+        N.check(N.lib().wc_discdemod_get_state(self._h, int(channel), N.np_ptr(s)))
+        keys = ("input_gain", "dc_estimate", "symbol_clock", "symbol_spread", "fine_freq_correction",
+                "coarse_freq_correction", "clock_is_python_float", "symbol_count")
+        return dict(zip(keys, (float(v) for v in s)))
+
+    def demodulate(self, audio):
+        if N.is_torch_cuda(audio):
+            import torch
+
+            x = audio.to(torch.float32).contiguous()
+            assert x.dim() == 2 and x.shape[0] == self.n_channels, x.shape
+            n = int(x.shape[1])
+            ms = max(1, self.max_symbols(n))
+            dib = torch.zeros((self.n_channels, ms), dtype=torch.uint8, device=x.device)
+            soft = torch.zeros((self.n_channels, ms), dtype=torch.float32, device=x.device)
+            cnt = torch.zeros((self.n_channels,), dtype=torch.int32, device=x.device)
+            if n:
+                N.check(N.lib().wc_discdemod_demod(self._h, C.c_void_p(x.data_ptr()), n, n, C.c_void_p(dib.data_ptr()),
+                                                   C.c_void_p(soft.data_ptr()), C.c_void_p(cnt.data_ptr()), ms,
+                                                   N.torch_stream_ptr()))
+            return dib, soft, cnt
+        x = np.ascontiguousarray(np.asarray(audio).astype(np.float32, copy=False))
+        assert x.ndim == 2 and x.shape[0] == self.n_channels, x.shape
+        n = int(x.shape[1])
+        ms = max(1, self.max_symbols(n))
+        dib = np.zeros((self.n_channels, ms), dtype=np.uint8)
+        soft = np.zeros((self.n_channels, ms), dtype=np.float32)
+        cnt = np.zeros((self.n_channels,), dtype=np.int32)
+        if n:
+            N.check(N.lib().wc_discdemod_demod_host(self._h, N.np_ptr(x), n, N.np_ptr(dib), N.np_ptr(soft), N.np_ptr(cnt), ms))
+        return dib, soft, cnt
+
+
+class DiscriminatorDemodulator:
+    """Drop-in for wavecapsdr.decoders.p25.DiscriminatorDemodulator (one channel)."""
+
+    BASEBAND_CUTOFF_HZ = 5200
+    MMSE_NTAPS = 8
+    MMSE_NSTEPS = 128
+
+    def __init__(self, sample_rate: int = 48000, symbol_rate: int = 4800) -> None:
+        self._bank = DiscriminatorBank(1, sample_rate, symbol_rate)
+        self.sample_rate = sample_rate
+        self.symbol_rate = symbol_rate
+        self.samples_per_symbol = sample_rate / symbol_rate
+        self._mmse_taps = self._bank._mmse_taps
+        self._baseband_taps = self._bank._baseband_taps
+
+    def demodulate(self, audio):
+        """decoders/p25.py:1197-1236: mono discriminator audio -> dibits (uint8)."""
+        a = np.asarray(audio)
+        if a.size == 0:
+            return np.array([], dtype=np.uint8)
+        dib, _soft, cnt = self._bank.demodulate(a.reshape(1, -1))
+        return dib[0, : int(cnt[0])].copy()
+
+    def reset(self) -> None:
+        self._bank.reset(0)
+
+    @property
+    def _symbol_spread(self) -> float:
+        return self._bank.state(0)["symbol_spread"]
+
+    @property
+    def _symbol_clock(self) -> float:
+        return self._bank.state(0)["symbol_clock"]
+
+    @property
+    def _input_gain(self) -> float:
+        return self._bank.state(0)["input_gain"]
+
+    @property
+    def _symbol_count(self) -> int:
+        return int(self._bank.state(0)["symbol_count"])

@@ -88,3 +88,36 @@ class DDCBank:
         if n:
             N.check(N.lib().wc_ddc_process_host(self._h, N.np_ptr(x), n, N.np_ptr(out)))
         return out
+
+
+class VoiceDiscriminator:
+    """FM discriminator of `VoiceRecorder.process_iq` (trunking/system.py:708-717) for C channels at once:
+    np.diff(np.unwrap([last_phase | np.angle(iq)])) with the last phase carried across calls. Input [C][n] complex64 or
+    complex128 (numpy or torch CUDA); output float64 [C][n] (same residency as the input)."""
+
+    def __init__(self, n_channels: int):
+        import torch
+
+        N.ensure_init()
+        self.n_channels = int(n_channels)
+        self._last = torch.zeros((self.n_channels,), dtype=torch.float64, device="cuda")
+
+    def reset(self) -> None:
+        self._last.zero_()
+
+    def process(self, iq):
+        import torch
+
+        on_dev = N.is_torch_cuda(iq)
+        x = iq if on_dev else torch.from_numpy(np.ascontiguousarray(iq)).cuda()
+        assert x.dim() == 2 and x.shape[0] == self.n_channels, x.shape
+        if x.dtype not in (torch.complex64, torch.complex128):
+            x = x.to(torch.complex64)
+        x = x.contiguous()
+        n = int(x.shape[1])
+        out = torch.empty((self.n_channels, n), dtype=torch.float64, device=x.device)
+        if n:
+            N.check(N.lib().wc_fm_discriminator(C.c_void_p(x.data_ptr()), 1 if x.dtype == torch.complex128 else 0, n, n,
+                                                self.n_channels, C.c_void_p(self._last.data_ptr()),
+                                                C.c_void_p(out.data_ptr()), N.torch_stream_ptr()))
+        return out if on_dev else out.cpu().numpy()
