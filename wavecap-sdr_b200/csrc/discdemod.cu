@@ -64,9 +64,25 @@ __global__ void dd_peak_kernel(const float* __restrict__ x, long long stride, in
 }
 
 // auto gain (p25.py:1213-1222) and DC removal (:1224-1229); y = x*gain - dc, float32 throughout
+// one warp stages the next tile of its 32 channel rows with 4-byte LDGSTS copies while the lanes walk the current one
+__device__ __forceinline__ void dd_stage(float (*tile)[DD_ROW], const float* __restrict__ x, long long stride, int c0, int C,
+                                         int base, int n, int lane) {
+    const int lim = min(DD_TILE, n - base);
+    for (int r = 0; r < 32; ++r) {
+        if (c0 + r >= C) break;
+        const float* xr = x + (long long)(c0 + r) * stride + base;
+#pragma unroll
+        for (int k = 0; k < DD_TILE / 32; ++k) {
+            const int i = lane + 32 * k;
+            if (i < lim) cp_async4(&tile[r][i], xr + i);
+        }
+    }
+    cp_async_commit();
+}
+
 __global__ void __launch_bounds__(32) dd_dc_kernel(const float* __restrict__ x, long long stride, int n, int C,
                                                    const float* __restrict__ peak, DDState* __restrict__ st, float* __restrict__ y) {
-    __shared__ float tile[32][DD_ROW];
+    __shared__ float tile[2][32][DD_ROW];
     const int lane = threadIdx.x;
     const int c0 = blockIdx.x * 32;
     const int c = c0 + lane;
@@ -79,21 +95,22 @@ __global__ void __launch_bounds__(32) dd_dc_kernel(const float* __restrict__ x, 
         if (n > 100 && pk > 0.01f)
             gain = __fadd_rn(__fmul_rn(gain, 0.9f), __fmul_rn(__fdiv_rn(3.0f, pk), 0.1f));
     }
-    for (int base = 0; base < n; base += DD_TILE) {
+    dd_stage(tile[0], x, stride, c0, C, 0, n, lane);
+    int buf = 0;
+    for (int base = 0; base < n; base += DD_TILE, buf ^= 1) {
         const int lim = min(DD_TILE, n - base);
-        __syncwarp();
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-            if (c0 + r >= C) break;
-            const float* xr = x + (long long)(c0 + r) * stride + base;
-            for (int i = lane; i < lim; i += 32) tile[r][i] = xr[i];
+        if (base + DD_TILE < n) {
+            dd_stage(tile[buf ^ 1], x, stride, c0, C, base + DD_TILE, n, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncwarp();
         if (live) {
             for (int i = 0; i < lim; ++i) {
-                const float v = __fmul_rn(tile[lane][i], gain);
+                const float v = __fmul_rn(tile[buf][lane][i], gain);
                 dc = __fadd_rn(__fmul_rn(dc, 0.999f), __fmul_rn(v, 0.001f));
-                tile[lane][i] = __fsub_rn(v, dc);
+                tile[buf][lane][i] = __fsub_rn(v, dc);
             }
         }
         __syncwarp();
@@ -101,8 +118,9 @@ __global__ void __launch_bounds__(32) dd_dc_kernel(const float* __restrict__ x, 
         for (int r = 0; r < 32; ++r) {
             if (c0 + r >= C) break;
             float* yr = y + (long long)(c0 + r) * n + base;
-            for (int i = lane; i < lim; i += 32) yr[i] = tile[r][i];
+            for (int i = lane; i < lim; i += 32) yr[i] = tile[buf][r][i];
         }
+        __syncwarp();
     }
     if (live) {
         st[c].gain = gain;
@@ -147,7 +165,7 @@ __global__ void __launch_bounds__(32) dd_mmse_kernel(const float* __restrict__ x
                                                      const float* __restrict__ taps_g, DDState* __restrict__ st,
                                                      unsigned char* __restrict__ dibits, float* __restrict__ soft_out,
                                                      int max_sym, int* __restrict__ n_sym) {
-    __shared__ float tile[32][DD_ROW];
+    __shared__ float tile[2][32][DD_ROW];
     __shared__ float taps[(DD_STEPS + 1) * DD_TAPS];
     const int lane = threadIdx.x;
     for (int i = lane; i < (DD_STEPS + 1) * DD_TAPS; i += 32) taps[i] = taps_g[i];
@@ -169,20 +187,22 @@ __global__ void __launch_bounds__(32) dd_mmse_kernel(const float* __restrict__ x
     int count = 0;
     unsigned char* dout = dibits + (long long)c * max_sym;
     float* sout = soft_out ? soft_out + (long long)c * max_sym : nullptr;
-    for (int base = 0; base < n; base += DD_TILE) {
+    dd_stage(tile[0], x, n, c0, C, 0, n, lane);
+    int buf = 0;
+    for (int base = 0; base < n; base += DD_TILE, buf ^= 1) {
         const int lim = min(DD_TILE, n - base);
-        __syncwarp();
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-            if (c0 + r >= C) break;
-            const float* xr = x + (long long)(c0 + r) * n + base;
-            for (int i = lane; i < lim; i += 32) tile[r][i] = xr[i];
+        __syncwarp();   // every lane is done with the buffer the next copies land in
+        if (base + DD_TILE < n) {
+            dd_stage(tile[buf ^ 1], x, n, c0, C, base + DD_TILE, n, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncwarp();
         if (!live) continue;
         for (int i = 0; i < lim; ++i) {
             // history ring with a compile-time-indexable copy: rotate instead of indexing dynamically
-            hist[hidx & 7] = tile[lane][i];
+            hist[hidx & 7] = tile[buf][lane][i];
             hidx = (hidx + 1) & 7;
             bool tick;
             if (s.clock_py) {

@@ -78,11 +78,7 @@ __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
+// cp_async_commit / cp_async_wait<N> live in common.cuh
 
 // pass A: grid (N2/16, n_frames)
 __global__ void __launch_bounds__(SP_THREADS, 4) spectrum_pass_a(const float2* __restrict__ iq, long long frame_stride,

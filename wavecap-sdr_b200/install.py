@@ -33,6 +33,8 @@ REBIND = [
     ("wavecapsdr.decoders.p25_framer", "P25P1SoftSyncDetector", "wavecap_sdr_b200.decoders.p25_framer", "P25P1SoftSyncDetector"),
     ("wavecapsdr.decoders.p25_framer", "P25P1MessageFramer", "wavecap_sdr_b200.decoders.p25_framer", "P25P1MessageFramer"),
     ("wavecapsdr.decoders.p25", "P25P1MessageFramer", "wavecap_sdr_b200.decoders.p25_framer", "P25P1MessageFramer"),
+    # voice-channel discriminator path
+    ("wavecapsdr.decoders.p25", "DiscriminatorDemodulator", "wavecap_sdr_b200.decoders.p25", "DiscriminatorDemodulator"),
 ]
 
 _saved: list[tuple[object, str, object]] = []
