@@ -222,6 +222,11 @@ int wc_spectral_nr(const float* x_dev, int n, long long seq_stride, int n_seq, f
 /* ---- output stage: capture.pack_iq16 / pack_pcm16 / pack_f32 (capture.py:102-144) and
  * Channel._update_audio_metrics (capture.py:633-661: sum of squares, peak |x|, count of |x| > 0.95 per sequence) ---- */
 int wc_pack(const float* x_dev, void* y_dev, long long total_floats, int fmt /* 0 int16, 1 clipped float32 */, void* stream);
+/* Channel.update_signal_metrics (capture.py:749-798), all channels of a chunk in one call: power[c] = sum |freq_shift(iq,
+ * offset_c)|^2 (RSSI = 10 log10(power/n + 1e-10)), pct[c] = the two order statistics np.partition picks (ranks n//10 and
+ * n - n//10 - 1) — exact radix select; zeros when want_snr is 0 or n is too short (:783). */
+int wc_signal_metrics(const void* iq_dev, int fmt, int n, int sample_rate, const double* offsets_hz, int n_ch, int want_snr,
+                      float* mag_scratch_dev, double* power_dev, float* pct_dev, void* chan_scratch_dev, void* stream);
 int wc_audio_levels(const float* x_dev, int n, long long seq_stride, int n_seq, double* sumsq_dev, float* peak_dev,
                     int* clip_count_dev, void* stream);
 

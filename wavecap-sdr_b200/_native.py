@@ -183,6 +183,7 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_spectral_nr", i32, vp, i32, i64, i32, f32, vp, i64, vp)
     fn("wc_pack", i32, vp, vp, i64, i32, vp)
     fn("wc_audio_levels", i32, vp, i32, i64, i32, vp, vp, vp, vp)
+    fn("wc_signal_metrics", i32, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp)
     # P25 framing
     fn("wc_bch_decode", i32, vp, vp, i32, vp, vp, vp)
     fn("wc_bch_decode_host", i32, vp, vp, i32, vp, vp)

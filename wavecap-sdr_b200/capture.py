@@ -326,3 +326,58 @@ def audio_levels(audio_rows):
         rms_db = np.where(rms > 1e-10, 20.0 * np.log10(np.maximum(rms, 1e-300)), -100.0)
         peak_db = np.where(peak > 1e-10, 20.0 * np.log10(np.maximum(peak, 1e-300)), -100.0)
     return rms_db, peak_db, cc.cpu().numpy()
+
+
+def signal_metrics(iq, sample_rate: int, offsets_hz, want_snr: bool = True, in_fmt: str = "cf32"):
+    """`Channel.update_signal_metrics` (capture.py:749-798) for every channel of a chunk in one call: freq_shift by each
+    channel's offset, RSSI from the mean squared magnitude, and the SNR estimate from the magnitudes np.partition would
+    put at ranks n//10 and n - n//10 - 1 (exact radix select on the GPU). Returns (rssi_db float list, snr_db list with
+    None where the reference leaves None)."""
+    import torch
+
+    N.ensure_init()
+    fmt = {"cf32": 0, "cs16": 1}[in_fmt]
+    x = S.to_device(iq, np.complex64 if fmt == 0 else np.int16)
+    n = int(x.numel()) if fmt == 0 else int(x.numel()) // 2
+    offs = np.ascontiguousarray(np.atleast_1d(np.asarray(offsets_hz, dtype=np.float64)))
+    k = int(offs.size)
+    if n == 0:
+        return [None] * k, [None] * k
+    mag = torch.empty((k, n), dtype=torch.float32, device=x.device)
+    power = torch.empty((k,), dtype=torch.float64, device=x.device)
+    pct = torch.empty((k, 2), dtype=torch.float32, device=x.device)
+    scratch = torch.empty((int(N.lib().wc_front_chan_scratch_bytes(k)),), dtype=torch.uint8, device=x.device)
+    N.check(N.lib().wc_signal_metrics(S.ptr(x), fmt, n, int(sample_rate), N.np_ptr(offs), k, 1 if want_snr else 0,
+                                      S.ptr(mag), S.ptr(power), S.ptr(pct), S.ptr(scratch), S.stream()))
+    p32 = (power.cpu().numpy() / n).astype(np.float32)
+    rssi = [float(np.float32(10.0) * np.log10(p + np.float32(1e-10))) for p in p32]
+    snr: list = [None] * k
+    k_noise, k_signal = n // 10, n - n // 10 - 1
+    if want_snr and k_noise > 0 and k_signal > k_noise:
+        q = pct.cpu().numpy()
+        for c in range(k):
+            noise_power, signal_power = q[c, 0] ** 2, q[c, 1] ** 2
+            if noise_power > 1e-10:
+                snr[c] = float(np.float32(10.0) * np.log10(signal_power / noise_power))
+    return rssi, snr
+
+
+class SignalMeter:
+    """The per-channel state `update_signal_metrics` keeps (rssi_db, snr_db, the every-10th-call SNR throttle,
+    capture.py:773-777) for a bank of channels metered together."""
+
+    def __init__(self, offsets_hz):
+        self.offsets_hz = list(np.atleast_1d(offsets_hz))
+        self.rssi_db = [None] * len(self.offsets_hz)
+        self.snr_db = [None] * len(self.offsets_hz)
+        self._snr_counter = 0
+
+    def update(self, iq, sample_rate: int, in_fmt: str = "cf32") -> None:
+        if _n(iq) == 0:
+            return
+        self._snr_counter += 1
+        want = self._snr_counter % 10 == 0
+        rssi, snr = signal_metrics(iq, sample_rate, self.offsets_hz, want_snr=want, in_fmt=in_fmt)
+        self.rssi_db = rssi
+        if want:
+            self.snr_db = snr

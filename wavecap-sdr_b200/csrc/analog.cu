@@ -574,6 +574,82 @@ static int launch_iir_typed(const IirCoef* d_cf, int K, const TIn* x, float* y, 
 #undef WC_IIR_CASE
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// live signal metrics (Channel.update_signal_metrics, capture.py:749-798): |freq_shift(iq)| per channel with the sum
+// of squares (RSSI), and the two order statistics np.partition picks for the SNR estimate — exact, by 4-pass radix
+// select on the IEEE bit patterns of the (non-negative) magnitudes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) metrics_mag_kernel(const void* __restrict__ iq, int fmt, int n, const FrontChan* __restrict__ chs,
+                                                          float* __restrict__ mag, double* __restrict__ power) {
+    __shared__ double red[8];
+    const int c = blockIdx.y;
+    const FrontChan ch = chs[c];
+    double psum = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float2 v;
+        if (fmt == 0) v = reinterpret_cast<const float2*>(iq)[i];
+        else {
+            const short2 q = reinterpret_cast<const short2*>(iq)[i];
+            v = make_float2((float)q.x / 32768.0f, (float)q.y / 32768.0f);
+        }
+        if (ch.shift) {
+            float cs, sn;
+            nco_f32(ch.k32, i, cs, sn);
+            v = make_float2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+        }
+        const float m = sqrtf(v.x * v.x + v.y * v.y);
+        mag[(long long)c * n + i] = m;
+        psum += (double)(m * m);
+    }
+    psum = warp_sum(psum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = psum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        atomicAdd(power + c, t);
+    }
+}
+
+// out[c][q] = the rank[q]-th smallest of mag[c][0..n) (0-based), q = 0, 1
+__global__ void __launch_bounds__(1024) metrics_select_kernel(const float* __restrict__ mag, int n, int rank0, int rank1,
+                                                              float* __restrict__ out) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_rank;
+    const float* xs = mag + (long long)blockIdx.x * n;
+    const int ranks[2] = {rank0, rank1};
+    for (int q = 0; q < 2; ++q) {
+        unsigned prefix = 0u, mask = 0u;
+        unsigned rank = (unsigned)ranks[q];
+        for (int pass = 3; pass >= 0; --pass) {
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const unsigned u = __float_as_uint(xs[i]);
+                if ((u & mask) == prefix) atomicAdd(&hist[(u >> (8 * pass)) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned cum = 0u;
+                int b = 0;
+                for (; b < 255; ++b) {
+                    if (cum + hist[b] > rank) break;
+                    cum += hist[b];
+                }
+                s_prefix = prefix | ((unsigned)b << (8 * pass));
+                s_rank = rank - cum;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            rank = s_rank;
+            mask |= 0xffu << (8 * pass);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[blockIdx.x * 2 + q] = __uint_as_float(prefix);
+    }
+}
+
 }  // namespace wc
 
 using namespace wc;
@@ -814,6 +890,42 @@ int wc_finalize(float* audio_dev, int n_out, int n_chunks, int n_seq, const doub
                                                                        squelch_db_dev, has_squelch_dev, rssi_db_dev,
                                                                        squelched_dev);
     WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* Channel.update_signal_metrics (capture.py:749-798) for n_ch channels of one chunk: power_dev[c] = sum |freq_shift(iq)|^2,
+ * pct_dev[c] = {magnitudes partitioned at n//10, at n - n//10 - 1} (only when want_snr and those ranks are usable,
+ * :781-785). mag_scratch_dev: float32 [n_ch][n]. */
+int wc_signal_metrics(const void* iq_dev, int fmt, int n, int sample_rate, const double* offsets_hz, int n_ch, int want_snr,
+                      float* mag_scratch_dev, double* power_dev, float* pct_dev, void* chan_scratch_dev, void* stream) {
+    WC_REQUIRE(iq_dev && offsets_hz && mag_scratch_dev && power_dev && pct_dev && chan_scratch_dev,
+               "wc_signal_metrics: null argument");
+    WC_REQUIRE(n_ch >= 1 && n_ch <= 4096 && n >= 0, "wc_signal_metrics: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<FrontChan> ch(n_ch);
+    for (int c = 0; c < n_ch; ++c) {
+        FrontChan& f = ch[c];
+        f.mode = WC_MODE_NONE;
+        f.shift = (offsets_hz[c] != 0.0) ? 1 : 0;
+        const double off = nearbyint(offsets_hz[c]);
+        f.k32 = (float)(-(2.0 * M_PI * (off / (double)sample_rate)));
+        f.bfo_turns = 0.0;
+        f.disc_scale = 0.f;
+    }
+    WC_CUDA(cudaMemcpyAsync(chan_scratch_dev, ch.data(), sizeof(FrontChan) * n_ch, cudaMemcpyHostToDevice, st));
+    WC_CUDA(cudaMemsetAsync(power_dev, 0, sizeof(double) * (size_t)n_ch, st));
+    WC_CUDA(cudaMemsetAsync(pct_dev, 0, sizeof(float) * 2 * (size_t)n_ch, st));
+    if (n > 0) {
+        int bx = (n + 255) / 256;
+        if (bx > 592) bx = 592;
+        metrics_mag_kernel<<<dim3(bx, n_ch), 256, 0, st>>>(iq_dev, fmt, n, reinterpret_cast<const FrontChan*>(chan_scratch_dev),
+                                                           mag_scratch_dev, power_dev);
+        const int k_noise = n / 10, k_signal = n - n / 10 - 1;
+        if (want_snr && k_noise > 0 && k_signal > k_noise)
+            metrics_select_kernel<<<n_ch, 1024, 0, st>>>(mag_scratch_dev, n, k_noise, k_signal, pct_dev);
+        WC_CUDA(cudaGetLastError());
+    }
+    WC_CUDA(cudaStreamSynchronize(st));  // the pageable host vector must outlive the async copy
     return 0;
 }
 
