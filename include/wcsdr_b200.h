@@ -251,6 +251,16 @@ int wc_bch_decode_host(const unsigned char* bits63_host, const int* tracked_nac_
  * the reference's partial state): 1 placeholder dispatch, 2 below minimum length (a = length, b = minimum), 3 not
  * aligned to 196-bit blocks, 4 length mismatch, 5 invalid dibit (a = dibit), 6 output buffers full (never with the
  * sizes below). scores (optional, float32 [C][n_symbols]) receives the soft sync scores. */
+/* 1/2-rate trellis (Viterbi) decoding: dsp/fec/trellis.py:214-272 TrellisDecoder.decode / trellis_decode for `count`
+ * blocks at once (hard decisions, or soft float64 values per dibit), and the TSBK block decode of decoders/p25.py:2037-2109
+ * (196 message bits -> deinterleave :2552-2660 -> decode -> 96 bits + last_block / protected / opcode / mfid / payload). */
+int wc_trellis12_decode(const unsigned char* dibits_dev, long long stride, const int* n_dibits_dev, int n_fixed,
+                        const double* soft_dev, int count, unsigned char* out_dev, long long out_stride, int* n_out_dev,
+                        int* metric_dev, void* stream);
+int wc_tsbk_decode(const unsigned char* bits196_dev, int count, unsigned char* bits96_dev, int* metric_dev, int* fields_dev,
+                   unsigned char* data8_dev, void* stream);
+int wc_tsbk_decode_host(const unsigned char* bits196_host, int count, unsigned char* bits96_host, int* metric_host,
+                        int* fields_host, unsigned char* data8_host);
 typedef struct wc_p25framer wc_p25framer;
 int wc_p25framer_create(int n_channels, wc_p25framer** out);
 void wc_p25framer_destroy(wc_p25framer* h);

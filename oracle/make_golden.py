@@ -487,7 +487,65 @@ def gen_p25_discriminator():
     np.savez_compressed(os.path.join(OUT, "p25_discriminator.npz"), **out)
 
 
-GENERATORS = {"p25_discriminator": gen_p25_discriminator, "p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+
+def gen_p25_trellis():
+    """dsp.fec.trellis.trellis_decode and the TSBK block decode (P25Decoder._deinterleave_data + P25TrellisDecoder.decode)
+    of the live reference on encoded blocks with injected dibit errors: (a) 300 blocks of random length 1-60 input dibits,
+    every third with soft values, every fifth with an odd received length; (b) 200 interleaved TSBK blocks."""
+    from wavecapsdr.decoders.p25 import P25Decoder, P25TrellisDecoder
+    from wavecapsdr.dsp.fec.trellis import trellis_decode
+    from oracle import trellis as ot
+
+    rng = np.random.default_rng(31)
+    rx_all = np.zeros((300, 120), dtype=np.uint8)
+    soft_all = np.zeros((300, 120), dtype=np.float64)
+    has_soft = np.zeros(300, dtype=np.uint8)
+    lens = np.zeros(300, dtype=np.int32)
+    dec_all = np.zeros((300, 60), dtype=np.uint8)
+    dec_len = np.zeros(300, dtype=np.int32)
+    met = np.zeros(300, dtype=np.int32)
+    for t in range(300):
+        n = int(rng.integers(1, 61))
+        rx = ot.encode(rng.integers(0, 4, n)).copy()
+        for p in rng.integers(0, len(rx), int(rng.integers(0, 8))):
+            rx[p] = rng.integers(0, 4)
+        if t % 5 == 0 and len(rx) > 1:
+            rx = rx[:-1]
+        soft = None
+        if t % 3 == 0:
+            soft = np.array(ot.LEVEL)[rx] + rng.normal(0, 0.8, len(rx))
+            has_soft[t] = 1
+            soft_all[t, :len(rx)] = soft
+        d, m = trellis_decode(rx, soft)
+        rx_all[t, :len(rx)] = rx
+        lens[t] = len(rx)
+        dec_all[t, :len(d)] = d
+        dec_len[t] = len(d)
+        met[t] = m
+    out = dict(rx=rx_all, soft=soft_all, has_soft=has_soft, lens=lens, dec=dec_all, dec_len=dec_len, metric=met)
+    bits = np.zeros((200, 196), dtype=np.uint8)
+    dec96 = np.zeros((200, 96), dtype=np.uint8)
+    tmet = np.zeros(200, dtype=np.int32)
+    tx96 = np.zeros((200, 96), dtype=np.uint8)
+    deint = np.array(P25Decoder.DATA_DEINTERLEAVE)
+    for t in range(200):
+        msg = np.concatenate([rng.integers(0, 4, 48), [0]])
+        blk = ot.interleave(ot.encode(msg))
+        for p in rng.integers(0, 98, int(rng.integers(0, 9))):
+            blk[p] = rng.integers(0, 4)
+        bits[t, 0::2] = blk >> 1
+        bits[t, 1::2] = blk & 1
+        d, m = P25TrellisDecoder().decode(blk[deint].astype(np.uint8))
+        dec96[t, 0::2] = (d[:48] >> 1) & 1
+        dec96[t, 1::2] = d[:48] & 1
+        tmet[t] = m
+        tx96[t, 0::2] = (msg[:48] >> 1) & 1
+        tx96[t, 1::2] = msg[:48] & 1
+    out.update(tsbk_bits=bits, tsbk_dec96=dec96, tsbk_metric=tmet, tsbk_tx96=tx96)
+    np.savez_compressed(os.path.join(OUT, "p25_trellis.npz"), **out)
+
+
+GENERATORS = {"p25_trellis": gen_p25_trellis, "p25_discriminator": gen_p25_discriminator, "p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

@@ -183,6 +183,16 @@ def test_c4fm_iq_to_decoded_frames(native, gold):
     assert log1[:len(ref_err)] == ref_err and len(log1) >= len(ref_err)
     ref_msgs = unpack(gold["e2e_stream_meta"], gold["e2e_stream_bits"])
     assert msgs1 == ref_msgs and len(ref_msgs) >= 8
+    # ... and on through the TSBK block decode (deinterleave + 1/2-rate Viterbi, decoders/p25.py:2037-2087)
+    from oracle import trellis as ot
+    from wavecap_sdr_b200.dsp.fec.trellis import tsbk_decode_batch
+
+    tsbk = [np.frombuffer(m[3], dtype=np.uint8) for m in msgs1 if m[0] in (0x7, 0x17, 0x27) and len(m[3]) == 196]
+    assert len(tsbk) >= 3
+    bits96, met, fields, data = tsbk_decode_batch(np.array(tsbk))
+    for j, b in enumerate(tsbk):
+        ob, om = ot.tsbk_decode_bits(b)
+        assert np.array_equal(bits96[j], ob) and int(met[j]) == om
 
 
 def test_bank_of_64_channels_vs_oracle(native, gold):

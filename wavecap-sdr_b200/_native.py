@@ -187,6 +187,9 @@ def _declare(l: C.CDLL) -> None:
     # P25 framing
     fn("wc_bch_decode", i32, vp, vp, i32, vp, vp, vp)
     fn("wc_bch_decode_host", i32, vp, vp, i32, vp, vp)
+    fn("wc_trellis12_decode", i32, vp, i64, vp, i32, vp, i32, vp, i64, vp, vp, vp)
+    fn("wc_tsbk_decode", i32, vp, i32, vp, vp, vp, vp, vp)
+    fn("wc_tsbk_decode_host", i32, vp, i32, vp, vp, vp, vp)
     fn("wc_p25framer_create", i32, i32, P(vp))
     fn("wc_p25framer_destroy", None, vp)
     fn("wc_p25framer_reset", i32, vp, i32, i32)

@@ -655,6 +655,151 @@ __global__ void framer_reset_kernel(FramerState* st, int C, int channel, int kee
         for (int i = threadIdx.x; i < 4096; i += blockDim.x) f.nac_seen[i] = 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 1/2-rate trellis (Viterbi) decoder: dsp/fec/trellis.py:89-289 TrellisDecoder.decode, one thread per block.
+// Survivors are register-exchange paths (2 bits per step). Output semantics of the reference: from the 12th step on,
+// every step emits the decision 12 steps back of the path that is best AT THAT STEP (first minimum over states);
+// the last 11 decisions come from the final best path. Metrics are float64 like the reference's Python floats
+// (hard decisions: bit-error counts, exact).
+// ---------------------------------------------------------------------------------------------
+__constant__ unsigned char c_tr_nibble[16] = {2, 12, 1, 15, 14, 0, 13, 3, 9, 7, 10, 4, 5, 11, 6, 8};  // [state][input]
+constexpr int TR_DEPTH = 12;
+constexpr int TR_MAXW = 32;   // 64-bit words per survivor: up to 1024 steps (2048 dibits) per block
+
+struct TrellisArgs {
+    const unsigned char* dibits;   // [B][stride]
+    long long stride;
+    const int* n_each;             // [B] or null
+    int n_fixed;
+    const double* soft;            // [B][stride] or null
+    int tsbk;                      // 1: rows are 196 message BITS -> 98 dibits, deinterleaved (decoders/p25.py:2037-2087)
+    unsigned char* out;            // tsbk 0: decoded dibits [B][out_stride]; tsbk 1: 96 decoded bits [B][96]
+    long long out_stride;
+    int* n_out;                    // [B] decoded dibits (tsbk 0)
+    int* metric;                   // [B] int(best path metric)
+    int* fields;                   // tsbk 1: [B][4] last_block, protected, opcode, mfid
+    unsigned char* data8;          // tsbk 1: [B][8] payload bytes
+    int B;
+};
+
+__device__ __forceinline__ int tsbk_deint(int i) {   // decoders/p25.py:2552-2660 as a rule
+    if (i >= 96) return 24 + (i - 96);
+    const int grp = i >> 3, r = i & 7;
+    const int base = (r < 2) ? 0 : (r < 4) ? 26 : (r < 6) ? 50 : 74;
+    return base + 2 * grp + (r & 1);
+}
+
+__global__ void __launch_bounds__(64) trellis12_kernel(const TrellisArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const unsigned char* row = a.dibits + (long long)b * a.stride;
+    const double* srow = a.soft ? a.soft + (long long)b * a.stride : nullptr;
+    int n = a.tsbk ? 98 : (a.n_each ? a.n_each[b] : a.n_fixed);
+    n &= ~1;   // odd length: the last dibit is dropped (:228-232)
+    const int steps_total = n >> 1;
+    const int W = (steps_total + 31) >> 5;
+    unsigned long long path[2][4][TR_MAXW];
+    double metric[4] = {0.0, INFINITY, INFINITY, INFINITY};
+    for (int s = 0; s < 4; ++s)
+        for (int w = 0; w < W; ++w) path[0][s][w] = 0ull;
+    int cur = 0, n_out = 0;
+    unsigned char* out = a.out + (long long)b * a.out_stride;
+    unsigned char first48[48];
+    auto emit = [&](int d) {
+        if (a.tsbk) {
+            if (n_out < 48) first48[n_out] = (unsigned char)d;
+        } else {
+            out[n_out] = (unsigned char)d;
+        }
+        ++n_out;
+    };
+    auto get = [&](int i) -> int {
+        if (!a.tsbk) return row[i] & 3;   // the reference indexes its tables with the dibit; > 3 would raise there
+        const int j = tsbk_deint(i);
+        return ((row[2 * j] & 1) << 1) | (row[2 * j + 1] & 1);
+    };
+    for (int step = 0; step < steps_total; ++step) {
+        const int r0 = get(2 * step), r1 = get(2 * step + 1);
+        double s0 = 0.0, s1 = 0.0;
+        if (srow) {
+            s0 = srow[2 * step];
+            s1 = srow[2 * step + 1];
+        }
+        double nm[4];
+        int bp[4];
+        for (int ns = 0; ns < 4; ++ns) {
+            double best = INFINITY;
+            int bprev = 0;
+            for (int p = 0; p < 4; ++p) {
+                const int nib = c_tr_nibble[p * 4 + ns];
+                const int e0 = nib >> 2, e1 = nib & 3;
+                double br;
+                if (srow) {
+                    const double l0 = (e0 == 0) ? 1.0 : (e0 == 1) ? 3.0 : (e0 == 2) ? -1.0 : -3.0;
+                    const double l1 = (e1 == 0) ? 1.0 : (e1 == 1) ? 3.0 : (e1 == 2) ? -1.0 : -3.0;
+                    br = (s0 - l0) * (s0 - l0) + (s1 - l1) * (s1 - l1);
+                } else {
+                    br = (double)(__popc(r0 ^ e0) + __popc(r1 ^ e1));
+                }
+                const double m = metric[p] + br;
+                if (m < best) {
+                    best = m;
+                    bprev = p;
+                }
+            }
+            nm[ns] = best;
+            bp[ns] = bprev;
+        }
+        const int nxt = cur ^ 1;
+        for (int ns = 0; ns < 4; ++ns) {
+            for (int w = 0; w < W; ++w) path[nxt][ns][w] = path[cur][bp[ns]][w];
+            const unsigned long long dec = (nm[ns] < INFINITY) ? (unsigned long long)ns : 0ull;
+            path[nxt][ns][step >> 5] |= dec << (2 * (step & 31));
+            metric[ns] = nm[ns];
+        }
+        cur = nxt;
+        const int steps = step + 1;
+        if (steps >= TR_DEPTH) {
+            int best = 0;
+            for (int st = 1; st < 4; ++st)
+                if (metric[st] < metric[best]) best = st;
+            const int k = steps - TR_DEPTH;
+            emit((int)((path[cur][best][k >> 5] >> (2 * (k & 31))) & 3ull));
+        }
+    }
+    int best = 0;
+    for (int st = 1; st < 4; ++st)
+        if (metric[st] < metric[best]) best = st;
+    for (int k = max(0, steps_total - TR_DEPTH + 1); k < steps_total; ++k)
+        emit((int)((path[cur][best][k >> 5] >> (2 * (k & 31))) & 3ull));
+    const double mb = metric[best];
+    a.metric[b] = (steps_total == 0) ? 0 : (int)mb;
+    if (!a.tsbk) {
+        a.n_out[b] = n_out;
+        return;
+    }
+    unsigned char* bits = a.out + (long long)b * 96;
+    for (int i = 0; i < 48; ++i) {
+        bits[2 * i] = (first48[i] >> 1) & 1;
+        bits[2 * i + 1] = first48[i] & 1;
+    }
+    int v = 0;
+    for (int i = 2; i < 8; ++i) v = (v << 1) | bits[i];
+    int* f = a.fields + (long long)b * 4;
+    f[0] = bits[0];
+    f[1] = bits[1];
+    f[2] = v;
+    v = 0;
+    for (int i = 8; i < 16; ++i) v = (v << 1) | bits[i];
+    f[3] = v;
+    for (int k = 0; k < 8; ++k) {
+        v = 0;
+        for (int i = 0; i < 8; ++i) v = (v << 1) | bits[16 + 8 * k + i];
+        a.data8[(long long)b * 8 + k] = (unsigned char)v;
+    }
+}
+
 static bool g_tables_ready = false;
 static int ensure_tables() {
     if (g_tables_ready) return 0;
@@ -915,6 +1060,87 @@ int wc_p25framer_get_state(wc_p25framer* h, int channel, int* state12) {
     state12[10] = k.previous_duid;
     state12[11] = (int)(k.symbols_total & 0x7fffffff);
     return 0;
+}
+
+/* dsp/fec/trellis.py:214-272 TrellisDecoder.decode for `count` blocks: dibits uint8 [count][stride] (n_dibits[b] valid, or
+ * n_fixed when n_dibits is NULL; an odd length drops its last dibit), soft float64 [count][stride] or NULL (hard decisions)
+ * -> decoded dibits [count][out_stride] (n_out[b] = n/2 of them), metric[b] = int(best path metric). */
+int wc_trellis12_decode(const unsigned char* dibits_dev, long long stride, const int* n_dibits_dev, int n_fixed,
+                        const double* soft_dev, int count, unsigned char* out_dev, long long out_stride, int* n_out_dev,
+                        int* metric_dev, void* stream_v) {
+    WC_REQUIRE(dibits_dev && out_dev && n_out_dev && metric_dev, "wc_trellis12_decode: null argument");
+    WC_REQUIRE(n_fixed >= 0 && n_fixed <= 2 * 32 * TR_MAXW && stride >= n_fixed && out_stride >= n_fixed / 2,
+               "wc_trellis12_decode: block length %d outside [0, %d]", n_fixed, 2 * 32 * TR_MAXW);
+    if (count <= 0) return 0;
+    TrellisArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dibits = dibits_dev;
+    a.stride = stride;
+    a.n_each = n_dibits_dev;
+    a.n_fixed = n_fixed;
+    a.soft = soft_dev;
+    a.tsbk = 0;
+    a.out = out_dev;
+    a.out_stride = out_stride;
+    a.n_out = n_out_dev;
+    a.metric = metric_dev;
+    a.B = count;
+    trellis12_kernel<<<(count + 63) / 64, 64, 0, (cudaStream_t)stream_v>>>(a);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* decoders/p25.py:2037-2109 for `count` TSBK blocks: 196 message bits (as P25P1Message.bits) -> 98 dibits -> deinterleave
+ * (:2552-2660) -> trellis decode -> 96 bits; fields [count][4] = last_block, protected, opcode, mfid; data8 = payload. */
+int wc_tsbk_decode(const unsigned char* bits196_dev, int count, unsigned char* bits96_dev, int* metric_dev, int* fields_dev,
+                   unsigned char* data8_dev, void* stream_v) {
+    WC_REQUIRE(bits196_dev && bits96_dev && metric_dev && fields_dev && data8_dev, "wc_tsbk_decode: null argument");
+    if (count <= 0) return 0;
+    TrellisArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dibits = bits196_dev;
+    a.stride = 196;
+    a.n_fixed = 98;
+    a.tsbk = 1;
+    a.out = bits96_dev;
+    a.out_stride = 96;
+    a.metric = metric_dev;
+    a.fields = fields_dev;
+    a.data8 = data8_dev;
+    a.B = count;
+    trellis12_kernel<<<(count + 63) / 64, 64, 0, (cudaStream_t)stream_v>>>(a);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wc_tsbk_decode_host(const unsigned char* bits196_host, int count, unsigned char* bits96_host, int* metric_host,
+                        int* fields_host, unsigned char* data8_host) {
+    WC_REQUIRE(bits196_host && bits96_host && metric_host && fields_host && data8_host, "wc_tsbk_decode_host: null argument");
+    if (count <= 0) return 0;
+    unsigned char *d_in = nullptr, *d_out = nullptr, *d_d8 = nullptr;
+    int *d_m = nullptr, *d_f = nullptr;
+    WC_CUDA(cudaMalloc(&d_in, (size_t)count * 196));
+    WC_CUDA(cudaMalloc(&d_out, (size_t)count * 96));
+    WC_CUDA(cudaMalloc(&d_d8, (size_t)count * 8));
+    WC_CUDA(cudaMalloc(&d_m, sizeof(int) * (size_t)count));
+    WC_CUDA(cudaMalloc(&d_f, sizeof(int) * 4 * (size_t)count));
+    cudaMemcpy(d_in, bits196_host, (size_t)count * 196, cudaMemcpyHostToDevice);
+    int rc = wc_tsbk_decode(d_in, count, d_out, d_m, d_f, d_d8, nullptr);
+    if (!rc) {
+        cudaMemcpy(bits96_host, d_out, (size_t)count * 96, cudaMemcpyDeviceToHost);
+        cudaMemcpy(metric_host, d_m, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost);
+        cudaMemcpy(fields_host, d_f, sizeof(int) * 4 * (size_t)count, cudaMemcpyDeviceToHost);
+        if (cudaMemcpy(data8_host, d_d8, (size_t)count * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("wc_tsbk_decode_host: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = -2;
+        }
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    cudaFree(d_d8);
+    cudaFree(d_m);
+    cudaFree(d_f);
+    return rc;
 }
 
 }  // extern "C"

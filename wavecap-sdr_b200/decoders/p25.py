@@ -262,3 +262,21 @@ class DiscriminatorDemodulator:
     @property
     def _symbol_count(self) -> int:
         return int(self._bank.state(0)["symbol_count"])
+
+
+class P25TrellisDecoder:
+    """Drop-in for wavecapsdr.decoders.p25.P25TrellisDecoder (decoders/p25.py:1348-1393): 1/2-rate Viterbi on the GPU,
+    truncated to the 48 dibits of a TSBK."""
+
+    def __init__(self) -> None:
+        from ..dsp.fec.trellis import TrellisDecoder
+
+        self._decoder = TrellisDecoder()
+
+    def decode(self, dibits):
+        if len(dibits) < 4:
+            return None, -1
+        decoded, error_metric = self._decoder.decode(dibits)
+        if len(decoded) == 0:
+            return None, -1
+        return decoded[:48], int(error_metric)

@@ -30,6 +30,8 @@ REBIND = [
     # P25 framing. decoders/p25.py binds P25P1MessageFramer / P25P1Message / P25P1DataUnitID by name
     # at import time (decoders/p25.py:25-29), so they are rebound there as well as in their home module.
     ("wavecapsdr.dsp.fec.bch", "bch_decode", "wavecap_sdr_b200.dsp.fec.bch", "bch_decode"),
+    ("wavecapsdr.dsp.fec.trellis", "trellis_decode", "wavecap_sdr_b200.dsp.fec.trellis", "trellis_decode"),
+    ("wavecapsdr.decoders.p25", "P25TrellisDecoder", "wavecap_sdr_b200.decoders.p25", "P25TrellisDecoder"),
     ("wavecapsdr.decoders.p25_framer", "P25P1SoftSyncDetector", "wavecap_sdr_b200.decoders.p25_framer", "P25P1SoftSyncDetector"),
     ("wavecapsdr.decoders.p25_framer", "P25P1MessageFramer", "wavecap_sdr_b200.decoders.p25_framer", "P25P1MessageFramer"),
     ("wavecapsdr.decoders.p25", "P25P1MessageFramer", "wavecap_sdr_b200.decoders.p25_framer", "P25P1MessageFramer"),
