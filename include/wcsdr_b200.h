@@ -299,6 +299,16 @@ int wc_discdemod_demod_host(wc_discdemod* h, const float* audio_host, int n_samp
                             float* soft_host, int* n_sym_host, int max_sym);
 int wc_discdemod_get_state(wc_discdemod* h, int channel, double* state8);
 
+/* ---- control-channel scanner: trunking/cc_scanner.py:166-351 ControlChannelScanner._measure_channel /
+ * _detect_sync_pattern for n_ch frequency offsets (candidates and the two band-edge noise probes) of one wideband block.
+ * iq complex64 [n]; taps65 = firwin(65, 0.8/D, kaiser 6.0), D = max(1, fs // 48000) (host); y complex128 [n_ch][m] with
+ * m = wc_ccscan_out_len; power_sum / power_max float64 [n_ch] = sum and max of |y|^2; corr float64 [n_ch] = best
+ * normalised sync correlation (0 when the block is shorter than 250 kept samples). scratch_dev: 8 * n_ch bytes. */
+int wc_ccscan_out_len(int n_samples, int sample_rate);
+int wc_ccscan_measure(const void* iq_dev, int n_samples, int sample_rate, const double* offsets_hz, int n_ch,
+                      const double* taps65, void* y_dev, double* power_sum_dev, double* power_max_dev, double* corr_dev,
+                      void* scratch_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -545,7 +545,28 @@ def gen_p25_trellis():
     np.savez_compressed(os.path.join(OUT, "p25_trellis.npz"), **out)
 
 
-GENERATORS = {"p25_trellis": gen_p25_trellis, "p25_discriminator": gen_p25_discriminator, "p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+
+def gen_cc_scanner():
+    """ControlChannelScanner.scan_all of the live reference on oracle.cc_scanner.synth_band() (regenerated from its seed in
+    the tests: the comparison is at float tolerance, not bit level)."""
+    from wavecapsdr.trunking.cc_scanner import ControlChannelScanner
+    from oracle import cc_scanner as oc
+
+    x, center, freqs = oc.synth_band()
+    sc = ControlChannelScanner(center_hz=center, sample_rate=1_200_000, control_channels=freqs)
+    m = sc.scan_all(x)
+    rows = []
+    for f in freqs:
+        if f in m:
+            r = m[f]
+            rows.append([f, r.power_db, r.peak_power_db, r.noise_floor_db, r.snr_db, float(r.sync_detected), r.sample_count])
+    best = sc.get_best_channel()
+    np.savez_compressed(os.path.join(OUT, "cc_scanner.npz"), rows=np.array(rows, dtype=np.float64), best=np.float64(best[0]),
+                        ranking=np.array([f for f, _ in sc.get_channel_ranking()], dtype=np.float64),
+                        x_checksum=np.float64(np.sum(np.abs(x.astype(np.complex128)) ** 2)))
+
+
+GENERATORS = {"cc_scanner": gen_cc_scanner, "p25_trellis": gen_p25_trellis, "p25_discriminator": gen_p25_discriminator, "p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

@@ -198,6 +198,9 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_p25framer_process", i32, vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp)
     fn("wc_p25framer_process_host", i32, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp)
     fn("wc_p25framer_get_state", i32, vp, i32, vp)
+    # control-channel scanner
+    fn("wc_ccscan_out_len", i32, i32, i32)
+    fn("wc_ccscan_measure", i32, vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp)
     # voice-channel discriminator path
     fn("wc_fm_discriminator", i32, vp, i32, i64, i32, i32, vp, vp, vp)
     fn("wc_discdemod_create", i32, i32, i32, i32, vp, vp, P(vp))

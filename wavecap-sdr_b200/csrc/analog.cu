@@ -57,14 +57,7 @@ struct FrontArgs {
     int* nonfinite;        // [n_chunks] set to 1 if any input sample is not finite
 };
 
-__device__ __forceinline__ void nco_f32(float k32, int n, float& c, float& s) {
-    // theta = fl32(k32 * fl32(n)) exactly as numpy computes it; then an accurate cos/sin of that
-    // float32 angle: reduce in double (theta < 2^24 rad is exact in double), evaluate in float.
-    const float th = __fmul_rn(k32, (float)n);
-    const double t = (double)th * 0.15915494309189535;  // turns
-    const double fr = t - rint(t);                       // [-0.5, 0.5]
-    sincospif((float)(2.0 * fr), &s, &c);
-}
+// nco_f32 (capture.freq_shift's float32-phase oscillator) lives in common.cuh
 
 __global__ void __launch_bounds__(FR_THREADS) front_kernel(const FrontArgs a) {
     __shared__ float2 tile[FR_TILE + 1];

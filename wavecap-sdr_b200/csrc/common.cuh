@@ -83,6 +83,16 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// capture.freq_shift (capture.py:166-193): exp(j * fl32(k32 * fl32(n))) with k32 = float32(-2*pi*round(off)/fs)
+__device__ __forceinline__ void nco_f32(float k32, int n, float& c, float& s) {
+    // theta = fl32(k32 * fl32(n)) exactly as numpy computes it; then an accurate cos/sin of that
+    // float32 angle: reduce in double (theta < 2^24 rad is exact in double), evaluate in float.
+    const float th = __fmul_rn(k32, (float)n);
+    const double t = (double)th * 0.15915494309189535;  // turns
+    const double fr = t - rint(t);                       // [-0.5, 0.5]
+    sincospif((float)(2.0 * fr), &s, &c);
+}
+
 // ---- small complex helpers on float2 ----
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
