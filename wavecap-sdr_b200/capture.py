@@ -224,35 +224,41 @@ def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig],
                 invalid[i] = ((~torch.isfinite(audio[i]).all(dim=1)) | (audio[i].abs().amax(dim=1) > AUDIO_MAX_ABS)).int()
         c = e
 
+    # one device->host transfer for all per-(channel, chunk) statistics instead of three per channel
+    have = [ci for ci in range(n_ch) if audio[ci] is not None]
+    stats_h = None
+    if have:
+        stats = torch.stack([torch.stack([apower[ci].double(), invalid[ci].double()]) for ci in have])  # [k][2][n_chunks]
+        stats_h = stats.cpu().numpy()
     power_h = power.cpu().numpy()
     nonfinite_h = nonfinite.cpu().numpy()
+    slot = {ci: j for j, ci in enumerate(have)}
+    # dB values for the whole [channel][chunk] grid at once, in the reference's float32 arithmetic (capture.py:331-334,436-437)
+    rssi_all = (np.float32(10.0) * np.log10((power_h / n).astype(np.float32) + np.float32(1e-10))).astype(np.float64)
     for ci, cfg in enumerate(cfgs):
-        a_h = p_h = inv_h = None
+        a_h = inv_h = sp_db = None
         if audio[ci] is not None:
-            inv_h = invalid[ci].cpu().numpy()
-            p_h = apower[ci].cpu().numpy()
+            inv_h = stats_h[slot[ci], 1] != 0
             a_h = audio[ci] if return_device else audio[ci].cpu().numpy()
+            n_a = int(a_h.shape[-1])
+            sp_db = 10.0 * np.log10((stats_h[slot[ci], 0] / max(n_a, 1)).astype(np.float32) + np.float32(1e-10))
+        digital = sigs[ci][0] == "digital"
+        squelch = cfg.squelch_db if (apply_squelch and cfg.squelch_db is not None) else None
         for b in range(n_chunks):
             if nonfinite_h[b]:
                 continue            # non-finite IQ: chunk dropped, empty metrics (capture.py:323-325)
-            rssi = float(np.float32(10.0) * np.log10(np.float32(power_h[ci, b] / n) + np.float32(1e-10)))
-            metrics: dict[str, Any] = {"rssi_db": rssi}
-            if sigs[ci][0] == "digital":
-                metrics["signal_power_db"] = rssi   # same power of the shifted IQ (capture.py:426-428)
-                results[b][ci] = (None, metrics)
+            rssi = float(rssi_all[ci, b])
+            if digital:
+                # same power of the shifted IQ (capture.py:426-428)
+                results[b][ci] = (None, {"rssi_db": rssi, "signal_power_db": rssi})
                 continue
-            if a_h is None:
-                results[b][ci] = (None, metrics)
-                continue
-            if inv_h[b]:
-                results[b][ci] = (None, metrics)    # _validate_audio_output failed (capture.py:433-435)
+            if a_h is None or inv_h[b]:
+                results[b][ci] = (None, {"rssi_db": rssi})   # no audio path / _validate_audio_output failed (:433-435)
                 continue
             au = a_h[b]
-            n_a = au.shape[-1]
-            metrics["signal_power_db"] = float(10.0 * np.log10(np.float32(p_h[b] / max(n_a, 1)) + np.float32(1e-10)))
-            if apply_squelch and cfg.squelch_db is not None and rssi < cfg.squelch_db:
+            if squelch is not None and rssi < squelch:
                 au = torch.zeros_like(au) if return_device else np.zeros_like(au)
-            results[b][ci] = (au, metrics)
+            results[b][ci] = (au, {"rssi_db": rssi, "signal_power_db": float(sp_db[b])})
     return results
 
 

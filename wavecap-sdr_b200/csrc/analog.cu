@@ -645,6 +645,47 @@ __global__ void __launch_bounds__(1024) metrics_select_kernel(const float* __res
 
 }  // namespace wc
 
+// Pinned staging ring for the small per-call parameter arrays of the stateless entry points: the async copy reads the
+// slot when the stream gets to it, so a slot is only reused after its event has completed (no stream synchronise on
+// the call path; the reference calls these entry points from several threads, hence the mutex).
+#include <mutex>
+namespace {
+constexpr int RING_SLOTS = 32;
+constexpr size_t RING_BYTES = 64 * 1024;
+struct ParamRing {
+    std::mutex mu;
+    void* host[RING_SLOTS] = {};
+    cudaEvent_t ev[RING_SLOTS] = {};
+    bool used[RING_SLOTS] = {};
+    int next = 0;
+    bool ok = false, tried = false;
+};
+ParamRing g_ring;
+
+// returns a pinned slot (or nullptr: caller falls back to pageable memory + synchronise)
+void* ring_acquire(size_t bytes, int* slot) {
+    if (bytes > RING_BYTES) return nullptr;
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    if (!g_ring.tried) {
+        g_ring.tried = true;
+        g_ring.ok = true;
+        for (int i = 0; i < RING_SLOTS && g_ring.ok; ++i) {
+            g_ring.ok = cudaHostAlloc(&g_ring.host[i], RING_BYTES, cudaHostAllocDefault) == cudaSuccess &&
+                        cudaEventCreateWithFlags(&g_ring.ev[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        if (!g_ring.ok) cudaGetLastError();
+    }
+    if (!g_ring.ok) return nullptr;
+    const int s = g_ring.next;
+    g_ring.next = (g_ring.next + 1) % RING_SLOTS;
+    if (g_ring.used[s]) cudaEventSynchronize(g_ring.ev[s]);
+    g_ring.used[s] = true;
+    *slot = s;
+    return g_ring.host[s];
+}
+void ring_release(int slot, cudaStream_t st) { cudaEventRecord(g_ring.ev[slot], st); }
+}  // namespace
+
 using namespace wc;
 
 // ---------------------------------------------------------------------------------------------
@@ -835,7 +876,11 @@ int wc_front_run(const void* iq_dev, int fmt, int n, int n_chunks, long long chu
                "wc_front_run: null argument");
     WC_REQUIRE(n_ch >= 1 && n_ch <= 4096, "wc_front_run: n_ch out of range");
     cudaStream_t st = (cudaStream_t)stream;
-    std::vector<FrontChan> ch(n_ch);
+    int slot = -1;
+    FrontChan* pinned = reinterpret_cast<FrontChan*>(ring_acquire(sizeof(FrontChan) * n_ch, &slot));
+    std::vector<FrontChan> pageable;
+    if (!pinned) pageable.resize(n_ch);
+    FrontChan* ch = pinned ? pinned : pageable.data();
     for (int c = 0; c < n_ch; ++c) {
         FrontChan& f = ch[c];
         f.mode = modes[c];
@@ -846,10 +891,14 @@ int wc_front_run(const void* iq_dev, int fmt, int n, int n_chunks, long long chu
         f.bfo_turns = bfo_hz ? bfo_hz[c] / (double)sample_rate : 0.0;
         f.disc_scale = (float)((double)sample_rate / (2.0 * M_PI * 75000.0));
     }
-    WC_CUDA(cudaMemcpyAsync(chan_scratch_dev, ch.data(), sizeof(FrontChan) * n_ch, cudaMemcpyHostToDevice, st));
+    WC_CUDA(cudaMemcpyAsync(chan_scratch_dev, ch, sizeof(FrontChan) * n_ch, cudaMemcpyHostToDevice, st));
+    if (pinned) ring_release(slot, st);
     WC_CUDA(cudaMemsetAsync(power_dev, 0, sizeof(double) * (size_t)n_chunks * n_ch, st));
     WC_CUDA(cudaMemsetAsync(nonfinite_dev, 0, sizeof(int) * (size_t)n_chunks, st));
-    if (n <= 0) return 0;
+    if (n <= 0) {
+        if (!pinned) WC_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
     FrontArgs a;
     a.iq = iq_dev;
     a.chunk_stride = chunk_stride;
@@ -864,8 +913,7 @@ int wc_front_run(const void* iq_dev, int fmt, int n, int n_chunks, long long chu
     a.nonfinite = nonfinite_dev;
     front_kernel<<<dim3((n + FR_TILE - 1) / FR_TILE, n_chunks), FR_THREADS, 0, st>>>(a);
     WC_CUDA(cudaGetLastError());
-    // the pageable host vector must outlive the async copy
-    WC_CUDA(cudaStreamSynchronize(st));
+    if (!pinned) WC_CUDA(cudaStreamSynchronize(st));   // a pageable host vector must outlive the async copy
     return 0;
 }
 
