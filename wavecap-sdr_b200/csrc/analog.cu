@@ -411,8 +411,99 @@ struct ResampArgs {
 };
 
 constexpr int RS_WARPS = 8;
+constexpr int RS_R = 8;   // outputs of one polyphase branch per warp task
 
+// One warp computes RS_R outputs that use the SAME polyphase branch (m = m0 + up*k: the branch index repeats every `up`
+// outputs once up/down are reduced), lanes striding over the branch's taps: every tap is loaded once per RS_R
+// multiply-adds instead of once per multiply-add. With one output per warp the kernel was bound by L1 bandwidth
+// (12 B per float64 FMA); this form moves 5 B.
 __global__ void __launch_bounds__(RS_WARPS * 32) resample_kernel(const ResampArgs a) {
+    const int seq = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* xs = a.x + (long long)seq * a.seq_stride;
+    float scale = 1.0f;
+    if (a.epi == 1 || a.epi == 3) {
+        const float rms = (float)sqrt(a.sumsq[seq] / (double)a.n_in);
+        if (rms > a.min_rms) scale = (float)((double)a.target_rms / (double)rms);
+    }
+    double pw = 0.0;
+    bool bad = false;
+    // tasks: (branch residue m0 in [0, up), group g of RS_R outputs m0 + up*(RS_R*g + r))
+    const int per_branch = (a.n_out + a.up - 1) / a.up;            // upper bound of outputs per residue
+    const int groups = (per_branch + RS_R - 1) / RS_R;
+    const long long n_tasks = (long long)groups * a.up;
+    for (long long task = (long long)blockIdx.x * RS_WARPS + warp; task < n_tasks; task += (long long)gridDim.x * RS_WARPS) {
+        const int m0 = (int)(task % a.up);
+        const int g = (int)(task / a.up);
+        const int mfirst = m0 + a.up * (RS_R * g);
+        if (mfirst >= a.n_out) continue;
+        const long long Q0 = a.q0 + (long long)mfirst * a.down;
+        long long phi = Q0 % a.up;
+        if (phi < 0) phi += a.up;
+        const double* h = a.hp + phi * a.tpp;
+        // output r: Q_r = Q0 + r*up*down -> nmax_r = nmax_0 + r*down (same branch)
+        const long long nmax0 = (Q0 - phi) / a.up;
+        int nr = 0;          // valid outputs in this task
+        while (nr < RS_R && mfirst + a.up * nr < a.n_out) ++nr;
+        double acc[RS_R];
+#pragma unroll
+        for (int r = 0; r < RS_R; ++r) acc[r] = 0.0;
+        // interior: every output of the task has all of [i_in_lo, i_in_hi] inside its input range
+        // valid i for output r: max(0, nmax_r - n_in + 1) <= i <= min(tpp - 1, nmax_r)
+        const long long nmax_last = nmax0 + (long long)(nr - 1) * a.down;
+        long long lo = nmax_last - a.n_in + 1;
+        if (lo < 0) lo = 0;
+        long long hi = (nmax0 < a.tpp - 1) ? nmax0 : a.tpp - 1;
+        if (nr == RS_R && lo <= hi) {
+            for (int i = (int)lo + lane; i <= (int)hi; i += 32) {
+                const double hv = h[i];
+                const float* xp = xs + (nmax0 - i);
+#pragma unroll
+                for (int r = 0; r < RS_R; ++r) acc[r] = fma(hv, (double)xp[(long long)r * a.down], acc[r]);
+            }
+            // edges of the individual outputs outside the common range
+#pragma unroll
+            for (int r = 0; r < RS_R; ++r) {
+                const long long nm = nmax0 + (long long)r * a.down;
+                long long l = nm - a.n_in + 1;
+                if (l < 0) l = 0;
+                const long long hh = (nm < a.tpp - 1) ? nm : a.tpp - 1;
+                for (long long i = l + lane; i < lo; i += 32) acc[r] = fma(h[i], (double)xs[nm - i], acc[r]);
+                for (long long i = hi + 1 + lane; i <= hh; i += 32) acc[r] = fma(h[i], (double)xs[nm - i], acc[r]);
+            }
+        } else {
+            for (int r = 0; r < nr; ++r) {
+                const long long nm = nmax0 + (long long)r * a.down;
+                long long l = nm - a.n_in + 1;
+                if (l < 0) l = 0;
+                const long long hh = (nm < a.tpp - 1) ? nm : a.tpp - 1;
+                for (long long i = l + lane; i <= hh; i += 32) acc[r] = fma(h[i], (double)xs[nm - i], acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RS_R; ++r) {
+            const double sum = warp_sum(acc[r]);
+            if (lane == 0 && r < nr) {
+                float v = (float)sum;  // resample_poly(...).astype(float32)
+                if (a.epi == 1) v = soft_clip_fm((float)(sum * (double)scale));
+                else if (a.epi == 2) v = soft_clip_fm(v);
+                else if (a.epi == 3) v = (float)(sum * (double)scale);
+                else if (a.epi == 4) v = soft_clip_agc(v);
+                a.out[(long long)seq * a.n_out + (mfirst + a.up * r)] = v;
+                pw += (double)(v * v);
+                if (!isfinite(v) || fabsf(v) > a.max_abs) bad = true;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (a.power && pw != 0.0) atomicAdd(a.power + seq, pw);
+        if (a.invalid && bad) atomicExch(a.invalid + seq, 1);
+    }
+}
+
+// one output per warp: used when the outputs of a branch are far apart in the input (large `down`), where the grouped
+// form above gains nothing — that case is bound by the float64 pipe (DFMA + the f32->f64 conversions), not by L1
+__global__ void __launch_bounds__(RS_WARPS * 32) resample_single_kernel(const ResampArgs a) {
     const int seq = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* xs = a.x + (long long)seq * a.seq_stride;
@@ -859,9 +950,20 @@ int wc_resampler_run(wc_resampler* h, const float* x_dev, int n_in, long long se
     a.power = power_dev;
     a.invalid = invalid_dev;
     a.max_abs = max_abs;
-    int bx = (int)((n_out + RS_WARPS - 1) / RS_WARPS);
+    const long long per_branch = (n_out + h->up - 1) / h->up;
+    const long long n_tasks = ((per_branch + RS_R - 1) / RS_R) * h->up;
+    int bx = (int)((n_tasks + RS_WARPS - 1) / RS_WARPS);
+    if (bx < 1) bx = 1;
     if (bx > 148 * 8) bx = 148 * 8;
-    resample_kernel<<<dim3(bx, n_seq), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    // grouped kernel only while the RS_R outputs of a task read one L1-friendly window (measured on B200: 1/50 resampler
+    // 11 % faster grouped, 3/625 resampler 14 % slower)
+    if ((long long)(RS_R - 1) * h->down * (long long)sizeof(float) <= 8192) {
+        resample_kernel<<<dim3(bx, n_seq), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    } else {
+        int b1 = (int)((n_out + RS_WARPS - 1) / RS_WARPS);
+        if (b1 > 148 * 8) b1 = 148 * 8;
+        resample_single_kernel<<<dim3(b1, n_seq), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
+    }
     WC_CUDA(cudaGetLastError());
     return 0;
 }
