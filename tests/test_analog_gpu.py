@@ -3,7 +3,7 @@ Tolerance (BASELINE.json north_star): audio within 1e-4 relative RMS; dB metrics
 import numpy as np
 import pytest
 
-from conftest import rel_rms, golden_path
+from conftest import rel_rms, golden_path, wrap_rel_rms
 from oracle import analog as oa
 
 pytestmark = pytest.mark.gpu
@@ -160,3 +160,22 @@ def test_decimate_iq_for_p25(native):
     assert r2 == 48000 and np.array_equal(y2, x[::100])
     y3, r3 = decimate_iq_for_p25(x, 48000)
     assert y3 is x and r3 == 48000
+
+
+def test_rds_path_input_is_the_front_end_output(native):
+    """capture.py:2869-2884: the RDS decoder is fed quadrature_demod(freq_shift(iq)); process_channels_batch hands it out."""
+    from oracle import analog as oa
+    from wavecap_sdr_b200.capture import ChannelConfig, apply_mode_defaults, process_channels_batch
+
+    fs, n = 2_400_000, 24_000
+    rng = np.random.default_rng(12)
+    x = ((rng.standard_normal(2 * n) + 1j * rng.standard_normal(2 * n)) * 0.2).astype(np.complex64)
+    cfg = apply_mode_defaults("wbfm", ChannelConfig(id="a", capture_id="c", mode="wbfm", offset_hz=150000.0))
+    res = process_channels_batch(x, fs, [cfg], n_chunks=2, want_fm_baseband=True)
+    for b in range(2):
+        ref = oa.quadrature_demod(oa.freq_shift(x[b * n:(b + 1) * n], 150000.0, fs), fs)
+        got = res[b][0][1]["fm_baseband"]
+        period = 2 * np.pi * float(np.float32(fs / (2.0 * np.pi * 75000.0)))
+        assert wrap_rel_rms(got, ref, period) < 1e-5
+    cfg.enable_rds = False
+    assert "fm_baseband" not in process_channels_batch(x, fs, [cfg], n_chunks=2, want_fm_baseband=True)[0][0][1]

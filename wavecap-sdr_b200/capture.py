@@ -166,14 +166,17 @@ def _chain_signature(cfg: ChannelConfig, sample_rate: int):
 
 
 def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig], *, n_chunks: int = 1,
-                           in_fmt: str = "cf32", apply_squelch: bool = False, return_device: bool = False):
+                           in_fmt: str = "cf32", apply_squelch: bool = False, return_device: bool = False,
+                           want_fm_baseband: bool = False):
     """`_process_channel_dsp_stateless` for every (chunk, channel) pair of a batch.
 
     samples: complex64 [n_chunks*N] / [n_chunks, N] (in_fmt="cf32") or interleaved int16 I,Q
     [n_chunks, N, 2] (in_fmt="cs16", scaled by 1/32768 like cli.py:449-453); numpy or CUDA tensor.
     Returns results[chunk][channel] = (audio float32 | None, metrics dict) with the reference's keys
     (`rssi_db`, `signal_power_db`). With apply_squelch, audio of channels whose rssi_db is below
-    cfg.squelch_db is zeroed (capture.py:2918-2921).
+    cfg.squelch_db is zeroed (capture.py:2918-2921). With want_fm_baseband, WBFM channels with enable_rds at a capture
+    rate >= 114 kHz also get `fm_baseband` in their metrics: quadrature_demod(freq_shift(iq)) before the MPX filter, the
+    input the reference hands its RDS decoder (capture.py:2869-2884) — it is the front end's own output, no extra pass.
     """
     import torch
 
@@ -259,6 +262,8 @@ def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig],
             if squelch is not None and rssi < squelch:
                 au = torch.zeros_like(au) if return_device else np.zeros_like(au)
             results[b][ci] = (au, {"rssi_db": rssi, "signal_power_db": float(sp_db[b])})
+            if want_fm_baseband and cfg.mode == "wbfm" and cfg.enable_rds and sample_rate >= 114000:
+                results[b][ci][1]["fm_baseband"] = out[ci, b] if return_device else out[ci, b].cpu().numpy()
     return results
 
 
