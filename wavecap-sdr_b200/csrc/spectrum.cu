@@ -407,6 +407,77 @@ __global__ void __launch_bounds__(SP_THREADS, 3) spectrum_pass_a3(const float2* 
     }
 }
 
+// pass A5 = A3 with the next frame's 16 operands prefetched into registers while the current frame is transformed
+// (A3 loads, waits, computes, stores: between the load bursts nothing is in flight). The Hann coefficients are re-read
+// from L1 every frame instead of being held in 16 registers, which pays for the prefetch buffer.
+template <int MINB>
+__global__ void __launch_bounds__(SP_THREADS, MINB) spectrum_pass_a5(const float2* __restrict__ iq, long long frame_stride,
+                                                                     const float* __restrict__ window, u64* __restrict__ scratch,
+                                                                     int n_frames) {
+    __shared__ SpSmemA3 sm;
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * SP_COLS;
+    {
+        float sn, cs;
+        sincospif(-(float)((tid >> 4) * (tid & 15)) * (1.0f / 128.0f), &sn, &cs);
+        sm.tw[tid] = make_float2(cs, sn);
+    }
+    const int t = tid >> 4, col = tid & 15;
+    const int n2 = c0 + col;
+    float2 base, step;
+    {
+        float sn, cs;
+        sincospif(-(float)(n2 * t) * (1.0f / 32768.0f), &sn, &cs);
+        base = make_float2(cs, sn);
+        sincospif(-(float)(n2 * 16) * (1.0f / 32768.0f), &sn, &cs);
+        step = make_float2(cs, sn);
+    }
+    u64* ex = sm.ex + col * SP_STRIDE;
+    const u64* xw = reinterpret_cast<const u64*>(iq);
+    const float* wp = window + t * SP_N2 + n2;
+    u64 nx[16];
+    int f = blockIdx.y;
+    if (f < n_frames) {
+        const u64* x = xw + (long long)f * frame_stride;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nx[i] = __ldcs(x + (t + 16 * i) * SP_N2 + n2);
+    }
+    for (; f < n_frames; f += gridDim.y) {
+        u64 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = mul2(nx[i], bc2(__ldg(wp + 16 * i * SP_N2)));
+        const int fn = f + gridDim.y;
+        if (fn < n_frames) {
+            const u64* x = xw + (long long)fn * frame_stride;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) nx[i] = __ldcs(x + (t + 16 * i) * SP_N2 + n2);
+        }
+        fft16(v);
+        __syncthreads();   // previous frame's exchange reads are done
+#pragma unroll
+        for (int ka = 0; ka < 16; ++ka) {
+            u64 w = v[rev4(ka)];
+            if (ka > 0) {
+                const float2 q = sm.tw[ka * 16 + t];
+                w = twid(w, q.x, -q.y);
+            }
+            ex[t * 17 + ka] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = ex[m * 17 + t];
+        fft16(v);
+        u64* T = scratch + (long long)f * SP_N;
+        float2 w = base;
+#pragma unroll
+        for (int kb = 0; kb < 16; ++kb) {
+            const int k1 = t + 16 * kb;
+            T[k1 * SP_N2 + n2] = twid(v[rev4(kb)], w.x, -w.y);
+            w = cmul(w, step);
+        }
+    }
+}
+
 // pass B3: thread (g = tid >> 4 row, t = tid & 15); the next frame's row is prefetched into registers while the
 // current one is transformed; exchange is half-warp local.
 struct SpSmemB3 {
@@ -470,6 +541,76 @@ __global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_b3(const u64* __r
         const int k2 = id >> 4, row = id & 15;
         const int k = (r0 + row) + SP_N1 * k2;
         o[k ^ (SP_N / 2)] = so[k2 * 17 + row];  // fftshift
+    }
+}
+
+// pass B5 = B3 made persistent over averaging groups: a CTA walks groups grp, grp + gridDim.y, ... and the row of the
+// NEXT frame (also across a group boundary) is always in flight while the current one is transformed. B3 handles one group
+// of `avg` (typically 4) frames per CTA, so a quarter of its loads and its table set-up were never overlapped.
+__global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_b5(const u64* __restrict__ scratch, int avg, int n_frames,
+                                                                  int n_groups, float* __restrict__ out) {
+    __shared__ SpSmemB3 sm;
+    float* const so_buf = reinterpret_cast<float*>(sm.ex);   // output staging shares the exchange area
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * SP_COLS;
+    {
+        float sn, cs;
+        sincospif(-(float)((tid >> 4) * (tid & 15)) * (1.0f / 128.0f), &sn, &cs);
+        sm.tw[tid] = make_float2(cs, sn);
+    }
+    __syncthreads();
+    const int g = tid >> 4, t = tid & 15;
+    u64* ex = sm.ex + g * SP_STRIDE;
+    const long long row_off = (long long)(r0 + g) * SP_N2 + t;
+    u64 nx[16];
+    int grp = blockIdx.y;
+    if (grp < n_groups) {
+        const u64* T = scratch + (long long)(grp * avg) * SP_N + row_off;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nx[i] = __ldg(T + 16 * i);
+    }
+    for (; grp < n_groups; grp += gridDim.y) {
+        const int f0 = grp * avg;
+        const int cnt = min(avg, n_frames - f0);
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        for (int f = 0; f < cnt; ++f) {
+            u64 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = nx[i];
+            // next frame of this group, or the first frame of this CTA's next group
+            long long nf = -1;
+            if (f + 1 < cnt) nf = f0 + f + 1;
+            else if (grp + (int)gridDim.y < n_groups) nf = (long long)(grp + gridDim.y) * avg;
+            if (nf >= 0) {
+                const u64* T = scratch + nf * SP_N + row_off;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) nx[i] = __ldg(T + 16 * i);
+            }
+            fft256_core(ex, sm.tw, t, v);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float re = lo2(v[rev4(q)]), im = hi2(v[rev4(q)]);
+                const float mag = sqrtf(fmaf(re, re, im * im));
+                acc[q] += 6.02059991327962f * __log2f(mag + 1e-10f);  // 20*log10(x) = 20*log10(2)*log2(x)
+            }
+            __syncwarp();
+        }
+        __syncthreads();   // every half-warp is done with its exchange area
+        const float inv = 1.0f / (float)cnt;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) so_buf[(t + 16 * q) * 17 + g] = acc[q] * inv;
+        __syncthreads();
+        float* o = out + (long long)grp * SP_N;
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) {
+            const int id = tid + SP_THREADS * j;
+            const int k2 = id >> 4, row = id & 15;
+            const int k = (r0 + row) + SP_N1 * k2;
+            o[k ^ (SP_N / 2)] = so_buf[k2 * 17 + row];  // fftshift
+        }
+        __syncthreads();   // staged output consumed before the next group's exchanges overwrite it
     }
 }
 
@@ -817,10 +958,25 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
                 spectrum_fused_kernel<<<3 * sm_count(), SP_THREADS, 0, st>>>(fa);
             } else if (variant == 3) {
                 int fy = (6 * sm_count()) / 16;   // frames in flight: ~6 CTAs per SM over the 16 column tiles
+                if (const char* e = getenv("WC_SPECTRUM_FY")) fy = atoi(e);
                 if (fy > cnt) fy = cnt;
                 if (fy < 1) fy = 1;
-                spectrum_pass_a3<<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
-                spectrum_pass_b3<<<dim3(SP_N1 / SP_COLS, groups), SP_THREADS, 0, st>>>(T, avg, cnt, o);
+                const char* pa = getenv("WC_SPECTRUM_PASS_A");
+                const int pav = pa ? atoi(pa) : 6;   // measured on B200, 4096 frames: A3 153 GS/s, A5<3> 166, A5<2> 200
+                if (pav == 5) spectrum_pass_a5<3><<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
+                else if (pav == 6) spectrum_pass_a5<2><<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
+                else spectrum_pass_a3<<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
+                const char* pb = getenv("WC_SPECTRUM_PASS_B");
+                const int pbv = pb ? atoi(pb) : 5;   // measured on B200, 4096 frames with pass A5<2>: B3 200 GS/s, B5 210
+                if (pbv == 5) {
+                    int gy = (4 * sm_count()) / 16;   // two waves of the 2 resident CTAs per SM over the 16 row tiles
+                    if (const char* e = getenv("WC_SPECTRUM_GY")) gy = atoi(e);
+                    if (gy > groups) gy = groups;
+                    if (gy < 1) gy = 1;
+                    spectrum_pass_b5<<<dim3(SP_N1 / SP_COLS, gy), SP_THREADS, 0, st>>>(T, avg, cnt, groups, o);
+                } else {
+                    spectrum_pass_b3<<<dim3(SP_N1 / SP_COLS, groups), SP_THREADS, 0, st>>>(T, avg, cnt, o);
+                }
             } else if (variant == 1) {
                 spectrum_pass_a<<<dim3(SP_N2 / SP_COLS, cnt), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T);
                 spectrum_pass_b<<<dim3(SP_N1 / SP_COLS, groups), SP_THREADS, 0, st>>>(T, avg, cnt, o);
