@@ -29,6 +29,10 @@
 
 namespace wc {
 
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
 constexpr int CQ_HIST = 32;     // MMSE_NTAPS (decoders/p25.py:221)
 constexpr int CQ_LPF = 63;
 
@@ -171,9 +175,13 @@ struct CqSyncArgs {
     int* n_sym;              // [C]
 };
 
+constexpr int CQ_TILE = 96;             // new samples staged per step
+constexpr int CQ_RING = 128;            // ring slots per channel: CQ_TILE new + CQ_HIST of look-back
+constexpr int CQ_PITCH = CQ_RING + 1;   // row pitch in float2: rows of different lanes start in different banks
+
 struct CqView {
-    const float2* tail;   // 32 carried samples
-    const float2* x;      // this call's filtered samples
+    const float2* ring;   // this lane's row of the shared-memory ring: sample j of the call sits in slot (j + 32) & 127,
+                          // the 32 carried samples of the previous call in slots 0..31
     const float* mmse;    // shared-memory copy of the 129 x 8 table, rows padded to 9 floats: every thread (channel)
                           // indexes its own row, which would serialise on the constant cache
 };
@@ -181,8 +189,7 @@ constexpr int CQ_ROW = 9;
 
 // sample `back` positions before sample index m of this call (m - back may reach into the tail)
 __device__ __forceinline__ float2 cq_hist(const CqView& v, int m, int back) {
-    const int j = m - back;
-    return (j >= 0) ? v.x[j] : v.tail[CQ_HIST + j];
+    return v.ring[(m - back + CQ_HIST) & (CQ_RING - 1)];
 }
 
 // _mmse_interpolate_at_offset (decoders/p25.py:325-359)
@@ -215,28 +222,52 @@ __device__ __forceinline__ float cq_abs(float2 z) {
 
 __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
     __shared__ float s_mmse[129 * CQ_ROW];
+    __shared__ float2 s_ring[32 * CQ_PITCH];
     for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) s_mmse[(i >> 3) * CQ_ROW + (i & 7)] = c_mmse[i >> 3][i & 7];
-    __syncthreads();
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= a.C) return;
-    CqState S = a.st[ch];
+    const int lane = threadIdx.x;
+    const int c0 = blockIdx.x * 32;
+    const int ch = c0 + lane;
+    const bool live = ch < a.C;
+    // the 32 carried samples of every row
+    for (int r = 0; r < 32 && c0 + r < a.C; ++r) s_ring[r * CQ_PITCH + lane] = a.st[c0 + r].tail[lane];
+    __syncwarp();
+    CqState S;
+    if (live) S = a.st[ch];
+    else memset(&S, 0, sizeof(S));
     CqView v;
     v.mmse = s_mmse;
-    v.tail = a.st[ch].tail;
-    v.x = a.filt + (long long)ch * a.n;
-    unsigned char* out = a.dibits + (long long)ch * a.max_sym;
+    v.ring = s_ring + lane * CQ_PITCH;
+    unsigned char* out = a.dibits + (long long)(live ? ch : 0) * a.max_sym;
     const float HALF_PI_F = (float)1.5707963267948966, PI_F = (float)3.141592653589793, TWO_PI_F = (float)6.283185307179586;
     const float Q_PI_F = (float)0.7853981633974483, TQ_PI_F = (float)2.356194490192345;
     const double PI_D = 3.141592653589793;
     const float omega_lo = (float)(a.k.sps * 0.95), omega_hi = (float)(a.k.sps * 1.05);
     int nsym = 0;
-    // Symbol-driven loop: every lane (channel) first advances its own sample clock to its next firing sample (a
-    // 9-11 iteration inner loop), then all lanes of the warp run the expensive symbol body together. A plain
-    // per-sample loop would execute the body at almost every sample index because the channels' clocks are not aligned.
+    // Tile loop: the filtered samples of the warp's 32 channels are staged CQ_TILE at a time into the shared-memory ring
+    // with 8-byte LDGSTS copies (lanes along the sample axis), then every lane walks its own row. Inside a tile the loop
+    // is symbol-driven: every lane first advances its own sample clock to its next firing sample (9-11 cheap iterations),
+    // then the lanes that fired run the expensive symbol body together — a plain per-sample loop would execute the body
+    // at almost every sample index because the channels' clocks are not aligned.
     int m = -1;
+    for (int base = 0; base < a.n; base += CQ_TILE) {
+        const int lim = min(CQ_TILE, a.n - base);
+        const int tile_end = base + lim;
+        __syncwarp();
+        for (int r = 0; r < 32 && c0 + r < a.C; ++r) {
+            const float2* xr = a.filt + (long long)(c0 + r) * a.n + base;
+            float2* row = s_ring + r * CQ_PITCH;
+#pragma unroll
+            for (int k = 0; k < CQ_TILE / 32; ++k) {
+                const int i = lane + 32 * k;
+                if (i < lim) cp_async8(&row[(base + i + CQ_HIST) & (CQ_RING - 1)], xr + i);
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
     for (;;) {
         bool fire = false;
-        while (m + 1 < a.n) {
+        while (live && m + 1 < tile_end) {
             ++m;
             if (S.clock_is_f32) {
                 S.clock_f = __fadd_rn(S.clock_f, S.sym_time_f);
@@ -247,7 +278,8 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
             }
             if (fire) break;
         }
-        if (!fire) break;
+        if (!__any_sync(0xffffffffu, fire)) break;
+        if (!fire) continue;
         int imu;
         if (S.clock_is_f32) {
             S.clock_f = __fsub_rn(S.clock_f, 1.0f);
@@ -351,12 +383,12 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
         S.prev = curr;
         S.first = 0;
     }
+    }
+    if (!live) return;
     // carry the ring: last 32 of (tail ++ x)
     float2 nt[CQ_HIST];
-#pragma unroll
     for (int i = 0; i < CQ_HIST; ++i) nt[i] = cq_hist(v, a.n - 1, CQ_HIST - 1 - i);
     CqState* G = &a.st[ch];
-#pragma unroll
     for (int i = 0; i < CQ_HIST; ++i) G->tail[i] = nt[i];
     G->freq_offset = S.freq_offset;
     G->clock_d = S.clock_d;
