@@ -183,3 +183,49 @@ def test_time_slabs_equal_the_unsharded_call(native, world):
             else:
                 assert torch.equal(got, exp)
             assert np.array_equal(ranks[-1].arm_history, whole.arm_history)
+
+
+@pytest.mark.parametrize("frames", [1, 2, 7, 8, 9, 15, 16, 17, 23, 24, 25, 31, 32, 33, 255, 256, 257, 263, 700])
+def test_c5_fused_fm_ragged_frame_counts(native, frames):
+    """run / sub-tile boundaries of the pipelined kernel: prologue only, one fast sub-tile, ragged last sub-tile, several
+    runs (first run emits R frames, later ones R-1 after a warm-up frame)."""
+    ch = _chan(native, 125_000_000, 488281)
+    o = ChannelizerOracle(125_000_000, 488281)
+    n = 256 + 128 * (frames - 1) + 57          # 57 trailing samples that do not make a frame
+    x = _iq(n, 100 + frames)
+    rate = int(ch.channel_sample_rate)
+    period = 2 * np.pi * float(np.float32(rate / (2.0 * np.pi * 75000.0)))
+    for rep in range(2):                        # second call: carried history instead of zeros
+        got = ch.process_fm(x, rate)
+        exp = channelize_fm(o.process_vectorized(x), rate)
+        assert got.shape == exp.shape == (frames, 256)
+        assert wrap_rel_rms(got, exp, period) < TOL if frames > 1 else not got.any()
+    y = ch.process_array(x)
+    assert rel_rms(y, o.process_vectorized(x)) < TOL
+
+
+def test_full_size_fused_fm_equals_discriminator_of_complex_frames(native):
+    """BASELINE config 5 size, 4 chunks in one launch (R = 256 runs): the fused discriminator output equals
+    angle(y_b * conj(y_{b-1})) * scale of the complex-mode output of the same kernel family, per chunk, d_0 = 0."""
+    import torch
+
+    ch = _chan(native, 125_000_000, 488281)
+    n, b = 6_250_000, 4
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.view_as_complex(torch.randn((n * b, 2), generator=g, device="cuda") * 0.5)
+    rate = int(ch.channel_sample_rate)
+    y = ch.process_batch(x, b)
+    ch.reset()
+    d = ch.process_batch(x, b, fm=True, demod_sample_rate=rate)
+    F = 48827
+    assert tuple(y.shape) == (b * F, 256) and tuple(d.shape) == (b * F, 256)
+    scale = float(np.float32(rate / (2.0 * np.pi * 75000.0)))
+    y = y.reshape(b, F, 256)
+    ref = torch.zeros((b, F, 256), dtype=torch.float32, device="cuda")
+    ref[:, 1:] = torch.angle(y[:, 1:] * torch.conj(y[:, :-1])) * scale
+    diff = d.reshape(b, F, 256) - ref
+    period = 2 * np.pi * scale
+    diff = diff - period * torch.round(diff / period)
+    err = float(diff.double().pow(2).mean().sqrt() / ref.double().pow(2).mean().sqrt())
+    assert err < 1e-4
+    assert not bool(d.reshape(b, F, 256)[:, 0].any())
