@@ -46,9 +46,16 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=128, help="50 ms chunks per step (device-resident leg)")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks per step of the host-buffer leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
-    ap.add_argument("--mode", default="replicas", choices=["replicas", "broadcast"],
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "broadcast", "pull"],
                     help="replicas: one independent capture per GPU (headline, weak scaling); broadcast: ONE capture, "
-                         "each block NCCL-broadcast from rank 0 and time-sharded over the ranks (north-star-literal, strong)")
+                         "each block NCCL-broadcast from rank 0 and time-sharded over the ranks (north-star-literal, strong); "
+                         "pull: ONE capture, rank 0's block mapped into every rank, each rank's channelizer kernel pulls "
+                         "only its weighted time slab over NVLink while it computes (no collective on the data path)")
+    ap.add_argument("--pull-local-share", type=float, default=0.0,
+                    help="pull mode: share of each block rank 0 keeps (0 = local/(local+link) from --pull-rates)")
+    ap.add_argument("--pull-tune-rounds", type=int, default=3,
+                    help="pull mode: rounds of share re-balancing from measured per-rank kernel times (0 = keep the initial shares)")
+    ap.add_argument("--pull-rates", default="207,96", help="pull mode: rank 0's resident rate and the NVLink egress bound, GS/s")
     ap.add_argument("--bcast-chunks", type=int, default=8, help="50 ms chunks per broadcast block")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-samples", type=int, default=3_000_000, help="cpu_baseline samples per worker")
@@ -306,6 +313,173 @@ def run_broadcast(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_pull(args, rank, local_rank, world):
+    """ONE capture for the whole box without a data-path collective: rank 0's blocks (bcast-chunks x 6.25 M samples,
+    double-buffered in ITS HBM = the ingest GPU) live in a sharding.PeerRegion mapped into every rank. Each rank's
+    channelizer kernel reads its time slab (9-frame halo) straight out of that memory — for the other ranks the bulk
+    async copies that feed the FIR cross NVLink, overlapped tile by tile with the FFT/discriminator of the previous
+    tile — so a rank receives only what it processes and rank 0, which reads at HBM speed, keeps the larger share
+    (`slab_weights`). Flags in the region order the ranks on their streams: rank 0 publishes READY[buffer] = block
+    number, rank r publishes DONE[r][buffer] when its kernel has finished reading, rank 0 re-uses a buffer only after
+    every DONE. Bound: rank 0's NVLink egress feeds all other ranks, so the job runs at about local + link rate."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import wavecap_sdr_b200._native as N
+    from wavecap_sdr_b200.dsp.channelizer import PolyphaseChannelizer
+    from wavecap_sdr_b200.sharding import PeerRegion, frame_slab, slab_weights
+
+    torch.cuda.set_device(local_rank)
+    N.init(local_rank)
+    if world > 1:
+        init_nccl(local_rank)
+    n = args.bcast_chunks * CHUNK
+    local_rate, link_rate = (float(v) for v in args.pull_rates.split(","))
+    if world == 1:
+        weights = [1.0]
+    elif args.pull_local_share > 0:
+        a = min(args.pull_local_share, 1.0)
+        weights = [a] + [(1.0 - a) / (world - 1)] * (world - 1)
+    else:
+        weights = slab_weights(world, local_rate, link_rate)
+    ch = PolyphaseChannelizer(FS, BW)
+    region = PeerRegion(2 * 8 * n, src=0)
+    if rank == 0:
+        g = torch.Generator(device="cuda").manual_seed(4321)
+        for b in range(2):
+            torch.view_as_real(region.payload_tensor(b * n, n)).normal_(0.0, 0.5, generator=g)
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    blocks = [region.payload_tensor(b * n, n) if rank == 0 else region.span(b * n, n) for b in range(2)]
+    timed_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    READY, DONE = 0, 16
+    it = [0]           # block counter: sequence numbers only grow, also across the tuning rounds
+
+    def step(kernel_events=None):
+        i = it[0]
+        it[0] += 1
+        b, seq = i & 1, i + 1
+        if rank == 0:
+            if world > 1 and i >= 2:        # the buffer is free once every reader has finished block i - 2
+                region.wait_flags(DONE + 2 + b, world - 1, seq - 2, timeout_ms=5000, timed_out=timed_out, stride=2)
+            region.set_flag(READY + b, seq)  # (a live capture writes block i into the buffer before this)
+        else:
+            region.wait_flags(READY + b, 1, seq, timeout_ms=5000, timed_out=timed_out)
+        if kernel_events is not None:
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+        rows, _ = ch.process_slab(blocks[b], world, rank, fm=True, weights=weights)
+        if kernel_events is not None:
+            eb.record()
+            kernel_events.append((ea, eb))
+        if rank != 0:
+            region.set_flag(DONE + 2 * rank + b, seq)
+        return rows
+
+    # share tuning: a rank's rate = its share / the time its own kernel took (flag waits excluded); new shares are
+    # proportional to the rates, which equalises the finish times (the pullers share rank 0's egress, so a few rounds)
+    tuning = []
+    for _ in range(args.pull_tune_rounds if world > 1 and args.pull_local_share <= 0 else 0):
+        evs = []
+        for k in range(6):
+            step(evs if k >= 2 else None)
+        torch.cuda.synchronize()
+        mine = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        t = torch.tensor([mine], device="cuda", dtype=torch.float64)
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        times = [max(float(x.item()), 1e-3) for x in every]
+        rates = [w_ / t_ for w_, t_ in zip(weights, times)]
+        tuning.append({"weights": [round(x, 4) for x in weights], "kernel_ms": [round(x, 4) for x in times]})
+        weights = [r_ / sum(rates) for r_ in rates]
+    slab = frame_slab(ch.frames_for(n), world, rank, weights=weights)
+
+    # cross-check on the real link: a slab pulled by the kernel equals the same slab staged with a plain copy first
+    check = None
+    if rank != 0 and slab.n_frames > 0:
+        probe = PolyphaseChannelizer(FS, BW)
+        pulled, _ = probe.process_slab(blocks[0], world, rank, fm=True, weights=weights)
+        staged = torch.empty((n,), dtype=torch.complex64, device="cuda")
+        N.check(N.lib().wc_peer_copy(C.c_void_p(staged.data_ptr() + 8 * slab.sample0), C.c_void_p(blocks[0].ptr + 8 * slab.sample0),
+                                     8 * slab.n_samples, N.torch_stream_ptr()))
+        probe2 = PolyphaseChannelizer(FS, BW)
+        local, _ = probe2.process_slab(staged, world, rank, fm=True, weights=weights)
+        check = bool(torch.equal(pulled, local)) and bool(torch.isfinite(pulled).all()) and bool(pulled.abs().sum() > 0)
+        del staged, pulled, local, probe, probe2
+        torch.cuda.synchronize()
+    ok = torch.tensor([1 if check in (None, True) else 0], device="cuda", dtype=torch.int32)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) != 1:
+        raise SystemExit("pull mode: a slab read through peer memory differs from the staged copy")
+
+    w = max(3, args.warmup)
+    rows = None
+    for _ in range(w):
+        rows = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        rows = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    my_ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([my_ms], device="cuda", dtype=torch.float64)
+    per_rank = [torch.zeros_like(t) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, t)
+        dist.all_reduce(timed_out, op=dist.ReduceOp.MAX)
+    else:
+        per_rank = [t]
+    if int(timed_out.item()) != 0:
+        raise SystemExit("pull mode: a flag wait timed out (a rank fell behind or died)")
+    ms = max(float(x.item()) for x in per_rank)
+    value = n / (ms * 1e-3) / 1e6
+    if rank == 0:
+        slabs = [frame_slab(ch.frames_for(n), world, r, weights=weights) for r in range(world)]
+        pulled_bytes = sum(8 * s.n_samples for s in slabs[1:])
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "MS/s", "n_gpus": world, "steps": args.steps,
+            "warmup": w, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mode": "pull",
+            "config": {
+                "workload": "C5: ONE 125 MS/s capture resident on rank 0, mapped into every rank (CUDA IPC over NVLink); each rank's "
+                            "256-ch channelizer + FM kernel pulls its own time slab while it computes",
+                "block_samples": n, "frames_per_rank": [s.n_frames for s in slabs], "halo_frames": 9,
+                "slab_weights": [round(x, 4) for x in weights], "share_tuning": tuning,
+                "parallelism": f"{world} weighted time slabs, no data-path collective; READY/DONE flags in peer memory",
+                "bound": "rank 0: its own HBM; the other ranks together: rank 0's NVLink egress (8 B/sample)",
+                "l2": "block (%.0f MB) exceeds the 126 MB L2" % (8 * n / 1e6),
+                "checked": "peer-pulled slab == staged-copy slab on every rank" if world > 1 else "single rank",
+            },
+            "link": {"bytes_pulled_from_rank0_per_step": pulled_bytes,
+                     "rank0_egress_gbs": round(pulled_bytes / (ms * 1e-3) / 1e9, 1) if world > 1 else None,
+                     "ms_per_step_by_rank": [round(float(x.item()), 4) for x in per_rank]},
+            "gpu_launches": (4 if world > 1 else 3) * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    del rows
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    region.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -313,6 +487,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.mode == "pull":
+        run_pull(args, rank, local_rank, world)
         return
     if args.mode == "broadcast":
         run_broadcast(args, rank, local_rank, world)

@@ -49,6 +49,10 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
 /* advance the carried history (arm_history) as if process() had been called on iq_dev[0..n_samples) without
  * computing outputs — for time-sharded multi-GPU runs where another rank emitted the tail of the call. */
 int wc_chan_carry_from(wc_chan* h, const void* iq_dev, long long n_samples, void* stream);
+/* frames each CTA of the M=256 kernels walks (rounded up to 8, clamped to [16, 256]); 0 = sized so the grid is ~6 waves.
+ * Every run re-reads T-1 halo rows, which local L2 absorbs but NVLink does not: callers whose iq_dev is peer memory
+ * (wc_peer_open) raise it so the halo traffic stays at (T-1)/run_frames of the slab. */
+int wc_chan_set_run_frames(wc_chan* h, int run_frames);
 /* same, host buffers: H2D copy + kernels + D2H copy + sync (the reference-facing call). */
 int wc_chan_process_host(wc_chan* h, const void* iq_host, long long n_samples, int n_chunks, int mode,
                          float fm_scale, void* out_host);
@@ -308,6 +312,25 @@ int wc_ccscan_out_len(int n_samples, int sample_rate);
 int wc_ccscan_measure(const void* iq_dev, int n_samples, int sample_rate, const double* offsets_hz, int n_ch,
                       const double* taps65, void* y_dev, double* power_sum_dev, double* power_max_dev, double* corr_dev,
                       void* scratch_dev, void* stream);
+
+/* ---- peer memory: ONE capture fanned out over the GPUs of a box (SURVEY §8e modes ii/iii; the reference's analogue is
+ * Capture._run_thread handing the SAME `samples` array to every channel worker, capture.py:2541-2546). The ingest
+ * rank allocates the IQ region with wc_peer_alloc and ships the 64-byte handle to the other processes (any transport);
+ * they map it with wc_peer_open and pass pointers into it to wc_chan_process / wc_front_run / ... like any device
+ * pointer: the kernels then pull their slab over NVLink themselves (no broadcast, no staging copy). wc_flag_set /
+ * wc_flag_wait order producer and consumers on the stream: sequence numbers in uint32 words of the same region,
+ * system-scope release/acquire; a wait gives up after timeout_ms and sets *timed_out_dev (int32, optional) to 1. */
+#define WC_PEER_HANDLE_BYTES 64
+int wc_peer_alloc(long long bytes, void** dev_out, void* handle_out /* WC_PEER_HANDLE_BYTES */);
+int wc_peer_free(void* dev);
+int wc_peer_open(const void* handle, void** dev_out);
+int wc_peer_close(void* dev);
+/* staging alternative / cross-check: plain async copy between any two device addresses (local or mapped) */
+int wc_peer_copy(void* dst_dev, const void* src_dev, long long bytes, void* stream);
+int wc_flag_set(unsigned* flag_dev, unsigned value, void* stream);
+/* waits until flags_dev[i * stride_words] >= value (wrap-safe) for every i < n_flags (<= 1024) */
+int wc_flag_wait(const unsigned* flags_dev, int n_flags, long long stride_words, unsigned value, int timeout_ms,
+                 int* timed_out_dev, void* stream);
 
 #ifdef __cplusplus
 }

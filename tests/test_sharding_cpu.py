@@ -32,6 +32,33 @@ def test_frame_slab_geometry():
     assert frame_slab(3, 8, 7).n_frames == 0 and frame_slab(3, 8, 7).n_samples == 0
 
 
+def test_weighted_slabs():
+    from wavecap_sdr_b200.sharding import slab_weights, weighted_range
+
+    w = slab_weights(8, 207.0, 96.0)
+    assert abs(sum(w) - 1.0) < 1e-12 and abs(w[0] - 207.0 / 303.0) < 1e-12 and len(set(w[1:])) == 1
+    assert slab_weights(1, 207.0, 96.0) == [1.0]
+    F = 390624
+    for weights in (w, [1, 1, 1], [0.0, 1.0], [5, 0, 1]):
+        world = len(weights)
+        r = [weighted_range(F, weights, k) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == F and all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+        tot = float(sum(weights))
+        assert all(abs((b - a) - F * wk / tot) <= 1.0 for (a, b), wk in zip(r, weights))
+        slabs = [frame_slab(F, world, k, weights=weights) for k in range(world)]
+        assert sum(s.n_frames for s in slabs) == F
+        for s in slabs:
+            if s.n_frames:
+                assert s.skip == min(CHAN_HALO_FRAMES, s.f0) and s.sample0 + s.n_samples == (s.f1 - 1) * 128 + 256
+            else:
+                assert s.n_samples == 0
+    assert [weighted_range(10, [1, 1], k) for k in range(2)] == [shard_range(10, 2, k) for k in range(2)]
+    with pytest.raises(ValueError):
+        weighted_range(10, [0, 0], 0)
+    with pytest.raises(ValueError):
+        frame_slab(10, 2, 0, weights=[1.0])
+
+
 def _worker(rank, world, port, n, q):
     import torch
     import torch.distributed as dist

@@ -122,6 +122,7 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_chan_reset", i32, vp)
     fn("wc_chan_process", i32, vp, vp, i64, i32, i64, i32, f32, vp, vp)
     fn("wc_chan_carry_from", i32, vp, vp, i64, vp)
+    fn("wc_chan_set_run_frames", i32, vp, i32)
     fn("wc_chan_process_host", i32, vp, vp, i64, i32, i32, f32, vp)
     # analog chain stages
     fn("wc_front_chan_scratch_bytes", i32, i32)
@@ -211,6 +212,14 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_discdemod_demod", i32, vp, vp, i64, i32, vp, vp, vp, i32, vp)
     fn("wc_discdemod_demod_host", i32, vp, vp, i32, vp, vp, vp, i32)
     fn("wc_discdemod_get_state", i32, vp, i32, vp)
+    # peer memory (one capture, many GPUs)
+    fn("wc_peer_alloc", i32, i64, P(vp), vp)
+    fn("wc_peer_free", i32, vp)
+    fn("wc_peer_open", i32, vp, P(vp))
+    fn("wc_peer_close", i32, vp)
+    fn("wc_peer_copy", i32, vp, vp, i64, vp)
+    fn("wc_flag_set", i32, vp, C.c_uint, vp)
+    fn("wc_flag_wait", i32, vp, i32, i64, C.c_uint, i32, vp, vp)
     for extra in _EXTRA_DECLS:
         extra(l, fn)
 

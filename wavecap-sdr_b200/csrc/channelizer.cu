@@ -688,6 +688,7 @@ struct wc_chan {
     float* d_taps = nullptr;   // [T][M] float32: h[k + j*M]
     float2* d_carried[2] = {nullptr, nullptr};
     int cur = 0;
+    int run_frames = 0;        // wc_chan_set_run_frames: frames per CTA run, 0 = sized from the grid target
     // workspaces
     float2* d_ws = nullptr;   size_t ws_bytes = 0;     // generic path u / y
     void* d_in = nullptr;     size_t in_bytes = 0;     // host API staging
@@ -843,7 +844,9 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
         int occ = 4;  // resident CTAs per SM of the fused-FM kernel; measured on B200: 4 -> 181 GS/s, 5 -> 165, 6 -> 159 (profiles/r01_chan_sweep2.jsonl)
         if (const char* e = getenv("WC_CHAN_OCC")) occ = atoi(e);
         if (mode == WC_CHAN_OUT_COMPLEX) occ = 4;
-        if (const char* e = getenv("WC_CHAN_R")) {
+        if (h->run_frames > 0) {
+            R = h->run_frames;
+        } else if (const char* e = getenv("WC_CHAN_R")) {
             R = atoi(e);
         } else {
             const long long total = F * n_chunks;
@@ -926,6 +929,12 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
 
 // Advance the carried history as if process() had just been called on these n_samples, without computing
 // any output: used by time-sharded runs where another rank emitted the tail of the call.
+int wc_chan_set_run_frames(wc_chan* h, int run_frames) {
+    WC_REQUIRE(h && run_frames >= 0, "wc_chan_set_run_frames: bad argument");
+    h->run_frames = run_frames;
+    return 0;
+}
+
 int wc_chan_carry_from(wc_chan* h, const void* iq_dev, long long n_samples, void* stream_v) {
     WC_REQUIRE(h && iq_dev, "wc_chan_carry_from: null argument");
     const long long F = wc_chan_frames_for(h, n_samples);

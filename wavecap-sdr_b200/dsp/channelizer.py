@@ -118,28 +118,44 @@ class PolyphaseChannelizer:
         return self._run(samples, OUT_FM if fm else OUT_COMPLEX, n_chunks=n_chunks,
                          scale=fm_scale(rate) if fm else 0.0)
 
-    def process_slab(self, block, world: int, rank: int, fm: bool = False, demod_sample_rate: int | None = None):
+    def process_slab(self, block, world: int, rank: int, fm: bool = False, demod_sample_rate: int | None = None,
+                     weights=None):
         """Time shard of ONE `process(block)` call for multi-GPU runs: this rank emits frames [f0, f1) of the call
-        (`sharding.frame_slab`), computing a 9-frame halo in front so the rows equal the unsharded call's. `block` is
-        the whole call's input as a CUDA tensor (every rank holds it after the NCCL broadcast). The carried history
-        is then advanced from the true end of the block, as if the whole call had run here.
+        (`sharding.frame_slab`, shares proportional to `weights` when given), computing a 9-frame halo in front so the
+        rows equal the unsharded call's. `block` is the whole call's input: a CUDA tensor (every rank holds it after
+        the NCCL broadcast) or a `sharding.DeviceSpan` into the ingest rank's memory mapped here (`PeerRegion`) — the
+        kernel then pulls just this slab over NVLink while it computes. The carried history is then advanced from the
+        true end of the block, as if the whole call had run here.
         Returns (rows [f1 - f0, channel_count], f0)."""
         import torch
 
-        from ..sharding import frame_slab
+        from ..sharding import DeviceSpan, frame_slab
 
-        assert N.is_torch_cuda(block) and block.dtype == torch.complex64 and block.is_contiguous()
+        if isinstance(block, DeviceSpan):
+            device = torch.device("cuda", torch.cuda.current_device())
+        else:
+            assert N.is_torch_cuda(block) and block.dtype == torch.complex64 and block.is_contiguous()
+            device = block.device
         n = int(block.numel())
         m = self.channel_count
-        s = frame_slab(self.frames_for(n), world, rank, channel_count=m, halo=self.taps_per_channel)
+        s = frame_slab(self.frames_for(n), world, rank, channel_count=m, halo=self.taps_per_channel, weights=weights)
         mode = OUT_FM if fm else OUT_COMPLEX
         rate = int(self.channel_sample_rate) if demod_sample_rate is None else int(demod_sample_rate)
         rows = s.f1 - s.start_frame
-        out = torch.empty((max(rows, 0), m), device=block.device, dtype=torch.float32 if fm else torch.complex64)
+        out = torch.empty((max(rows, 0), m), device=device, dtype=torch.float32 if fm else torch.complex64)
         if s.n_frames > 0:
-            N.check(N.lib().wc_chan_process(self._h, C.c_void_p(block.data_ptr() + 8 * s.sample0), s.n_samples, 1,
-                                            s.n_samples, mode, fm_scale(rate) if fm else 0.0,
-                                            C.c_void_p(out.data_ptr()), N.torch_stream_ptr()))
+            peer = isinstance(block, DeviceSpan)
+            if peer:
+                # halo rows of every CTA run cross NVLink again: one wave of long runs instead of six of short ones
+                slots = 4 * torch.cuda.get_device_properties(device).multi_processor_count
+                N.check(N.lib().wc_chan_set_run_frames(self._h, min(256, max(32, -(-rows // slots)))))
+            try:
+                N.check(N.lib().wc_chan_process(self._h, C.c_void_p(block.data_ptr() + 8 * s.sample0), s.n_samples, 1,
+                                                s.n_samples, mode, fm_scale(rate) if fm else 0.0,
+                                                C.c_void_p(out.data_ptr()), N.torch_stream_ptr()))
+            finally:
+                if peer:
+                    N.check(N.lib().wc_chan_set_run_frames(self._h, 0))
         N.check(N.lib().wc_chan_carry_from(self._h, C.c_void_p(block.data_ptr()), n, N.torch_stream_ptr()))
         return out[s.skip:], s.f0
 
