@@ -335,6 +335,7 @@ def run_pull(args, rank, local_rank, world):
     N.init(local_rank)
     if world > 1:
         init_nccl(local_rank)
+    bind_to_gpu_numa(local_rank)
     n = args.bcast_chunks * CHUNK
     local_rate, link_rate = (float(v) for v in args.pull_rates.split(","))
     if world == 1:
@@ -358,10 +359,13 @@ def run_pull(args, rank, local_rank, world):
     READY, DONE = 0, 16
     it = [0]           # block counter: sequence numbers only grow, also across the tuning rounds
 
-    def step(kernel_events=None):
+    def step(kernel_events=None, trace=None):
         i = it[0]
         it[0] += 1
         b, seq = i & 1, i + 1
+        if trace is not None:
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            marks[0].record()
         if rank == 0:
             if world > 1 and i >= 2:        # the buffer is free once every reader has finished block i - 2
                 region.wait_flags(DONE + 2 + b, world - 1, seq - 2, timeout_ms=5000, timed_out=timed_out, stride=2)
@@ -371,12 +375,19 @@ def run_pull(args, rank, local_rank, world):
         if kernel_events is not None:
             ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ea.record()
+        if trace is not None:
+            marks[1].record()
         rows, _ = ch.process_slab(blocks[b], world, rank, fm=True, weights=weights)
+        if trace is not None:
+            marks[2].record()
         if kernel_events is not None:
             eb.record()
             kernel_events.append((ea, eb))
         if rank != 0:
             region.set_flag(DONE + 2 * rank + b, seq)
+        if trace is not None:
+            marks[3].record()
+            trace.append(marks)
         return rows
 
     # share tuning: a rank's rate = its share / the time its own kernel took (flag waits excluded); new shares are
@@ -418,24 +429,44 @@ def run_pull(args, rank, local_rank, world):
 
     w = max(3, args.warmup)
     rows = None
+    sampler = ClockSampler(local_rank)
     for _ in range(w):
         rows = step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
     sampler.start()
+    # The ranks leave the host barrier up to a few ms apart — as long as the whole timed region of a short run. Three
+    # more untimed steps let the READY/DONE flags bring the STREAMS back into lockstep (the hosts enqueue ~3x faster
+    # than the GPUs execute), so the start event of every rank sits at the same block boundary.
+    for _ in range(3):
+        rows = step()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(args.steps):
         rows = step()
     e1.record()
+    host_ms = (time.perf_counter() - h0) * 1e3 / args.steps     # host enqueue time per step (no sync inside)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop()
+    # untimed trace of a few more steps: where a rank's step goes (flag wait | slab kernels | flag set), stream time
+    trace = []
+    for _ in range(12):
+        rows = step(trace=trace)
+    torch.cuda.synchronize()
+    seg = [sum(m[k].elapsed_time(m[k + 1]) for m in trace[6:]) / len(trace[6:]) for k in range(3)]
+    per_step = trace[6][0].elapsed_time(trace[-1][0]) / (len(trace) - 7)
+    tr = torch.tensor(seg + [per_step, host_ms], device="cuda", dtype=torch.float64)
+    traces = [torch.zeros_like(tr) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(traces, tr)
+    else:
+        traces = [tr]
     my_ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([my_ms], device="cuda", dtype=torch.float64)
     per_rank = [torch.zeros_like(t) for _ in range(world)]
@@ -467,7 +498,8 @@ def run_pull(args, rank, local_rank, world):
             },
             "link": {"bytes_pulled_from_rank0_per_step": pulled_bytes,
                      "rank0_egress_gbs": round(pulled_bytes / (ms * 1e-3) / 1e9, 1) if world > 1 else None,
-                     "ms_per_step_by_rank": [round(float(x.item()), 4) for x in per_rank]},
+                     "ms_per_step_by_rank": [round(float(x.item()), 4) for x in per_rank],
+                     "trace_ms_by_rank[wait,slab,set,step,host_enqueue]": [[round(float(v), 4) for v in x.tolist()] for x in traces]},
             "gpu_launches": (4 if world > 1 else 3) * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
