@@ -88,28 +88,46 @@ __global__ void __launch_bounds__(FR_THREADS) front_kernel(const FrontArgs a) {
         const FrontChan ch = a.ch[c];
         const long long obase = ((long long)c * a.n_chunks + chunk) * a.n;
         double psum = 0.0;
-        for (int i = tid; i < cnt; i += FR_THREADS) {
+        const bool is_fm = (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM);
+        // whole warps walk the tile (the trip count is warp-uniform): lane l's previous mixed sample is lane l-1's
+        // current one, so the oscillator and the complex product are evaluated once per sample, not twice
+        for (int base = 0; base < cnt; base += FR_THREADS) {
+            const int i = base + tid;
+            const bool live = i < cnt;
             const int n = t0 + i;
-            float2 x1 = tile[i + 1];
-            float2 x0 = tile[i];
-            float2 b1 = x1, b0 = x0;
-            if (ch.shift) {
-                float c1, s1, c0, s0;
-                nco_f32(ch.k32, n, c1, s1);
-                b1 = make_float2(x1.x * c1 - x1.y * s1, x1.x * s1 + x1.y * c1);
-                if (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM) {
-                    nco_f32(ch.k32, n - 1, c0, s0);
-                    b0 = make_float2(x0.x * c0 - x0.y * s0, x0.x * s0 + x0.y * c0);
+            float2 b1 = make_float2(0.f, 0.f);
+            if (live) {
+                const float2 x1 = tile[i + 1];
+                b1 = x1;
+                if (ch.shift) {
+                    float c1, s1;
+                    nco_f32(ch.k32, n, c1, s1);
+                    b1 = make_float2(x1.x * c1 - x1.y * s1, x1.x * s1 + x1.y * c1);
                 }
             }
+            float2 b0 = make_float2(0.f, 0.f);
+            if (is_fm) {
+                b0.x = __shfl_up_sync(0xffffffffu, b1.x, 1);
+                b0.y = __shfl_up_sync(0xffffffffu, b1.y, 1);
+                if ((tid & 31) == 0 && live) {
+                    const float2 x0 = tile[i];
+                    b0 = x0;
+                    if (ch.shift) {
+                        float c0, s0;
+                        nco_f32(ch.k32, n - 1, c0, s0);
+                        b0 = make_float2(x0.x * c0 - x0.y * s0, x0.x * s0 + x0.y * c0);
+                    }
+                }
+            }
+            if (!live) continue;
             const float mag = sqrtf(b1.x * b1.x + b1.y * b1.y);  // np.abs(base)
             psum += (double)(mag * mag);
             float o;
-            if (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM) {
+            if (is_fm) {
                 // angle(x[n] * conj(x[n-1])) * scale, out[0] = 0
                 const float pr = b1.x * b0.x + b1.y * b0.y;
                 const float pi = b1.y * b0.x - b1.x * b0.y;
-                o = (n == 0) ? 0.0f : atan2f(pi, pr) * ch.disc_scale;
+                o = (n == 0) ? 0.0f : fast_atan2f_hi(pi, pr) * ch.disc_scale;
             } else if (ch.mode == WC_MODE_AM) {
                 o = mag;
             } else if (ch.mode == WC_MODE_SSB) {
@@ -400,6 +418,10 @@ struct ResampArgs {
     int ntaps;               // len(h) (unpadded)
     int tpp;                 // taps per phase (ceil(ntaps/up))
     const double* hp;        // [up][tpp] polyphase taps: hp[phi][i] = h[phi + up*i] (0 past the end)
+    const double* g;         // residue form: [up][E][down] taps g[mu][j][r0] = h[B(mu,r0) + up*down*(e_lo[r0] + j)] (0 outside)
+    const float* gf;         // the same table rounded to float32 (mixed-precision residue kernel)
+    const int* e_lo;         // [down] first tap offset of residue r0 (the union over mu of its tap ranges starts here)
+    int E;                   // padded taps per (mu, r0)
     float* out;              // [n_seq][n_out]
     // epilogue
     int epi;                 // 0 none, 1 rms-scale + fm soft clip, 2 fm soft clip, 3 rms-scale only, 4 agc soft clip
@@ -542,6 +564,134 @@ __global__ void __launch_bounds__(RS_WARPS * 32) resample_single_kernel(const Re
     if (lane == 0) {
         if (a.power && pw != 0.0) atomicAdd(a.power + seq, pw);
         if (a.invalid && bad) atomicExch(a.invalid + seq, 1);
+    }
+}
+
+// Residue form of the same sum, for decimating ratios (down >> up), where it removes the per-tap loads entirely.
+// With m = up*a + mu and n = r0 + down*k (r0 in [0, down)), the tap of (m, n) is h[B(mu, r0) + up*down*(a - k)],
+// B = q0 + down*mu - up*r0: for a fixed residue r0 and output phase mu the resampler is a SHORT FIR along k — E ~
+// ntaps/(up*down) taps (7 for 3/625, 21 for 1/50) — and the output is the sum of those FIRs over the residues:
+//   y[up*a + mu] = sum_{r0} sum_{j<E} g[mu][j][r0] * x[r0 + down*(a - e_lo[r0] - j)].
+// A thread owns residues r0 = tid, tid + T, ...; per residue it holds the up*E taps and the RS_A + E - 1 inputs of an
+// RS_A-output block in registers (lanes run along r0: every load is coalesced) and issues up*RS_A*E float64 FMAs for
+// up*E + RS_A + E - 1 loads (3/625: 168 FMAs per 35 loads; the one-output-per-warp form needs two loads per FMA and
+// was bound by L1 bandwidth). Float64 accumulation as scipy does; the per-thread partial sums are reduced across the
+// CTA once per block of up*RS_A outputs.
+constexpr int RS_A = 8;          // outputs per phase per block of outputs
+constexpr int RS_RT = 128;       // threads per CTA (residue owners)
+constexpr int RS_NB = 1;         // output blocks a thread group walks in sequence (measured on B200: 1, 2, 4 within 4 %)
+
+// Thread groups: with down <= 64 residues a CTA splits into G = 2 or 4 groups of 64 / 32 threads, each walking its own
+// output blocks, so small decimation factors (1/50) do not leave most of the CTA idle.
+// T = double: float64 products and sums like scipy. T = float (default): a thread's partial sum — its ~down/128
+// residues x E taps, 40 terms for 3/625 — is formed in float32 (FFMA at 8x the rate of this part's FP64 pipe, no
+// conversions) and everything after that, i.e. the sum over the 128 threads, is float64. Measured against scipy's
+// float64 result: 3/625 and 1/50 outputs differ by a few 1e-8 relative RMS either way — the float32 rounding of the
+// OUTPUT, which the reference applies too (`.astype(np.float32)`), not the accumulation.
+template <int UP, int E, typename T>
+__global__ void __launch_bounds__(RS_RT) resample_residue_kernel(const ResampArgs a, int n_blocks, int G, int NB) {
+    constexpr int W = RS_A + E - 1;
+    __shared__ double part[RS_RT / 32][UP * RS_A];
+    const int seq = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gt = RS_RT / G;                 // threads per group
+    const int grp = tid / gt, gtid = tid - grp * gt;
+    const int wpg = gt >> 5;                  // warps per group
+    const float* xs = a.x + (long long)seq * a.seq_stride;
+    float scale = 1.0f;
+    if (a.epi == 1 || a.epi == 3) {
+        const float rms = (float)sqrt(a.sumsq[seq] / (double)a.n_in);
+        if (rms > a.min_rms) scale = (float)((double)a.target_rms / (double)rms);
+    }
+    double pw = 0.0;
+    bool bad = false;
+    for (int nb = 0; nb < NB; ++nb) {
+        const int blk = (blockIdx.x * G + grp) * NB + nb;       // may run past n_blocks: computes nothing, keeps the barriers
+        const int a0 = blk * RS_A;
+        T pacc[UP][RS_A];
+#pragma unroll
+        for (int mu = 0; mu < UP; ++mu)
+#pragma unroll
+            for (int i = 0; i < RS_A; ++i) pacc[mu][i] = (T)0;
+        if (blk < n_blocks) {
+            const T* gt_tab = (sizeof(T) == 8) ? reinterpret_cast<const T*>(a.g) : reinterpret_cast<const T*>(a.gf);
+            for (int r0 = gtid; r0 < a.down; r0 += gt) {
+                const long long kbase = (long long)a0 - __ldg(a.e_lo + r0) - (E - 1);
+                T w[W];
+#pragma unroll
+                for (int q = 0; q < W; ++q) {
+                    const long long n = r0 + (long long)a.down * (kbase + q);
+                    w[q] = (n >= 0 && n < a.n_in) ? (T)xs[n] : (T)0;     // zero extension, as upfirdn
+                }
+#pragma unroll
+                for (int mu = 0; mu < UP; ++mu) {
+                    T g[E];
+#pragma unroll
+                    for (int j = 0; j < E; ++j) g[j] = __ldg(gt_tab + ((long long)mu * E + j) * a.down + r0);
+#pragma unroll
+                    for (int j = 0; j < E; ++j)
+#pragma unroll
+                        for (int i = 0; i < RS_A; ++i) pacc[mu][i] = fma(g[j], w[E - 1 + i - j], pacc[mu][i]);
+                }
+            }
+        }
+        double acc[UP][RS_A];
+#pragma unroll
+        for (int mu = 0; mu < UP; ++mu)
+#pragma unroll
+            for (int i = 0; i < RS_A; ++i) acc[mu][i] = (double)pacc[mu][i];
+        // warp reduction by recursive halving: three exchange steps leave every lane with UP of the UP*RS_A sums over
+        // its group of 8 lanes (sum index = UP * (4*b0 + 2*b1 + b2) + k, b = bits of the lane), two plain steps finish
+        // them over the 4 groups: 6.75 shuffles per value instead of 10 x 24
+        {
+            double* v = &acc[0][0];
+            constexpr int N0 = UP * RS_A;
+#pragma unroll
+            for (int st = 0; st < 3; ++st) {
+                const int half = N0 >> (st + 1);
+                const bool up_half = (lane >> st) & 1;
+#pragma unroll
+                for (int k = 0; k < half; ++k) {
+                    const double send = up_half ? v[k] : v[k + half];
+                    const double keep = up_half ? v[k + half] : v[k];
+                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << st);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < UP; ++k) {
+                double t = v[k];
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                if (lane < 8) part[warp][UP * (4 * (lane & 1) + 2 * ((lane >> 1) & 1) + ((lane >> 2) & 1)) + k] = t;
+            }
+        }
+        __syncthreads();
+        if (gtid < UP * RS_A && blk < n_blocks) {
+            double sum = 0.0;
+            for (int wv = 0; wv < wpg; ++wv) sum += part[grp * wpg + wv][gtid];
+            const int mu = gtid / RS_A, i = gtid % RS_A;
+            const long long m = (long long)UP * (a0 + i) + mu;
+            if (m < a.n_out) {
+                float v = (float)sum;  // resample_poly(...).astype(float32)
+                if (a.epi == 1) v = soft_clip_fm((float)(sum * (double)scale));
+                else if (a.epi == 2) v = soft_clip_fm(v);
+                else if (a.epi == 3) v = (float)(sum * (double)scale);
+                else if (a.epi == 4) v = soft_clip_agc(v);
+                a.out[(long long)seq * a.n_out + m] = v;
+                pw += (double)(v * v);
+                bad = bad || !isfinite(v) || fabsf(v) > a.max_abs;
+            }
+        }
+        __syncthreads();
+    }
+    // the writers are the first UP * RS_A <= 32 threads of every group: lane-0 warps of the groups hold pw / bad
+    if (gtid < 32) {
+        pw = warp_sum(pw);
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            if (a.power && pw != 0.0) atomicAdd(a.power + seq, pw);
+            if (a.invalid && bad) atomicExch(a.invalid + seq, 1);
+        }
     }
 }
 
@@ -883,7 +1033,19 @@ struct wc_resampler {
     int up, down, ntaps, tpp, half_len;
     long long n_pre_pad, n_pre_remove;
     double* d_hp = nullptr;
+    double* d_g = nullptr;     // residue-form taps [up][E][down] when the ratio qualifies (E > 0)
+    float* d_gf = nullptr;     // the same, float32
+    int* d_elo = nullptr;      // [down]
+    int E = 0, E_need = 0;
 };
+
+// template instances of resample_residue_kernel: (up, padded E)
+static int residue_slot(int up, int e_need) {
+    if (up == 1 && e_need <= 21) return 21;
+    if (up == 2 && e_need <= 12) return 12;
+    if (up == 3 && e_need <= 8) return 8;
+    return 0;
+}
 
 extern "C" {
 
@@ -908,6 +1070,51 @@ int wc_resampler_create(int up, int down, const double* taps, int ntaps, wc_resa
         return -2;
     }
     cudaMemcpy(h->d_hp, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice);
+    // residue form (decimating ratios): tap of (m = up*a + mu, n = r0 + down*k) is h[B + up*down*e], e = a - k
+    if (down >= 32 && up <= 3) {
+        const long long q0 = h->n_pre_remove * down - h->n_pre_pad, UD = (long long)up * down;
+        auto fdiv = [](long long x, long long y) { return (x >= 0) ? x / y : -((-x + y - 1) / y); };   // floor
+        std::vector<int> elo(down, 0);
+        int e_need = 0;
+        for (int r0 = 0; r0 < down; ++r0) {
+            long long lo_min = 1LL << 40, hi_max = -(1LL << 40);
+            for (int mu = 0; mu < up; ++mu) {
+                const long long B = q0 + (long long)down * mu - (long long)up * r0;
+                const long long lo = -fdiv(B, UD);                 // ceil(-B / UD)
+                const long long hi = fdiv((long long)ntaps - 1 - B, UD);
+                if (lo <= hi) {
+                    if (lo < lo_min) lo_min = lo;
+                    if (hi > hi_max) hi_max = hi;
+                }
+            }
+            if (hi_max >= lo_min) {
+                elo[r0] = (int)lo_min;
+                if ((int)(hi_max - lo_min + 1) > e_need) e_need = (int)(hi_max - lo_min + 1);
+            }
+        }
+        const int E = e_need ? residue_slot(up, e_need) : 0;
+        if (E) {
+            std::vector<double> g((size_t)up * E * down, 0.0);
+            for (int mu = 0; mu < up; ++mu)
+                for (int r0 = 0; r0 < down; ++r0) {
+                    const long long B = q0 + (long long)down * mu - (long long)up * r0;
+                    for (int j = 0; j < E; ++j) {
+                        const long long t = B + UD * (elo[r0] + j);
+                        if (t >= 0 && t < ntaps) g[((size_t)mu * E + j) * down + r0] = taps[t];
+                    }
+                }
+            std::vector<float> gf(g.begin(), g.end());
+            if (cudaMalloc(&h->d_g, g.size() * sizeof(double)) == cudaSuccess &&
+                cudaMalloc(&h->d_gf, gf.size() * sizeof(float)) == cudaSuccess &&
+                cudaMalloc(&h->d_elo, elo.size() * sizeof(int)) == cudaSuccess) {
+                cudaMemcpy(h->d_g, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice);
+                cudaMemcpy(h->d_gf, gf.data(), gf.size() * sizeof(float), cudaMemcpyHostToDevice);
+                cudaMemcpy(h->d_elo, elo.data(), elo.size() * sizeof(int), cudaMemcpyHostToDevice);
+                h->E = E;
+                h->E_need = e_need;
+            }
+        }
+    }
     *out = h;
     return 0;
 }
@@ -915,6 +1122,9 @@ int wc_resampler_create(int up, int down, const double* taps, int ntaps, wc_resa
 void wc_resampler_destroy(wc_resampler* h) {
     if (!h) return;
     if (h->d_hp) cudaFree(h->d_hp);
+    if (h->d_g) cudaFree(h->d_g);
+    if (h->d_gf) cudaFree(h->d_gf);
+    if (h->d_elo) cudaFree(h->d_elo);
     delete h;
 }
 
@@ -942,6 +1152,10 @@ int wc_resampler_run(wc_resampler* h, const float* x_dev, int n_in, long long se
     a.ntaps = h->ntaps;
     a.tpp = h->tpp;
     a.hp = h->d_hp;
+    a.g = h->d_g;
+    a.gf = h->d_gf;
+    a.e_lo = h->d_elo;
+    a.E = h->E;
     a.out = out_dev;
     a.epi = epilogue;
     a.sumsq = sumsq_dev;
@@ -955,6 +1169,28 @@ int wc_resampler_run(wc_resampler* h, const float* x_dev, int n_in, long long se
     int bx = (int)((n_tasks + RS_WARPS - 1) / RS_WARPS);
     if (bx < 1) bx = 1;
     if (bx > 148 * 8) bx = 148 * 8;
+    static const bool no_residue = getenv("WC_RESAMPLE_RESIDUE") && atoi(getenv("WC_RESAMPLE_RESIDUE")) == 0;   // A/B timing
+    if (h->E && !no_residue) {
+        const long long per_phase = (n_out + h->up - 1) / h->up;
+        const int n_blocks = (int)((per_phase + RS_A - 1) / RS_A);
+        const int G = (h->down <= 32) ? 4 : (h->down <= 64) ? 2 : 1;
+        int NB = RS_NB;
+        if (const char* e = getenv("WC_RS_NB")) NB = atoi(e);
+        const dim3 grid((unsigned)((n_blocks + G * NB - 1) / (G * NB)), (unsigned)n_seq);
+        cudaStream_t st = (cudaStream_t)stream;
+        static const bool f64 = getenv("WC_RESAMPLE_F64") && atoi(getenv("WC_RESAMPLE_F64")) == 1;   // A/B: all-float64 kernel
+        if (f64) {
+            if (h->up == 1) resample_residue_kernel<1, 21, double><<<grid, RS_RT, 0, st>>>(a, n_blocks, G, NB);
+            else if (h->up == 2) resample_residue_kernel<2, 12, double><<<grid, RS_RT, 0, st>>>(a, n_blocks, G, NB);
+            else resample_residue_kernel<3, 8, double><<<grid, RS_RT, 0, st>>>(a, n_blocks, G, NB);
+        } else {
+            if (h->up == 1) resample_residue_kernel<1, 21, float><<<grid, RS_RT, 0, st>>>(a, n_blocks, G, NB);
+            else if (h->up == 2) resample_residue_kernel<2, 12, float><<<grid, RS_RT, 0, st>>>(a, n_blocks, G, NB);
+            else resample_residue_kernel<3, 8, float><<<grid, RS_RT, 0, st>>>(a, n_blocks, G, NB);
+        }
+        WC_CUDA(cudaGetLastError());
+        return 0;
+    }
     // grouped kernel only while the RS_R outputs of a task read one L1-friendly window (measured on B200: 1/50 resampler
     // 11 % faster grouped, 3/625 resampler 14 % slower)
     if ((long long)(RS_R - 1) * h->down * (long long)sizeof(float) <= 8192) {

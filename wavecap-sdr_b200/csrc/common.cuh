@@ -163,6 +163,29 @@ __device__ __forceinline__ float fast_atan2f(float y, float x) {
     return copysignf(a, y);
 }
 
+// degree-17 variant for the analog chain's discriminator (dsp/fm.py:65-97 feeds audio filters whose parity budget is
+// tighter than the channelizer's): max relative error 1.4e-7 in float32 Horner arithmetic (tools/fit_atan.py 9) plus the
+// 2-ulp quotient — the accuracy class of libm's atan2f at about half its instructions (no IEEE-division slow path).
+__device__ __forceinline__ float fast_atan2f_hi(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = __fdividef(mn, fmaxf(mx, 1e-37f));
+    const float s = t * t;
+    float p = 0.0028179744258522987f;
+    p = fmaf(p, s, -0.01606472209095955f);
+    p = fmaf(p, s, 0.04292432218790054f);
+    p = fmaf(p, s, -0.07548770308494568f);
+    p = fmaf(p, s, 0.10676739364862442f);
+    p = fmaf(p, s, -0.1421811282634735f);
+    p = fmaf(p, s, 0.19995509088039398f);
+    p = fmaf(p, s, -0.3333330750465393f);
+    p = fmaf(p, s, 1.0f);
+    float a = p * t;
+    a = (ay > ax) ? (1.57079632679489662f - a) : a;
+    a = (x < 0.0f) ? (3.14159265358979324f - a) : a;
+    return copysignf(a, y);
+}
+
 __device__ __forceinline__ float rcp_approx(float v) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
