@@ -59,6 +59,76 @@ struct FrontArgs {
 
 // nco_f32 (capture.freq_shift's float32-phase oscillator) lives in common.cuh
 
+// One channel over one staged tile, specialised on what the channel needs so that the sample loop carries no mode
+// tests (ncu: the generic loop spent 14 of its 200 instructions per sample on branches). KIND: 0 = power only (NONE /
+// RAW), 1 = FM discriminator, 2 = AM envelope, 3 = SSB product. Returns this thread's float32 partial of sum |base|^2.
+template <int KIND, bool SHIFT, bool BASE>
+__device__ __forceinline__ float front_tile(const FrontArgs& a, const FrontChan& ch, const float2* tile, int t0, int cnt,
+                                            long long obase, int tid) {
+    float psum32 = 0.f;   // this thread's <= 16 samples of the tile; everything above that level is float64
+    const bool exact_idx = (t0 + FR_TILE) <= (1 << 24);   // float32 index by exact increments (numpy's float32 arange)
+    float nf = (float)(t0 + tid);
+    // whole warps walk the tile (the trip count is warp-uniform): lane l's previous mixed sample is lane l-1's current
+    // one, so the oscillator and the complex product are evaluated once per sample, not twice
+#pragma unroll 2
+    for (int base = 0; base < cnt; base += FR_THREADS, nf += (float)FR_THREADS) {
+        const int i = base + tid;
+        const bool live = i < cnt;
+        const int n = t0 + i;
+        float2 b1 = live ? tile[i + 1] : make_float2(0.f, 0.f);
+        if (SHIFT) {
+            float c1, s1;
+            nco_f32f(ch.k32, exact_idx ? nf : (float)n, c1, s1);
+            b1 = make_float2(b1.x * c1 - b1.y * s1, b1.x * s1 + b1.y * c1);
+        }
+        float o = 0.f;
+        if (KIND == 1) {
+            float2 b0;
+            b0.x = __shfl_up_sync(0xffffffffu, b1.x, 1);
+            b0.y = __shfl_up_sync(0xffffffffu, b1.y, 1);
+            if ((tid & 31) == 0) {
+                b0 = tile[live ? i : 0];
+                if (SHIFT) {
+                    float c0, s0;
+                    nco_f32(ch.k32, n - 1, c0, s0);
+                    b0 = make_float2(b0.x * c0 - b0.y * s0, b0.x * s0 + b0.y * c0);
+                }
+            }
+            // angle(x[n] * conj(x[n-1])) * scale, out[0] = 0
+            const float pr = b1.x * b0.x + b1.y * b0.y;
+            const float pi = b1.y * b0.x - b1.x * b0.y;
+            o = (n == 0) ? 0.0f : fast_atan2f_hi(pi, pr) * ch.disc_scale;
+        }
+        const float pw = fmaf(b1.x, b1.x, b1.y * b1.y);      // |base|^2 (np.abs(base)**2 to 1 ulp); 0 for dead lanes
+        psum32 += pw;
+        if (KIND == 2) o = sqrtf(pw);                         // np.abs(base)
+        if (KIND == 3) {
+            // t = n / fs in float64; shift = complex64(exp(2j*pi*f*t)); real(iq * shift)
+            double s, co;
+            const double ph = ch.bfo_turns * (double)n;
+            sincospi(2.0 * (ph - rint(ph)), &s, &co);
+            o = b1.x * (float)co - b1.y * (float)s;
+        }
+        if (live) {
+            // RAW (capture.py:415-420) is served by base_out; NONE only needs the power sum
+            if (KIND != 0) a.out[obase + n] = o;
+            if (BASE) a.base_out[obase + n] = b1;
+        }
+    }
+    return psum32;
+}
+
+template <int KIND>
+__device__ __forceinline__ float front_tile_dispatch(const FrontArgs& a, const FrontChan& ch, const float2* tile, int t0,
+                                                     int cnt, long long obase, int tid) {
+    if (ch.shift) {
+        return a.base_out ? front_tile<KIND, true, true>(a, ch, tile, t0, cnt, obase, tid)
+                          : front_tile<KIND, true, false>(a, ch, tile, t0, cnt, obase, tid);
+    }
+    return a.base_out ? front_tile<KIND, false, true>(a, ch, tile, t0, cnt, obase, tid)
+                      : front_tile<KIND, false, false>(a, ch, tile, t0, cnt, obase, tid);
+}
+
 __global__ void __launch_bounds__(FR_THREADS) front_kernel(const FrontArgs a) {
     __shared__ float2 tile[FR_TILE + 1];
     __shared__ double red[FR_THREADS / 32];
@@ -87,62 +157,12 @@ __global__ void __launch_bounds__(FR_THREADS) front_kernel(const FrontArgs a) {
     for (int c = 0; c < a.n_ch; ++c) {
         const FrontChan ch = a.ch[c];
         const long long obase = ((long long)c * a.n_chunks + chunk) * a.n;
-        double psum = 0.0;
-        const bool is_fm = (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM);
-        // whole warps walk the tile (the trip count is warp-uniform): lane l's previous mixed sample is lane l-1's
-        // current one, so the oscillator and the complex product are evaluated once per sample, not twice
-        for (int base = 0; base < cnt; base += FR_THREADS) {
-            const int i = base + tid;
-            const bool live = i < cnt;
-            const int n = t0 + i;
-            float2 b1 = make_float2(0.f, 0.f);
-            if (live) {
-                const float2 x1 = tile[i + 1];
-                b1 = x1;
-                if (ch.shift) {
-                    float c1, s1;
-                    nco_f32(ch.k32, n, c1, s1);
-                    b1 = make_float2(x1.x * c1 - x1.y * s1, x1.x * s1 + x1.y * c1);
-                }
-            }
-            float2 b0 = make_float2(0.f, 0.f);
-            if (is_fm) {
-                b0.x = __shfl_up_sync(0xffffffffu, b1.x, 1);
-                b0.y = __shfl_up_sync(0xffffffffu, b1.y, 1);
-                if ((tid & 31) == 0 && live) {
-                    const float2 x0 = tile[i];
-                    b0 = x0;
-                    if (ch.shift) {
-                        float c0, s0;
-                        nco_f32(ch.k32, n - 1, c0, s0);
-                        b0 = make_float2(x0.x * c0 - x0.y * s0, x0.x * s0 + x0.y * c0);
-                    }
-                }
-            }
-            if (!live) continue;
-            const float mag = sqrtf(b1.x * b1.x + b1.y * b1.y);  // np.abs(base)
-            psum += (double)(mag * mag);
-            float o;
-            if (is_fm) {
-                // angle(x[n] * conj(x[n-1])) * scale, out[0] = 0
-                const float pr = b1.x * b0.x + b1.y * b0.y;
-                const float pi = b1.y * b0.x - b1.x * b0.y;
-                o = (n == 0) ? 0.0f : fast_atan2f_hi(pi, pr) * ch.disc_scale;
-            } else if (ch.mode == WC_MODE_AM) {
-                o = mag;
-            } else if (ch.mode == WC_MODE_SSB) {
-                // t = n / fs in float64; shift = complex64(exp(2j*pi*f*t)); real(iq * shift)
-                double s, co;
-                const double ph = ch.bfo_turns * (double)n;
-                sincospi(2.0 * (ph - rint(ph)), &s, &co);
-                o = b1.x * (float)co - b1.y * (float)s;
-            } else {
-                o = 0.f;
-            }
-            // RAW (capture.py:415-420) is served by base_out; NONE only needs the power sum
-            if (ch.mode != WC_MODE_NONE && ch.mode != WC_MODE_RAW) a.out[obase + n] = o;
-            if (a.base_out) a.base_out[obase + n] = b1;
-        }
+        float p32;
+        if (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM) p32 = front_tile_dispatch<1>(a, ch, tile, t0, cnt, obase, tid);
+        else if (ch.mode == WC_MODE_AM) p32 = front_tile_dispatch<2>(a, ch, tile, t0, cnt, obase, tid);
+        else if (ch.mode == WC_MODE_SSB) p32 = front_tile_dispatch<3>(a, ch, tile, t0, cnt, obase, tid);
+        else p32 = front_tile_dispatch<0>(a, ch, tile, t0, cnt, obase, tid);
+        double psum = (double)p32;
         psum = warp_sum(psum);
         if ((tid & 31) == 0) red[tid >> 5] = psum;
         __syncthreads();

@@ -84,14 +84,22 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // capture.freq_shift (capture.py:166-193): exp(j * fl32(k32 * fl32(n))) with k32 = float32(-2*pi*round(off)/fs)
-__device__ __forceinline__ void nco_f32(float k32, int n, float& c, float& s) {
-    // theta = fl32(k32 * fl32(n)) exactly as numpy computes it; then an accurate cos/sin of that
-    // float32 angle: reduce in double (theta < 2^24 rad is exact in double), evaluate in float.
-    const float th = __fmul_rn(k32, (float)n);
-    const double t = (double)th * 0.15915494309189535;  // turns
-    const double fr = t - rint(t);                       // [-0.5, 0.5]
-    sincospif((float)(2.0 * fr), &s, &c);
+// nf = float32(n), the value numpy's float32 arange holds.
+__device__ __forceinline__ void nco_f32f(float k32, float nf, float& c, float& s) {
+    // theta = fl32(k32 * fl32(n)) exactly as numpy computes it; then an accurate cos/sin of that float32 angle. The
+    // turn count theta/(2 pi) is formed in float-float arithmetic — product by the leading part of 1/(2 pi), its exact
+    // rounding error (FMA), the trailing part — so the fractional turn is good to ~3e-8 (2e-7 rad, the float32 rounding
+    // of the reduced angle itself) for |theta| far beyond 2^24, without touching the FP64 pipe or its conversions:
+    // the float64 reduction this replaces cost the analog front end most of its XU-pipe time (ncu, round 1).
+    const float th = __fmul_rn(k32, nf);
+    const float C_HI = 0.15915493667125702f, C_LO = 6.4206382432985265e-09f;   // 1/(2 pi) = C_HI + C_LO
+    const float hi = __fmul_rn(th, C_HI);
+    const float e = __fmaf_rn(th, C_HI, -hi);
+    const float lo = __fmaf_rn(th, C_LO, e);
+    const float fr = __fadd_rn(__fsub_rn(hi, rintf(hi)), lo);   // hi - rint(hi) is exact
+    sincospif(2.0f * fr, &s, &c);
 }
+__device__ __forceinline__ void nco_f32(float k32, int n, float& c, float& s) { nco_f32f(k32, (float)n, c, s); }
 
 // ---- small complex helpers on float2 ----
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
