@@ -82,6 +82,13 @@ int wc_front_run(const void* iq_dev, int fmt, int n, int n_chunks, long long chu
                  const int* modes, const double* offsets_hz, const double* bfo_hz, int sample_rate,
                  float* out_dev, void* base_out_dev, double* power_dev, int* nonfinite_dev, void* chan_scratch_dev,
                  void* stream);
+/* same, and out_sumsq_dev float64 [n_ch][n_chunks] (optional) = sum(out**2) per sequence: the input of
+ * rms_normalize (dsp/fm.py:42-62) when no filter sits between discriminator and normaliser (nbfm defaults,
+ * capture.py:3444-3452) — saves the separate wc_sumsq pass over the full-rate signal. */
+int wc_front_run_ex(const void* iq_dev, int fmt, int n, int n_chunks, long long chunk_stride, int n_ch,
+                    const int* modes, const double* offsets_hz, const double* bfo_hz, int sample_rate,
+                    float* out_dev, void* base_out_dev, double* power_dev, double* out_sumsq_dev, int* nonfinite_dev,
+                    void* chan_scratch_dev, void* stream);
 
 /* scipy.signal.lfilter(b, a, x), zero initial state, float64 DF2T, order <= 10, as a block scan
  * (dsp/fm.py:123,178; dsp/filters.py:124,170,217,260; dsp/agc.py:93,100). */

@@ -127,6 +127,7 @@ def _declare(l: C.CDLL) -> None:
     # analog chain stages
     fn("wc_front_chan_scratch_bytes", i32, i32)
     fn("wc_front_run", i32, vp, i32, i32, i32, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp)
+    fn("wc_front_run_ex", i32, vp, i32, i32, i32, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp)
     fn("wc_iir_create", i32, vp, i32, vp, i32, P(vp))
     fn("wc_iir_destroy", None, vp)
     fn("wc_iir_lfilter", i32, vp, vp, vp, i32, i64, i32, i32, vp)

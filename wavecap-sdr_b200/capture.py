@@ -197,8 +197,11 @@ def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig],
     bfo = [(c.ssb_bfo_offset_hz if c.ssb_mode.lower() == "usb" else -c.ssb_bfo_offset_hz) if c.mode == "ssb" else 0.0
            for c in cfgs]
     want_base = any(s[0] == "raw" for s in sigs)
-    out, base, power, nonfinite = S.front(x, fmt, n, n_chunks, modes, [float(c.offset_hz) for c in cfgs], bfo,
-                                          int(sample_rate), want_out=True, want_base=want_base)
+    # channels whose chain has nothing between discriminator and rms_normalize take sum(out**2) from the front end
+    want_ss = any(s[0] == "fm" and not s[1] and s[5] is None and s[6] is None for s in sigs)
+    out, base, power, nonfinite, *rest = S.front(x, fmt, n, n_chunks, modes, [float(c.offset_hz) for c in cfgs], bfo,
+                                                 int(sample_rate), want_out=True, want_base=want_base, want_sumsq=want_ss)
+    out_ss = rest[0] if rest else None
 
     audio = [None] * n_ch          # per channel: CUDA [n_chunks, n_audio]
     apower = [None] * n_ch
@@ -212,7 +215,9 @@ def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig],
         if sig[0] in ("fm", "am"):
             rows = out[c:e].reshape((e - c) * n_chunks, n)
             if sig[0] == "fm":
-                a, p, inv = FM.fm_tail(rows, int(sample_rate), sig[4], sig[1], want_stats=True, blanker_db=sig[5], nr_db=sig[6])
+                ss_rows = out_ss[c:e].reshape(-1) if out_ss is not None else None
+                a, p, inv = FM.fm_tail(rows, int(sample_rate), sig[4], sig[1], want_stats=True, blanker_db=sig[5], nr_db=sig[6],
+                                       sumsq_rows=ss_rows)
             else:
                 a, p, inv = AM.am_tail(rows, int(sample_rate), sig[4], sig[1], sig[2], sig[3], want_stats=True)
             a = a.reshape(e - c, n_chunks, -1)

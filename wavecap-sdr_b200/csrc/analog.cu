@@ -53,6 +53,7 @@ struct FrontArgs {
     float* out;            // [n_ch][n_chunks][n] demod front-end output
     float2* base_out;      // optional [n_ch][n_chunks][n] shifted IQ (freq_shift result), may be null
     double* power;         // [n_ch][n_chunks] sum |base|^2
+    double* out_sumsq;     // optional [n_ch][n_chunks] sum out^2 (rms_normalize input when no filter sits in between)
     int n_chunks;
     int* nonfinite;        // [n_chunks] set to 1 if any input sample is not finite
 };
@@ -61,11 +62,12 @@ struct FrontArgs {
 
 // One channel over one staged tile, specialised on what the channel needs so that the sample loop carries no mode
 // tests (ncu: the generic loop spent 14 of its 200 instructions per sample on branches). KIND: 0 = power only (NONE /
-// RAW), 1 = FM discriminator, 2 = AM envelope, 3 = SSB product. Returns this thread's float32 partial of sum |base|^2.
+// RAW), 1 = FM discriminator, 2 = AM envelope, 3 = SSB product. Returns this thread's float32 partials of
+// (sum |base|^2, sum out^2).
 template <int KIND, bool SHIFT, bool BASE>
-__device__ __forceinline__ float front_tile(const FrontArgs& a, const FrontChan& ch, const float2* tile, int t0, int cnt,
+__device__ __forceinline__ float2 front_tile(const FrontArgs& a, const FrontChan& ch, const float2* tile, int t0, int cnt,
                                             long long obase, int tid) {
-    float psum32 = 0.f;   // this thread's <= 16 samples of the tile; everything above that level is float64
+    float psum32 = 0.f, osum32 = 0.f;   // this thread's <= 16 samples of the tile; everything above that level is float64
     const bool exact_idx = (t0 + FR_TILE) <= (1 << 24);   // float32 index by exact increments (numpy's float32 arange)
     float nf = (float)(t0 + tid);
     // whole warps walk the tile (the trip count is warp-uniform): lane l's previous mixed sample is lane l-1's current
@@ -111,15 +113,18 @@ __device__ __forceinline__ float front_tile(const FrontArgs& a, const FrontChan&
         }
         if (live) {
             // RAW (capture.py:415-420) is served by base_out; NONE only needs the power sum
-            if (KIND != 0) a.out[obase + n] = o;
+            if (KIND != 0) {
+                a.out[obase + n] = o;
+                osum32 = fmaf(o, o, osum32);
+            }
             if (BASE) a.base_out[obase + n] = b1;
         }
     }
-    return psum32;
+    return make_float2(psum32, osum32);
 }
 
 template <int KIND>
-__device__ __forceinline__ float front_tile_dispatch(const FrontArgs& a, const FrontChan& ch, const float2* tile, int t0,
+__device__ __forceinline__ float2 front_tile_dispatch(const FrontArgs& a, const FrontChan& ch, const float2* tile, int t0,
                                                      int cnt, long long obase, int tid) {
     if (ch.shift) {
         return a.base_out ? front_tile<KIND, true, true>(a, ch, tile, t0, cnt, obase, tid)
@@ -132,6 +137,7 @@ __device__ __forceinline__ float front_tile_dispatch(const FrontArgs& a, const F
 __global__ void __launch_bounds__(FR_THREADS) front_kernel(const FrontArgs a) {
     __shared__ float2 tile[FR_TILE + 1];
     __shared__ double red[FR_THREADS / 32];
+    __shared__ double red2[FR_THREADS / 32];
     const int chunk = blockIdx.y;
     const int t0 = blockIdx.x * FR_TILE;
     const int cnt = min(FR_TILE, a.n - t0);
@@ -157,19 +163,26 @@ __global__ void __launch_bounds__(FR_THREADS) front_kernel(const FrontArgs a) {
     for (int c = 0; c < a.n_ch; ++c) {
         const FrontChan ch = a.ch[c];
         const long long obase = ((long long)c * a.n_chunks + chunk) * a.n;
-        float p32;
+        float2 p32;
         if (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM) p32 = front_tile_dispatch<1>(a, ch, tile, t0, cnt, obase, tid);
         else if (ch.mode == WC_MODE_AM) p32 = front_tile_dispatch<2>(a, ch, tile, t0, cnt, obase, tid);
         else if (ch.mode == WC_MODE_SSB) p32 = front_tile_dispatch<3>(a, ch, tile, t0, cnt, obase, tid);
         else p32 = front_tile_dispatch<0>(a, ch, tile, t0, cnt, obase, tid);
-        double psum = (double)p32;
-        psum = warp_sum(psum);
-        if ((tid & 31) == 0) red[tid >> 5] = psum;
+        const double psum = warp_sum((double)p32.x);
+        const double osum = a.out_sumsq ? warp_sum((double)p32.y) : 0.0;
+        if ((tid & 31) == 0) {
+            red[tid >> 5] = psum;
+            red2[tid >> 5] = osum;
+        }
         __syncthreads();
         if (tid == 0) {
-            double s = 0.0;
-            for (int w = 0; w < FR_THREADS / 32; ++w) s += red[w];
+            double s = 0.0, s2 = 0.0;
+            for (int w = 0; w < FR_THREADS / 32; ++w) {
+                s += red[w];
+                s2 += red2[w];
+            }
             atomicAdd(a.power + (long long)c * a.n_chunks + chunk, s);
+            if (a.out_sumsq) atomicAdd(a.out_sumsq + (long long)c * a.n_chunks + chunk, s2);
         }
         __syncthreads();
     }
@@ -1230,6 +1243,14 @@ int wc_front_run(const void* iq_dev, int fmt, int n, int n_chunks, long long chu
                  const int* modes, const double* offsets_hz, const double* bfo_hz, int sample_rate,
                  float* out_dev, void* base_out_dev, double* power_dev, int* nonfinite_dev, void* chan_scratch_dev,
                  void* stream) {
+    return wc_front_run_ex(iq_dev, fmt, n, n_chunks, chunk_stride, n_ch, modes, offsets_hz, bfo_hz, sample_rate, out_dev,
+                           base_out_dev, power_dev, nullptr, nonfinite_dev, chan_scratch_dev, stream);
+}
+
+int wc_front_run_ex(const void* iq_dev, int fmt, int n, int n_chunks, long long chunk_stride, int n_ch,
+                    const int* modes, const double* offsets_hz, const double* bfo_hz, int sample_rate,
+                    float* out_dev, void* base_out_dev, double* power_dev, double* out_sumsq_dev, int* nonfinite_dev,
+                    void* chan_scratch_dev, void* stream) {
     WC_REQUIRE(iq_dev && modes && offsets_hz && power_dev && nonfinite_dev && chan_scratch_dev,
                "wc_front_run: null argument");
     WC_REQUIRE(n_ch >= 1 && n_ch <= 4096, "wc_front_run: n_ch out of range");
@@ -1253,6 +1274,7 @@ int wc_front_run(const void* iq_dev, int fmt, int n, int n_chunks, long long chu
     if (pinned) ring_release(slot, st);
     WC_CUDA(cudaMemsetAsync(power_dev, 0, sizeof(double) * (size_t)n_chunks * n_ch, st));
     WC_CUDA(cudaMemsetAsync(nonfinite_dev, 0, sizeof(int) * (size_t)n_chunks, st));
+    if (out_sumsq_dev) WC_CUDA(cudaMemsetAsync(out_sumsq_dev, 0, sizeof(double) * (size_t)n_chunks * n_ch, st));
     if (n <= 0) {
         if (!pinned) WC_CUDA(cudaStreamSynchronize(st));
         return 0;
@@ -1268,6 +1290,7 @@ int wc_front_run(const void* iq_dev, int fmt, int n, int n_chunks, long long chu
     a.out = out_dev;
     a.base_out = reinterpret_cast<float2*>(base_out_dev);
     a.power = power_dev;
+    a.out_sumsq = out_sumsq_dev;
     a.nonfinite = nonfinite_dev;
     front_kernel<<<dim3((n + FR_TILE - 1) / FR_TILE, n_chunks), FR_THREADS, 0, st>>>(a);
     WC_CUDA(cudaGetLastError());

@@ -153,9 +153,10 @@ def resample(x, up: int, down: int, epilogue: int = EPI_NONE, sumsq_dev=None, ta
 
 
 def front(iq, fmt: int, n: int, n_chunks: int, modes, offsets_hz, bfo_hz, sample_rate: int,
-          want_out: bool = True, want_base: bool = False):
+          want_out: bool = True, want_base: bool = False, want_sumsq: bool = False):
     """Frequency shift + RSSI power + demod front end for all channels of all chunks.
-    Returns (out [C,B,n] f32 | None, base [C,B,n] c64 | None, power [C,B] f64, nonfinite [B] i32)."""
+    Returns (out [C,B,n] f32 | None, base [C,B,n] c64 | None, power [C,B] f64, nonfinite [B] i32)
+    (+ sum(out**2) [C,B] f64 as a fifth item when want_sumsq)."""
     torch = _torch()
     n_ch = len(modes)
     dev = iq.device
@@ -167,7 +168,10 @@ def front(iq, fmt: int, n: int, n_chunks: int, modes, offsets_hz, bfo_hz, sample
     m = np.ascontiguousarray(modes, dtype=np.int32)
     o = np.ascontiguousarray(offsets_hz, dtype=np.float64)
     b = np.ascontiguousarray(bfo_hz if bfo_hz is not None else np.zeros(n_ch), dtype=np.float64)
-    N.check(N.lib().wc_front_run(ptr(iq), fmt, n, n_chunks, n, n_ch, N.np_ptr(m), N.np_ptr(o), N.np_ptr(b),
-                                 int(sample_rate), ptr(out), ptr(base), ptr(power), ptr(nonfinite), ptr(scratch),
-                                 stream()))
+    ss = torch.empty((n_ch, n_chunks), dtype=torch.float64, device=dev) if want_sumsq else None
+    N.check(N.lib().wc_front_run_ex(ptr(iq), fmt, n, n_chunks, n, n_ch, N.np_ptr(m), N.np_ptr(o), N.np_ptr(b),
+                                    int(sample_rate), ptr(out), ptr(base), ptr(power), ptr(ss), ptr(nonfinite),
+                                    ptr(scratch), stream()))
+    if want_sumsq:
+        return out, base, power, nonfinite, ss
     return out, base, power, nonfinite

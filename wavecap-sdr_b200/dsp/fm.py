@@ -115,9 +115,11 @@ def fm_post_chain(sample_rate: int, *, wide: bool, enable_deemphasis: bool, deem
     return [s for s in stages if s is not None]
 
 
-def fm_tail(fm_rows, sample_rate: int, audio_rate: int, stages, want_stats: bool = False, blanker_db=None, nr_db=None):
+def fm_tail(fm_rows, sample_rate: int, audio_rate: int, stages, want_stats: bool = False, blanker_db=None, nr_db=None,
+            sumsq_rows=None):
     """[noise blanker] -> IIR stages -> [spectral noise reduction] -> RMS -> resample with fused scale + soft clip
-    (dsp/fm.py:277-314, :368-406). fm_rows: CUDA [n_seq, n] float32."""
+    (dsp/fm.py:277-314, :368-406). fm_rows: CUDA [n_seq, n] float32. sumsq_rows: sum(fm_rows**2) per row when the front
+    end already produced it (only used if nothing between discriminator and RMS changes the signal)."""
     y = fm_rows
     if blanker_db is not None:
         y = F.noise_blanker_rows(y, blanker_db, 3)
@@ -125,7 +127,7 @@ def fm_tail(fm_rows, sample_rate: int, audio_rate: int, stages, want_stats: bool
         y = S.lfilter(b, a, y)
     if nr_db is not None:
         y = F.spectral_nr_rows(y, nr_db)
-    ss = S.sumsq(y)
+    ss = sumsq_rows if (sumsq_rows is not None and y is fm_rows) else S.sumsq(y)
     if sample_rate == audio_rate:
         # resample_linear returns its input; scale and clip elementwise
         import torch
