@@ -204,8 +204,8 @@ def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig],
     out_ss = rest[0] if rest else None
 
     audio = [None] * n_ch          # per channel: CUDA [n_chunks, n_audio]
-    apower = [None] * n_ch
-    invalid = [None] * n_ch
+    stat_parts = []                # per run of channels: [k, 2, n_chunks] float64 (audio power, invalid flag)
+    have = []                      # channel index of every row of the concatenated statistics
     c = 0
     while c < n_ch:                 # runs of adjacent channels with identical chains share launches
         e = c + 1
@@ -221,22 +221,25 @@ def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig],
             else:
                 a, p, inv = AM.am_tail(rows, int(sample_rate), sig[4], sig[1], sig[2], sig[3], want_stats=True)
             a = a.reshape(e - c, n_chunks, -1)
-            p = p.reshape(e - c, n_chunks)
-            inv = inv.reshape(e - c, n_chunks)
+            # per-run statistics stay one tensor [channels of the run][power | invalid][chunk]: a handful of launches per
+            # run instead of three per channel
+            stat_parts.append(torch.stack([p.reshape(e - c, n_chunks).double(), inv.reshape(e - c, n_chunks).double()], dim=1))
+            have.extend(range(c, e))
             for i in range(c, e):
-                audio[i], apower[i], invalid[i] = a[i - c], p[i - c], inv[i - c]
+                audio[i] = a[i - c]
         elif sig[0] == "raw":
             for i in range(c, e):
                 audio[i] = torch.view_as_real(base[i]).reshape(n_chunks, 2 * n)   # interleaved I,Q (capture.py:415-420)
-                apower[i] = (audio[i].double() ** 2).sum(dim=1)
-                invalid[i] = ((~torch.isfinite(audio[i]).all(dim=1)) | (audio[i].abs().amax(dim=1) > AUDIO_MAX_ABS)).int()
+                pw_i = (audio[i].double() ** 2).sum(dim=1)
+                inv_i = ((~torch.isfinite(audio[i]).all(dim=1)) | (audio[i].abs().amax(dim=1) > AUDIO_MAX_ABS))
+                stat_parts.append(torch.stack([pw_i, inv_i.double()]).unsqueeze(0))
+                have.append(i)
         c = e
 
     # one device->host transfer for all per-(channel, chunk) statistics instead of three per channel
-    have = [ci for ci in range(n_ch) if audio[ci] is not None]
     stats_h = None
     if have:
-        stats = torch.stack([torch.stack([apower[ci].double(), invalid[ci].double()]) for ci in have])  # [k][2][n_chunks]
+        stats = stat_parts[0] if len(stat_parts) == 1 else torch.cat(stat_parts, dim=0)  # [k][2][n_chunks], rows in `have` order
         stats_h = stats.cpu().numpy()
     power_h = power.cpu().numpy()
     nonfinite_h = nonfinite.cpu().numpy()
