@@ -179,3 +179,44 @@ def test_rds_path_input_is_the_front_end_output(native):
         assert wrap_rel_rms(got, ref, period) < 1e-5
     cfg.enable_rds = False
     assert "fm_baseband" not in process_channels_batch(x, fs, [cfg], n_chunks=2, want_fm_baseband=True)[0][0][1]
+
+
+@pytest.mark.parametrize("in_rate,out_rate", [(2_400_000, 48_000), (10_000_000, 48_000), (1_800_000, 48_000),
+                                              (2_048_000, 48_000), (1_536_000, 48_000), (6_000_000, 48_000)])
+def test_resampler_residue_form_edges(native, in_rate, out_rate):
+    """The residue-form resampler (1/50, 3/625, 2/75, 3/128, 1/32, 1/125) against scipy's float64 resample_poly at lengths
+    around its block and zero-extension edges: shorter than one decimation period, shorter than the filter, ragged ends."""
+    from math import gcd
+
+    from scipy import signal
+    from wavecap_sdr_b200.dsp import fm
+
+    g = gcd(in_rate, out_rate)
+    up, down = out_rate // g, in_rate // g
+    rng = np.random.default_rng(down)
+    for n in (1, down - 1, down + 1, 8 * down - 3, 10 * down + 1, 20 * down + 7, 67 * down + down // 2):
+        x = rng.standard_normal(n).astype(np.float32)
+        got = fm.resample_poly(x, in_rate, out_rate)
+        exp = signal.resample_poly(x.astype(np.float64), up, down).astype(np.float32)
+        assert got.shape == exp.shape and got.dtype == np.float32
+        scale = max(float(np.sqrt(np.mean(exp.astype(np.float64) ** 2))), 1e-3)
+        assert float(np.sqrt(np.mean((got.astype(np.float64) - exp) ** 2))) / scale < 2e-6, (n, up, down)
+
+
+def test_front_end_sum_of_squares_matches_the_separate_pass(native):
+    """wc_front_run_ex's fused sum(out**2) (rms_normalize input of the default NBFM chain) against wc_sumsq of the same output."""
+    import torch
+
+    from wavecap_sdr_b200.dsp import _stages as S
+
+    fs, n, n_chunks = 1_000_000, 50_001, 3
+    rng = np.random.default_rng(21)
+    x = torch.from_numpy(((rng.standard_normal(n * n_chunks) + 1j * rng.standard_normal(n * n_chunks)) * 0.1).astype(np.complex64)).cuda()
+    modes = [S.MODE_NBFM, S.MODE_AM, S.MODE_SSB, S.MODE_WBFM]
+    out, _, power, _, ss = S.front(x, S.FMT_CF32, n, n_chunks, modes, [12_000.0, 0.0, -40_000.0, 250_000.0], [0.0, 0.0, 1500.0, 0.0],
+                                   fs, want_sumsq=True)
+    ref = S.sumsq(out.reshape(len(modes) * n_chunks, n)).reshape(len(modes), n_chunks)
+    torch.cuda.synchronize()
+    assert torch.allclose(ss, ref, rtol=1e-6, atol=0.0)
+    out2, _, power2, _ = S.front(x, S.FMT_CF32, n, n_chunks, modes, [12_000.0, 0.0, -40_000.0, 250_000.0], [0.0, 0.0, 1500.0, 0.0], fs)
+    assert torch.equal(out, out2) and torch.allclose(power, power2, rtol=1e-12)
