@@ -1202,16 +1202,15 @@ int wc_resampler_run(wc_resampler* h, const float* x_dev, int n_in, long long se
     int bx = (int)((n_tasks + RS_WARPS - 1) / RS_WARPS);
     if (bx < 1) bx = 1;
     if (bx > 148 * 8) bx = 148 * 8;
-    static const bool no_residue = getenv("WC_RESAMPLE_RESIDUE") && atoi(getenv("WC_RESAMPLE_RESIDUE")) == 0;   // A/B timing
+    const bool no_residue = env_int("WC_RESAMPLE_RESIDUE", 1) == 0;   // A/B timing
     if (h->E && !no_residue) {
         const long long per_phase = (n_out + h->up - 1) / h->up;
         const int n_blocks = (int)((per_phase + RS_A - 1) / RS_A);
         const int G = (h->down <= 32) ? 4 : (h->down <= 64) ? 2 : 1;
-        int NB = RS_NB;
-        if (const char* e = getenv("WC_RS_NB")) NB = atoi(e);
+        const int NB = max(1, env_int("WC_RS_NB", RS_NB));
         const dim3 grid((unsigned)((n_blocks + G * NB - 1) / (G * NB)), (unsigned)n_seq);
         cudaStream_t st = (cudaStream_t)stream;
-        static const bool f64 = getenv("WC_RESAMPLE_F64") && atoi(getenv("WC_RESAMPLE_F64")) == 1;   // A/B: all-float64 kernel
+        const bool f64 = env_int("WC_RESAMPLE_F64", 0) == 1;   // A/B: all-float64 kernel
         if (f64) {
             if (h->up == 1) resample_residue_kernel<1, 21, double><<<grid, RS_RT, 0, st>>>(a, n_blocks, G, NB);
             else if (h->up == 2) resample_residue_kernel<2, 12, double><<<grid, RS_RT, 0, st>>>(a, n_blocks, G, NB);

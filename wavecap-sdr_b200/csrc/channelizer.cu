@@ -842,12 +842,17 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
         a.scale = fm_scale;
         int R;
         int occ = 4;  // resident CTAs per SM of the fused-FM kernel; measured on B200: 4 -> 181 GS/s, 5 -> 165, 6 -> 159 (profiles/r01_chan_sweep2.jsonl)
-        if (const char* e = getenv("WC_CHAN_OCC")) occ = atoi(e);
+        // dev switches, read per call (~100 ns) so the sweep tools can change them inside one process
+        const int occ_env = env_int("WC_CHAN_OCC", 0), r_env = env_int("WC_CHAN_R", 0), var_env = env_int("WC_CHAN_VAR", 1);
+#ifdef WC_DEV_ABLATE
+        const int abl_env = env_int("WC_CHAN_ABL", 0);
+#endif
+        if (occ_env > 0) occ = occ_env;
         if (mode == WC_CHAN_OUT_COMPLEX) occ = 4;
         if (h->run_frames > 0) {
             R = h->run_frames;
-        } else if (const char* e = getenv("WC_CHAN_R")) {
-            R = atoi(e);
+        } else if (r_env > 0) {
+            R = r_env;
         } else {
             const long long total = F * n_chunks;
             const long long target = (long long)sm_count() * occ * 6;
@@ -871,24 +876,24 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
             a.at.hp = (float)(1.5707963267948966 * fm_scale);
             a.at.pi = (float)(3.141592653589793 * fm_scale);
         }
-        int var = 1;  // 1 = software-pipelined kernel (FIR of sub-tile n+1 inside the FFT of sub-tile n); 0 = phase-serial
-        if (const char* e = getenv("WC_CHAN_VAR")) var = atoi(e);
+        const int var = var_env;  // 1 = software-pipelined kernel (FIR of sub-tile n+1 inside the FFT of sub-tile n); 0 = phase-serial
         if (var == 1) {
-            static bool attr_done = false;
-            if (!attr_done) {
-                WC_CUDA(cudaFuncSetAttribute(chan256p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChanSmemP)));
-                WC_CUDA(cudaFuncSetAttribute(chan256p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChanSmemP)));
-                attr_done = true;
-            }
+            // once per process (thread-safe static initialisation); the attribute is per function, not per device context
+            static const cudaError_t attr_rc = [] {
+                cudaError_t e = cudaFuncSetAttribute(chan256p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChanSmemP));
+                if (e != cudaSuccess) return e;
+                return cudaFuncSetAttribute(chan256p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChanSmemP));
+            }();
+            WC_CUDA(attr_rc);
             if (mode == WC_CHAN_OUT_COMPLEX) chan256p_kernel<0><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);
             else chan256p_kernel<1><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);
         } else
         if (mode == WC_CHAN_OUT_COMPLEX) chan256_kernel<0, 4><<<grid, CH_THREADS, 0, stream>>>(a);
 #ifdef WC_DEV_ABLATE
-        else if (getenv("WC_CHAN_ABL") && atoi(getenv("WC_CHAN_ABL")) == 1) chan256_kernel<1, 4, 1><<<grid, CH_THREADS, 0, stream>>>(a);
-        else if (getenv("WC_CHAN_ABL") && atoi(getenv("WC_CHAN_ABL")) == 2) chan256_kernel<1, 4, 2><<<grid, CH_THREADS, 0, stream>>>(a);
-        else if (getenv("WC_CHAN_ABL") && atoi(getenv("WC_CHAN_ABL")) == 3) chan256_kernel<1, 4, 3><<<grid, CH_THREADS, 0, stream>>>(a);
-        else if (getenv("WC_CHAN_ABL") && atoi(getenv("WC_CHAN_ABL")) == 4) chan256_kernel<1, 4, 4><<<grid, CH_THREADS, 0, stream>>>(a);
+        else if (abl_env == 1) chan256_kernel<1, 4, 1><<<grid, CH_THREADS, 0, stream>>>(a);
+        else if (abl_env == 2) chan256_kernel<1, 4, 2><<<grid, CH_THREADS, 0, stream>>>(a);
+        else if (abl_env == 3) chan256_kernel<1, 4, 3><<<grid, CH_THREADS, 0, stream>>>(a);
+        else if (abl_env == 4) chan256_kernel<1, 4, 4><<<grid, CH_THREADS, 0, stream>>>(a);
 #endif
         else if (occ == 4) chan256_kernel<1, 4><<<grid, CH_THREADS, 0, stream>>>(a);
         else if (occ == 6) chan256_kernel<1, 6><<<grid, CH_THREADS, 0, stream>>>(a);

@@ -30,6 +30,8 @@ const char* get_error();
     } while (0)
 
 int sm_count();
+// tuning / A-B switches for the dev tools (WC_* environment variables); absent in production use
+int env_int(const char* name, int dflt);
 
 // ---- device helpers ----
 #ifdef __CUDACC__

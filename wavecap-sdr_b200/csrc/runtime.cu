@@ -1,5 +1,6 @@
 // Library-level entry points: init, error string, device info.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/wcsdr_b200.h"
@@ -17,6 +18,11 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
 
 int sm_count() {
     if (g_sm_count == 0) {

@@ -909,12 +909,11 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
     // stay L2-resident at any useful slab size (ncu: pass A writes it to DRAM), small slabs only starve the grid
     // (16 MB: 79 GS/s, 64 MB: 124, 512 MB: 150), so slabs are sized for parallelism.
     size_t slab_bytes = 512ull << 20;
-    if (const char* e = getenv("WC_SPECTRUM_SLAB_MB")) slab_bytes = (size_t)atoi(e) << 20;
+    slab_bytes = (size_t)env_int("WC_SPECTRUM_SLAB_MB", 512) << 20;
     int slab = (int)(slab_bytes / (sizeof(float2) * (size_t)n));
     if (slab < avg) slab = avg;
     slab -= slab % avg;
-    const char* var = getenv("WC_SPECTRUM_VARIANT");
-    const int variant = var ? atoi(var) : 3;   // 3 = two register-direct passes (fastest measured), 4 = fused ring kernel
+    const int variant = env_int("WC_SPECTRUM_VARIANT", 3);   // 3 = two register-direct passes (fastest measured), 4 = fused ring kernel
     const bool fused = (n == SP_N && variant == 4);
     if (fused) slab = 1 << 20;   // the fused kernel's scratch is a ring: no slab limit (ctrl is 4 bytes per frame)
     if (slab > n_frames) slab = ((n_frames + avg - 1) / avg) * avg;
@@ -932,12 +931,12 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
             if (variant == 4) {
                 // fused persistent kernel: ring of R frames, pass B lags pass A by `lag` groups
                 int lagf = 32;
-                if (const char* e = getenv("WC_SPECTRUM_LAG")) lagf = atoi(e);
+                lagf = env_int("WC_SPECTRUM_LAG", lagf);
                 int lag = lagf / avg;
                 if (lag < 1) lag = 1;
                 int R = 2 * (lag + 1) * avg;
                 if (R < 64) R = 64;
-                if (const char* e = getenv("WC_SPECTRUM_RING")) R = atoi(e);
+                R = env_int("WC_SPECTRUM_RING", R);
                 if (R < (lag + 2) * avg) R = (lag + 2) * avg;
                 if (sp_ensure(&h->d_ring, &h->ring_bytes, sizeof(float2) * (size_t)n * R)) return -2;
                 const size_t ctrl_need = sizeof(int) * (size_t)(1 + cnt + groups);
@@ -958,19 +957,17 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
                 spectrum_fused_kernel<<<3 * sm_count(), SP_THREADS, 0, st>>>(fa);
             } else if (variant == 3) {
                 int fy = (6 * sm_count()) / 16;   // frames in flight: ~6 CTAs per SM over the 16 column tiles
-                if (const char* e = getenv("WC_SPECTRUM_FY")) fy = atoi(e);
+                fy = env_int("WC_SPECTRUM_FY", fy);
                 if (fy > cnt) fy = cnt;
                 if (fy < 1) fy = 1;
-                const char* pa = getenv("WC_SPECTRUM_PASS_A");
-                const int pav = pa ? atoi(pa) : 6;   // measured on B200, 4096 frames: A3 153 GS/s, A5<3> 166, A5<2> 200
+                const int pav = env_int("WC_SPECTRUM_PASS_A", 6);   // measured on B200, 4096 frames: A3 153 GS/s, A5<3> 166, A5<2> 200
                 if (pav == 5) spectrum_pass_a5<3><<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
                 else if (pav == 6) spectrum_pass_a5<2><<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
                 else spectrum_pass_a3<<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
-                const char* pb = getenv("WC_SPECTRUM_PASS_B");
-                const int pbv = pb ? atoi(pb) : 5;   // measured on B200, 4096 frames with pass A5<2>: B3 200 GS/s, B5 210
+                const int pbv = env_int("WC_SPECTRUM_PASS_B", 5);   // measured on B200, 4096 frames with pass A5<2>: B3 200 GS/s, B5 210
                 if (pbv == 5) {
                     int gy = (4 * sm_count()) / 16;   // two waves of the 2 resident CTAs per SM over the 16 row tiles
-                    if (const char* e = getenv("WC_SPECTRUM_GY")) gy = atoi(e);
+                    gy = env_int("WC_SPECTRUM_GY", gy);
                     if (gy > groups) gy = groups;
                     if (gy < 1) gy = 1;
                     spectrum_pass_b5<<<dim3(SP_N1 / SP_COLS, gy), SP_THREADS, 0, st>>>(T, avg, cnt, groups, o);
