@@ -830,6 +830,10 @@ struct wc_spectrum {
     void* d_out = nullptr;
     size_t out_bytes = 0;
     cudaStream_t stream = nullptr;
+    // variant 5: pass A and pass B on two internal streams over a ring of small slabs
+    static constexpr int PIPE_Q = 3;
+    cudaStream_t s_a = nullptr, s_b = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_a[PIPE_Q] = {}, ev_b[PIPE_Q] = {}, ev_join_a = nullptr, ev_join_b = nullptr;
 };
 
 static int sp_ensure(void** p, size_t* cap, size_t need) {
@@ -887,6 +891,15 @@ void wc_spectrum_destroy(wc_spectrum* h) {
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->s_a) cudaStreamDestroy(h->s_a);
+    if (h->s_b) cudaStreamDestroy(h->s_b);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join_a) cudaEventDestroy(h->ev_join_a);
+    if (h->ev_join_b) cudaEventDestroy(h->ev_join_b);
+    for (int q = 0; q < wc_spectrum::PIPE_Q; ++q) {
+        if (h->ev_a[q]) cudaEventDestroy(h->ev_a[q]);
+        if (h->ev_b[q]) cudaEventDestroy(h->ev_b[q]);
+    }
     delete h;
 }
 
@@ -913,7 +926,65 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
     int slab = (int)(slab_bytes / (sizeof(float2) * (size_t)n));
     if (slab < avg) slab = avg;
     slab -= slab % avg;
-    const int variant = env_int("WC_SPECTRUM_VARIANT", 3);   // 3 = two register-direct passes (fastest measured), 4 = fused ring kernel
+    // 3 = two register-direct passes on the caller's stream, 4 = fused ring kernel, 5 = the same two passes pipelined over
+    // two internal streams (default once a call spans more than one 128 MB slab: 210 -> 229 GS/s at 4096 frames)
+    const size_t pipe_slab_bytes = (size_t)env_int("WC_SPECTRUM_PIPE_SLAB_MB", 128) << 20;
+    // (a call of two or three slabs gains nothing from the pipeline: 368 frames 200 GS/s single-stream, 179 pipelined)
+    const int variant = env_int("WC_SPECTRUM_VARIANT", (sizeof(float2) * (size_t)n * n_frames >= 4 * pipe_slab_bytes) ? 5 : 3);
+    if (n == SP_N && variant == 5) {
+        // Two-stream pipeline: pass A of slab k+1 runs while pass B of slab k drains, over a ring of PIPE_Q slabs: the
+        // tail of one launch is filled by the head of the other instead of idling the SMs. Measured on B200 (4096 frames,
+        // profiles/r01_spectrum_notes.md): 8 MB slabs 89 GS/s ... 64 MB 225, 128 MB 229, 512 MB 218; single-stream 210.
+        constexpr int Q = wc_spectrum::PIPE_Q;
+        int sl = (int)(pipe_slab_bytes / (sizeof(float2) * (size_t)n));
+        if (sl < avg) sl = avg;
+        sl -= sl % avg;
+        {   // equal slabs: a short last slab would end the pipeline on an unoverlapped tail
+            const int n_slabs = (n_frames + sl - 1) / sl;
+            int even = (n_frames + n_slabs - 1) / n_slabs;
+            even = ((even + avg - 1) / avg) * avg;
+            if (even < sl) sl = even;
+        }
+        if (sp_ensure(&h->d_scratch, &h->scratch_bytes, sizeof(float2) * (size_t)n * sl * Q)) return -2;
+        if (!h->s_a) {
+            WC_CUDA(cudaStreamCreateWithFlags(&h->s_a, cudaStreamNonBlocking));
+            WC_CUDA(cudaStreamCreateWithFlags(&h->s_b, cudaStreamNonBlocking));
+            WC_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            WC_CUDA(cudaEventCreateWithFlags(&h->ev_join_a, cudaEventDisableTiming));
+            WC_CUDA(cudaEventCreateWithFlags(&h->ev_join_b, cudaEventDisableTiming));
+            for (int q = 0; q < Q; ++q) {
+                WC_CUDA(cudaEventCreateWithFlags(&h->ev_a[q], cudaEventDisableTiming));
+                WC_CUDA(cudaEventCreateWithFlags(&h->ev_b[q], cudaEventDisableTiming));
+            }
+        }
+        WC_CUDA(cudaEventRecord(h->ev_fork, st));
+        WC_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_fork, 0));
+        WC_CUDA(cudaStreamWaitEvent(h->s_b, h->ev_fork, 0));
+        int k = 0;
+        for (int f0 = 0; f0 < n_frames; f0 += sl, ++k) {
+            const int cnt = (n_frames - f0 < sl) ? n_frames - f0 : sl;
+            const int groups = (cnt + avg - 1) / avg;
+            float* o = power_db_dev + (long long)(f0 / avg) * n;
+            const float2* x = iq + (long long)f0 * frame_stride;
+            u64* T = reinterpret_cast<u64*>(h->d_scratch) + (size_t)(k % Q) * (size_t)n * sl;
+            if (k >= Q) WC_CUDA(cudaStreamWaitEvent(h->s_a, h->ev_b[k % Q], 0));   // pass B of slab k - Q has left the slot
+            int fy = (6 * sm_count()) / 16;
+            if (fy > cnt) fy = cnt;
+            spectrum_pass_a5<2><<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, h->s_a>>>(x, frame_stride, h->d_window, T, cnt);
+            WC_CUDA(cudaEventRecord(h->ev_a[k % Q], h->s_a));
+            WC_CUDA(cudaStreamWaitEvent(h->s_b, h->ev_a[k % Q], 0));
+            int gy = (4 * sm_count()) / 16;
+            if (gy > groups) gy = groups;
+            spectrum_pass_b5<<<dim3(SP_N1 / SP_COLS, gy), SP_THREADS, 0, h->s_b>>>(T, avg, cnt, groups, o);
+            WC_CUDA(cudaEventRecord(h->ev_b[k % Q], h->s_b));
+            WC_CUDA(cudaGetLastError());
+        }
+        WC_CUDA(cudaEventRecord(h->ev_join_a, h->s_a));
+        WC_CUDA(cudaEventRecord(h->ev_join_b, h->s_b));
+        WC_CUDA(cudaStreamWaitEvent(st, h->ev_join_a, 0));
+        WC_CUDA(cudaStreamWaitEvent(st, h->ev_join_b, 0));
+        return 0;
+    }
     const bool fused = (n == SP_N && variant == 4);
     if (fused) slab = 1 << 20;   // the fused kernel's scratch is a ring: no slab limit (ctrl is 4 bytes per frame)
     if (slab > n_frames) slab = ((n_frames + avg - 1) / avg) * avg;
