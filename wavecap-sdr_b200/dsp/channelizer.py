@@ -146,9 +146,9 @@ class PolyphaseChannelizer:
         if s.n_frames > 0:
             peer = isinstance(block, DeviceSpan)
             if peer:
-                # halo rows of every CTA run cross NVLink again: one wave of long runs instead of six of short ones
+                # halo rows of every CTA run cross NVLink again (8 per run: 8 % at 96 frames): one wave of long runs, not six of short ones
                 slots = 4 * torch.cuda.get_device_properties(device).multi_processor_count
-                N.check(N.lib().wc_chan_set_run_frames(self._h, min(256, max(32, -(-rows // slots)))))
+                N.check(N.lib().wc_chan_set_run_frames(self._h, min(256, max(96, -(-rows // slots)))))
             try:
                 N.check(N.lib().wc_chan_process(self._h, C.c_void_p(block.data_ptr() + 8 * s.sample0), s.n_samples, 1,
                                                 s.n_samples, mode, fm_scale(rate) if fm else 0.0,
