@@ -69,55 +69,67 @@ __device__ __forceinline__ float2 front_tile(const FrontArgs& a, const FrontChan
                                             long long obase, int tid) {
     float psum32 = 0.f, osum32 = 0.f;   // this thread's <= 16 samples of the tile; everything above that level is float64
     const bool exact_idx = (t0 + FR_TILE) <= (1 << 24);   // float32 index by exact increments (numpy's float32 arange)
-    float nf = (float)(t0 + tid);
-    // whole warps walk the tile (the trip count is warp-uniform): lane l's previous mixed sample is lane l-1's current
-    // one, so the oscillator and the complex product are evaluated once per sample, not twice
-#pragma unroll 2
-    for (int base = 0; base < cnt; base += FR_THREADS, nf += (float)FR_THREADS) {
-        const int i = base + tid;
-        const bool live = i < cnt;
-        const int n = t0 + i;
-        float2 b1 = live ? tile[i + 1] : make_float2(0.f, 0.f);
-        if (SHIFT) {
-            float c1, s1;
-            nco_f32f(ch.k32, exact_idx ? nf : (float)n, c1, s1);
-            b1 = make_float2(b1.x * c1 - b1.y * s1, b1.x * s1 + b1.y * c1);
-        }
-        float o = 0.f;
+    // Each warp walks its own contiguous segment of the tile, 32 consecutive samples per step (coalesced stores). The FM
+    // discriminator's previous mixed sample is the neighbouring lane's current one (shuffle) and, for lane 0, lane 31's of
+    // the previous step — so the oscillator and the complex product run once per sample; only a segment's very first
+    // sample evaluates them a second time (ncu: recomputing it in lane 0 of every step cost the whole warp ~35 issue
+    // slots per step).
+    constexpr int SEG = FR_TILE / (FR_THREADS / 32);
+    const int lane = tid & 31;
+    const int seg0 = (tid >> 5) * SEG;
+    float nf = (float)(t0 + seg0 + lane);
+    float2 carry = make_float2(0.f, 0.f);     // lane 31's mixed sample of the previous step
+    if (seg0 < cnt) {
         if (KIND == 1) {
-            float2 b0;
-            b0.x = __shfl_up_sync(0xffffffffu, b1.x, 1);
-            b0.y = __shfl_up_sync(0xffffffffu, b1.y, 1);
-            if ((tid & 31) == 0) {
-                b0 = tile[live ? i : 0];
-                if (SHIFT) {
-                    float c0, s0;
-                    nco_f32(ch.k32, n - 1, c0, s0);
-                    b0 = make_float2(b0.x * c0 - b0.y * s0, b0.x * s0 + b0.y * c0);
+            carry = tile[seg0];               // sample t0 + seg0 - 1 (the tile carries one sample of halo in front)
+            if (SHIFT) {
+                float c0, s0;
+                nco_f32(ch.k32, t0 + seg0 - 1, c0, s0);
+                carry = make_float2(carry.x * c0 - carry.y * s0, carry.x * s0 + carry.y * c0);
+            }
+        }
+#pragma unroll 2
+        for (int base = seg0; base < min(cnt, seg0 + SEG); base += 32, nf += 32.0f) {
+            const int i = base + lane;
+            const bool live = i < cnt;
+            const int n = t0 + i;
+            float2 b1 = live ? tile[i + 1] : make_float2(0.f, 0.f);
+            if (SHIFT) {
+                float c1, s1;
+                nco_f32f(ch.k32, exact_idx ? nf : (float)n, c1, s1);
+                b1 = make_float2(b1.x * c1 - b1.y * s1, b1.x * s1 + b1.y * c1);
+            }
+            float o = 0.f;
+            if (KIND == 1) {
+                float2 b0;
+                b0.x = __shfl_up_sync(0xffffffffu, b1.x, 1);
+                b0.y = __shfl_up_sync(0xffffffffu, b1.y, 1);
+                if (lane == 0) b0 = carry;
+                carry.x = __shfl_sync(0xffffffffu, b1.x, 31);
+                carry.y = __shfl_sync(0xffffffffu, b1.y, 31);
+                // angle(x[n] * conj(x[n-1])) * scale, out[0] = 0
+                const float pr = b1.x * b0.x + b1.y * b0.y;
+                const float pi = b1.y * b0.x - b1.x * b0.y;
+                o = (n == 0) ? 0.0f : fast_atan2f_hi(pi, pr) * ch.disc_scale;
+            }
+            const float pw = fmaf(b1.x, b1.x, b1.y * b1.y);      // |base|^2 (np.abs(base)**2 to 1 ulp); 0 for dead lanes
+            psum32 += pw;
+            if (KIND == 2) o = sqrtf(pw);                         // np.abs(base)
+            if (KIND == 3) {
+                // t = n / fs in float64; shift = complex64(exp(2j*pi*f*t)); real(iq * shift)
+                double s, co;
+                const double ph = ch.bfo_turns * (double)n;
+                sincospi(2.0 * (ph - rint(ph)), &s, &co);
+                o = b1.x * (float)co - b1.y * (float)s;
+            }
+            if (live) {
+                // RAW (capture.py:415-420) is served by base_out; NONE only needs the power sum
+                if (KIND != 0) {
+                    a.out[obase + n] = o;
+                    osum32 = fmaf(o, o, osum32);
                 }
+                if (BASE) a.base_out[obase + n] = b1;
             }
-            // angle(x[n] * conj(x[n-1])) * scale, out[0] = 0
-            const float pr = b1.x * b0.x + b1.y * b0.y;
-            const float pi = b1.y * b0.x - b1.x * b0.y;
-            o = (n == 0) ? 0.0f : fast_atan2f_hi(pi, pr) * ch.disc_scale;
-        }
-        const float pw = fmaf(b1.x, b1.x, b1.y * b1.y);      // |base|^2 (np.abs(base)**2 to 1 ulp); 0 for dead lanes
-        psum32 += pw;
-        if (KIND == 2) o = sqrtf(pw);                         // np.abs(base)
-        if (KIND == 3) {
-            // t = n / fs in float64; shift = complex64(exp(2j*pi*f*t)); real(iq * shift)
-            double s, co;
-            const double ph = ch.bfo_turns * (double)n;
-            sincospi(2.0 * (ph - rint(ph)), &s, &co);
-            o = b1.x * (float)co - b1.y * (float)s;
-        }
-        if (live) {
-            // RAW (capture.py:415-420) is served by base_out; NONE only needs the power sum
-            if (KIND != 0) {
-                a.out[obase + n] = o;
-                osum32 = fmaf(o, o, osum32);
-            }
-            if (BASE) a.base_out[obase + n] = b1;
         }
     }
     return make_float2(psum32, osum32);
@@ -134,7 +146,7 @@ __device__ __forceinline__ float2 front_tile_dispatch(const FrontArgs& a, const 
                       : front_tile<KIND, false, false>(a, ch, tile, t0, cnt, obase, tid);
 }
 
-__global__ void __launch_bounds__(FR_THREADS) front_kernel(const FrontArgs a) {
+__global__ void __launch_bounds__(FR_THREADS, 4) front_kernel(const FrontArgs a) {
     __shared__ float2 tile[FR_TILE + 1];
     __shared__ double red[FR_THREADS / 32];
     __shared__ double red2[FR_THREADS / 32];
@@ -160,7 +172,8 @@ __global__ void __launch_bounds__(FR_THREADS) front_kernel(const FrontArgs a) {
     }
     if (__syncthreads_or(bad) && tid == 0) atomicExch(a.nonfinite + chunk, 1);
 
-    for (int c = 0; c < a.n_ch; ++c) {
+    // blockIdx.z splits the channel loop when (tiles x chunks) alone would leave the last wave mostly empty
+    for (int c = blockIdx.z; c < a.n_ch; c += gridDim.z) {
         const FrontChan ch = a.ch[c];
         const long long obase = ((long long)c * a.n_chunks + chunk) * a.n;
         float2 p32;
@@ -1291,7 +1304,14 @@ int wc_front_run_ex(const void* iq_dev, int fmt, int n, int n_chunks, long long 
     a.power = power_dev;
     a.out_sumsq = out_sumsq_dev;
     a.nonfinite = nonfinite_dev;
-    front_kernel<<<dim3((n + FR_TILE - 1) / FR_TILE, n_chunks), FR_THREADS, 0, st>>>(a);
+    // ncu, C2 (123 tiles x 8 chunks = 984 CTAs at 5 per SM): 1.33 waves, i.e. a third of the run on a quarter-full machine.
+    // Channel groups bring the grid to >= 4 waves; the tile is then staged once per group (L2 hits, 1/16 of a channel's work).
+    const int tiles = (n + FR_TILE - 1) / FR_TILE;
+    const long long base_ctas = (long long)tiles * n_chunks;
+    long long groups = (4LL * 5 * sm_count() + base_ctas - 1) / base_ctas;
+    if (groups > n_ch) groups = n_ch;
+    if (groups < 1) groups = 1;
+    front_kernel<<<dim3(tiles, n_chunks, (unsigned)groups), FR_THREADS, 0, st>>>(a);
     WC_CUDA(cudaGetLastError());
     if (!pinned) WC_CUDA(cudaStreamSynchronize(st));   // a pageable host vector must outlive the async copy
     return 0;
