@@ -635,7 +635,7 @@ constexpr int RS_NB = 1;         // output blocks a thread group walks in sequen
 // float64 result: 3/625 and 1/50 outputs differ by a few 1e-8 relative RMS either way — the float32 rounding of the
 // OUTPUT, which the reference applies too (`.astype(np.float32)`), not the accumulation.
 template <int UP, int E, typename T>
-__global__ void __launch_bounds__(RS_RT) resample_residue_kernel(const ResampArgs a, int n_blocks, int G, int NB) {
+__global__ void __launch_bounds__(RS_RT, (sizeof(T) == 4 ? 6 : 3)) resample_residue_kernel(const ResampArgs a, int n_blocks, int G, int NB) {
     constexpr int W = RS_A + E - 1;
     __shared__ double part[RS_RT / 32][UP * RS_A];
     const int seq = blockIdx.y;
@@ -664,16 +664,24 @@ __global__ void __launch_bounds__(RS_RT) resample_residue_kernel(const ResampArg
             for (int r0 = gtid; r0 < a.down; r0 += gt) {
                 const long long kbase = (long long)a0 - __ldg(a.e_lo + r0) - (E - 1);
                 T w[W];
+                const long long n_first = r0 + (long long)a.down * kbase;
+                if (n_first >= 0 && n_first + (long long)a.down * (W - 1) < a.n_in) {
+                    // interior block (all but the first and last few): no bounds tests, 32-bit strides
+                    const float* xp = xs + n_first;
 #pragma unroll
-                for (int q = 0; q < W; ++q) {
-                    const long long n = r0 + (long long)a.down * (kbase + q);
-                    w[q] = (n >= 0 && n < a.n_in) ? (T)xs[n] : (T)0;     // zero extension, as upfirdn
+                    for (int q = 0; q < W; ++q) w[q] = (T)xp[q * a.down];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < W; ++q) {
+                        const long long n = n_first + (long long)a.down * q;
+                        w[q] = (n >= 0 && n < a.n_in) ? (T)xs[n] : (T)0;     // zero extension, as upfirdn
+                    }
                 }
 #pragma unroll
                 for (int mu = 0; mu < UP; ++mu) {
                     T g[E];
 #pragma unroll
-                    for (int j = 0; j < E; ++j) g[j] = __ldg(gt_tab + ((long long)mu * E + j) * a.down + r0);
+                    for (int j = 0; j < E; ++j) g[j] = __ldg(gt_tab + (mu * E + j) * a.down + r0);   // table < 2^31 entries
 #pragma unroll
                     for (int j = 0; j < E; ++j)
 #pragma unroll
