@@ -90,11 +90,15 @@ int wc_front_run_ex(const void* iq_dev, int fmt, int n, int n_chunks, long long 
                     float* out_dev, void* base_out_dev, double* power_dev, double* out_sumsq_dev, int* nonfinite_dev,
                     void* chan_scratch_dev, void* stream);
 
-/* scipy.signal.lfilter(b, a, x), zero initial state, float64 DF2T, order <= 10, as a block scan
- * (dsp/fm.py:123,178; dsp/filters.py:124,170,217,260; dsp/agc.py:93,100). */
+/* scipy.signal.lfilter(b, a, x), zero initial state, float64 DF2T, order <= 10
+ * (dsp/fm.py:123,178; dsp/filters.py:124,170,217,260; dsp/agc.py:93,100). Well-conditioned filters run as a block
+ * scan; tf-form filters with large transient growth (the order-10 band-pass of dsp/filters.py:177-217) replay
+ * lfilter's recursion operation for operation (bit-equal to scipy) — chosen at create time, wc_iir_is_sequential.
+ * Handles may be shared between threads: every call owns its scratch (stream-ordered allocation). */
 typedef struct wc_iir wc_iir;
 int wc_iir_create(const double* b, int nb, const double* a, int na, wc_iir** out);
 void wc_iir_destroy(wc_iir* h);
+int wc_iir_is_sequential(const wc_iir* h);
 int wc_iir_lfilter(wc_iir* h, const float* x_dev, float* y_dev, int n, long long seq_stride, int n_seq,
                    int abs_input, void* stream);
 

@@ -203,11 +203,14 @@ def am_freq_shift(iq, offset_hz, sample_rate):
 
 
 def am_demod(iq, sample_rate, audio_rate=48_000, enable_agc=True, enable_highpass=True, highpass_hz=100,
-             enable_lowpass=True, lowpass_hz=5000, agc_target_db=-20.0, notch_frequencies=None):
+             enable_lowpass=True, lowpass_hz=5000, agc_target_db=-20.0, notch_frequencies=None,
+             enable_noise_blanker=False, noise_blanker_threshold_db=10.0):
     """dsp/am.py:45-141."""
     if iq.size == 0:
         return np.empty(0, dtype=F32)
     audio = np.abs(iq).astype(F32)
+    if enable_noise_blanker:                                  # dsp/am.py:100-101
+        audio = noise_blanker(audio, noise_blanker_threshold_db, 3)
     if enable_highpass and highpass_hz > 0:
         audio = highpass_filter(audio, sample_rate, highpass_hz)
     if enable_lowpass and lowpass_hz > 0:
@@ -223,12 +226,14 @@ def am_demod(iq, sample_rate, audio_rate=48_000, enable_agc=True, enable_highpas
 
 def ssb_demod(iq, sample_rate, audio_rate=48_000, mode="usb", enable_agc=True, enable_bandpass=True,
               bandpass_low=300, bandpass_high=3000, agc_target_db=-20.0, notch_frequencies=None,
-              bfo_offset_hz=1500.0):
+              bfo_offset_hz=1500.0, enable_noise_blanker=False, noise_blanker_threshold_db=10.0):
     """dsp/am.py:144-247."""
     if iq.size == 0:
         return np.empty(0, dtype=F32)
     shifted = am_freq_shift(iq, bfo_offset_hz if mode.lower() == "usb" else -bfo_offset_hz, sample_rate)
     audio = np.real(shifted).astype(F32)
+    if enable_noise_blanker:                                  # dsp/am.py:213-215
+        audio = noise_blanker(audio, noise_blanker_threshold_db, 3)
     if enable_bandpass:
         audio = bandpass_filter(audio, sample_rate, bandpass_low, bandpass_high)
     for f in notch_frequencies or []:

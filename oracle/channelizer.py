@@ -87,3 +87,34 @@ def channelize_fm(frames: np.ndarray, demod_sample_rate: int) -> np.ndarray:
     for k in range(frames.shape[1]):
         out[:, k] = quadrature_demod(np.ascontiguousarray(frames[:, k]), demod_sample_rate)
     return out
+
+
+class ChannelCalculatorOracle:
+    """Frequency <-> FFT-bin bookkeeping, channelizer.py:161-231 (bin order = FFT order: 0 = DC, negative offsets wrap
+    to the end; a negative offset beyond -channel_count is NOT wrapped, like the reference)."""
+
+    def __init__(self, center_frequency: float, sample_rate: float, channel_bandwidth: int = 25000):
+        self.center_frequency = center_frequency
+        self.channel_bandwidth = channel_bandwidth
+        self.channel_count = int(sample_rate / channel_bandwidth)          # :181-184
+        if self.channel_count % 2 != 0:
+            self.channel_count -= 1
+
+    def get_channel_index(self, target_frequency: float) -> int:          # :186-214
+        steps = int(round((target_frequency - self.center_frequency) / self.channel_bandwidth))
+        if steps < 0:
+            return self.channel_count + steps
+        return steps % self.channel_count
+
+    def get_channel_center_frequency(self, channel_index: int) -> float:  # :216-231
+        if channel_index < self.channel_count // 2:
+            return self.center_frequency + channel_index * self.channel_bandwidth
+        return self.center_frequency + (channel_index - self.channel_count) * self.channel_bandwidth
+
+
+def channelize_samples(samples, sample_rate, target_frequency, center_frequency, channel_bandwidth=25000):
+    """channelizer.py:234-268: fresh channelizer, one process() call, the target bin of every frame."""
+    ch = ChannelizerOracle(sample_rate, channel_bandwidth)
+    idx = ChannelCalculatorOracle(center_frequency, sample_rate, channel_bandwidth).get_channel_index(target_frequency)
+    frames = ch.process_vectorized(np.asarray(samples))
+    return np.ascontiguousarray(frames[:, idx]).astype(np.complex64), ch.channel_sample_rate

@@ -43,6 +43,46 @@ def gen_channelizer_c5():
                         demod_rate=rate)
 
 
+def channel_calc_cases():
+    """(center, fs, bw, targets) grids for ChannelCalculator: even and odd raw counts, offsets on / between bin centres,
+    beyond +-Nyquist and beyond -channel_count (which the reference does not wrap)."""
+    cases = []
+    for center, fs, bw in ((851.0e6, 6.0e6, 12500), (460.0e6, 1.0e6, 25000), (100.0e6, 125.0e6, 488281), (155.0e6, 2.4e6, 7000)):
+        count = int(fs / bw)
+        steps = np.concatenate([np.arange(-count - 3, count + 4, max(1, count // 37)), [0, 1, -1, count // 2, -count // 2]])
+        frac = np.array([0.0, 0.49, -0.49, 0.5, -0.5, 0.51])
+        targets = (center + (steps[:, None] + frac[None, :]) * bw).reshape(-1)
+        cases.append((center, fs, bw, targets))
+    return cases
+
+
+def channelize_samples_input():
+    rng = np.random.default_rng(61)
+    fs, bw, center = 1.0e6, 25000, 460.0e6
+    n = 40 * 9 + 20 * 57 + 11
+    t = np.arange(n)
+    x = cnoise(rng, n, 0.05) + (0.5 * np.exp(2j * np.pi * (-75000.0 / fs) * t)).astype(np.complex64)
+    return x.astype(np.complex64), fs, bw, center
+
+
+def gen_channel_calc():
+    """ChannelCalculator / channelize_samples (dsp/channelizer.py:161-268)."""
+    from wavecapsdr.dsp.channelizer import ChannelCalculator, channelize_samples
+
+    out = {}
+    for i, (center, fs, bw, targets) in enumerate(channel_calc_cases()):
+        calc = ChannelCalculator(center, fs, bw)
+        out[f"count{i}"] = np.int64(calc.channel_count)
+        out[f"index{i}"] = np.array([calc.get_channel_index(float(f)) for f in targets], dtype=np.int64)
+        out[f"center{i}"] = np.array([calc.get_channel_center_frequency(k) for k in range(calc.channel_count)], dtype=np.float64)
+    x, fs, bw, center = channelize_samples_input()
+    for j, target in enumerate((center - 75000.0, center + 200000.0, center)):
+        y, rate = channelize_samples(x, fs, target, center, bw)
+        out[f"chan{j}"] = np.asarray(y)
+        out[f"rate{j}"] = np.float64(rate)
+    np.savez_compressed(os.path.join(OUT, "channel_calc.npz"), **out)
+
+
 def gen_analog():
     """C1 (WBFM, 2.4 MS/s cf32), C2 (16 NBFM from one 10 MS/s int16 capture) and 48 kS/s AM/SSB/AGC
     through the reference's own capture._process_channel_dsp_stateless / dsp functions. Inputs are
@@ -244,6 +284,28 @@ def gen_audiofx():
     iq = oa.synth_c1(seed=1, n=120_000)
     out["wbfm_nb_nr"] = rfm.wbfm_demod(oa_shift(iq), 2_400_000, 48000, enable_noise_blanker=True, enable_noise_reduction=True)
     np.savez_compressed(os.path.join(OUT, "audiofx.npz"), **out)
+
+
+def am_blanker_input():
+    """48 kS/s AM-ish signal with impulse noise (the stable regime of the AM/SSB filters)."""
+    rng = np.random.default_rng(31)
+    n = 9600
+    t = np.arange(n) / 48000.0
+    x = ((0.3 * (1 + 0.5 * np.sin(2 * np.pi * 700 * t))) * np.exp(2j * np.pi * 1200 * t)
+         + 0.01 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    x[[50, 51, 4000, 9599]] += np.array([3, -4j, 2.5 + 2j, 5], dtype=np.complex64)
+    return x
+
+
+def gen_am_blanker():
+    """am_demod / ssb_demod with enable_noise_blanker=True (dsp/am.py:100-101, 213-215)."""
+    from wavecapsdr.dsp import am as ram
+
+    x = am_blanker_input()
+    out = {"am_nb": ram.am_demod(x, 48000, 16000, enable_noise_blanker=True, noise_blanker_threshold_db=8.0),
+           "am_nb_noagc": ram.am_demod(x, 48000, 48000, enable_agc=False, enable_noise_blanker=True),
+           "ssb_nb": ram.ssb_demod(x, 48000, 16000, mode="lsb", enable_noise_blanker=True, noise_blanker_threshold_db=6.0)}
+    np.savez_compressed(os.path.join(OUT, "am_blanker.npz"), **out)
 
 
 def oa_shift(iq):
@@ -566,7 +628,7 @@ def gen_cc_scanner():
                         x_checksum=np.float64(np.sum(np.abs(x.astype(np.complex128)) ** 2)))
 
 
-GENERATORS = {"cc_scanner": gen_cc_scanner, "p25_trellis": gen_p25_trellis, "p25_discriminator": gen_p25_discriminator, "p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+GENERATORS = {"channel_calc": gen_channel_calc, "am_blanker": gen_am_blanker, "cc_scanner": gen_cc_scanner, "p25_trellis": gen_p25_trellis, "p25_discriminator": gen_p25_discriminator, "p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

@@ -16,6 +16,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
 
 
+# one-line parity facts the tests want visible in every run's output (e.g. the CQPSK knife-edge mismatch count), printed
+# in the terminal summary even under -q so a regression from "1 symbol in 218 000" shows up in the driver's log
+PARITY_NOTES: list[str] = []
+
+
+def parity_note(line: str) -> None:
+    PARITY_NOTES.append(line)
+
+
+def pytest_terminal_summary(terminalreporter):
+    if PARITY_NOTES:
+        terminalreporter.write_line("parity notes:")
+        for line in PARITY_NOTES:
+            terminalreporter.write_line("  " + line)
+
+
 def rel_rms(a, b) -> float:
     """relative RMS error ||a-b|| / ||b|| (b = oracle)."""
     a = np.asarray(a)

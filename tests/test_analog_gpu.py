@@ -139,13 +139,72 @@ def test_long_iir_matches_sequential_recursion(native):
     fs = 2_400_000
     assert rel_rms(F.lowpass_filter(x, fs, 15000), oa.lowpass_filter(x, fs, 15000)) < TOL
     assert rel_rms(F.highpass_filter(x, 48000, 300), oa.highpass_filter(x, 48000, 300)) < TOL
-    # order-10 tf-form band-pass: |A^64| ~ 2e9, the reference's own float64 recursion carries ~4e-6
-    # of rounding noise and rounding each segment's start state to float64 adds ~1e-4 on white noise
-    # (DESIGN.md "IIR scan"); the SSB chain that uses this filter passes at 1e-4 on its golden.
-    assert rel_rms(F.bandpass_filter(x, 48000, 300, 3000), oa.bandpass_filter(x, 48000, 300, 3000)) < 5e-4
+    # order-10 tf-form band-pass (ssb_demod, dsp/filters.py:177-217): too ill-conditioned for the block scan, so the handle
+    # replays lfilter's recursion operation for operation — bit-equal to scipy, not just inside the 1e-4 budget
+    got_bp, exp_bp = F.bandpass_filter(x, 48000, 300, 3000), oa.bandpass_filter(x, 48000, 300, 3000)
+    assert rel_rms(got_bp, exp_bp) < TOL
+    assert np.array_equal(got_bp, exp_bp)
     assert rel_rms(F.notch_filter(x, 48000, 1000.0), oa.notch_filter(x, 48000, 1000.0)) < TOL
     # invalid cut-offs return the input unchanged
     assert np.array_equal(F.lowpass_filter(x[:100], 48000, 30000), x[:100])
+
+
+def test_ill_conditioned_iirs_replay_lfilter_bit_for_bit(native):
+    """where the tf-form recursion is ill-conditioned (3 kHz low-pass / 300 Hz high-pass at
+    multi-MS/s rates, the AM chain's 100 Hz high-pass) only an exact replay of the sequential float64 recursion matches
+    the reference. wc_iir_create picks the replay kernel for those filters and keeps the block scan for the rest."""
+    from wavecap_sdr_b200 import _native as N
+    from wavecap_sdr_b200.dsp import _stages as S
+    from wavecap_sdr_b200.dsp import filters as F
+
+    def is_seq(coeffs):
+        b, a = coeffs
+        return bool(N.lib().wc_iir_is_sequential(S.iir_handle(tuple(map(float, b)), tuple(map(float, a))).h))
+
+    assert is_seq(F.bandpass_coeffs(48000, 300, 3000)) and is_seq(F.lowpass_coeffs(10_000_000, 3000))
+    assert is_seq(F.highpass_coeffs(976_560, 300)) and is_seq(F.highpass_coeffs(48000, 100))
+    assert not is_seq(F.lowpass_coeffs(2_400_000, 15000)) and not is_seq(F.highpass_coeffs(48000, 300))
+    assert not is_seq(F.notch_coeffs(48000, 1000.0)) and not is_seq(F.lowpass_coeffs(48000, 3000))
+    rng = np.random.default_rng(41)
+    x = rng.standard_normal((5, 30_011)).astype(np.float32)       # 5 sequences, ragged against the 64-sample staging tile
+    for fs, fn, ofn, args in ((10_000_000, F.lowpass_filter, oa.lowpass_filter, (3000,)),
+                              (976_560, F.highpass_filter, oa.highpass_filter, (300,)),
+                              (48000, F.highpass_filter, oa.highpass_filter, (100,)),
+                              (48000, F.bandpass_filter, oa.bandpass_filter, (300, 3000))):
+        got = fn(x, fs, *args)
+        exp = np.stack([ofn(r, fs, *args) for r in x])
+        assert got.shape == exp.shape and np.array_equal(got, exp), (fs, args)
+
+
+def test_shared_iir_handle_from_two_threads(native):
+    """dsp/_stages.iir_handle caches one handle per coefficient set and the reference calls the stateless chain from a
+    3-worker pool (capture.py:1906-1925): concurrent calls on one handle, each on its own stream, must not share scratch."""
+    import threading
+
+    import torch
+
+    from wavecap_sdr_b200.dsp import filters as F
+
+    rng = np.random.default_rng(43)
+    xs = [rng.standard_normal(n).astype(np.float32) for n in (400_000, 90_000, 250_000)]
+    exp = [oa.lowpass_filter(x, 2_400_000, 15000) for x in xs]
+    errs = []
+
+    def worker(i):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(6):
+                    got = F.lowpass_filter(torch.from_numpy(xs[i]).cuda(), 2_400_000, 15000)
+                    torch.cuda.current_stream().synchronize()
+                    if rel_rms(got.cpu().numpy(), exp[i]) >= TOL:
+                        errs.append(i)
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(3)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
 
 
 def test_decimate_iq_for_p25(native):

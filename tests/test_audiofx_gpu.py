@@ -47,3 +47,18 @@ def test_wbfm_chain_with_both_flags(native):
     got = wbfm_demod(iq, 2_400_000, 48000, enable_noise_blanker=True, enable_noise_reduction=True)
     exp = g["wbfm_nb_nr"]
     assert got.shape == exp.shape and rel_rms(got, exp) < 1e-4
+
+
+def test_am_ssb_demod_with_noise_blanker(native):
+    """am_demod / ssb_demod(enable_noise_blanker=True) against outputs of the reference itself (dsp/am.py:100-101, 213-215)."""
+    from oracle.make_golden import am_blanker_input
+    from wavecap_sdr_b200.dsp.am import am_demod, ssb_demod
+
+    g = np.load(golden_path("am_blanker.npz"))
+    x = am_blanker_input()
+    cases = ((am_demod(x, 48000, 16000, enable_noise_blanker=True, noise_blanker_threshold_db=8.0), g["am_nb"]),
+             (am_demod(x, 48000, 48000, enable_agc=False, enable_noise_blanker=True), g["am_nb_noagc"]),
+             (ssb_demod(x, 48000, 16000, mode="lsb", enable_noise_blanker=True, noise_blanker_threshold_db=6.0), g["ssb_nb"]))
+    for got, exp in cases:
+        assert got.shape == exp.shape and got.dtype == np.float32
+        assert rel_rms(got, exp) < 1e-4

@@ -58,33 +58,42 @@ def test_matches_reference_golden(native, case):
     assert dm._sync_count == int(g[name + "_sync_count"])
 
 
-@pytest.mark.parametrize("fs,chunk", [(48000, 2400), (50000, 2500), (48000, 72000)])
-def test_bank_matches_oracle(native, fs, chunk):
-    """8 channels with different CFO / timing / SNR / content advanced together."""
+@pytest.mark.parametrize("fs,chunk,C", [(48000, 2400, 8), (50000, 2500, 8), (48000, 72000, 8),
+                                        (48000, 2400, 64), (50000, 2500, 64), (48000, 72000, 64), (50000, 75000, 64)],
+                         ids=lambda v: str(v))
+def test_bank_matches_oracle(native, fs, chunk, C):
+    """C channels with different CFO / timing / SNR / content advanced together; C = 64 is BASELINE.json configs[3]
+    (generic path: 50 ms chunks; control-channel path: 1.5 s chunks, longer than the 65 536-sample history buffer, so the
+    half-shift happens inside a call and the run spans several calls)."""
+    from conftest import parity_note
     from wavecap_sdr_b200.dsp.p25.c4fm import C4FMBank
 
-    C = 8
-    nfr = 5 if chunk < 10000 else 30
+    nfr = 5 if chunk < 10000 else (30 if C <= 8 else 50)
     xs = []
     for c in range(C):
         rng = np.random.default_rng(400 + c)
         dib = random_frames(rng, n_frames=nfr, payload=150, gap=40)
-        xs.append(modulate_c4fm(dib, fs, snr_db=20.0 + 1.5 * c, cfo_hz=-200.0 + 57.0 * c, timing=0.11 * c, seed=400 + c))
+        xs.append(modulate_c4fm(dib, fs, snr_db=20.0 + (10.0 * c) / max(C - 1, 1), cfo_hz=-200.0 + (400.0 * c) / max(C - 1, 1),
+                                timing=(0.11 * c) % 1.0, seed=400 + c))
     n = min(len(x) for x in xs)
     xs = np.stack([x[:n] for x in xs])
     bank = C4FMBank(C, sample_rate=fs)
     gd, gs, gc = run_bank(bank, xs, chunk)
-    worst = 0.0
+    worst, total, syncs = 0.0, 0, 0
     for c in range(C):
         d, so, cnt, o = run_oracle(fs, xs[c], chunk)
         assert np.array_equal(gc[c], cnt), f"channel {c}: symbol counts differ"
         assert np.array_equal(gd[c], d), f"channel {c}: {int((gd[c] != d).sum())} dibit mismatches of {len(d)}"
         worst = max(worst, float(np.max(np.abs(gs[c] - so))))
+        total += len(d)
+        syncs += o.sync_count
         st = bank.state(c)
         assert st["sync_count"] == o.sync_count and st["fine_sync"] == o.fine
         assert abs(st["pll"] - o.pll) < 1e-6 and abs(st["gain"] - o.gain) < 1e-6
         assert abs(st["sample_point"] - o.sample_point) < 1e-6 and st["buffer_pointer"] == o.buf_ptr
     assert worst <= 2e-6, worst
+    parity_note(f"c4fm bank C={C} fs={fs} chunk={chunk}: {total} dibits identical to the oracle, {syncs} sync events, "
+                f"{-(-n // chunk)} calls of <= {chunk} samples, max |soft - oracle| = {worst:.1e}")
 
 
 def test_reset_and_empty(native):

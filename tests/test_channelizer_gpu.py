@@ -229,3 +229,32 @@ def test_full_size_fused_fm_equals_discriminator_of_complex_frames(native):
     err = float(diff.double().pow(2).mean().sqrt() / ref.double().pow(2).mean().sqrt())
     assert err < 1e-4
     assert not bool(d.reshape(b, F, 256)[:, 0].any())
+
+
+def test_channelize_samples_and_calculator(native):
+    """channelize_samples (dsp/channelizer.py:234-268) for a 40-channel grid (generic path) and the C5 grid (fast path)
+    against outputs of the reference itself and the oracle; the tone lands in the bin ChannelCalculator names."""
+    from oracle.channelizer import ChannelCalculatorOracle
+    from oracle.channelizer import channelize_samples as oracle_channelize
+    from oracle.make_golden import channelize_samples_input
+    from wavecap_sdr_b200.dsp.channelizer import ChannelCalculator, PolyphaseChannelizer, channelize_samples
+
+    g = np.load(golden_path("channel_calc.npz"))
+    x, fs, bw, center = channelize_samples_input()
+    for j, target in enumerate((center - 75000.0, center + 200000.0, center)):
+        y, rate = channelize_samples(x, fs, target, center, bw)
+        assert rate == float(g[f"rate{j}"]) and y.dtype == np.complex64 and y.shape == g[f"chan{j}"].shape
+        assert rel_rms(y, g[f"chan{j}"]) < TOL
+    # the -75 kHz tone: strongest in the bin the calculator returns
+    frames = PolyphaseChannelizer(fs, bw).process_array(x)
+    k = ChannelCalculator(center, fs, bw).get_channel_index(center - 75000.0)
+    assert k == 37 and int(np.argmax(np.mean(np.abs(frames[8:]) ** 2, axis=0))) == k
+    # C5 grid, negative offset wrapping to the top bins
+    rng = np.random.default_rng(62)
+    n = 256 + 128 * 700 + 5
+    xc = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.1).astype(np.complex64)
+    tgt = 100.0e6 - 9 * 488281.0
+    y, rate = channelize_samples(xc, 125.0e6, tgt, 100.0e6, 488281)
+    ye, re_ = oracle_channelize(xc, 125.0e6, tgt, 100.0e6, 488281)
+    assert ChannelCalculatorOracle(100.0e6, 125.0e6, 488281).get_channel_index(tgt) == 247
+    assert rate == re_ and y.shape == ye.shape and rel_rms(y, ye) < TOL

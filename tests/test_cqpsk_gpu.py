@@ -42,17 +42,21 @@ def test_matches_reference_golden(native, case):
     assert abs(dm._freq_offset - st[0]) < 1e-5 and abs(dm._symbol_clock - st[2]) < 1e-4 and abs(dm._agc_gain - st[4]) < 1e-5
 
 
-@pytest.mark.parametrize("fs,sr,chunk", [(48000, 4800, 2400), (50000, 4800, 2500), (48000, 4800, 72000)])
-def test_bank_matches_oracle(native, fs, sr, chunk):
+@pytest.mark.parametrize("fs,sr,chunk,C", [(48000, 4800, 2400, 8), (50000, 4800, 2500, 8), (48000, 4800, 72000, 8),
+                                           (48000, 4800, 2400, 64), (50000, 4800, 2500, 64), (48000, 4800, 72000, 64),
+                                           (50000, 4800, 75000, 64)], ids=lambda v: str(v))
+def test_bank_matches_oracle(native, fs, sr, chunk, C):
+    """C = 64 is BASELINE.json configs[3]; the knife-edge mismatch count of every run goes to the terminal summary."""
+    from conftest import parity_note
     from wavecap_sdr_b200.decoders.p25 import CQPSKBank
 
-    C = 8
-    nd = 1500 if chunk < 10000 else 9000
+    nd = 1500 if chunk < 10000 else (9000 if C <= 8 else 10500)
     xs = []
     for c in range(C):
         rng = np.random.default_rng(500 + c)
-        xs.append(modulate_cqpsk(rng.integers(0, 4, nd), fs, sr, snr_db=19.0 + 1.5 * c, cfo_hz=-70.0 + 20.0 * c,
-                                 timing=0.12 * c, seed=500 + c, amp=0.2 + 0.05 * c))
+        xs.append(modulate_cqpsk(rng.integers(0, 4, nd), fs, sr, snr_db=19.0 + (11.0 * c) / max(C - 1, 1),
+                                 cfo_hz=-70.0 + (140.0 * c) / max(C - 1, 1), timing=(0.12 * c) % 1.0, seed=500 + c,
+                                 amp=0.2 + 0.4 * c / max(C - 1, 1)))
     n = min(len(x) for x in xs)
     xs = np.stack([x[:n] for x in xs])
     bank = CQPSKBank(C, sample_rate=fs, symbol_rate=sr)
@@ -61,6 +65,7 @@ def test_bank_matches_oracle(native, fs, sr, chunk):
         d, cnt = bank.demodulate(xs[:, s:s + chunk])
         for c in range(C):
             got[c].append(d[c, : int(cnt[c])].copy())
+    total, knife, min_margin = 0, 0, np.inf
     for c in range(C):
         o = CQPSKOracle(sample_rate=fs, symbol_rate=sr, portable=True)
         exp, phases = [], []
@@ -70,6 +75,7 @@ def test_bank_matches_oracle(native, fs, sr, chunk):
         exp = np.concatenate(exp)
         g = np.concatenate(got[c])
         assert len(g) == len(exp), f"channel {c}: {len(g)} vs {len(exp)} symbols"
+        total += len(exp)
         bad = np.nonzero(g != exp)[0]
         if bad.size:
             ph = np.array(phases)
@@ -77,10 +83,14 @@ def test_bank_matches_oracle(native, fs, sr, chunk):
             margin = np.min(np.abs(ph[bad, None] - bounds[None, :]), axis=1)
             assert bad.size <= 2 and np.all(margin < 1e-4), (
                 f"channel {c}: {bad.size} dibit mismatches of {len(exp)}, decision margins {margin}")
+            knife += int(bad.size)
+            min_margin = min(min_margin, float(margin.min()))
         st = bank.state(c)
         assert abs(st["freq_offset"] - float(o.freq_offset)) < 1e-5
         assert abs(st["symbol_clock"] - float(o.clock)) < 1e-4
         assert abs(st["agc_gain"] - float(o.agc_gain)) < 1e-5
+    parity_note(f"cqpsk bank C={C} fs={fs} chunk={chunk}: {total - knife} of {total} dibits identical to the oracle, "
+                f"{knife} knife-edge mismatches" + (f" (decision margin >= {min_margin:.1e} rad)" if knife else ""))
 
 
 def test_empty_and_zero_input(native):

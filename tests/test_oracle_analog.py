@@ -91,3 +91,27 @@ def test_oracle_matches_live_reference_on_fresh_input():
         assert (a_r is None) == (a_o is None)
         if a_r is not None:
             assert np.array_equal(a_r, a_o)
+
+
+def test_lfilter_is_the_separately_rounded_df2t_recursion():
+    """csrc/analog.cu:iir_seq_kernel replays scipy's lfilter with every product and sum rounded on its own (no FMA).
+    That is what the scipy build in this image executes: a plain-Python float64 replay is bit-equal to lfilter even for
+    the ill-conditioned order-10 band-pass of ssb_demod (dsp/filters.py:177-217)."""
+    from scipy import signal
+
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(6000).astype(np.float32).astype(np.float64)
+    for b, a in (signal.butter(5, [300 / 24000, 3000 / 24000], btype="band"), signal.butter(5, 3000 / 5e6),
+                 signal.butter(5, 100 / 24000, btype="high")):
+        ref = signal.lfilter(b, a, x)
+        K = len(a) - 1
+        bl, al = [float(v / a[0]) for v in b], [float(v / a[0]) for v in a]
+        z = [0.0] * K
+        out = np.empty_like(x)
+        for n, xn in enumerate(x.tolist()):
+            yn = z[0] + bl[0] * xn
+            for i in range(K - 1):
+                z[i] = (z[i + 1] + xn * bl[i + 1]) - yn * al[i + 1]
+            z[K - 1] = xn * bl[K] - yn * al[K]
+            out[n] = yn
+        assert np.array_equal(out, ref)

@@ -108,5 +108,12 @@ def test_flag_wait_times_out_instead_of_hanging(native):
         torch.cuda.synchronize()
         assert int(timed_out.item()) == 1
         assert int(region.flags_tensor()[3].item()) == 7
+        # without an explicit flag the region's own one records the time-out and check() raises (then re-arms)
+        region.wait_flags(3, 1, 7, timeout_ms=50)
+        region.check()
+        region.wait_flags(4, 1, 1, timeout_ms=50)
+        with pytest.raises(TimeoutError):
+            region.check()
+        region.check()
     finally:
         region.close()

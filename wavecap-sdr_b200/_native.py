@@ -37,6 +37,8 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} not found — build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
                 "wavecap_sdr_b200 has no CPU fallback."
             )
+        import torch  # noqa: F401  (loads the process's libcudart first; the library links the shared runtime)
+
         l = C.CDLL(str(LIB_PATH))
         _declare(l)
         _lib = l
@@ -54,15 +56,26 @@ def init(device: int | None = None) -> None:
     global _inited_device
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
-    if _inited_device == device:
+    if _inited_device == device and getattr(_tls, "device", None) == device:
         return
     check(lib().wc_init(device))
     _inited_device = device
+    _tls.device = device
+
+
+_tls = threading.local()
 
 
 def ensure_init() -> None:
+    """The CUDA current device is per host thread: the reference's DSP pool threads (capture.py:1906-1925) never select
+    one, so every thread that reaches the library binds itself to the device init() chose."""
     if _inited_device is None:
         init()
+    elif getattr(_tls, "device", None) != _inited_device:
+        import torch
+
+        torch.cuda.set_device(_inited_device)      # cudaSetDevice for this thread (torch and the C ABI share the runtime)
+        _tls.device = _inited_device
 
 
 # ---- pointer helpers -------------------------------------------------------------------------------
@@ -130,6 +143,7 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_front_run_ex", i32, vp, i32, i32, i32, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp)
     fn("wc_iir_create", i32, vp, i32, vp, i32, P(vp))
     fn("wc_iir_destroy", None, vp)
+    fn("wc_iir_is_sequential", i32, vp)
     fn("wc_iir_lfilter", i32, vp, vp, vp, i32, i64, i32, i32, vp)
     fn("wc_sumsq", i32, vp, i32, i64, i32, vp, vp)
     fn("wc_elementwise", i32, vp, vp, i64, i32, f32, vp)

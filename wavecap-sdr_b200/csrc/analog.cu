@@ -400,6 +400,62 @@ __global__ void iir_chain_kernel(const IirCoef* __restrict__ cf, const dd* __res
     }
 }
 
+// Exact replay of scipy.signal.lfilter's float64 recursion (scipy/signal/_lfilter.c.in: y = z0 + b0*x;
+// z[i] = z[i+1] + x*b[i+1] - y*a[i+1]; products and sums rounded separately — x86-64 wheels are built without FMA
+// contraction, and a numpy replay of exactly these operations is bit-equal to lfilter, tests/test_oracle_analog.py).
+// For tf-form filters whose transition matrix has large transient growth (the order-10 band-pass of ssb_demod,
+// dsp/filters.py:177-217: |A^64| ~ 2e9) a block scan that hands each segment an independently rounded start state
+// perturbs the state off the manifold the sequential recursion stays on, and that perturbation is amplified to
+// ~5e-4 of the output; replaying the recursion reproduces the reference's own rounding bit for bit instead.
+// One lane per sequence, a warp stages 32 sequences x 64 samples through shared memory so global traffic is coalesced.
+constexpr int IIRS_SEG = 64;
+template <int K>
+__global__ void __launch_bounds__(32) iir_seq_kernel(const IirCoef* __restrict__ cf, const float* __restrict__ x,
+                                                     float* __restrict__ y, int n, long long seq_stride, int n_seq,
+                                                     int absin) {
+    __shared__ float tile[32][IIRS_SEG + 1];
+    const int lane = threadIdx.x;
+    const int seq0 = blockIdx.x * 32;
+    const int rows = min(32, n_seq - seq0);
+    double cb[K], ca[K], z[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        cb[i] = cf->b[i];
+        ca[i] = cf->a[i];
+        z[i] = 0.0;
+    }
+    const double b0 = cf->b0;
+    for (int t0 = 0; t0 < n; t0 += IIRS_SEG) {
+        const int cnt = min(IIRS_SEG, n - t0);
+        for (int r = 0; r < rows; ++r) {
+            const float* xs = x + (long long)(seq0 + r) * seq_stride + t0;
+            for (int e = lane; e < cnt; e += 32) {
+                const float v = xs[e];
+                tile[r][e] = absin ? fabsf(v) : v;
+            }
+        }
+        __syncwarp();
+        if (lane < rows) {
+#pragma unroll 2
+            for (int j = 0; j < cnt; ++j) {
+                const double xv = (double)tile[lane][j];
+                const double yv = __dadd_rn(z[0], __dmul_rn(b0, xv));
+#pragma unroll
+                for (int i = 0; i < K - 1; ++i)
+                    z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(xv, cb[i])), __dmul_rn(yv, ca[i]));
+                z[K - 1] = __dsub_rn(__dmul_rn(xv, cb[K - 1]), __dmul_rn(yv, ca[K - 1]));
+                tile[lane][j] = (float)yv;
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; ++r) {
+            float* ys = y + (long long)(seq0 + r) * seq_stride + t0;
+            for (int e = lane; e < cnt; e += 32) ys[e] = tile[r][e];
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // reductions / elementwise
 // ---------------------------------------------------------------------------------------------
@@ -811,6 +867,52 @@ static int make_iir_coef(const double* b, int nb, const double* a, int na, IirCo
     return 0;
 }
 
+// Does the block scan stay inside the parity budget for this filter? Measured directly at create time: 4096 samples
+// of white noise through (a) lfilter's sequential float64 recursion — the reference — and (b) what the scan computes:
+// every 64-sample segment restarted from the exact state (long double here, double-double on the device) rounded to
+// float64. For a well-conditioned filter the two agree to ~1e-9 (MPX low-pass 15 kHz @ 2.4 MS/s: 1.0e-9); tf-form
+// filters with large transient growth do not: order-10 band-pass 300-3000 Hz @ 48 kS/s 3.8e-6 here and 5e-4 on the
+// device over 500 000 samples, 100 Hz high-pass @ 48 kS/s 2.1e-7, 3 kHz low-pass @ 10 MS/s 4.5e-4 (the regime SURVEY
+// App. A.3(iii) describes). Above 1e-7 the handle replays the recursion sequentially (bit-equal to scipy).
+static bool iir_needs_sequential(const IirCoef& c) {
+    const int K = c.K;
+    if (K < 2) return false;
+    typedef long double ld;
+    const int N = 4096;
+    uint64_t lcg = 0x9E3779B97F4A7C15ull;
+    std::vector<double> x(N);
+    for (int n = 0; n < N; ++n) {
+        lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+        x[n] = (double)(lcg >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    }
+    std::vector<double> zs(K, 0.0), zb(K, 0.0);
+    std::vector<ld> ze(K, 0.0L);
+    double num = 0.0, den = 0.0;
+    for (int n = 0; n < N; ++n) {
+        if ((n & (IIR_L - 1)) == 0)
+            for (int i = 0; i < K; ++i) zb[i] = (double)ze[i];
+        const double xv = x[n];
+        // (a) lfilter: products and sums rounded separately
+        const double ya = zs[0] + c.b0 * xv;
+        for (int i = 0; i < K - 1; ++i) zs[i] = (zs[i + 1] + xv * c.b[i]) - ya * c.a[i];
+        zs[K - 1] = xv * c.b[K - 1] - ya * c.a[K - 1];
+        // (b) the scan's segment body (df2t_step)
+        const double yb = fma(c.b0, xv, zb[0]);
+        for (int i = 0; i < K - 1; ++i) zb[i] = fma(c.b[i], xv, fma(-c.a[i], yb, zb[i + 1]));
+        zb[K - 1] = fma(c.b[K - 1], xv, -c.a[K - 1] * yb);
+        // exact state
+        const ld xe = (ld)xv, ye = ze[0] + (ld)c.b0 * xe;
+        for (int i = 0; i < K - 1; ++i) ze[i] = ze[i + 1] + xe * (ld)c.b[i] - ye * (ld)c.a[i];
+        ze[K - 1] = xe * (ld)c.b[K - 1] - ye * (ld)c.a[K - 1];
+        if (n >= N / 2) {
+            num += (yb - ya) * (yb - ya);
+            den += ya * ya;
+        }
+    }
+    if (!(den > 0.0) || !(num == num)) return true;   // unstable / non-finite: replay, so the garbage matches too
+    return sqrt(num / den) > 1e-7;
+}
+
 struct Workspace {
     void* p = nullptr;
     size_t cap = 0;
@@ -832,12 +934,9 @@ template <int K, typename TIn>
 static int launch_iir_k(const IirCoef* d_cf, const TIn* x, float* y, int n, long long seq_stride, int n_seq,
                         int absin, double* zseg, dd* ztile, dd* stile, int tiles, cudaStream_t st) {
     const size_t smem = iir_smem_bytes<K>();
-    static bool configured = false;
-    if (!configured) {
-        WC_CUDA(cudaFuncSetAttribute(iir_kernel<K, 0, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        WC_CUDA(cudaFuncSetAttribute(iir_kernel<K, 1, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static std::atomic<unsigned long long> done0{0}, done1{0};
+    WC_CUDA(smem_optin(iir_kernel<K, 0, TIn>, (int)smem, done0));
+    WC_CUDA(smem_optin(iir_kernel<K, 1, TIn>, (int)smem, done1));
     dim3 grid(tiles, n_seq);
     iir_kernel<K, 0, TIn><<<grid, IIR_T, smem, st>>>(d_cf, x, y, n, seq_stride, zseg, ztile, stile, tiles, absin);
     iir_chain_kernel<K><<<(n_seq + 3) / 4, 128, 0, st>>>(d_cf, ztile, stile, tiles, n_seq);
@@ -989,8 +1088,50 @@ using namespace wc;
 struct wc_iir {
     IirCoef h_cf;
     IirCoef* d_cf = nullptr;
-    Workspace ws;
+    bool sequential = false;   // exact-replay kernel instead of the block scan (iir_needs_sequential)
 };
+
+template <int K>
+static int launch_iir_seq_k(const IirCoef* d_cf, const float* x, float* y, int n, long long seq_stride, int n_seq,
+                            int absin, cudaStream_t st) {
+    iir_seq_kernel<K><<<(n_seq + 31) / 32, 32, 0, st>>>(d_cf, x, y, n, seq_stride, n_seq, absin);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+static int launch_iir_seq(const IirCoef* d_cf, int K, const float* x, float* y, int n, long long seq_stride, int n_seq,
+                          int absin, cudaStream_t st) {
+#define WC_IIRS_CASE(KK) \
+    case KK:             \
+        return launch_iir_seq_k<KK>(d_cf, x, y, n, seq_stride, n_seq, absin, st);
+    switch (K) {
+        WC_IIRS_CASE(1) WC_IIRS_CASE(2) WC_IIRS_CASE(3) WC_IIRS_CASE(4) WC_IIRS_CASE(5) WC_IIRS_CASE(6) WC_IIRS_CASE(7)
+        WC_IIRS_CASE(8) WC_IIRS_CASE(9) WC_IIRS_CASE(10)
+        default:
+            set_error("iir: unsupported order %d", K);
+            return -1;
+    }
+#undef WC_IIRS_CASE
+}
+
+// scratch bytes of the block scan for n_seq sequences of n samples (zseg | ztile | stile)
+static size_t iir_scan_scratch_bytes(int K, int n, int n_seq) {
+    const size_t nz = (size_t)n_seq * ((n + IIR_TILE - 1) / IIR_TILE);
+    return sizeof(double) * nz * IIR_T * K + sizeof(dd) * 2 * nz * K;
+}
+
+// the filter proper on caller-provided scratch (iir_scan_scratch_bytes; unused by the sequential replay)
+static int iir_run(const wc_iir* h, const float* x_dev, float* y_dev, int n, long long seq_stride, int n_seq,
+                   int abs_input, void* scratch, cudaStream_t st) {
+    const int K = h->h_cf.K;
+    if (h->sequential) return launch_iir_seq(h->d_cf, K, x_dev, y_dev, n, seq_stride, n_seq, abs_input, st);
+    const int tiles = (n + IIR_TILE - 1) / IIR_TILE;
+    const size_t nz = (size_t)n_seq * tiles;
+    double* zseg = reinterpret_cast<double*>(scratch);
+    dd* ztile = reinterpret_cast<dd*>(zseg + nz * IIR_T * K);
+    dd* stile = ztile + nz * K;
+    return launch_iir_typed<float>(h->d_cf, K, x_dev, y_dev, n, seq_stride, n_seq, abs_input, zseg, ztile, stile,
+                                   tiles, st);
+}
 
 extern "C" {
 
@@ -1008,9 +1149,13 @@ int wc_iir_create(const double* b, int nb, const double* a, int na, wc_iir** out
         return -2;
     }
     cudaMemcpy(h->d_cf, &h->h_cf, sizeof(IirCoef), cudaMemcpyHostToDevice);
+    h->sequential = iir_needs_sequential(h->h_cf);
     *out = h;
     return 0;
 }
+
+// 1 when the handle runs the sequential exact replay (ill-conditioned tf-form filter), 0 for the block scan
+int wc_iir_is_sequential(const wc_iir* h) { return (h && h->sequential) ? 1 : 0; }
 
 void wc_iir_destroy(wc_iir* h) {
     if (!h) return;
@@ -1034,15 +1179,15 @@ int wc_iir_lfilter(wc_iir* h, const float* x_dev, float* y_dev, int n, long long
         WC_CUDA(cudaGetLastError());
         return 0;
     }
-    const int tiles = (n + IIR_TILE - 1) / IIR_TILE;
-    const size_t nz = (size_t)n_seq * tiles;
-    const size_t need = sizeof(double) * nz * IIR_T * K + sizeof(dd) * 2 * nz * K;
-    if (h->ws.reserve(need)) return -2;
-    double* zseg = reinterpret_cast<double*>(h->ws.p);
-    dd* ztile = reinterpret_cast<dd*>(zseg + nz * IIR_T * K);
-    dd* stile = ztile + nz * K;
-    return launch_iir_typed<float>(h->d_cf, K, x_dev, y_dev, n, seq_stride, n_seq, abs_input, zseg, ztile, stile,
-                                   tiles, st);
+    if (h->sequential) return iir_run(h, x_dev, y_dev, n, seq_stride, n_seq, abs_input, nullptr, st);
+    // Handles are shared between threads (dsp/_stages.py caches them by coefficients and the reference calls
+    // _process_channel_dsp_stateless from a 3-worker pool, capture.py:1906-1925), so a call owns its scratch:
+    // stream-ordered allocation from the device's default pool (wc_init keeps the pool from trimming).
+    void* scratch = nullptr;
+    WC_CUDA(cudaMallocAsync(&scratch, iir_scan_scratch_bytes(K, n, n_seq), st));
+    const int rc = iir_run(h, x_dev, y_dev, n, seq_stride, n_seq, abs_input, scratch, st);
+    cudaFreeAsync(scratch, st);
+    return rc;
 }
 
 // sum of squares per sequence (float64 accumulators); out_dev[n_seq] is overwritten.

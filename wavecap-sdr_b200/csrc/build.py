@@ -21,7 +21,8 @@ OBJ = CSRC / "build"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3", "--expt-relaxed-constexpr",
-         "-Xptxas", "-v"] + (["-DWC_DEV_ABLATE"] if os.environ.get("WC_DEV_ABLATE") else [])
+         "-Xptxas", "-v"] + (["-DWC_DEV_ABLATE", "-DWC_DEV"] if os.environ.get("WC_DEV_ABLATE") else []) \
+        + (["-DWC_DEV"] if os.environ.get("WC_DEV") else [])   # dev build: WC_* env switches + superseded kernel variants
 # per-file extras: the P25 kernels replay the reference's float32/float64 operation order, so the
 # compiler must not contract a*b+c into one fused multiply-add there (explicit fma() calls stay fused)
 EXTRA = {"p25.cu": ["-fmad=false"], "cqpsk.cu": ["-fmad=false"], "discdemod.cu": ["-fmad=false"]}
@@ -56,7 +57,10 @@ def build(verbose: bool = False, force: bool = False) -> Path:
             if log:
                 print(log, file=sys.stderr)
     if force or any(_newer(o, LIB) for o in objs):
-        cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs)]
+        # shared cudart: one CUDA runtime per process (torch's, loaded first by _native.lib()) instead of a second,
+        # statically embedded copy; the rpath covers a process that loads the library without torch
+        cmd = [NVCC, *ARCH, "-shared", "--cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
+               "-o", str(LIB), *map(str, objs)]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")

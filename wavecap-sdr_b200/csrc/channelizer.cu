@@ -65,6 +65,7 @@ __device__ __forceinline__ float2 blk_fetch(const ChanArgs& a, const float2* xc,
     return a.carried[(i + CH_T) * CH_M + k];
 }
 
+#ifdef WC_DEV   // phase-serial predecessor of chan256p_kernel: dev builds only, for A/B timing (WC_CHAN_VAR=0)
 // ABL (dev builds only, -DWC_DEV_ABLATE): timing ablations that skip one phase; results are then wrong by design.
 template <int MODE, int MINB, int ABL = 0>
 __global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArgs a) {
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArg
         fft_and_emit(fs, nv);
     }
 }
+#endif  // WC_DEV
 
 // ---------------------------------------------------------------------------------------------
 // Software-pipelined variant ("P"): the FIR of sub-tile n+1 is issued inside the FFT of sub-tile n.
@@ -842,11 +844,8 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
         a.scale = fm_scale;
         int R;
         int occ = 4;  // resident CTAs per SM of the fused-FM kernel; measured on B200: 4 -> 181 GS/s, 5 -> 165, 6 -> 159 (profiles/r01_chan_sweep2.jsonl)
-        // dev switches, read per call (~100 ns) so the sweep tools can change them inside one process
-        const int occ_env = env_int("WC_CHAN_OCC", 0), r_env = env_int("WC_CHAN_R", 0), var_env = env_int("WC_CHAN_VAR", 1);
-#ifdef WC_DEV_ABLATE
-        const int abl_env = env_int("WC_CHAN_ABL", 0);
-#endif
+        // dev switches (dev builds only; env_int is the inlined default in the product library)
+        const int occ_env = env_int("WC_CHAN_OCC", 0), r_env = env_int("WC_CHAN_R", 0);
         if (occ_env > 0) occ = occ_env;
         if (mode == WC_CHAN_OUT_COMPLEX) occ = 4;
         if (h->run_frames > 0) {
@@ -876,28 +875,35 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
             a.at.hp = (float)(1.5707963267948966 * fm_scale);
             a.at.pi = (float)(3.141592653589793 * fm_scale);
         }
-        const int var = var_env;  // 1 = software-pipelined kernel (FIR of sub-tile n+1 inside the FFT of sub-tile n); 0 = phase-serial
-        if (var == 1) {
-            // once per process (thread-safe static initialisation); the attribute is per function, not per device context
-            static const cudaError_t attr_rc = [] {
-                cudaError_t e = cudaFuncSetAttribute(chan256p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChanSmemP));
-                if (e != cudaSuccess) return e;
-                return cudaFuncSetAttribute(chan256p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChanSmemP));
-            }();
-            WC_CUDA(attr_rc);
-            if (mode == WC_CHAN_OUT_COMPLEX) chan256p_kernel<0><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);
-            else chan256p_kernel<1><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);
-        } else
-        if (mode == WC_CHAN_OUT_COMPLEX) chan256_kernel<0, 4><<<grid, CH_THREADS, 0, stream>>>(a);
+#ifdef WC_DEV
+        if (env_int("WC_CHAN_VAR", 1) == 0) {   // phase-serial kernel
 #ifdef WC_DEV_ABLATE
-        else if (abl_env == 1) chan256_kernel<1, 4, 1><<<grid, CH_THREADS, 0, stream>>>(a);
-        else if (abl_env == 2) chan256_kernel<1, 4, 2><<<grid, CH_THREADS, 0, stream>>>(a);
-        else if (abl_env == 3) chan256_kernel<1, 4, 3><<<grid, CH_THREADS, 0, stream>>>(a);
-        else if (abl_env == 4) chan256_kernel<1, 4, 4><<<grid, CH_THREADS, 0, stream>>>(a);
+            const int abl_env = env_int("WC_CHAN_ABL", 0);
 #endif
-        else if (occ == 4) chan256_kernel<1, 4><<<grid, CH_THREADS, 0, stream>>>(a);
-        else if (occ == 6) chan256_kernel<1, 6><<<grid, CH_THREADS, 0, stream>>>(a);
-        else chan256_kernel<1, 5><<<grid, CH_THREADS, 0, stream>>>(a);
+            if (mode == WC_CHAN_OUT_COMPLEX) chan256_kernel<0, 4><<<grid, CH_THREADS, 0, stream>>>(a);
+#ifdef WC_DEV_ABLATE
+            else if (abl_env == 1) chan256_kernel<1, 4, 1><<<grid, CH_THREADS, 0, stream>>>(a);
+            else if (abl_env == 2) chan256_kernel<1, 4, 2><<<grid, CH_THREADS, 0, stream>>>(a);
+            else if (abl_env == 3) chan256_kernel<1, 4, 3><<<grid, CH_THREADS, 0, stream>>>(a);
+            else if (abl_env == 4) chan256_kernel<1, 4, 4><<<grid, CH_THREADS, 0, stream>>>(a);
+#endif
+            else if (occ == 4) chan256_kernel<1, 4><<<grid, CH_THREADS, 0, stream>>>(a);
+            else if (occ == 6) chan256_kernel<1, 6><<<grid, CH_THREADS, 0, stream>>>(a);
+            else chan256_kernel<1, 5><<<grid, CH_THREADS, 0, stream>>>(a);
+        } else
+#endif
+        {
+            // software-pipelined kernel (FIR of sub-tile n+1 inside the FFT of sub-tile n). The dynamic shared-memory
+            // opt-in is a per-(function, device) attribute: set once per device this process launches on.
+            static std::atomic<unsigned long long> done0{0}, done1{0};
+            if (mode == WC_CHAN_OUT_COMPLEX) {
+                WC_CUDA(smem_optin(chan256p_kernel<0>, (int)sizeof(ChanSmemP), done0));
+                chan256p_kernel<0><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);
+            } else {
+                WC_CUDA(smem_optin(chan256p_kernel<1>, (int)sizeof(ChanSmemP), done1));
+                chan256p_kernel<1><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);
+            }
+        }
         WC_CUDA(cudaGetLastError());
     } else {
         const size_t need = sizeof(float2) * (size_t)F * n_chunks * h->M * (mode == WC_CHAN_OUT_FM ? 2 : 1);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 namespace wc {
@@ -30,8 +31,27 @@ const char* get_error();
     } while (0)
 
 int sm_count();
-// tuning / A-B switches for the dev tools (WC_* environment variables); absent in production use
+
+// Opt-in to > 48 KB of dynamic shared memory. The attribute belongs to the (function, device) pair, so it is set once
+// for every device this process launches on (one bit per device ordinal in `done`), not once per process.
+template <typename F>
+inline cudaError_t smem_optin(F* func, int bytes, std::atomic<unsigned long long>& done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+// tuning / A-B switches for the dev tools (WC_* environment variables): read only in dev builds (-DWC_DEV, i.e.
+// WC_DEV=1 python csrc/build.py). The product library never looks at the environment: env_int is the default, inlined.
+#ifdef WC_DEV
 int env_int(const char* name, int dflt);
+#else
+inline int env_int(const char*, int dflt) { return dflt; }
+#endif
 
 // ---- device helpers ----
 #ifdef __CUDACC__

@@ -295,11 +295,21 @@ int wc_fir_complex(const void* x_dev, int n, const double* taps_host, int n_taps
     WC_REQUIRE(n >= 1 && n_taps >= 1 && n_taps <= 4096 && decim >= 1, "wc_fir_complex: bad sizes");
     cudaStream_t s = (cudaStream_t)stream_v;
     const int hl = n_taps - 1;
-    double* d_taps = nullptr;
-    double2 *d_h = nullptr, *d_h2 = nullptr;
-    WC_CUDA(cudaMalloc((void**)&d_taps, sizeof(double) * n_taps));
-    WC_CUDA(cudaMalloc((void**)&d_h, sizeof(double2) * (hl > 0 ? hl : 1)));
-    WC_CUDA(cudaMalloc((void**)&d_h2, sizeof(double2) * (hl > 0 ? hl : 1)));
+    // one stream-ordered scratch block: taps | history in | history out; released on every exit path
+    const size_t hbytes = sizeof(double2) * (size_t)(hl > 0 ? hl : 1);
+    const size_t tbytes = (sizeof(double) * (size_t)n_taps + 15) & ~size_t(15);
+    struct Scratch {
+        void* p = nullptr;
+        cudaStream_t s;
+        ~Scratch() {
+            if (p) cudaFreeAsync(p, s);
+        }
+    } ws;
+    ws.s = s;
+    WC_CUDA(cudaMallocAsync(&ws.p, tbytes + 2 * hbytes, s));
+    double* d_taps = reinterpret_cast<double*>(ws.p);
+    double2* d_h = reinterpret_cast<double2*>(reinterpret_cast<char*>(ws.p) + tbytes);
+    double2* d_h2 = reinterpret_cast<double2*>(reinterpret_cast<char*>(ws.p) + tbytes + hbytes);
     WC_CUDA(cudaMemcpyAsync(d_taps, taps_host, sizeof(double) * n_taps, cudaMemcpyHostToDevice, s));
     if (hl > 0) {
         if (zi_host) WC_CUDA(cudaMemcpyAsync(d_h, zi_host, sizeof(double2) * hl, cudaMemcpyHostToDevice, s));
@@ -315,10 +325,8 @@ int wc_fir_complex(const void* x_dev, int n, const double* taps_host, int n_taps
         WC_CUDA(cudaMemcpyAsync(zi_out_host, d_h2, sizeof(double2) * hl, cudaMemcpyDeviceToHost, s));
     }
     WC_CUDA(cudaGetLastError());
+    // taps_host / zi_host are pageable caller memory and zi_out_host is read by the caller on return
     WC_CUDA(cudaStreamSynchronize(s));
-    cudaFree(d_taps);
-    cudaFree(d_h);
-    cudaFree(d_h2);
     return 0;
 }
 
@@ -511,9 +519,8 @@ int wc_ddc_process(wc_ddc* h, const void* iq_dev, int n_samples, void* out_dev, 
     groups = (K + a.ch_per_cta - 1) / a.ch_per_cta;
     a.span_max = (((a.out_tile - 1) * h->D1 + h->T1) + 1) & ~1;
     const size_t smem1 = (sizeof(double2) + sizeof(float2)) * (size_t)a.span_max + sizeof(double) * (size_t)h->T1;
-    static const cudaError_t attr_rc = cudaFuncSetAttribute(ddc_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                            (int)((sizeof(double2) + sizeof(float2)) * DDC_MAX_SPAN + sizeof(double) * DDC_MAX_T1));
-    WC_CUDA(attr_rc);
+    static std::atomic<unsigned long long> attr_done{0};
+    WC_CUDA(smem_optin(ddc_stage1_kernel, (int)((sizeof(double2) + sizeof(float2)) * DDC_MAX_SPAN + sizeof(double) * DDC_MAX_T1), attr_done));
     ddc_stage1_kernel<<<dim3(tiles, groups), DDC_THREADS, smem1, s>>>(a);
     ddc_hist1_kernel<<<K, 128, 0, s>>>(x, n_samples, (double)h->fs, h->d_chan, h->d_hist1[h->cur], h->d_hist1[h->cur ^ 1], hl1);
     if (two) {

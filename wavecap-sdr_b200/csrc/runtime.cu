@@ -19,10 +19,12 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+#ifdef WC_DEV
 int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return (e && *e) ? atoi(e) : dflt;
 }
+#endif
 
 int sm_count() {
     if (g_sm_count == 0) {
@@ -56,6 +58,16 @@ int wc_init(int device) {
     WC_REQUIRE(major == 10, "wc_init: device %d is sm_%d%d; this build carries sm_100a code only", device, major, minor);
     wc::g_sm_count = 0;
     wc::sm_count();
+    {
+        // stream-ordered scratch (cudaMallocAsync in the stateless entry points) comes from the device's default pool;
+        // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     return 0;
 }
 

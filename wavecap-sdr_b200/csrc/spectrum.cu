@@ -80,6 +80,7 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
 }
 // cp_async_commit / cp_async_wait<N> live in common.cuh
 
+#ifdef WC_DEV   // superseded variants, kept for A/B timing in dev builds only (-DWC_DEV)
 // pass A: grid (N2/16, n_frames)
 __global__ void __launch_bounds__(SP_THREADS, 4) spectrum_pass_a(const float2* __restrict__ iq, long long frame_stride,
                                                                  const float* __restrict__ window,
@@ -171,7 +172,9 @@ __global__ void __launch_bounds__(SP_THREADS, 4) spectrum_pass_b(const u64* __re
         o[k ^ (SP_N / 2)] = so[k2 * 17 + row];  // fftshift
     }
 }
+#endif  // WC_DEV
 
+#ifdef WC_DEV
 // ---- pipelined, persistent versions (the ones the 65536-point path launches) ------------------------
 // Both passes are streaming kernels whose only problem is latency, so each CTA keeps TWO tiles in shared
 // memory: while the 256-point FFTs of tile k run, the LDGSTS copies of tile k+1 are in flight.
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(SP_THREADS, 3) spectrum_pass_b2(const u64* __r
         buf ^= 1;
     }
 }
+#endif  // WC_DEV
 
 // ---- register-direct versions: no staging through shared memory -------------------------------------
 // ncu on the staged kernels shows them bound by shared-memory wavefronts (stage in, FFT read, exchange, stage out),
@@ -347,6 +351,7 @@ struct SpSmemA3 {
     float2 tw[256];
 };
 
+#ifdef WC_DEV
 __global__ void __launch_bounds__(SP_THREADS, 3) spectrum_pass_a3(const float2* __restrict__ iq, long long frame_stride,
                                                                   const float* __restrict__ window, u64* __restrict__ scratch,
                                                                   int n_frames) {
@@ -406,6 +411,7 @@ __global__ void __launch_bounds__(SP_THREADS, 3) spectrum_pass_a3(const float2* 
         }
     }
 }
+#endif  // WC_DEV
 
 // pass A5 = A3 with the next frame's 16 operands prefetched into registers while the current frame is transformed
 // (A3 loads, waits, computes, stores: between the load bursts nothing is in flight). The Hann coefficients are re-read
@@ -485,6 +491,7 @@ struct SpSmemB3 {
     float2 tw[256];
 };
 
+#ifdef WC_DEV
 __global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_b3(const u64* __restrict__ scratch, int avg, int n_frames,
                                                                   float* __restrict__ out) {
     __shared__ SpSmemB3 sm;
@@ -543,6 +550,7 @@ __global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_b3(const u64* __r
         o[k ^ (SP_N / 2)] = so[k2 * 17 + row];  // fftshift
     }
 }
+#endif  // WC_DEV
 
 // pass B5 = B3 made persistent over averaging groups: a CTA walks groups grp, grp + gridDim.y, ... and the row of the
 // NEXT frame (also across a group boundary) is always in flight while the current one is transformed. B3 handles one group
@@ -614,6 +622,7 @@ __global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_b5(const u64* __r
     }
 }
 
+#ifdef WC_DEV
 // ---- fused persistent version: both passes in ONE kernel, scratch is a small L2-resident ring --------
 // The two-pass design moves 8 (in) + 8 (scratch write) + 8 (scratch read) + 4/K (out) bytes per sample through
 // HBM because a slab's scratch does not survive in L2 between two launches. Here a single persistent grid pulls
@@ -768,6 +777,7 @@ __global__ void __launch_bounds__(SP_THREADS, 3) spectrum_fused_kernel(const SpF
         }
     }
 }
+#endif  // WC_DEV
 
 // ---- generic power-of-two path: Stockham autosort radix-2 in global memory --------------------
 __global__ void sp_window_kernel(const float2* __restrict__ iq, long long frame_stride, const float* __restrict__ window,
@@ -867,8 +877,7 @@ int wc_spectrum_create(int fft_size, wc_spectrum** out) {
         return -2;
     }
     cudaMemcpy(h->d_window, h->h_window.data(), sizeof(float) * fft_size, cudaMemcpyHostToDevice);
-    // both passes are latency-bound streaming kernels: 4 resident CTAs per SM (64 registers, 41 KB of shared memory
-    // each) need the large shared-memory carve-out
+#ifdef WC_DEV
     cudaFuncSetAttribute(spectrum_pass_a, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(spectrum_pass_b, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(spectrum_pass_a2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSmemA));
@@ -878,6 +887,7 @@ int wc_spectrum_create(int fft_size, wc_spectrum** out) {
     cudaFuncSetAttribute(spectrum_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(spectrum_pass_b3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(spectrum_pass_b2, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+#endif
     *out = h;
     return 0;
 }
@@ -985,7 +995,11 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
         WC_CUDA(cudaStreamWaitEvent(st, h->ev_join_b, 0));
         return 0;
     }
+#ifdef WC_DEV
     const bool fused = (n == SP_N && variant == 4);
+#else
+    const bool fused = false;
+#endif
     if (fused) slab = 1 << 20;   // the fused kernel's scratch is a ring: no slab limit (ctrl is 4 bytes per frame)
     if (slab > n_frames) slab = ((n_frames + avg - 1) / avg) * avg;
     if (!fused) {
@@ -999,6 +1013,7 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
         const float2* x = iq + (long long)f0 * frame_stride;
         if (n == SP_N) {
             u64* T = reinterpret_cast<u64*>(h->d_scratch);
+#ifdef WC_DEV
             if (variant == 4) {
                 // fused persistent kernel: ring of R frames, pass B lags pass A by `lag` groups
                 int lagf = 32;
@@ -1026,29 +1041,10 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
                 fa.out = o;
                 fa.ctrl = reinterpret_cast<int*>(h->d_ctrl);
                 spectrum_fused_kernel<<<3 * sm_count(), SP_THREADS, 0, st>>>(fa);
-            } else if (variant == 3) {
-                int fy = (6 * sm_count()) / 16;   // frames in flight: ~6 CTAs per SM over the 16 column tiles
-                fy = env_int("WC_SPECTRUM_FY", fy);
-                if (fy > cnt) fy = cnt;
-                if (fy < 1) fy = 1;
-                const int pav = env_int("WC_SPECTRUM_PASS_A", 6);   // measured on B200, 4096 frames: A3 153 GS/s, A5<3> 166, A5<2> 200
-                if (pav == 5) spectrum_pass_a5<3><<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
-                else if (pav == 6) spectrum_pass_a5<2><<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
-                else spectrum_pass_a3<<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
-                const int pbv = env_int("WC_SPECTRUM_PASS_B", 5);   // measured on B200, 4096 frames with pass A5<2>: B3 200 GS/s, B5 210
-                if (pbv == 5) {
-                    int gy = (4 * sm_count()) / 16;   // two waves of the 2 resident CTAs per SM over the 16 row tiles
-                    gy = env_int("WC_SPECTRUM_GY", gy);
-                    if (gy > groups) gy = groups;
-                    if (gy < 1) gy = 1;
-                    spectrum_pass_b5<<<dim3(SP_N1 / SP_COLS, gy), SP_THREADS, 0, st>>>(T, avg, cnt, groups, o);
-                } else {
-                    spectrum_pass_b3<<<dim3(SP_N1 / SP_COLS, groups), SP_THREADS, 0, st>>>(T, avg, cnt, o);
-                }
             } else if (variant == 1) {
                 spectrum_pass_a<<<dim3(SP_N2 / SP_COLS, cnt), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T);
                 spectrum_pass_b<<<dim3(SP_N1 / SP_COLS, groups), SP_THREADS, 0, st>>>(T, avg, cnt, o);
-            } else {
+            } else if (variant == 2) {
                 // persistent grids: 2 (pass A) / 3 (pass B) CTAs per SM, each double-buffering its tiles
                 int ga = (2 * sm_count()) / 16;
                 if (ga > cnt) ga = cnt;
@@ -1057,6 +1053,35 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
                 int gb = 3 * sm_count();
                 if (gb > groups * 16) gb = groups * 16;
                 spectrum_pass_b2<<<gb, SP_THREADS, sizeof(SpSmemB), st>>>(T, avg, cnt, groups, o);
+            } else
+#endif
+            {
+                // two register-direct passes on the caller's stream
+                int fy = (6 * sm_count()) / 16;   // frames in flight: ~6 CTAs per SM over the 16 column tiles
+                fy = env_int("WC_SPECTRUM_FY", fy);
+                if (fy > cnt) fy = cnt;
+                if (fy < 1) fy = 1;
+                // measured on B200, 4096 frames: A3 153 GS/s, A5<3> 166, A5<2> 200
+#ifdef WC_DEV
+                const int pav = env_int("WC_SPECTRUM_PASS_A", 6);
+                if (pav == 5) spectrum_pass_a5<3><<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
+                else if (pav != 6) spectrum_pass_a3<<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
+                else
+#endif
+                spectrum_pass_a5<2><<<dim3(SP_N2 / SP_COLS, fy), SP_THREADS, 0, st>>>(x, frame_stride, h->d_window, T, cnt);
+                // measured on B200, 4096 frames with pass A5<2>: B3 200 GS/s, B5 210
+#ifdef WC_DEV
+                if (env_int("WC_SPECTRUM_PASS_B", 5) != 5) {
+                    spectrum_pass_b3<<<dim3(SP_N1 / SP_COLS, groups), SP_THREADS, 0, st>>>(T, avg, cnt, o);
+                } else
+#endif
+                {
+                    int gy = (4 * sm_count()) / 16;   // two waves of the 2 resident CTAs per SM over the 16 row tiles
+                    gy = env_int("WC_SPECTRUM_GY", gy);
+                    if (gy > groups) gy = groups;
+                    if (gy < 1) gy = 1;
+                    spectrum_pass_b5<<<dim3(SP_N1 / SP_COLS, gy), SP_THREADS, 0, st>>>(T, avg, cnt, groups, o);
+                }
             }
         } else {
             float2* A = reinterpret_cast<float2*>(h->d_scratch);

@@ -53,9 +53,11 @@ def ssb_post_chain(sample_rate: int, enable_bandpass=True, bandpass_low=300, ban
 
 
 def am_tail(rows, sample_rate: int, audio_rate: int, stages, enable_agc: bool, agc_target_db: float,
-            want_stats: bool = False):
-    """IIRs -> [AGC] -> resample -> [agc soft clip when AGC is off] (dsp/am.py:105-141, 231-247)."""
+            want_stats: bool = False, blanker_db=None):
+    """[noise blanker] -> IIRs -> [AGC] -> resample -> [agc soft clip when AGC is off] (dsp/am.py:100-141, 213-247)."""
     y = rows
+    if blanker_db is not None:
+        y = F.noise_blanker_rows(y, blanker_db, 3)   # on the real envelope / real part, ahead of the filters (:100-101, :213-215)
     for b, a in stages:
         y = S.lfilter(b, a, y)
     if enable_agc:
@@ -77,14 +79,13 @@ def am_demod(iq, sample_rate: int, audio_rate: int = 48_000, enable_agc: bool = 
              enable_noise_blanker: bool = False, noise_blanker_threshold_db: float = 10.0,
              agc_target_db: float = -20.0, notch_frequencies=None):
     """Envelope AM demodulation (dsp/am.py:45-141)."""
-    if enable_noise_blanker:
-        F.noise_blanker(None)
     if _n(iq) == 0:
         return np.empty(0, dtype=np.float32)
     x = S.to_device(iq, np.complex64).reshape(-1)
     env, _, _, _ = S.front(x, S.FMT_CF32, x.numel(), 1, [S.MODE_AM], [0.0], None, int(sample_rate))
     stages = am_post_chain(sample_rate, enable_highpass, highpass_hz, enable_lowpass, lowpass_hz, notch_frequencies)
-    out = am_tail(env.reshape(1, -1), int(sample_rate), int(audio_rate), stages, enable_agc, agc_target_db)
+    out = am_tail(env.reshape(1, -1), int(sample_rate), int(audio_rate), stages, enable_agc, agc_target_db,
+                  blanker_db=noise_blanker_threshold_db if enable_noise_blanker else None)
     return S.like_input(out.reshape(-1), iq)
 
 
@@ -93,13 +94,12 @@ def ssb_demod(iq, sample_rate: int, audio_rate: int = 48_000, mode: str = "usb",
               enable_noise_blanker: bool = False, noise_blanker_threshold_db: float = 10.0,
               agc_target_db: float = -20.0, notch_frequencies=None, bfo_offset_hz: float = 1500.0):
     """SSB product detection with BFO (dsp/am.py:144-247)."""
-    if enable_noise_blanker:
-        F.noise_blanker(None)
     if _n(iq) == 0:
         return np.empty(0, dtype=np.float32)
     x = S.to_device(iq, np.complex64).reshape(-1)
     bfo = bfo_offset_hz if mode.lower() == "usb" else -bfo_offset_hz
     re, _, _, _ = S.front(x, S.FMT_CF32, x.numel(), 1, [S.MODE_SSB], [0.0], [bfo], int(sample_rate))
     stages = ssb_post_chain(sample_rate, enable_bandpass, bandpass_low, bandpass_high, notch_frequencies)
-    out = am_tail(re.reshape(1, -1), int(sample_rate), int(audio_rate), stages, enable_agc, agc_target_db)
+    out = am_tail(re.reshape(1, -1), int(sample_rate), int(audio_rate), stages, enable_agc, agc_target_db,
+                  blanker_db=noise_blanker_threshold_db if enable_noise_blanker else None)
     return S.like_input(out.reshape(-1), iq)

@@ -207,13 +207,36 @@ class PeerRegion:
         N.check(N.lib().wc_flag_set(C.c_void_p(self.flag_ptr(index)), value & 0xFFFFFFFF, N.torch_stream_ptr()))
 
     def wait_flags(self, index: int, count: int, value: int, timeout_ms: int = 2000, timed_out=None, stride: int = 1) -> None:
-        """Stream waits until flags index, index+stride, ... (count of them) reach `value`; `timed_out`: int32 CUDA tensor."""
+        """Stream waits until flags index, index+stride, ... (count of them) reach `value`. A wait that gives up (dead or
+        stalled peer) sets `timed_out` (int32 CUDA tensor; default: a flag this region owns) instead of hanging the GPU —
+        whatever the stream computes after that read a buffer that was never published, so the caller MUST look at the
+        flag before using any result: `check()` raises, and results produced since the last clean check are void."""
         import ctypes as C
 
         from . import _native as N
 
+        if timed_out is None:
+            timed_out = self._own_timeout_flag()
         N.check(N.lib().wc_flag_wait(C.c_void_p(self.flag_ptr(index)), count, stride, value & 0xFFFFFFFF, timeout_ms,
-                                     C.c_void_p(timed_out.data_ptr() if timed_out is not None else 0), N.torch_stream_ptr()))
+                                     C.c_void_p(timed_out.data_ptr()), N.torch_stream_ptr()))
+
+    def _own_timeout_flag(self):
+        import torch
+
+        if getattr(self, "_timed_out", None) is None:
+            self._timed_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+        return self._timed_out
+
+    def check(self) -> None:
+        """Synchronise the current stream and raise if any wait_flags() since the last check timed out."""
+        import torch
+
+        torch.cuda.current_stream().synchronize()
+        t = getattr(self, "_timed_out", None)
+        if t is not None and int(t.item()) != 0:
+            t.zero_()
+            raise TimeoutError("PeerRegion: a flag wait timed out — the peer never published the block; "
+                               "discard every result computed since the last check()")
 
     def close(self) -> None:
         import ctypes as C
