@@ -26,6 +26,8 @@ import sys
 import threading
 import time
 
+import numpy as np
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -57,7 +59,12 @@ def parse_args():
                     help="pull mode: rounds of share re-balancing from measured per-rank kernel times (0 = keep the initial shares)")
     ap.add_argument("--pull-rates", default="207,96", help="pull mode: rank 0's resident rate and the NVLink egress bound, GS/s")
     ap.add_argument("--bcast-chunks", type=int, default=8, help="50 ms chunks per broadcast block")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1-C4 `configs` legs (N=1 only)")
+    ap.add_argument("--no-one-capture", action="store_true", help="N>1: skip the `one_capture` (pull-mode) leg")
+    ap.add_argument("--sustained-seconds", type=float, default=2.5,
+                    help="extra back-to-back C5 steps after the K timed ones, for the sustained number (0 = off)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="cpu_baseline: seconds of CPU work per core (C5)")
     ap.add_argument("--cpu-samples", type=int, default=3_000_000, help="cpu_baseline samples per worker")
     return ap.parse_args()
 
@@ -169,48 +176,62 @@ WORKLOAD = ("C5: 256-ch polyphase channelizer (M=256, 9 taps/arm, hop 128) + FM 
             "of every channel, 125 MS/s cf32, 50 ms chunks (6.25 M samples)")
 
 
-def cpu_baseline(samples_per_worker: int, workers: int) -> dict:
-    from oracle.cpu_baseline import channelizer_fm_cpu
+def cpu_baseline(samples_per_worker: int, workers: int, seconds: float = 12.0) -> dict:
+    """C5 on the host cores: the UNMODIFIED reference (oracle/_ref, staged by oracle/build_ref.py) when it travelled with
+    the snapshot (`kind: "reference"`), else the oracle port of its per-frame loop (`kind: "port"`)."""
+    from oracle.cpu_baseline import channelizer_fm_cpu, config_cpu
 
-    # bounded sample: ~10 s of CPU work per core (12 passes over the per-worker slice)
-    r = channelizer_fm_cpu(samples_per_worker, workers, faithful=True, reps=12)
-    v = channelizer_fm_cpu(samples_per_worker * 4, workers, faithful=False)
-    return {
-        "value": round(r["msps"], 3), "unit": "MS/s", "cores": workers, "kind": "port",
-        "sample": f"{workers} processes x 12 passes x {samples_per_worker} cf32 samples each: oracle restatement of "
-                  f"PolyphaseChannelizer.process (per-frame loop, channelizer.py:114-135) + quadrature_demod "
-                  f"of all 256 channels; {r['seconds']:.1f} s",
-        "vectorized_port_msps": round(v["msps"], 3),
-    }
+    r = config_cpu("C5", workers, seconds=seconds)
+    try:
+        v = channelizer_fm_cpu(samples_per_worker * 4, workers, faithful=False)
+        r["vectorized_port_msps"] = round(v["msps"], 3)
+    except Exception:
+        pass
+    r["value"] = round(r["value"], 3)
+    return r
+
+
+def config_cpu_baselines(workers: int, seconds: float = 2.5) -> dict:
+    """CPU arm of every `configs` entry (C1..C4), same kind selection as cpu_baseline()."""
+    from oracle.cpu_baseline import config_cpu
+
+    out = {}
+    for name in ("C1", "C2", "C3", "C4-c4fm", "C4-cqpsk"):
+        try:
+            out[name] = config_cpu(name, workers, seconds=seconds)
+        except Exception as e:
+            out[name] = {"value": None, "unit": "MS/s", "cores": workers, "kind": "port", "sample": f"failed: {e}"}
+    return out
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference is pure Python
-    and cannot travel to the GPU box) on all host cores, same metric/config."""
+    """--impl reference: the reference's own CPU implementation of the C5 path (oracle/_ref: PolyphaseChannelizer.process +
+    quadrature_demod per channel, unmodified; the oracle port only if the staged copy is absent) on all host cores, same
+    metric/config. Each step is a bounded sample: every core loops process() over a 512 256-sample slice of the chunk for ~`seconds`."""
     if rank != 0:
         return
     workers = os.cpu_count() or 1
-    from oracle.cpu_baseline import channelizer_fm_cpu
+    from oracle.cpu_baseline import config_cpu
 
-    per_worker = max(256 + 128 * 64, min(2 * args.cpu_samples, 6_000_000))
-    for _ in range(max(0, min(args.warmup, 1))):
-        channelizer_fm_cpu(per_worker // 4, workers, faithful=True)
-    times, total = [], 0
-    for _ in range(max(1, args.steps if args.steps <= 5 else 5)):
-        r = channelizer_fm_cpu(per_worker, workers, faithful=True)
-        times.append(r["seconds"])
-        total += r["samples"]
-    steps = len(times)
-    msps = total / sum(times) / 1e6
+    steps = max(1, min(args.steps, 5))
+    warm = max(0, min(args.warmup, 1))
+    per_step_s = max(2.0, min(args.cpu_seconds, 6.0))
+    for _ in range(warm):
+        config_cpu("C5", workers, seconds=1.0)
+    rs = [config_cpu("C5", workers, seconds=per_step_s) for _ in range(steps)]
+    total = sum(r["samples"] for r in rs)
+    secs = sum(r["seconds"] for r in rs)
+    msps = sum(r["value"] for r in rs) / steps
+    kind = rs[0]["kind"]
     line = {
         "impl": "reference", "metric": METRIC, "value": round(msps, 3), "unit": "MS/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(1e3 * sum(times) / steps, 2),
+        "steps": steps, "warmup": warm, "ms_per_step": round(1e3 * secs / steps, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (numpy)",
         "data": "synthetic",
         "config": {"workload": WORKLOAD,
-                   "step": f"{workers} x {per_worker} samples (bounded sample of the 50 ms chunk)"},
-        "cpu_baseline": {"value": round(msps, 3), "unit": "MS/s", "cores": workers, "kind": "port",
-                         "sample": f"{steps} steps of {workers} processes x {per_worker} samples"},
+                   "step": f"{workers} processes x ~{per_step_s:.0f} s of process() calls on a 512 256-sample slice of the 50 ms chunk (bounded sample)"},
+        "cpu_baseline": {"value": round(msps, 3), "unit": "MS/s", "cores": workers, "kind": kind,
+                         "sample": f"{steps} steps; {rs[0]['sample']}; {total} samples in total"},
         "e2e": {"value": round(msps, 3), "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -313,7 +334,7 @@ def run_broadcast(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def run_pull(args, rank, local_rank, world):
+def run_pull(args, rank, local_rank, world, standalone=True):
     """ONE capture for the whole box without a data-path collective: rank 0's blocks (bcast-chunks x 6.25 M samples,
     double-buffered in ITS HBM = the ingest GPU) live in a sharding.PeerRegion mapped into every rank. Each rank's
     channelizer kernel reads its time slab (9-frame halo) straight out of that memory — for the other ranks the bulk
@@ -331,11 +352,12 @@ def run_pull(args, rank, local_rank, world):
     from wavecap_sdr_b200.dsp.channelizer import PolyphaseChannelizer
     from wavecap_sdr_b200.sharding import PeerRegion, frame_slab, slab_weights
 
-    torch.cuda.set_device(local_rank)
-    N.init(local_rank)
-    if world > 1:
-        init_nccl(local_rank)
-    bind_to_gpu_numa(local_rank)
+    if standalone:
+        torch.cuda.set_device(local_rank)
+        N.init(local_rank)
+        if world > 1:
+            init_nccl(local_rank)
+        bind_to_gpu_numa(local_rank)
     n = args.bcast_chunks * CHUNK
     local_rate, link_rate = (float(v) for v in args.pull_rates.split(","))
     if world == 1:
@@ -502,14 +524,18 @@ def run_pull(args, rank, local_rank, world):
                      "trace_ms_by_rank[wait,slab,set,step,host_enqueue]": [[round(float(v), 4) for v in x.tolist()] for x in traces]},
             "gpu_launches": (4 if world > 1 else 3) * args.steps, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        if standalone:
+            print(json.dumps(line), flush=True)
+    else:
+        line = None
     del rows
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     region.close()
-    if world > 1:
+    if world > 1 and standalone:
         dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -528,12 +554,14 @@ def main():
         return
 
     # CPU baseline first (rank 0, N=1 only), before CUDA is touched in this process.
-    cpu = None
+    cpu, cfg_cpu = None, {}
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            cpu = cpu_baseline(args.cpu_samples, os.cpu_count() or 1)
+            cpu = cpu_baseline(args.cpu_samples, os.cpu_count() or 1, args.cpu_seconds)
         except Exception as e:  # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": "MS/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        if not args.no_configs:
+            cfg_cpu = config_cpu_baselines(os.cpu_count() or 1)
 
     import torch
     import torch.distributed as dist
@@ -591,6 +619,30 @@ def main():
     value = world * samples_per_step / (ms * 1e-3) / 1e6
     checksum = float(out[:: max(1, out.shape[0] // 997)].double().abs().sum().item())
 
+    # sustained: the K timed steps above are a burst (tens of ms); this kernel is FMA/issue-bound, so its rate follows
+    # the SM clock, which settles lower under seconds of load. Same launches back to back for >= --sustained-seconds, the
+    # clock sampled inside; reported beside the burst number, not instead of it.
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / ms) + 1)
+        barrier()
+        s_sampler = ClockSampler(local_rank)
+        s_sampler.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_sus):
+            step()
+        s1.record()
+        barrier()
+        s_clocks = s_sampler.stop()
+        s_ms = s0.elapsed_time(s1) / n_sus
+        ts = torch.tensor([s_ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        s_ms = float(ts.item())
+        sustained = {"value": round(world * samples_per_step / (s_ms * 1e-3) / 1e6, 1), "unit": "MS/s", "steps": n_sus,
+                     "seconds": round(n_sus * s_ms * 1e-3, 2), "ms_per_step": round(s_ms, 4), "clocks": s_clocks}
+
     # secondary, informational: the channelizer alone (mode 0 = what PolyphaseChannelizer.process() returns,
     # complex64 frames, 24 algorithmic bytes per input sample) on a sub-batch that fits beside the FM buffers
     from wavecap_sdr_b200.dsp.channelizer import OUT_COMPLEX
@@ -645,6 +697,95 @@ def main():
     e2e_value = world * eb * CHUNK / (e_ms * 1e-3) / 1e6
     g_sub = max(1, min(eb, (4 << 20) // CHUNK))  # sub-batches of the pipelined host call (channelizer.cu)
 
+    # the ceiling the e2e leg runs under: the same bytes moved by plain pinned cudaMemcpyAsync, H2D and D2H concurrently on
+    # two streams, all ranks at once, no kernel — what this box's host<->device path gives the whole job
+    ceiling = None
+    try:
+        d_in = torch.empty((eb * CHUNK,), dtype=torch.complex64, device="cuda")
+        d_o = torch.empty((eb * frames, 256), dtype=torch.float32, device="cuda")
+        t_in, t_o = torch.from_numpy(hx), torch.from_numpy(hout)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copy_step():
+            with torch.cuda.stream(s_up):
+                d_in.copy_(t_in, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                t_o.copy_(d_o, non_blocking=True)
+            s_up.synchronize()
+            s_dn.synchronize()
+
+        copy_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            copy_step()
+        c_ms = (time.perf_counter() - t0) * 1e3 / 3
+        tc = torch.tensor([c_ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        c_ms = float(tc.item())
+        ceiling = {"value": round(world * eb * CHUNK / (c_ms * 1e-3) / 1e6, 1), "unit": "MS/s", "ms_per_step": round(c_ms, 3),
+                   "h2d_plus_d2h_gbs_per_gpu": round((hx.nbytes + hout.nbytes) / (c_ms * 1e-3) / 1e9, 1),
+                   "what": "plain pinned cudaMemcpyAsync of the step's input and output, both directions concurrently, every rank "
+                           "at once, no kernel"}
+        del d_in, d_o
+    except Exception as e:
+        ceiling = {"error": f"{type(e).__name__}: {e}"}
+
+    # the reference-facing Python call itself: PolyphaseChannelizer.process(numpy chunk) -> list of per-frame arrays
+    # (pageable input like the reference's callers hand over, 48 827 row views built on return)
+    api = None
+    if rank == 0:
+        try:
+            one = np.ascontiguousarray(hx[:CHUNK])
+            ch3 = PolyphaseChannelizer(FS, BW)
+            ch3.process(one)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                res = ch3.process(one)
+            a_ms = (time.perf_counter() - t0) * 1e3 / 2
+            api = {"value": round(CHUNK / (a_ms * 1e-3) / 1e6, 1), "unit": "MS/s", "ms_per_chunk": round(a_ms, 2),
+                   "frames_returned": len(res), "what": "PolyphaseChannelizer.process(complex64 ndarray of one 50 ms chunk) -> list of "
+                   "48 827 complex64[256] arrays, pageable host memory, one GPU"}
+            del res, ch3
+        except Exception as e:
+            api = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- C1..C4 (N=1 only): the other BASELINE configs, each with its own roofline, clocks and CPU arm ----------
+    cfg_recs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        del x
+        torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs
+
+            cfg_recs = bench_configs.headline_configs(ClockSampler)
+            for r in cfg_recs:
+                r["cpu_baseline"] = cfg_cpu.get(r.get("config"))
+                cb = r["cpu_baseline"]
+                if cb and cb.get("value") and r.get("value"):
+                    r["gpu_over_cpu"] = round(r["value"] / cb["value"], 1)
+        except Exception as e:
+            cfg_recs = [{"error": f"{type(e).__name__}: {e}"}]
+
+    # ---- N>1: the north-star-literal split — ONE capture over all ranks (pull mode) — beside the replicas headline
+    one_capture = None
+    if world > 1 and not args.no_one_capture:
+        try:
+            del x
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        barrier()
+        try:
+            oc = run_pull(args, rank, local_rank, world, standalone=False)
+            if rank == 0 and oc is not None:
+                one_capture = {k: oc[k] for k in ("mode", "value", "unit", "ms_per_step", "steps", "scaling", "link", "clocks")}
+                one_capture["config"] = {k: oc["config"][k] for k in ("workload", "block_samples", "slab_weights", "parallelism", "bound", "checked")}
+        except BaseException as e:  # noqa: BLE001 — SystemExit from a failed cross-check included
+            one_capture = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved = ALG_BYTES_PER_SAMPLE * samples_per_step / (ms * 1e-3) / 1e9
@@ -680,7 +821,13 @@ def main():
             },
             "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_value, 1), "unit": "MS/s", "ms_per_step": round(e_ms, 3),
-                    "h2d_bytes_per_step": int(eb * CHUNK * 8), "d2h_bytes_per_step": int(eb * frames * 256 * 4)},
+                    "h2d_bytes_per_step": int(eb * CHUNK * 8), "d2h_bytes_per_step": int(eb * frames * 256 * 4),
+                    "copy_ceiling": ceiling,
+                    "frac_of_copy_ceiling": round(e2e_value / ceiling["value"], 3) if ceiling and ceiling.get("value") else None,
+                    "python_process_api": api},
+            "sustained": dict(sustained, roofline_frac=round(ALG_BYTES_PER_SAMPLE * sustained["value"] / world / 1e3 / peak, 4)) if sustained else None,
+            "configs": cfg_recs,
+            "one_capture": one_capture,
             "gpu_launches": 2 * args.steps + 2 * ((eb + g_sub - 1) // g_sub) * (e_steps + 1),
             "clocks": clocks,
         }

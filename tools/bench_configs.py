@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Throughput of the non-headline configs (BASELINE.json configs[0..3] + the trunking fan-out) on one B200.
-Not the bench.py contract — a measurement aid whose JSON lines are kept under profiles/.
 
-Each line: config, what one "step" is, ms per step (CUDA events, after warm-up, inputs resident in HBM), the
-metric in the unit natural to the config, algorithmic HBM bytes per step and the HBM fraction they imply
-(SURVEY §8d says which configs are HBM-bound and which are compute/latency-bound by construction).
+`headline_configs()` is what bench.py folds into its JSON line as `configs`: C1, C2, C3 and C4 (C4FM + CQPSK banks, 64
+channels), each with ms per step (CUDA events after warm-up, inputs resident in HBM), the config's natural metric, its
+roofline (algorithmic HBM bytes of SURVEY §8d; for the compute-bound C2 also the share of the FP32 peak) and the SM
+clocks sampled during its own timed region. The CLI prints the same records plus the §8f rows as JSON lines
+(kept under profiles/).
 """
 import json
 import os
@@ -14,17 +15,18 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 import wavecap_sdr_b200._native as N  # noqa: E402
 
-N.init(0)
 PEAK = 6550.1
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # SMs x lanes x FMA x max SM clock
 
 
 def timeit(fn, warm=3, iters=10):
@@ -40,6 +42,31 @@ def timeit(fn, warm=3, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
+def timed_with_clocks(fn, sampler_cls=None, warm=3, min_seconds=0.25, max_iters=2000):
+    """ms per call (CUDA events around a region of >= min_seconds) + the SM clocks NVML reported inside that region."""
+    ms0 = timeit(fn, warm=warm, iters=3)
+    iters = int(min(max_iters, max(5, min_seconds * 1e3 / max(ms0, 1e-3))))
+    sampler = sampler_cls(torch.cuda.current_device()) if sampler_cls else None
+    if sampler:
+        sampler.start()
+    ms = timeit(fn, warm=0, iters=iters)
+    clocks = sampler.stop() if sampler else None
+    return ms, iters, clocks
+
+
+def roofline(alg_bytes, ms, kernel, note=None, flops=None):
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": round(gbs, 1), "peak": PEAK, "unit": "GB/s", "frac": round(gbs / PEAK, 4),
+         "alg_bytes_per_step": int(alg_bytes), "kernel": kernel, "traffic": None}
+    if flops:
+        tf = flops / (ms * 1e-3) / 1e12
+        r["fp32"] = {"achieved_tflops": round(tf, 2), "peak_tflops": round(FP32_PEAK_TFLOPS, 1),
+                     "frac": round(tf / FP32_PEAK_TFLOPS, 4), "flops_per_step": int(flops)}
+    if note:
+        r["note"] = note
+    return r
+
+
 def emit(**kw):
     if "alg_bytes" in kw and kw.get("ms"):
         kw["alg_gbs"] = round(kw["alg_bytes"] / (kw["ms"] * 1e-3) / 1e9, 1)
@@ -47,71 +74,132 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def c1_c2():
+def cfg_c1(sampler_cls=None, B=64):
+    """C1: one WBFM channel, 2.4 MS/s cf32, B chunks of 120 000 per call (capture._process_channel_dsp_stateless batch)."""
     from wavecap_sdr_b200.capture import ChannelConfig, apply_mode_defaults, process_channels_batch
 
-    # C1: one WBFM channel, 2.4 MS/s cf32, B chunks of 120 000 per call
-    fs, n, B = 2_400_000, 120_000, 64
+    fs, n = 2_400_000, 120_000
     x = torch.view_as_complex(torch.randn((B * n, 2), device="cuda") * 0.3)
     cfg = apply_mode_defaults("wbfm", ChannelConfig(id="a", capture_id="c", mode="wbfm", offset_hz=200000.0))
-    ms = timeit(lambda: process_channels_batch(x, fs, [cfg], n_chunks=B, return_device=True), iters=5)
-    emit(config="C1 WBFM 1 ch, 2.4 MS/s cf32", step=f"{B} chunks x {n} samples, full wbfm chain incl. host result assembly",
-         ms=round(ms, 3), msps=round(B * n / ms / 1e3, 1), realtime_x=round(B * n / fs / (ms * 1e-3), 1),
-         alg_bytes=B * n * 8 + B * 2400 * 4)
-    # C2: 16 NBFM channels, 10 MS/s int16, B chunks of 500 000
-    fs, n, B = 10_000_000, 500_000, 8
+    ms, iters, clocks = timed_with_clocks(lambda: process_channels_batch(x, fs, [cfg], n_chunks=B, return_device=True), sampler_cls)
+    return {"config": "C1", "workload": "WBFM 1 channel from 2.4 MS/s cf32 (freq_shift, RSSI, discriminator, de-emphasis, 15 kHz MPX "
+                                        "low-pass, RMS, 1/50 resampler, soft clip)",
+            "step": f"{B} chunks x {n} samples", "ms": round(ms, 4), "steps": iters, "metric": "input MS/s",
+            "value": round(B * n / ms / 1e3, 1), "unit": "MS/s", "realtime_x": round(B * n / fs / (ms * 1e-3), 1),
+            "roofline": roofline(B * n * 8 + B * 2400 * 4, ms, "iir_kernel (block scan) + front_kernel + resample_residue_kernel",
+                                 note="8.08 B/sample algorithmic; the chain is latency/FP64-bound (SURVEY §8d), the HBM fraction is stated for completeness",
+                                 flops=60 * B * n),
+            "clocks": clocks}
+
+
+def cfg_c2(sampler_cls=None, B=8):
+    """C2: 16 NBFM channels + squelch from one 10 MS/s int16 capture, B chunks of 500 000."""
+    from wavecap_sdr_b200.capture import ChannelConfig, apply_mode_defaults, process_channels_batch
+
+    fs, n = 10_000_000, 500_000
     q = torch.randint(-2000, 2000, (B, n, 2), device="cuda", dtype=torch.int16)
     cfgs = []
     for i in range(16):
         c = apply_mode_defaults("nbfm", ChannelConfig(id=str(i), capture_id="c", mode="nbfm", offset_hz=-3.75e6 + 5e5 * i))
         c.squelch_db = -45.0
         cfgs.append(c)
-    ms = timeit(lambda: process_channels_batch(q, fs, cfgs, n_chunks=B, in_fmt="cs16", apply_squelch=True,
-                                               return_device=True), iters=5)
-    emit(config="C2 16 NBFM ch + squelch, 10 MS/s cs16", step=f"{B} chunks x {n} samples x 16 channels",
-         ms=round(ms, 3), input_msps=round(B * n / ms / 1e3, 1), channel_msps=round(16 * B * n / ms / 1e3, 1),
-         realtime_x=round(B * n / fs / (ms * 1e-3), 1), alg_bytes=B * n * 4 + 16 * B * 2400 * 4)
+    ms, iters, clocks = timed_with_clocks(lambda: process_channels_batch(q, fs, cfgs, n_chunks=B, in_fmt="cs16", apply_squelch=True,
+                                                                         return_device=True), sampler_cls)
+    return {"config": "C2", "workload": "16 NBFM channels + squelch from one 10 MS/s cs16 capture (per channel: NCO, discriminator, RMS, "
+                                        "3/625 resampler, soft clip)",
+            "step": f"{B} chunks x {n} samples x 16 channels", "ms": round(ms, 4), "steps": iters, "metric": "input MS/s",
+            "value": round(B * n / ms / 1e3, 1), "unit": "MS/s", "channel_msps": round(16 * B * n / ms / 1e3, 1),
+            "realtime_x": round(B * n / fs / (ms * 1e-3), 1),
+            "roofline": roofline(B * n * 4 + 16 * B * 2400 * 4, ms, "front_kernel + resample_residue_kernel",
+                                 note="4.31 B/sample algorithmic; FP32/SFU compute-bound by construction (16 sincos + 16 atan2 per input sample, "
+                                      "SURVEY §8d): the fp32 block is the relevant fraction",
+                                 flops=1900 * B * n),
+            "clocks": clocks}
 
 
-def c3():
+def cfg_c3(sampler_cls=None, frames=4096):
+    """C3: 65536-point Hann spectrum, dB, fftshift, K=4 dB mean on contiguous frames of a 61.44 MS/s stream."""
     from wavecap_sdr_b200.dsp.fft.cuda_backend import CudaFFTBackend
 
     be = CudaFFTBackend(65536)
+    x = torch.view_as_complex(torch.randn((frames * 65536, 2), device="cuda") * 0.2)
+    be.execute_frames(x, frames, 65536, 4)
+    ms, iters, clocks = timed_with_clocks(lambda: be.execute_frames(x, frames, 65536, 4), sampler_cls)
+    return {"config": "C3", "workload": "65536-pt windowed spectrum (Hann, |X| dB, fftshift) with K=4 dB averaging, 61.44 MS/s cf32",
+            "step": f"{frames} contiguous frames", "ms": round(ms, 4), "steps": iters, "metric": "input MS/s",
+            "value": round(frames * 65536 / ms / 1e3, 1), "unit": "MS/s", "frames_per_s": round(frames / (ms * 1e-3)),
+            "realtime_x": round(frames * 65536 / 61.44e6 / (ms * 1e-3), 1),
+            "roofline": roofline(frames * 65536 * 8 + frames // 4 * 65536 * 4, ms, "spectrum passes (csrc/spectrum.cu)",
+                                 note="9 B/sample algorithmic (8 in + 4/K out)"),
+            "clocks": clocks}
+
+
+def cfg_c4(sampler_cls=None, C=64, n=72000):
+    """C4: P25 C4FM and CQPSK banks, C channels at 48 kS/s, one demodulate() of n samples per channel."""
+    from oracle.c4fm import modulate_c4fm, random_frames
+    from oracle.cqpsk import modulate_cqpsk
+    from wavecap_sdr_b200.decoders.p25 import CQPSKBank
+    from wavecap_sdr_b200.dsp.p25.c4fm import C4FMBank
+
+    fs = 48000
+    rng = np.random.default_rng(1)
+    base = modulate_c4fm(random_frames(rng, n_frames=(n // 2140) + 2, payload=150, gap=40), fs, seed=1)[:n]
+    x = torch.from_numpy(np.ascontiguousarray(np.tile(base, (C, 1)))).cuda()
+    x = x * torch.exp(1j * torch.rand((C, 1), device="cuda") * 6.28).to(torch.complex64)
+    bank = C4FMBank(C, fs)
+    out = []
+    ms, iters, clocks = timed_with_clocks(lambda: bank.demodulate(x), sampler_cls, warm=2)
+    out.append({"config": "C4-c4fm", "workload": f"P25 C4FM symbol recovery bank, {C} channels at 48 kS/s", "step": f"one demodulate() of {n} samples/channel "
+                f"({n / fs * 1e3:.0f} ms of signal)", "ms": round(ms, 4), "steps": iters, "metric": "channel MS/s", "value": round(C * n / ms / 1e3, 2),
+                "unit": "MS/s", "channels_x_realtime": round(C * n / fs / (ms * 1e-3)),
+                "roofline": roofline(C * n * 8 + C * (n // 10) * 5, ms, "p25_fir_kernel + c4fm_phase_kernel + c4fm_sync_kernel",
+                                     note="8.5 B per channel-sample algorithmic; sequential per channel, latency-bound by construction (SURVEY §8d)"),
+                "clocks": clocks})
+    cb = modulate_cqpsk(rng.integers(0, 4, n // 10 + 8), fs, 4800, seed=2)[:n]
+    xq = torch.from_numpy(np.ascontiguousarray(np.tile(cb, (C, 1)))).cuda()
+    qb = CQPSKBank(C, fs)
+    ms, iters, clocks = timed_with_clocks(lambda: qb.demodulate(xq), sampler_cls, warm=2)
+    out.append({"config": "C4-cqpsk", "workload": f"P25 CQPSK symbol recovery bank, {C} channels at 48 kS/s", "step": f"one demodulate() of {n} samples/channel",
+                "ms": round(ms, 4), "steps": iters, "metric": "channel MS/s", "value": round(C * n / ms / 1e3, 2), "unit": "MS/s",
+                "channels_x_realtime": round(C * n / fs / (ms * 1e-3)),
+                "roofline": roofline(C * n * 8 + C * (n // 10), ms, "cqpsk_* kernels (csrc/cqpsk.cu)",
+                                     note="sequential MMSE/Gardner/frequency loop per channel, latency-bound by construction (SURVEY §8d)"),
+                "clocks": clocks})
+    return out
+
+
+def headline_configs(sampler_cls=None):
+    """C1..C4 records for bench.py's `configs` array (inputs generated on the device, resident in HBM when timed)."""
+    recs = []
+    for fn in (cfg_c1, cfg_c2, cfg_c3):
+        try:
+            recs.append(fn(sampler_cls))
+        except Exception as e:  # a config must never take the headline down with it
+            recs.append({"config": fn.__name__[4:].upper(), "error": f"{type(e).__name__}: {e}"})
+        torch.cuda.empty_cache()
+    try:
+        recs.extend(cfg_c4(sampler_cls))
+    except Exception as e:
+        recs.append({"config": "C4", "error": f"{type(e).__name__}: {e}"})
+    torch.cuda.empty_cache()
+    return recs
+
+
+def c1_c2():
+    for r in (cfg_c1(), cfg_c2()):
+        print(json.dumps(r), flush=True)
+
+
+def c3():
     for frames in (46 * 8, 4096):
-        x = torch.view_as_complex(torch.randn((frames * 65536, 2), device="cuda") * 0.2)
-        out = be.execute_frames(x, frames, 65536, 4)
-        ms = timeit(lambda: be.execute_frames(x, frames, 65536, 4))
-        emit(config="C3 65536-pt spectrum, Hann, dB, fftshift, K=4 mean, 61.44 MS/s", step=f"{frames} contiguous frames",
-             ms=round(ms, 3), msps=round(frames * 65536 / ms / 1e3, 1), frames_per_s=round(frames / (ms * 1e-3)),
-             realtime_x=round(frames * 65536 / 61.44e6 / (ms * 1e-3), 1), alg_bytes=frames * 65536 * 8 + frames // 4 * 65536 * 4)
-        del x, out
+        print(json.dumps(cfg_c3(frames=frames)), flush=True)
 
 
 def c4():
-    from wavecap_sdr_b200.decoders.p25 import CQPSKBank
-    from wavecap_sdr_b200.dsp.p25.c4fm import C4FMBank
-    from oracle.c4fm import modulate_c4fm, random_frames
-    from oracle.cqpsk import modulate_cqpsk
-
-    fs = 48000
     for C in (64, 1024):
         for n in (2400, 72000):
-            rng = np.random.default_rng(1)
-            base = modulate_c4fm(random_frames(rng, n_frames=(n // 2140) + 2, payload=150, gap=40), fs, seed=1)[:n]
-            x = torch.from_numpy(np.ascontiguousarray(np.tile(base, (C, 1)))).cuda()
-            x = x * torch.exp(1j * torch.rand((C, 1), device="cuda") * 6.28).to(torch.complex64)
-            bank = C4FMBank(C, fs)
-            ms = timeit(lambda: bank.demodulate(x), warm=2, iters=5)
-            emit(config=f"C4 C4FM bank, {C} ch, 48 kS/s", step=f"one demodulate() of {n} samples/channel ({n / fs * 1e3:.0f} ms of signal)",
-                 ms=round(ms, 3), channel_msps=round(C * n / ms / 1e3, 2), realtime_x_per_channel=round(n / fs / (ms * 1e-3), 1),
-                 channels_x_realtime=round(C * n / fs / (ms * 1e-3)), alg_bytes=C * n * 8 + C * (n // 10) * 5)
-            cb = modulate_cqpsk(rng.integers(0, 4, n // 10 + 8), fs, 4800, seed=2)[:n]
-            xq = torch.from_numpy(np.ascontiguousarray(np.tile(cb, (C, 1)))).cuda()
-            qb = CQPSKBank(C, fs)
-            ms = timeit(lambda: qb.demodulate(xq), warm=2, iters=5)
-            emit(config=f"C4 CQPSK bank, {C} ch, 48 kS/s", step=f"one demodulate() of {n} samples/channel",
-                 ms=round(ms, 3), channel_msps=round(C * n / ms / 1e3, 2), realtime_x_per_channel=round(n / fs / (ms * 1e-3), 1),
-                 channels_x_realtime=round(C * n / fs / (ms * 1e-3)), alg_bytes=C * n * 8 + C * (n // 10))
+            for r in cfg_c4(C=C, n=n):
+                print(json.dumps(r), flush=True)
 
 
 def framer():
@@ -208,6 +296,7 @@ def ddc():
 
 
 if __name__ == "__main__":
+    N.init(0)
     which = sys.argv[1:] or ["c1c2", "c3", "c4", "ddc", "framer", "voice", "scanner"]
     t0 = time.time()
     if "c1c2" in which:
