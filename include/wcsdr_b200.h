@@ -31,6 +31,9 @@ const char* wc_version(void);
 typedef struct wc_chan wc_chan;
 #define WC_CHAN_OUT_COMPLEX 0 /* process(): complex64 frames [F][M]                channelizer.py:91  */
 #define WC_CHAN_OUT_FM 1      /* fused quadrature_demod() of every bin: float32 [F][M] dsp/fm.py:65   */
+#define WC_CHAN_OUT_AUDIO 2   /* nbfm_demod() of every bin: float32 [ceil(F/D)][M]   dsp/fm.py:317-406 */
+#define WC_CHAN_IN_CF32 0     /* complex64 IQ                                                          */
+#define WC_CHAN_IN_CS16 1     /* interleaved int16 I,Q, scaled by 1/32768 like cli.py:449-453          */
 
 /* __init__ (channelizer.py:35-67): M = int(fs/bw) made even; prototype = firwin(M*T-1, 0.9*bw/(fs/2),
  * kaiser 8.0) designed on the host inside the library (no scipy at run time). */
@@ -56,6 +59,21 @@ int wc_chan_set_run_frames(wc_chan* h, int run_frames);
 /* same, host buffers: H2D copy + kernels + D2H copy + sync (the reference-facing call). */
 int wc_chan_process_host(wc_chan* h, const void* iq_host, long long n_samples, int n_chunks, int mode,
                          float fm_scale, void* out_host);
+
+/* Input formats and the audio mode (SURVEY §8d "C5 + audio /20"). in_fmt WC_CHAN_IN_CS16 reads the capture as
+ * interleaved int16 I,Q (4 bytes per sample over PCIe and HBM instead of 8; converted to the exact float32 the
+ * reference's /32768.0 produces as each row enters the FIR; M = 256 / 9-tap grid, 16-byte aligned chunks).
+ * Mode WC_CHAN_OUT_AUDIO is nbfm_demod(extract_channel(process(x), k), demod_rate, audio_rate) with the reference's
+ * defaults (dsp/fm.py:317-406: quadrature_demod -> rms_normalize over the chunk -> resample_poly -> soft_clip) for
+ * every channel k: float32 [n_chunks][wc_chan_audio_len][M], built for integer decimation (audio_rate divides
+ * demod_rate: resample_poly's up = 1), e.g. 976560 -> 48828 = /20 for the 125 MS/s grid. fm_scale is ignored in this
+ * mode (the discriminator scale is float32(demod_rate/(2 pi 75000)), dsp/fm.py:94). */
+int wc_chan_audio_config(wc_chan* h, int demod_rate, int audio_rate);
+long long wc_chan_audio_len(const wc_chan* h, long long n_samples);   /* ceil(frames / D) per chunk and channel */
+int wc_chan_process_ex(wc_chan* h, const void* iq_dev, int in_fmt, long long n_samples, int n_chunks, long long chunk_stride,
+                       int mode, float fm_scale, void* out_dev, void* stream);
+int wc_chan_process_host_ex(wc_chan* h, const void* iq_host, int in_fmt, long long n_samples, int n_chunks, int mode,
+                            float fm_scale, void* out_host);
 
 /* ---- analog demod chain: wavecapsdr/capture.py:298-439, dsp/fm.py, dsp/am.py, dsp/agc.py, dsp/filters.py ----
  * Stage-level operators on device buffers; the Python host (wavecap_sdr_b200/capture.py, dsp/*.py) chains

@@ -258,3 +258,107 @@ def test_channelize_samples_and_calculator(native):
     ye, re_ = oracle_channelize(xc, 125.0e6, tgt, 100.0e6, 488281)
     assert ChannelCalculatorOracle(100.0e6, 125.0e6, 488281).get_channel_index(tgt) == 247
     assert rate == re_ and y.shape == ye.shape and rel_rms(y, ye) < TOL
+
+
+# ---- int16 capture format and the audio (/20) output mode: SURVEY §8d row "C5 + audio", cli.py:449-453 ------------------
+
+def _cs16(n, seed, amp=6000):
+    rng = np.random.default_rng(seed)
+    return rng.integers(-amp, amp, size=(n, 2), dtype=np.int16)
+
+
+@pytest.mark.parametrize("n", [256 + 128 * 77, 256 + 128 * 7 + 5, 256 + 128 * 600 + 127, 4000])
+def test_cs16_input_equals_the_converted_cf32_call(native, n):
+    """int16 I,Q scaled by 1/32768 is an exact float32 value, so the int16 path must give the very same bits as the
+    complex64 path fed with the reference's own conversion (cli.py:449-453), and match the oracle to 1e-4."""
+    from oracle import analog as oa
+
+    q = _cs16(n, seed=n)
+    xc = oa.cs16_to_cf32(q)
+    a, b, o = _chan(native, 125_000_000, 488281), _chan(native, 125_000_000, 488281), ChannelizerOracle(125_000_000, 488281)
+    cut = (n // 3) & ~3                                  # two calls: carried history comes from int16 rows too
+    for part_q, part_c in ((q[:cut], xc[:cut]), (q[cut:], xc[cut:])):
+        fa, fb = a.process_array(part_q), b.process_array(part_c)
+        assert fa.dtype == np.complex64 and np.array_equal(fa, fb)
+        exp = o.process_vectorized(part_c)
+        if len(exp):
+            assert rel_rms(fa, exp) < TOL
+    assert np.array_equal(a.arm_history, b.arm_history)
+    a.reset(), b.reset()
+    assert np.array_equal(a.process_fm(q), b.process_fm(xc))
+
+
+def test_cs16_batched_chunks_and_device_tensors(native):
+    import torch
+    from oracle import analog as oa
+
+    n, B = 256 + 128 * 300, 3
+    q = _cs16(n * B, seed=5)
+    a, b = _chan(native, 125_000_000, 488281), _chan(native, 125_000_000, 488281)
+    batched = a.process_batch(torch.from_numpy(q).cuda(), B, fm=True).cpu().numpy()
+    seq = np.concatenate([b.process_fm(oa.cs16_to_cf32(q[i * n:(i + 1) * n])) for i in range(B)])
+    assert np.array_equal(batched, seq)
+
+
+def _audio_oracle(frames, demod_rate, audio_rate):
+    from oracle import analog as oa
+
+    return np.stack([oa.nbfm_demod(np.ascontiguousarray(frames[:, k]), demod_rate, audio_rate) for k in range(frames.shape[1])], axis=1)
+
+
+def _knife_edge_channels(frames, tol=1e-5):
+    """channels holding a discriminator sample within `tol` rad of +-pi: there the sign of the wrapped angle depends on the
+    last bit of x[n] conj(x[n-1]) and a flip moves that sample by 2 pi (same reason the FM tests compare modulo 2 pi)."""
+    ang = np.angle(frames[1:] * np.conj(frames[:-1]))
+    return np.nonzero((np.pi - np.abs(ang) < tol).any(axis=0))[0]
+
+
+def test_audio_mode_matches_nbfm_demod_of_every_channel(native):
+    """wc_chan_process_ex(mode AUDIO) == nbfm_demod(extract_channel(process(x), k), 976560, 48828) for all 256 channels."""
+    from conftest import parity_note
+
+    fs, bw = 125_000_000, 488281
+    n = 256 + 128 * 2999 + 17                                  # 3000 frames -> 150 audio samples per channel
+    rng = np.random.default_rng(71)
+    t = np.arange(n)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.02
+    for k in range(0, 256, 5):                                 # FM carriers on every fifth bin centre
+        dev = 5e3 + 270.0 * k
+        x += 0.2 * np.exp(1j * (2 * np.pi * k * 488281.25 / fs * t + (dev / 2e3) * np.sin(2 * np.pi * (2e3 + 10 * k) / fs * t)))
+    x = x.astype(np.complex64)
+    ch, o = _chan(native, fs, bw), ChannelizerOracle(fs, bw)
+    got = ch.process_audio(x)
+    frames = o.process_vectorized(x)
+    exp = _audio_oracle(frames, 976560, 48828)
+    assert got.shape == exp.shape == (150, 256) and got.dtype == np.float32
+    skip = set(_knife_edge_channels(frames).tolist())
+    worst = 0.0
+    for k in range(256):
+        if k in skip:
+            continue
+        worst = max(worst, rel_rms(got[:, k], exp[:, k]))
+    assert len(skip) <= 6 and worst < TOL, (len(skip), worst)
+    parity_note(f"channelizer audio mode (/20): {256 - len(skip)} channels vs nbfm_demod, worst rel-RMS {worst:.1e}; "
+                f"{len(skip)} channels skipped (a discriminator sample within 1e-5 rad of +-pi)")
+
+
+def test_audio_mode_cs16_batched_host_and_device(native):
+    """int16 in, audio out, several chunks per call: numpy (host C-ABI call with copies inside) == CUDA tensors == one
+    chunk at a time; each chunk is an independent nbfm_demod call (RMS and zero-extended resampler per chunk)."""
+    import torch
+    from oracle import analog as oa
+
+    n, B = 256 + 128 * 1203 + 60, 3                            # 1204 frames -> 61 audio samples (ragged last block)
+    q = _cs16(n * B, seed=9, amp=3000)
+    t = np.arange(n * B)
+    q[:, 0] += (8000 * np.cos(2 * np.pi * (20 * 488281.25 / 125e6) * t + 3 * np.sin(2 * np.pi * 2e-5 * t))).astype(np.int16)
+    q[:, 1] += (8000 * np.sin(2 * np.pi * (20 * 488281.25 / 125e6) * t + 3 * np.sin(2 * np.pi * 2e-5 * t))).astype(np.int16)
+    a, b, c = (_chan(native, 125_000_000, 488281) for _ in range(3))
+    host = a.process_audio(q, n_chunks=B)
+    dev = b.process_audio(torch.from_numpy(q).cuda(), n_chunks=B).cpu().numpy()
+    seq = np.concatenate([c.process_audio(q[i * n:(i + 1) * n]) for i in range(B)])
+    assert host.shape == (61 * B, 256) and np.array_equal(host, dev) and np.array_equal(host, seq)
+    o = ChannelizerOracle(125_000_000, 488281)
+    frames = o.process_vectorized(oa.cs16_to_cf32(q[:n]))
+    exp = _audio_oracle(frames[:, 18:23], 976560, 48828)
+    assert rel_rms(host[:61, 20], exp[:, 2]) < TOL

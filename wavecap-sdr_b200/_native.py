@@ -137,6 +137,10 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_chan_carry_from", i32, vp, vp, i64, vp)
     fn("wc_chan_set_run_frames", i32, vp, i32)
     fn("wc_chan_process_host", i32, vp, vp, i64, i32, i32, f32, vp)
+    fn("wc_chan_audio_config", i32, vp, i32, i32)
+    fn("wc_chan_audio_len", i64, vp, i64)
+    fn("wc_chan_process_ex", i32, vp, vp, i32, i64, i32, i64, i32, f32, vp, vp)
+    fn("wc_chan_process_host_ex", i32, vp, vp, i32, i64, i32, i32, f32, vp)
     # analog chain stages
     fn("wc_front_chan_scratch_bytes", i32, i32)
     fn("wc_front_run", i32, vp, i32, i32, i32, i64, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp)

@@ -35,8 +35,25 @@ constexpr int CH_S = 8;          // frames per sub-tile
 constexpr int CH_THREADS = 128;  // one thread per residue class
 constexpr int CH_REGION = 280;   // complex words per frame region (16 x 17 padded exchange + bank offset)
 
+// input sample formats: complex64, or interleaved int16 I,Q scaled by 1/32768 like cli.py:449-453 (an exact float32 value)
+constexpr int IN_CF32 = 0, IN_CS16 = 1;
+constexpr float CS16_SCALE = 1.0f / 32768.0f;
+__device__ __forceinline__ u64 cs16_to_pair(uint32_t w) {
+    return pk2((float)(short)(w & 0xffffu) * CS16_SCALE, (float)(short)(w >> 16) * CS16_SCALE);
+}
+// sample `idx` of an input array (global or shared) of format FMT as a packed (re, im) float pair
+template <int FMT>
+__device__ __forceinline__ u64 in_pair(const void* base, long long idx) {
+    if (FMT == IN_CS16) return cs16_to_pair(reinterpret_cast<const uint32_t*>(base)[idx]);
+    return reinterpret_cast<const u64*>(base)[idx];
+}
+template <int FMT>
+__device__ __forceinline__ const void* in_offset(const void* base, long long samples) {
+    return reinterpret_cast<const char*>(base) + samples * (FMT == IN_CS16 ? 4 : 8);
+}
+
 struct ChanArgs {
-    const float2* x;       // [n_chunks][chunk_stride] complex64
+    const void* x;         // [n_chunks][chunk_stride] complex64 (IN_CF32) or int16 pairs (IN_CS16)
     long long chunk_stride;
     int F;                 // frames per chunk
     int R;                 // frames per CTA run (multiple of 8, >= 16)
@@ -59,10 +76,13 @@ struct __align__(128) ChanSmem {
 };
 
 // block value for the slow prologue path: blk_i[k] of chunk c, i may be negative (history)
-__device__ __forceinline__ float2 blk_fetch(const ChanArgs& a, const float2* xc, int c, int i, int k) {
-    if (i >= 0) return xc[(long long)i * CH_H + k];
-    if (c > 0) return (xc - a.chunk_stride)[(long long)(a.F + i) * CH_H + k];
-    return a.carried[(i + CH_T) * CH_M + k];
+template <int FMT = IN_CF32>
+__device__ __forceinline__ float2 blk_fetch(const ChanArgs& a, const void* xc, int c, int i, int k) {
+    u64 v;
+    if (i >= 0) v = in_pair<FMT>(xc, (long long)i * CH_H + k);
+    else if (c > 0) v = in_pair<FMT>(xc, (long long)(a.F + i) * CH_H + k - a.chunk_stride);
+    else return a.carried[(i + CH_T) * CH_M + k];
+    return make_float2(lo2(v), hi2(v));
 }
 
 #ifdef WC_DEV   // phase-serial predecessor of chan256p_kernel: dev builds only, for A/B timing (WC_CHAN_VAR=0)
@@ -286,11 +306,11 @@ struct FirState {
 };
 
 // FIR rows [I0, I1) of one sub-tile: new row from the staged tile, two packed accumulations, window shift
-template <int I0, int I1>
+template <int I0, int I1, int FMT>
 __device__ __forceinline__ void fir_rows(FirState& f, const u64* __restrict__ st, u64* __restrict__ ub, int r) {
 #pragma unroll
     for (int i = I0; i < I1; ++i) {
-        f.w[9] = st[i * CH_H + r];
+        f.w[9] = in_pair<FMT>(st, i * CH_H + r);
         u64 lo = mul2(f.w[8], bc2(f.hlo[0])), hi = mul2(f.w[9], bc2(f.hhi[0]));
 #pragma unroll
         for (int j = 1; j < CH_T; ++j) {
@@ -307,10 +327,10 @@ __device__ __forceinline__ void fir_rows(FirState& f, const u64* __restrict__ st
 // The same two rows split into load / math / store so that the caller can keep every shared-memory load of a
 // segment ahead of every shared-memory store (ptxas cannot prove that the stage, exchange and twiddle regions do
 // not alias, so it never moves an LDS above an earlier STS).
-template <int I>
+template <int I, int FMT>
 __device__ __forceinline__ void fir2_load(FirState& f, const u64* __restrict__ st, int r) {
-    f.w[9] = st[I * CH_H + r];
-    f.w[10] = st[(I + 1) * CH_H + r];
+    f.w[9] = in_pair<FMT>(st, I * CH_H + r);
+    f.w[10] = in_pair<FMT>(st, (I + 1) * CH_H + r);
 }
 __device__ __forceinline__ void fir2_math(FirState& f, u64 (&o)[4]) {
     o[0] = mul2(f.w[8], bc2(f.hlo[0]));
@@ -338,7 +358,7 @@ __device__ __forceinline__ void fir2_store(const u64 (&o)[4], u64* __restrict__ 
 // FFT-256 of the sub-tile in `uc` (16 threads per frame), optionally with the FIR of the next sub-tile
 // (stage tile `st` -> `un`) interleaved two rows per segment. FULL: all 8 frames valid (no guards).
 // Every segment (between warp barriers) is written loads -> math -> stores.
-template <int MODE, bool FULL, bool FIR>
+template <int MODE, bool FULL, bool FIR, int FMT>
 __device__ __forceinline__ void fft_fir_phase(const ChanArgs& a, u64* __restrict__ uc, const float2* __restrict__ tws,
                                               FirState& f, const u64* __restrict__ st, u64* __restrict__ un,
                                               int tid, int fs, int nv, int f0, long long out_base,
@@ -354,7 +374,7 @@ __device__ __forceinline__ void fft_fir_phase(const ChanArgs& a, u64* __restrict
         for (int i = 0; i < 16; ++i) v[i] = reg[t + 16 * i];
     }
     if (FIR) {
-        fir2_load<0>(f, st, tid);
+        fir2_load<0, FMT>(f, st, tid);
         fir2_math(f, o);
         // `un` was read by the discriminator of the sub-tile before last: wait (late) for every thread's reads
         if (drained_parity >= 0) mbar_wait(drained, (uint32_t)drained_parity);
@@ -362,7 +382,7 @@ __device__ __forceinline__ void fft_fir_phase(const ChanArgs& a, u64* __restrict
     }
     __syncwarp();
     // segment 2: radix-16 pass 1, four-step twiddle in place, exchange store + FIR rows 2,3
-    if (FIR) fir2_load<2>(f, st, tid);
+    if (FIR) fir2_load<2, FMT>(f, st, tid);
     if (on) {
         fft16(v);
 #pragma unroll
@@ -384,13 +404,13 @@ __device__ __forceinline__ void fft_fir_phase(const ChanArgs& a, u64* __restrict
         for (int n2 = 0; n2 < 16; ++n2) v[n2] = reg[n2 * 17 + t];
     }
     if (FIR) {
-        fir2_load<4>(f, st, tid);
+        fir2_load<4, FMT>(f, st, tid);
         fir2_math(f, o);
         fir2_store<4>(o, un, tid);
     }
     __syncwarp();
     // segment 4: radix-16 pass 2, output + FIR rows 6,7
-    if (FIR) fir2_load<6>(f, st, tid);
+    if (FIR) fir2_load<6, FMT>(f, st, tid);
     if (on) fft16(v);
     if (FIR) fir2_math(f, o);
     if (on) {
@@ -413,7 +433,7 @@ __device__ __forceinline__ void fft_fir_phase(const ChanArgs& a, u64* __restrict
     if (FIR) fir2_store<6>(o, un, tid);
 }
 
-template <int MODE>
+template <int MODE, int FMT>
 __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs a) {
     extern __shared__ __align__(128) unsigned char chan_smem_raw[];
     ChanSmemP& sm = *reinterpret_cast<ChanSmemP*>(chan_smem_raw);
@@ -424,7 +444,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
     const int f0 = (blockIdx.x == 0) ? 0 : a.R + (blockIdx.x - 1) * step;
     if (f0 >= a.F) return;
     const int f1 = min(a.F, (blockIdx.x == 0) ? a.R : f0 + step);
-    const float2* __restrict__ xc = a.x + (long long)c * a.chunk_stride;
+    const void* __restrict__ xc = in_offset<FMT>(a.x, (long long)c * a.chunk_stride);
     const long long out_base = (long long)c * a.F;
 
     const int fe = (MODE == 1 && f0 > 0) ? f0 - 1 : f0;
@@ -447,9 +467,9 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
     auto issue = [&](int n) {
         const int fs = fast_start + CH_S * n;
         const int nrows = min(CH_S, a.F - fs);
-        const uint32_t bytes = (uint32_t)nrows * CH_H * sizeof(float2);
+        const uint32_t bytes = (uint32_t)nrows * CH_H * (FMT == IN_CS16 ? 4u : 8u);
         mbar_expect_tx(&sm.full[n & 1], bytes);
-        bulk_g2s(sm.stage[n & 1], xc + (long long)(fs + 1) * CH_H, bytes, &sm.full[n & 1]);
+        bulk_g2s(sm.stage[n & 1], in_offset<FMT>(xc, (long long)(fs + 1) * CH_H), bytes, &sm.full[n & 1]);
     };
     if (tid == 0) {
         if (n_fast > 0) issue(0);
@@ -499,8 +519,8 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
             float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < CH_T; ++j) {
-                const float2 vl = blk_fetch(a, xc, c, b - j, r);
-                const float2 vh = blk_fetch(a, xc, c, b - j, r + CH_H);
+                const float2 vl = blk_fetch<FMT>(a, xc, c, b - j, r);
+                const float2 vh = blk_fetch<FMT>(a, xc, c, b - j, r + CH_H);
                 lo.x = fmaf(f.hlo[j], vl.x, lo.x);
                 lo.y = fmaf(f.hlo[j], vl.y, lo.y);
                 hi.x = fmaf(f.hhi[j], vh.x, hi.x);
@@ -510,7 +530,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
             sm.u[0][b * CH_REGION + r + CH_H] = pk2(hi.x, hi.y);
         }
         __syncthreads();
-        fft_fir_phase<MODE, false, false>(a, sm.u[0], sm.tw, f, nullptr, nullptr, tid, 0, nv, f0, out_base, nullptr, -1);
+        fft_fir_phase<MODE, false, false, FMT>(a, sm.u[0], sm.tw, f, nullptr, nullptr, tid, 0, nv, f0, out_base, nullptr, -1);
         __syncthreads();
         if (MODE == 1) {
             disc(sm.u[0], 0, nv);
@@ -519,14 +539,11 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
     }
     if (n_fast == 0) return;
 
-    {
-        const u64* xr = reinterpret_cast<const u64*>(xc);
 #pragma unroll
-        for (int m = 0; m < 9; ++m) f.w[m] = __ldg(xr + (long long)(fast_start - 8 + m) * CH_H + r);
-    }
+    for (int m = 0; m < 9; ++m) f.w[m] = in_pair<FMT>(xc, (long long)(fast_start - 8 + m) * CH_H + r);
     // pre-loop: FIR of fast sub-tile 0
     mbar_wait(&sm.full[0], 0);
-    fir_rows<0, 8>(f, sm.stage[0], sm.u[0], r);
+    fir_rows<0, 8, FMT>(f, sm.stage[0], sm.u[0], r);
     __syncthreads();
     if (tid == 0 && 2 < n_fast) issue(2);
 
@@ -537,10 +554,10 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
         if (n + 1 < n_fast) {
             // nv == 8 here: only the last sub-tile of a run can be ragged
             mbar_wait(&sm.full[(n + 1) & 1], ((n + 1) >> 1) & 1);
-            fft_fir_phase<MODE, true, true>(a, uc, sm.tw, f, sm.stage[(n + 1) & 1], sm.u[(n + 1) & 1], tid, fs, nv, f0,
+            fft_fir_phase<MODE, true, true, FMT>(a, uc, sm.tw, f, sm.stage[(n + 1) & 1], sm.u[(n + 1) & 1], tid, fs, nv, f0,
                                             out_base, &sm.drained, (MODE == 1 && n > 0) ? ((n - 1) & 1) : -1);
         } else {
-            fft_fir_phase<MODE, false, false>(a, uc, sm.tw, f, nullptr, nullptr, tid, fs, nv, f0, out_base, nullptr, -1);
+            fft_fir_phase<MODE, false, false, FMT>(a, uc, sm.tw, f, nullptr, nullptr, tid, fs, nv, f0, out_base, nullptr, -1);
         }
         __syncthreads();
         if (tid == 0 && n + 3 < n_fast) issue(n + 3);
@@ -554,16 +571,98 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
 }
 
 // ---- carried-history update: blk_{-8..-1} for the next call (double buffered) ----
-__global__ void chan_carry_kernel(const float2* x_last, int F, int M, int T1, const float2* old_c, float2* new_c) {
+template <int FMT>
+__global__ void chan_carry_kernel(const void* x_last, int F, int M, int T1, const float2* old_c, float2* new_c) {
     // new_c[m][k], m = 0..T1-1 <-> block index F + m - T1 of the last chunk (or older history); T1 = T
     const int m = blockIdx.x;
     const int H = M / 2;
     for (int k = threadIdx.x; k < M; k += blockDim.x) {
         const int i = F + m - T1;
         float2 v;
-        if (i >= 0) v = x_last[(long long)i * H + k];
-        else v = old_c[(i + T1) * M + k];
+        if (i >= 0) {
+            const u64 p = in_pair<FMT>(x_last, (long long)i * H + k);
+            v = make_float2(lo2(p), hi2(p));
+        } else {
+            v = old_c[(i + T1) * M + k];
+        }
         new_c[m * M + k] = v;
+    }
+}
+
+// ---- audio mode: nbfm_demod(extract_channel(k), demod_rate, audio_rate) for every channel ----------------------
+// (dsp/fm.py:317-406 with its defaults: quadrature_demod -> rms_normalize -> resample_poly -> soft_clip.) The fused FM
+// kernel leaves the discriminator rows d[chunk][frame][channel] in a workspace; this kernel is scipy's resample_poly
+// for an integer decimation D (up = 1: taps firwin(2*10*D+1, 1/D, kaiser 5.0), y[m] = sum_j h[j] d[D m + 10 D - j],
+// zero extension at the chunk ends) along the frame axis of every channel, plus the per-(chunk, channel) sum of
+// squares rms_normalize needs. The RMS scale commutes with the (linear) resampler, so it is applied afterwards by
+// chan_audio_finish_kernel together with the tanh soft clip. Lanes run along channels (coalesced rows); a warp owns AO
+// consecutive outputs: per tap phase p it holds the 21 taps h[p + D k] and walks the inputs d[D q + p], every input
+// feeding up to AO accumulators — 2*10*AO*... FMAs for ~(AO + 20) D loads.
+constexpr int AO = 8;          // outputs per warp
+constexpr int AU_WARPS = 8;    // warps per CTA: AU_WARPS * AO consecutive outputs of 32 channels
+struct AudioArgs {
+    const float* d;        // [n_chunks][F][M]
+    float* audio;          // [n_chunks][n_out][M] (unscaled)
+    double* sumsq;         // [n_chunks][M]
+    const float* taps;     // [2*10*D + 1]
+    int F, M, D, n_out;
+};
+__global__ void __launch_bounds__(32 * AU_WARPS) chan_audio_kernel(const AudioArgs a) {
+    extern __shared__ float au_taps[];   // [D][K1] phase table: au_taps[p * K1 + k] = h[D k - p] (0 outside the filter)
+    const int D = a.D, half = 10 * D, K1 = 21;
+    for (int i = threadIdx.x; i < D * K1; i += blockDim.x) {
+        const int p = i / K1, k = i % K1, j = D * k - p;
+        au_taps[i] = (j >= 0 && j <= 2 * half) ? a.taps[j] : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = blockIdx.x * 32 + lane;
+    const int c = blockIdx.z;
+    const int m0 = (blockIdx.y * AU_WARPS + warp) * AO;
+    if (m0 >= a.n_out || ch >= a.M) return;
+    const float* dc = a.d + (long long)c * a.F * a.M + ch;
+    float acc[AO];
+#pragma unroll
+    for (int i = 0; i < AO; ++i) acc[i] = 0.f;
+    float ss = 0.f;
+    // Output m0 + i reads inputs n = D (m0 + i) + half - j, j = 0 .. 2 half. Walking the inputs as n = base + p + D q with
+    // base = D m0 - half, phase p = 0 .. D-1 and q = 0 .. AO + 19, input (p, q) meets output i at tap
+    // j = D (i + 20 - q) - p, i.e. entry k = i + 20 - q of phase row p: every index below is a compile-time constant.
+    const long long base = (long long)D * m0 - half;
+    for (int p = 0; p < D; ++p) {
+        float h[21];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) h[k] = au_taps[p * K1 + k];
+#pragma unroll
+        for (int q = 0; q < AO + 20; ++q) {
+            const long long n = base + p + (long long)D * q;
+            const float x = (n >= 0 && n < a.F) ? __ldg(dc + n * a.M) : 0.f;
+            // own range for the sum of squares: inputs [D m0, D (m0 + AO)) = q in [10, 10 + AO)
+            if (q >= 10 && q < 10 + AO) ss = fmaf(x, x, ss);
+#pragma unroll
+            for (int i = 0; i < AO; ++i) {
+                const int k = i + 20 - q;
+                if (k >= 0 && k <= 20) acc[i] = fmaf(x, h[k], acc[i]);
+            }
+        }
+    }
+    float* o = a.audio + ((long long)c * a.n_out + m0) * a.M + ch;
+#pragma unroll
+    for (int i = 0; i < AO; ++i)
+        if (m0 + i < a.n_out) o[(long long)i * a.M] = acc[i];
+    atomicAdd(a.sumsq + (long long)c * a.M + ch, (double)ss);
+}
+
+// rms_normalize (dsp/fm.py:42-62: rms = sqrt(mean(x^2)) in float32, scale = target/rms when rms > min_rms) applied after the
+// resampler, then dsp.fm.soft_clip (:26-39)
+__global__ void chan_audio_finish_kernel(float* __restrict__ audio, const double* __restrict__ sumsq, int F, int M, int n_out,
+                                         long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % M);
+        const long long c = i / ((long long)n_out * M);
+        const float rms = sqrtf((float)(sumsq[c * M + ch] / (double)F));
+        const float scale = (rms > 1e-4f) ? (float)(0.18 / (double)rms) : 1.0f;
+        audio[i] = tanhf(audio[i] * scale * 1.5f) * 1.1047914f * 0.95f;
     }
 }
 
@@ -691,6 +790,11 @@ struct wc_chan {
     float2* d_carried[2] = {nullptr, nullptr};
     int cur = 0;
     int run_frames = 0;        // wc_chan_set_run_frames: frames per CTA run, 0 = sized from the grid target
+    // audio mode (wc_chan_audio_config): nbfm_demod(extract_channel(k), demod_rate, audio_rate), integer decimation D
+    int audio_D = 0, audio_demod_rate = 0;
+    float* d_audio_taps = nullptr;                     // [2*10*D + 1] firwin(.., 1/D, kaiser 5.0)
+    float* d_disc = nullptr;  size_t disc_bytes = 0;   // discriminator rows [n_chunks][F][M]
+    double* d_sumsq = nullptr; size_t sumsq_bytes = 0; // [n_chunks][M]
     // workspaces
     float2* d_ws = nullptr;   size_t ws_bytes = 0;     // generic path u / y
     void* d_in = nullptr;     size_t in_bytes = 0;     // host API staging
@@ -759,6 +863,9 @@ void wc_chan_destroy(wc_chan* h) {
     cudaFree(h->d_taps);
     cudaFree(h->d_carried[0]);
     cudaFree(h->d_carried[1]);
+    if (h->d_audio_taps) cudaFree(h->d_audio_taps);
+    if (h->d_disc) cudaFree(h->d_disc);
+    if (h->d_sumsq) cudaFree(h->d_sumsq);
     if (h->d_ws) cudaFree(h->d_ws);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
@@ -817,11 +924,26 @@ int wc_chan_get_history(wc_chan* h, void* arm_history_host) {
     return 0;
 }
 
-int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_chunks, long long chunk_stride,
-                    int mode, float fm_scale, void* out_dev, void* stream_v) {
+static int chan_audio_stage(wc_chan* h, long long F, int n_chunks, float* audio_out, cudaStream_t stream);
+
+int wc_chan_process_ex(wc_chan* h, const void* iq_dev, int in_fmt, long long n_samples, int n_chunks, long long chunk_stride,
+                       int mode, float fm_scale, void* out_dev, void* stream_v) {
     WC_REQUIRE(h && iq_dev && out_dev, "wc_chan_process: null argument");
-    WC_REQUIRE(mode == WC_CHAN_OUT_COMPLEX || mode == WC_CHAN_OUT_FM, "wc_chan_process: bad mode %d", mode);
+    WC_REQUIRE(mode == WC_CHAN_OUT_COMPLEX || mode == WC_CHAN_OUT_FM || mode == WC_CHAN_OUT_AUDIO, "wc_chan_process: bad mode %d", mode);
+    WC_REQUIRE(in_fmt == WC_CHAN_IN_CF32 || in_fmt == WC_CHAN_IN_CS16, "wc_chan_process: bad input format %d", in_fmt);
     WC_REQUIRE(n_chunks >= 1, "wc_chan_process: n_chunks must be >= 1");
+    void* audio_out = nullptr;
+    if (mode == WC_CHAN_OUT_AUDIO) {
+        // discriminator rows go to the handle's workspace, the decimating audio stage writes the caller's buffer
+        WC_REQUIRE(h->audio_D > 0, "wc_chan_process: audio mode needs wc_chan_audio_config first");
+        const long long Fa = wc_chan_frames_for(h, n_samples);
+        if (Fa == 0) return 0;
+        if (ensure((void**)&h->d_disc, &h->disc_bytes, sizeof(float) * (size_t)Fa * n_chunks * h->M)) return -2;
+        audio_out = out_dev;
+        out_dev = h->d_disc;
+        mode = WC_CHAN_OUT_FM;
+        fm_scale = (float)(h->audio_demod_rate / (2.0 * M_PI * 75000.0));   // dsp/fm.py:94
+    }
     cudaStream_t stream = (cudaStream_t)stream_v;  // taken literally: NULL = the CUDA default stream
     const long long F = wc_chan_frames_for(h, n_samples);
     if (F == 0) return 0;
@@ -830,12 +952,15 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
     WC_REQUIRE(n_chunks == 1 || F >= T1, "wc_chan_process: batched chunks need >= %d frames each", T1);
     WC_REQUIRE(n_chunks == 1 || chunk_stride >= n_samples, "wc_chan_process: chunk_stride < n_samples");
     const float2* x = reinterpret_cast<const float2*>(iq_dev);
+    const int align_samples = (in_fmt == WC_CHAN_IN_CS16) ? 4 : 2;   // bulk async copies need 16-byte aligned row bases
 
     const bool fast = (h->M == CH_M && h->T == CH_T && ((uintptr_t)iq_dev % 16 == 0) &&
-                       (n_chunks == 1 || chunk_stride % 2 == 0));
+                       (n_chunks == 1 || chunk_stride % align_samples == 0));
+    WC_REQUIRE(fast || in_fmt == WC_CHAN_IN_CF32,
+               "wc_chan_process: int16 input is built for the 256-channel / 9-tap grid with 16-byte aligned chunks only");
     if (fast) {
         ChanArgs a;
-        a.x = x;
+        a.x = iq_dev;
         a.chunk_stride = chunk_stride;
         a.F = (int)F;
         a.taps = h->d_taps;
@@ -895,14 +1020,20 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
         {
             // software-pipelined kernel (FIR of sub-tile n+1 inside the FFT of sub-tile n). The dynamic shared-memory
             // opt-in is a per-(function, device) attribute: set once per device this process launches on.
-            static std::atomic<unsigned long long> done0{0}, done1{0};
+            static std::atomic<unsigned long long> done[4] = {};
+#define WC_CHAN_LAUNCH(MODE, FMT, SLOT)                                                                    \
+    do {                                                                                                   \
+        WC_CUDA(smem_optin(chan256p_kernel<MODE, FMT>, (int)sizeof(ChanSmemP), done[SLOT]));               \
+        chan256p_kernel<MODE, FMT><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);                    \
+    } while (0)
             if (mode == WC_CHAN_OUT_COMPLEX) {
-                WC_CUDA(smem_optin(chan256p_kernel<0>, (int)sizeof(ChanSmemP), done0));
-                chan256p_kernel<0><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);
+                if (in_fmt == WC_CHAN_IN_CS16) WC_CHAN_LAUNCH(0, IN_CS16, 0);
+                else WC_CHAN_LAUNCH(0, IN_CF32, 1);
             } else {
-                WC_CUDA(smem_optin(chan256p_kernel<1>, (int)sizeof(ChanSmemP), done1));
-                chan256p_kernel<1><<<grid, CH_THREADS, sizeof(ChanSmemP), stream>>>(a);
+                if (in_fmt == WC_CHAN_IN_CS16) WC_CHAN_LAUNCH(1, IN_CS16, 2);
+                else WC_CHAN_LAUNCH(1, IN_CF32, 3);
             }
+#undef WC_CHAN_LAUNCH
         }
         WC_CUDA(cudaGetLastError());
     } else {
@@ -930,13 +1061,83 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
         WC_CUDA(cudaGetLastError());
     }
     {
-        const float2* x_last = x + (long long)(n_chunks - 1) * chunk_stride;
-        chan_carry_kernel<<<T1, 256, 0, stream>>>(x_last, (int)F, h->M, T1, h->d_carried[h->cur], h->d_carried[h->cur ^ 1]);
+        if (in_fmt == WC_CHAN_IN_CS16) {
+            const void* x_last = reinterpret_cast<const uint32_t*>(iq_dev) + (long long)(n_chunks - 1) * chunk_stride;
+            chan_carry_kernel<IN_CS16><<<T1, 256, 0, stream>>>(x_last, (int)F, h->M, T1, h->d_carried[h->cur], h->d_carried[h->cur ^ 1]);
+        } else {
+            const float2* x_last = x + (long long)(n_chunks - 1) * chunk_stride;
+            chan_carry_kernel<IN_CF32><<<T1, 256, 0, stream>>>(x_last, (int)F, h->M, T1, h->d_carried[h->cur], h->d_carried[h->cur ^ 1]);
+        }
         WC_CUDA(cudaGetLastError());
         h->cur ^= 1;
     }
+    if (audio_out) return chan_audio_stage(h, F, n_chunks, reinterpret_cast<float*>(audio_out), stream);
     return 0;
 }
+
+int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_chunks, long long chunk_stride,
+                    int mode, float fm_scale, void* out_dev, void* stream_v) {
+    return wc_chan_process_ex(h, iq_dev, WC_CHAN_IN_CF32, n_samples, n_chunks, chunk_stride, mode, fm_scale, out_dev, stream_v);
+}
+
+// nbfm_demod(ch_iq, demod_rate, audio_rate) with the reference's defaults (dsp/fm.py:317-406) for every channel:
+// resample_poly reduces audio_rate/demod_rate by their gcd; built for up == 1 (integer decimation D = down).
+int wc_chan_audio_config(wc_chan* h, int demod_rate, int audio_rate) {
+    WC_REQUIRE(h && demod_rate > 0 && audio_rate > 0, "wc_chan_audio_config: bad argument");
+    long long a = demod_rate, b = audio_rate;
+    while (b) {
+        const long long t = a % b;
+        a = b;
+        b = t;
+    }
+    const long long up = audio_rate / a, down = demod_rate / a;
+    WC_REQUIRE(up == 1 && down >= 2 && down <= 64,
+               "wc_chan_audio_config: only integer decimation 2..64 is built (got up/down = %lld/%lld)", up, down);
+    const int D = (int)down, ntaps = 2 * 10 * D + 1;
+    std::vector<double> hd;
+    firwin_kaiser_lowpass(ntaps, 1.0 / D, 5.0, hd);      // scipy resample_poly's design (x up = 1)
+    std::vector<float> hf(ntaps);
+    for (int i = 0; i < ntaps; ++i) hf[i] = (float)hd[i];
+    if (h->d_audio_taps) cudaFree(h->d_audio_taps);
+    h->d_audio_taps = nullptr;
+    WC_CUDA(cudaMalloc(&h->d_audio_taps, sizeof(float) * ntaps));
+    WC_CUDA(cudaMemcpy(h->d_audio_taps, hf.data(), sizeof(float) * ntaps, cudaMemcpyHostToDevice));
+    h->audio_D = D;
+    h->audio_demod_rate = demod_rate;
+    return 0;
+}
+
+// audio samples per channel per chunk: ceil(frames / D) (scipy resample_poly output length for up = 1)
+long long wc_chan_audio_len(const wc_chan* h, long long n_samples) {
+    if (!h || h->audio_D <= 0) return 0;
+    const long long F = wc_chan_frames_for(h, n_samples);
+    return (F + h->audio_D - 1) / h->audio_D;
+}
+
+static int chan_audio_stage(wc_chan* h, long long F, int n_chunks, float* audio_out, cudaStream_t stream) {
+    const int D = h->audio_D, M = h->M;
+    const long long n_out = (F + D - 1) / D;
+    if (ensure((void**)&h->d_sumsq, &h->sumsq_bytes, sizeof(double) * (size_t)n_chunks * M)) return -2;
+    WC_CUDA(cudaMemsetAsync(h->d_sumsq, 0, sizeof(double) * (size_t)n_chunks * M, stream));
+    AudioArgs a;
+    a.d = h->d_disc;
+    a.audio = audio_out;
+    a.sumsq = h->d_sumsq;
+    a.taps = h->d_audio_taps;
+    a.F = (int)F;
+    a.M = M;
+    a.D = D;
+    a.n_out = (int)n_out;
+    dim3 grid((M + 31) / 32, (unsigned)((n_out + AU_WARPS * AO - 1) / (AU_WARPS * AO)), (unsigned)n_chunks);
+    chan_audio_kernel<<<grid, 32 * AU_WARPS, sizeof(float) * D * 21, stream>>>(a);
+    const long long total = (long long)n_chunks * n_out * M;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+    chan_audio_finish_kernel<<<(unsigned)blocks, 256, 0, stream>>>(audio_out, h->d_sumsq, (int)F, M, (int)n_out, total);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 
 // Advance the carried history as if process() had just been called on these n_samples, without computing
 // any output: used by time-sharded runs where another rank emitted the tail of the call.
@@ -951,29 +1152,35 @@ int wc_chan_carry_from(wc_chan* h, const void* iq_dev, long long n_samples, void
     const long long F = wc_chan_frames_for(h, n_samples);
     if (F == 0) return 0;
     WC_REQUIRE(F < (1LL << 30), "wc_chan_carry_from: chunk too long");
-    chan_carry_kernel<<<h->T, 256, 0, (cudaStream_t)stream_v>>>(reinterpret_cast<const float2*>(iq_dev), (int)F, h->M, h->T,
-                                                               h->d_carried[h->cur], h->d_carried[h->cur ^ 1]);
+    chan_carry_kernel<IN_CF32><<<h->T, 256, 0, (cudaStream_t)stream_v>>>(iq_dev, (int)F, h->M, h->T,
+                                                                        h->d_carried[h->cur], h->d_carried[h->cur ^ 1]);
     WC_CUDA(cudaGetLastError());
     h->cur ^= 1;
     return 0;
 }
 
-int wc_chan_process_host(wc_chan* h, const void* iq_host, long long n_samples, int n_chunks, int mode,
-                         float fm_scale, void* out_host) {
+int wc_chan_process_host_ex(wc_chan* h, const void* iq_host, int in_fmt, long long n_samples, int n_chunks, int mode,
+                            float fm_scale, void* out_host) {
     WC_REQUIRE(h && iq_host && out_host, "wc_chan_process_host: null argument");
     WC_REQUIRE(n_chunks >= 1, "wc_chan_process_host: n_chunks must be >= 1");
+    WC_REQUIRE(in_fmt == WC_CHAN_IN_CF32 || in_fmt == WC_CHAN_IN_CS16, "wc_chan_process_host: bad input format %d", in_fmt);
     const long long F = wc_chan_frames_for(h, n_samples);
     if (F == 0) return 0;
     WC_REQUIRE(n_chunks == 1 || F >= h->T, "wc_chan_process_host: batched chunks need >= %d frames each", h->T);
     // Software pipeline over sub-batches of g chunks: H2D (copy stream) | kernels (compute stream) |
     // D2H (copy stream), double-buffered on the device. Chunk bases stay 16-byte aligned.
-    const long long stride = (n_samples + 1) & ~1LL;
+    const size_t isz = (in_fmt == WC_CHAN_IN_CS16) ? 4 : 8;
+    const long long al = (in_fmt == WC_CHAN_IN_CS16) ? 3 : 1;
+    const long long stride = (n_samples + al) & ~al;
     int g = (int)((4LL << 20) / n_samples);
     if (g < 1) g = 1;
     if (g > n_chunks) g = n_chunks;
-    const size_t esz = (mode == WC_CHAN_OUT_FM) ? sizeof(float) : sizeof(float2);
-    const size_t in_sub = sizeof(float2) * (size_t)stride * g;
-    const size_t out_sub = esz * (size_t)F * g * h->M;
+    // rows of the result per chunk and bytes per row element: frames x complex64 / float32, or audio samples x float32
+    const long long rows = (mode == WC_CHAN_OUT_AUDIO) ? wc_chan_audio_len(h, n_samples) : F;
+    WC_REQUIRE(mode != WC_CHAN_OUT_AUDIO || h->audio_D > 0, "wc_chan_process_host: audio mode needs wc_chan_audio_config first");
+    const size_t esz = (mode == WC_CHAN_OUT_COMPLEX) ? sizeof(float2) : sizeof(float);
+    const size_t in_sub = isz * (size_t)stride * g;
+    const size_t out_sub = esz * (size_t)rows * g * h->M;
     if (ensure(&h->d_in, &h->in_bytes, 2 * in_sub)) return -2;
     if (ensure(&h->d_out, &h->out_bytes, 2 * out_sub)) return -2;
     if (!h->s_h2d) {
@@ -994,27 +1201,32 @@ int wc_chan_process_host(wc_chan* h, const void* iq_host, long long n_samples, i
         char* din = reinterpret_cast<char*>(h->d_in) + (size_t)b * in_sub;
         char* dout = reinterpret_cast<char*>(h->d_out) + (size_t)b * out_sub;
         if (it >= 2) WC_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));  // d_in[b] free again
-        const char* hs = src + sizeof(float2) * (size_t)n_samples * c0;
+        const char* hs = src + isz * (size_t)n_samples * c0;
         if (stride == n_samples) {
-            WC_CUDA(cudaMemcpyAsync(din, hs, sizeof(float2) * (size_t)n_samples * gc, cudaMemcpyHostToDevice, h->s_h2d));
+            WC_CUDA(cudaMemcpyAsync(din, hs, isz * (size_t)n_samples * gc, cudaMemcpyHostToDevice, h->s_h2d));
         } else {
-            WC_CUDA(cudaMemcpy2DAsync(din, sizeof(float2) * stride, hs, sizeof(float2) * n_samples,
-                                      sizeof(float2) * n_samples, gc, cudaMemcpyHostToDevice, h->s_h2d));
+            WC_CUDA(cudaMemcpy2DAsync(din, isz * stride, hs, isz * n_samples, isz * n_samples, gc, cudaMemcpyHostToDevice,
+                                      h->s_h2d));
         }
         WC_CUDA(cudaEventRecord(h->ev_in[b], h->s_h2d));
         WC_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
         if (it >= 2) WC_CUDA(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));  // d_out[b] drained
-        int rc = wc_chan_process(h, din, n_samples, gc, stride, mode, fm_scale, dout, h->stream);
+        int rc = wc_chan_process_ex(h, din, in_fmt, n_samples, gc, stride, mode, fm_scale, dout, h->stream);
         if (rc) return rc;
         WC_CUDA(cudaEventRecord(h->ev_comp[b], h->stream));
         WC_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
-        const size_t obytes = esz * (size_t)F * gc * h->M;
-        WC_CUDA(cudaMemcpyAsync(dst + esz * (size_t)F * c0 * h->M, dout, obytes, cudaMemcpyDeviceToHost, h->s_d2h));
+        const size_t obytes = esz * (size_t)rows * gc * h->M;
+        WC_CUDA(cudaMemcpyAsync(dst + esz * (size_t)rows * c0 * h->M, dout, obytes, cudaMemcpyDeviceToHost, h->s_d2h));
         WC_CUDA(cudaEventRecord(h->ev_out[b], h->s_d2h));
     }
     WC_CUDA(cudaStreamSynchronize(h->s_d2h));
     WC_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+int wc_chan_process_host(wc_chan* h, const void* iq_host, long long n_samples, int n_chunks, int mode,
+                         float fm_scale, void* out_host) {
+    return wc_chan_process_host_ex(h, iq_host, WC_CHAN_IN_CF32, n_samples, n_chunks, mode, fm_scale, out_host);
 }
 
 }  // extern "C"

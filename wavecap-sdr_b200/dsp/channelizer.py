@@ -22,6 +22,9 @@ PERFECT_RECONSTRUCTION_GAIN = 0.5
 
 OUT_COMPLEX = 0
 OUT_FM = 1
+OUT_AUDIO = 2
+IN_CF32 = 0
+IN_CS16 = 1
 
 
 def fm_scale(sample_rate: int) -> float:
@@ -73,29 +76,56 @@ class PolyphaseChannelizer:
 
     # -- core ------------------------------------------------------------------------------------
     def _run(self, samples, mode: int, n_chunks: int = 1, scale: float = 0.0):
+        """numpy in -> numpy out, CUDA tensor in -> CUDA tensor out. complex input is complex64 IQ; int16 input
+        ([..., 2] or flat interleaved I,Q) is the raw capture format, scaled by 1/32768 on the device (cli.py:449-453)."""
         m = self.channel_count
+        out_dtype = np.complex64 if mode == OUT_COMPLEX else np.float32
         if N.is_torch_cuda(samples):
             import torch
 
             x = samples
-            if x.dtype != torch.complex64:
+            cs16 = x.dtype == torch.int16
+            if not cs16 and x.dtype != torch.complex64:
                 x = x.to(torch.complex64)
             x = x.contiguous()
-            n = x.numel() // n_chunks
-            frames = self.frames_for(n)
-            out = torch.empty((frames * n_chunks, m), device=x.device,
-                              dtype=torch.float32 if mode == OUT_FM else torch.complex64)
-            if frames:
-                N.check(N.lib().wc_chan_process(self._h, C.c_void_p(x.data_ptr()), n, n_chunks, n, mode,
-                                                scale, C.c_void_p(out.data_ptr()), N.torch_stream_ptr()))
+            n = (x.numel() // 2 if cs16 else x.numel()) // n_chunks
+            rows = self._rows_for(n, mode)
+            out = torch.empty((rows * n_chunks, m), device=x.device,
+                              dtype=torch.complex64 if mode == OUT_COMPLEX else torch.float32)
+            if rows:
+                N.check(N.lib().wc_chan_process_ex(self._h, C.c_void_p(x.data_ptr()), IN_CS16 if cs16 else IN_CF32, n, n_chunks, n,
+                                                   mode, scale, C.c_void_p(out.data_ptr()), N.torch_stream_ptr()))
             return out
-        x = np.ascontiguousarray(samples, dtype=np.complex64)
-        n = x.size // n_chunks
-        frames = self.frames_for(n)
-        out = np.empty((frames * n_chunks, m), dtype=np.float32 if mode == OUT_FM else np.complex64)
-        if frames:
-            N.check(N.lib().wc_chan_process_host(self._h, N.np_ptr(x), n, n_chunks, mode, scale, N.np_ptr(out)))
+        a = np.asarray(samples)
+        cs16 = a.dtype == np.int16
+        x = np.ascontiguousarray(a, dtype=np.int16 if cs16 else np.complex64)
+        n = (x.size // 2 if cs16 else x.size) // n_chunks
+        rows = self._rows_for(n, mode)
+        out = np.empty((rows * n_chunks, m), dtype=out_dtype)
+        if rows:
+            N.check(N.lib().wc_chan_process_host_ex(self._h, N.np_ptr(x), IN_CS16 if cs16 else IN_CF32, n, n_chunks, mode, scale,
+                                                    N.np_ptr(out)))
         return out
+
+    def _rows_for(self, n_samples: int, mode: int) -> int:
+        if mode == OUT_AUDIO:
+            return int(N.lib().wc_chan_audio_len(self._h, int(n_samples)))
+        return self.frames_for(n_samples)
+
+    def process_audio(self, samples, demod_sample_rate: int | None = None, audio_rate: int | None = None, n_chunks: int = 1):
+        """`nbfm_demod(extract_channel(process(samples), k), demod_sample_rate, audio_rate)` (dsp/fm.py:317-406, defaults) for
+        every channel k in one pass: float32 [n_audio, channel_count] per chunk, n_audio = ceil(frames / D). Built for
+        integer decimation D = demod_sample_rate / audio_rate; defaults: the channel rate rounded down to a multiple of
+        20 and a twentieth of it (976560 -> 48828 for the 125 MS/s / 256-channel grid)."""
+        if demod_sample_rate is None:
+            demod_sample_rate = (int(self.channel_sample_rate) // 20) * 20
+        if audio_rate is None:
+            audio_rate = demod_sample_rate // 20
+        key = (int(demod_sample_rate), int(audio_rate))
+        if getattr(self, "_audio_key", None) != key:
+            N.check(N.lib().wc_chan_audio_config(self._h, key[0], key[1]))
+            self._audio_key = key
+        return self._run(samples, OUT_AUDIO, n_chunks=n_chunks)
 
     def process(self, samples) -> list:
         """One array of `channel_count` complex64 values per output frame (channelizer.py:91-137)."""
