@@ -697,6 +697,64 @@ def main():
     e2e_value = world * eb * CHUNK / (e_ms * 1e-3) / 1e6
     g_sub = max(1, min(eb, (4 << 20) // CHUNK))  # sub-batches of the pipelined host call (channelizer.cu)
 
+    # the same end-to-end call in the formats that shrink the PCIe traffic: int16 capture input (4 B/sample up) and the
+    # fused nbfm audio /20 output (0.4 B/sample down) — SURVEY §8d "C5 + audio"; the cf32 -> FM leg above stays the headline
+    from wavecap_sdr_b200.dsp.channelizer import IN_CF32, IN_CS16, OUT_AUDIO
+
+    e2e_modes = {}
+    try:
+        hq = N.pinned_empty((eb * CHUNK, 2), "int16")
+        hq[:CHUNK] = np.clip(np.stack([hx[:CHUNK].real, hx[:CHUNK].imag], axis=1) * 8192.0, -32767, 32767).astype(np.int16)
+        for i in range(1, eb):
+            hq[i * CHUNK:(i + 1) * CHUNK] = hq[:CHUNK]
+        N.check(lib.wc_chan_audio_config(ch2._h, 976560, 48828))
+        n_audio = int(lib.wc_chan_audio_len(ch2._h, CHUNK))
+        haud = N.pinned_empty((eb * n_audio, 256), "float32")
+        for name, fmt, src, mode, dst in (("cs16_to_fm", IN_CS16, hq, OUT_FM, hout), ("cf32_to_audio", IN_CF32, hx, OUT_AUDIO, haud),
+                                          ("cs16_to_audio", IN_CS16, hq, OUT_AUDIO, haud)):
+            def m_step():
+                N.check(lib.wc_chan_process_host_ex(ch2._h, N.np_ptr(src), fmt, CHUNK, eb, mode, scale, N.np_ptr(dst)))
+                return float(dst[-1, 17])
+            m_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                m_step()
+            torch.cuda.synchronize()
+            m_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+            tm = torch.tensor([m_ms], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            m_ms = float(tm.item())
+            e2e_modes[name] = {"value": round(world * eb * CHUNK / (m_ms * 1e-3) / 1e6, 1), "unit": "MS/s", "ms_per_step": round(m_ms, 3),
+                               "h2d_bytes_per_step": int(src.nbytes), "d2h_bytes_per_step": int(dst.nbytes)}
+        # device-resident rate of the audio mode (its own roofline: 8 B in + 2 x 4/20 B out per input sample)
+        nba = min(nb, 32)
+        daud = torch.empty((nba * n_audio, 256), dtype=torch.float32, device="cuda")
+
+        def a_step():
+            N.check(lib.wc_chan_process_ex(ch2._h, C.c_void_p(x.data_ptr()), IN_CF32, CHUNK, nba, CHUNK, OUT_AUDIO, scale,
+                                           C.c_void_p(daud.data_ptr()), stream))
+        for _ in range(3):
+            a_step()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(5):
+            a_step()
+        a1.record()
+        torch.cuda.synchronize()
+        a_ms = a0.elapsed_time(a1) / 5
+        audio_msps = nba * CHUNK / (a_ms * 1e-3) / 1e6
+        e2e_modes["audio_device_resident"] = {"msps_per_gpu": round(audio_msps, 1), "alg_bytes_per_sample": 8.4,
+                                              "achieved_gbs": round(8.4 * audio_msps / 1e3, 1), "ms_per_step": round(a_ms, 3),
+                                              "chunks_per_step": nba,
+                                              "note": "FM kernel -> discriminator rows in HBM -> /20 polyphase decimator + RMS/clip: "
+                                                      "moves 24.4 B/sample, compute-bound by construction (SURVEY §8d)"}
+        del daud
+    except Exception as e:
+        e2e_modes["error"] = f"{type(e).__name__}: {e}"
+
     # the ceiling the e2e leg runs under: the same bytes moved by plain pinned cudaMemcpyAsync, H2D and D2H concurrently on
     # two streams, all ranks at once, no kernel — what this box's host<->device path gives the whole job
     ceiling = None
@@ -824,7 +882,7 @@ def main():
                     "h2d_bytes_per_step": int(eb * CHUNK * 8), "d2h_bytes_per_step": int(eb * frames * 256 * 4),
                     "copy_ceiling": ceiling,
                     "frac_of_copy_ceiling": round(e2e_value / ceiling["value"], 3) if ceiling and ceiling.get("value") else None,
-                    "python_process_api": api},
+                    "python_process_api": api, "modes": e2e_modes},
             "sustained": dict(sustained, roofline_frac=round(ALG_BYTES_PER_SAMPLE * sustained["value"] / world / 1e3 / peak, 4)) if sustained else None,
             "configs": cfg_recs,
             "one_capture": one_capture,

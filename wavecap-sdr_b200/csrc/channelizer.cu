@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArg
 
 // ---------------------------------------------------------------------------------------------
 // Software-pipelined variant ("P"): the FIR of sub-tile n+1 is issued inside the FFT of sub-tile n.
+// MODE 0: complex frames; 1: fused FM discriminator (degree-9 atan2); 2: the same with the degree-13 atan2 (audio mode).
 //
 // Why: in chan256_kernel the FIR phase is a burst of FFMA2 (FMA-pipe bound, issue slots idle) and the FFT
 // phase is bound by shared-memory latency (short-scoreboard stalls, FMA pipe idle) — ncu attributes 30 % /
@@ -440,14 +441,14 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
     const int tid = threadIdx.x;
     const int r = tid;
     const int c = blockIdx.y;
-    const int step = (MODE == 1) ? a.R - 1 : a.R;
+    const int step = (MODE >= 1) ? a.R - 1 : a.R;
     const int f0 = (blockIdx.x == 0) ? 0 : a.R + (blockIdx.x - 1) * step;
     if (f0 >= a.F) return;
     const int f1 = min(a.F, (blockIdx.x == 0) ? a.R : f0 + step);
     const void* __restrict__ xc = in_offset<FMT>(a.x, (long long)c * a.chunk_stride);
     const long long out_base = (long long)c * a.F;
 
-    const int fe = (MODE == 1 && f0 > 0) ? f0 - 1 : f0;
+    const int fe = (MODE >= 1 && f0 > 0) ? f0 - 1 : f0;
     const int fast_start = (f0 == 0) ? 8 : fe;
     const int n_fast = (fast_start < f1) ? (f1 - fast_start + CH_S - 1) / CH_S : 0;
 
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
             const u64 yim = *reinterpret_cast<const u64*>(w + CH_YIM);
             const u64 px = fma2(yre, pre, mul2(yim, pim));
             const u64 py = sub2(mul2(yim, pre), mul2(yre, pim));
-            const u64 d = scaled_atan2f_x2(py, px, at);
+            const u64 d = (MODE == 2) ? scaled_atan2f_hi_x2(py, px, at) : scaled_atan2f_x2(py, px, at);
             if (!guard || fs + i >= f0) *reinterpret_cast<u64*>(o + (long long)i * CH_M) = d;
             pre = yre;
             pim = yim;
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
         __syncthreads();
         fft_fir_phase<MODE, false, false, FMT>(a, sm.u[0], sm.tw, f, nullptr, nullptr, tid, 0, nv, f0, out_base, nullptr, -1);
         __syncthreads();
-        if (MODE == 1) {
+        if (MODE >= 1) {
             disc(sm.u[0], 0, nv);
             __syncthreads();
         }
@@ -555,13 +556,13 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
             // nv == 8 here: only the last sub-tile of a run can be ragged
             mbar_wait(&sm.full[(n + 1) & 1], ((n + 1) >> 1) & 1);
             fft_fir_phase<MODE, true, true, FMT>(a, uc, sm.tw, f, sm.stage[(n + 1) & 1], sm.u[(n + 1) & 1], tid, fs, nv, f0,
-                                            out_base, &sm.drained, (MODE == 1 && n > 0) ? ((n - 1) & 1) : -1);
+                                            out_base, &sm.drained, (MODE >= 1 && n > 0) ? ((n - 1) & 1) : -1);
         } else {
             fft_fir_phase<MODE, false, false, FMT>(a, uc, sm.tw, f, nullptr, nullptr, tid, fs, nv, f0, out_base, nullptr, -1);
         }
         __syncthreads();
         if (tid == 0 && n + 3 < n_fast) issue(n + 3);
-        if (MODE == 1) {
+        if (MODE >= 1) {
             disc(uc, fs, nv);
             // split barrier instead of __syncthreads: u[n&1] is next written by the FIR stores of iteration n+1,
             // which wait on this phase (parity n&1) only after their own loads and math
@@ -999,6 +1000,9 @@ int wc_chan_process_ex(wc_chan* h, const void* iq_dev, int in_fmt, long long n_s
             a.at.k4 = (float)(c[4] * fm_scale);
             a.at.hp = (float)(1.5707963267948966 * fm_scale);
             a.at.pi = (float)(3.141592653589793 * fm_scale);
+            const double ch[7] = {0.9999994039535522, -0.3332701623439789, 0.198873370885849, -0.13512229919433594,
+                                  0.08435501158237457, -0.037443727254867554, 0.008007131516933441};
+            for (int i = 0; i < 7; ++i) a.at.h[i] = (float)(ch[i] * fm_scale);
         }
 #ifdef WC_DEV
         if (env_int("WC_CHAN_VAR", 1) == 0) {   // phase-serial kernel
@@ -1020,7 +1024,7 @@ int wc_chan_process_ex(wc_chan* h, const void* iq_dev, int in_fmt, long long n_s
         {
             // software-pipelined kernel (FIR of sub-tile n+1 inside the FFT of sub-tile n). The dynamic shared-memory
             // opt-in is a per-(function, device) attribute: set once per device this process launches on.
-            static std::atomic<unsigned long long> done[4] = {};
+            static std::atomic<unsigned long long> done[6] = {};
 #define WC_CHAN_LAUNCH(MODE, FMT, SLOT)                                                                    \
     do {                                                                                                   \
         WC_CUDA(smem_optin(chan256p_kernel<MODE, FMT>, (int)sizeof(ChanSmemP), done[SLOT]));               \
@@ -1029,6 +1033,9 @@ int wc_chan_process_ex(wc_chan* h, const void* iq_dev, int in_fmt, long long n_s
             if (mode == WC_CHAN_OUT_COMPLEX) {
                 if (in_fmt == WC_CHAN_IN_CS16) WC_CHAN_LAUNCH(0, IN_CS16, 0);
                 else WC_CHAN_LAUNCH(0, IN_CF32, 1);
+            } else if (audio_out) {
+                if (in_fmt == WC_CHAN_IN_CS16) WC_CHAN_LAUNCH(2, IN_CS16, 4);
+                else WC_CHAN_LAUNCH(2, IN_CF32, 5);
             } else {
                 if (in_fmt == WC_CHAN_IN_CS16) WC_CHAN_LAUNCH(1, IN_CS16, 2);
                 else WC_CHAN_LAUNCH(1, IN_CF32, 3);
