@@ -148,6 +148,33 @@ int wc_finalize(float* audio_dev, int n_out, int n_chunks, int n_seq, const doub
                 const float* squelch_db_dev, const int* has_squelch_dev, float* rssi_db_dev,
                 unsigned char* squelched_dev, void* stream);
 
+/* ---- analog plan: the whole analog chain of a capture as one call ------------------------------------
+ * Replaces one _process_channel_dsp_stateless call per (chunk, channel) from the capture's worker pool
+ * (capture.py:298-439, caller :2489-2597) by ONE call per batch of chunks: front end (freq_shift, RSSI power, demod)
+ * -> [IIR stages] -> [apply_agc] -> rms_normalize -> resample_poly with fused scale / soft clip -> dB metrics, validity
+ * gate (validation.py:41-52), squelch (capture.py:2918-2921). The plan owns handles, scratch and statistics; a call
+ * allocates nothing and never synchronises; repeated (iq_dev, audio_dev, metrics_dev, n_chunks) keys replay a captured
+ * CUDA graph. Filter design stays with the caller (scipy, as in the reference): stages arrive as (b, a) pairs.
+ * Build: create -> add_run (adjacent channels sharing one chain; kind 0 metrics only, 1 FM, 2 AM/SSB) -> add_iir* ->
+ * [set_agc] -> finish. */
+typedef struct wc_analog_plan wc_analog_plan;
+int wc_analog_plan_create(int sample_rate, int chunk_len, int in_fmt /* 0 cf32, 1 cs16 */, int n_channels, const int* modes,
+                          const double* offsets_hz, const double* bfo_hz, const float* squelch_db /* NaN = none */,
+                          wc_analog_plan** out);
+int wc_analog_plan_add_run(wc_analog_plan* p, int first, int count, int kind, int up, int down, const double* taps, int n_taps);
+int wc_analog_plan_add_iir(wc_analog_plan* p, int run, const double* b, int nb, const double* a, int na);
+int wc_analog_plan_set_agc(wc_analog_plan* p, int run, const double* attack_b, const double* attack_a, const double* release_b,
+                           const double* release_a, float target_linear, float max_gain_linear);
+int wc_analog_plan_finish(wc_analog_plan* p);
+void wc_analog_plan_destroy(wc_analog_plan* p);
+long long wc_analog_plan_audio_floats(const wc_analog_plan* p);            /* audio floats per chunk, all channels   */
+int wc_analog_plan_audio_len(const wc_analog_plan* p, int channel);        /* audio samples per chunk of a channel   */
+long long wc_analog_plan_audio_offset(const wc_analog_plan* p, int channel);
+int wc_analog_plan_use_graph(wc_analog_plan* p, int on);                   /* default on                             */
+/* audio_dev: channel c, chunk b at audio_dev + n_chunks * audio_offset(c) + b * audio_len(c); metrics_dev: float32
+ * [3][n_channels][n_chunks] = rssi_db | signal_power_db | valid (1 audio valid, 0.5 RSSI only, 0 chunk dropped). */
+int wc_analog_run(wc_analog_plan* p, const void* iq_dev, int n_chunks, float* audio_dev, float* metrics_dev, void* stream);
+
 /* ---- spectrum / waterfall: wavecapsdr/dsp/fft/base.py:31-77 (FFTBackend), scipy_backend.py:38-79 ----
  * power_db = float32(20*log10(|fftshift(fft(iq[:N] * float32(hanning(N))))| + 1e-10)); consecutive groups of
  * `avg` frames are averaged in dB (the frontend's spectrum averaging, SpectrumAnalyzer.react.tsx:309-327).

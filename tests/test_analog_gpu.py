@@ -279,3 +279,50 @@ def test_front_end_sum_of_squares_matches_the_separate_pass(native):
     assert torch.allclose(ss, ref, rtol=1e-6, atol=0.0)
     out2, _, power2, _ = S.front(x, S.FMT_CF32, n, n_chunks, modes, [12_000.0, 0.0, -40_000.0, 250_000.0], [0.0, 0.0, 1500.0, 0.0], fs)
     assert torch.equal(out, out2) and torch.allclose(power, power2, rtol=1e-12)
+
+
+def test_one_call_plan_equals_the_stage_path_and_replays_its_graph(native):
+    """wc_analog_run (one C call per batch, captured CUDA graph on repeats) against the stage-by-stage path it replaces:
+    mixed chains (FM with and without IIR stages, AM with AGC, SSB without, a digital and an unknown mode), squelch, a
+    chunk with non-finite IQ, int16 and complex64 input, numpy and CUDA-tensor input, four calls in a row."""
+    import torch
+
+    from wavecap_sdr_b200.capture import process_channels_batch
+
+    fs, n, B = 48000, 4801, 3
+    rng = np.random.default_rng(51)
+    t = np.arange(n * B) / fs
+    x = (0.3 * np.exp(1j * (2 * np.pi * 3000 * t + 2.5 * np.sin(2 * np.pi * 600 * t))) * (1 + 0.5 * np.sin(2 * np.pi * 300 * t))
+         + 0.01 * (rng.standard_normal(n * B) + 1j * rng.standard_normal(n * B))).astype(np.complex64)
+    x[n + 5] = np.inf                                            # chunk 1 is dropped
+    specs = [dict(mode="nbfm", offset_hz=3000.0, enable_deemphasis=False, audio_rate=16000, squelch_db=-3.0),
+             dict(mode="nbfm", offset_hz=3000.0, enable_deemphasis=False, audio_rate=16000, squelch_db=-60.0),
+             dict(mode="wbfm", offset_hz=3000.0, audio_rate=48000),
+             dict(mode="am", offset_hz=3000.0, enable_agc=True, audio_rate=16000),
+             dict(mode="ssb", offset_hz=3000.0, enable_agc=False, audio_rate=8000),
+             dict(mode="p25", offset_hz=0.0), dict(mode="bogus", offset_hz=10.0)]
+    cfgs = [_cfg(native, **s) for s in specs]
+
+    def same(a, b):
+        for ra, rb in zip(a, b):
+            for (aa, ma), (ab, mb) in zip(ra, rb):
+                assert (aa is None) == (ab is None) and set(ma) == set(mb)
+                for k in ma:
+                    assert abs(ma[k] - mb[k]) < 1e-3, k
+                if aa is not None:
+                    assert aa.shape == ab.shape and rel_rms(aa, ab) < 1e-6
+
+    ref = process_channels_batch(x, fs, cfgs, n_chunks=B, apply_squelch=True, use_plan=False)
+    assert ref[1][0] == (None, {}) and ref[0][5][0] is None and "signal_power_db" in ref[0][5][1] and ref[0][6] == (None, {"rssi_db": ref[0][6][1]["rssi_db"]})
+    assert not ref[0][0][0].any() and ref[0][1][0].any()         # squelch closed / open
+    xd = torch.from_numpy(x).cuda()
+    for rep in range(4):                                         # eager, capture, replay, replay
+        same(process_channels_batch(x, fs, cfgs, n_chunks=B, apply_squelch=True), ref)
+        got = process_channels_batch(xd, fs, cfgs, n_chunks=B, apply_squelch=True, return_device=True)
+        same([[(a.cpu().numpy() if a is not None else None, m) for a, m in row] for row in got], ref)
+    # int16 input
+    q = np.stack([np.clip(x.real, -1, 1), np.clip(x.imag, -1, 1)], axis=1)
+    q = (np.nan_to_num(q, posinf=0.0) * 20000).astype(np.int16)
+    r0 = process_channels_batch(q, fs, cfgs[:5], n_chunks=B, in_fmt="cs16", use_plan=False)
+    for rep in range(3):
+        same(process_channels_batch(q, fs, cfgs[:5], n_chunks=B, in_fmt="cs16"), r0)

@@ -51,6 +51,14 @@ def check(rc: int) -> None:
         raise NativeError(f"wcsdr_b200 error {rc}: {msg}")
 
 
+def check_nonneg(rc: int) -> int:
+    """for entry points that return an index (>= 0) or a negative error code"""
+    if rc < 0:
+        msg = lib().wc_last_error().decode("utf-8", "replace")
+        raise NativeError(f"wcsdr_b200 error {rc}: {msg}")
+    return rc
+
+
 def init(device: int | None = None) -> None:
     """Select the CUDA device (default: LOCAL_RANK or 0) and verify it is sm_100."""
     global _inited_device
@@ -157,6 +165,18 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_resampler_out_len", i64, vp, i64)
     fn("wc_resampler_run", i32, vp, vp, i32, i64, i32, vp, i32, vp, f32, f32, vp, vp, f32, vp)
     fn("wc_finalize", i32, vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp)
+    # analog plan
+    fn("wc_analog_plan_create", i32, i32, i32, i32, i32, vp, vp, vp, vp, P(vp))
+    fn("wc_analog_plan_add_run", i32, vp, i32, i32, i32, i32, i32, vp, i32)
+    fn("wc_analog_plan_add_iir", i32, vp, i32, vp, i32, vp, i32)
+    fn("wc_analog_plan_set_agc", i32, vp, i32, vp, vp, vp, vp, f32, f32)
+    fn("wc_analog_plan_finish", i32, vp)
+    fn("wc_analog_plan_destroy", None, vp)
+    fn("wc_analog_plan_audio_floats", i64, vp)
+    fn("wc_analog_plan_audio_len", i32, vp, i32)
+    fn("wc_analog_plan_audio_offset", i64, vp, i32)
+    fn("wc_analog_plan_use_graph", i32, vp, i32)
+    fn("wc_analog_run", i32, vp, vp, i32, vp, vp, vp)
     # spectrum
     fn("wc_spectrum_create", i32, i32, P(vp))
     fn("wc_spectrum_destroy", None, vp)

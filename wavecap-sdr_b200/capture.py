@@ -165,9 +165,46 @@ def _chain_signature(cfg: ChannelConfig, sample_rate: int):
     return ("unknown",)
 
 
+def _plan_eligible(sig) -> bool:
+    """chains the one-call plan (csrc/analog.cu wc_analog_run) covers: FM without blanker / spectral NR, AM / SSB, and the
+    metrics-only modes. RAW (IQ pass-through) and the optional clean-up stages take the stage-by-stage path."""
+    if sig[0] == "fm":
+        return sig[5] is None and sig[6] is None
+    return sig[0] in ("am", "digital", "unknown")
+
+
+def _run_plan(x, sample_rate, cfgs, sigs, modes, bfo, n, n_chunks, fmt, apply_squelch, return_device, results):
+    """process_channels_batch through ONE wc_analog_run call (+ one device->host transfer of the metrics)."""
+    from .analog_plan import get_plan
+
+    chains = [s[:5] if s[0] in ("fm", "am") else (s[0],) for s in sigs]
+    squelch = [(c.squelch_db if apply_squelch else None) for c in cfgs]
+    plan = get_plan(sample_rate, n, fmt, modes, [float(c.offset_hz) for c in cfgs], bfo, squelch, chains)
+    audio, metrics = plan.run(x.reshape(n_chunks, n, 2) if fmt == S.FMT_CS16 else x.reshape(n_chunks, n), n_chunks)
+    m = metrics.cpu().numpy().astype(np.float64)          # [3][C][B]: rssi_db | signal_power_db | valid
+    a_host = None if return_device else audio.cpu().numpy()
+    for ci, cfg in enumerate(cfgs):
+        kind = sigs[ci][0]
+        n_a, off = plan.audio_len[ci], n_chunks * plan.audio_off[ci]
+        for b in range(n_chunks):
+            valid = m[2, ci, b]
+            if valid == 0.0:
+                continue                                   # non-finite IQ: chunk dropped, empty metrics (capture.py:323-325)
+            rssi = float(m[0, ci, b])
+            if kind == "digital":
+                results[b][ci] = (None, {"rssi_db": rssi, "signal_power_db": rssi})
+            elif kind == "unknown" or valid < 1.0:
+                results[b][ci] = (None, {"rssi_db": rssi})   # no audio path / _validate_audio_output failed (:433-435)
+            else:
+                s0 = off + b * n_a
+                au = audio[s0:s0 + n_a].clone() if return_device else a_host[s0:s0 + n_a].copy()
+                results[b][ci] = (au, {"rssi_db": rssi, "signal_power_db": float(m[1, ci, b])})
+    return results
+
+
 def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig], *, n_chunks: int = 1,
                            in_fmt: str = "cf32", apply_squelch: bool = False, return_device: bool = False,
-                           want_fm_baseband: bool = False):
+                           want_fm_baseband: bool = False, use_plan: bool = True):
     """`_process_channel_dsp_stateless` for every (chunk, channel) pair of a batch.
 
     samples: complex64 [n_chunks*N] / [n_chunks, N] (in_fmt="cf32") or interleaved int16 I,Q
@@ -182,15 +219,27 @@ def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig],
 
     N.ensure_init()
     n_ch = len(cfgs)
-    if in_fmt == "cs16":
-        x = S.to_device(samples, np.int16).reshape(n_chunks, -1, 2)
-        n, fmt = x.shape[1], S.FMT_CS16
-    else:
-        x = S.to_device(samples, np.complex64).reshape(n_chunks, -1)
-        n, fmt = x.shape[1], S.FMT_CF32
+    fmt = S.FMT_CS16 if in_fmt == "cs16" else S.FMT_CF32
+    total = int(samples.numel()) if N.is_torch_cuda(samples) else int(np.asarray(samples).size)
+    n = total // (2 * n_chunks) if fmt == S.FMT_CS16 else total // n_chunks
     results = [[(None, {}) for _ in range(n_ch)] for _ in range(n_chunks)]
     if n == 0 or n_ch == 0:
         return results
+    if use_plan and not want_fm_baseband:
+        sigs = [_chain_signature(c, sample_rate) for c in cfgs]
+        if all(_plan_eligible(s) for s in sigs):
+            modes = [_MODE_CODE.get(c.mode, S.MODE_NONE) for c in cfgs]
+            bfo = [(c.ssb_bfo_offset_hz if c.ssb_mode.lower() == "usb" else -c.ssb_bfo_offset_hz) if c.mode == "ssb" else 0.0
+                   for c in cfgs]
+            if N.is_torch_cuda(samples):
+                src = S.to_device(samples, np.int16 if fmt == S.FMT_CS16 else np.complex64)
+            else:   # staged into the plan's own device buffer (fixed address: repeated calls replay the captured graph)
+                src = np.ascontiguousarray(samples, dtype=np.int16 if fmt == S.FMT_CS16 else np.complex64)
+            return _run_plan(src, sample_rate, cfgs, sigs, modes, bfo, n, n_chunks, fmt, apply_squelch, return_device, results)
+    if in_fmt == "cs16":
+        x = S.to_device(samples, np.int16).reshape(n_chunks, -1, 2)
+    else:
+        x = S.to_device(samples, np.complex64).reshape(n_chunks, -1)
 
     sigs = [_chain_signature(c, sample_rate) for c in cfgs]
     modes = [_MODE_CODE.get(c.mode, S.MODE_NONE) for c in cfgs]

@@ -273,10 +273,10 @@ __device__ __forceinline__ void dd_matvec_acc(const dd* __restrict__ M, const dd
     }
 }
 
-// Dynamic shared memory layout: float sx[T*(L+1)] | dd vb[2][T][K]
+// Dynamic shared memory layout: float sx[T*(L+1)] | dd vb[2][T][K] | dd sP[LOG_T][K*K]
 template <int K>
 constexpr size_t iir_smem_bytes() {
-    return sizeof(float) * IIR_T * (IIR_L + 1) + sizeof(dd) * 2 * IIR_T * K + 16;
+    return sizeof(float) * IIR_T * (IIR_L + 1) + sizeof(dd) * 2 * IIR_T * K + sizeof(dd) * IIR_LOG_T * K * K + 16;
 }
 
 // FINAL = 0 (pass 1): zero-state run of every 64-sample segment -> z_i (global), inclusive scan
@@ -291,7 +291,11 @@ __global__ void __launch_bounds__(IIR_T) iir_kernel(const IirCoef* __restrict__ 
     extern __shared__ __align__(16) unsigned char iir_smem[];
     float* sx = reinterpret_cast<float*>(iir_smem);
     dd* vb = reinterpret_cast<dd*>(iir_smem + ((sizeof(float) * IIR_T * (IIR_L + 1) + 15) & ~size_t(15)));
+    // transition powers staged once per CTA: the scan reads K*K of them per step and thread, and from global memory
+    // every one of those was a long-scoreboard stall (ncu round 1: 10.3 stalled warps per issue at 21 % of the warp slots)
+    dd* sP = vb + 2 * IIR_T * K;
     const int tid = threadIdx.x;
+    for (int e = tid; e < IIR_LOG_T * K * K; e += IIR_T) sP[e] = cf->Ppow[e / (K * K)][e % (K * K)];
     const int tile = blockIdx.x, seq = blockIdx.y;
     const int t0 = tile * IIR_TILE;
     const int cnt = min(IIR_TILE, n - t0);
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(IIR_T) iir_kernel(const IirCoef* __restrict__ 
     if (FINAL) {
 #pragma unroll
         for (int i = 0; i < K; ++i) sc[i] = stile[tix * K + i];
-        if (tid == 0) dd_matvec_acc<K>(cf->Ppow[0], sc, v);  // end(seg 0) = P*S_c + z_0
+        if (tid == 0) dd_matvec_acc<K>(sP, sc, v);  // end(seg 0) = P*S_c + z_0
     }
     // Kogge-Stone inclusive scan: v_i <- v_i + P^(2^k) * v_{i-2^k}
     int cur = 0;
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(IIR_T) iir_kernel(const IirCoef* __restrict__ 
         for (int i = 0; i < K; ++i) buf[tid * K + i] = v[i];
         __syncthreads();
         const int d = 1 << k;
-        if (tid >= d) dd_matvec_acc<K>(cf->Ppow[k], buf + (tid - d) * K, v);
+        if (tid >= d) dd_matvec_acc<K>(sP + k * K * K, buf + (tid - d) * K, v);
         cur ^= 1;
     }
     if (!FINAL) {
@@ -1520,6 +1524,469 @@ int wc_signal_metrics(const void* iq_dev, int fmt, int n, int sample_rate, const
         WC_CUDA(cudaGetLastError());
     }
     WC_CUDA(cudaStreamSynchronize(st));  // the pageable host vector must outlive the async copy
+    return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Analog plan: the whole per-chunk analog chain of a capture as ONE call (SURVEY §8b wc_analog_plan_create / wc_analog_run)
+// =================================================================================================
+// The caller this replaces makes one _process_channel_dsp_stateless call per (chunk, channel) from its worker pool
+// (capture.py:2489-2597). The stage-level entry points above reproduce that chain operator by operator, but chaining them
+// from Python costs ~40-50 % of a C1/C2 step in host orchestration (tensor allocation, ctypes, handle lookup). A plan
+// owns everything the chain needs — per-channel oscillator parameters on the device, IIR / resampler handles, scratch,
+// statistics — and wc_analog_run enqueues the whole batch of chunks: front end -> [IIR stages] -> [AGC] -> RMS ->
+// resampler with fused scale / clip -> dB metrics, validity gate and squelch, with no allocation, no host
+// synchronisation and no per-stage Python. Calls that repeat the same (input, output, n_chunks) triple are replayed
+// from a captured CUDA graph (one cudaGraphLaunch instead of ~10-20 launches).
+namespace {
+
+constexpr int PLAN_MAX_IIR = 8;
+constexpr int PLAN_GRAPHS = 4;
+
+struct PlanRun {
+    int first = 0, count = 0;
+    int kind = 0;                 // 0: metrics only (raw / digital / unknown), 1: FM chain, 2: AM / SSB chain
+    std::vector<wc_iir*> iir;     // stages between the front end and the gain stage, in order
+    bool agc = false;
+    wc_iir *agc_attack = nullptr, *agc_release = nullptr;
+    float agc_target = 0.f, agc_max_gain = 0.f;
+    int up = 1, down = 1;
+    wc_resampler* rs = nullptr;
+    int n_audio = 0;              // output samples per chunk and channel
+    long long audio_off = 0;      // float offset of the run's first channel inside the audio buffer, per chunk count 1
+};
+
+struct PlanGraph {
+    const void* iq = nullptr;
+    float* audio = nullptr;
+    float* metrics = nullptr;
+    int n_chunks = 0;
+    int seen = 0;                 // 1 after an eager run with this key; the next one is captured
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long stamp = 0;
+};
+
+// rssi_db / signal_power_db / valid for every (channel, chunk), squelch decision (capture.py:331-334, 436-437, 323-325,
+// 433-435, 2918-2921). metrics: float32 [3][n_ch][n_chunks].
+__global__ void plan_metrics_kernel(const double* __restrict__ power, const double* __restrict__ apower,
+                                    const int* __restrict__ invalid, const int* __restrict__ nonfinite,
+                                    const int* __restrict__ n_audio, const int* __restrict__ kind,
+                                    const float* __restrict__ squelch_db, int n, int n_ch, int n_chunks,
+                                    float* __restrict__ metrics, unsigned char* __restrict__ squelched) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ch * n_chunks) return;
+    const int c = i / n_chunks, b = i % n_chunks;
+    const float rssi = 10.0f * log10f((float)(power[i] / (double)n) + 1e-10f);
+    float sig = rssi;             // digital modes report the same power twice (capture.py:426-428)
+    float valid = nonfinite[b] ? 0.f : 1.f;
+    if (kind[c] != 0) {
+        sig = 10.0f * log10f((float)(apower[i] / (double)max(n_audio[c], 1)) + 1e-10f);
+        if (invalid[i]) valid = valid != 0.f ? 0.5f : 0.f;   // 0.5: RSSI is reported, the audio is dropped (:433-435)
+    } else if (kind[c] == 0 && n_audio[c] < 0) {
+        valid = valid != 0.f ? 0.5f : 0.f;                   // unknown mode: no audio path
+    }
+    metrics[i] = rssi;
+    metrics[(size_t)n_ch * n_chunks + i] = sig;
+    metrics[2 * (size_t)n_ch * n_chunks + i] = valid;
+    const float sq = squelch_db[c];
+    squelched[i] = (sq == sq && rssi < sq) ? 1 : 0;          // NaN = no squelch
+}
+
+// zero the audio of squelched sequences (capture.py:2918-2921); rows: [count * n_chunks][n_audio] starting at audio
+__global__ void plan_squelch_kernel(float* __restrict__ audio, int n_audio, const unsigned char* __restrict__ squelched) {
+    if (!squelched[blockIdx.y]) return;
+    float* a = audio + (long long)blockIdx.y * n_audio;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_audio; i += gridDim.x * blockDim.x) a[i] = 0.f;
+}
+
+// the resampler's epilogue for chains whose audio rate equals the capture rate (resample_poly returns its input,
+// dsp/fm.py:202-203): scale / clip, audio power and validity per sequence. epi as WC_EPI_*.
+__global__ void plan_tail_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int epi,
+                                 const double* __restrict__ sumsq, float target_rms, float min_rms,
+                                 double* __restrict__ power, int* __restrict__ invalid, float max_abs) {
+    __shared__ double red[8];
+    __shared__ int bad_s;
+    const int seq = blockIdx.y;
+    if (threadIdx.x == 0) bad_s = 0;
+    __syncthreads();
+    float scale = 1.f;
+    if (epi == WC_EPI_RMS_CLIP || epi == WC_EPI_RMS) {
+        const float rms = sqrtf((float)(sumsq[seq] / (double)n));
+        if (rms > min_rms) scale = (float)((double)target_rms / (double)rms);
+    }
+    double acc = 0.0;
+    int bad = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float v = x[(long long)seq * n + i] * scale;
+        if (epi == WC_EPI_RMS_CLIP || epi == WC_EPI_CLIP) v = soft_clip_fm(v);
+        else if (epi == WC_EPI_CLIP_AGC) v = soft_clip_agc(v);
+        y[(long long)seq * n + i] = v;
+        acc += (double)v * (double)v;
+        if (!(fabsf(v) <= max_abs)) bad = 1;
+    }
+    acc = warp_sum(acc);
+    if (bad) bad_s = 1;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+        atomicAdd(power + seq, s);
+        if (bad_s) invalid[seq] = 1;
+    }
+}
+
+}  // namespace
+
+struct wc_analog_plan {
+    int fs = 0, n = 0, fmt = 0, n_ch = 0;
+    std::vector<FrontChan> h_chan;
+    std::vector<float> h_squelch;
+    std::vector<int> h_kind, h_naudio;
+    std::vector<PlanRun> runs;
+    bool finished = false;
+    // device state
+    FrontChan* d_chan = nullptr;
+    float* d_squelch = nullptr;
+    int *d_kind = nullptr, *d_naudio = nullptr;
+    int cap_chunks = 0;           // buffers below are sized for this many chunks
+    float* d_front = nullptr;     // [n_ch][B][n]
+    float *d_env_a = nullptr, *d_env_r = nullptr;   // AGC envelopes, sized for the widest AGC run
+    double *d_power = nullptr, *d_ss = nullptr, *d_apower = nullptr;
+    int *d_invalid = nullptr, *d_nonfinite = nullptr;
+    unsigned char* d_squelched = nullptr;
+    void* d_iir_scratch = nullptr;
+    long long audio_per_chunk = 0;  // floats of audio per chunk over all channels
+    PlanGraph graphs[PLAN_GRAPHS];
+    unsigned long long clock = 0;
+    int use_graph = 1;
+};
+
+static void plan_free_buffers(wc_analog_plan* p) {
+    for (void* q : {(void*)p->d_front, (void*)p->d_env_a, (void*)p->d_env_r, (void*)p->d_power, (void*)p->d_ss, (void*)p->d_apower,
+                    (void*)p->d_invalid, (void*)p->d_nonfinite, (void*)p->d_squelched, p->d_iir_scratch})
+        if (q) cudaFree(q);
+    p->d_front = p->d_env_a = p->d_env_r = nullptr;
+    p->d_power = p->d_ss = p->d_apower = nullptr;
+    p->d_invalid = p->d_nonfinite = nullptr;
+    p->d_squelched = nullptr;
+    p->d_iir_scratch = nullptr;
+    for (PlanGraph& g : p->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = PlanGraph();
+    }
+    p->cap_chunks = 0;
+}
+
+static int plan_reserve(wc_analog_plan* p, int B) {
+    if (B <= p->cap_chunks) return 0;
+    plan_free_buffers(p);
+    const size_t seqs = (size_t)p->n_ch * B;
+    size_t agc_rows = 0, scratch = 16;
+    for (const PlanRun& r : p->runs) {
+        if (r.agc) agc_rows = std::max(agc_rows, (size_t)r.count * B);
+        for (const wc_iir* f : r.iir)
+            if (!f->sequential) scratch = std::max(scratch, iir_scan_scratch_bytes(f->h_cf.K, p->n, r.count * B));
+        if (r.agc) scratch = std::max(scratch, iir_scan_scratch_bytes(1, p->n, r.count * B));
+    }
+    WC_CUDA(cudaMalloc(&p->d_front, sizeof(float) * seqs * (size_t)p->n));
+    if (agc_rows) {
+        WC_CUDA(cudaMalloc(&p->d_env_a, sizeof(float) * agc_rows * (size_t)p->n));
+        WC_CUDA(cudaMalloc(&p->d_env_r, sizeof(float) * agc_rows * (size_t)p->n));
+    }
+    WC_CUDA(cudaMalloc(&p->d_power, sizeof(double) * seqs));
+    WC_CUDA(cudaMalloc(&p->d_ss, sizeof(double) * seqs));
+    WC_CUDA(cudaMalloc(&p->d_apower, sizeof(double) * seqs));
+    WC_CUDA(cudaMalloc(&p->d_invalid, sizeof(int) * seqs));
+    WC_CUDA(cudaMalloc(&p->d_nonfinite, sizeof(int) * (size_t)B));
+    WC_CUDA(cudaMalloc(&p->d_squelched, seqs));
+    WC_CUDA(cudaMalloc(&p->d_iir_scratch, scratch));
+    p->cap_chunks = B;
+    return 0;
+}
+
+// everything wc_analog_run enqueues, on `st` (capturable: no allocation, no synchronisation, no host-side parameters)
+static int plan_enqueue(wc_analog_plan* p, const void* iq_dev, int B, float* audio_dev, float* metrics_dev, cudaStream_t st) {
+    const int n = p->n, C = p->n_ch;
+    const size_t seqs = (size_t)C * B;
+    WC_CUDA(cudaMemsetAsync(p->d_power, 0, sizeof(double) * seqs, st));
+    WC_CUDA(cudaMemsetAsync(p->d_ss, 0, sizeof(double) * seqs, st));
+    WC_CUDA(cudaMemsetAsync(p->d_apower, 0, sizeof(double) * seqs, st));
+    WC_CUDA(cudaMemsetAsync(p->d_invalid, 0, sizeof(int) * seqs, st));
+    WC_CUDA(cudaMemsetAsync(p->d_nonfinite, 0, sizeof(int) * (size_t)B, st));
+    {
+        FrontArgs a;
+        a.iq = iq_dev;
+        a.chunk_stride = n;
+        a.n = n;
+        a.fmt = p->fmt;
+        a.n_ch = C;
+        a.n_chunks = B;
+        a.ch = p->d_chan;
+        a.out = p->d_front;
+        a.base_out = nullptr;
+        a.power = p->d_power;
+        a.out_sumsq = p->d_ss;
+        a.nonfinite = p->d_nonfinite;
+        const int tiles = (n + FR_TILE - 1) / FR_TILE;
+        const long long base_ctas = (long long)tiles * B;
+        long long groups = (4LL * 5 * sm_count() + base_ctas - 1) / base_ctas;
+        if (groups > C) groups = C;
+        if (groups < 1) groups = 1;
+        front_kernel<<<dim3(tiles, B, (unsigned)groups), FR_THREADS, 0, st>>>(a);
+        WC_CUDA(cudaGetLastError());
+    }
+    for (const PlanRun& r : p->runs) {
+        if (r.kind == 0) continue;
+        const int rows = r.count * B;
+        float* x = p->d_front + (size_t)r.first * B * n;
+        double* ss = p->d_ss + (size_t)r.first * B;
+        double* ap = p->d_apower + (size_t)r.first * B;
+        int* inv = p->d_invalid + (size_t)r.first * B;
+        for (const wc_iir* f : r.iir) {
+            if (f->h_cf.K == 0) {
+                elementwise_kernel<<<148 * 8, 256, 0, st>>>(x, x, (long long)rows * n, 2, (float)f->h_cf.b0);
+            } else if (int rc = iir_run(f, x, x, n, n, rows, 0, p->d_iir_scratch, st)) {
+                return rc;
+            }
+        }
+        int epi;
+        if (r.kind == 1) {
+            epi = WC_EPI_RMS_CLIP;
+            if (!r.iir.empty()) {   // the front end's sum(out**2) only holds when nothing changed the signal since
+                WC_CUDA(cudaMemsetAsync(ss, 0, sizeof(double) * rows, st));
+                int bx = (n + 255) / 256;
+                if (bx > 64) bx = 64;
+                sumsq_kernel<<<dim3(bx, rows), 256, 0, st>>>(x, n, n, ss);
+            }
+        } else {
+            if (r.agc) {
+                if (int rc = iir_run(r.agc_attack, x, p->d_env_a, n, n, rows, 1, p->d_iir_scratch, st)) return rc;
+                if (int rc = iir_run(r.agc_release, p->d_env_a, p->d_env_r, n, n, rows, 0, p->d_iir_scratch, st)) return rc;
+                agc_apply_kernel<<<148 * 8, 256, 0, st>>>(x, p->d_env_a, p->d_env_r, x, (long long)rows * n, r.agc_target, r.agc_max_gain);
+                epi = WC_EPI_NONE;
+            } else {
+                epi = WC_EPI_CLIP_AGC;
+            }
+        }
+        float* au = audio_dev + r.audio_off * B;
+        if (r.rs) {
+            if (int rc = wc_resampler_run(r.rs, x, n, n, rows, au, epi, ss, 0.18f, 1e-4f, ap, inv, 1.2f, st)) return rc;
+        } else {
+            int bx = (n + 1023) / 1024;
+            if (bx > 32) bx = 32;
+            plan_tail_kernel<<<dim3(bx, rows), 256, 0, st>>>(x, au, n, epi, ss, 0.18f, 1e-4f, ap, inv, 1.2f);
+        }
+        WC_CUDA(cudaGetLastError());
+    }
+    plan_metrics_kernel<<<(unsigned)((seqs + 127) / 128), 128, 0, st>>>(p->d_power, p->d_apower, p->d_invalid, p->d_nonfinite, p->d_naudio,
+                                                                         p->d_kind, p->d_squelch, n, C, B, metrics_dev, p->d_squelched);
+    for (const PlanRun& r : p->runs) {
+        if (r.kind == 0 || r.n_audio <= 0) continue;
+        bool any = false;
+        for (int c = r.first; c < r.first + r.count; ++c) any = any || (p->h_squelch[c] == p->h_squelch[c]);
+        if (!any) continue;
+        int bx = (r.n_audio + 255) / 256;
+        if (bx > 8) bx = 8;
+        plan_squelch_kernel<<<dim3(bx, r.count * B), 256, 0, st>>>(audio_dev + r.audio_off * B, r.n_audio, p->d_squelched + (size_t)r.first * B);
+    }
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int wc_analog_plan_create(int sample_rate, int chunk_len, int in_fmt, int n_channels, const int* modes, const double* offsets_hz,
+                          const double* bfo_hz, const float* squelch_db, wc_analog_plan** out) {
+    WC_REQUIRE(out && modes && offsets_hz, "wc_analog_plan_create: null argument");
+    WC_REQUIRE(sample_rate > 0 && chunk_len >= 1 && n_channels >= 1 && n_channels <= 4096, "wc_analog_plan_create: bad sizes");
+    WC_REQUIRE(in_fmt == 0 || in_fmt == 1, "wc_analog_plan_create: in_fmt must be 0 (cf32) or 1 (cs16)");
+    wc_analog_plan* p = new wc_analog_plan();
+    p->fs = sample_rate;
+    p->n = chunk_len;
+    p->fmt = in_fmt;
+    p->n_ch = n_channels;
+    p->h_chan.resize(n_channels);
+    p->h_squelch.assign(n_channels, nanf(""));
+    p->h_kind.assign(n_channels, 0);
+    p->h_naudio.assign(n_channels, 0);
+    for (int c = 0; c < n_channels; ++c) {
+        FrontChan& f = p->h_chan[c];
+        f.mode = modes[c];
+        f.shift = (offsets_hz[c] != 0.0) ? 1 : 0;
+        const double off = nearbyint(offsets_hz[c]);
+        f.k32 = (float)(-(2.0 * M_PI * (off / (double)sample_rate)));
+        f.bfo_turns = bfo_hz ? bfo_hz[c] / (double)sample_rate : 0.0;
+        f.disc_scale = (float)((double)sample_rate / (2.0 * M_PI * 75000.0));
+        if (squelch_db) p->h_squelch[c] = squelch_db[c];
+    }
+    *out = p;
+    return 0;
+}
+
+// A run = `count` adjacent channels starting at `first` that share one chain. kind 0: metrics only; 1: FM (rms_normalize +
+// fm soft clip); 2: AM / SSB. up/down/taps: scipy resample_poly's design (up == down == 1: no resampler). Returns the run index.
+int wc_analog_plan_add_run(wc_analog_plan* p, int first, int count, int kind, int up, int down, const double* taps, int n_taps) {
+    WC_REQUIRE(p && !p->finished, "wc_analog_plan_add_run: plan missing or already finished");
+    WC_REQUIRE(first >= 0 && count >= 1 && first + count <= p->n_ch && kind >= 0 && kind <= 2, "wc_analog_plan_add_run: bad run");
+    PlanRun r;
+    r.first = first;
+    r.count = count;
+    r.kind = kind;
+    r.up = up;
+    r.down = down;
+    if (kind != 0) {
+        if (up != 1 || down != 1) {
+            WC_REQUIRE(taps && n_taps >= 1, "wc_analog_plan_add_run: resampler taps missing");
+            if (int rc = wc_resampler_create(up, down, taps, n_taps, &r.rs)) return rc < 0 ? rc : -rc;
+            r.n_audio = (int)wc_resampler_out_len(r.rs, p->n);
+        } else {
+            r.n_audio = p->n;
+        }
+    }
+    p->runs.push_back(r);
+    return (int)p->runs.size() - 1;
+}
+
+int wc_analog_plan_add_iir(wc_analog_plan* p, int run, const double* b, int nb, const double* a, int na) {
+    WC_REQUIRE(p && !p->finished && run >= 0 && run < (int)p->runs.size(), "wc_analog_plan_add_iir: bad plan / run");
+    WC_REQUIRE((int)p->runs[run].iir.size() < PLAN_MAX_IIR, "wc_analog_plan_add_iir: too many stages");
+    wc_iir* f = nullptr;
+    if (int rc = wc_iir_create(b, nb, a, na, &f)) return rc;
+    p->runs[run].iir.push_back(f);
+    return 0;
+}
+
+// apply_agc (dsp/agc.py:169-242): the two float32 one-pole envelope filters as (b, a) pairs, target and maximum gain (linear)
+int wc_analog_plan_set_agc(wc_analog_plan* p, int run, const double* attack_b, const double* attack_a, const double* release_b,
+                           const double* release_a, float target_linear, float max_gain_linear) {
+    WC_REQUIRE(p && !p->finished && run >= 0 && run < (int)p->runs.size() && p->runs[run].kind == 2, "wc_analog_plan_set_agc: bad plan / run");
+    PlanRun& r = p->runs[run];
+    if (int rc = wc_iir_create(attack_b, 1, attack_a, 2, &r.agc_attack)) return rc;
+    if (int rc = wc_iir_create(release_b, 1, release_a, 2, &r.agc_release)) return rc;
+    r.agc = true;
+    r.agc_target = target_linear;
+    r.agc_max_gain = max_gain_linear;
+    return 0;
+}
+
+int wc_analog_plan_finish(wc_analog_plan* p) {
+    WC_REQUIRE(p && !p->finished, "wc_analog_plan_finish: plan missing or already finished");
+    std::vector<int> covered(p->n_ch, 0);
+    long long off = 0;
+    for (PlanRun& r : p->runs) {
+        r.audio_off = off;
+        off += (long long)r.count * r.n_audio;
+        for (int c = r.first; c < r.first + r.count; ++c) {
+            WC_REQUIRE(!covered[c], "wc_analog_plan_finish: channel %d is in two runs", c);
+            covered[c] = 1;
+            p->h_kind[c] = r.kind;
+            p->h_naudio[c] = r.n_audio;
+        }
+    }
+    for (int c = 0; c < p->n_ch; ++c) WC_REQUIRE(covered[c], "wc_analog_plan_finish: channel %d is in no run", c);
+    p->audio_per_chunk = off;
+    WC_CUDA(cudaMalloc(&p->d_chan, sizeof(FrontChan) * p->n_ch));
+    WC_CUDA(cudaMalloc(&p->d_squelch, sizeof(float) * p->n_ch));
+    WC_CUDA(cudaMalloc(&p->d_kind, sizeof(int) * p->n_ch));
+    WC_CUDA(cudaMalloc(&p->d_naudio, sizeof(int) * p->n_ch));
+    WC_CUDA(cudaMemcpy(p->d_chan, p->h_chan.data(), sizeof(FrontChan) * p->n_ch, cudaMemcpyHostToDevice));
+    WC_CUDA(cudaMemcpy(p->d_squelch, p->h_squelch.data(), sizeof(float) * p->n_ch, cudaMemcpyHostToDevice));
+    WC_CUDA(cudaMemcpy(p->d_kind, p->h_kind.data(), sizeof(int) * p->n_ch, cudaMemcpyHostToDevice));
+    WC_CUDA(cudaMemcpy(p->d_naudio, p->h_naudio.data(), sizeof(int) * p->n_ch, cudaMemcpyHostToDevice));
+    p->finished = true;
+    return 0;
+}
+
+void wc_analog_plan_destroy(wc_analog_plan* p) {
+    if (!p) return;
+    plan_free_buffers(p);
+    for (PlanRun& r : p->runs) {
+        for (wc_iir* f : r.iir) wc_iir_destroy(f);
+        wc_iir_destroy(r.agc_attack);
+        wc_iir_destroy(r.agc_release);
+        wc_resampler_destroy(r.rs);
+    }
+    for (void* q : {(void*)p->d_chan, (void*)p->d_squelch, (void*)p->d_kind, (void*)p->d_naudio})
+        if (q) cudaFree(q);
+    delete p;
+}
+
+/* floats of audio per chunk over all channels; channel c's audio of chunk b of a B-chunk call starts at
+ * audio + B * wc_analog_plan_audio_offset(c) + b * wc_analog_plan_audio_len(c). */
+long long wc_analog_plan_audio_floats(const wc_analog_plan* p) { return p ? p->audio_per_chunk : 0; }
+int wc_analog_plan_audio_len(const wc_analog_plan* p, int channel) {
+    return (p && channel >= 0 && channel < p->n_ch) ? p->h_naudio[channel] : 0;
+}
+long long wc_analog_plan_audio_offset(const wc_analog_plan* p, int channel) {
+    if (!p || channel < 0 || channel >= p->n_ch) return -1;
+    for (const PlanRun& r : p->runs)
+        if (channel >= r.first && channel < r.first + r.count) return r.audio_off + (long long)(channel - r.first) * r.n_audio;
+    return -1;
+}
+int wc_analog_plan_use_graph(wc_analog_plan* p, int on) {
+    WC_REQUIRE(p != nullptr, "wc_analog_plan_use_graph: null plan");
+    p->use_graph = on ? 1 : 0;
+    return 0;
+}
+
+/* n_chunks consecutive chunks of chunk_len samples at iq_dev (cf32 or cs16 as configured).
+ * audio_dev: float32 [n_chunks * wc_analog_plan_audio_floats()] (layout above; squelched sequences are zeroed);
+ * metrics_dev: float32 [3][n_channels][n_chunks] = rssi_db | signal_power_db | valid (1 = audio valid, 0.5 = RSSI only:
+ * the audio failed the validity gate or the mode has no audio path, 0 = chunk dropped for non-finite IQ). */
+int wc_analog_run(wc_analog_plan* p, const void* iq_dev, int n_chunks, float* audio_dev, float* metrics_dev, void* stream) {
+    WC_REQUIRE(p && p->finished && iq_dev && metrics_dev, "wc_analog_run: null argument or unfinished plan");
+    WC_REQUIRE(audio_dev || p->audio_per_chunk == 0, "wc_analog_run: audio_dev is null");
+    WC_REQUIRE(n_chunks >= 1, "wc_analog_run: n_chunks must be >= 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan_reserve(p, n_chunks)) return -2;
+    if (!p->use_graph || st == nullptr || st == cudaStreamLegacy) return plan_enqueue(p, iq_dev, n_chunks, audio_dev, metrics_dev, st);
+    PlanGraph* slot = nullptr;
+    for (PlanGraph& g : p->graphs)
+        if (g.seen && g.iq == iq_dev && g.audio == audio_dev && g.metrics == metrics_dev && g.n_chunks == n_chunks) slot = &g;
+    ++p->clock;
+    if (slot && slot->exec) {
+        slot->stamp = p->clock;
+        WC_CUDA(cudaGraphLaunch(slot->exec, st));
+        return 0;
+    }
+    if (!slot) {   // first sight of this key: run eagerly (also sets the per-device function attributes), remember it
+        PlanGraph* lru = &p->graphs[0];
+        for (PlanGraph& g : p->graphs)
+            if (g.stamp < lru->stamp) lru = &g;
+        if (lru->exec) cudaGraphExecDestroy(lru->exec);
+        *lru = PlanGraph();
+        lru->iq = iq_dev;
+        lru->audio = audio_dev;
+        lru->metrics = metrics_dev;
+        lru->n_chunks = n_chunks;
+        lru->seen = 1;
+        lru->stamp = p->clock;
+        return plan_enqueue(p, iq_dev, n_chunks, audio_dev, metrics_dev, st);
+    }
+    // second call with the same key: capture it, then launch the graph
+    slot->stamp = p->clock;
+    cudaGraph_t graph = nullptr;
+    WC_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = plan_enqueue(p, iq_dev, n_chunks, audio_dev, metrics_dev, st);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        p->use_graph = 0;   // capture is not available here: stay on the eager path
+        return rc ? rc : plan_enqueue(p, iq_dev, n_chunks, audio_dev, metrics_dev, st);
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+        slot->exec = nullptr;
+        cudaGetLastError();
+        p->use_graph = 0;
+        return plan_enqueue(p, iq_dev, n_chunks, audio_dev, metrics_dev, st);
+    }
+    WC_CUDA(cudaGraphLaunch(slot->exec, st));
     return 0;
 }
 
