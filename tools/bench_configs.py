@@ -74,27 +74,57 @@ def emit(**kw):
     print(json.dumps(kw), flush=True)
 
 
+def _plan_for(cfgs, fs, n, fmt):
+    from wavecap_sdr_b200 import analog_plan as AP
+    from wavecap_sdr_b200 import capture as CAP
+    from wavecap_sdr_b200.dsp import _stages as S
+
+    sigs = [CAP._chain_signature(c, fs) for c in cfgs]
+    chains = [s[:5] if s[0] in ("fm", "am") else (s[0],) for s in sigs]
+    modes = [CAP._MODE_CODE.get(c.mode, 0) for c in cfgs]
+    return AP.get_plan(fs, n, S.FMT_CS16 if fmt == "cs16" else S.FMT_CF32, modes, [float(c.offset_hz) for c in cfgs],
+                       [0.0] * len(cfgs), [c.squelch_db for c in cfgs], chains)
+
+
+def _analog_cfg(sampler_cls, name, workload, x, xr, fs, n, B, cfgs, fmt, alg_bytes, flops, kernels, note):
+    """step = ONE wc_analog_run call for B chunks x all channels (what capture.py:2489-2597 would issue per batch) + the
+    device->host read of its metrics; `python_batch_api_ms` = the same batch through capture.process_channels_batch
+    (adds the per-(chunk, channel) Python result assembly the reference's callers expect)."""
+    from wavecap_sdr_b200.capture import process_channels_batch
+
+    plan = _plan_for(cfgs, fs, n, fmt)
+
+    def step():
+        _, metrics = plan.run(xr, B)
+        return metrics.cpu()
+    ms, iters, clocks = timed_with_clocks(step, sampler_cls)
+    api_ms = timeit(lambda: process_channels_batch(x, fs, cfgs, n_chunks=B, in_fmt=fmt, apply_squelch=True, return_device=True), iters=10)
+    stage_ms = timeit(lambda: process_channels_batch(x, fs, cfgs, n_chunks=B, in_fmt=fmt, apply_squelch=True, return_device=True,
+                                                     use_plan=False), iters=10)
+    return {"config": name, "workload": workload, "step": f"{B} chunks x {n} samples" + (f" x {len(cfgs)} channels" if len(cfgs) > 1 else ""),
+            "ms": round(ms, 4), "steps": iters, "metric": "input MS/s", "value": round(B * n / ms / 1e3, 1), "unit": "MS/s",
+            "channel_msps": round(len(cfgs) * B * n / ms / 1e3, 1), "realtime_x": round(B * n / fs / (ms * 1e-3), 1),
+            "api": "wc_analog_run (one call per batch, CUDA-graph replay) + metrics read on the host",
+            "python_batch_api_ms": round(api_ms, 4), "stage_by_stage_path_ms": round(stage_ms, 4),
+            "roofline": roofline(alg_bytes, ms, kernels, note=note, flops=flops), "clocks": clocks}
+
+
 def cfg_c1(sampler_cls=None, B=64):
     """C1: one WBFM channel, 2.4 MS/s cf32, B chunks of 120 000 per call (capture._process_channel_dsp_stateless batch)."""
-    from wavecap_sdr_b200.capture import ChannelConfig, apply_mode_defaults, process_channels_batch
+    from wavecap_sdr_b200.capture import ChannelConfig, apply_mode_defaults
 
     fs, n = 2_400_000, 120_000
     x = torch.view_as_complex(torch.randn((B * n, 2), device="cuda") * 0.3)
     cfg = apply_mode_defaults("wbfm", ChannelConfig(id="a", capture_id="c", mode="wbfm", offset_hz=200000.0))
-    ms, iters, clocks = timed_with_clocks(lambda: process_channels_batch(x, fs, [cfg], n_chunks=B, return_device=True), sampler_cls)
-    return {"config": "C1", "workload": "WBFM 1 channel from 2.4 MS/s cf32 (freq_shift, RSSI, discriminator, de-emphasis, 15 kHz MPX "
-                                        "low-pass, RMS, 1/50 resampler, soft clip)",
-            "step": f"{B} chunks x {n} samples", "ms": round(ms, 4), "steps": iters, "metric": "input MS/s",
-            "value": round(B * n / ms / 1e3, 1), "unit": "MS/s", "realtime_x": round(B * n / fs / (ms * 1e-3), 1),
-            "roofline": roofline(B * n * 8 + B * 2400 * 4, ms, "iir_kernel (block scan) + front_kernel + resample_residue_kernel",
-                                 note="8.08 B/sample algorithmic; the chain is latency/FP64-bound (SURVEY §8d), the HBM fraction is stated for completeness",
-                                 flops=60 * B * n),
-            "clocks": clocks}
+    return _analog_cfg(sampler_cls, "C1", "WBFM 1 channel from 2.4 MS/s cf32 (freq_shift, RSSI, discriminator, de-emphasis, 15 kHz MPX "
+                       "low-pass, RMS, 1/50 resampler, soft clip)", x, x.reshape(B, n), fs, n, B, [cfg], "cf32",
+                       B * n * 8 + B * 2400 * 4, 60 * B * n, "iir_kernel (block scan) + front_kernel + resample_residue_kernel",
+                       "8.08 B/sample algorithmic; the chain is latency/FP64-bound (SURVEY §8d), the HBM fraction is stated for completeness")
 
 
 def cfg_c2(sampler_cls=None, B=8):
     """C2: 16 NBFM channels + squelch from one 10 MS/s int16 capture, B chunks of 500 000."""
-    from wavecap_sdr_b200.capture import ChannelConfig, apply_mode_defaults, process_channels_batch
+    from wavecap_sdr_b200.capture import ChannelConfig, apply_mode_defaults
 
     fs, n = 10_000_000, 500_000
     q = torch.randint(-2000, 2000, (B, n, 2), device="cuda", dtype=torch.int16)
@@ -103,18 +133,11 @@ def cfg_c2(sampler_cls=None, B=8):
         c = apply_mode_defaults("nbfm", ChannelConfig(id=str(i), capture_id="c", mode="nbfm", offset_hz=-3.75e6 + 5e5 * i))
         c.squelch_db = -45.0
         cfgs.append(c)
-    ms, iters, clocks = timed_with_clocks(lambda: process_channels_batch(q, fs, cfgs, n_chunks=B, in_fmt="cs16", apply_squelch=True,
-                                                                         return_device=True), sampler_cls)
-    return {"config": "C2", "workload": "16 NBFM channels + squelch from one 10 MS/s cs16 capture (per channel: NCO, discriminator, RMS, "
-                                        "3/625 resampler, soft clip)",
-            "step": f"{B} chunks x {n} samples x 16 channels", "ms": round(ms, 4), "steps": iters, "metric": "input MS/s",
-            "value": round(B * n / ms / 1e3, 1), "unit": "MS/s", "channel_msps": round(16 * B * n / ms / 1e3, 1),
-            "realtime_x": round(B * n / fs / (ms * 1e-3), 1),
-            "roofline": roofline(B * n * 4 + 16 * B * 2400 * 4, ms, "front_kernel + resample_residue_kernel",
-                                 note="4.31 B/sample algorithmic; FP32/SFU compute-bound by construction (16 sincos + 16 atan2 per input sample, "
-                                      "SURVEY §8d): the fp32 block is the relevant fraction",
-                                 flops=1900 * B * n),
-            "clocks": clocks}
+    return _analog_cfg(sampler_cls, "C2", "16 NBFM channels + squelch from one 10 MS/s cs16 capture (per channel: NCO, discriminator, RMS, "
+                       "3/625 resampler, soft clip)", q, q, fs, n, B, cfgs, "cs16", B * n * 4 + 16 * B * 2400 * 4, 1900 * B * n,
+                       "front_kernel + resample_residue_kernel",
+                       "4.31 B/sample algorithmic; FP32/SFU compute-bound by construction (16 sincos + 16 atan2 per input sample, "
+                       "SURVEY §8d): the fp32 block is the relevant fraction")
 
 
 def cfg_c3(sampler_cls=None, frames=4096):

@@ -181,24 +181,25 @@ def _run_plan(x, sample_rate, cfgs, sigs, modes, bfo, n, n_chunks, fmt, apply_sq
     squelch = [(c.squelch_db if apply_squelch else None) for c in cfgs]
     plan = get_plan(sample_rate, n, fmt, modes, [float(c.offset_hz) for c in cfgs], bfo, squelch, chains)
     audio, metrics = plan.run(x.reshape(n_chunks, n, 2) if fmt == S.FMT_CS16 else x.reshape(n_chunks, n), n_chunks)
-    m = metrics.cpu().numpy().astype(np.float64)          # [3][C][B]: rssi_db | signal_power_db | valid
-    a_host = None if return_device else audio.cpu().numpy()
+    m = metrics.cpu().numpy().astype(np.float64)          # [3][C][B]: rssi_db | signal_power_db | valid (one transfer)
+    # the audio buffer is the plan's (overwritten by the next call): hand out views of ONE copy of it
+    a_all = audio.clone() if return_device else audio.cpu().numpy()
+    rssi_l, sig_l, valid_l = m[0].tolist(), m[1].tolist(), m[2].tolist()
     for ci, cfg in enumerate(cfgs):
         kind = sigs[ci][0]
         n_a, off = plan.audio_len[ci], n_chunks * plan.audio_off[ci]
+        rows = a_all[off:off + n_chunks * n_a].reshape(n_chunks, n_a) if n_a > 0 else None
         for b in range(n_chunks):
-            valid = m[2, ci, b]
+            valid = valid_l[ci][b]
             if valid == 0.0:
                 continue                                   # non-finite IQ: chunk dropped, empty metrics (capture.py:323-325)
-            rssi = float(m[0, ci, b])
+            rssi = rssi_l[ci][b]
             if kind == "digital":
                 results[b][ci] = (None, {"rssi_db": rssi, "signal_power_db": rssi})
             elif kind == "unknown" or valid < 1.0:
                 results[b][ci] = (None, {"rssi_db": rssi})   # no audio path / _validate_audio_output failed (:433-435)
             else:
-                s0 = off + b * n_a
-                au = audio[s0:s0 + n_a].clone() if return_device else a_host[s0:s0 + n_a].copy()
-                results[b][ci] = (au, {"rssi_db": rssi, "signal_power_db": float(m[1, ci, b])})
+                results[b][ci] = (rows[b], {"rssi_db": rssi, "signal_power_db": sig_l[ci][b]})
     return results
 
 
