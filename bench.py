@@ -48,11 +48,14 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=128, help="50 ms chunks per step (device-resident leg)")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks per step of the host-buffer leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
-    ap.add_argument("--mode", default="replicas", choices=["replicas", "broadcast", "pull"],
+    ap.add_argument("--stripe-chunks", type=int, default=64, help="stripe mode: 50 ms chunks per block (one process() call, cut into N slabs)")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "broadcast", "pull", "stripe"],
                     help="replicas: one independent capture per GPU (headline, weak scaling); broadcast: ONE capture, "
                          "each block NCCL-broadcast from rank 0 and time-sharded over the ranks (north-star-literal, strong); "
                          "pull: ONE capture, rank 0's block mapped into every rank, each rank's channelizer kernel pulls "
-                         "only its weighted time slab over NVLink while it computes (no collective on the data path)")
+                         "only its weighted time slab over NVLink while it computes (no collective on the data path); "
+                         "stripe: ONE capture striped at ingest — slab r of every block lands in rank r's own memory, only the "
+                         "9-row halo crosses NVLink")
     ap.add_argument("--pull-local-share", type=float, default=0.0,
                     help="pull mode: share of each block rank 0 keeps (0 = local/(local+link) from --pull-rates)")
     ap.add_argument("--pull-tune-rounds", type=int, default=3,
@@ -538,6 +541,116 @@ def run_pull(args, rank, local_rank, world, standalone=True):
     return line
 
 
+def run_stripe(args, rank, local_rank, world, standalone=True):
+    """ONE capture for the whole box, striped at ingest (sharding.StripedCapture): every block (stripe-chunks x 6.25 M samples
+    = one process() call) is cut into N time slabs and slab r is resident in rank r's HBM when the timed region starts, as
+    if each GPU's own PCIe link / DMA target had received it. Per block a rank fetches the 9 halo rows (9 KB) from the
+    previous slab's owner over NVLink (rank 0: the 10 tail rows of the previous block from the last rank -> carried
+    history), then runs the SAME fused kernel on [halo | slab]. No rank's egress carries the capture, so the job scales
+    with N; frames are bit-equal to the unsharded call (tests/test_stripe_gpu.py). `e2e` repeats it with the ingest inside
+    the timed region: every rank copies its slab from pinned host memory first (PCIe-bound)."""
+    import torch
+    import torch.distributed as dist
+
+    import wavecap_sdr_b200._native as N
+    from wavecap_sdr_b200.dsp.channelizer import PolyphaseChannelizer
+    from wavecap_sdr_b200.sharding import StripedCapture
+
+    if standalone:
+        torch.cuda.set_device(local_rank)
+        N.init(local_rank)
+        if world > 1:
+            init_nccl(local_rank)
+        bind_to_gpu_numa(local_rank)
+    n = args.stripe_chunks * CHUNK
+    ch = PolyphaseChannelizer(FS, BW)
+    sc = StripedCapture(ch, n)
+    g = torch.Generator(device="cuda").manual_seed(4321 + rank)
+    for b in range(2):
+        torch.view_as_real(sc.own_tensor(b)).normal_(0.0, 0.5, generator=g)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    host = None
+
+    def step(ingest=False):
+        b = sc.wait_free()
+        if ingest:
+            sc.own_tensor(b).copy_(host, non_blocking=True)
+        sc.publish()
+        rows, _ = sc.process(fm=True)
+        return rows
+
+    def timed(k, ingest=False):
+        barrier()
+        for _ in range(3):                      # re-align the streams after the host barrier (see run_pull)
+            rows = step(ingest)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            rows = step(ingest)
+        if ingest:
+            float(rows[-1, 17].item())          # the step's result is read on the host
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / k], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), rows
+
+    w = max(3, args.warmup)
+    for _ in range(w):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, rows = timed(args.steps)
+    clocks = sampler.stop()
+    finite = bool(torch.isfinite(rows).all()) and bool(rows.abs().sum() > 0)
+    # e2e: the ingest inside the timed region
+    host = torch.empty((sc.own_n[rank],), dtype=torch.complex64, pin_memory=True)
+    torch.view_as_real(host).fill_(0.25)
+    e_steps = max(2, min(args.steps, 5))
+    e_ms, _ = timed(e_steps, ingest=True)
+    sc.check()
+    ok = torch.tensor([1 if finite else 0], device="cuda", dtype=torch.int32)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(n / (ms * 1e-3) / 1e6, 1), "unit": "MS/s", "n_gpus": world, "steps": args.steps,
+            "warmup": w, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mode": "stripe",
+            "config": {
+                "workload": "C5: ONE 125 MS/s capture striped at ingest: slab r of every block resident in rank r's HBM; 256-ch "
+                            "channelizer + FM on [9-row halo from the previous slab's owner | own slab]",
+                "block_samples": n, "frames_per_rank": [s_.n_frames for s_ in sc.slabs], "halo_rows": 9,
+                "parallelism": f"{world} equal time slabs, no data-path collective; 9 KB halo per rank per block over NVLink, "
+                               "READY/DONE flags in peer memory",
+                "bound": "each rank: its own HBM / SMs (the single-GPU kernel rate); NVLink carries 9 KB per rank per block",
+                "l2": "slab (%.0f MB per rank) exceeds the 126 MB L2" % (8 * n / world / 1e6),
+                "checked": "finite, non-zero output on every rank" if int(ok.item()) == 1 else "OUTPUT CHECK FAILED",
+            },
+            "link": {"halo_bytes_per_rank_per_step": 8 * 9 * 128 if world > 1 else 0},
+            "e2e": {"value": round(n / (e_ms * 1e-3) / 1e6, 1), "unit": "MS/s", "ms_per_step": round(e_ms, 3),
+                    "h2d_bytes_per_step": int(8 * n), "d2h_bytes_per_step": 4,
+                    "what": "every rank copies its slab from pinned host memory into its own buffer first (its own PCIe link)"},
+            "gpu_launches": (5 if world > 1 else 3) * args.steps, "clocks": clocks,
+        }
+        if standalone:
+            print(json.dumps(line), flush=True)
+    del rows
+    barrier()
+    sc.close()
+    if world > 1 and standalone:
+        dist.destroy_process_group()
+    return line
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -548,6 +661,9 @@ def main():
         return
     if args.mode == "pull":
         run_pull(args, rank, local_rank, world)
+        return
+    if args.mode == "stripe":
+        run_stripe(args, rank, local_rank, world)
         return
     if args.mode == "broadcast":
         run_broadcast(args, rank, local_rank, world)
@@ -836,13 +952,25 @@ def main():
             pass
         torch.cuda.empty_cache()
         barrier()
-        try:
-            oc = run_pull(args, rank, local_rank, world, standalone=False)
-            if rank == 0 and oc is not None:
-                one_capture = {k: oc[k] for k in ("mode", "value", "unit", "ms_per_step", "steps", "scaling", "link", "clocks")}
-                one_capture["config"] = {k: oc["config"][k] for k in ("workload", "block_samples", "slab_weights", "parallelism", "bound", "checked")}
-        except BaseException as e:  # noqa: BLE001 — SystemExit from a failed cross-check included
-            one_capture = {"error": f"{type(e).__name__}: {e}"}
+        one_capture = {}
+        for name, fn in (("stripe", run_stripe), ("pull", run_pull)):
+            try:
+                oc = fn(args, rank, local_rank, world, standalone=False)
+                if rank == 0 and oc is not None:
+                    rec = {k: oc[k] for k in ("mode", "value", "unit", "ms_per_step", "steps", "scaling", "link", "clocks") if k in oc}
+                    rec["config"] = {k: oc["config"][k] for k in ("workload", "block_samples", "slab_weights", "parallelism", "bound", "checked")
+                                     if k in oc["config"]}
+                    if "e2e" in oc:
+                        rec["e2e"] = oc["e2e"]
+                    one_capture[name] = rec
+            except BaseException as e:  # noqa: BLE001 — SystemExit from a failed cross-check included
+                one_capture[name] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+            barrier()
+        if rank == 0:
+            best = max((v for v in one_capture.values() if "value" in v), key=lambda v: v["value"], default=None)
+            if best is not None:
+                one_capture["value"], one_capture["unit"], one_capture["mode"] = best["value"], best["unit"], best["mode"]
 
     if rank == 0:
         peak, peak_src = load_peaks()

@@ -52,6 +52,9 @@ int wc_chan_process(wc_chan* h, const void* iq_dev, long long n_samples, int n_c
 /* advance the carried history (arm_history) as if process() had been called on iq_dev[0..n_samples) without
  * computing outputs — for time-sharded multi-GPU runs where another rank emitted the tail of the call. */
 int wc_chan_carry_from(wc_chan* h, const void* iq_dev, long long n_samples, void* stream);
+/* the same from just the tail of the previous call: tail_dev = its samples [(F - T) * M/2, (F + 1) * M/2) (T + 1 hop rows,
+ * complex64), e.g. fetched from the GPU that owns the end of the previous block of a striped capture. */
+int wc_chan_carry_tail(wc_chan* h, const void* tail_dev, void* stream);
 /* frames each CTA of the M=256 kernels walks (rounded up to 8, clamped to [16, 256]); 0 = sized so the grid is ~6 waves.
  * Every run re-reads T-1 halo rows, which local L2 absorbs but NVLink does not: callers whose iq_dev is peer memory
  * (wc_peer_open) raise it so the halo traffic stays at (T-1)/run_frames of the slab. */

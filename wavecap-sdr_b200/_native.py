@@ -143,6 +143,7 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_chan_reset", i32, vp)
     fn("wc_chan_process", i32, vp, vp, i64, i32, i64, i32, f32, vp, vp)
     fn("wc_chan_carry_from", i32, vp, vp, i64, vp)
+    fn("wc_chan_carry_tail", i32, vp, vp, vp)
     fn("wc_chan_set_run_frames", i32, vp, i32)
     fn("wc_chan_process_host", i32, vp, vp, i64, i32, i32, f32, vp)
     fn("wc_chan_audio_config", i32, vp, i32, i32)

@@ -1154,6 +1154,19 @@ int wc_chan_set_run_frames(wc_chan* h, int run_frames) {
     return 0;
 }
 
+// Set the carried history from the last (T + 1) hop rows of the previous process() call — samples
+// [(F - T) * M/2, (F + 1) * M/2) of that call, F its frame count — wherever they now live (e.g. copied out of another
+// GPU's slab of a striped capture): identical to what wc_chan_carry_from(prev_call) would leave behind when F >= T.
+int wc_chan_carry_tail(wc_chan* h, const void* tail_dev, void* stream_v) {
+    WC_REQUIRE(h && tail_dev, "wc_chan_carry_tail: null argument");
+    // chan_carry_kernel with F = T reads block i = m (m = 0 .. T-1) at x_last[i * M/2 + k], k < M: exactly the tail layout
+    chan_carry_kernel<IN_CF32><<<h->T, 256, 0, (cudaStream_t)stream_v>>>(tail_dev, h->T, h->M, h->T, h->d_carried[h->cur],
+                                                                        h->d_carried[h->cur ^ 1]);
+    WC_CUDA(cudaGetLastError());
+    h->cur ^= 1;
+    return 0;
+}
+
 int wc_chan_carry_from(wc_chan* h, const void* iq_dev, long long n_samples, void* stream_v) {
     WC_REQUIRE(h && iq_dev, "wc_chan_carry_from: null argument");
     const long long F = wc_chan_frames_for(h, n_samples);

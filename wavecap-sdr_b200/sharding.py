@@ -250,3 +250,128 @@ class PeerRegion:
             N.check(N.lib().wc_peer_free(C.c_void_p(self.base)))
         else:
             N.check(N.lib().wc_peer_close(C.c_void_p(self.base)))
+
+
+class StripedCapture:
+    """ONE capture over all ranks, striped at ingest: every block (= one `PolyphaseChannelizer.process()` call of
+    `block_samples` samples) is cut into `world` time slabs and slab r is delivered straight into rank r's memory (its own
+    PCIe link / DMA target), so no rank's NVLink egress or HBM carries the whole capture. What a rank lacks is only the
+    9 hop rows in front of its slab (8 rows of polyphase history + 1 for the FM discriminator): 1152 samples = 9 KB per
+    block, copied from the previous slab's owner over NVLink (peer-mapped regions, stream-ordered flags); rank 0 takes
+    the 10 tail rows of the previous block from the last rank instead and installs them as the carried history
+    (`wc_chan_carry_tail`). Emitted frames are bit-equal to the unsharded call's.
+
+    Flags in rank r's region (owner r): READY[b] = block number whose slab is in buffer b; DONE[b] = block number whose
+    tail the reader (rank (r + 1) % world) has finished copying — the owner may overwrite buffer b after that.
+    Collective: every rank constructs it at the same point."""
+
+    HALO_ROWS = CHAN_HALO_FRAMES          # rows a rank > 0 needs in front of its slab
+    AREA = (CHAN_HALO_FRAMES + 1) * 128   # samples reserved in front of the own part (rank 0's tail fetch needs T + 1 rows)
+    READY, DONE = 0, 16
+
+    def __init__(self, chan, block_samples: int, group=None):
+        import torch.distributed as dist
+
+        assert chan.channel_count == 256 and chan.taps_per_channel == 9
+        self.chan = chan
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.block_samples = int(block_samples)
+        self.frames = chan.frames_for(self.block_samples)
+        self.slabs = [frame_slab(self.frames, self.world, r, halo=0) for r in range(self.world)]
+        assert all(s.n_frames > CHAN_HALO_FRAMES + 1 for s in self.slabs), "block too short for this many ranks"
+        # own part of rank r: the samples its frames [f0, f1) cover = [128 f0, 128 (f1 - 1) + 256)
+        self.own0 = [128 * s.f0 for s in self.slabs]
+        self.own_n = [(s.f1 - 1 - s.f0) * 128 + 256 for s in self.slabs]
+        self.stride = self.AREA + ((max(self.own_n) + 15) & ~15)      # samples per buffer
+        self.regions = [PeerRegion(8 * 2 * self.stride, src=r, group=group) for r in range(self.world)]
+        self.mine = self.regions[self.rank]
+        self.block = 0                        # blocks processed so far
+
+    # -- addressing (sample offsets inside a region's payload) ----------------------------------------
+    def _own_off(self, b: int) -> int:
+        return b * self.stride + self.AREA
+
+    def own_tensor(self, b: int):
+        """complex64 view of this rank's slab in buffer b: where the ingest writes."""
+        return self.mine.payload_tensor(self._own_off(b), self.own_n[self.rank])
+
+    def slab_of(self, block_tensor_or_array, r: int | None = None):
+        """the samples of a whole block that belong to rank r's slab (for the ingest side / the tests)"""
+        r = self.rank if r is None else r
+        return block_tensor_or_array[self.own0[r]: self.own0[r] + self.own_n[r]]
+
+    # -- one block --------------------------------------------------------------------------------------
+    def publish(self, timeout_ms: int = 5000) -> int:
+        """Call after the ingest of the next block's slab into buffer (block & 1) has been enqueued on the current
+        stream: marks it READY. Returns the buffer index. (Before overwriting a buffer the ingest side calls
+        `wait_free` first.)"""
+        b = self.block & 1
+        self.mine.set_flag(self.READY + b, self.block + 1)
+        return b
+
+    def wait_free(self, timeout_ms: int = 5000) -> int:
+        """stream waits until the reader of this rank's buffer (block & 1) has copied the tail of block - 2"""
+        b = self.block & 1
+        if self.block >= 2 and self.world > 1:
+            self.mine.wait_flags(self.DONE + b, 1, self.block - 1, timeout_ms=timeout_ms)
+        return b
+
+    def process(self, fm: bool = True, timeout_ms: int = 5000):
+        """Channelize (+ FM-demodulate) this rank's slab of the current block; returns (rows [n_frames, 256], f0)."""
+        import ctypes as C
+
+        import torch
+
+        from . import _native as N
+        from .dsp.channelizer import OUT_COMPLEX, OUT_FM, fm_scale
+
+        i, r, W = self.block, self.rank, self.world
+        b, seq = i & 1, i + 1
+        lib, st = N.lib(), N.torch_stream_ptr()
+        s = self.slabs[r]
+        own_ptr = self.mine.payload_ptr(8 * self._own_off(b))
+        mode = OUT_FM if fm else OUT_COMPLEX
+        scale = fm_scale(int(self.chan.channel_sample_rate)) if fm else 0.0
+        if r == 0:
+            # history = the T + 1 tail rows of the previous block, owned by the last rank (previous buffer)
+            if i > 0:
+                last = self.regions[W - 1]
+                pb = (i - 1) & 1
+                if W > 1:
+                    last.wait_flags(self.READY + pb, 1, seq - 1, timeout_ms=timeout_ms)
+                tail_off = pb * self.stride + self.AREA + ((self.frames - CHAN_HALO_FRAMES) * 128 - self.own0[W - 1])
+                dst = self.mine.payload_ptr(8 * (b * self.stride))          # the area in front of my own part
+                N.check(lib.wc_peer_copy(C.c_void_p(dst), C.c_void_p(last.payload_ptr(8 * tail_off)), 8 * self.AREA, st))
+                if W > 1:
+                    last.set_flag(self.DONE + pb, seq - 1)
+                N.check(lib.wc_chan_carry_tail(self.chan._h, C.c_void_p(dst), st))
+            else:
+                self.chan.reset()
+            rows = torch.empty((s.n_frames, 256), device="cuda", dtype=torch.float32 if fm else torch.complex64)
+            N.check(lib.wc_chan_process(self.chan._h, C.c_void_p(own_ptr), self.own_n[0], 1, self.own_n[0], mode, scale,
+                                        C.c_void_p(rows.data_ptr()), st))
+            out = rows
+        else:
+            prev = self.regions[r - 1]
+            prev.wait_flags(self.READY + b, 1, seq, timeout_ms=timeout_ms)
+            halo = self.HALO_ROWS * 128
+            src_off = b * self.stride + self.AREA + (self.own0[r] - halo - self.own0[r - 1])
+            dst = own_ptr - 8 * halo
+            N.check(lib.wc_peer_copy(C.c_void_p(dst), C.c_void_p(prev.payload_ptr(8 * src_off)), 8 * halo, st))
+            prev.set_flag(self.DONE + b, seq)
+            n_local = halo + self.own_n[r]
+            rows = torch.empty((s.n_frames + self.HALO_ROWS, 256), device="cuda", dtype=torch.float32 if fm else torch.complex64)
+            N.check(lib.wc_chan_process(self.chan._h, C.c_void_p(dst), n_local, 1, n_local, mode, scale,
+                                        C.c_void_p(rows.data_ptr()), st))
+            out = rows[self.HALO_ROWS:]       # the first 9 local frames only rebuilt the FIR / discriminator state
+        self.block += 1
+        return out, s.f0
+
+    def check(self) -> None:
+        for reg in self.regions:
+            reg.check()
+
+    def close(self) -> None:
+        for reg in self.regions:
+            reg.close()
