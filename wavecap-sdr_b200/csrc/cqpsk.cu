@@ -173,6 +173,8 @@ struct CqSyncArgs {
     const float2* filt;      // [C][n]
     unsigned char* dibits;   // [C][max_sym]
     int* n_sym;              // [C]
+    float2* sym;             // [C][max_sym] interpolated symbols of this call (timing kernel -> slicer kernel)
+    double* delta;           // [C][max_sym] frequency-loop increments (slicer kernel -> frequency scan)
 };
 
 constexpr int CQ_TILE = 96;             // new samples staged per step
@@ -237,10 +239,7 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
     CqView v;
     v.mmse = s_mmse;
     v.ring = s_ring + lane * CQ_PITCH;
-    unsigned char* out = a.dibits + (long long)(live ? ch : 0) * a.max_sym;
-    const float HALF_PI_F = (float)1.5707963267948966, PI_F = (float)3.141592653589793, TWO_PI_F = (float)6.283185307179586;
-    const float Q_PI_F = (float)0.7853981633974483, TQ_PI_F = (float)2.356194490192345;
-    const double PI_D = 3.141592653589793;
+    float2* sym_out = a.sym + (long long)(live ? ch : 0) * a.max_sym;
     const float omega_lo = (float)(a.k.sps * 0.95), omega_hi = (float)(a.k.sps * 1.05);
     int nsym = 0;
     // Tile loop: the filtered samples of the warp's 32 channels are staged CQ_TILE at a time into the shared-memory ring
@@ -294,71 +293,12 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
         }
         imu = min(imu, 128);
         const float2 curr = cq_interp(v, m, 0, imu);
-        const float cm = cq_abs(curr);
-        int dibit;
-        if (S.first) {
-            // prev is Python 0j: diff = curr * np.conj(0j) is complex128 (+-0); phase = arctan2(+-0, +-0) in float64
-            const bool neg_r = signbit(curr.x) != 0, neg_i = signbit(curr.y) != 0;
-            // real = re*0 - im*(-0), imag = re*(-0) + im*0
-            const double re0 = (double)curr.x * 0.0 - (double)curr.y * (-0.0);
-            const double im0 = (double)curr.x * (-0.0) + (double)curr.y * 0.0;
-            (void)neg_r;
-            (void)neg_i;
-            const double phase = atan2(im0, re0);
-            double expected;
-            if (phase >= 1.5707963267948966) {
-                dibit = 1;
-                expected = 2.356194490192345;
-            } else if (phase >= 0.0) {
-                dibit = 0;
-                expected = 0.7853981633974483;
-            } else if (phase >= -1.5707963267948966) {
-                dibit = 2;
-                expected = -0.7853981633974483;
-            } else {
-                dibit = 3;
-                expected = -2.356194490192345;
-            }
-            double pe = phase - expected;
-            if (pe > PI_D) pe -= 2.0 * PI_D;
-            else if (pe < -PI_D) pe += 2.0 * PI_D;
-            S.freq_offset += (0.0005 * pe) * (double)cm;
-        } else {
-            const float pm = cq_abs(S.prev);
-            float dr, di;
-            if (cm > 1e-6f && pm > 1e-6f) {
-                const float sc = __fdiv_rn(1.0f, cm), sp = __fdiv_rn(1.0f, pm);
-                const float ar = __fmul_rn(curr.x, sc), ai = __fmul_rn(curr.y, sc);
-                const float br = __fmul_rn(S.prev.x, sp), bi = -__fmul_rn(S.prev.y, sp);  // conj
-                dr = __fsub_rn(__fmul_rn(ar, br), __fmul_rn(ai, bi));
-                di = __fadd_rn(__fmul_rn(ar, bi), __fmul_rn(ai, br));
-            } else {
-                const float br = S.prev.x, bi = -S.prev.y;
-                dr = __fsub_rn(__fmul_rn(curr.x, br), __fmul_rn(curr.y, bi));
-                di = __fadd_rn(__fmul_rn(curr.x, bi), __fmul_rn(curr.y, br));
-            }
-            const float phase = (float)atan2((double)di, (double)dr);
-            float expected;
-            if (phase >= HALF_PI_F) {
-                dibit = 1;
-                expected = TQ_PI_F;
-            } else if (phase >= 0.0f) {
-                dibit = 0;
-                expected = Q_PI_F;
-            } else if (phase >= -HALF_PI_F) {
-                dibit = 2;
-                expected = -Q_PI_F;
-            } else {
-                dibit = 3;
-                expected = -TQ_PI_F;
-            }
-            float pe = __fsub_rn(phase, expected);
-            if (pe > PI_F) pe = __fsub_rn(pe, TWO_PI_F);
-            else if (pe < -PI_F) pe = __fadd_rn(pe, TWO_PI_F);
-            S.freq_offset += (double)__fmul_rn(__fmul_rn(0.0005f, pe), cm);
-        }
-        S.freq_offset = fmin(fmax(S.freq_offset, -0.02), 0.02);
-        if (nsym < a.max_sym) out[nsym] = (unsigned char)dibit;
+        // The differential slicer and the frequency loop (decoders/p25.py:540-585) read this symbol and the previous one
+        // but feed nothing back into the symbol clock within a call (the frequency offset only steers the NEXT call's
+        // NCO): they run afterwards, in parallel over all symbols (cqpsk_slice_kernel) with a short per-channel scan for
+        // the clamped accumulation (cqpsk_freq_kernel). What stays here is the genuinely sequential part: clock,
+        // interpolation, Gardner error. Measured on B200, 64 channels x 72 000 samples: 14.5 ms with the slicer inline.
+        if (nsym < a.max_sym) sym_out[nsym] = curr;
         ++nsym;
         // Gardner TED (decoders/p25.py:587-608); full_sps + 4 < 32 is guaranteed at create
         {
@@ -380,8 +320,6 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
         }
         while (S.clock_f >= 1.0f) S.clock_f = __fsub_rn(S.clock_f, 1.0f);
         while (S.clock_f < 0.0f) S.clock_f = __fadd_rn(S.clock_f, 1.0f);
-        S.prev = curr;
-        S.first = 0;
     }
     }
     if (!live) return;
@@ -390,15 +328,106 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
     for (int i = 0; i < CQ_HIST; ++i) nt[i] = cq_hist(v, a.n - 1, CQ_HIST - 1 - i);
     CqState* G = &a.st[ch];
     for (int i = 0; i < CQ_HIST; ++i) G->tail[i] = nt[i];
-    G->freq_offset = S.freq_offset;
     G->clock_d = S.clock_d;
     G->clock_f = S.clock_f;
     G->sym_time_f = S.sym_time_f;
     G->omega_f = S.omega_f;
-    G->prev = S.prev;
-    G->first = S.first;
     G->clock_is_f32 = S.clock_is_f32;
     a.n_sym[ch] = min(nsym, a.max_sym);
+}
+
+// Differential slicer (decoders/p25.py:540-585), one thread per (channel, symbol): normalised curr * conj(prev), the
+// correctly rounded float32 phase, dibit, and the frequency-loop increment 0.0005 * phase_error * |curr| as float64.
+// Symbol 0 of a call pairs with the state's previous symbol; the very first symbol after a reset pairs with Python's 0j
+// and follows the reference's float64 path.
+__global__ void cqpsk_slice_kernel(const CqSyncArgs a) {
+    const int ch = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n_sym[ch]) return;
+    const float HALF_PI_F = (float)1.5707963267948966, PI_F = (float)3.141592653589793, TWO_PI_F = (float)6.283185307179586;
+    const float Q_PI_F = (float)0.7853981633974483, TQ_PI_F = (float)2.356194490192345;
+    const double PI_D = 3.141592653589793;
+    const float2* sym = a.sym + (long long)ch * a.max_sym;
+    const float2 curr = sym[k];
+    const float cm = cq_abs(curr);
+    int dibit;
+    double delta;
+    if (k == 0 && a.st[ch].first) {
+        // prev is Python 0j: diff = curr * np.conj(0j) is complex128 (+-0); phase = arctan2(+-0, +-0) in float64
+        const double re0 = (double)curr.x * 0.0 - (double)curr.y * (-0.0);
+        const double im0 = (double)curr.x * (-0.0) + (double)curr.y * 0.0;
+        const double phase = atan2(im0, re0);
+        double expected;
+        if (phase >= 1.5707963267948966) {
+            dibit = 1;
+            expected = 2.356194490192345;
+        } else if (phase >= 0.0) {
+            dibit = 0;
+            expected = 0.7853981633974483;
+        } else if (phase >= -1.5707963267948966) {
+            dibit = 2;
+            expected = -0.7853981633974483;
+        } else {
+            dibit = 3;
+            expected = -2.356194490192345;
+        }
+        double pe = phase - expected;
+        if (pe > PI_D) pe -= 2.0 * PI_D;
+        else if (pe < -PI_D) pe += 2.0 * PI_D;
+        delta = (0.0005 * pe) * (double)cm;
+    } else {
+        const float2 prev = (k == 0) ? a.st[ch].prev : sym[k - 1];
+        const float pm = cq_abs(prev);
+        float dr, di;
+        if (cm > 1e-6f && pm > 1e-6f) {
+            const float sc = __fdiv_rn(1.0f, cm), sp = __fdiv_rn(1.0f, pm);
+            const float ar = __fmul_rn(curr.x, sc), ai = __fmul_rn(curr.y, sc);
+            const float br = __fmul_rn(prev.x, sp), bi = -__fmul_rn(prev.y, sp);  // conj
+            dr = __fsub_rn(__fmul_rn(ar, br), __fmul_rn(ai, bi));
+            di = __fadd_rn(__fmul_rn(ar, bi), __fmul_rn(ai, br));
+        } else {
+            const float br = prev.x, bi = -prev.y;
+            dr = __fsub_rn(__fmul_rn(curr.x, br), __fmul_rn(curr.y, bi));
+            di = __fadd_rn(__fmul_rn(curr.x, bi), __fmul_rn(curr.y, br));
+        }
+        const float phase = (float)atan2((double)di, (double)dr);
+        float expected;
+        if (phase >= HALF_PI_F) {
+            dibit = 1;
+            expected = TQ_PI_F;
+        } else if (phase >= 0.0f) {
+            dibit = 0;
+            expected = Q_PI_F;
+        } else if (phase >= -HALF_PI_F) {
+            dibit = 2;
+            expected = -Q_PI_F;
+        } else {
+            dibit = 3;
+            expected = -TQ_PI_F;
+        }
+        float pe = __fsub_rn(phase, expected);
+        if (pe > PI_F) pe = __fsub_rn(pe, TWO_PI_F);
+        else if (pe < -PI_F) pe = __fadd_rn(pe, TWO_PI_F);
+        delta = (double)__fmul_rn(__fmul_rn(0.0005f, pe), cm);
+    }
+    a.dibits[(long long)ch * a.max_sym + k] = (unsigned char)dibit;
+    a.delta[(long long)ch * a.max_sym + k] = delta;
+}
+
+// Frequency loop state: freq_offset = clip(freq_offset + delta_k, +-0.02) symbol by symbol (:583-585) — the clip makes it
+// order dependent, so one thread per channel replays the additions (two dependent float64 operations per symbol);
+// previous-symbol / first-symbol state for the next call.
+__global__ void cqpsk_freq_kernel(const CqSyncArgs a) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= a.C) return;
+    const int n = a.n_sym[ch];
+    if (n <= 0) return;
+    const double* d = a.delta + (long long)ch * a.max_sym;
+    double f = a.st[ch].freq_offset;
+    for (int k = 0; k < n; ++k) f = fmin(fmax(f + d[k], -0.02), 0.02);
+    a.st[ch].freq_offset = f;
+    a.st[ch].prev = a.sym[(long long)ch * a.max_sym + n - 1];
+    a.st[ch].first = 0;
 }
 
 __global__ void cqpsk_reset_kernel(CqState* st, int lo, int hi) {
@@ -425,6 +454,8 @@ struct wc_cqpsk {
     void* d_in = nullptr;      size_t in_cap = 0;
     unsigned char* d_dib = nullptr; size_t dib_cap = 0;
     int* d_nsym = nullptr;
+    float2* d_sym = nullptr;   size_t sym_cap = 0;     // [C][max_sym] symbols of the call
+    double* d_delta = nullptr;
     cudaStream_t stream = nullptr;
 };
 
@@ -512,6 +543,8 @@ void wc_cqpsk_destroy(wc_cqpsk* h) {
     if (h->d_filt) cudaFree(h->d_filt);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_dib) cudaFree(h->d_dib);
+    if (h->d_sym) cudaFree(h->d_sym);
+    if (h->d_delta) cudaFree(h->d_delta);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -552,6 +585,17 @@ int wc_cqpsk_demod(wc_cqpsk* h, const void* iq_dev, long long chan_stride, int n
         WC_CUDA(cudaMalloc((void**)&h->d_filt, need * sizeof(float2)));
         h->filt_cap = need;
     }
+    const size_t sneed = (size_t)C * max_sym;
+    if (h->sym_cap < sneed) {
+        if (h->d_sym) cudaFree(h->d_sym);
+        if (h->d_delta) cudaFree(h->d_delta);
+        h->d_sym = nullptr;
+        h->d_delta = nullptr;
+        h->sym_cap = 0;
+        WC_CUDA(cudaMalloc((void**)&h->d_sym, sneed * sizeof(float2)));
+        WC_CUDA(cudaMalloc((void**)&h->d_delta, sneed * sizeof(double)));
+        h->sym_cap = sneed;
+    }
     const float2* x = reinterpret_cast<const float2*>(iq_dev);
     cqpsk_agc_kernel<<<C, 256, 0, s>>>(x, chan_stride, n_samples, h->d_state, h->d_chunk);
     dim3 fg((n_samples + CQF_TILE - 1) / CQF_TILE, C);
@@ -565,7 +609,11 @@ int wc_cqpsk_demod(wc_cqpsk* h, const void* iq_dev, long long chan_stride, int n
     a.filt = h->d_filt;
     a.dibits = dibits_dev;
     a.n_sym = n_sym_dev;
+    a.sym = h->d_sym;
+    a.delta = h->d_delta;
     cqpsk_sync_kernel<<<(C + 31) / 32, 32, 0, s>>>(a);
+    cqpsk_slice_kernel<<<dim3((max_sym + 127) / 128, C), 128, 0, s>>>(a);
+    cqpsk_freq_kernel<<<(C + 31) / 32, 32, 0, s>>>(a);
     WC_CUDA(cudaGetLastError());
     return 0;
 }
