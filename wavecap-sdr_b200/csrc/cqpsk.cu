@@ -177,9 +177,13 @@ struct CqSyncArgs {
     double* delta;           // [C][max_sym] frequency-loop increments (slicer kernel -> frequency scan)
 };
 
+constexpr int CQ_CH = 8;                // channels per warp: the loop is latency-bound per symbol whatever the lane count, and a
+                                        // warp stages the rows of all its channels every tile, so fewer channels per warp = less
+                                        // staging per symbol and more SMs in use (64 channels: 8 warps instead of 2)
 constexpr int CQ_TILE = 96;             // new samples staged per step
 constexpr int CQ_RING = 128;            // ring slots per channel: CQ_TILE new + CQ_HIST of look-back
-constexpr int CQ_PITCH = CQ_RING + 1;   // row pitch in float2: rows of different lanes start in different banks
+constexpr int CQ_MIRROR = CQ_HIST;      // slots 0..31 are kept twice (also at 128..159) so that look-back reads never wrap
+constexpr int CQ_PITCH = CQ_RING + CQ_MIRROR + 1;   // row pitch in float2: rows of different lanes start in different banks
 
 struct CqView {
     const float2* ring;   // this lane's row of the shared-memory ring: sample j of the call sits in slot (j + 32) & 127,
@@ -189,22 +193,27 @@ struct CqView {
 };
 constexpr int CQ_ROW = 9;
 
-// sample `back` positions before sample index m of this call (m - back may reach into the tail)
+// sample `back` positions before sample index m of this call (m - back may reach into the tail); generic, wrapping form
 __device__ __forceinline__ float2 cq_hist(const CqView& v, int m, int back) {
     return v.ring[(m - back + CQ_HIST) & (CQ_RING - 1)];
 }
 
-// _mmse_interpolate_at_offset (decoders/p25.py:325-359)
-__device__ __forceinline__ float2 cq_interp(const CqView& v, int m, int back, int imu) {
+// _mmse_interpolate_at_offset (decoders/p25.py:325-359) with the tap row already in registers (the symbol, mid-point and
+// previous-symbol interpolations of one symbol share it: same mu). `p` points at the ring slot of the sample `back`
+// positions before the current one, in the unwrapped half of the mirrored ring: p[-(tap - 3)] is tap's sample, a load
+// with an immediate offset. Products rounded separately, summed left to right in float32 like the reference's loop.
+// FULL: all 8 taps lie inside the 32-sample history (3 <= back, back + 4 < 32); otherwise taps whose offset is negative
+// are skipped (back = 0: taps 3..7).
+template <bool FULL>
+__device__ __forceinline__ float2 cq_interp(const float2* __restrict__ p, int back, const float (&t)[8]) {
     float rr = 0.f, ri = 0.f;
     bool any = false;
 #pragma unroll
     for (int tap = 0; tap < 8; ++tap) {
         const int off = back + (tap - 3);
-        if (off >= 0 && off < CQ_HIST) {
-            const float2 h = cq_hist(v, m, off);
-            const float t = v.mmse[imu * CQ_ROW + tap];
-            const float pr = __fmul_rn(t, h.x), pi = __fmul_rn(t, h.y);
+        if (FULL || (off >= 0 && off < CQ_HIST)) {
+            const float2 h = p[-(tap - 3)];
+            const float pr = __fmul_rn(t[tap], h.x), pi = __fmul_rn(t[tap], h.y);
             if (!any) {
                 rr = pr;
                 ri = pi;
@@ -224,23 +233,28 @@ __device__ __forceinline__ float cq_abs(float2 z) {
 
 __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
     __shared__ float s_mmse[129 * CQ_ROW];
-    __shared__ float2 s_ring[32 * CQ_PITCH];
+    __shared__ float2 s_ring[CQ_CH * CQ_PITCH];
     for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) s_mmse[(i >> 3) * CQ_ROW + (i & 7)] = c_mmse[i >> 3][i & 7];
     const int lane = threadIdx.x;
-    const int c0 = blockIdx.x * 32;
+    const int c0 = blockIdx.x * CQ_CH;
     const int ch = c0 + lane;
-    const bool live = ch < a.C;
+    const bool live = lane < CQ_CH && ch < a.C;
     // the 32 carried samples of every row
-    for (int r = 0; r < 32 && c0 + r < a.C; ++r) s_ring[r * CQ_PITCH + lane] = a.st[c0 + r].tail[lane];
+    for (int r = 0; r < CQ_CH && c0 + r < a.C; ++r) {
+        const float2 tv = a.st[c0 + r].tail[lane];
+        s_ring[r * CQ_PITCH + lane] = tv;
+        s_ring[r * CQ_PITCH + CQ_RING + lane] = tv;
+    }
     __syncwarp();
     CqState S;
     if (live) S = a.st[ch];
     else memset(&S, 0, sizeof(S));
     CqView v;
     v.mmse = s_mmse;
-    v.ring = s_ring + lane * CQ_PITCH;
+    v.ring = s_ring + (lane < CQ_CH ? lane : 0) * CQ_PITCH;
     float2* sym_out = a.sym + (long long)(live ? ch : 0) * a.max_sym;
     const float omega_lo = (float)(a.k.sps * 0.95), omega_hi = (float)(a.k.sps * 1.05);
+    const bool full_taps = a.k.half_sps >= 3 && a.k.full_sps + 4 < CQ_HIST;   // every Gardner tap inside the history
     int nsym = 0;
     // Tile loop: the filtered samples of the warp's 32 channels are staged CQ_TILE at a time into the shared-memory ring
     // with 8-byte LDGSTS copies (lanes along the sample axis), then every lane walks its own row. Inside a tile the loop
@@ -252,13 +266,17 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
         const int lim = min(CQ_TILE, a.n - base);
         const int tile_end = base + lim;
         __syncwarp();
-        for (int r = 0; r < 32 && c0 + r < a.C; ++r) {
+        for (int r = 0; r < CQ_CH && c0 + r < a.C; ++r) {
             const float2* xr = a.filt + (long long)(c0 + r) * a.n + base;
             float2* row = s_ring + r * CQ_PITCH;
 #pragma unroll
             for (int k = 0; k < CQ_TILE / 32; ++k) {
                 const int i = lane + 32 * k;
-                if (i < lim) cp_async8(&row[(base + i + CQ_HIST) & (CQ_RING - 1)], xr + i);
+                if (i < lim) {
+                    const int slot = (base + i + CQ_HIST) & (CQ_RING - 1);
+                    cp_async8(&row[slot], xr + i);
+                    if (slot < CQ_MIRROR) cp_async8(&row[slot + CQ_RING], xr + i);
+                }
             }
         }
         cp_async_commit();
@@ -266,16 +284,34 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
         __syncwarp();
     for (;;) {
         bool fire = false;
-        while (live && m + 1 < tile_end) {
-            ++m;
-            if (S.clock_is_f32) {
-                S.clock_f = __fadd_rn(S.clock_f, S.sym_time_f);
-                fire = S.clock_f >= 1.0f;
-            } else {
+        if (live && S.clock_is_f32) {
+            // the clock advances by one rounded float32 addition per sample (exactly the reference's sequence); four
+            // samples per trip: the additions stay a dependent chain, but compare / branch / index work shrinks to a quarter
+            // (a single warp serves 32 channels, so this loop's latency is the demodulator's)
+            while (m + 1 < tile_end) {
+                const int room = tile_end - 1 - m;
+                const float c1 = __fadd_rn(S.clock_f, S.sym_time_f);
+                const float c2 = __fadd_rn(c1, S.sym_time_f);
+                const float c3 = __fadd_rn(c2, S.sym_time_f);
+                const float c4 = __fadd_rn(c3, S.sym_time_f);
+                int j = 4;                                   // first sample of the four whose clock value reaches 1
+                if (c3 >= 1.0f) j = 3;
+                if (c2 >= 1.0f) j = 2;
+                if (c1 >= 1.0f) j = 1;
+                const bool crossed = (c1 >= 1.0f) | (c2 >= 1.0f) | (c3 >= 1.0f) | (c4 >= 1.0f);
+                const int take = min(j, room);
+                S.clock_f = take == 1 ? c1 : take == 2 ? c2 : take == 3 ? c3 : c4;
+                m += take;
+                fire = crossed && take == j;
+                if (fire) break;
+            }
+        } else {
+            while (live && m + 1 < tile_end) {
+                ++m;
                 S.clock_d += a.k.sym_time0;
                 fire = S.clock_d >= 1.0;
+                if (fire) break;
             }
-            if (fire) break;
         }
         if (!__any_sync(0xffffffffu, fire)) break;
         if (!fire) continue;
@@ -292,7 +328,22 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
             imu = (int)rint(mu * 128.0);
         }
         imu = min(imu, 128);
-        const float2 curr = cq_interp(v, m, 0, imu);
+        float taps[8];
+#pragma unroll
+        for (int tap = 0; tap < 8; ++tap) taps[tap] = v.mmse[imu * CQ_ROW + tap];
+        // the three interpolations are independent: issue them together, the Gardner error needs all of them
+        int slot = (m + CQ_HIST) & (CQ_RING - 1);
+        if (slot < CQ_MIRROR) slot += CQ_RING;                    // mirrored copy: slot - 31 .. slot are all valid, no wrap
+        const float2* pc = v.ring + slot;
+        const float2 curr = cq_interp<false>(pc, 0, taps);
+        float2 mid, prv;
+        if (full_taps) {
+            mid = cq_interp<true>(pc - a.k.half_sps, a.k.half_sps, taps);
+            prv = cq_interp<true>(pc - a.k.full_sps, a.k.full_sps, taps);
+        } else {
+            mid = cq_interp<false>(pc - a.k.half_sps, a.k.half_sps, taps);
+            prv = cq_interp<false>(pc - a.k.full_sps, a.k.full_sps, taps);
+        }
         // The differential slicer and the frequency loop (decoders/p25.py:540-585) read this symbol and the previous one
         // but feed nothing back into the symbol clock within a call (the frequency offset only steers the NEXT call's
         // NCO): they run afterwards, in parallel over all symbols (cqpsk_slice_kernel) with a short per-channel scan for
@@ -302,12 +353,11 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
         ++nsym;
         // Gardner TED (decoders/p25.py:587-608); full_sps + 4 < 32 is guaranteed at create
         {
-            const float2 mid = cq_interp(v, m, a.k.half_sps, imu);
-            const float2 prv = cq_interp(v, m, a.k.full_sps, imu);
             const float er = __fsub_rn(curr.x, prv.x), ei = __fsub_rn(curr.y, prv.y);
             // real((e) * conj(mid)) = er*mr - ei*(-mi)
             const float ted = __fsub_rn(__fmul_rn(er, mid.x), __fmul_rn(ei, -mid.y));
             const float adj = __fmul_rn(0.015f, ted);
+            const bool was_f64 = !S.clock_is_f32;
             if (!S.clock_is_f32) {
                 S.clock_f = (float)S.clock_d;   // Python float + np.float32 -> float32
                 S.omega_f = (float)a.k.sps;
@@ -315,8 +365,11 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
             }
             S.clock_f = __fadd_rn(S.clock_f, adj);
             S.omega_f = __fadd_rn(S.omega_f, __fmul_rn(0.0f, ted));
-            S.omega_f = fminf(fmaxf(S.omega_f, omega_lo), omega_hi);
-            S.sym_time_f = __fdiv_rn(1.0f, S.omega_f);
+            const float om = fminf(fmaxf(S.omega_f, omega_lo), omega_hi);
+            if (om != S.omega_f || was_f64) {   // gain_omega is 0 in the reference (:274): omega only moves when ted is not finite
+                S.omega_f = om;
+                S.sym_time_f = __fdiv_rn(1.0f, S.omega_f);
+            }
         }
         while (S.clock_f >= 1.0f) S.clock_f = __fsub_rn(S.clock_f, 1.0f);
         while (S.clock_f < 0.0f) S.clock_f = __fadd_rn(S.clock_f, 1.0f);
@@ -417,17 +470,23 @@ __global__ void cqpsk_slice_kernel(const CqSyncArgs a) {
 // Frequency loop state: freq_offset = clip(freq_offset + delta_k, +-0.02) symbol by symbol (:583-585) — the clip makes it
 // order dependent, so one thread per channel replays the additions (two dependent float64 operations per symbol);
 // previous-symbol / first-symbol state for the next call.
-__global__ void cqpsk_freq_kernel(const CqSyncArgs a) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= a.C) return;
+__global__ void __launch_bounds__(32) cqpsk_freq_kernel(const CqSyncArgs a) {
+    const int ch = blockIdx.x, lane = threadIdx.x;
     const int n = a.n_sym[ch];
     if (n <= 0) return;
     const double* d = a.delta + (long long)ch * a.max_sym;
     double f = a.st[ch].freq_offset;
-    for (int k = 0; k < n; ++k) f = fmin(fmax(f + d[k], -0.02), 0.02);
-    a.st[ch].freq_offset = f;
-    a.st[ch].prev = a.sym[(long long)ch * a.max_sym + n - 1];
-    a.st[ch].first = 0;
+    // one warp per channel: 32 increments per coalesced load, broadcast one by one; every lane replays the same additions
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const double mine = (k0 + lane < n) ? d[k0 + lane] : 0.0;
+        const int cnt = min(32, n - k0);
+        for (int k = 0; k < cnt; ++k) f = fmin(fmax(f + __shfl_sync(0xffffffffu, mine, k), -0.02), 0.02);
+    }
+    if (lane == 0) {
+        a.st[ch].freq_offset = f;
+        a.st[ch].prev = a.sym[(long long)ch * a.max_sym + n - 1];
+        a.st[ch].first = 0;
+    }
 }
 
 __global__ void cqpsk_reset_kernel(CqState* st, int lo, int hi) {
@@ -611,9 +670,9 @@ int wc_cqpsk_demod(wc_cqpsk* h, const void* iq_dev, long long chan_stride, int n
     a.n_sym = n_sym_dev;
     a.sym = h->d_sym;
     a.delta = h->d_delta;
-    cqpsk_sync_kernel<<<(C + 31) / 32, 32, 0, s>>>(a);
+    cqpsk_sync_kernel<<<(C + CQ_CH - 1) / CQ_CH, 32, 0, s>>>(a);
     cqpsk_slice_kernel<<<dim3((max_sym + 127) / 128, C), 128, 0, s>>>(a);
-    cqpsk_freq_kernel<<<(C + 31) / 32, 32, 0, s>>>(a);
+    cqpsk_freq_kernel<<<C, 32, 0, s>>>(a);
     WC_CUDA(cudaGetLastError());
     return 0;
 }
