@@ -120,6 +120,7 @@ typedef struct wc_iir wc_iir;
 int wc_iir_create(const double* b, int nb, const double* a, int na, wc_iir** out);
 void wc_iir_destroy(wc_iir* h);
 int wc_iir_is_sequential(const wc_iir* h);
+int wc_iir_kind(const wc_iir* h);   /* 0 scan chained in double-double, 1 scan chained in float64, 2 sequential replay */
 int wc_iir_lfilter(wc_iir* h, const float* x_dev, float* y_dev, int n, long long seq_stride, int n_seq,
                    int abs_input, void* stream);
 

@@ -165,6 +165,19 @@ def test_ill_conditioned_iirs_replay_lfilter_bit_for_bit(native):
     assert is_seq(F.highpass_coeffs(976_560, 300)) and is_seq(F.highpass_coeffs(48000, 100))
     assert not is_seq(F.lowpass_coeffs(2_400_000, 15000)) and not is_seq(F.highpass_coeffs(48000, 300))
     assert not is_seq(F.notch_coeffs(48000, 1000.0)) and not is_seq(F.lowpass_coeffs(48000, 3000))
+
+    def kind(coeffs):
+        b, a = coeffs
+        return int(N.lib().wc_iir_kind(S.iir_handle(tuple(map(float, b)), tuple(map(float, a))).h))
+
+    from wavecap_sdr_b200.dsp import fm as FMm
+
+    # the C1 chain's filters (one-pole de-emphasis, 15 kHz MPX low-pass) chain their scan in plain float64
+    assert kind(FMm.deemphasis_coeffs(2_400_000)) == 1 and kind(FMm.mpx_coeffs(2_400_000)) == 1
+    assert kind(F.bandpass_coeffs(48000, 300, 3000)) == 2
+    y = rng_check = np.random.default_rng(42).standard_normal(300_000).astype(np.float32)
+    assert rel_rms(FMm.lpf_audio(y, 2_400_000), oa.lpf_audio(y, 2_400_000)) < 1e-6
+    assert rel_rms(FMm.deemphasis_filter(y, 2_400_000), oa.deemphasis_filter(y, 2_400_000)) < 1e-6
     rng = np.random.default_rng(41)
     x = rng.standard_normal((5, 30_011)).astype(np.float32)       # 5 sequences, ragged against the 64-sample staging tile
     for fs, fn, ofn, args in ((10_000_000, F.lowpass_filter, oa.lowpass_filter, (3000,)),

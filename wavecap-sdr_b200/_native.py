@@ -157,6 +157,7 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_iir_create", i32, vp, i32, vp, i32, P(vp))
     fn("wc_iir_destroy", None, vp)
     fn("wc_iir_is_sequential", i32, vp)
+    fn("wc_iir_kind", i32, vp)
     fn("wc_iir_lfilter", i32, vp, vp, vp, i32, i64, i32, i32, vp)
     fn("wc_sumsq", i32, vp, i32, i64, i32, vp, vp)
     fn("wc_elementwise", i32, vp, vp, i64, i32, f32, vp)

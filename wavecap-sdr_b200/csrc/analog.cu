@@ -263,12 +263,17 @@ __device__ __forceinline__ double df2t_step(const double b0, const double (&cb)[
     return y;
 }
 
-// o = M * s + o   (row-major K x K double-double)
-template <int K>
+// o = M * s + o   (row-major K x K double-double). PLAIN: float64 only (the .hi parts) — enough for well-conditioned
+// filters, 20 x fewer FP64 operations per term; chosen per handle at create time (iir_scan_plain_ok).
+template <int K, bool PLAIN>
 __device__ __forceinline__ void dd_matvec_acc(const dd* __restrict__ M, const dd* s, dd* o) {
     for (int r = 0; r < K; ++r) {
         dd acc = o[r];
-        for (int c = 0; c < K; ++c) acc = dd_add(acc, dd_mul(M[r * K + c], s[c]));
+        if (PLAIN) {
+            for (int c = 0; c < K; ++c) acc.hi = fma(M[r * K + c].hi, s[c].hi, acc.hi);
+        } else {
+            for (int c = 0; c < K; ++c) acc = dd_add(acc, dd_mul(M[r * K + c], s[c]));
+        }
         o[r] = acc;
     }
 }
@@ -283,11 +288,14 @@ constexpr size_t iir_smem_bytes() {
 //   -> tile aggregate Z_c (double-double).
 // FINAL = 1 (pass 3): scan again with the true tile-start state S_c folded into segment 0, then
 //   re-run every segment from its true start state and write y.
-template <int K, int FINAL, typename TIn>
+// sumsq (FINAL only, optional): per-sequence sum of the float32 outputs squared, for rms_normalize right after the
+// last stage of a chain (saves the separate pass over the filtered signal).
+template <int K, int FINAL, bool PLAIN, typename TIn>
 __global__ void __launch_bounds__(IIR_T) iir_kernel(const IirCoef* __restrict__ cf, const TIn* __restrict__ x,
                                                     float* __restrict__ y, int n, long long seq_stride,
                                                     double* __restrict__ zseg, dd* __restrict__ ztile,
-                                                    const dd* __restrict__ stile, int tiles, int absin) {
+                                                    const dd* __restrict__ stile, int tiles, int absin,
+                                                    double* __restrict__ sumsq) {
     extern __shared__ __align__(16) unsigned char iir_smem[];
     float* sx = reinterpret_cast<float*>(iir_smem);
     dd* vb = reinterpret_cast<dd*>(iir_smem + ((sizeof(float) * IIR_T * (IIR_L + 1) + 15) & ~size_t(15)));
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(IIR_T) iir_kernel(const IirCoef* __restrict__ 
     if (FINAL) {
 #pragma unroll
         for (int i = 0; i < K; ++i) sc[i] = stile[tix * K + i];
-        if (tid == 0) dd_matvec_acc<K>(sP, sc, v);  // end(seg 0) = P*S_c + z_0
+        if (tid == 0) dd_matvec_acc<K, PLAIN>(sP, sc, v);  // end(seg 0) = P*S_c + z_0
     }
     // Kogge-Stone inclusive scan: v_i <- v_i + P^(2^k) * v_{i-2^k}
     int cur = 0;
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(IIR_T) iir_kernel(const IirCoef* __restrict__ 
         for (int i = 0; i < K; ++i) buf[tid * K + i] = v[i];
         __syncthreads();
         const int d = 1 << k;
-        if (tid >= d) dd_matvec_acc<K>(sP + k * K * K, buf + (tid - d) * K, v);
+        if (tid >= d) dd_matvec_acc<K, PLAIN>(sP + k * K * K, buf + (tid - d) * K, v);
         cur ^= 1;
     }
     if (!FINAL) {
@@ -375,12 +383,21 @@ __global__ void __launch_bounds__(IIR_T) iir_kernel(const IirCoef* __restrict__ 
     }
     __syncthreads();
     float* ys = y + (long long)seq * seq_stride + t0;
-    for (int e = tid; e < cnt; e += IIR_T) ys[e] = sx[(e >> 6) * (IIR_L + 1) + (e & 63)];
+    double ss = 0.0;
+    for (int e = tid; e < cnt; e += IIR_T) {
+        const float v = sx[(e >> 6) * (IIR_L + 1) + (e & 63)];
+        ys[e] = v;
+        ss += (double)(v * v);   // x**2 is float32 in the reference (dsp/fm.py:58)
+    }
+    if (sumsq) {
+        ss = warp_sum(ss);
+        if ((tid & 31) == 0) atomicAdd(sumsq + seq, ss);
+    }
 }
 
 // pass 2: chain tile aggregates in double-double: S_0 = 0, S_{c+1} = PT * S_c + Z_c.
 // One warp per sequence, lane r computes row r.
-template <int K>
+template <int K, bool PLAIN>
 __global__ void iir_chain_kernel(const IirCoef* __restrict__ cf, const dd* __restrict__ ztile,
                                  dd* __restrict__ stile, int tiles, int n_seq) {
     __shared__ dd s_sh[4][IIR_KMAX];
@@ -397,7 +414,11 @@ __global__ void iir_chain_kernel(const IirCoef* __restrict__ cf, const dd* __res
         __syncwarp();
         if (lane < K) {
             dd acc = ztile[off + lane];
-            for (int j = 0; j < K; ++j) acc = dd_add(acc, dd_mul(cf->PT[lane * K + j], s_sh[w][j]));
+            if (PLAIN) {
+                for (int j = 0; j < K; ++j) acc.hi = fma(cf->PT[lane * K + j].hi, s_sh[w][j].hi, acc.hi);
+            } else {
+                for (int j = 0; j < K; ++j) acc = dd_add(acc, dd_mul(cf->PT[lane * K + j], s_sh[w][j]));
+            }
             s = acc;
         }
         __syncwarp();
@@ -917,6 +938,52 @@ static bool iir_needs_sequential(const IirCoef& c) {
     return sqrt(num / den) > 1e-7;
 }
 
+// May the scan chain its segment states in plain float64 (transition powers and states rounded to double) instead of
+// double-double? Measured like iir_needs_sequential: 4096 samples of noise, state chained segment by segment as
+// s' = fl(P s + z) with P = A^64 rounded to float64 and z the segment's zero-state response, outputs re-run from those
+// states, against lfilter's sequential recursion. Well-conditioned filters (one-pole de-emphasis / AGC envelopes, the MPX
+// low-pass) agree to ~1e-12 and take the plain scan: ~20 x fewer FP64 operations per scan term (ncu: the double-double scan
+// was ~3/4 of the kernel's FP64 work for K = 5).
+static bool iir_scan_plain_ok(const IirCoef& c) {
+    const int K = c.K;
+    if (K < 1) return true;
+    const int N = 4096;
+    uint64_t lcg = 0x9E3779B97F4A7C15ull;
+    std::vector<double> zs(K, 0.0), z0(K, 0.0), zr(K, 0.0), sp(K, 0.0), nx(K);
+    double num = 0.0, den = 0.0;
+    for (int n = 0; n < N; ++n) {
+        if ((n & (IIR_L - 1)) == 0) {
+            if (n > 0) {   // chain: state at the end of the previous segment = P * (its start state) + (its zero-state response)
+                for (int r = 0; r < K; ++r) {
+                    double acc = z0[r];
+                    for (int q = 0; q < K; ++q) acc = fma(c.Ppow[0][r * K + q].hi, sp[q], acc);
+                    nx[r] = acc;
+                }
+                sp = nx;
+            }
+            zr = sp;
+            std::fill(z0.begin(), z0.end(), 0.0);
+        }
+        lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+        const double xv = (double)(lcg >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        const double ya = zs[0] + c.b0 * xv;
+        for (int i = 0; i < K - 1; ++i) zs[i] = (zs[i + 1] + xv * c.b[i]) - ya * c.a[i];
+        zs[K - 1] = xv * c.b[K - 1] - ya * c.a[K - 1];
+        const double y0 = fma(c.b0, xv, z0[0]);
+        for (int i = 0; i < K - 1; ++i) z0[i] = fma(c.b[i], xv, fma(-c.a[i], y0, z0[i + 1]));
+        z0[K - 1] = fma(c.b[K - 1], xv, -c.a[K - 1] * y0);
+        const double yc = fma(c.b0, xv, zr[0]);
+        for (int i = 0; i < K - 1; ++i) zr[i] = fma(c.b[i], xv, fma(-c.a[i], yc, zr[i + 1]));
+        zr[K - 1] = fma(c.b[K - 1], xv, -c.a[K - 1] * yc);
+        if (n >= N / 2) {
+            num += (yc - ya) * (yc - ya);
+            den += ya * ya;
+        }
+    }
+    if (!(den > 0.0) || !(num == num)) return false;
+    return sqrt(num / den) < 1e-8;
+}
+
 struct Workspace {
     void* p = nullptr;
     size_t cap = 0;
@@ -934,27 +1001,28 @@ struct Workspace {
     }
 };
 
-template <int K, typename TIn>
+template <int K, bool PLAIN, typename TIn>
 static int launch_iir_k(const IirCoef* d_cf, const TIn* x, float* y, int n, long long seq_stride, int n_seq,
-                        int absin, double* zseg, dd* ztile, dd* stile, int tiles, cudaStream_t st) {
+                        int absin, double* zseg, dd* ztile, dd* stile, int tiles, double* sumsq, cudaStream_t st) {
     const size_t smem = iir_smem_bytes<K>();
     static std::atomic<unsigned long long> done0{0}, done1{0};
-    WC_CUDA(smem_optin(iir_kernel<K, 0, TIn>, (int)smem, done0));
-    WC_CUDA(smem_optin(iir_kernel<K, 1, TIn>, (int)smem, done1));
+    WC_CUDA(smem_optin(iir_kernel<K, 0, PLAIN, TIn>, (int)smem, done0));
+    WC_CUDA(smem_optin(iir_kernel<K, 1, PLAIN, TIn>, (int)smem, done1));
     dim3 grid(tiles, n_seq);
-    iir_kernel<K, 0, TIn><<<grid, IIR_T, smem, st>>>(d_cf, x, y, n, seq_stride, zseg, ztile, stile, tiles, absin);
-    iir_chain_kernel<K><<<(n_seq + 3) / 4, 128, 0, st>>>(d_cf, ztile, stile, tiles, n_seq);
-    iir_kernel<K, 1, TIn><<<grid, IIR_T, smem, st>>>(d_cf, x, y, n, seq_stride, zseg, ztile, stile, tiles, absin);
+    iir_kernel<K, 0, PLAIN, TIn><<<grid, IIR_T, smem, st>>>(d_cf, x, y, n, seq_stride, zseg, ztile, stile, tiles, absin, nullptr);
+    iir_chain_kernel<K, PLAIN><<<(n_seq + 3) / 4, 128, 0, st>>>(d_cf, ztile, stile, tiles, n_seq);
+    iir_kernel<K, 1, PLAIN, TIn><<<grid, IIR_T, smem, st>>>(d_cf, x, y, n, seq_stride, zseg, ztile, stile, tiles, absin, sumsq);
     WC_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <typename TIn>
-static int launch_iir_typed(const IirCoef* d_cf, int K, const TIn* x, float* y, int n, long long seq_stride,
-                            int n_seq, int absin, double* zseg, dd* ztile, dd* stile, int tiles, cudaStream_t st) {
-#define WC_IIR_CASE(KK) \
-    case KK:            \
-        return launch_iir_k<KK, TIn>(d_cf, x, y, n, seq_stride, n_seq, absin, zseg, ztile, stile, tiles, st);
+static int launch_iir_typed(const IirCoef* d_cf, int K, bool plain, const TIn* x, float* y, int n, long long seq_stride,
+                            int n_seq, int absin, double* zseg, dd* ztile, dd* stile, int tiles, double* sumsq, cudaStream_t st) {
+#define WC_IIR_CASE(KK)                                                                                                   \
+    case KK:                                                                                                              \
+        return plain ? launch_iir_k<KK, true, TIn>(d_cf, x, y, n, seq_stride, n_seq, absin, zseg, ztile, stile, tiles, sumsq, st) \
+                     : launch_iir_k<KK, false, TIn>(d_cf, x, y, n, seq_stride, n_seq, absin, zseg, ztile, stile, tiles, sumsq, st);
     switch (K) {
         WC_IIR_CASE(1) WC_IIR_CASE(2) WC_IIR_CASE(3) WC_IIR_CASE(4) WC_IIR_CASE(5) WC_IIR_CASE(6) WC_IIR_CASE(7)
         WC_IIR_CASE(8) WC_IIR_CASE(9) WC_IIR_CASE(10)
@@ -1093,6 +1161,7 @@ struct wc_iir {
     IirCoef h_cf;
     IirCoef* d_cf = nullptr;
     bool sequential = false;   // exact-replay kernel instead of the block scan (iir_needs_sequential)
+    bool plain = false;        // block scan with float64 chaining instead of double-double (iir_scan_plain_ok)
 };
 
 template <int K>
@@ -1124,17 +1193,21 @@ static size_t iir_scan_scratch_bytes(int K, int n, int n_seq) {
 }
 
 // the filter proper on caller-provided scratch (iir_scan_scratch_bytes; unused by the sequential replay)
+// sumsq_dev (optional, zeroed by the caller): per-sequence sum of squares of the float32 output, for the scan flavours;
+// returns 1 in *sumsq_done when it was produced (the sequential replay does not fuse it)
 static int iir_run(const wc_iir* h, const float* x_dev, float* y_dev, int n, long long seq_stride, int n_seq,
-                   int abs_input, void* scratch, cudaStream_t st) {
+                   int abs_input, void* scratch, cudaStream_t st, double* sumsq_dev = nullptr, bool* sumsq_done = nullptr) {
     const int K = h->h_cf.K;
+    if (sumsq_done) *sumsq_done = false;
     if (h->sequential) return launch_iir_seq(h->d_cf, K, x_dev, y_dev, n, seq_stride, n_seq, abs_input, st);
+    if (sumsq_done) *sumsq_done = sumsq_dev != nullptr;
     const int tiles = (n + IIR_TILE - 1) / IIR_TILE;
     const size_t nz = (size_t)n_seq * tiles;
     double* zseg = reinterpret_cast<double*>(scratch);
     dd* ztile = reinterpret_cast<dd*>(zseg + nz * IIR_T * K);
     dd* stile = ztile + nz * K;
-    return launch_iir_typed<float>(h->d_cf, K, x_dev, y_dev, n, seq_stride, n_seq, abs_input, zseg, ztile, stile,
-                                   tiles, st);
+    return launch_iir_typed<float>(h->d_cf, K, h->plain, x_dev, y_dev, n, seq_stride, n_seq, abs_input, zseg, ztile, stile,
+                                   tiles, sumsq_dev, st);
 }
 
 extern "C" {
@@ -1154,12 +1227,15 @@ int wc_iir_create(const double* b, int nb, const double* a, int na, wc_iir** out
     }
     cudaMemcpy(h->d_cf, &h->h_cf, sizeof(IirCoef), cudaMemcpyHostToDevice);
     h->sequential = iir_needs_sequential(h->h_cf);
+    h->plain = !h->sequential && iir_scan_plain_ok(h->h_cf);
     *out = h;
     return 0;
 }
 
 // 1 when the handle runs the sequential exact replay (ill-conditioned tf-form filter), 0 for the block scan
 int wc_iir_is_sequential(const wc_iir* h) { return (h && h->sequential) ? 1 : 0; }
+// 0: block scan chained in double-double, 1: block scan chained in float64, 2: sequential exact replay
+int wc_iir_kind(const wc_iir* h) { return !h ? -1 : h->sequential ? 2 : h->plain ? 1 : 0; }
 
 void wc_iir_destroy(wc_iir* h) {
     if (!h) return;
@@ -1745,17 +1821,22 @@ static int plan_enqueue(wc_analog_plan* p, const void* iq_dev, int B, float* aud
         double* ss = p->d_ss + (size_t)r.first * B;
         double* ap = p->d_apower + (size_t)r.first * B;
         int* inv = p->d_invalid + (size_t)r.first * B;
-        for (const wc_iir* f : r.iir) {
+        bool ss_done = r.iir.empty();   // the front end's sum(out**2) holds only while nothing has changed the signal
+        for (size_t k = 0; k < r.iir.size(); ++k) {
+            const wc_iir* f = r.iir[k];
+            const bool last = (k + 1 == r.iir.size()) && r.kind == 1;
             if (f->h_cf.K == 0) {
                 elementwise_kernel<<<148 * 8, 256, 0, st>>>(x, x, (long long)rows * n, 2, (float)f->h_cf.b0);
-            } else if (int rc = iir_run(f, x, x, n, n, rows, 0, p->d_iir_scratch, st)) {
-                return rc;
+            } else {
+                if (last) WC_CUDA(cudaMemsetAsync(ss, 0, sizeof(double) * rows, st));
+                if (int rc = iir_run(f, x, x, n, n, rows, 0, p->d_iir_scratch, st, last ? ss : nullptr, last ? &ss_done : nullptr))
+                    return rc;
             }
         }
         int epi;
         if (r.kind == 1) {
             epi = WC_EPI_RMS_CLIP;
-            if (!r.iir.empty()) {   // the front end's sum(out**2) only holds when nothing changed the signal since
+            if (!ss_done) {   // the last stage could not fuse it (sequential replay / pure gain)
                 WC_CUDA(cudaMemsetAsync(ss, 0, sizeof(double) * rows, st));
                 int bx = (n + 255) / 256;
                 if (bx > 64) bx = 64;
