@@ -172,8 +172,9 @@ def test_ill_conditioned_iirs_replay_lfilter_bit_for_bit(native):
 
     from wavecap_sdr_b200.dsp import fm as FMm
 
-    # the C1 chain's filters (one-pole de-emphasis, 15 kHz MPX low-pass) chain their scan in plain float64
-    assert kind(FMm.deemphasis_coeffs(2_400_000)) == 1 and kind(FMm.mpx_coeffs(2_400_000)) == 1
+    # one-pole filters (de-emphasis, AGC envelopes) chain their scan in plain float64; the order-5 MPX low-pass (|A^64| ~ 7e5)
+    # needs the double-double chain; the order-10 band-pass is replayed sequentially
+    assert kind(FMm.deemphasis_coeffs(2_400_000)) == 1 and kind(FMm.mpx_coeffs(2_400_000)) == 0
     assert kind(F.bandpass_coeffs(48000, 300, 3000)) == 2
     y = rng_check = np.random.default_rng(42).standard_normal(300_000).astype(np.float32)
     assert rel_rms(FMm.lpf_audio(y, 2_400_000), oa.lpf_audio(y, 2_400_000)) < 1e-6
