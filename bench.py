@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=128, help="50 ms chunks per step (device-resident leg)")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks per step of the host-buffer leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
-    ap.add_argument("--stripe-chunks", type=int, default=64, help="stripe mode: 50 ms chunks per block (one process() call, cut into N slabs)")
+    ap.add_argument("--stripe-chunks", type=int, default=128, help="stripe mode: 50 ms chunks per block (one process() call, cut into N slabs)")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "broadcast", "pull", "stripe"],
                     help="replicas: one independent capture per GPU (headline, weak scaling); broadcast: ONE capture, "
                          "each block NCCL-broadcast from rank 0 and time-sharded over the ranks (north-star-literal, strong); "
