@@ -334,6 +334,20 @@ def test_one_call_plan_equals_the_stage_path_and_replays_its_graph(native):
         same(process_channels_batch(x, fs, cfgs, n_chunks=B, apply_squelch=True), ref)
         got = process_channels_batch(xd, fs, cfgs, n_chunks=B, apply_squelch=True, return_device=True)
         same([[(a.cpu().numpy() if a is not None else None, m) for a, m in row] for row in got], ref)
+    # on a non-default stream the plan captures its launch sequence on the second call with the same buffers and replays
+    # the graph afterwards (the legacy default stream cannot be captured, so the calls above all ran eagerly)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        xs = torch.from_numpy(x).cuda()
+        for rep in range(5):                                     # eager, capture + launch, replay x3
+            got = process_channels_batch(xs, fs, cfgs, n_chunks=B, apply_squelch=True, return_device=True)
+            side.synchronize()
+            same([[(a.cpu().numpy() if a is not None else None, m) for a, m in row] for row in got], ref)
+        # a single small chunk through the same plan object family (different n_chunks -> buffers re-reserved, graphs rebuilt)
+        one = process_channels_batch(xs[:n], fs, cfgs, n_chunks=1, apply_squelch=True)
+        same(one, ref[:1])
+        for rep in range(3):
+            same(process_channels_batch(xs[:n], fs, cfgs, n_chunks=1, apply_squelch=True), ref[:1])
     # int16 input
     q = np.stack([np.clip(x.real, -1, 1), np.clip(x.imag, -1, 1)], axis=1)
     q = (np.nan_to_num(q, posinf=0.0) * 20000).astype(np.int16)

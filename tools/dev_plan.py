@@ -33,10 +33,20 @@ def case(name, x, fs, cfgs, B, fmt):
     plan = AP.get_plan(fs, n, S.FMT_CS16 if fmt == "cs16" else S.FMT_CF32, modes, [float(c.offset_hz) for c in cfgs], [0.0] * len(cfgs),
                        [c.squelch_db for c in cfgs], chains)
     xr = x.reshape(B, n, 2) if fmt == "cs16" else x.reshape(B, n)
-    c = timeit(lambda: plan.run(xr, B))
-    N.check(N.lib().wc_analog_plan_use_graph(plan._h, 0))
-    d = timeit(lambda: plan.run(xr, B))
-    N.check(N.lib().wc_analog_plan_use_graph(plan._h, 1))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):        # graphs need a capturable (non-legacy) stream
+        c = timeit(lambda: plan.run(xr, B))
+        N.check(N.lib().wc_analog_plan_use_graph(plan._h, 0))
+        d = timeit(lambda: plan.run(xr, B))
+        N.check(N.lib().wc_analog_plan_use_graph(plan._h, 1))
+        if B > 1:                        # one chunk per call: where launch overhead matters
+            x1 = xr[:1].contiguous()
+            g1 = timeit(lambda: plan.run(x1, 1), iters=100)
+            N.check(N.lib().wc_analog_plan_use_graph(plan._h, 0))
+            e1 = timeit(lambda: plan.run(x1, 1), iters=100)
+            N.check(N.lib().wc_analog_plan_use_graph(plan._h, 1))
+            print(f"{name} single chunk: graph {g1[0]:.4f} ms (host {g1[1]:.4f}) | eager {e1[0]:.4f} ms (host {e1[1]:.4f})", flush=True)
     print(f"{name}: stage path {a[0]:.3f} ms (host {a[1]:.3f}) | process_channels_batch via plan {b[0]:.3f} (host {b[1]:.3f}) | "
           f"bare wc_analog_run graph {c[0]:.3f} (host {c[1]:.3f}) | bare eager {d[0]:.3f} (host {d[1]:.3f})", flush=True)
 
