@@ -272,7 +272,21 @@ __device__ __forceinline__ void dd_matvec_acc(const dd* __restrict__ M, const dd
         if (PLAIN) {
             for (int c = 0; c < K; ++c) acc.hi = fma(M[r * K + c].hi, s[c].hi, acc.hi);
         } else {
-            for (int c = 0; c < K; ++c) acc = dd_add(acc, dd_mul(M[r * K + c], s[c]));
+            // compensated dot product (Dot2 style): exact product error by FMA, the running high part by two_sum, all low-order
+            // terms collected in one float64 and folded back once per row — double-double accuracy for the K-term sum at 12
+            // FP64 operations per term instead of 28 for a full dd_mul + dd_add (the scan is ~6/7 of this kernel's FP64 work)
+            double hi = acc.hi, lo = acc.lo;
+            for (int c = 0; c < K; ++c) {
+                const dd m = M[r * K + c], v = s[c];
+                const double p = m.hi * v.hi;
+                double e = fma(m.hi, v.hi, -p);
+                e = fma(m.hi, v.lo, e);
+                e = fma(m.lo, v.hi, e);
+                const dd t = dd_two_sum(hi, p);
+                hi = t.hi;
+                lo += t.lo + e;
+            }
+            acc = dd_quick(hi, lo);
         }
         o[r] = acc;
     }
