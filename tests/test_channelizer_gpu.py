@@ -362,3 +362,27 @@ def test_audio_mode_cs16_batched_host_and_device(native):
     frames = o.process_vectorized(oa.cs16_to_cf32(q[:n]))
     exp = _audio_oracle(frames[:, 18:23], 976560, 48828)
     assert rel_rms(host[:61, 20], exp[:, 2]) < TOL
+
+
+@pytest.mark.parametrize("frames", [1, 6, 19, 20, 21, 41, 97])
+def test_audio_mode_short_calls(native, frames):
+    """audio mode on calls shorter than the 401-tap resampler / a decimation period: zero extension at both ends, one
+    output for fewer than 20 frames, ceil(F / 20) in general — against nbfm_demod of the oracle's frames."""
+    fs, bw = 125_000_000, 488281
+    n = 256 + 128 * (frames - 1) + 13
+    rng = np.random.default_rng(900 + frames)
+    t = np.arange(n)
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.01
+         + 0.3 * np.exp(1j * (2 * np.pi * 7 * 488281.25 / fs * t + 4.0 * np.sin(2 * np.pi * 3e-5 * t)))).astype(np.complex64)
+    got = _chan(native, fs, bw).process_audio(x)
+    fr = ChannelizerOracle(fs, bw).process_vectorized(x)
+    assert fr.shape[0] == frames and got.shape == (-(-frames // 20), 256)
+    exp = _audio_oracle(fr[:, 5:10], 976560, 48828)
+    skip = set((_knife_edge_channels(fr[:, 5:10]) + 5).tolist())
+    for k in range(5, 10):
+        if k not in skip:
+            # a one-frame call has a single discriminator sample (0 by definition): rms below min_rms, audio 0 on both sides
+            if np.max(np.abs(exp[:, k - 5])) == 0:
+                assert np.max(np.abs(got[:, k])) == 0
+            else:
+                assert rel_rms(got[:, k], exp[:, k - 5]) < TOL, (frames, k)
