@@ -121,3 +121,105 @@ def test_broadcast_time_slabs_gloo_world2():
         got[f0:f1] = part
     # slab 0 starts at frame 0 with the same (zero) history as the unsharded run; slab 1 is halo-complete
     assert np.array_equal(got, full)
+
+
+# ---- one capture striped at ingest (sharding.stripe_layout / StripedCapture): host logic on CPU, gloo world 2 ------------
+
+def test_stripe_layout_geometry():
+    from wavecap_sdr_b200.sharding import stripe_layout
+
+    for frames, world in ((48827, 8), (3124999, 8), (1500, 3), (390624, 2), (97, 1)):
+        L = stripe_layout(frames, world)
+        assert L.f0[0] == 0 and L.f1[-1] == frames and all(a == b for a, b in zip(L.f1[:-1], L.f0[1:]))
+        for r in range(world):
+            assert L.own0[r] == 128 * L.f0[r] and L.own0[r] + L.own_n[r] == 128 * (L.f1[r] - 1) + 256
+            if r:
+                # the halo sits entirely inside the previous rank's own part and ends where this rank's own part begins
+                assert 0 <= L.halo_src(r) and L.halo_src(r) + L.halo == L.own0[r] - L.own0[r - 1] <= L.own_n[r - 1]
+        assert L.tail_n == 1280 and 0 <= L.tail_src() and L.tail_src() + L.tail_n == L.own_n[-1]
+    with pytest.raises(ValueError):
+        stripe_layout(40, 8)
+
+
+def _stripe_worker(rank, world, port, n, q):
+    """every rank holds ONLY its own slab of each block; halo / tail travel by send/recv; the oracle stands in for the kernel"""
+    import torch
+    import torch.distributed as dist
+
+    from oracle.channelizer import ChannelizerOracle, channelize_fm
+    from wavecap_sdr_b200.sharding import stripe_layout
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        F = (n - 256) // 128 + 1
+        L = stripe_layout(F, world)
+        out = []
+        prev_tail = None
+        for blk in range(2):
+            rng = np.random.default_rng(500 + blk)                    # the "ingest": every rank cuts its slab out of the block
+            full = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.5).astype(np.complex64)
+            own = full[L.own0[rank]: L.own0[rank] + L.own_n[rank]].copy()
+            del full
+            o = ChannelizerOracle(125_000_000, 488281)
+            rate = int(o.channel_sample_rate)
+            # message order without cycles: receive my halo, serve the next rank's, the last rank ships the block's tail to
+            # rank 0 (which collects it after its own work)
+            halo = None
+            if rank > 0:
+                buf = torch.zeros(2 * L.halo, dtype=torch.float32)
+                dist.recv(buf, src=rank - 1)
+                halo = buf.numpy().view(np.complex64).copy()
+            if rank + 1 < world:                                      # serve the next rank's halo out of my own part
+                h = own[L.halo_src(rank + 1): L.halo_src(rank + 1) + L.halo]
+                dist.send(torch.from_numpy(np.ascontiguousarray(h).view(np.float32).copy()), dst=rank + 1)
+            if rank == world - 1 and world > 1:                       # the block's tail goes to rank 0 for its next block
+                t = own[L.tail_src(): L.tail_src() + L.tail_n]
+                dist.send(torch.from_numpy(np.ascontiguousarray(t).view(np.float32).copy()), dst=0)
+            if rank == 0:
+                if prev_tail is not None:
+                    # carried history: arm_history[:, j] = the 256-sample block fed j frames ago = tail rows (8 - j, 9 - j)
+                    hist = np.stack([prev_tail[(8 - j) * 128: (8 - j) * 128 + 256] for j in range(9)], axis=1)
+                    o.arm_history = hist.astype(np.complex64)
+                rows = channelize_fm(o.process_vectorized(own), rate)
+                if world > 1:
+                    buf = torch.zeros(2 * L.tail_n, dtype=torch.float32)
+                    dist.recv(buf, src=world - 1)
+                    prev_tail = buf.numpy().view(np.complex64).copy()
+                else:
+                    prev_tail = own[L.tail_src(): L.tail_src() + L.tail_n].copy()
+            else:
+                local = np.concatenate([halo, own])
+                rows = channelize_fm(o.process_vectorized(local), rate)[9:]
+            out.append((rows, L.f0[rank]))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_striped_capture_gloo_world2():
+    import torch.multiprocessing as mp
+
+    from oracle.channelizer import ChannelizerOracle, channelize_fm
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    world, n = 2, 256 + 128 * 149 + 40
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_stripe_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = ChannelizerOracle(125_000_000, 488281)
+    for blk in range(2):
+        rng = np.random.default_rng(500 + blk)
+        full = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.5).astype(np.complex64)
+        exp = channelize_fm(o.process_vectorized(full), int(o.channel_sample_rate))
+        got = np.concatenate([res[r][blk][0] for r in range(world)])
+        assert got.shape == exp.shape and np.array_equal(got, exp), f"block {blk}"

@@ -252,6 +252,37 @@ class PeerRegion:
             N.check(N.lib().wc_peer_close(C.c_void_p(self.base)))
 
 
+@dataclass(frozen=True)
+class StripeLayout:
+    """Where the samples of one block (one process() call of `frames` frames, hop 128, frame 256) live when the block is
+    striped over `world` ranks, and what each rank fetches from its neighbour (all offsets in samples of the block)."""
+    frames: int
+    f0: tuple        # first frame each rank emits
+    f1: tuple        # one past the last
+    own0: tuple      # first sample of each rank's own part: 128 * f0
+    own_n: tuple     # samples of the own part: its frames' rows, (f1 - 1 - f0) * 128 + 256
+    halo: int        # samples a rank > 0 needs in front of its own part (from rank r - 1): 9 hop rows
+    tail0: int       # first sample of the (T + 1)-row tail of the block that rank 0 installs as carried history next block
+    tail_n: int
+
+    def halo_src(self, r: int) -> int:
+        """offset of rank r's halo inside rank r - 1's own part"""
+        return self.own0[r] - self.halo - self.own0[r - 1]
+
+    def tail_src(self) -> int:
+        """offset of the block's tail inside the last rank's own part"""
+        return self.tail0 - self.own0[-1]
+
+
+def stripe_layout(frames: int, world: int) -> StripeLayout:
+    slabs = [frame_slab(frames, world, r, halo=0) for r in range(world)]
+    if any(s.n_frames <= CHAN_HALO_FRAMES + 1 for s in slabs):
+        raise ValueError("block too short for this many ranks")
+    return StripeLayout(frames, tuple(s.f0 for s in slabs), tuple(s.f1 for s in slabs), tuple(128 * s.f0 for s in slabs),
+                        tuple((s.f1 - 1 - s.f0) * 128 + 256 for s in slabs), CHAN_HALO_FRAMES * 128,
+                        (frames - CHAN_HALO_FRAMES) * 128, (CHAN_HALO_FRAMES + 1) * 128)
+
+
 class StripedCapture:
     """ONE capture over all ranks, striped at ingest: every block (= one `PolyphaseChannelizer.process()` call of
     `block_samples` samples) is cut into `world` time slabs and slab r is delivered straight into rank r's memory (its own
@@ -279,10 +310,10 @@ class StripedCapture:
         self.block_samples = int(block_samples)
         self.frames = chan.frames_for(self.block_samples)
         self.slabs = [frame_slab(self.frames, self.world, r, halo=0) for r in range(self.world)]
-        assert all(s.n_frames > CHAN_HALO_FRAMES + 1 for s in self.slabs), "block too short for this many ranks"
+        self.layout = stripe_layout(self.frames, self.world)
         # own part of rank r: the samples its frames [f0, f1) cover = [128 f0, 128 (f1 - 1) + 256)
-        self.own0 = [128 * s.f0 for s in self.slabs]
-        self.own_n = [(s.f1 - 1 - s.f0) * 128 + 256 for s in self.slabs]
+        self.own0 = list(self.layout.own0)
+        self.own_n = list(self.layout.own_n)
         self.stride = self.AREA + ((max(self.own_n) + 15) & ~15)      # samples per buffer
         self.regions = [PeerRegion(8 * 2 * self.stride, src=r, group=group) for r in range(self.world)]
         self.mine = self.regions[self.rank]
@@ -340,7 +371,7 @@ class StripedCapture:
                 pb = (i - 1) & 1
                 if W > 1:
                     last.wait_flags(self.READY + pb, 1, seq - 1, timeout_ms=timeout_ms)
-                tail_off = pb * self.stride + self.AREA + ((self.frames - CHAN_HALO_FRAMES) * 128 - self.own0[W - 1])
+                tail_off = pb * self.stride + self.AREA + self.layout.tail_src()
                 dst = self.mine.payload_ptr(8 * (b * self.stride))          # the area in front of my own part
                 N.check(lib.wc_peer_copy(C.c_void_p(dst), C.c_void_p(last.payload_ptr(8 * tail_off)), 8 * self.AREA, st))
                 if W > 1:
@@ -356,7 +387,7 @@ class StripedCapture:
             prev = self.regions[r - 1]
             prev.wait_flags(self.READY + b, 1, seq, timeout_ms=timeout_ms)
             halo = self.HALO_ROWS * 128
-            src_off = b * self.stride + self.AREA + (self.own0[r] - halo - self.own0[r - 1])
+            src_off = b * self.stride + self.AREA + self.layout.halo_src(r)
             dst = own_ptr - 8 * halo
             N.check(lib.wc_peer_copy(C.c_void_p(dst), C.c_void_p(prev.payload_ptr(8 * src_off)), 8 * halo, st))
             prev.set_flag(self.DONE + b, seq)
