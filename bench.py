@@ -64,7 +64,8 @@ def parse_args():
     ap.add_argument("--bcast-chunks", type=int, default=8, help="50 ms chunks per broadcast block")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1-C4 `configs` legs (N=1 only)")
-    ap.add_argument("--no-one-capture", action="store_true", help="N>1: skip the `one_capture` (pull-mode) leg")
+    ap.add_argument("--no-one-capture", action="store_true", help="N>1: skip the `one_capture` (stripe / pull) legs")
+    ap.add_argument("--no-modes", action="store_true", help="skip the int16 / audio e2e modes (profiling runs)")
     ap.add_argument("--sustained-seconds", type=float, default=2.5,
                     help="extra back-to-back C5 steps after the K timed ones, for the sustained number (0 = off)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="cpu_baseline: seconds of CPU work per core (C5)")
@@ -819,6 +820,8 @@ def main():
 
     e2e_modes = {}
     try:
+        if args.no_modes:
+            raise RuntimeError("skipped (--no-modes)")
         hq = N.pinned_empty((eb * CHUNK, 2), "int16")
         hq[:CHUNK] = np.clip(np.stack([hx[:CHUNK].real, hx[:CHUNK].imag], axis=1) * 8192.0, -32767, 32767).astype(np.int16)
         for i in range(1, eb):

@@ -22,7 +22,7 @@ if build_ref.staged():
 else:
     print("oracle/_ref not staged")
 PY
-B="python bench.py --steps 2 --warmup 3 --chunks 16 --e2e-chunks 2 --no-cpu --no-configs --sustained-seconds 0"
+B="python bench.py --steps 2 --warmup 3 --chunks 16 --e2e-chunks 2 --no-cpu --no-configs --no-modes --sustained-seconds 0"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv $B > $O/r02/ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:chan256p -c 2 -o $O/prof_chan_fm -f $B > $O/r02/ncu2.log 2>&1
 ncu -i $O/prof_chan_fm.ncu-rep --page raw --csv > $O/raw.csv 2>/dev/null
