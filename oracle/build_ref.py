@@ -1,64 +1,105 @@
 """Recipe: make the UNMODIFIED reference runnable on the GPU box as the checker / CPU baseline.
 
-Test infrastructure only. The reference is pure Python, so "building" it is staging its own files where they can
-travel: `/root/reference/backend/wavecapsdr/**/*.py` and `/root/reference/backend/benchmark_dsp.py` are copied
-byte for byte into `oracle/_ref/backend/` — git-ignored (no reference source ever enters the history), NOT
-gpurun-ignored (so the copy ships with the snapshot like the built .so). `__graft_entry__.build()` runs this when
-`/root/reference` is present (the build container); on the GPU box only the staged copy is used:
+Test infrastructure only. The reference is pure Python, so "building" it is packing its own files where they can
+travel: `/root/reference/backend/wavecapsdr/**/*.py` (+ its json/yaml data files) and
+`/root/reference/backend/benchmark_dsp.py` go, byte for byte, into ONE archive `oracle/_ref/reference_backend.tar` —
+git-ignored (no reference source ever enters the history or sits in the tree as source files), NOT gpurun-ignored (the
+archive ships with the snapshot like the built .so). `__graft_entry__.build()` runs this when `/root/reference` is present
+(the build container). At run time `load()` unpacks the archive into a scratch directory under the system temp dir
+(once per archive version; real files, so numba's `cache=True` kernels work) and puts it on `sys.path`:
 
   * tests/test_reference_benchmark_gpu.py runs the reference's own backend/benchmark_dsp.py against
-    wavecap_sdr_b200.install();
-  * bench.py --impl reference / cpu_baseline time the reference's own PolyphaseChannelizer.process + quadrature_demod
-    on the box's host cores (`cpu_baseline.kind: "reference"`); without the copy they fall back to the oracle port.
+    wavecap_sdr_b200.install() and compares the rebound functions with the original ones executed on the box's CPU;
+  * bench.py --impl reference / cpu_baseline time the reference's own functions on the box's host cores
+    (`cpu_baseline.kind: "reference"`); without the archive they fall back to the oracle port.
 
 Nothing under wavecap-sdr_b200/ may import from here.
 """
 from __future__ import annotations
 
+import hashlib
+import io
 import os
-import shutil
 import sys
+import tarfile
+import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference/backend"
-DST = os.path.join(ROOT, "oracle", "_ref", "backend")
+ARCHIVE = os.path.join(ROOT, "oracle", "_ref", "reference_backend.tar")
+_loaded_dir: str | None = None
 
 
 def staged() -> bool:
-    return os.path.isfile(os.path.join(DST, "wavecapsdr", "dsp", "channelizer.py"))
+    return os.path.isfile(ARCHIVE)
 
 
 def build(verbose: bool = False) -> bool:
-    """Stage the reference when /root/reference exists; returns whether a staged copy is available afterwards."""
+    """Pack the reference when /root/reference exists; returns whether an archive is available afterwards."""
     if not os.path.isdir(os.path.join(SRC, "wavecapsdr")):
         return staged()
-    n = 0
-    for base, _dirs, files in os.walk(os.path.join(SRC, "wavecapsdr")):
-        if "__pycache__" in base:
-            continue
-        rel = os.path.relpath(base, SRC)
-        for f in files:
-            if not f.endswith((".py", ".json", ".yaml", ".yml")):
-                continue
-            os.makedirs(os.path.join(DST, rel), exist_ok=True)
-            shutil.copyfile(os.path.join(base, f), os.path.join(DST, rel, f))
-            n += 1
-    shutil.copyfile(os.path.join(SRC, "benchmark_dsp.py"), os.path.join(DST, "benchmark_dsp.py"))
+    os.makedirs(os.path.dirname(ARCHIVE), exist_ok=True)
+    members = []
+    for base, dirs, files in os.walk(os.path.join(SRC, "wavecapsdr")):
+        dirs[:] = sorted(d for d in dirs if d != "__pycache__")
+        for f in sorted(files):
+            if f.endswith((".py", ".json", ".yaml", ".yml")):
+                members.append(os.path.join(base, f))
+    members.append(os.path.join(SRC, "benchmark_dsp.py"))
+    buf = io.BytesIO()
+    with tarfile.open(fileobj=buf, mode="w") as tar:        # deterministic: sorted members, zeroed metadata
+        for path in members:
+            info = tar.gettarinfo(path, arcname=os.path.join("backend", os.path.relpath(path, SRC)))
+            info.mtime, info.uid, info.gid, info.uname, info.gname = 0, 0, 0, "", ""
+            with open(path, "rb") as fh:
+                tar.addfile(info, fh)
+    data = buf.getvalue()
+    if not (os.path.isfile(ARCHIVE) and open(ARCHIVE, "rb").read() == data):
+        with open(ARCHIVE, "wb") as fh:
+            fh.write(data)
     if verbose:
-        print(f"staged {n + 1} reference files under {DST}")
+        print(f"packed {len(members)} reference files into {ARCHIVE} ({len(data)} bytes)")
     return True
 
 
+def unpacked_dir() -> str:
+    """<tmp>/wcsdr_b200_ref_<digest>/backend, unpacking the archive there on first use (atomic rename: safe under many
+    concurrent worker processes)."""
+    global _loaded_dir
+    if _loaded_dir and os.path.isdir(_loaded_dir):
+        return _loaded_dir
+    if not staged():
+        raise RuntimeError("oracle/_ref/reference_backend.tar is missing (run oracle/build_ref.py in the build container)")
+    with open(ARCHIVE, "rb") as fh:
+        digest = hashlib.sha1(fh.read()).hexdigest()[:16]
+    final = os.path.join(tempfile.gettempdir(), f"wcsdr_b200_ref_{digest}")
+    if not os.path.isdir(os.path.join(final, "backend", "wavecapsdr")):
+        tmp = tempfile.mkdtemp(prefix="wcsdr_b200_ref_unpack_")
+        with tarfile.open(ARCHIVE) as tar:
+            tar.extractall(tmp)
+        try:
+            os.rename(tmp, final)
+        except OSError:                                      # another process won the race
+            import shutil
+
+            shutil.rmtree(tmp, ignore_errors=True)
+    _loaded_dir = os.path.join(final, "backend")
+    return _loaded_dir
+
+
+def benchmark_script() -> str:
+    return os.path.join(unpacked_dir(), "benchmark_dsp.py")
+
+
 def load():
-    """Import the staged reference (SURVEY §8c recipe: trunking before capture). Returns the wavecapsdr package."""
+    """Import the packed reference (SURVEY §8c recipe: trunking before capture). Returns the wavecapsdr package."""
     import logging
 
-    if not staged():
-        raise RuntimeError("oracle/_ref is not staged (run oracle/build_ref.py in the build container)")
+    d = unpacked_dir()
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
     sys.dont_write_bytecode = True
-    if DST not in sys.path:
-        sys.path.insert(0, DST)
+    if d not in sys.path:
+        sys.path.insert(0, d)
     logging.disable(logging.CRITICAL)
     import wavecapsdr.trunking  # noqa: F401
     import wavecapsdr.capture  # noqa: F401
@@ -66,4 +107,4 @@ def load():
 
 
 if __name__ == "__main__":
-    print("staged" if build(verbose=True) else "reference not available")
+    print("packed" if build(verbose=True) else "reference not available")

@@ -5,8 +5,9 @@ implementation and its five benchmark functions run to completion and meet the t
 (channelizer >= 8 MS/s, C4FM >= 50 kS/s per channel). The same session also compares the rebound functions with the
 ORIGINAL reference functions executed on the box's CPU (live parity, not a golden file).
 
-The reference travels as oracle/_ref (staged by oracle/build_ref.py from /root/reference in the build container;
-git-ignored, shipped with the snapshot). Without it the test is skipped."""
+The reference travels as one archive, oracle/_ref/reference_backend.tar (packed by oracle/build_ref.py from /root/reference in
+the build container; git-ignored, shipped with the snapshot, unpacked into the temp dir at run time). Without it the test is
+skipped."""
 import importlib.util
 import os
 
@@ -36,7 +37,7 @@ def installed(native):
 
 
 def _script():
-    path = os.path.join(build_ref.DST, "benchmark_dsp.py")
+    path = build_ref.benchmark_script()
     spec = importlib.util.spec_from_file_location("reference_benchmark_dsp", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

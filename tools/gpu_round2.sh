@@ -18,7 +18,7 @@ if build_ref.staged():
     import wavecap_sdr_b200.install as b200
     print("rebound:", len(b200.install(0)), "names")
     sys.argv = ["benchmark_dsp.py"]
-    runpy.run_path(os.path.join(build_ref.DST, "benchmark_dsp.py"), run_name="__main__")
+    runpy.run_path(build_ref.benchmark_script(), run_name="__main__")
 else:
     print("oracle/_ref not staged")
 PY
