@@ -76,7 +76,7 @@ def unpacked_dir() -> str:
     if not os.path.isdir(os.path.join(final, "backend", "wavecapsdr")):
         tmp = tempfile.mkdtemp(prefix="wcsdr_b200_ref_unpack_")
         with tarfile.open(ARCHIVE) as tar:
-            tar.extractall(tmp)
+            tar.extractall(tmp, filter="data")
         try:
             os.rename(tmp, final)
         except OSError:                                      # another process won the race

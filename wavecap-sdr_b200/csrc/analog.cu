@@ -60,13 +60,38 @@ struct FrontArgs {
 
 // nco_f32 (capture.freq_shift's float32-phase oscillator) lives in common.cuh
 
+// The same oscillator for the front end's sample loop, where it is a quarter of the instruction stream: theta =
+// fl32(k32 * fl32(n)) exactly as numpy forms it, reduced to turns in float-float arithmetic (as nco_f32f), then
+// cos/sin from a 256-entry table (shared memory, one 8-byte load) times a small-angle rotation for the remaining
+// |delta| <= 2 pi / 512: sin d = d (1 - d^2/6) and cos d = 1 - d^2/2 + d^4/24 are exact to 2e-12 there, the table entries to
+// float32 rounding — the accuracy class of sincospif at about half its instructions (no quadrant logic, two short
+// polynomials instead of two long ones).
+constexpr int NCO_TAB = 256;
+__device__ __forceinline__ void nco_f32f_tab(float k32, float nf, const float2* __restrict__ tab, float& c, float& s) {
+    const float th = __fmul_rn(k32, nf);
+    const float C_HI = 0.15915493667125702f, C_LO = 6.4206382432985265e-09f;   // 1/(2 pi) = C_HI + C_LO
+    const float hi = __fmul_rn(th, C_HI);
+    const float e = __fmaf_rn(th, C_HI, -hi);
+    const float lo = __fmaf_rn(th, C_LO, e);
+    const float fr = __fadd_rn(__fsub_rn(hi, rintf(hi)), lo);        // turns, |fr| <= 0.5 (+ a few ulp)
+    const float kf = rintf(fr * (float)NCO_TAB);
+    const float rem = fmaf(kf, -1.0f / (float)NCO_TAB, fr);           // exact: |rem| <= 1 / 512 turn
+    const float2 t = tab[(int)kf & (NCO_TAB - 1)];                    // (cos, sin)(2 pi k / 256); k = -128 and 128 share an entry
+    const float d = rem * 6.283185307179586f;
+    const float d2 = d * d;
+    const float sd = d * fmaf(d2, -1.0f / 6.0f, 1.0f);
+    const float cd = fmaf(d2, fmaf(d2, 1.0f / 24.0f, -0.5f), 1.0f);
+    c = fmaf(t.x, cd, -t.y * sd);
+    s = fmaf(t.y, cd, t.x * sd);
+}
+
 // One channel over one staged tile, specialised on what the channel needs so that the sample loop carries no mode
 // tests (ncu: the generic loop spent 14 of its 200 instructions per sample on branches). KIND: 0 = power only (NONE /
 // RAW), 1 = FM discriminator, 2 = AM envelope, 3 = SSB product. Returns this thread's float32 partials of
 // (sum |base|^2, sum out^2).
 template <int KIND, bool SHIFT, bool BASE>
-__device__ __forceinline__ float2 front_tile(const FrontArgs& a, const FrontChan& ch, const float2* tile, int t0, int cnt,
-                                            long long obase, int tid) {
+__device__ __forceinline__ float2 front_tile(const FrontArgs& a, const FrontChan& ch, const float2* tile, const float2* nco_tab,
+                                            int t0, int cnt, long long obase, int tid) {
     float psum32 = 0.f, osum32 = 0.f;   // this thread's <= 16 samples of the tile; everything above that level is float64
     const bool exact_idx = (t0 + FR_TILE) <= (1 << 24);   // float32 index by exact increments (numpy's float32 arange)
     // Each warp walks its own contiguous segment of the tile, 32 consecutive samples per step (coalesced stores). The FM
@@ -96,7 +121,7 @@ __device__ __forceinline__ float2 front_tile(const FrontArgs& a, const FrontChan
             float2 b1 = live ? tile[i + 1] : make_float2(0.f, 0.f);
             if (SHIFT) {
                 float c1, s1;
-                nco_f32f(ch.k32, exact_idx ? nf : (float)n, c1, s1);
+                nco_f32f_tab(ch.k32, exact_idx ? nf : (float)n, nco_tab, c1, s1);
                 b1 = make_float2(b1.x * c1 - b1.y * s1, b1.x * s1 + b1.y * c1);
             }
             float o = 0.f;
@@ -136,20 +161,26 @@ __device__ __forceinline__ float2 front_tile(const FrontArgs& a, const FrontChan
 }
 
 template <int KIND>
-__device__ __forceinline__ float2 front_tile_dispatch(const FrontArgs& a, const FrontChan& ch, const float2* tile, int t0,
-                                                     int cnt, long long obase, int tid) {
+__device__ __forceinline__ float2 front_tile_dispatch(const FrontArgs& a, const FrontChan& ch, const float2* tile,
+                                                     const float2* nco_tab, int t0, int cnt, long long obase, int tid) {
     if (ch.shift) {
-        return a.base_out ? front_tile<KIND, true, true>(a, ch, tile, t0, cnt, obase, tid)
-                          : front_tile<KIND, true, false>(a, ch, tile, t0, cnt, obase, tid);
+        return a.base_out ? front_tile<KIND, true, true>(a, ch, tile, nco_tab, t0, cnt, obase, tid)
+                          : front_tile<KIND, true, false>(a, ch, tile, nco_tab, t0, cnt, obase, tid);
     }
-    return a.base_out ? front_tile<KIND, false, true>(a, ch, tile, t0, cnt, obase, tid)
-                      : front_tile<KIND, false, false>(a, ch, tile, t0, cnt, obase, tid);
+    return a.base_out ? front_tile<KIND, false, true>(a, ch, tile, nco_tab, t0, cnt, obase, tid)
+                      : front_tile<KIND, false, false>(a, ch, tile, nco_tab, t0, cnt, obase, tid);
 }
 
 __global__ void __launch_bounds__(FR_THREADS, 4) front_kernel(const FrontArgs a) {
     __shared__ float2 tile[FR_TILE + 1];
+    __shared__ float2 nco_tab[NCO_TAB];
     __shared__ double red[FR_THREADS / 32];
     __shared__ double red2[FR_THREADS / 32];
+    for (int i = threadIdx.x; i < NCO_TAB; i += FR_THREADS) {
+        float sv, cv;
+        sincospif((float)i * (2.0f / (float)NCO_TAB), &sv, &cv);
+        nco_tab[i] = make_float2(cv, sv);
+    }
     const int chunk = blockIdx.y;
     const int t0 = blockIdx.x * FR_TILE;
     const int cnt = min(FR_TILE, a.n - t0);
@@ -177,10 +208,10 @@ __global__ void __launch_bounds__(FR_THREADS, 4) front_kernel(const FrontArgs a)
         const FrontChan ch = a.ch[c];
         const long long obase = ((long long)c * a.n_chunks + chunk) * a.n;
         float2 p32;
-        if (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM) p32 = front_tile_dispatch<1>(a, ch, tile, t0, cnt, obase, tid);
-        else if (ch.mode == WC_MODE_AM) p32 = front_tile_dispatch<2>(a, ch, tile, t0, cnt, obase, tid);
-        else if (ch.mode == WC_MODE_SSB) p32 = front_tile_dispatch<3>(a, ch, tile, t0, cnt, obase, tid);
-        else p32 = front_tile_dispatch<0>(a, ch, tile, t0, cnt, obase, tid);
+        if (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM) p32 = front_tile_dispatch<1>(a, ch, tile, nco_tab, t0, cnt, obase, tid);
+        else if (ch.mode == WC_MODE_AM) p32 = front_tile_dispatch<2>(a, ch, tile, nco_tab, t0, cnt, obase, tid);
+        else if (ch.mode == WC_MODE_SSB) p32 = front_tile_dispatch<3>(a, ch, tile, nco_tab, t0, cnt, obase, tid);
+        else p32 = front_tile_dispatch<0>(a, ch, tile, nco_tab, t0, cnt, obase, tid);
         const double psum = warp_sum((double)p32.x);
         const double osum = a.out_sumsq ? warp_sum((double)p32.y) : 0.0;
         if ((tid & 31) == 0) {
