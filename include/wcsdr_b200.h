@@ -152,6 +152,14 @@ int wc_finalize(float* audio_dev, int n_out, int n_chunks, int n_seq, const doub
                 const float* squelch_db_dev, const int* has_squelch_dev, float* rssi_db_dev,
                 unsigned char* squelched_dev, void* stream);
 
+/* Synchronous AM carrier recovery: CarrierRecoveryPLL.process (dsp/sam.py:73-123) for n_seq independent sequences —
+ * lo = exp(-1j phase), mixed = iq * lo, phase error arctan2(Q, |I| + 1e-10), second-order loop filter, all float64,
+ * sequential per sequence. state_dev float64 [n_seq][3] = (phase, frequency, integrator), read and updated (zeros = the
+ * fresh PLL sam_demod builds, :195-198). Optional float32 [n_seq][n] outputs: audio_dev = sam_demod's sideband selection
+ * (:214-221; 0 dsb, 1 usb, 2 lsb), coh_i_dev / coh_q_dev = the coherent components. */
+int wc_sam_pll(const void* iq_dev, long long seq_stride, int n, int n_seq, double alpha, double beta, int sideband,
+               double* state_dev, float* audio_dev, float* coh_i_dev, float* coh_q_dev, void* stream);
+
 /* ---- analog plan: the whole analog chain of a capture as one call ------------------------------------
  * Replaces one _process_channel_dsp_stateless call per (chunk, channel) from the capture's worker pool
  * (capture.py:298-439, caller :2489-2597) by ONE call per batch of chunks: front end (freq_shift, RSSI power, demod)

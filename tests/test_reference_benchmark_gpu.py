@@ -54,9 +54,11 @@ def test_reference_benchmark_functions_run_on_the_gpu(installed):
     assert rc4.C4FMDemodulator.__module__.startswith("wavecap_sdr_b200")
     b = _script()
     np.random.seed(0)
+    b.benchmark_channelizer(iterations=1)       # warm-up: the first call of a new geometry builds its tap tables and allocations
+    b.benchmark_full_demodulator(iterations=1)
     res = [b.benchmark_fm_demodulator(iterations=3), b.benchmark_interpolator(iterations=1),
            b.benchmark_sync_detector(iterations=1), b.benchmark_full_demodulator(iterations=3),
-           b.benchmark_channelizer(iterations=2)]
+           b.benchmark_channelizer(iterations=5)]
     by = {r["component"]: r for r in res}
     assert set(by) == {"FM Demodulator", "8-tap Interpolator", "Sync Detector", "Full C4FM Demodulator", "Polyphase Channelizer"}
     for r in res:

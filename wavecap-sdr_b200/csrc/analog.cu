@@ -1651,6 +1651,99 @@ int wc_signal_metrics(const void* iq_dev, int fmt, int n, int sample_rate, const
 }  // extern "C"
 
 // =================================================================================================
+// Synchronous AM: carrier-recovery PLL (dsp/sam.py:26-129 CarrierRecoveryPLL.process, :132-270 sam_demod)
+// =================================================================================================
+// The reference walks the samples in a Python loop: lo = exp(-1j * phase) (complex128), mixed = iq[i] * lo, coherent
+// I / Q stored as float32, phase_error = arctan2(imag, |real| + 1e-10), second-order loop filter, phase wrap — all in
+// float64, state (phase, frequency, integrator) carried by the PLL object. Each sample depends on the previous one, so a
+// sequence is one thread; sequences (channels x chunks) are independent: 32 per warp, rows staged 64 samples at a time
+// through shared memory so that global traffic is coalesced (the layout of iir_seq_kernel). numpy's complex product
+// rounds every product and sum separately: __dmul_rn / __dadd_rn keep the compiler from contracting them.
+namespace {
+constexpr int SAM_SEG = 64;
+__global__ void __launch_bounds__(32) sam_pll_kernel(const float2* __restrict__ iq, long long seq_stride, int n, int n_seq,
+                                                     double alpha, double beta, int sideband,   // 0 dsb, 1 usb, 2 lsb
+                                                     double* __restrict__ state,                // [n_seq][3] phase, frequency, integrator
+                                                     float* __restrict__ audio, float* __restrict__ coh_i,
+                                                     float* __restrict__ coh_q) {
+    __shared__ float2 tin[32][SAM_SEG + 1];
+    __shared__ float to[3][32][SAM_SEG + 1];
+    const int lane = threadIdx.x;
+    const int seq0 = blockIdx.x * 32;
+    const int rows = min(32, n_seq - seq0);
+    double phase = 0.0, freq = 0.0, integ = 0.0;
+    if (lane < rows) {
+        phase = state[(seq0 + lane) * 3 + 0];
+        freq = state[(seq0 + lane) * 3 + 1];
+        integ = state[(seq0 + lane) * 3 + 2];
+    }
+    const double PI = 3.141592653589793, TWO_PI = 6.283185307179586;
+    for (int t0 = 0; t0 < n; t0 += SAM_SEG) {
+        const int cnt = min(SAM_SEG, n - t0);
+        for (int r = 0; r < rows; ++r) {
+            const float2* xs = iq + (long long)(seq0 + r) * seq_stride + t0;
+            for (int e = lane; e < cnt; e += 32) tin[r][e] = xs[e];
+        }
+        __syncwarp();
+        if (lane < rows) {
+            for (int j = 0; j < cnt; ++j) {
+                const float2 x = tin[lane][j];
+                double sn, cs;
+                sincos(phase, &sn, &cs);                      // lo = exp(-1j * phase) = (cos phase, -sin phase)
+                const double a = (double)x.x, b = (double)x.y, c = cs, d = -sn;
+                const double re = __dsub_rn(__dmul_rn(a, c), __dmul_rn(b, d));
+                const double im = __dadd_rn(__dmul_rn(a, d), __dmul_rn(b, c));
+                const float ci = (float)re, cq = (float)im;
+                const double pe = atan2(im, fabs(re) + 1e-10);
+                integ = __dadd_rn(integ, __dmul_rn(beta, pe));
+                const double fc = __dadd_rn(__dmul_rn(alpha, pe), integ);
+                freq = fc;
+                phase = __dadd_rn(phase, fc);
+                if (phase > PI) phase = __dsub_rn(phase, TWO_PI);
+                else if (phase < -PI) phase = __dadd_rn(phase, TWO_PI);
+                to[0][lane][j] = sideband == 1 ? __fadd_rn(ci, cq) : sideband == 2 ? __fsub_rn(ci, cq) : ci;
+                to[1][lane][j] = ci;
+                to[2][lane][j] = cq;
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; ++r) {
+            const long long o = (long long)(seq0 + r) * n + t0;
+            for (int e = lane; e < cnt; e += 32) {
+                if (audio) audio[o + e] = to[0][r][e];
+                if (coh_i) coh_i[o + e] = to[1][r][e];
+                if (coh_q) coh_q[o + e] = to[2][r][e];
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < rows) {
+        state[(seq0 + lane) * 3 + 0] = phase;
+        state[(seq0 + lane) * 3 + 1] = freq;
+        state[(seq0 + lane) * 3 + 2] = integ;
+    }
+}
+}  // namespace
+
+extern "C" {
+/* CarrierRecoveryPLL.process for n_seq independent sequences of n complex64 samples (row r at iq_dev + r * seq_stride).
+ * alpha / beta: the loop coefficients of dsp/sam.py:63-65; state_dev float64 [n_seq][3] = (phase, frequency, integrator),
+ * read and updated (zeros = a fresh PLL, which is what sam_demod builds when no pll_state is passed). Outputs, any of them
+ * optional, float32 [n_seq][n]: audio_dev = the sideband selection of sam_demod (:214-221: 0 dsb = I, 1 usb = I + Q,
+ * 2 lsb = I - Q), coh_i_dev / coh_q_dev = the coherent components process() returns. */
+int wc_sam_pll(const void* iq_dev, long long seq_stride, int n, int n_seq, double alpha, double beta, int sideband,
+               double* state_dev, float* audio_dev, float* coh_i_dev, float* coh_q_dev, void* stream) {
+    WC_REQUIRE(iq_dev && state_dev, "wc_sam_pll: null argument");
+    WC_REQUIRE(sideband >= 0 && sideband <= 2, "wc_sam_pll: sideband must be 0 (dsb), 1 (usb) or 2 (lsb)");
+    if (n <= 0 || n_seq <= 0) return 0;
+    sam_pll_kernel<<<(n_seq + 31) / 32, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(iq_dev), seq_stride, n, n_seq, alpha,
+                                                                        beta, sideband, state_dev, audio_dev, coh_i_dev, coh_q_dev);
+    WC_CUDA(cudaGetLastError());
+    return 0;
+}
+}  // extern "C"
+
+// =================================================================================================
 // Analog plan: the whole per-chunk analog chain of a capture as ONE call (SURVEY §8b wc_analog_plan_create / wc_analog_run)
 // =================================================================================================
 // The caller this replaces makes one _process_channel_dsp_stateless call per (chunk, channel) from its worker pool
