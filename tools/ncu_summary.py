@@ -40,8 +40,8 @@ def short_kernel(name: str) -> str:
     return (m.group(2) + (m.group(3) or "")) if m else name[:60]
 
 
-def launches(tag: str) -> None:
-    path = os.path.join(OUT, "launches.csv")
+def launches(tag: str, csv_name: str = "launches.csv", title: str | None = None) -> None:
+    path = os.path.join(OUT, csv_name)
     if not os.path.exists(path):
         return
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
@@ -53,6 +53,8 @@ def launches(tag: str) -> None:
         a[1] += float(r[-1])
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(PROF, f"{tag}_launches.txt"), "w") as f:
+        if title:
+            f.write(f"# {title}\n")
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
         f.write(f"# {len(rows)} launches, total {tot / 1e6:.3f} ms\n")
         f.write(f"{'kernel':44s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}  grid block\n")
@@ -115,8 +117,13 @@ if __name__ == "__main__":
     ap.add_argument("tag")
     ap.add_argument("--kernel", default="chan256")
     ap.add_argument("--samples-per-launch", type=int, default=None)
+    ap.add_argument("--launches-csv", default=None, help="only summarise this launch list (file name under gpurun_out/)")
+    ap.add_argument("--title", default=None)
     a = ap.parse_args()
     os.makedirs(PROF, exist_ok=True)
-    launches(a.tag)
-    full(a.tag, a.kernel, a.samples_per_launch)
+    if a.launches_csv:
+        launches(a.tag, a.launches_csv, a.title)
+    else:
+        launches(a.tag)
+        full(a.tag, a.kernel, a.samples_per_launch)
     print(sorted(os.listdir(PROF)))
