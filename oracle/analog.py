@@ -245,6 +245,64 @@ def ssb_demod(iq, sample_rate, audio_rate=48_000, mode="usb", enable_agc=True, e
     return audio if enable_agc else soft_clip_agc(audio)
 
 
+# ---- dsp/sam.py ----------------------------------------------------------------------------------
+
+class CarrierRecoveryPLLOracle:
+    """dsp/sam.py:25-129: type-2 PLL, proportional + integral loop filter, one Python-float (float64) update per sample."""
+
+    def __init__(self, sample_rate, loop_bandwidth=50.0, damping=0.707):
+        self.sample_rate, self.loop_bandwidth, self.damping = float(sample_rate), loop_bandwidth, damping
+        omega_n = 2 * np.pi * loop_bandwidth                               # :63-65
+        self.alpha = 2 * damping * omega_n / self.sample_rate
+        self.beta = (omega_n ** 2) / (self.sample_rate ** 2)
+        self.phase = self.frequency = self.integrator = 0.0
+
+    def process(self, iq):
+        n = len(iq)
+        ci, cq = np.zeros(n, dtype=F32), np.zeros(n, dtype=F32)
+        phase, integ, freq, alpha, beta = self.phase, self.integrator, self.frequency, self.alpha, self.beta
+        x = np.asarray(iq, dtype=np.complex128)                            # complex64 scalar * complex128 lo -> complex128 (:96)
+        for i in range(n):
+            lo = complex(math.cos(phase), -math.sin(phase))                # np.exp(-1j * phase) (:93)
+            mixed = complex(x[i]) * lo
+            ci[i], cq[i] = mixed.real, mixed.imag
+            pe = math.atan2(mixed.imag, abs(mixed.real) + 1e-10)           # :103
+            integ += beta * pe                                             # :106-107
+            freq = alpha * pe + integ
+            phase += freq
+            if phase > math.pi:                                            # :114-117
+                phase -= 2 * math.pi
+            elif phase < -math.pi:
+                phase += 2 * math.pi
+        self.phase, self.integrator, self.frequency = phase, integ, freq
+        return ci, cq, freq * self.sample_rate / (2 * np.pi)
+
+
+def sam_demod(iq, sample_rate, audio_rate=48_000, sideband="dsb", pll_bandwidth=50.0, pll_damping=0.707, enable_agc=True,
+              enable_highpass=True, highpass_hz=100.0, enable_lowpass=True, lowpass_hz=5000.0, enable_noise_blanker=False,
+              noise_blanker_threshold_db=10.0, agc_target_db=-20.0, notch_frequencies=None, pll_state=None):
+    """dsp/sam.py:132-270 -> (audio, carrier offset Hz, pll)."""
+    if iq.size == 0:
+        return np.empty(0, dtype=F32), 0.0, pll_state
+    pll = pll_state or CarrierRecoveryPLLOracle(sample_rate, pll_bandwidth, pll_damping)
+    ci, cq, f_off = pll.process(iq)
+    sb = sideband.lower()
+    audio = ci + cq if sb == "usb" else ci - cq if sb == "lsb" else ci     # :214-221, float32 arithmetic
+    if enable_noise_blanker:
+        audio = noise_blanker(audio, noise_blanker_threshold_db, 3)
+    if enable_highpass and highpass_hz > 0:
+        audio = highpass_filter(audio, sample_rate, highpass_hz)
+    if enable_lowpass and lowpass_hz > 0:
+        audio = lowpass_filter(audio, sample_rate, lowpass_hz)
+    for f in notch_frequencies or []:
+        if 0 < f < sample_rate / 2:
+            audio = notch_filter(audio, sample_rate, f)
+    if enable_agc:
+        audio = apply_agc(audio, sample_rate, target_db=agc_target_db, attack_ms=5.0, release_ms=50.0)
+    audio = resample_poly(audio, sample_rate, audio_rate)
+    return (audio if enable_agc else soft_clip_agc(audio)), f_off, pll
+
+
 # ---- capture._process_channel_dsp_stateless ------------------------------------------------------
 
 @dataclass
@@ -271,6 +329,8 @@ class OracleChannelConfig:
     ssb_bandpass_high_hz: float = 3_000
     ssb_mode: str = "usb"
     ssb_bfo_offset_hz: float = 1500.0
+    sam_sideband: str = "dsb"
+    sam_pll_bandwidth_hz: float = 50.0
     enable_agc: bool = False
     agc_target_db: float = -20.0
     notch_frequencies: list = field(default_factory=list)
@@ -304,6 +364,11 @@ def process_channel_dsp_stateless(samples, sample_rate, cfg):
         audio = ssb_demod(base, sample_rate, cfg.audio_rate, cfg.ssb_mode, cfg.enable_agc, cfg.enable_ssb_bandpass,
                           cfg.ssb_bandpass_low_hz, cfg.ssb_bandpass_high_hz, cfg.agc_target_db, notch,
                           cfg.ssb_bfo_offset_hz)
+    elif cfg.mode == "sam":                                                # capture.py:385-398 (sam_demod_simple: fresh PLL)
+        audio = sam_demod(base, sample_rate, cfg.audio_rate, cfg.sam_sideband, cfg.sam_pll_bandwidth_hz,
+                          enable_agc=cfg.enable_agc, enable_highpass=cfg.enable_am_highpass, highpass_hz=cfg.am_highpass_hz,
+                          enable_lowpass=cfg.enable_am_lowpass, lowpass_hz=cfg.am_lowpass_hz,
+                          agc_target_db=cfg.agc_target_db)[0]
     elif cfg.mode == "raw":
         audio = np.empty(base.size * 2, dtype=F32)
         audio[0::2] = base.real

@@ -308,6 +308,69 @@ def gen_am_blanker():
     np.savez_compressed(os.path.join(OUT, "am_blanker.npz"), **out)
 
 
+def sam_input(n=14400, fs=48000, carrier_hz=7.0, seed=41):
+    """AM broadcast-like signal: carrier `carrier_hz` off centre with an initial phase, two audio tones, noise and one impulse."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / float(fs)
+    env = 0.4 * (1 + 0.45 * np.sin(2 * np.pi * 620 * t) + 0.25 * np.sin(2 * np.pi * 1870 * t + 0.4))
+    x = env * np.exp(1j * (2 * np.pi * carrier_hz * t + 0.9)) + 0.004 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    x[n // 3] += 2.0 - 1.0j
+    return x.astype(np.complex64)
+
+
+def gen_sam():
+    """dsp/sam.py: CarrierRecoveryPLL.process over two consecutive calls (carried state), sam_demod in its three sideband
+    settings, sam_demod_simple, and capture._process_channel_dsp_stateless(mode='sam') with an offset."""
+    import wavecapsdr.capture as rc
+    from wavecapsdr.dsp import sam as rs
+
+    x = sam_input()
+    out = {}
+    pll = rs.CarrierRecoveryPLL(sample_rate=48000.0, loop_bandwidth=50.0)
+    for k, part in enumerate((x[:5001], x[5001:9000])):
+        ci, cq, f = pll.process(part)
+        out[f"pll_i{k}"], out[f"pll_q{k}"] = ci, cq
+        out[f"pll_state{k}"] = np.array([pll._phase, pll._frequency, pll._integrator, f], dtype=np.float64)
+    a, f, st = rs.sam_demod(x, 48000, 48000)
+    out["dsb"], out["dsb_f"] = a, np.float64(f)
+    a2, f2, _ = rs.sam_demod(x[:4000], 48000, 48000, pll_state=st)          # carried PLL
+    out["dsb_cont"], out["dsb_cont_f"] = a2, np.float64(f2)
+    out["usb_noagc"] = rs.sam_demod(x, 48000, 16000, sideband="usb", pll_bandwidth=30.0, enable_agc=False, lowpass_hz=3000.0)[0]
+    out["lsb_nb_notch"] = rs.sam_demod(x, 48000, 16000, sideband="LSB", pll_bandwidth=100.0, pll_damping=1.0,
+                                       enable_noise_blanker=True, noise_blanker_threshold_db=8.0,
+                                       notch_frequencies=[1870.0, 30000.0])[0]
+    out["simple"] = rs.sam_demod_simple(x, 48000, 24000, sideband="dsb", enable_highpass=False)
+    # the capture path, channel SAM_OFFSET_HZ off centre: 48 kS/s (the regime where the tf-form 100 Hz high-pass is well enough
+    # conditioned for a 1e-4 comparison, SURVEY App. A.6) and one 240 kS/s case (kept to document the reference's own floor there)
+    for fs, tag in ((48000, "st"), (240000, "st240")):
+        xs = sam_stateless_input(fs)
+        for name, kw in sam_stateless_cases():
+            if fs == 240000 and name != "default":
+                continue
+            cfg = rc.ChannelConfig(id="s", capture_id="c", mode="sam", offset_hz=SAM_OFFSET_HZ)
+            for k, v in kw.items():
+                setattr(cfg, k, v)
+            audio, m = rc._process_channel_dsp_stateless(xs, fs, cfg)
+            out[f"{tag}_{name}"] = audio
+            out[f"{tag}_{name}_m"] = np.array([m["rssi_db"], m["signal_power_db"]], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "sam.npz"), **out)
+
+
+SAM_OFFSET_HZ = 6000.0
+
+
+def sam_stateless_input(fs=48000):
+    n = fs // 4
+    x = sam_input(n=n, fs=fs, carrier_hz=-11.0, seed=43)
+    t = np.arange(n) / float(fs)
+    return (x * np.exp(2j * np.pi * SAM_OFFSET_HZ * t)).astype(np.complex64)
+
+
+def sam_stateless_cases():
+    return [("default", {}), ("usb_agc", {"sam_sideband": "usb", "enable_agc": True, "sam_pll_bandwidth_hz": 80.0}),
+            ("lsb_16k", {"sam_sideband": "lsb", "audio_rate": 16000, "enable_am_highpass": False})]
+
+
 def oa_shift(iq):
     """the C1 carrier sits at +200 kHz: bring it to baseband like capture.freq_shift does"""
     import wavecapsdr.capture as rc
@@ -628,7 +691,7 @@ def gen_cc_scanner():
                         x_checksum=np.float64(np.sum(np.abs(x.astype(np.complex128)) ** 2)))
 
 
-GENERATORS = {"channel_calc": gen_channel_calc, "am_blanker": gen_am_blanker, "cc_scanner": gen_cc_scanner, "p25_trellis": gen_p25_trellis, "p25_discriminator": gen_p25_discriminator, "p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
+GENERATORS = {"sam": gen_sam, "channel_calc": gen_channel_calc, "am_blanker": gen_am_blanker, "cc_scanner": gen_cc_scanner, "p25_trellis": gen_p25_trellis, "p25_discriminator": gen_p25_discriminator, "p25_c4fm_disc": gen_p25_c4fm_disc, "p25_framer": gen_p25_framer, "audiofx": gen_audiofx, "ddc": gen_ddc, "p25_c4fm": gen_p25_c4fm, "p25_cqpsk": gen_p25_cqpsk, "channelizer_c5": gen_channelizer_c5, "analog": gen_analog, "spectrum": gen_spectrum}
 
 
 def main(argv):

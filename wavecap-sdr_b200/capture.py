@@ -21,6 +21,7 @@ from . import _native as N
 from .dsp import _stages as S
 from .dsp import am as AM
 from .dsp import fm as FM
+from .dsp import sam as SAM
 
 AUDIO_MAX_ABS = 1.2  # validation.py:9
 
@@ -161,13 +162,17 @@ def _chain_signature(cfg: ChannelConfig, sample_rate: int):
     if cfg.mode in _DIGITAL:
         return ("digital",)
     if cfg.mode == "sam":
-        raise NotImplementedError("sam_demod_simple (dsp/sam.py) is outside the accelerated hot path (SURVEY §8a)")
+        # sam_demod_simple (capture.py:385-398): the AM tail behind a carrier-recovery PLL; no notch list is forwarded
+        st = AM.am_post_chain(sample_rate, cfg.enable_am_highpass, cfg.am_highpass_hz, cfg.enable_am_lowpass, cfg.am_lowpass_hz, ())
+        return ("sam", tuple(st), bool(cfg.enable_agc), float(cfg.agc_target_db), int(cfg.audio_rate),
+                SAM.SIDEBAND.get(str(cfg.sam_sideband).lower(), 0), float(cfg.sam_pll_bandwidth_hz))
     return ("unknown",)
 
 
 def _plan_eligible(sig) -> bool:
     """chains the one-call plan (csrc/analog.cu wc_analog_run) covers: FM without blanker / spectral NR, AM / SSB, and the
-    metrics-only modes. RAW (IQ pass-through) and the optional clean-up stages take the stage-by-stage path."""
+    metrics-only modes. RAW (IQ pass-through), SAM (sequential carrier-recovery loop) and the optional clean-up stages take the
+    stage-by-stage path."""
     if sig[0] == "fm":
         return sig[5] is None and sig[6] is None
     return sig[0] in ("am", "digital", "unknown")
@@ -246,7 +251,7 @@ def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig],
     modes = [_MODE_CODE.get(c.mode, S.MODE_NONE) for c in cfgs]
     bfo = [(c.ssb_bfo_offset_hz if c.ssb_mode.lower() == "usb" else -c.ssb_bfo_offset_hz) if c.mode == "ssb" else 0.0
            for c in cfgs]
-    want_base = any(s[0] == "raw" for s in sigs)
+    want_base = any(s[0] in ("raw", "sam") for s in sigs)
     # channels whose chain has nothing between discriminator and rms_normalize take sum(out**2) from the front end
     want_ss = any(s[0] == "fm" and not s[1] and s[5] is None and s[6] is None for s in sigs)
     out, base, power, nonfinite, *rest = S.front(x, fmt, n, n_chunks, modes, [float(c.offset_hz) for c in cfgs], bfo,
@@ -273,6 +278,16 @@ def process_channels_batch(samples, sample_rate: int, cfgs: list[ChannelConfig],
             a = a.reshape(e - c, n_chunks, -1)
             # per-run statistics stay one tensor [channels of the run][power | invalid][chunk]: a handful of launches per
             # run instead of three per channel
+            stat_parts.append(torch.stack([p.reshape(e - c, n_chunks).double(), inv.reshape(e - c, n_chunks).double()], dim=1))
+            have.extend(range(c, e))
+            for i in range(c, e):
+                audio[i] = a[i - c]
+        elif sig[0] == "sam":
+            # fresh PLL per (channel, chunk) like the stateless reference call; every sequence of the run advances in one launch
+            alpha, beta = SAM.pll_coefficients(float(sample_rate), sig[6], 0.707)
+            rows, _, _ = SAM.pll_rows(base[c:e].reshape((e - c) * n_chunks, n), alpha, beta, sig[5])
+            a, p, inv = AM.am_tail(rows, int(sample_rate), sig[4], sig[1], sig[2], sig[3], want_stats=True)
+            a = a.reshape(e - c, n_chunks, -1)
             stat_parts.append(torch.stack([p.reshape(e - c, n_chunks).double(), inv.reshape(e - c, n_chunks).double()], dim=1))
             have.extend(range(c, e))
             for i in range(c, e):

@@ -19,6 +19,8 @@ REBIND = [
       ("quadrature_demod", "deemphasis_filter", "lpf_audio", "resample_poly", "rms_normalize", "soft_clip", "wbfm_demod",
        "nbfm_demod")],
     *[("wavecapsdr.dsp.am", n, "wavecap_sdr_b200.dsp.am", n) for n in ("freq_shift", "am_demod", "ssb_demod")],
+    *[("wavecapsdr.dsp.sam", n, "wavecap_sdr_b200.dsp.sam", n) for n in ("CarrierRecoveryPLL", "sam_demod", "sam_demod_simple")],
+    ("wavecapsdr.capture", "sam_demod_simple", "wavecap_sdr_b200.dsp.sam", "sam_demod_simple"),   # bound by name at capture.py:45
     *[("wavecapsdr.dsp.agc", n, "wavecap_sdr_b200.dsp.agc", n) for n in ("apply_agc", "apply_simple_agc", "soft_clip")],
     *[("wavecapsdr.dsp.filters", n, "wavecap_sdr_b200.dsp.filters", n) for n in
       ("highpass_filter", "lowpass_filter", "bandpass_filter", "notch_filter", "fir_filter_complex", "fir_decimate")],
