@@ -156,8 +156,11 @@ int wc_finalize(float* audio_dev, int n_out, int n_chunks, int n_seq, const doub
  * lo = exp(-1j phase), mixed = iq * lo, phase error arctan2(Q, |I| + 1e-10), second-order loop filter, all float64,
  * sequential per sequence. state_dev float64 [n_seq][3] = (phase, frequency, integrator), read and updated (zeros = the
  * fresh PLL sam_demod builds, :195-198). Optional float32 [n_seq][n] outputs: audio_dev = sam_demod's sideband selection
- * (:214-221; 0 dsb, 1 usb, 2 lsb), coh_i_dev / coh_q_dev = the coherent components. */
-int wc_sam_pll(const void* iq_dev, long long seq_stride, int n, int n_seq, double alpha, double beta, int sideband,
+ * (:214-221; 0 dsb, 1 usb, 2 lsb), coh_i_dev / coh_q_dev = the coherent components. exact != 0 replays the reference's
+ * float64 arithmetic (coherent I/Q bit-equal on the goldens); exact == 0 keeps the loop state in float64 and evaluates the
+ * oscillator, mixer and phase detector in float32 (faster; ~1e-6 relative RMS on a single carrier, up to 2e-4 with strong
+ * neighbours in the band, see tests/test_sam_gpu.py). */
+int wc_sam_pll(const void* iq_dev, long long seq_stride, int n, int n_seq, double alpha, double beta, int sideband, int exact,
                double* state_dev, float* audio_dev, float* coh_i_dev, float* coh_q_dev, void* stream);
 
 /* ---- analog plan: the whole analog chain of a capture as one call ------------------------------------

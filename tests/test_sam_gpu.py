@@ -13,12 +13,23 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
+@pytest.fixture(params=[False, True], ids=["fast", "exact"])
+def exact(request, native):
+    """both PLL flavours: the float32-detector default and the float64 replay (dsp/sam.py EXACT)"""
+    from wavecap_sdr_b200.dsp import sam as gs
+
+    old = gs.EXACT
+    gs.EXACT = request.param
+    yield request.param
+    gs.EXACT = old
+
+
 @pytest.fixture(scope="module")
 def g():
     return np.load(golden_path("sam.npz"))
 
 
-def test_pll_matches_reference_golden(native, g):
+def test_pll_matches_reference_golden(native, g, exact):
     from wavecap_sdr_b200.dsp.sam import CarrierRecoveryPLL
 
     x = sam_input()
@@ -29,23 +40,26 @@ def test_pll_matches_reference_golden(native, g):
         assert ci.dtype == np.float32 and ci.shape == g[f"pll_i{k}"].shape
         worst = max(worst, rel_rms(ci, g[f"pll_i{k}"]), rel_rms(cq, g[f"pll_q{k}"]))
         st = g[f"pll_state{k}"]
-        assert np.allclose([pll._phase, pll._frequency, pll._integrator, f], st, rtol=1e-9, atol=1e-9)
-    assert worst < 1e-6
+        assert np.allclose([pll._phase, pll._frequency, pll._integrator, f], st, rtol=1e-9 if exact else 1e-4, atol=1e-9 if exact else 1e-5)
+    assert worst < (1e-6 if exact else 5e-5)
     e = pll.process(np.zeros(0, np.complex64))
     assert e[0].size == 0 and e[2] == 0.0
     pll.reset()
     assert pll._phase == 0.0 and pll._integrator == 0.0
-    parity_note(f"sam PLL: coherent I/Q over two carried calls vs the reference golden, worst rel-RMS {worst:.1e}; state within 1e-9")
+    parity_note(f"sam PLL ({'float64 replay' if exact else 'float32 detector'}): coherent I/Q over two carried calls vs the reference "
+                f"golden, worst rel-RMS {worst:.1e}")
 
 
-def test_sam_demod_variants_match_reference_golden(native, g):
+def test_sam_demod_variants_match_reference_golden(native, g, exact):
     from wavecap_sdr_b200.dsp import sam as gs
 
     x = sam_input()
+    ftol = 1e-6 if exact else 2e-2      # carrier offset estimate in Hz (the instantaneous loop frequency of the last sample)
+    ftol = 1e-6 if exact else 1e-3      # carrier offset estimate in Hz (the loop frequency after the last sample)
     a, f, st = gs.sam_demod(x, 48000, 48000)
-    assert rel_rms(a, g["dsb"]) < TOL and abs(f - float(g["dsb_f"])) < 1e-6
+    assert rel_rms(a, g["dsb"]) < TOL and abs(f - float(g["dsb_f"])) < ftol
     a2, f2, _ = gs.sam_demod(x[:4000], 48000, 48000, pll_state=st)
-    assert rel_rms(a2, g["dsb_cont"]) < TOL and abs(f2 - float(g["dsb_cont_f"])) < 1e-6
+    assert rel_rms(a2, g["dsb_cont"]) < TOL and abs(f2 - float(g["dsb_cont_f"])) < ftol
     a = gs.sam_demod(x, 48000, 16000, sideband="usb", pll_bandwidth=30.0, enable_agc=False, lowpass_hz=3000.0)[0]
     assert a.shape == g["usb_noagc"].shape and rel_rms(a, g["usb_noagc"]) < TOL
     a = gs.sam_demod(x, 48000, 16000, sideband="LSB", pll_bandwidth=100.0, pll_damping=1.0, enable_noise_blanker=True,
@@ -57,7 +71,7 @@ def test_sam_demod_variants_match_reference_golden(native, g):
     assert out[0].size == 0 and out[1] == 0.0
 
 
-def test_stateless_sam_branch_matches_reference_golden(native, g):
+def test_stateless_sam_branch_matches_reference_golden(native, g, exact):
     from wavecap_sdr_b200.capture import ChannelConfig, _process_channel_dsp_stateless
 
     xs = sam_stateless_input(48000)
@@ -79,11 +93,11 @@ def test_stateless_sam_branch_matches_reference_golden(native, g):
     e240 = rel_rms(a, g["st240_default"])
     assert a.shape == g["st240_default"].shape and e240 < 1e-2
     assert np.allclose([m["rssi_db"], m["signal_power_db"]], g["st240_default_m"], rtol=0, atol=2e-3)
-    parity_note(f"sam stateless branch (3 configs, 48 kS/s) vs the reference golden: worst audio rel-RMS {worst:.1e}; "
+    parity_note(f"sam stateless branch ({'exact' if exact else 'fast'}; 3 configs, 48 kS/s) vs the reference golden: worst audio rel-RMS {worst:.1e}; "
                 f"240 kS/s (reference's own 1-ulp floor > 1e-4): {e240:.1e}")
 
 
-def test_batch_of_sam_channels_matches_oracle(native):
+def test_batch_of_sam_channels_matches_oracle(native, exact):
     """4 chunks x 5 channels (three SAM settings between an AM and an NBFM channel) in one call vs the oracle per pair."""
     from wavecap_sdr_b200.capture import ChannelConfig, process_channels_batch
 
@@ -111,5 +125,9 @@ def test_batch_of_sam_channels_matches_oracle(native):
             assert a.shape == ea.shape
             worst = max(worst, rel_rms(a, ea))
             assert abs(m["rssi_db"] - em["rssi_db"]) < 2e-3 and abs(m["signal_power_db"] - em["signal_power_db"]) < 2e-3
-    assert worst < TOL
-    parity_note(f"sam in a mixed batch (4 chunks x 5 channels: am, sam dsb, sam usb+agc, nbfm, sam lsb): worst rel-RMS {worst:.1e}")
+    # Five carriers share the 48 kS/s band and the PLL sees all of them (the reference mixes the whole capture, no channel
+    # filter ahead of the loop): the mixed vector passes close to the origin, where arctan2(Q, |I|) turns a 1e-7 input change
+    # into an O(1) detector change. The float64 replay stays inside 1e-4 here (3.9e-5, from the float32 frequency shift ahead
+    # of it); the float32-detector flavour is held to 5e-4 on this input and to 1e-4 on the single-carrier cases above.
+    assert worst < (TOL if exact else 5e-4)
+    parity_note(f"sam ({'exact' if exact else 'fast'}) in a mixed batch (4 chunks x 5 channels: am, sam dsb, sam usb+agc, nbfm, sam lsb): worst rel-RMS {worst:.1e}")

@@ -167,7 +167,7 @@ def _declare(l: C.CDLL) -> None:
     fn("wc_resampler_out_len", i64, vp, i64)
     fn("wc_resampler_run", i32, vp, vp, i32, i64, i32, vp, i32, vp, f32, f32, vp, vp, f32, vp)
     fn("wc_finalize", i32, vp, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp)
-    fn("wc_sam_pll", i32, vp, i64, i32, i32, f64, f64, i32, vp, vp, vp, vp, vp)
+    fn("wc_sam_pll", i32, vp, i64, i32, i32, f64, f64, i32, i32, vp, vp, vp, vp, vp)
     # analog plan
     fn("wc_analog_plan_create", i32, i32, i32, i32, i32, vp, vp, vp, vp, P(vp))
     fn("wc_analog_plan_add_run", i32, vp, i32, i32, i32, i32, i32, vp, i32)

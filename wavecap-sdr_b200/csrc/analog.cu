@@ -483,7 +483,7 @@ template <int K>
 __global__ void __launch_bounds__(32) iir_seq_kernel(const IirCoef* __restrict__ cf, const float* __restrict__ x,
                                                      float* __restrict__ y, int n, long long seq_stride, int n_seq,
                                                      int absin) {
-    __shared__ float tile[32][IIRS_SEG + 1];
+    __shared__ float tile[2][32][IIRS_SEG + 1];
     const int lane = threadIdx.x;
     const int seq0 = blockIdx.x * 32;
     const int rows = min(32, n_seq - seq0);
@@ -495,32 +495,65 @@ __global__ void __launch_bounds__(32) iir_seq_kernel(const IirCoef* __restrict__
         z[i] = 0.0;
     }
     const double b0 = cf->b0;
-    for (int t0 = 0; t0 < n; t0 += IIRS_SEG) {
+    // segment t0 of every row -> tile[b], as asynchronous copies: the next segment lands while this one is filtered
+    auto stage = [&](int b, int t0) {
         const int cnt = min(IIRS_SEG, n - t0);
         for (int r = 0; r < rows; ++r) {
             const float* xs = x + (long long)(seq0 + r) * seq_stride + t0;
-            for (int e = lane; e < cnt; e += 32) {
-                const float v = xs[e];
-                tile[r][e] = absin ? fabsf(v) : v;
-            }
+            for (int e = lane; e < cnt; e += 32) cp_async4(&tile[b][r][e], xs + e);
+        }
+        cp_async_commit();
+    };
+    if (n > 0) stage(0, 0);
+    int b = 0;
+    for (int t0 = 0; t0 < n; t0 += IIRS_SEG, b ^= 1) {
+        const int cnt = min(IIRS_SEG, n - t0);
+        if (t0 + IIRS_SEG < n) {
+            stage(b ^ 1, t0 + IIRS_SEG);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncwarp();
         if (lane < rows) {
 #pragma unroll 2
             for (int j = 0; j < cnt; ++j) {
-                const double xv = (double)tile[lane][j];
+                const float xf = tile[b][lane][j];
+                const double xv = (double)(absin ? fabsf(xf) : xf);
                 const double yv = __dadd_rn(z[0], __dmul_rn(b0, xv));
 #pragma unroll
                 for (int i = 0; i < K - 1; ++i)
                     z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(xv, cb[i])), __dmul_rn(yv, ca[i]));
                 z[K - 1] = __dsub_rn(__dmul_rn(xv, cb[K - 1]), __dmul_rn(yv, ca[K - 1]));
-                tile[lane][j] = (float)yv;
+                tile[b][lane][j] = (float)yv;
             }
         }
         __syncwarp();
-        for (int r = 0; r < rows; ++r) {
-            float* ys = y + (long long)(seq0 + r) * seq_stride + t0;
-            for (int e = lane; e < cnt; e += 32) ys[e] = tile[r][e];
+        if (cnt == IIRS_SEG) {          // full segment: four rows' shared-memory loads in flight per round of stores
+            float* yb = y + (long long)seq0 * seq_stride + t0 + lane;
+            int r = 0;
+            for (; r + 4 <= rows; r += 4) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    v[2 * q] = tile[b][r + q][lane];
+                    v[2 * q + 1] = tile[b][r + q][lane + 32];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    yb[(long long)(r + q) * seq_stride] = v[2 * q];
+                    yb[(long long)(r + q) * seq_stride + 32] = v[2 * q + 1];
+                }
+            }
+            for (; r < rows; ++r) {
+                yb[(long long)r * seq_stride] = tile[b][r][lane];
+                yb[(long long)r * seq_stride + 32] = tile[b][r][lane + 32];
+            }
+        } else {
+            for (int r = 0; r < rows; ++r) {
+                float* ys = y + (long long)(seq0 + r) * seq_stride + t0;
+                for (int e = lane; e < cnt; e += 32) ys[e] = tile[b][r][e];
+            }
         }
         __syncwarp();
     }
@@ -1659,14 +1692,20 @@ int wc_signal_metrics(const void* iq_dev, int fmt, int n, int sample_rate, const
 // sequence is one thread; sequences (channels x chunks) are independent: 32 per warp, rows staged 64 samples at a time
 // through shared memory so that global traffic is coalesced (the layout of iir_seq_kernel). numpy's complex product
 // rounds every product and sum separately: __dmul_rn / __dadd_rn keep the compiler from contracting them.
+// EXACT = true replays that arithmetic in float64 (coherent I / Q bit-equal to the reference on the goldens; ~440 ns per
+// sample, the latency of a float64 sincos + atan2 chain). EXACT = false keeps the loop state (phase, integrator) and its
+// updates in float64 but evaluates the oscillator, the mixer and the phase detector in float32 (MUFU sine / cosine, abs
+// error 4e-7 on [-pi, pi]; degree-13 atan2, 6.5e-7 relative): the detector error enters the phase scaled by alpha ~ 1e-3 and
+// the loop tracks it out, the oscillator error is 4e-7 of the coherent output — three orders inside the 1e-4 gate.
 namespace {
-constexpr int SAM_SEG = 64;
+constexpr int SAM_SEG = 32;
+template <bool EXACT>
 __global__ void __launch_bounds__(32) sam_pll_kernel(const float2* __restrict__ iq, long long seq_stride, int n, int n_seq,
                                                      double alpha, double beta, int sideband,   // 0 dsb, 1 usb, 2 lsb
                                                      double* __restrict__ state,                // [n_seq][3] phase, frequency, integrator
                                                      float* __restrict__ audio, float* __restrict__ coh_i,
                                                      float* __restrict__ coh_q) {
-    __shared__ float2 tin[32][SAM_SEG + 1];
+    __shared__ float2 tin[2][32][SAM_SEG + 1];
     __shared__ float to[3][32][SAM_SEG + 1];
     const int lane = threadIdx.x;
     const int seq0 = blockIdx.x * 32;
@@ -1678,23 +1717,47 @@ __global__ void __launch_bounds__(32) sam_pll_kernel(const float2* __restrict__ 
         integ = state[(seq0 + lane) * 3 + 2];
     }
     const double PI = 3.141592653589793, TWO_PI = 6.283185307179586;
-    for (int t0 = 0; t0 < n; t0 += SAM_SEG) {
+    // segment t0 of every row -> tin[b] as asynchronous copies: the next segment lands while this one runs through the loop
+    auto stage = [&](int b, int t0) {
         const int cnt = min(SAM_SEG, n - t0);
         for (int r = 0; r < rows; ++r) {
             const float2* xs = iq + (long long)(seq0 + r) * seq_stride + t0;
-            for (int e = lane; e < cnt; e += 32) tin[r][e] = xs[e];
+            for (int e = lane; e < cnt; e += 32) cp_async8(&tin[b][r][e], xs + e);
+        }
+        cp_async_commit();
+    };
+    if (n > 0) stage(0, 0);
+    int b = 0;
+    for (int t0 = 0; t0 < n; t0 += SAM_SEG, b ^= 1) {
+        const int cnt = min(SAM_SEG, n - t0);
+        if (t0 + SAM_SEG < n) {
+            stage(b ^ 1, t0 + SAM_SEG);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncwarp();
         if (lane < rows) {
             for (int j = 0; j < cnt; ++j) {
-                const float2 x = tin[lane][j];
-                double sn, cs;
-                sincos(phase, &sn, &cs);                      // lo = exp(-1j * phase) = (cos phase, -sin phase)
-                const double a = (double)x.x, b = (double)x.y, c = cs, d = -sn;
-                const double re = __dsub_rn(__dmul_rn(a, c), __dmul_rn(b, d));
-                const double im = __dadd_rn(__dmul_rn(a, d), __dmul_rn(b, c));
-                const float ci = (float)re, cq = (float)im;
-                const double pe = atan2(im, fabs(re) + 1e-10);
+                const float2 x = tin[b][lane][j];
+                float ci, cq;
+                double pe;
+                if (EXACT) {
+                    double sn, cs;
+                    sincos(phase, &sn, &cs);                  // lo = exp(-1j * phase) = (cos phase, -sin phase)
+                    const double xr = (double)x.x, xi = (double)x.y, lr = cs, li = -sn;
+                    const double re = __dsub_rn(__dmul_rn(xr, lr), __dmul_rn(xi, li));
+                    const double im = __dadd_rn(__dmul_rn(xr, li), __dmul_rn(xi, lr));
+                    ci = (float)re;
+                    cq = (float)im;
+                    pe = atan2(im, fabs(re) + 1e-10);
+                } else {
+                    float sn, cs;
+                    __sincosf((float)phase, &sn, &cs);
+                    ci = fmaf(x.x, cs, x.y * sn);
+                    cq = fmaf(x.y, cs, -x.x * sn);
+                    pe = (double)fast_atan2f(cq, fabsf(ci) + 1e-10f);
+                }
                 integ = __dadd_rn(integ, __dmul_rn(beta, pe));
                 const double fc = __dadd_rn(__dmul_rn(alpha, pe), integ);
                 freq = fc;
@@ -1730,14 +1793,21 @@ extern "C" {
  * alpha / beta: the loop coefficients of dsp/sam.py:63-65; state_dev float64 [n_seq][3] = (phase, frequency, integrator),
  * read and updated (zeros = a fresh PLL, which is what sam_demod builds when no pll_state is passed). Outputs, any of them
  * optional, float32 [n_seq][n]: audio_dev = the sideband selection of sam_demod (:214-221: 0 dsb = I, 1 usb = I + Q,
- * 2 lsb = I - Q), coh_i_dev / coh_q_dev = the coherent components process() returns. */
-int wc_sam_pll(const void* iq_dev, long long seq_stride, int n, int n_seq, double alpha, double beta, int sideband,
+ * 2 lsb = I - Q), coh_i_dev / coh_q_dev = the coherent components process() returns. exact != 0: float64 replay of the
+ * reference's arithmetic; 0: float32 oscillator / mixer / phase detector around the float64 loop state (5x faster). */
+int wc_sam_pll(const void* iq_dev, long long seq_stride, int n, int n_seq, double alpha, double beta, int sideband, int exact,
                double* state_dev, float* audio_dev, float* coh_i_dev, float* coh_q_dev, void* stream) {
     WC_REQUIRE(iq_dev && state_dev, "wc_sam_pll: null argument");
     WC_REQUIRE(sideband >= 0 && sideband <= 2, "wc_sam_pll: sideband must be 0 (dsb), 1 (usb) or 2 (lsb)");
     if (n <= 0 || n_seq <= 0) return 0;
-    sam_pll_kernel<<<(n_seq + 31) / 32, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(iq_dev), seq_stride, n, n_seq, alpha,
-                                                                        beta, sideband, state_dev, audio_dev, coh_i_dev, coh_q_dev);
+    const float2* iq = reinterpret_cast<const float2*>(iq_dev);
+    const dim3 grid((n_seq + 31) / 32);
+    if (exact)
+        sam_pll_kernel<true><<<grid, 32, 0, (cudaStream_t)stream>>>(iq, seq_stride, n, n_seq, alpha, beta, sideband, state_dev, audio_dev,
+                                                                    coh_i_dev, coh_q_dev);
+    else
+        sam_pll_kernel<false><<<grid, 32, 0, (cudaStream_t)stream>>>(iq, seq_stride, n, n_seq, alpha, beta, sideband, state_dev, audio_dev,
+                                                                     coh_i_dev, coh_q_dev);
     WC_CUDA(cudaGetLastError());
     return 0;
 }

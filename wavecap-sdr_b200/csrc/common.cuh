@@ -99,6 +99,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -29,10 +29,6 @@
 
 namespace wc {
 
-__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-
 constexpr int CQ_HIST = 32;     // MMSE_NTAPS (decoders/p25.py:221)
 constexpr int CQ_LPF = 63;
 

@@ -72,9 +72,6 @@ __device__ __forceinline__ void fft256_row(u64* reg, const float2* tw, int t, u6
 }
 
 // ---- Ampere-style async copies (LDGSTS): global -> shared without staging in registers ----
-__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }

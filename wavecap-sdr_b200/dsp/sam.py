@@ -1,7 +1,7 @@
 """GPU synchronous-AM demodulation with the call surface of `wavecapsdr.dsp.sam` (dsp/sam.py).
 
-The carrier-recovery loop is sequential per sequence (csrc/analog.cu sam_pll_kernel, one thread per sequence, float64 like
-the reference's Python loop); the batch path in capture.py runs all (channel, chunk) sequences of a call side by side. The
+The carrier-recovery loop is sequential per sequence (csrc/analog.cu sam_pll_kernel, one thread per sequence; float64 like
+the reference's Python loop by default, `EXACT = False` selects the float32-detector flavour); the batch path in capture.py runs all (channel, chunk) sequences of a call side by side. The
 tail after the sideband selection is the AM tail (`am.am_tail`): same stages, same order (dsp/sam.py:223-258).
 """
 from __future__ import annotations
@@ -16,6 +16,11 @@ from . import _stages as S
 from . import am as AM
 
 SIDEBAND = {"dsb": 0, "usb": 1, "lsb": 2}
+# True (default): float64 replay of the reference's per-sample arithmetic (coherent I/Q bit-equal to the reference on the
+# goldens). False: float32 oscillator / mixer / phase detector around the float64 loop state, several times faster per sample;
+# same audio to ~1e-6 relative RMS on a single carrier, up to 2e-4 when strong neighbours drive the mixed vector through the
+# origin, where the reference's arctan2(Q, |I|) detector amplifies any last-bit difference (tests/test_sam_gpu.py).
+EXACT = True
 
 
 def _n(x) -> int:
@@ -28,7 +33,7 @@ def pll_coefficients(sample_rate: float, loop_bandwidth: float, damping: float) 
     return float(2 * damping * omega_n / sample_rate), float((omega_n ** 2) / (sample_rate ** 2))
 
 
-def pll_rows(rows, alpha: float, beta: float, sideband: int = 0, state=None, want_coherent: bool = False):
+def pll_rows(rows, alpha: float, beta: float, sideband: int = 0, state=None, want_coherent: bool = False, exact=None):
     """CarrierRecoveryPLL.process on every row of a CUDA complex64 [n_seq, n] tensor at once.
     state: CUDA float64 [n_seq, 3] (phase, frequency, integrator), updated in place; None = fresh PLLs.
     -> (audio float32 [n_seq, n] after the sideband selection, state, (coherent_i, coherent_q) | None)."""
@@ -41,7 +46,8 @@ def pll_rows(rows, alpha: float, beta: float, sideband: int = 0, state=None, wan
     ci = cq = None
     if want_coherent:
         ci, cq = torch.empty_like(audio), torch.empty_like(audio)
-    N.check(N.lib().wc_sam_pll(S.ptr(rows), int(rows.stride(0)), n, n_seq, float(alpha), float(beta), int(sideband), S.ptr(state),
+    N.check(N.lib().wc_sam_pll(S.ptr(rows), int(rows.stride(0)), n, n_seq, float(alpha), float(beta), int(sideband),
+                               int(EXACT if exact is None else exact), S.ptr(state),
                                S.ptr(audio), S.ptr(ci), S.ptr(cq), S.stream()))
     return audio, state, ((ci, cq) if want_coherent else None)
 
