@@ -423,12 +423,11 @@ __device__ __forceinline__ void fft_fir_phase(const ChanArgs& a, u64* __restrict
                 for (int k2 = 0; k2 < 16; ++k2) og[16 * k2] = v[rev4(k2)];
             }
         } else {
-            float* w = reinterpret_cast<float*>(uc) + g * CH_REGION_W + t;
+            // bins in natural order, complex, in place over the frame's exchange area (all of its reads precede the warp
+            // barrier above): one 64-bit store per bin, and the discriminator fetches two neighbouring bins per 128-bit load
+            u64* w = uc + g * CH_REGION + t;
 #pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) {
-                w[16 * k2] = lo2(v[rev4(k2)]);
-                w[CH_YIM + 16 * k2] = hi2(v[rev4(k2)]);
-            }
+            for (int k2 = 0; k2 < 16; ++k2) w[16 * k2] = v[rev4(k2)];
         }
     }
     if (FIR) fir2_store<6>(o, un, tid);
@@ -484,23 +483,22 @@ __global__ void __launch_bounds__(CH_THREADS, 4) chan256p_kernel(const ChanArgs 
         f.hhi[j] = __ldg(a.taps + r + CH_H + CH_M * j);
     }
 
-    u64 pre = 0ull, pim = 0ull;
+    u64 p0 = 0ull, p1 = 0ull;   // previous frame's bins 2*tid and 2*tid + 1
 
-    // discriminator of the sub-tile whose planar FFT output sits in `ub` (frames fs .. fs+nv-1)
+    // discriminator of the sub-tile whose FFT output sits in `ub` (frames fs .. fs+nv-1): y_b * conj(y_{b-1}) =
+    // Re(p) * y + Im(p) * (-j y), two packed operations per bin
     auto disc = [&](const u64* ub, int fs, int nv) {
-        const float* sw = reinterpret_cast<const float*>(ub);
         float* o = reinterpret_cast<float*>(a.out) + (out_base + fs) * CH_M + 2 * tid;
         const AtanScaled at = a.at;
         auto one = [&](int i, bool guard) {
-            const float* w = sw + i * CH_REGION_W + 2 * tid;
-            const u64 yre = *reinterpret_cast<const u64*>(w);
-            const u64 yim = *reinterpret_cast<const u64*>(w + CH_YIM);
-            const u64 px = fma2(yre, pre, mul2(yim, pim));
-            const u64 py = sub2(mul2(yim, pre), mul2(yre, pim));
+            const ulonglong2 yy = *reinterpret_cast<const ulonglong2*>(ub + i * CH_REGION + 2 * tid);
+            const u64 z0 = fma2(mulmj(yy.x), bc2(hi2(p0)), mul2(yy.x, bc2(lo2(p0))));
+            const u64 z1 = fma2(mulmj(yy.y), bc2(hi2(p1)), mul2(yy.y, bc2(lo2(p1))));
+            const u64 px = pk2(lo2(z0), lo2(z1)), py = pk2(hi2(z0), hi2(z1));
             const u64 d = (MODE == 2) ? scaled_atan2f_hi_x2(py, px, at) : scaled_atan2f_x2(py, px, at);
             if (!guard || fs + i >= f0) *reinterpret_cast<u64*>(o + (long long)i * CH_M) = d;
-            pre = yre;
-            pim = yim;
+            p0 = yy.x;
+            p1 = yy.y;
         };
         if (nv == CH_S && fs >= f0) {
 #pragma unroll
