@@ -1,7 +1,7 @@
 """Randomised GPU-vs-oracle sweep (dev tool; the fixed cases live in tests/): ragged call sequences, awkward sizes and random
 channel configurations, every result compared with the oracle restatement.
 
-    python tools/fuzz_gpu.py [--seed S] [--rounds R] [--only chan,fm,analog,spectrum,c4fm,cqpsk]
+    python tools/fuzz_gpu.py [--seed S] [--rounds R] [--only chan,fm,analog,spectrum,c4fm,cqpsk,fir,ddc]
 
 Prints one line per family and exits non-zero on the first mismatch (with the parameters that reproduce it)."""
 from __future__ import annotations
@@ -244,7 +244,71 @@ def fuzz_cqpsk(rng, rounds):
     return f"cqpsk: {total - knife} of {total} dibits identical over {rounds} signals in random chunk lengths, {knife} knife-edge"
 
 
-FAMILIES = {"chan": fuzz_chan, "fm": fuzz_fm, "analog": fuzz_analog, "spectrum": fuzz_spectrum, "c4fm": fuzz_c4fm, "cqpsk": fuzz_cqpsk}
+def fuzz_fir(rng, rounds):
+    """streaming complex FIR / FIR-decimate (dsp/filters.py:558-668): random tap counts, decimation factors and call lengths,
+    state carried through zi exactly as the trunking code does"""
+    from scipy import signal
+    from oracle import ddc
+    from wavecap_sdr_b200.dsp.filters import fir_decimate, fir_filter_complex
+
+    worst, calls = 0.0, 0
+    for r in range(rounds):
+        nt = int(rng.choice([9, 33, 73, 157, 255]))
+        taps = signal.firwin(nt, float(rng.uniform(0.02, 0.4)), window=("kaiser", 7.857))
+        d = int(rng.choice([1, 2, 5, 30]))
+        x = iq(rng, int(rng.integers(nt, 60000)))
+        zi_g = zi_o = signal.lfilter_zi(taps, 1.0).astype(np.complex128) * x[0] if rng.integers(0, 2) else None
+        s = 0
+        while s < len(x):
+            n = int(rng.choice([1, 7, nt - 1, nt, nt + 1, 1000, 12077, 30000]))
+            part = x[s:s + n]
+            if d == 1:
+                (g, zi_g), (e, zi_o) = fir_filter_complex(part, taps, zi_g), ddc.fir_filter_complex(part, taps, zi_o)
+            else:
+                (g, zi_g), (e, zi_o) = fir_decimate(part, taps, d, zi=zi_g), ddc.fir_decimate(part, taps, d, zi=zi_o)
+            assert g.shape == e.shape and g.dtype == e.dtype, ("fir shape", r, nt, d, s, n, g.shape, e.shape, g.dtype, e.dtype)
+            assert np.array_equal(zi_g, zi_o), ("fir zi", r, nt, d, s, n)
+            if e.size:
+                err = rel_rms(g, e) if float(np.abs(e).max()) > 0 else float(np.abs(g).max())
+                assert err < TOL, ("fir", r, nt, d, s, n, err)
+                worst = max(worst, err)
+            calls += 1
+            s += n
+    return f"streaming FIR: {calls} calls over {rounds} filters (9..255 taps, decimation 1..30, call lengths 1..30000), worst rel-RMS {worst:.1e}"
+
+
+def fuzz_ddc(rng, rounds):
+    from oracle import ddc
+    from wavecap_sdr_b200.trunking import DDCBank
+
+    worst, calls = 0.0, 0
+    for r in range(rounds):
+        fs, d1, d2 = [(6_000_000, 30, 4), (2_400_000, 25, 2), (2_400_000, 25, 1), (10_000_000, 50, 4)][r % 4]
+        flavor = "control" if rng.integers(0, 2) else "voice"
+        K = int(rng.integers(1, 9))
+        offs = [float(int(rng.integers(-fs // 2 + 50_000, fs // 2 - 50_000) // 12_500) * 12_500) for _ in range(K)]
+        x = ddc.synth_wideband(int(rng.integers(0, 1 << 30)), int(rng.integers(20_000, 200_000)), fs, offs[:3])
+        bank = DDCBank(K, fs, d1, d2, flavor=flavor)
+        bank.set_offsets(offs)
+        cls = ddc.ControlChannelDDC if flavor == "control" else ddc.VoiceDDC
+        orc = [cls(fs, d1, d2, o) for o in offs]
+        s = 0
+        while s < len(x):
+            n = int(rng.choice([d1 * d2 * 3, 5000, 30_000, 123_457]))
+            got = bank.process(x[s:s + n])
+            for k in range(K):
+                exp = orc[k].process(x[s:s + n])
+                assert got.shape[1] == len(exp), ("ddc count", r, fs, d1, d2, flavor, k, s, n, got.shape, len(exp))
+                if len(exp):
+                    err = rel_rms(got[k], exp)
+                    assert err < TOL, ("ddc", r, fs, d1, d2, flavor, k, s, n, err)
+                    worst = max(worst, err)
+            calls += 1
+            s += n
+    return f"trunking DDC bank: {calls} calls over {rounds} banks (1..8 channels, control / voice, 4 rate plans), worst rel-RMS {worst:.1e}"
+
+
+FAMILIES = {"chan": fuzz_chan, "fm": fuzz_fm, "analog": fuzz_analog, "spectrum": fuzz_spectrum, "c4fm": fuzz_c4fm, "cqpsk": fuzz_cqpsk, "fir": fuzz_fir, "ddc": fuzz_ddc}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
