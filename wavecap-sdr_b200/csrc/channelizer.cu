@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(CH_THREADS, MINB) chan256_kernel(const ChanArg
     const int f0 = (blockIdx.x == 0) ? 0 : a.R + (blockIdx.x - 1) * step;
     if (f0 >= a.F) return;
     const int f1 = min(a.F, (blockIdx.x == 0) ? a.R : f0 + step);
-    const float2* __restrict__ xc = a.x + (long long)c * a.chunk_stride;
+    const float2* __restrict__ xc = reinterpret_cast<const float2*>(a.x) + (long long)c * a.chunk_stride;   // cf32 input only
     const long long out_base = (long long)c * a.F;
 
     // one warm-up frame so the discriminator has y_{f0-1}

@@ -619,6 +619,181 @@ __global__ void __launch_bounds__(SP_THREADS, 2) spectrum_pass_b5(const u64* __r
     }
 }
 
+#ifdef WC_DEV   // measured and not adopted (profiles/r02_c3_notes.md): 8.9 B/sample of DRAM traffic, but 183 GS/s against 228
+// ---- both passes in ONE kernel, the scratch never leaves L2: groups of 16 CTAs walk their frames together ----------------
+// The two launches above move 8 (in) + 8 (scratch write) + 8 (scratch read) + 4/K (out) bytes per sample through HBM because a
+// slab's scratch does not survive in L2 between them. Here the 16 CTAs that hold the 16 column tiles of a frame in pass A are
+// the same 16 that hold its 16 row tiles in pass B; they take every frame of their share of the averaging groups through
+// A and B together, exchanging it through a private 4-frame ring (2 MB per group, 36 MB for the 18 groups of a 148-SM grid)
+// that is re-dirtied in place every few microseconds and therefore stays in L2. One monotonic arrival counter per ring slot
+// orders the hand-over (a single counter per group would not do: a CTA runs up to one frame ahead of the others, so a sum of
+// arrivals can reach 16 (j + 1) before every CTA has delivered frame j); the wait for frame j is taken only after pass A of
+// frame j + 1 has been issued, so it has a whole A phase (~2 us) to complete in:
+//
+//     A(0) arrive | A(1) arrive  wait(0) B(0) | A(2) arrive  wait(1) B(1) | ...           (per CTA)
+//
+// A(j) writes ring slot j & 3. A CTA that is writing slot j has passed wait(j - 2), i.e. every CTA of the group has arrived
+// for frame j - 2 and is at the earliest in B(j - 3), which reads slot (j - 3) & 3: four slots, no write-after-read hazard.
+// The grid is launched cooperatively (co-residency guaranteed, never more CTAs than fit), ring reads bypass L1 (ld.global.cg:
+// L1 is not coherent across SMs and slots are reused).
+constexpr int SPG_SLOTS = 4;
+struct SpGroupArgs {
+    const u64* iq;
+    long long frame_stride;
+    const float* window;
+    u64* ring;           // [CTA groups][SPG_SLOTS][65536]
+    unsigned* cnt;       // [CTA groups][SPG_SLOTS] arrivals per ring slot, zero at launch
+    int avg, n_frames, n_groups;
+    float* out;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 2) spectrum_group_kernel(const SpGroupArgs a) {
+    __shared__ SpSmemA3 sm;
+    float* const so_buf = reinterpret_cast<float*>(sm.ex);   // output staging shares the exchange area
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x & 15;       // column tile in pass A, row tile in pass B
+    const int cg = blockIdx.x >> 4;      // CTA group
+    const int n_cg = gridDim.x >> 4;
+    {
+        float sn, cs;
+        sincospif(-(float)((tid >> 4) * (tid & 15)) * (1.0f / 128.0f), &sn, &cs);
+        sm.tw[tid] = make_float2(cs, sn);
+    }
+    __syncthreads();
+    const int t = tid >> 4, col = tid & 15;   // pass A: (row of the 16 x 16 block, column); pass B: (row g = t, lane tb = col)
+    const int n2 = c * SP_COLS + col;
+    float2 base, step;
+    {
+        float sn, cs;
+        sincospif(-(float)(n2 * t) * (1.0f / 32768.0f), &sn, &cs);
+        base = make_float2(cs, sn);
+        sincospif(-(float)(n2 * 16) * (1.0f / 32768.0f), &sn, &cs);
+        step = make_float2(cs, sn);
+    }
+    u64* const exA = sm.ex + col * SP_STRIDE;
+    u64* const exB = sm.ex + t * SP_STRIDE;
+    const float* const wp = a.window + t * SP_N2 + n2;
+    u64* const ring = a.ring + (size_t)cg * SPG_SLOTS * SP_N;
+    unsigned* const cnt = a.cnt + cg * SPG_SLOTS;
+    const long long row_off = (long long)(c * SP_COLS + t) * SP_N2 + col;
+
+    // this group's averaging groups: cg, cg + n_cg, ...; J = its frames in processing order
+    int J = 0;
+    for (int ag = cg; ag < a.n_groups; ag += n_cg) J += min(a.avg, a.n_frames - ag * a.avg);
+    if (J == 0) return;
+    int agA = cg, fA = 0;                 // next frame pass A loads
+    int agB = cg, fB = 0;                 // next frame pass B takes
+    u64 nx[16];
+    {
+        const u64* x = a.iq + (long long)(agA * a.avg + fA) * a.frame_stride;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nx[i] = __ldcs(x + (t + 16 * i) * SP_N2 + n2);
+    }
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+
+    auto pass_b = [&](int jb) {
+        if (tid == 0) {
+            const unsigned target = 16u * (unsigned)(jb / SPG_SLOTS + 1);   // frames jb, jb - 4, ... all went through this slot
+            const unsigned* cs = cnt + (jb & (SPG_SLOTS - 1));
+            const long long t0 = clock64();
+            while (ld_acquire_u32(cs) < target) {
+                if (clock64() - t0 > (1ll << 31)) __trap();   // ~1 s: cannot happen under a cooperative launch
+            }
+        }
+        __syncthreads();
+        const u64* T = ring + (size_t)(jb & (SPG_SLOTS - 1)) * SP_N + row_off;
+        u64 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __ldcg(T + 16 * i);
+        fft256_core(exB, sm.tw, col, v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float re = lo2(v[rev4(q)]), im = hi2(v[rev4(q)]);
+            const float mag = sqrtf(fmaf(re, re, im * im));
+            acc[q] += 6.02059991327962f * __log2f(mag + 1e-10f);  // 20*log10(x) = 20*log10(2)*log2(x)
+        }
+        const int cntB = min(a.avg, a.n_frames - agB * a.avg);
+        if (++fB == cntB) {               // averaging group complete: mean, fftshift, store
+            __syncthreads();              // every half-warp is done with its exchange area
+            const float inv = 1.0f / (float)cntB;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                so_buf[(col + 16 * q) * 17 + t] = acc[q] * inv;
+                acc[q] = 0.f;
+            }
+            __syncthreads();
+            float* o = a.out + (long long)agB * SP_N;
+#pragma unroll 4
+            for (int j = 0; j < 16; ++j) {
+                const int id = tid + SP_THREADS * j;
+                const int k2 = id >> 4, row = id & 15;
+                const int k = (c * SP_COLS + row) + SP_N1 * k2;
+                o[k ^ (SP_N / 2)] = so_buf[k2 * 17 + row];  // fftshift
+            }
+            agB += n_cg;
+            fB = 0;
+        }
+    };
+
+    for (int j = 0; j < J; ++j) {
+        // ---- pass A of frame j (column tile c): window, column FFT-256, four-step twiddle, into ring slot j & 3
+        u64 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = mul2(nx[i], bc2(__ldg(wp + 16 * i * SP_N2)));
+        if (++fA == min(a.avg, a.n_frames - agA * a.avg)) {
+            agA += n_cg;
+            fA = 0;
+        }
+        if (j + 1 < J) {
+            const u64* x = a.iq + (long long)(agA * a.avg + fA) * a.frame_stride;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) nx[i] = __ldcs(x + (t + 16 * i) * SP_N2 + n2);
+        }
+        fft16(v);
+        __syncthreads();   // the previous phase's exchange reads and staged output are consumed
+#pragma unroll
+        for (int ka = 0; ka < 16; ++ka) {
+            u64 w = v[rev4(ka)];
+            if (ka > 0) {
+                const float2 q = sm.tw[ka * 16 + t];
+                w = twid(w, q.x, -q.y);
+            }
+            exA[t * 17 + ka] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = exA[m * 17 + t];
+        fft16(v);
+        {
+            u64* T = ring + (size_t)(j & (SPG_SLOTS - 1)) * SP_N;
+            float2 w = base;
+#pragma unroll
+            for (int kb = 0; kb < 16; ++kb) {
+                const int k1 = t + 16 * kb;
+                T[k1 * SP_N2 + n2] = twid(v[rev4(kb)], w.x, -w.y);
+                w = cmul(w, step);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(cnt + (j & (SPG_SLOTS - 1)), 1u);
+        }
+        // ---- pass B of frame j - 1 (row tile c)
+        if (j >= 1) pass_b(j - 1);
+    }
+    pass_b(J - 1);
+}
+#endif  // WC_DEV
+
 #ifdef WC_DEV
 // ---- fused persistent version: both passes in ONE kernel, scratch is a small L2-resident ring --------
 // The two-pass design moves 8 (in) + 8 (scratch write) + 8 (scratch read) + 4/K (out) bytes per sample through
@@ -938,6 +1113,33 @@ int wc_spectrum_execute(wc_spectrum* h, const void* iq_dev, long long frame_stri
     const size_t pipe_slab_bytes = (size_t)env_int("WC_SPECTRUM_PIPE_SLAB_MB", 128) << 20;
     // (a call of two or three slabs gains nothing from the pipeline: 368 frames 200 GS/s single-stream, 179 pipelined)
     const int variant = env_int("WC_SPECTRUM_VARIANT", (sizeof(float2) * (size_t)n * n_frames >= 4 * pipe_slab_bytes) ? 5 : 3);
+#ifdef WC_DEV
+    if (n == SP_N && variant == 6) {
+        // one cooperative launch: groups of 16 CTAs, scratch = their private L2-resident rings
+        int occ = 0;
+        WC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spectrum_group_kernel, SP_THREADS, 0));
+        int n_cg = (occ * sm_count()) / 16;
+        const int groups = (n_frames + avg - 1) / avg;
+        if (n_cg > groups) n_cg = groups;
+        WC_REQUIRE(n_cg >= 1, "wc_spectrum_execute: the group kernel does not fit this device");
+        if (sp_ensure(&h->d_ring, &h->ring_bytes, sizeof(float2) * (size_t)n * SPG_SLOTS * n_cg)) return -2;
+        if (sp_ensure(&h->d_ctrl, &h->ctrl_bytes, sizeof(unsigned) * 1024)) return -2;
+        WC_CUDA(cudaMemsetAsync(h->d_ctrl, 0, sizeof(unsigned) * SPG_SLOTS * n_cg, st));
+        SpGroupArgs ga;
+        ga.iq = reinterpret_cast<const u64*>(iq);
+        ga.frame_stride = frame_stride;
+        ga.window = h->d_window;
+        ga.ring = reinterpret_cast<u64*>(h->d_ring);
+        ga.cnt = reinterpret_cast<unsigned*>(h->d_ctrl);
+        ga.avg = avg;
+        ga.n_frames = n_frames;
+        ga.n_groups = groups;
+        ga.out = power_db_dev;
+        void* args[] = {&ga};
+        WC_CUDA(cudaLaunchCooperativeKernel((const void*)spectrum_group_kernel, dim3(16 * n_cg), dim3(SP_THREADS), args, 0, st));
+        return 0;
+    }
+#endif
     if (n == SP_N && variant == 5) {
         // Two-stream pipeline: pass A of slab k+1 runs while pass B of slab k drains, over a ring of PIPE_Q slabs: the
         // tail of one launch is filled by the head of the other instead of idling the SMs. Measured on B200 (4096 frames,
