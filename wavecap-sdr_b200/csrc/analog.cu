@@ -160,6 +160,70 @@ __device__ __forceinline__ float2 front_tile(const FrontArgs& a, const FrontChan
     return make_float2(psum32, osum32);
 }
 
+// FM channels of one capture share ONE discriminator. The reference mixes the whole capture down per channel and runs the
+// discriminator on the unfiltered result (capture.py:298-369: freq_shift -> quadrature_demod, no channel filter in
+// between), and angle(z[n] conj(z[n-1])) with z[n] = x[n] e^{j th[n]} is angle(x[n] conj(x[n-1])) + (th[n] - th[n-1]) mod
+// 2 pi, where th[n] = fl32(k32 * fl32(n)) is the float32 phase numpy hands to exp() (its sample-to-sample increment jitters
+// by ulp(th) around k32; both values are formed here exactly as numpy forms them and their float32 difference is exact). So
+// the tile's discriminator d[n] is evaluated once (`dsh`), and a channel costs two multiplies, three adds and a wrap per sample
+// instead of an oscillator, a complex product and an atan2. The two ways differ by the float32 roundings of z (~3e-7 rad);
+// where that could decide which side of the branch cut a sample falls on (within 1e-4 rad of +-pi: 3 samples in 100 000),
+// or where the product is exactly zero (d = NaN), the sample is redone in the reference's own order of operations.
+// Returns this thread's partial of sum out^2.
+// slow form: per-sample test for the branch cut / zero product, n = 0 -> 0 (quadrature_demod's out[0])
+__device__ __noinline__ float front_tile_fm_shared_checked(const FrontArgs& a, const FrontChan& ch, const float2* tile,
+                                                           const float* dsh, int t0, int cnt, long long obase, int tid) {
+    const float PI_F = 3.14159265358979324f, TWO_PI_F = 6.28318530717958648f;
+    float osum32 = 0.f;
+    for (int i = tid; i < cnt; i += FR_THREADS) {
+        const int n = t0 + i;
+        float sft = __fadd_rn(dsh[i], __fsub_rn(__fmul_rn(ch.k32, (float)n), __fmul_rn(ch.k32, (float)(n - 1))));
+        sft = (sft > PI_F) ? sft - TWO_PI_F : ((sft <= -PI_F) ? sft + TWO_PI_F : sft);
+        if (!(fabsf(sft) < PI_F - 1e-4f)) {
+            float c1, s1, c0, s0;
+            nco_f32(ch.k32, n, c1, s1);
+            nco_f32(ch.k32, n - 1, c0, s0);
+            const float2 x1 = tile[i + 1], x0 = tile[i];
+            const float2 b1 = make_float2(x1.x * c1 - x1.y * s1, x1.x * s1 + x1.y * c1);
+            const float2 b0 = make_float2(x0.x * c0 - x0.y * s0, x0.x * s0 + x0.y * c0);
+            sft = fast_atan2f_hi(b1.y * b0.x - b1.x * b0.y, b1.x * b0.x + b1.y * b0.y);
+        }
+        const float o = (n == 0) ? 0.0f : sft * ch.disc_scale;
+        a.out[obase + n] = o;
+        osum32 = fmaf(o, o, osum32);
+    }
+    return osum32;
+}
+
+// fast form: branch-free sample loop that only NOTES whether one of this thread's samples came within 1e-4 rad of the cut
+// (or hit a zero product); such a thread (5 in 10 000), and the one that owns sample 0, redoes its 16 samples the slow way.
+template <bool EXACT_IDX>
+__device__ __forceinline__ float front_tile_fm_shared(const FrontArgs& a, const FrontChan& ch, const float2* tile, const float* dsh,
+                                                      int t0, int cnt, long long obase, int tid) {
+    const float PI_F = 3.14159265358979324f, TWO_PI_F = 6.28318530717958648f;
+    float nf = (float)(t0 + tid);      // EXACT_IDX: the float32 sample index advances by exact float additions (no int -> float
+    float osum32 = 0.f;                // conversions, a quarter-rate pipe, in the loop); beyond 2^24 it is converted per sample
+    bool redo = (t0 == 0 && tid == 0);
+    const float* dp = dsh + tid;
+    float* op = a.out + obase + t0 + tid;
+#pragma unroll 4
+    for (int i = tid; i < cnt; i += FR_THREADS) {
+        const float n1 = EXACT_IDX ? nf : (float)(t0 + i);
+        const float n0 = EXACT_IDX ? nf - 1.0f : (float)(t0 + i - 1);
+        float sft = __fadd_rn(*dp, __fsub_rn(__fmul_rn(ch.k32, n1), __fmul_rn(ch.k32, n0)));
+        sft = (sft > PI_F) ? sft - TWO_PI_F : ((sft <= -PI_F) ? sft + TWO_PI_F : sft);
+        redo |= !(fabsf(sft) < PI_F - 1e-4f);
+        const float o = sft * ch.disc_scale;
+        *op = o;
+        osum32 = fmaf(o, o, osum32);
+        dp += FR_THREADS;
+        op += FR_THREADS;
+        nf += (float)FR_THREADS;
+    }
+    if (redo) osum32 = front_tile_fm_shared_checked(a, ch, tile, dsh, t0, cnt, obase, tid);
+    return osum32;
+}
+
 template <int KIND>
 __device__ __forceinline__ float2 front_tile_dispatch(const FrontArgs& a, const FrontChan& ch, const float2* tile,
                                                      const float2* nco_tab, int t0, int cnt, long long obase, int tid) {
@@ -171,11 +235,34 @@ __device__ __forceinline__ float2 front_tile_dispatch(const FrontArgs& a, const 
                       : front_tile<KIND, false, false>(a, ch, tile, nco_tab, t0, cnt, obase, tid);
 }
 
+// Channel groups (blockIdx.z) for a front-end launch: enough CTAs for ~5 waves of the 4 resident per SM; when every channel
+// takes the shared-discriminator path the per-CTA set-up (staging + one atan2 per sample) is the larger part of a CTA's work,
+// so half as many groups (each CTA then serves more channels from one discriminator).
+static int front_groups(long long base_ctas, int n_ch, bool all_fm_shared) {
+    const long long want = (all_fm_shared ? 2LL : 4LL) * 5 * sm_count();
+    long long groups = (want + base_ctas - 1) / base_ctas;
+    if (groups > n_ch) groups = n_ch;
+    if (groups < 1) groups = 1;
+    return (int)groups;
+}
+
+struct FrontSmem {                       // 51.3 KB: dynamic shared memory (above the 48 KB static limit), 4 CTAs per SM
+    double red[FR_THREADS / 32];
+    double red2[FR_THREADS / 32];
+    float2 tile[FR_TILE + 1];            // staged input, one halo sample in front
+    float2 nco_tab[NCO_TAB];
+    float dsh[FR_TILE];                  // discriminator of the un-shifted tile, shared by the shifted FM channels
+};
+static std::atomic<unsigned long long> g_front_optin{0};
+
 __global__ void __launch_bounds__(FR_THREADS, 4) front_kernel(const FrontArgs a) {
-    __shared__ float2 tile[FR_TILE + 1];
-    __shared__ float2 nco_tab[NCO_TAB];
-    __shared__ double red[FR_THREADS / 32];
-    __shared__ double red2[FR_THREADS / 32];
+    extern __shared__ __align__(16) unsigned char front_smem_raw[];
+    FrontSmem& fsm = *reinterpret_cast<FrontSmem*>(front_smem_raw);
+    float2* const tile = fsm.tile;
+    float* const dsh = fsm.dsh;
+    float2* const nco_tab = fsm.nco_tab;
+    double* const red = fsm.red;
+    double* const red2 = fsm.red2;
     for (int i = threadIdx.x; i < NCO_TAB; i += FR_THREADS) {
         float sv, cv;
         sincospif((float)i * (2.0f / (float)NCO_TAB), &sv, &cv);
@@ -197,17 +284,64 @@ __global__ void __launch_bounds__(FR_THREADS, 4) front_kernel(const FrontArgs a)
                 const short2 q = reinterpret_cast<const short2*>(a.iq)[(long long)chunk * a.chunk_stride + n];
                 v = make_float2((float)q.x / 32768.0f, (float)q.y / 32768.0f);
             }
-            if (i > 0 && !(isfinite(v.x) && isfinite(v.y))) bad = true;
+            if (a.fmt == 0 && i > 0 && !(isfinite(v.x) && isfinite(v.y))) bad = true;   // int16 samples are always finite
         }
         tile[i] = v;
     }
     if (__syncthreads_or(bad) && tid == 0) atomicExch(a.nonfinite + chunk, 1);
+
+    // shifted FM channels (no base output wanted) share one discriminator and one power sum of the un-shifted tile
+    bool fm_shared = false;
+    if (!a.base_out) {
+        for (int c = blockIdx.z; c < a.n_ch; c += gridDim.z) {
+            const int m = a.ch[c].mode;
+            fm_shared |= (m == WC_MODE_WBFM || m == WC_MODE_NBFM) && a.ch[c].shift;
+        }
+    }
+    double shared_pw = 0.0;        // sum |x|^2 of the tile (thread 0): the power of every shifted FM channel
+    if (fm_shared) {
+        float tile_pw = 0.f;
+        for (int i = tid; i < cnt; i += FR_THREADS) {
+            const float2 x1 = tile[i + 1], x0 = tile[i];
+            const float pr = x1.x * x0.x + x1.y * x0.y, pi = x1.y * x0.x - x1.x * x0.y;
+            dsh[i] = (pr == 0.0f && pi == 0.0f) ? __int_as_float(0x7fc00000) : fast_atan2f_hi(pi, pr);
+            tile_pw += fmaf(x1.x, x1.x, x1.y * x1.y);       // |x e^{j th}|^2 = |x|^2 to one float32 rounding
+        }
+        const double w = warp_sum((double)tile_pw);
+        if ((tid & 31) == 0) red[tid >> 5] = w;
+        __syncthreads();
+        if (tid == 0)
+            for (int q = 0; q < FR_THREADS / 32; ++q) shared_pw += red[q];
+        __syncthreads();
+    }
+    const bool exact_idx = (t0 + FR_TILE) <= (1 << 24);
 
     // blockIdx.z splits the channel loop when (tiles x chunks) alone would leave the last wave mostly empty
     for (int c = blockIdx.z; c < a.n_ch; c += gridDim.z) {
         const FrontChan ch = a.ch[c];
         const long long obase = ((long long)c * a.n_chunks + chunk) * a.n;
         float2 p32;
+        if ((ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM) && ch.shift && !a.base_out) {
+            const float o32 = exact_idx ? front_tile_fm_shared<true>(a, ch, tile, dsh, t0, cnt, obase, tid)
+                                        : front_tile_fm_shared<false>(a, ch, tile, dsh, t0, cnt, obase, tid);
+            if (a.out_sumsq) {          // only sum out^2 is this channel's own: <= 512 samples per warp in float32, float64 above
+                float w32 = o32;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) w32 += __shfl_xor_sync(0xffffffffu, w32, off);
+                if ((tid & 31) == 0) red2[tid >> 5] = (double)w32;
+                __syncthreads();
+            }
+            if (tid == 0) {
+                atomicAdd(a.power + (long long)c * a.n_chunks + chunk, shared_pw);
+                if (a.out_sumsq) {
+                    double s2 = 0.0;
+                    for (int q = 0; q < FR_THREADS / 32; ++q) s2 += red2[q];
+                    atomicAdd(a.out_sumsq + (long long)c * a.n_chunks + chunk, s2);
+                }
+            }
+            if (a.out_sumsq) __syncthreads();
+            continue;
+        }
         if (ch.mode == WC_MODE_WBFM || ch.mode == WC_MODE_NBFM) p32 = front_tile_dispatch<1>(a, ch, tile, nco_tab, t0, cnt, obase, tid);
         else if (ch.mode == WC_MODE_AM) p32 = front_tile_dispatch<2>(a, ch, tile, nco_tab, t0, cnt, obase, tid);
         else if (ch.mode == WC_MODE_SSB) p32 = front_tile_dispatch<3>(a, ch, tile, nco_tab, t0, cnt, obase, tid);
@@ -1619,10 +1753,12 @@ int wc_front_run_ex(const void* iq_dev, int fmt, int n, int n_chunks, long long 
     // Channel groups bring the grid to >= 4 waves; the tile is then staged once per group (L2 hits, 1/16 of a channel's work).
     const int tiles = (n + FR_TILE - 1) / FR_TILE;
     const long long base_ctas = (long long)tiles * n_chunks;
-    long long groups = (4LL * 5 * sm_count() + base_ctas - 1) / base_ctas;
-    if (groups > n_ch) groups = n_ch;
-    if (groups < 1) groups = 1;
-    front_kernel<<<dim3(tiles, n_chunks, (unsigned)groups), FR_THREADS, 0, st>>>(a);
+    bool all_fm_shared = base_out_dev == nullptr;
+    for (int c = 0; c < n_ch; ++c)
+        all_fm_shared = all_fm_shared && (modes[c] == WC_MODE_WBFM || modes[c] == WC_MODE_NBFM) && offsets_hz[c] != 0.0;
+    const int groups = front_groups(base_ctas, n_ch, all_fm_shared);
+    WC_CUDA(smem_optin(front_kernel, (int)sizeof(FrontSmem), g_front_optin));
+    front_kernel<<<dim3(tiles, n_chunks, (unsigned)groups), FR_THREADS, sizeof(FrontSmem), st>>>(a);
     WC_CUDA(cudaGetLastError());
     if (!pinned) WC_CUDA(cudaStreamSynchronize(st));   // a pageable host vector must outlive the async copy
     return 0;
@@ -1931,6 +2067,7 @@ struct wc_analog_plan {
     std::vector<int> h_kind, h_naudio;
     std::vector<PlanRun> runs;
     bool finished = false;
+    bool all_fm_shared = false;   // every channel is a shifted FM channel: the front end shares one discriminator (front_groups)
     // device state
     FrontChan* d_chan = nullptr;
     float* d_squelch = nullptr;
@@ -2016,10 +2153,9 @@ static int plan_enqueue(wc_analog_plan* p, const void* iq_dev, int B, float* aud
         a.nonfinite = p->d_nonfinite;
         const int tiles = (n + FR_TILE - 1) / FR_TILE;
         const long long base_ctas = (long long)tiles * B;
-        long long groups = (4LL * 5 * sm_count() + base_ctas - 1) / base_ctas;
-        if (groups > C) groups = C;
-        if (groups < 1) groups = 1;
-        front_kernel<<<dim3(tiles, B, (unsigned)groups), FR_THREADS, 0, st>>>(a);
+        const int groups = front_groups(base_ctas, C, p->all_fm_shared);
+        WC_CUDA(smem_optin(front_kernel, (int)sizeof(FrontSmem), g_front_optin));
+        front_kernel<<<dim3(tiles, B, (unsigned)groups), FR_THREADS, sizeof(FrontSmem), st>>>(a);
         WC_CUDA(cudaGetLastError());
     }
     for (const PlanRun& r : p->runs) {
@@ -2111,6 +2247,9 @@ int wc_analog_plan_create(int sample_rate, int chunk_len, int in_fmt, int n_chan
         f.disc_scale = (float)((double)sample_rate / (2.0 * M_PI * 75000.0));
         if (squelch_db) p->h_squelch[c] = squelch_db[c];
     }
+    p->all_fm_shared = true;
+    for (int c = 0; c < n_channels; ++c)
+        p->all_fm_shared = p->all_fm_shared && (modes[c] == WC_MODE_WBFM || modes[c] == WC_MODE_NBFM) && offsets_hz[c] != 0.0;
     *out = p;
     return 0;
 }
