@@ -65,8 +65,9 @@ __global__ void dd_peak_kernel(const float* __restrict__ x, long long stride, in
 
 // auto gain (p25.py:1213-1222) and DC removal (:1224-1229); y = x*gain - dc, float32 throughout
 // one warp stages the next tile of its 32 channel rows with 4-byte LDGSTS copies while the lanes walk the current one
-__device__ __forceinline__ void dd_stage(float (*tile)[DD_ROW], const float* __restrict__ x, long long stride, int c0, int C,
-                                         int base, int n, int lane) {
+template <int PITCH, int COL0>
+__device__ __forceinline__ void dd_stage_t(float (*tile)[PITCH], const float* __restrict__ x, long long stride, int c0, int C,
+                                           int base, int n, int lane) {
     const int lim = min(DD_TILE, n - base);
     for (int r = 0; r < 32; ++r) {
         if (c0 + r >= C) break;
@@ -74,10 +75,14 @@ __device__ __forceinline__ void dd_stage(float (*tile)[DD_ROW], const float* __r
 #pragma unroll
         for (int k = 0; k < DD_TILE / 32; ++k) {
             const int i = lane + 32 * k;
-            if (i < lim) cp_async4(&tile[r][i], xr + i);
+            if (i < lim) cp_async4(&tile[r][COL0 + i], xr + i);
         }
     }
     cp_async_commit();
+}
+__device__ __forceinline__ void dd_stage(float (*tile)[DD_ROW], const float* __restrict__ x, long long stride, int c0, int C,
+                                         int base, int n, int lane) {
+    dd_stage_t<DD_ROW, 0>(tile, x, stride, c0, C, base, n, lane);
 }
 
 __global__ void __launch_bounds__(32) dd_dc_kernel(const float* __restrict__ x, long long stride, int n, int C,
@@ -152,66 +157,83 @@ __global__ void __launch_bounds__(256) dd_lpf_kernel(const float* __restrict__ x
     y[(long long)ch * n + i] = (float)acc;
 }
 
-__device__ __forceinline__ float dd_interp(const float* __restrict__ taps, const float* hist, int hidx, int imu) {
-    // p25.py:1238-1248: float32 products summed in order into a float32 accumulator (0.0 + first product = that product)
-    float acc = __fmul_rn(taps[imu * DD_TAPS], hist[hidx & 7]);
+constexpr int DD_PAD = DD_TAPS;                 // carried history in front of every staged row
+constexpr int DD_ROWH = DD_PAD + DD_TILE + 1;   // 137 floats: odd pitch, 32 channel rows in 32 different banks
+constexpr int DD_TROW = DD_TAPS + 1;            // interpolator rows padded to 9 floats (lanes index different rows)
+
+__device__ __forceinline__ float dd_interp(const float* __restrict__ taps, const float* __restrict__ w, int imu) {
+    // p25.py:1238-1248: float32 products summed in order into a float32 accumulator (0.0 + first product = that product);
+    // w = the last 8 samples, oldest first (the reference's ring read from hist_idx onwards)
+    float acc = __fmul_rn(taps[imu * DD_TROW], w[0]);
 #pragma unroll
-    for (int i = 1; i < DD_TAPS; ++i) acc = __fadd_rn(acc, __fmul_rn(taps[imu * DD_TAPS + i], hist[(hidx + i) & 7]));
+    for (int i = 1; i < DD_TAPS; ++i) acc = __fadd_rn(acc, __fmul_rn(taps[imu * DD_TROW + i], w[i]));
     return acc;
 }
 
-// _mmse_timing_recovery (p25.py:1250-1333)
+// _mmse_timing_recovery (p25.py:1250-1333). One lane per channel, 32 channels per warp; the channels' symbol clocks are not
+// aligned, so each lane walks its own row: it advances its clock sample by sample (a float32 add and a compare) up to its
+// next symbol instant or the end of the staged tile, then the warp runs the symbol update for every lane that reached one —
+// the ~150-instruction update executes once per symbol, not once per sample whenever any of the 32 channels ticks. The
+// 8-sample history the interpolator reads is the staged row itself (8 carried samples in front of every tile).
 __global__ void __launch_bounds__(32) dd_mmse_kernel(const float* __restrict__ x, int n, int C, DDConst k,
                                                      const float* __restrict__ taps_g, DDState* __restrict__ st,
                                                      unsigned char* __restrict__ dibits, float* __restrict__ soft_out,
                                                      int max_sym, int* __restrict__ n_sym) {
-    __shared__ float tile[2][32][DD_ROW];
-    __shared__ float taps[(DD_STEPS + 1) * DD_TAPS];
+    __shared__ float tile[2][32][DD_ROWH];
+    __shared__ float taps[(DD_STEPS + 1) * DD_TROW];
     const int lane = threadIdx.x;
-    for (int i = lane; i < (DD_STEPS + 1) * DD_TAPS; i += 32) taps[i] = taps_g[i];
+    for (int i = lane; i < (DD_STEPS + 1) * DD_TAPS; i += 32) taps[(i >> 3) * DD_TROW + (i & 7)] = taps_g[i];
     const int c0 = blockIdx.x * 32;
     const int c = c0 + lane;
     const bool live = c < C;
     DDState s;
-    float hist[DD_TAPS];
-    if (live) {
-        s = st[c];
-#pragma unroll
-        for (int i = 0; i < DD_TAPS; ++i) hist[i] = s.hist[i];
-    } else {
-        memset(&s, 0, sizeof(s));
-#pragma unroll
-        for (int i = 0; i < DD_TAPS; ++i) hist[i] = 0.f;
-    }
-    int hidx = s.hidx;
+    if (live) s = st[c];
+    else memset(&s, 0, sizeof(s));
+    // the ring, oldest first, in front of the first tile
+    for (int j = 0; j < DD_PAD; ++j) tile[0][lane][j] = live ? st[c].hist[(s.hidx + j) & 7] : 0.f;
     int count = 0;
     unsigned char* dout = dibits + (long long)c * max_sym;
     float* sout = soft_out ? soft_out + (long long)c * max_sym : nullptr;
-    dd_stage(tile[0], x, n, c0, C, 0, n, lane);
+    dd_stage_t<DD_ROWH, DD_PAD>(tile[0], x, n, c0, C, 0, n, lane);
     int buf = 0;
     for (int base = 0; base < n; base += DD_TILE, buf ^= 1) {
         const int lim = min(DD_TILE, n - base);
         __syncwarp();   // every lane is done with the buffer the next copies land in
         if (base + DD_TILE < n) {
-            dd_stage(tile[buf ^ 1], x, n, c0, C, base + DD_TILE, n, lane);
+            dd_stage_t<DD_ROWH, DD_PAD>(tile[buf ^ 1], x, n, c0, C, base + DD_TILE, n, lane);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncwarp();
-        if (!live) continue;
-        for (int i = 0; i < lim; ++i) {
-            // history ring with a compile-time-indexable copy: rotate instead of indexing dynamically
-            hist[hidx & 7] = tile[buf][lane][i];
-            hidx = (hidx + 1) & 7;
-            bool tick;
-            if (s.clock_py) {
-                s.clock_d += k.symbol_time;
-                tick = s.clock_d > 1.0;
-            } else {
-                s.clock_f = __fadd_rn(s.clock_f, k.symbol_time_f);
-                tick = s.clock_f > 1.0f;
+        const float* row = tile[buf][lane];
+        int i = 0;   // samples of this tile consumed by this lane
+        while (true) {
+            bool tick = false;
+            if (live) {
+                if (s.clock_py) {
+                    while (i < lim) {
+                        ++i;
+                        s.clock_d += k.symbol_time;
+                        if (s.clock_d > 1.0) {
+                            tick = true;
+                            break;
+                        }
+                    }
+                } else {
+                    float cf = s.clock_f;
+                    while (i < lim) {
+                        ++i;
+                        cf = __fadd_rn(cf, k.symbol_time_f);
+                        if (cf > 1.0f) {
+                            tick = true;
+                            break;
+                        }
+                    }
+                    s.clock_f = cf;
+                }
             }
+            if (!__any_sync(0xffffffffu, tick)) break;
             if (!tick) continue;
             int imu, imu1;
             if (s.clock_py) {
@@ -234,8 +256,12 @@ __global__ void __launch_bounds__(32) dd_mmse_kernel(const float* __restrict__ x
                     imu1 = (1.0f < m1) ? DD_STEPS : min((int)rintf(__fmul_rn(m1, 128.0f)), DD_STEPS);
                 }
             }
-            float y = dd_interp(taps, hist, hidx, imu);
-            float y1 = dd_interp(taps, hist, hidx, imu1);
+            // samples cur-7 .. cur (cur = i - 1) sit at row[DD_PAD + cur - 7 ...] = row[i ...]
+            float w[DD_TAPS];
+#pragma unroll
+            for (int j = 0; j < DD_TAPS; ++j) w[j] = row[i + j];
+            float y = dd_interp(taps, w, imu);
+            float y1 = dd_interp(taps, w, imu1);
             y = __fsub_rn(y, s.fine);
             y1 = __fsub_rn(y1, s.fine);
             const float sp = s.spread;
@@ -274,13 +300,24 @@ __global__ void __launch_bounds__(32) dd_mmse_kernel(const float* __restrict__ x
             }
             ++count;
         }
+        // the last 8 samples (carried ones included when the tile is shorter) lead the next tile
+#pragma unroll
+        for (int j = 0; j < DD_PAD; ++j) tile[buf ^ 1][lane][j] = row[lim + j];
     }
     if (live) {
-        s.hidx = hidx;
-        s.symbols += count;
-#pragma unroll
-        for (int i = 0; i < DD_TAPS; ++i) s.hist[i] = hist[i];
-        st[c] = s;
+        // `buf` now names the buffer whose pad holds the newest 8 samples, oldest first: back into ring order
+        const int hend = (s.hidx + n) & 7;
+        for (int j = 0; j < DD_PAD; ++j) st[c].hist[(hend + j) & 7] = tile[buf][lane][j];
+        DDState* o = &st[c];
+        o->clock_d = s.clock_d;
+        o->clock_f = s.clock_f;
+        o->clock_py = s.clock_py;
+        o->spread = s.spread;
+        o->spread_py = s.spread_py;
+        o->fine = s.fine;
+        o->coarse = s.coarse;
+        o->hidx = hend;
+        o->symbols = s.symbols + count;
         n_sym[c] = min(count, max_sym);
     }
 }

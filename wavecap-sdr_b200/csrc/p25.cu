@@ -333,8 +333,13 @@ __device__ double c4_score(const SyncCtx& c, double offset, int lane, double* st
     __syncwarp();
     double score = 0.0;
     if (lane == 0) {
-        for (int i = 0; i < 24; ++i)
-            if (vm & (1u << i)) score += sterm[i];
+        if ((vm & 0xffffffu) == 0xffffffu) {  // the usual case: all 24 samples inside the buffer — same order, loads up front
+#pragma unroll
+            for (int i = 0; i < 24; ++i) score += sterm[i];
+        } else {
+            for (int i = 0; i < 24; ++i)
+                if (vm & (1u << i)) score += sterm[i];
+        }
     }
     __syncwarp();
     return shfl_d(score, 0);
@@ -382,6 +387,7 @@ template <bool DISC>
 __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
     __shared__ double sterm[24];
     __shared__ float lagbuf[24 + 32];
+    __shared__ float s_soft[56];
     __shared__ int pos_n[32];
     __shared__ double pos_mu[32];
     __shared__ float s_taps[129 * C4_ROW];
@@ -487,13 +493,17 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
         if (fine) L = min(L, max(1, 3601 - since));
         const int k = k0 + lane;
         const bool active = lane < L;
+        // the 55 soft values this step's 32 correlations read, staged once (two loads per lane) instead of 24 dependent
+        // global round trips per lane
+        for (int i = lane; i < 55; i += 32) {
+            const int t = k0 - 23 + i;
+            s_soft[i] = (t < 0) ? S.det[24 + t] : ((t < nsym) ? soft[t] : 0.f);
+        }
+        __syncwarp();
         double sp_score = 0.0;
         if (active) {
-            for (int i = 0; i < 24; ++i) {
-                const int t = k - 23 + i;
-                const float sv = (t >= 0) ? soft[t] : S.det[24 + t];
-                sp_score += (double)__fmul_rn(c_sync[i], sv);
-            }
+#pragma unroll
+            for (int i = 0; i < 24; ++i) sp_score += (double)__fmul_rn(c_sync[i], s_soft[lane + i]);
         }
         // lagging detector (:2626-2659), only while acquiring
         bool fed = false;
