@@ -12,7 +12,7 @@ from wavecap_sdr_b200.dsp.p25.c4fm import C4FMBank
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 72000
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-rng = np.random.default_rng(1)
+rng = np.random.default_rng(1); torch.manual_seed(0)
 base = modulate_c4fm(random_frames(rng, n_frames=(n // 2140) + 2, payload=150, gap=40), 48000, seed=1)[:n]
 x = torch.from_numpy(np.ascontiguousarray(np.tile(base, (C, 1)))).cuda()
 x = x * torch.exp(1j * torch.rand((C, 1), device="cuda") * 6.28).to(torch.complex64)

@@ -26,6 +26,7 @@
 
 #include "../../include/wcsdr_b200.h"
 #include "common.cuh"
+#include "seqloop.cuh"
 
 namespace wc {
 
@@ -281,26 +282,16 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
     for (;;) {
         bool fire = false;
         if (live && S.clock_is_f32) {
-            // the clock advances by one rounded float32 addition per sample (exactly the reference's sequence); four
-            // samples per trip: the additions stay a dependent chain, but compare / branch / index work shrinks to a quarter
-            // (a single warp serves 32 channels, so this loop's latency is the demodulator's)
+            // the clock advances by one rounded float32 addition per sample (exactly the reference's sequence); eight
+            // samples per trip in straight-line code (clock_run8): the additions stay a dependent chain, the compare /
+            // branch per sample goes (a single warp serves its channels, so this loop's latency is the demodulator's;
+            // the four-wide predecessor spent 48 % of the kernel here, five branches per trip in the ncu source view)
+            float cf = S.clock_f;
             while (m + 1 < tile_end) {
-                const int room = tile_end - 1 - m;
-                const float c1 = __fadd_rn(S.clock_f, S.sym_time_f);
-                const float c2 = __fadd_rn(c1, S.sym_time_f);
-                const float c3 = __fadd_rn(c2, S.sym_time_f);
-                const float c4 = __fadd_rn(c3, S.sym_time_f);
-                int j = 4;                                   // first sample of the four whose clock value reaches 1
-                if (c3 >= 1.0f) j = 3;
-                if (c2 >= 1.0f) j = 2;
-                if (c1 >= 1.0f) j = 1;
-                const bool crossed = (c1 >= 1.0f) | (c2 >= 1.0f) | (c3 >= 1.0f) | (c4 >= 1.0f);
-                const int take = min(j, room);
-                S.clock_f = take == 1 ? c1 : take == 2 ? c2 : take == 3 ? c3 : c4;
-                m += take;
-                fire = crossed && take == j;
+                m += clock_run8<true>(cf, S.sym_time_f, tile_end - 1 - m, fire);
                 if (fire) break;
             }
+            S.clock_f = cf;
         } else {
             while (live && m + 1 < tile_end) {
                 ++m;

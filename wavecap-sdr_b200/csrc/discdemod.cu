@@ -21,6 +21,7 @@
 
 #include "../../include/wcsdr_b200.h"
 #include "common.cuh"
+#include "seqloop.cuh"
 
 namespace wc {
 
@@ -65,33 +66,36 @@ __global__ void dd_peak_kernel(const float* __restrict__ x, long long stride, in
 
 // auto gain (p25.py:1213-1222) and DC removal (:1224-1229); y = x*gain - dc, float32 throughout
 // one warp stages the next tile of its 32 channel rows with 4-byte LDGSTS copies while the lanes walk the current one
-template <int PITCH, int COL0>
-__device__ __forceinline__ void dd_stage_t(float (*tile)[PITCH], const float* __restrict__ x, long long stride, int c0, int C,
-                                           int base, int n, int lane) {
-    const int lim = min(DD_TILE, n - base);
-    for (int r = 0; r < 32; ++r) {
-        if (c0 + r >= C) break;
+// Layout of the two sequential kernels: warp 0 walks the rows (lane = channel); three helper warps move the tiles between
+// global and shared memory (4-byte LDGSTS in, coalesced stores out), one CTA barrier per tile. With the copies on the
+// walking warp they were 80 % of its instructions (ncu source view, 36 instructions per sample against 6 of arithmetic).
+constexpr int DD_HELPERS = 3;
+constexpr int DD_THREADS = 32 * (1 + DD_HELPERS);
+constexpr int DC_TILE = 124, DC_ROW = DC_TILE + 1;   // three tiles of 32 rows inside the 48 KB static limit
+
+template <int TILE, int PITCH, int COL0>
+__device__ __forceinline__ void dd_helper_load(float (*tile)[PITCH], const float* __restrict__ x, long long stride, int c0, int C,
+                                               int base, int n, int hw, int lane) {
+    const int lim = min(TILE, n - base);
+    for (int r = hw; r < 32 && c0 + r < C; r += DD_HELPERS) {
         const float* xr = x + (long long)(c0 + r) * stride + base;
 #pragma unroll
-        for (int k = 0; k < DD_TILE / 32; ++k) {
+        for (int k = 0; k < (TILE + 31) / 32; ++k) {
             const int i = lane + 32 * k;
             if (i < lim) cp_async4(&tile[r][COL0 + i], xr + i);
         }
     }
     cp_async_commit();
 }
-__device__ __forceinline__ void dd_stage(float (*tile)[DD_ROW], const float* __restrict__ x, long long stride, int c0, int C,
-                                         int base, int n, int lane) {
-    dd_stage_t<DD_ROW, 0>(tile, x, stride, c0, C, base, n, lane);
-}
 
-__global__ void __launch_bounds__(32) dd_dc_kernel(const float* __restrict__ x, long long stride, int n, int C,
-                                                   const float* __restrict__ peak, DDState* __restrict__ st, float* __restrict__ y) {
-    __shared__ float tile[2][32][DD_ROW];
-    const int lane = threadIdx.x;
+__global__ void __launch_bounds__(DD_THREADS) dd_dc_kernel(const float* __restrict__ x, long long stride, int n, int C,
+                                                           const float* __restrict__ peak, DDState* __restrict__ st,
+                                                           float* __restrict__ y) {
+    __shared__ float tile[3][32][DC_ROW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 32;
     const int c = c0 + lane;
-    const bool live = c < C;
+    const bool live = warp == 0 && c < C;
     float gain = 1.f, dc = 0.f;
     if (live) {
         gain = st[c].gain;
@@ -100,32 +104,57 @@ __global__ void __launch_bounds__(32) dd_dc_kernel(const float* __restrict__ x, 
         if (n > 100 && pk > 0.01f)
             gain = __fadd_rn(__fmul_rn(gain, 0.9f), __fmul_rn(__fdiv_rn(3.0f, pk), 0.1f));
     }
-    dd_stage(tile[0], x, stride, c0, C, 0, n, lane);
-    int buf = 0;
-    for (int base = 0; base < n; base += DD_TILE, buf ^= 1) {
-        const int lim = min(DD_TILE, n - base);
-        if (base + DD_TILE < n) {
-            dd_stage(tile[buf ^ 1], x, stride, c0, C, base + DD_TILE, n, lane);
-            cp_async_wait<1>();
+    const int T = (n + DC_TILE - 1) / DC_TILE;
+    if (warp > 0) {
+        dd_helper_load<DC_TILE, DC_ROW, 0>(tile[0], x, stride, c0, C, 0, n, warp - 1, lane);
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+    for (int t = 0; t <= T; ++t) {
+        if (warp == 0) {
+            if (live && t < T) {
+                float* row = tile[t % 3][lane];
+                const int lim = min(DC_TILE, n - t * DC_TILE);
+                int i = 0;
+                for (; i + 4 <= lim; i += 4) {
+                    const float v0 = __fmul_rn(row[i], gain), v1 = __fmul_rn(row[i + 1], gain);
+                    const float v2 = __fmul_rn(row[i + 2], gain), v3 = __fmul_rn(row[i + 3], gain);
+                    const float w0 = __fmul_rn(v0, 0.001f), w1 = __fmul_rn(v1, 0.001f);
+                    const float w2 = __fmul_rn(v2, 0.001f), w3 = __fmul_rn(v3, 0.001f);
+                    const float d0 = __fadd_rn(__fmul_rn(dc, 0.999f), w0);
+                    const float d1 = __fadd_rn(__fmul_rn(d0, 0.999f), w1);
+                    const float d2 = __fadd_rn(__fmul_rn(d1, 0.999f), w2);
+                    dc = __fadd_rn(__fmul_rn(d2, 0.999f), w3);
+                    row[i] = __fsub_rn(v0, d0);
+                    row[i + 1] = __fsub_rn(v1, d1);
+                    row[i + 2] = __fsub_rn(v2, d2);
+                    row[i + 3] = __fsub_rn(v3, dc);
+                }
+                for (; i < lim; ++i) {
+                    const float v = __fmul_rn(row[i], gain);
+                    dc = __fadd_rn(__fmul_rn(dc, 0.999f), __fmul_rn(v, 0.001f));
+                    row[i] = __fsub_rn(v, dc);
+                }
+            }
         } else {
+            const int hw = warp - 1;
+            if (t + 1 < T) dd_helper_load<DC_TILE, DC_ROW, 0>(tile[(t + 1) % 3], x, stride, c0, C, (t + 1) * DC_TILE, n, hw, lane);
+            if (t >= 1) {   // tile t-1 is finished: out, coalesced
+                const int base = (t - 1) * DC_TILE;
+                const int lim = min(DC_TILE, n - base);
+                for (int r = hw; r < 32 && c0 + r < C; r += DD_HELPERS) {
+                    float* yr = y + (long long)(c0 + r) * n + base;
+                    const float* tr = tile[(t - 1) % 3][r];
+#pragma unroll
+                    for (int k = 0; k < (DC_TILE + 31) / 32; ++k) {
+                        const int i = lane + 32 * k;
+                        if (i < lim) yr[i] = tr[i];
+                    }
+                }
+            }
             cp_async_wait<0>();
         }
-        __syncwarp();
-        if (live) {
-            for (int i = 0; i < lim; ++i) {
-                const float v = __fmul_rn(tile[buf][lane][i], gain);
-                dc = __fadd_rn(__fmul_rn(dc, 0.999f), __fmul_rn(v, 0.001f));
-                tile[buf][lane][i] = __fsub_rn(v, dc);
-            }
-        }
-        __syncwarp();
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-            if (c0 + r >= C) break;
-            float* yr = y + (long long)(c0 + r) * n + base;
-            for (int i = lane; i < lim; i += 32) yr[i] = tile[buf][r][i];
-        }
-        __syncwarp();
+        __syncthreads();
     }
     if (live) {
         st[c].gain = gain;
@@ -170,144 +199,149 @@ __device__ __forceinline__ float dd_interp(const float* __restrict__ taps, const
     return acc;
 }
 
-// _mmse_timing_recovery (p25.py:1250-1333). One lane per channel, 32 channels per warp; the channels' symbol clocks are not
-// aligned, so each lane walks its own row: it advances its clock sample by sample (a float32 add and a compare) up to its
-// next symbol instant or the end of the staged tile, then the warp runs the symbol update for every lane that reached one —
-// the ~150-instruction update executes once per symbol, not once per sample whenever any of the 32 channels ticks. The
-// 8-sample history the interpolator reads is the staged row itself (8 carried samples in front of every tile).
-__global__ void __launch_bounds__(32) dd_mmse_kernel(const float* __restrict__ x, int n, int C, DDConst k,
-                                                     const float* __restrict__ taps_g, DDState* __restrict__ st,
-                                                     unsigned char* __restrict__ dibits, float* __restrict__ soft_out,
-                                                     int max_sym, int* __restrict__ n_sym) {
+// One symbol of _mmse_timing_recovery (p25.py:1262-1333) for a lane whose clock just crossed 1: interpolate at mu and
+// mu + 1/128, slicer error, spread / clock / frequency loop updates. Straight-line: every alternative of the reference's
+// if-chains is computed and selected. PY = some lane may still carry the Python-float clock of a fresh / reset demodulator.
+template <bool PY>
+__device__ __forceinline__ void dd_symbol(DDState& s, const DDConst& k, const float* __restrict__ taps, const float* __restrict__ w8,
+                                          unsigned char* __restrict__ dout, float* __restrict__ sout, int max_sym, int& count) {
+    int imu, imu1;
+    if (PY && s.clock_py) {
+        s.clock_d -= 1.0;
+        double mu = s.clock_d / k.symbol_time;
+        if (1.0 < mu) mu = 1.0;
+        imu = min((int)rint(mu * 128.0), DD_STEPS);
+        double m1 = mu + 0.0078125;
+        if (1.0 < m1) m1 = 1.0;
+        imu1 = min((int)rint(m1 * 128.0), DD_STEPS);
+    } else {
+        s.clock_f = __fsub_rn(s.clock_f, 1.0f);
+        const float mu = __fdiv_rn(s.clock_f, k.symbol_time_f);
+        const float m1 = __fadd_rn(mu, 0.0078125f);
+        const int ia = min((int)rintf(__fmul_rn(mu, 128.0f)), DD_STEPS);
+        const int ib = min((int)rintf(__fmul_rn(m1, 128.0f)), DD_STEPS);
+        imu = (1.0f < mu) ? DD_STEPS : ia;                  // min() returned the Python float 1.0
+        imu1 = (1.0f < mu || 1.0f < m1) ? DD_STEPS : ib;
+    }
+    float w[DD_TAPS];
+#pragma unroll
+    for (int j = 0; j < DD_TAPS; ++j) w[j] = w8[j];
+    float y = dd_interp(taps, w, imu);
+    float y1 = dd_interp(taps, w, imu1);
+    y = __fsub_rn(y, s.fine);
+    y1 = __fsub_rn(y1, s.fine);
+    const float sp = s.spread;
+    const float soft = __fdiv_rn(__fmul_rn(2.0f, y), sp);
+    const float c15 = (s.spread_py == 1) ? (float)(1.5 * 1.6) : (s.spread_py == 2) ? (float)(1.5 * 2.4) : __fmul_rn(1.5f, sp);
+    const float c05 = __fmul_rn(0.5f, sp);
+    const bool lo = y < -sp, neg = y < 0.0f, mid = y < sp;
+    const float e_lo = __fadd_rn(y, c15), e_neg = __fadd_rn(y, c05), e_mid = __fsub_rn(y, c05), e_hi = __fsub_rn(y, c15);
+    const float err = lo ? e_lo : neg ? e_neg : mid ? e_mid : e_hi;
+    const float e01 = __fmul_rn(err, 0.01f);
+    const float n_out = __fsub_rn(sp, __fmul_rn(__fmul_rn(err, 0.5f), 0.01f));
+    const float n_neg = __fsub_rn(sp, e01), n_pos = __fadd_rn(sp, e01);
+    const float ns = (lo || !mid) ? n_out : neg ? n_neg : n_pos;
+    // max(1.6, min(2.4, spread)): the literals win when the float32 value reaches them
+    const bool top = !(ns < 2.4f), bot = !(ns > 1.6f);
+    s.spread = top ? 2.4f : bot ? 1.6f : ns;
+    s.spread_py = top ? 2 : bot ? 1 : 0;
+    const float cf = (PY && s.clock_py) ? (float)s.clock_d : s.clock_f;
+    const float tadj = __fmul_rn(err, 0.025f);
+    s.clock_f = (y1 < y) ? __fadd_rn(cf, tadj) : __fsub_rn(cf, tadj);
+    s.clock_py = 0;
+    s.coarse = __fadd_rn(s.coarse, __fmul_rn(__fsub_rn(s.fine, s.coarse), 0.00125f));
+    s.fine = __fadd_rn(s.fine, __fmul_rn(err, 0.125f));
+    if (count < max_sym) {
+        dout[count] = (soft < -2.0f) ? 3 : (soft < 0.0f) ? 2 : (soft < 2.0f) ? 0 : 1;
+        if (sout) sout[count] = soft;
+    }
+    ++count;
+}
+
+// One staged tile of one warp's 32 channels. The channels' symbol clocks are not aligned, so each lane walks its own row:
+// it advances its clock (clock_run8: the reference's rounded float32 additions, eight per trip, no branch per sample) up
+// to its next symbol instant or the end of the tile, then the warp runs the symbol update for every lane that reached one —
+// once per symbol, not once per sample whenever any of the 32 channels ticks. The interpolator's 8-sample history is the
+// staged row itself (8 carried samples in front of every tile): row[i .. i + 7] after i consumed samples.
+template <bool PY>
+__device__ __forceinline__ void dd_walk_tile(DDState& s, const DDConst& k, const float* __restrict__ taps, const float* __restrict__ row,
+                                             int lim, bool live, unsigned char* __restrict__ dout, float* __restrict__ sout,
+                                             int max_sym, int& count) {
+    int i = 0;   // samples of this tile consumed by this lane
+    while (true) {
+        bool tick = false;
+        if (live) {
+            if (PY && s.clock_py) {
+                while (i < lim) {
+                    ++i;
+                    s.clock_d += k.symbol_time;
+                    if (s.clock_d > 1.0) {
+                        tick = true;
+                        break;
+                    }
+                }
+            } else {
+                float cf = s.clock_f;
+                while (i < lim) {
+                    i += clock_run8<false>(cf, k.symbol_time_f, lim - i, tick);
+                    if (tick) break;
+                }
+                s.clock_f = cf;
+            }
+        }
+        if (!__any_sync(0xffffffffu, tick)) break;
+        if (tick) dd_symbol<PY>(s, k, taps, row + i, dout, sout, max_sym, count);
+    }
+}
+
+// _mmse_timing_recovery (p25.py:1250-1333): warp 0 walks (lane = channel), the helper warps stage the next tile.
+__global__ void __launch_bounds__(DD_THREADS) dd_mmse_kernel(const float* __restrict__ x, int n, int C, DDConst k,
+                                                             const float* __restrict__ taps_g, DDState* __restrict__ st,
+                                                             unsigned char* __restrict__ dibits, float* __restrict__ soft_out,
+                                                             int max_sym, int* __restrict__ n_sym) {
     __shared__ float tile[2][32][DD_ROWH];
     __shared__ float taps[(DD_STEPS + 1) * DD_TROW];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < (DD_STEPS + 1) * DD_TAPS; i += 32) taps[(i >> 3) * DD_TROW + (i & 7)] = taps_g[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (DD_STEPS + 1) * DD_TAPS; i += DD_THREADS) taps[(i >> 3) * DD_TROW + (i & 7)] = taps_g[i];
     const int c0 = blockIdx.x * 32;
     const int c = c0 + lane;
-    const bool live = c < C;
+    const bool live = warp == 0 && c < C;
     DDState s;
     if (live) s = st[c];
     else memset(&s, 0, sizeof(s));
+    const int hidx0 = s.hidx;
     // the ring, oldest first, in front of the first tile
-    for (int j = 0; j < DD_PAD; ++j) tile[0][lane][j] = live ? st[c].hist[(s.hidx + j) & 7] : 0.f;
+    if (warp == 0)
+        for (int j = 0; j < DD_PAD; ++j) tile[0][lane][j] = live ? st[c].hist[(hidx0 + j) & 7] : 0.f;
     int count = 0;
     unsigned char* dout = dibits + (long long)c * max_sym;
     float* sout = soft_out ? soft_out + (long long)c * max_sym : nullptr;
-    dd_stage_t<DD_ROWH, DD_PAD>(tile[0], x, n, c0, C, 0, n, lane);
-    int buf = 0;
-    for (int base = 0; base < n; base += DD_TILE, buf ^= 1) {
-        const int lim = min(DD_TILE, n - base);
-        __syncwarp();   // every lane is done with the buffer the next copies land in
-        if (base + DD_TILE < n) {
-            dd_stage_t<DD_ROWH, DD_PAD>(tile[buf ^ 1], x, n, c0, C, base + DD_TILE, n, lane);
-            cp_async_wait<1>();
-        } else {
+    const int T = (n + DD_TILE - 1) / DD_TILE;
+    if (warp > 0) {
+        dd_helper_load<DD_TILE, DD_ROWH, DD_PAD>(tile[0], x, n, c0, C, 0, n, warp - 1, lane);
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+        const int buf = t & 1;
+        if (warp == 0) {
+            const int lim = min(DD_TILE, n - t * DD_TILE);
+            const float* row = tile[buf][lane];
+            if (__any_sync(0xffffffffu, live && s.clock_py)) dd_walk_tile<true>(s, k, taps, row, lim, live, dout, sout, max_sym, count);
+            else dd_walk_tile<false>(s, k, taps, row, lim, live, dout, sout, max_sym, count);
+            // the last 8 samples (carried ones included when the tile is shorter) lead the next tile
+#pragma unroll
+            for (int j = 0; j < DD_PAD; ++j) tile[buf ^ 1][lane][j] = row[lim + j];
+        } else if (t + 1 < T) {
+            dd_helper_load<DD_TILE, DD_ROWH, DD_PAD>(tile[buf ^ 1], x, n, c0, C, (t + 1) * DD_TILE, n, warp - 1, lane);
             cp_async_wait<0>();
         }
-        __syncwarp();
-        const float* row = tile[buf][lane];
-        int i = 0;   // samples of this tile consumed by this lane
-        while (true) {
-            bool tick = false;
-            if (live) {
-                if (s.clock_py) {
-                    while (i < lim) {
-                        ++i;
-                        s.clock_d += k.symbol_time;
-                        if (s.clock_d > 1.0) {
-                            tick = true;
-                            break;
-                        }
-                    }
-                } else {
-                    float cf = s.clock_f;
-                    while (i < lim) {
-                        ++i;
-                        cf = __fadd_rn(cf, k.symbol_time_f);
-                        if (cf > 1.0f) {
-                            tick = true;
-                            break;
-                        }
-                    }
-                    s.clock_f = cf;
-                }
-            }
-            if (!__any_sync(0xffffffffu, tick)) break;
-            if (!tick) continue;
-            int imu, imu1;
-            if (s.clock_py) {
-                s.clock_d -= 1.0;
-                double mu = s.clock_d / k.symbol_time;
-                if (1.0 < mu) mu = 1.0;
-                imu = min((int)rint(mu * 128.0), DD_STEPS);
-                double m1 = mu + 0.0078125;
-                if (1.0 < m1) m1 = 1.0;
-                imu1 = min((int)rint(m1 * 128.0), DD_STEPS);
-            } else {
-                s.clock_f = __fsub_rn(s.clock_f, 1.0f);
-                const float mu = __fdiv_rn(s.clock_f, k.symbol_time_f);
-                if (1.0f < mu) {
-                    imu = DD_STEPS;   // min() returned the Python float 1.0
-                    imu1 = DD_STEPS;
-                } else {
-                    imu = min((int)rintf(__fmul_rn(mu, 128.0f)), DD_STEPS);
-                    const float m1 = __fadd_rn(mu, 0.0078125f);
-                    imu1 = (1.0f < m1) ? DD_STEPS : min((int)rintf(__fmul_rn(m1, 128.0f)), DD_STEPS);
-                }
-            }
-            // samples cur-7 .. cur (cur = i - 1) sit at row[DD_PAD + cur - 7 ...] = row[i ...]
-            float w[DD_TAPS];
-#pragma unroll
-            for (int j = 0; j < DD_TAPS; ++j) w[j] = row[i + j];
-            float y = dd_interp(taps, w, imu);
-            float y1 = dd_interp(taps, w, imu1);
-            y = __fsub_rn(y, s.fine);
-            y1 = __fsub_rn(y1, s.fine);
-            const float sp = s.spread;
-            const float soft = __fdiv_rn(__fmul_rn(2.0f, y), sp);
-            const float c15 = (s.spread_py == 1) ? (float)(1.5 * 1.6) : (s.spread_py == 2) ? (float)(1.5 * 2.4) : __fmul_rn(1.5f, sp);
-            const float c05 = __fmul_rn(0.5f, sp);
-            float err;
-            if (y < -sp) err = __fadd_rn(y, c15);
-            else if (y < 0.0f) err = __fadd_rn(y, c05);
-            else if (y < sp) err = __fsub_rn(y, c05);
-            else err = __fsub_rn(y, c15);
-            float ns;
-            if (y < -sp || y >= sp) ns = __fsub_rn(sp, __fmul_rn(__fmul_rn(err, 0.5f), 0.01f));
-            else if (y < 0.0f) ns = __fsub_rn(sp, __fmul_rn(err, 0.01f));
-            else ns = __fadd_rn(sp, __fmul_rn(err, 0.01f));
-            // max(1.6, min(2.4, spread)): the literals win when the float32 value reaches them
-            if (!(ns < 2.4f)) {
-                s.spread = 2.4f;
-                s.spread_py = 2;
-            } else if (!(ns > 1.6f)) {
-                s.spread = 1.6f;
-                s.spread_py = 1;
-            } else {
-                s.spread = ns;
-                s.spread_py = 0;
-            }
-            const float cf = s.clock_py ? (float)s.clock_d : s.clock_f;
-            const float tadj = __fmul_rn(err, 0.025f);
-            s.clock_f = (y1 < y) ? __fadd_rn(cf, tadj) : __fsub_rn(cf, tadj);
-            s.clock_py = 0;
-            s.coarse = __fadd_rn(s.coarse, __fmul_rn(__fsub_rn(s.fine, s.coarse), 0.00125f));
-            s.fine = __fadd_rn(s.fine, __fmul_rn(err, 0.125f));
-            if (count < max_sym) {
-                dout[count] = (soft < -2.0f) ? 3 : (soft < 0.0f) ? 2 : (soft < 2.0f) ? 0 : 1;
-                if (sout) sout[count] = soft;
-            }
-            ++count;
-        }
-        // the last 8 samples (carried ones included when the tile is shorter) lead the next tile
-#pragma unroll
-        for (int j = 0; j < DD_PAD; ++j) tile[buf ^ 1][lane][j] = row[lim + j];
+        __syncthreads();
     }
     if (live) {
-        // `buf` now names the buffer whose pad holds the newest 8 samples, oldest first: back into ring order
-        const int hend = (s.hidx + n) & 7;
-        for (int j = 0; j < DD_PAD; ++j) st[c].hist[(hend + j) & 7] = tile[buf][lane][j];
+        // buffer T & 1 holds, in its pad, the newest 8 samples, oldest first: back into ring order
+        const int hend = (hidx0 + n) & 7;
+        for (int j = 0; j < DD_PAD; ++j) st[c].hist[(hend + j) & 7] = tile[T & 1][lane][j];
         DDState* o = &st[c];
         o->clock_d = s.clock_d;
         o->clock_f = s.clock_f;
@@ -517,10 +551,10 @@ int wc_discdemod_demod(wc_discdemod* h, const float* audio_dev, long long chan_s
     if (dd_ensure(&h->d_a, &h->a_cap, (size_t)C * n_samples)) return -2;
     if (dd_ensure(&h->d_b, &h->b_cap, (size_t)C * n_samples)) return -2;
     dd_peak_kernel<<<C, 256, 0, s>>>(audio_dev, chan_stride, n_samples, h->d_peak);
-    dd_dc_kernel<<<(C + 31) / 32, 32, 0, s>>>(audio_dev, chan_stride, n_samples, C, h->d_peak, h->d_state, h->d_a);
+    dd_dc_kernel<<<(C + 31) / 32, DD_THREADS, 0, s>>>(audio_dev, chan_stride, n_samples, C, h->d_peak, h->d_state, h->d_a);
     dim3 lg((n_samples + 255) / 256, C);
     dd_lpf_kernel<<<lg, 256, 0, s>>>(h->d_a, n_samples, h->d_lpf, h->d_b);
-    dd_mmse_kernel<<<(C + 31) / 32, 32, 0, s>>>(h->d_b, n_samples, C, h->k, h->d_taps, h->d_state, dibits_dev, soft_dev,
+    dd_mmse_kernel<<<(C + 31) / 32, DD_THREADS, 0, s>>>(h->d_b, n_samples, C, h->k, h->d_taps, h->d_state, dibits_dev, soft_dev,
                                                 max_sym, n_sym_dev);
     WC_CUDA(cudaGetLastError());
     return 0;

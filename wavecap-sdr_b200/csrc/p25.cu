@@ -285,15 +285,26 @@ struct SyncCtx {
     const float* ring;
     const float* taps;    // shared-memory copy of the 129 x 8 interpolator table, rows padded to 9 floats (the lanes of
                           // a score evaluation index 24 different rows: that would serialise on the constant cache)
+    const float* win;     // shared-memory copy of the buffer values win_lo .. win_lo + win_n - 1 around the sync word
+    int win_lo, win_n;    // being timed (one fill per event instead of eight L2 round trips per score); 0 = none
     int ptr, shift_mod;
     double sps, pll, gain;
     float my_sync;        // c_sync[lane]
 };
 constexpr int C4_ROW = 9;
+constexpr int C4_WIN = 1024;        // floats; a sync word spans 24 * sps samples
+constexpr int C4_SOFTWIN = 256;     // symbols of the soft / index window the sync loop reads from shared memory
 
 __device__ __forceinline__ float c4_buf(const SyncCtx& c, int v) {
     if (v < 0 || v > c.ptr) return 0.0f;
     return c.ring[(v + c.shift_mod) & (C4_RING - 1)];
+}
+
+// the same value through the per-event window when it covers v
+__device__ __forceinline__ float c4_get(const SyncCtx& c, int v) {
+    const unsigned u = (unsigned)(v - c.win_lo);
+    if (u < (unsigned)c.win_n) return c.win[u];
+    return c4_buf(c, v);
 }
 
 __device__ __forceinline__ int c4_slice(double sr) {
@@ -310,39 +321,66 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
 // per-lane interpolated soft value of sync symbol `lane` (< 24) for the pointer sequence starting at
 // offset - 23*sps (c4fm.py:416-459). Returns validity.
 __device__ __forceinline__ bool c4_sync_sample(const SyncCtx& c, double offset, int lane, double& soft) {
-    double p = offset - (23.0 * c.sps);
-    for (int t = 0; t < lane; ++t) p += c.sps;       // the reference accumulates ptr += sps
+    // the reference accumulates ptr += sps: every lane runs the 23-term chain (unrolled, no branch) and keeps its own term
+    double q = offset - (23.0 * c.sps);
+    double p = q;
+#pragma unroll
+    for (int t = 1; t < 24; ++t) {
+        q += c.sps;
+        p = (lane >= t) ? q : p;
+    }
     const int bi = (int)p;
     const int io = bi - 3;
     if (lane >= 24 || io < 0 || io > C4_RING - 8) return false;
     int row = (int)((1.0 - (p - (double)bi)) * 128.0 + 0.5);
     row = min(max(row, 0), 128);
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = c4_get(c, io + j);
     double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc += (double)__fmul_rn(c4_buf(c, io + j), c.taps[row * C4_ROW + j]);
+    for (int j = 0; j < 8; ++j) acc += (double)__fmul_rn(x[j], c.taps[row * C4_ROW + j]);
     soft = (acc + c.pll) * c.gain;
     return true;
 }
 
-// _timing_score_jit: sum over the 24 sync symbols in order i = 0..23 (lane 0 adds, result broadcast)
-__device__ double c4_score(const SyncCtx& c, double offset, int lane, double* sterm) {
-    double soft = 0.0;
-    const bool ok = c4_sync_sample(c, offset, lane, soft);
-    const unsigned vm = __ballot_sync(0xffffffffu, ok);
-    if (lane < 24) sterm[lane] = ok ? soft * (double)c.my_sync : 0.0;
+// _timing_score_jit at NS offsets at once: per offset the sum over the 24 sync symbols in order i = 0..23. The NS
+// evaluations are independent, so their chains interleave, and lane q adds up offset q's terms (results broadcast).
+template <int NS>
+__device__ __forceinline__ void c4_scores(const SyncCtx& c, const double (&offs)[NS], int lane, double* sterm, double (&out)[NS]) {
+    unsigned vm[NS];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        double soft = 0.0;
+        const bool ok = c4_sync_sample(c, offs[q], lane, soft);
+        vm[q] = __ballot_sync(0xffffffffu, ok);
+        if (lane < 24) sterm[q * 24 + lane] = ok ? soft * (double)c.my_sync : 0.0;
+    }
     __syncwarp();
     double score = 0.0;
-    if (lane == 0) {
-        if ((vm & 0xffffffu) == 0xffffffu) {  // the usual case: all 24 samples inside the buffer — same order, loads up front
+    if (lane < NS) {
+        unsigned v = vm[0];
 #pragma unroll
-            for (int i = 0; i < 24; ++i) score += sterm[i];
+        for (int q = 1; q < NS; ++q) v = (lane == q) ? vm[q] : v;
+        const double* t = sterm + lane * 24;
+        if ((v & 0xffffffu) == 0xffffffu) {  // the usual case: all 24 samples inside the buffer — same order, loads up front
+#pragma unroll
+            for (int i = 0; i < 24; ++i) score += t[i];
         } else {
             for (int i = 0; i < 24; ++i)
-                if (vm & (1u << i)) score += sterm[i];
+                if (v & (1u << i)) score += t[i];
         }
     }
     __syncwarp();
-    return shfl_d(score, 0);
+#pragma unroll
+    for (int q = 0; q < NS; ++q) out[q] = shfl_d(score, q);
+}
+
+__device__ __forceinline__ double c4_score(const SyncCtx& c, double offset, int lane, double* sterm) {
+    const double o[1] = {offset};
+    double r[1];
+    c4_scores<1>(c, o, lane, sterm, r);
+    return r[0];
 }
 
 // _timing_correction_jit (c4fm.py:462-540)
@@ -385,11 +423,13 @@ __device__ void c4_correction(const SyncCtx& c, double offset, int lane, double*
 // correction, no re-slicing, no sync counter — and the optimiser is handed the sample point as its buffer offset.
 template <bool DISC>
 __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
-    __shared__ double sterm[24];
+    __shared__ double sterm[3 * 24];
     __shared__ float lagbuf[24 + 32];
-    __shared__ float s_soft[56];
-    __shared__ int pos_n[32];
-    __shared__ double pos_mu[32];
+    __shared__ float s_soft[23 + C4_SOFTWIN];   // soft[kw - 23 .. kw + 255] of the sync loop's current window
+    __shared__ int s_idx[C4_SOFTWIN];
+    __shared__ float s_win[C4_WIN];
+    __shared__ int pos_n[2][32];
+    __shared__ double pos_mu[2][32];
     __shared__ float s_taps[129 * C4_ROW];
     for (int i = threadIdx.x; i < 129 * 8; i += 32) s_taps[(i >> 3) * C4_ROW + (i & 7)] = c_interp[i >> 3][i & 7];
     __syncwarp();
@@ -413,46 +453,75 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
     const float prev_phase = S.prev_phase;
     int nsym = 0;
     {
+        // Positions are a sequential float64 recurrence (lane 0); the 32 interpolations of a block are parallel. The two
+        // are software-pipelined: while the block's phase loads are in flight, lane 0 works out the next block's positions.
         double sp = S.sample_point;
         int nn = -1;  // chunk-relative index of the last consumed sample
         bool done = (a.n == 0);
-        while (!done) {
+        auto positions = [&](int* pn, double* pm) -> int {   // lane 0: up to 32 symbol positions; sets `done` at the end
             int cnt = 0;
-            if (lane == 0) {
-                while (cnt < 32) {
-                    const int left = a.n - 1 - nn;
-                    if (left <= 0) {
-                        done = true;
-                        break;
+            while (cnt < 32) {
+                const int left = a.n - 1 - nn;
+                // eight symbols in straight-line code while the end of the chunk is out of reach: each takes
+                // floor(sp) <= sp < sps + 1 samples. floor() by a round-down addition of 2^52 (sp < 2^31 here), the
+                // subtractions are exact, (int)f == the reference's int(floor(sp)).
+                if (cnt <= 24 && sp >= 1.0 && sp < 1.0e9 && sps >= 1.0 && sps < 1.0e6 && (double)left > sp + 8.0 * (sps + 1.0)) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const double f = __dadd_rd(sp, 4503599627370496.0) - 4503599627370496.0;
+                        sp = sp - f;
+                        nn += (int)f;
+                        pn[cnt + q] = nn;
+                        pm[cnt + q] = 1.0 - sp;
+                        sp += sps;
                     }
-                    // number of `sp -= 1.0` steps until sp < 1.0 (each step is exact for sp >= 1)
-                    int j = 1;
-                    if (sp >= 1.0) {
-                        const double f = floor(sp);
-                        j = (f > 2.0e9) ? 2000000000 : (int)f;
-                    }
-                    if (j > left) {
-                        sp = sp - (double)left;
-                        nn += left;
-                        done = true;
-                        break;
-                    }
-                    sp = sp - (double)j;
-                    nn += j;
-                    pos_n[cnt] = nn;
-                    pos_mu[cnt] = 1.0 - sp;
-                    ++cnt;
-                    sp += sps;
+                    cnt += 8;
+                    continue;
                 }
+                if (left <= 0) {
+                    done = true;
+                    break;
+                }
+                // number of `sp -= 1.0` steps until sp < 1.0 (each step is exact for sp >= 1)
+                int j = 1;
+                if (sp >= 1.0) {
+                    const double f = floor(sp);
+                    j = (f > 2.0e9) ? 2000000000 : (int)f;
+                }
+                if (j > left) {
+                    sp = sp - (double)left;
+                    nn += left;
+                    done = true;
+                    break;
+                }
+                sp = sp - (double)j;
+                nn += j;
+                pn[cnt] = nn;
+                pm[cnt] = 1.0 - sp;
+                ++cnt;
+                sp += sps;
             }
-            cnt = __shfl_sync(0xffffffffu, cnt, 0);
-            done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
-            __syncwarp();
-            if (lane < cnt && nsym + lane < a.max_sym) {
-                const int m = pos_n[lane];
-                const double mu = pos_mu[lane];
-                const float x2 = ph[m];
-                const float x1 = (m > 0) ? ph[m - 1] : prev_phase;
+            return cnt;
+        };
+        int cur = 0, cnt = 0;
+        if (!done && lane == 0) cnt = positions(pos_n[0], pos_mu[0]);
+        cnt = __shfl_sync(0xffffffffu, cnt, 0);
+        done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
+        __syncwarp();
+        while (cnt > 0) {
+            const bool mine = lane < cnt && nsym + lane < a.max_sym;
+            int m = 0;
+            double mu = 0.0;
+            float x1 = 0.f, x2 = 0.f;
+            if (mine) {
+                m = pos_n[cur][lane];
+                mu = pos_mu[cur][lane];
+                x2 = ph[m];
+                x1 = (m > 0) ? ph[m - 1] : prev_phase;
+            }
+            int ncnt = 0;
+            if (!done && lane == 0) ncnt = positions(pos_n[cur ^ 1], pos_mu[cur ^ 1]);
+            if (mine) {
                 double v;
                 if (mu < 0.0) v = (double)x1;
                 else if (mu > 1.0) v = (double)x2;
@@ -464,6 +533,9 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
                 idx[nsym + lane] = (vi >= 0) ? (int)vi : -1;
             }
             nsym = min(nsym + cnt, a.max_sym);
+            cnt = __shfl_sync(0xffffffffu, ncnt, 0);
+            done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
+            cur ^= 1;
             __syncwarp();
         }
         sp = shfl_d(sp, 0);
@@ -479,6 +551,9 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
     c.pll = pll0;
     c.gain = gain0;
     c.taps = s_taps;
+    c.win = s_win;
+    c.win_lo = 0;
+    c.win_n = 0;
     c.my_sync = (lane < 24) ? c_sync[lane] : 0.f;
     int fine = S.fine, since = S.since_sync, eq_init = S.eq_init, sync_count = S.sync_count, n_events = 0;
     double sample_point = S.sample_point;
@@ -488,27 +563,35 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
 
     // ---- sync loop (c4fm.py:2596-2807), 32 symbols per step until the first threshold crossing
     int k0 = 0;
+    int kw = 0;             // first symbol of the staged soft / index window
+    bool win_ok = false;    // false: the window has to be (re)read — at the start and after a message was re-sliced
     while (k0 < nsym) {
         int L = min(32, nsym - k0);
         if (fine) L = min(L, max(1, 3601 - since));
         const int k = k0 + lane;
         const bool active = lane < L;
-        // the 55 soft values this step's 32 correlations read, staged once (two loads per lane) instead of 24 dependent
-        // global round trips per lane
-        for (int i = lane; i < 55; i += 32) {
-            const int t = k0 - 23 + i;
-            s_soft[i] = (t < 0) ? S.det[24 + t] : ((t < nsym) ? soft[t] : 0.f);
+        // the soft values (and buffer indices) the correlations of the next 256 symbols read, staged once: one pipelined
+        // batch of loads per eight steps instead of a dependent global round trip per step
+        if (!win_ok || k0 + 32 > kw + C4_SOFTWIN) {
+            kw = k0;
+            for (int i = lane; i < 23 + C4_SOFTWIN; i += 32) {
+                const int t = kw - 23 + i;
+                s_soft[i] = (t < 0) ? S.det[24 + t] : ((t < nsym) ? soft[t] : 0.f);
+            }
+            for (int i = lane; i < C4_SOFTWIN; i += 32) s_idx[i] = (kw + i < nsym) ? idx[kw + i] : -1;
+            win_ok = true;
+            __syncwarp();
         }
-        __syncwarp();
+        const int wo = k0 - kw;
         double sp_score = 0.0;
         if (active) {
 #pragma unroll
-            for (int i = 0; i < 24; ++i) sp_score += (double)__fmul_rn(c_sync[i], s_soft[lane + i]);
+            for (int i = 0; i < 24; ++i) sp_score += (double)__fmul_rn(c_sync[i], s_soft[wo + lane + i]);
         }
         // lagging detector (:2626-2659), only while acquiring
         bool fed = false;
         float fedval = 0.f;
-        const int my_idx = active ? idx[k] : -1;
+        const int my_idx = active ? s_idx[wo + lane] : -1;
         if (active && !fine && my_idx >= 0) {
             const int lag_pos = my_idx - a.k.lag_int;
             if (lag_pos >= 4 && lag_pos < C4_RING) {
@@ -573,14 +656,34 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
         }
         // demodulate: buffer offset of the sync symbol; demodulate_discriminator passes self._sample_point (:2947-2949)
         const double off = DISC ? sample_point : ((double)idxe + 0.5) + extra;
+        // every interpolation of this event reads buffer values within 23 symbols below and (max_adj + step <= 1.125 sps)
+        // above / below `off`: staged once
+        {
+            const int need = (int)(27.0 * sps) + 24;
+            if (sps < 1.0e3 && need <= C4_WIN && fabs(off) < 1.0e9) {
+                c.win_lo = (int)floor(off - 25.0 * sps) - 8;
+                c.win_n = need;
+                __syncwarp();
+                for (int u = lane; u < need; u += 32) s_win[u] = c4_buf(c, c.win_lo + u);
+                __syncwarp();
+            } else {
+                c.win_n = 0;
+            }
+        }
         // _timing_optimize_jit (:543-644)
         double step = fine ? sps / 16.0 : sps / 8.0;
         const double step_min = sps / 200.0;
         const double max_adj = fine ? sps : sps / 2.0;
         double adj = 0.0;
-        double sc = c4_score(c, off, lane, sterm);
-        double sL = c4_score(c, off - step, lane, sterm);
-        double sR = c4_score(c, off + step, lane, sterm);
+        double sc, sL, sR;
+        {
+            const double o3[3] = {off, off - step, off + step};
+            double r3[3];
+            c4_scores<3>(c, o3, lane, sterm, r3);
+            sc = r3[0];
+            sL = r3[1];
+            sR = r3[2];
+        }
         while (step > step_min && fabs(adj) <= max_adj) {
             if (sL > sR && sL > sc) {
                 adj -= step;
@@ -595,8 +698,11 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
             } else {
                 step *= 0.5;
                 if (step > step_min) {
-                    sL = c4_score(c, (off + adj) - step, lane, sterm);
-                    sR = c4_score(c, (off + adj) + step, lane, sterm);
+                    const double o2[2] = {(off + adj) - step, (off + adj) + step};
+                    double r2[2];
+                    c4_scores<2>(c, o2, lane, sterm, r2);
+                    sL = r2[0];
+                    sR = r2[1];
                 }
             }
         }
@@ -636,23 +742,43 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
             const double start0 = (((double)idxe - 23.0 * sps) + adj) + extra;
             const double start = start0 + 24.0 * sps;
             const int nres = min(C4_MSG_DIBITS, nsym - (ke + 1));
-            for (int i = lane; i < nres; i += 32) {
-                const double pos = start + (double)i * sps;
-                const int bi = (int)pos;
-                const double mu = pos - (double)bi;
-                double v;
-                if (bi >= 0 && bi + 1 < C4_RING) {
-                    const float x1 = c4_buf(c, bi), x2 = c4_buf(c, bi + 1);
-                    if (mu < 0.0) v = (double)x1;
-                    else if (mu > 1.0) v = (double)x2;
-                    else v = (double)x1 + (double)__fsub_rn(x2, x1) * mu;
-                } else {
-                    v = (double)c4_buf(c, min(max(bi, 0), C4_RING - 1));
+            for (int i0 = 0; i0 < nres; i0 += 128) {   // four symbols per lane per trip: the eight loads go out together
+                float x1[4], x2[4];
+                double mu4[4];
+                bool two[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + 32 * u + lane;
+                    const double pos = start + (double)i * sps;
+                    const int bi = (int)pos;
+                    mu4[u] = pos - (double)bi;
+                    two[u] = bi >= 0 && bi + 1 < C4_RING;
+                    x1[u] = 0.f;
+                    x2[u] = 0.f;
+                    if (i < nres) {
+                        x1[u] = c4_buf(c, two[u] ? bi : min(max(bi, 0), C4_RING - 1));
+                        if (two[u]) x2[u] = c4_buf(c, bi + 1);
+                    }
                 }
-                const double sr = (v + c.pll) * c.gain;
-                dib[ke + 1 + i] = (unsigned char)c4_slice(sr);
-                soft[ke + 1 + i] = (float)(sr * C4_NORM);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + 32 * u + lane;
+                    if (i < nres) {
+                        double v;
+                        if (two[u]) {
+                            if (mu4[u] < 0.0) v = (double)x1[u];
+                            else if (mu4[u] > 1.0) v = (double)x2[u];
+                            else v = (double)x1[u] + (double)__fsub_rn(x2[u], x1[u]) * mu4[u];
+                        } else {
+                            v = (double)x1[u];
+                        }
+                        const double sr = (v + c.pll) * c.gain;
+                        dib[ke + 1 + i] = (unsigned char)c4_slice(sr);
+                        soft[ke + 1 + i] = (float)(sr * C4_NORM);
+                    }
+                }
             }
+            win_ok = false;   // the staged soft window is stale from ke + 1 on
             __threadfence_block();
             __syncwarp();
         }

@@ -1,0 +1,29 @@
+// Helpers for the sequential per-channel loops (symbol clocks of the P25 demodulators). One warp serves up to 32 channels
+// and nothing else runs on its SM, so every taken branch and every dependent issue is exposed latency: the helpers below
+// are straight-line code.
+#pragma once
+
+namespace wc {
+
+// Advance a float32 symbol clock by rounded additions of `st` — exactly the reference's per-sample `clock += symbol_time`
+// sequence — until it crosses 1 or `room` (>= 1) samples are consumed, at most eight samples per call. Returns the number
+// of samples consumed; `fired` says the last of them took the clock across (GE: clock >= 1, else clock > 1).
+// The eight sums are a dependent chain either way; what this removes is the compare-and-branch per sample.
+template <bool GE>
+__device__ __forceinline__ int clock_run8(float& cf, float st, int room, bool& fired) {
+    const float c0 = __fadd_rn(cf, st), c1 = __fadd_rn(c0, st), c2 = __fadd_rn(c1, st), c3 = __fadd_rn(c2, st);
+    const float c4 = __fadd_rn(c3, st), c5 = __fadd_rn(c4, st), c6 = __fadd_rn(c5, st), c7 = __fadd_rn(c6, st);
+#define WC_X(c) (GE ? ((c) >= 1.0f) : ((c) > 1.0f))
+    const unsigned m = (WC_X(c0) ? 1u : 0u) | (WC_X(c1) ? 2u : 0u) | (WC_X(c2) ? 4u : 0u) | (WC_X(c3) ? 8u : 0u) |
+                       (WC_X(c4) ? 16u : 0u) | (WC_X(c5) ? 32u : 0u) | (WC_X(c6) ? 64u : 0u) | (WC_X(c7) ? 128u : 0u);
+#undef WC_X
+    const int j = m ? __ffs(m) : 8;   // samples up to and including the first crossing
+    const int take = min(j, room);
+    const float lo = take <= 2 ? (take <= 1 ? c0 : c1) : (take == 3 ? c2 : c3);
+    const float hi = take <= 6 ? (take == 5 ? c4 : c5) : (take == 7 ? c6 : c7);
+    cf = take <= 4 ? lo : hi;
+    fired = (m != 0u) && take == j;
+    return take;
+}
+
+}  // namespace wc
