@@ -11,6 +11,6 @@ cap() {  # name regex command...
 }
 cap c4fm_sync c4fm_sync python tools/dev_c4fm.py 64 72000 1
 cap dd_mmse dd_mmse python tools/dev_discdemod.py 64 72000 1
-cap dd_dc dd_dc python tools/dev_discdemod.py 64 72000 1
+
 cap cqpsk_sync cqpsk_sync python tools/dev_cqpsk.py 64 72000 1
 ls -la $O

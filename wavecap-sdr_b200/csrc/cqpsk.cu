@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
             // the four-wide predecessor spent 48 % of the kernel here, five branches per trip in the ncu source view)
             float cf = S.clock_f;
             while (m + 1 < tile_end) {
-                m += clock_run8<true>(cf, S.sym_time_f, tile_end - 1 - m, fire);
+                m += clock_run<true>(cf, S.sym_time_f, tile_end - 1 - m, fire);
                 if (fire) break;
             }
             S.clock_f = cf;

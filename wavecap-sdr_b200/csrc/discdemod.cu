@@ -283,7 +283,7 @@ __device__ __forceinline__ void dd_walk_tile(DDState& s, const DDConst& k, const
             } else {
                 float cf = s.clock_f;
                 while (i < lim) {
-                    i += clock_run8<false>(cf, k.symbol_time_f, lim - i, tick);
+                    i += clock_run<false>(cf, k.symbol_time_f, lim - i, tick);
                     if (tick) break;
                 }
                 s.clock_f = cf;

@@ -14,6 +14,8 @@
 // some flows; the machine stops that channel at the same symbol with the same partial state and reports a code.
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/wcsdr_b200.h"
@@ -800,9 +802,17 @@ __global__ void __launch_bounds__(64) trellis12_kernel(const TrellisArgs a) {
     }
 }
 
-static bool g_tables_ready = false;
+// The tables live in __constant__ / __device__ symbols, i.e. once per device: one bit per device ordinal, filled under a
+// mutex (framers are created from several threads when a process serves several captures).
+static std::atomic<unsigned long long> g_tables_ready{0};
+static std::mutex g_tables_mu;
 static int ensure_tables() {
-    if (g_tables_ready) return 0;
+    int dev = 0;
+    WC_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (g_tables_ready.load(std::memory_order_acquire) & bit) return 0;
+    std::lock_guard<std::mutex> lk(g_tables_mu);
+    if (g_tables_ready.load(std::memory_order_acquire) & bit) return 0;
     unsigned char pw[128], lg[64];
     memset(pw, 0, sizeof(pw));
     memset(lg, 0, sizeof(lg));
@@ -838,7 +848,7 @@ static int ensure_tables() {
     WC_CUDA(cudaMemcpyToSymbol(c_gf_lg, lg, sizeof(lg)));
     WC_CUDA(cudaMemcpyToSymbol(c_fsync, sync, sizeof(sync)));
     WC_CUDA(cudaMemcpyToSymbol(g_syn, tab.data(), sizeof(uint4) * tab.size()));
-    g_tables_ready = true;
+    g_tables_ready.fetch_or(bit, std::memory_order_release);
     return 0;
 }
 
