@@ -100,3 +100,38 @@ def test_bank_of_40_channels_vs_oracle(native):
         assert abs(s["symbol_spread"] - float(oracles[c].spread)) <= 1e-6
         assert abs(s["symbol_clock"] - float(oracles[c].clock)) <= 1e-6
     assert clamped > 0  # the literal-1.6/2.4 branch was really exercised
+
+
+@pytest.mark.gpu
+def test_bank_rows_do_not_depend_on_the_bank(native):
+    """A channel's dibits / soft values / loop state are the same whichever lane, CTA and bank size it runs in: 67 channels
+    (three CTAs, the last with three live rows) against the same rows demodulated one at a time, over calls whose lengths
+    leave partial tiles (and one call shorter than the interpolator history)."""
+    from wavecap_sdr_b200.decoders.p25 import DiscriminatorBank
+    C = 67
+    rng = np.random.default_rng(77)
+    base = []
+    for c in range(5):
+        x = modulate_c4fm(random_frames(rng, n_frames=4, payload=150, gap=40), 48000, snr_db=20.0, cfo_hz=60.0 * c,
+                          timing=0.2 * c, seed=900 + c)
+        au, _ = od.fm_discriminator(x, 0.0)
+        base.append(au.astype(np.float32))
+    n = min(len(a) for a in base)
+    A = np.stack([np.roll(base[c % 5][:n], 7 * c) * [1.0, 0.3, 4.0][c % 3] for c in range(C)]).astype(np.float32)
+    bank = DiscriminatorBank(C, 48000)
+    picks = [0, 31, 32, 63, 64, 66]
+    singles = {c: DiscriminatorBank(1, 48000) for c in picks}
+    s0 = 0
+    for ln in [5, 1000, 129, 128, 4801, n]:
+        seg = A[:, s0:s0 + ln]
+        if seg.shape[1] == 0:
+            break
+        dib, soft, cnt = bank.demodulate(seg)
+        for c in picks:
+            d1, s1, c1 = singles[c].demodulate(seg[c:c + 1])
+            k = int(cnt[c])
+            assert k == int(c1[0]), (c, s0, ln)
+            assert np.array_equal(dib[c, :k], d1[0, :k]) and np.array_equal(soft[c, :k], s1[0, :k]), (c, s0, ln)
+        s0 += ln
+    for c in picks:
+        assert bank.state(c) == singles[c].state(0), c
