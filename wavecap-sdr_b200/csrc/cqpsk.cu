@@ -178,12 +178,14 @@ constexpr int CQ_CH = 8;                // channels per warp: the loop is latenc
                                         // warp stages the rows of all its channels every tile, so fewer channels per warp = less
                                         // staging per symbol and more SMs in use (64 channels: 8 warps instead of 2)
 constexpr int CQ_TILE = 96;             // new samples staged per step
-constexpr int CQ_RING = 128;            // ring slots per channel: CQ_TILE new + CQ_HIST of look-back
+constexpr int CQ_RING = 256;            // ring slots per channel: the tile being walked + its CQ_HIST of look-back + the next
+                                        // tile landing meanwhile (samples 256 apart share a slot: 2 * CQ_TILE + CQ_HIST <= 256)
+constexpr int CQ_THREADS = 64;          // warp 0 walks the symbols, warp 1 stages the next tile
 constexpr int CQ_MIRROR = CQ_HIST;      // slots 0..31 are kept twice (also at 128..159) so that look-back reads never wrap
 constexpr int CQ_PITCH = CQ_RING + CQ_MIRROR + 1;   // row pitch in float2: rows of different lanes start in different banks
 
 struct CqView {
-    const float2* ring;   // this lane's row of the shared-memory ring: sample j of the call sits in slot (j + 32) & 127,
+    const float2* ring;   // this lane's row of the shared-memory ring: sample j of the call sits in slot (j + 32) & 255,
                           // the 32 carried samples of the previous call in slots 0..31
     const float* mmse;    // shared-memory copy of the 129 x 8 table, rows padded to 9 floats: every thread (channel)
                           // indexes its own row, which would serialise on the constant cache
@@ -228,41 +230,26 @@ __device__ __forceinline__ float cq_abs(float2 z) {
     return (float)sqrt((double)z.x * (double)z.x + (double)z.y * (double)z.y);
 }
 
-__global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
+__global__ void __launch_bounds__(CQ_THREADS) cqpsk_sync_kernel(const CqSyncArgs a) {
     __shared__ float s_mmse[129 * CQ_ROW];
     __shared__ float2 s_ring[CQ_CH * CQ_PITCH];
     for (int i = threadIdx.x; i < 129 * 8; i += blockDim.x) s_mmse[(i >> 3) * CQ_ROW + (i & 7)] = c_mmse[i >> 3][i & 7];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * CQ_CH;
     const int ch = c0 + lane;
-    const bool live = lane < CQ_CH && ch < a.C;
+    const bool live = warp == 0 && lane < CQ_CH && ch < a.C;
     // the 32 carried samples of every row
-    for (int r = 0; r < CQ_CH && c0 + r < a.C; ++r) {
-        const float2 tv = a.st[c0 + r].tail[lane];
-        s_ring[r * CQ_PITCH + lane] = tv;
-        s_ring[r * CQ_PITCH + CQ_RING + lane] = tv;
+    if (warp == 0) {
+        for (int r = 0; r < CQ_CH && c0 + r < a.C; ++r) {
+            const float2 tv = a.st[c0 + r].tail[lane];
+            s_ring[r * CQ_PITCH + lane] = tv;
+            s_ring[r * CQ_PITCH + CQ_RING + lane] = tv;
+        }
     }
-    __syncwarp();
-    CqState S;
-    if (live) S = a.st[ch];
-    else memset(&S, 0, sizeof(S));
-    CqView v;
-    v.mmse = s_mmse;
-    v.ring = s_ring + (lane < CQ_CH ? lane : 0) * CQ_PITCH;
-    float2* sym_out = a.sym + (long long)(live ? ch : 0) * a.max_sym;
-    const float omega_lo = (float)(a.k.sps * 0.95), omega_hi = (float)(a.k.sps * 1.05);
-    const bool full_taps = a.k.half_sps >= 3 && a.k.full_sps + 4 < CQ_HIST;   // every Gardner tap inside the history
-    int nsym = 0;
-    // Tile loop: the filtered samples of the warp's 32 channels are staged CQ_TILE at a time into the shared-memory ring
-    // with 8-byte LDGSTS copies (lanes along the sample axis), then every lane walks its own row. Inside a tile the loop
-    // is symbol-driven: every lane first advances its own sample clock to its next firing sample (9-11 cheap iterations),
-    // then the lanes that fired run the expensive symbol body together — a plain per-sample loop would execute the body
-    // at almost every sample index because the channels' clocks are not aligned.
-    int m = -1;
-    for (int base = 0; base < a.n; base += CQ_TILE) {
+    // tile t of every row -> ring slots, 8-byte LDGSTS copies, lanes along the sample axis (warp 1 only)
+    auto stage = [&](int t) {
+        const int base = t * CQ_TILE;
         const int lim = min(CQ_TILE, a.n - base);
-        const int tile_end = base + lim;
-        __syncwarp();
         for (int r = 0; r < CQ_CH && c0 + r < a.C; ++r) {
             const float2* xr = a.filt + (long long)(c0 + r) * a.n + base;
             float2* row = s_ring + r * CQ_PITCH;
@@ -278,7 +265,31 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
         }
         cp_async_commit();
         cp_async_wait<0>();
-        __syncwarp();
+    };
+    const int T = (a.n + CQ_TILE - 1) / CQ_TILE;
+    if (warp == 1 && T > 0) stage(0);
+    __syncthreads();
+    CqState S;
+    if (live) S = a.st[ch];
+    else memset(&S, 0, sizeof(S));
+    CqView v;
+    v.mmse = s_mmse;
+    v.ring = s_ring + (lane < CQ_CH ? lane : 0) * CQ_PITCH;
+    float2* sym_out = a.sym + (long long)(live ? ch : 0) * a.max_sym;
+    const float omega_lo = (float)(a.k.sps * 0.95), omega_hi = (float)(a.k.sps * 1.05);
+    const bool full_taps = a.k.half_sps >= 3 && a.k.full_sps + 4 < CQ_HIST;   // every Gardner tap inside the history
+    int nsym = 0;
+    // Tile loop: warp 1 stages tile t + 1 into the ring while warp 0 walks tile t (one CTA barrier per tile; with the copies
+    // and their wait on the walking warp they were 19 % of the kernel). Inside a tile the loop is symbol-driven: every lane
+    // first advances its own sample clock to its next firing sample, then the lanes that fired run the expensive symbol body
+    // together — a plain per-sample loop would execute the body at almost every sample index because the channels' clocks
+    // are not aligned.
+    int m = -1;
+    for (int t = 0; t < T; ++t) {
+        const int tile_end = min((t + 1) * CQ_TILE, a.n);
+        if (warp == 1) {
+            if (t + 1 < T) stage(t + 1);
+        } else {
     for (;;) {
         bool fire = false;
         if (live && S.clock_is_f32) {
@@ -361,6 +372,8 @@ __global__ void __launch_bounds__(32) cqpsk_sync_kernel(const CqSyncArgs a) {
         while (S.clock_f >= 1.0f) S.clock_f = __fsub_rn(S.clock_f, 1.0f);
         while (S.clock_f < 0.0f) S.clock_f = __fadd_rn(S.clock_f, 1.0f);
     }
+        }
+        __syncthreads();
     }
     if (!live) return;
     // carry the ring: last 32 of (tail ++ x)
@@ -657,7 +670,7 @@ int wc_cqpsk_demod(wc_cqpsk* h, const void* iq_dev, long long chan_stride, int n
     a.n_sym = n_sym_dev;
     a.sym = h->d_sym;
     a.delta = h->d_delta;
-    cqpsk_sync_kernel<<<(C + CQ_CH - 1) / CQ_CH, 32, 0, s>>>(a);
+    cqpsk_sync_kernel<<<(C + CQ_CH - 1) / CQ_CH, CQ_THREADS, 0, s>>>(a);
     cqpsk_slice_kernel<<<dim3((max_sym + 127) / 128, C), 128, 0, s>>>(a);
     cqpsk_freq_kernel<<<C, 32, 0, s>>>(a);
     WC_CUDA(cudaGetLastError());
