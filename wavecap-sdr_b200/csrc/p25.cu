@@ -421,8 +421,15 @@ __device__ void c4_correction(const SyncCtx& c, double offset, int lane, double*
 // DISC = true: the sync loop of C4FMDemodulator.demodulate_discriminator (c4fm.py:2896-2966) instead of demodulate's
 // (:2596-2807): same detectors and lagging path, but an accepted sync only re-times the sample point — no PLL / gain
 // correction, no re-slicing, no sync counter — and the optimiser is handed the sample point as its buffer offset.
+// Two warps per channel: warp 1 extracts the symbols (a float64 recurrence on one lane + 32 interpolations per block) and
+// publishes how far it is; warp 0 runs the sync loop a window behind it. The two halves were 22 % / 78 % of a serial kernel.
+constexpr int C4_THREADS = 64;
+constexpr int C4_ADJ = 256;   // sample-point corrections warp 0 may hold back until warp 1 has delivered the final sample point
 template <bool DISC>
-__global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
+__global__ void __launch_bounds__(C4_THREADS) c4fm_sync_kernel(const SyncArgs a) {
+    __shared__ volatile int s_prod, s_done, s_nsym;
+    __shared__ volatile double s_sp;
+    __shared__ double s_adj[C4_ADJ];
     __shared__ double sterm[3 * 24];
     __shared__ float lagbuf[24 + 32];
     __shared__ float s_soft[23 + C4_SOFTWIN];   // soft[kw - 23 .. kw + 255] of the sync loop's current window
@@ -431,10 +438,14 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
     __shared__ int pos_n[2][32];
     __shared__ double pos_mu[2][32];
     __shared__ float s_taps[129 * C4_ROW];
-    for (int i = threadIdx.x; i < 129 * 8; i += 32) s_taps[(i >> 3) * C4_ROW + (i & 7)] = c_interp[i >> 3][i & 7];
-    __syncwarp();
+    for (int i = threadIdx.x; i < 129 * 8; i += C4_THREADS) s_taps[(i >> 3) * C4_ROW + (i & 7)] = c_interp[i >> 3][i & 7];
+    if (threadIdx.x == 0) {
+        s_prod = 0;
+        s_done = 0;
+    }
+    __syncthreads();
     const int ch = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     C4State& S = a.st[ch];
     const float* ph = a.ph + (long long)ch * a.n;
     unsigned char* dib = a.dibits + (long long)ch * a.max_sym;
@@ -451,8 +462,8 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
     // ---- symbol extraction at the start-of-call pll/gain (c4fm.py:649-783)
     const double pll0 = S.pll, gain0 = S.gain;
     const float prev_phase = S.prev_phase;
-    int nsym = 0;
-    {
+    if (warp == 1) {
+        int nsym = 0;
         // Positions are a sequential float64 recurrence (lane 0); the 32 interpolations of a block are parallel. The two
         // are software-pipelined: while the block's phase loads are in flight, lane 0 works out the next block's positions.
         double sp = S.sample_point;
@@ -536,12 +547,42 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
             cnt = __shfl_sync(0xffffffffu, ncnt, 0);
             done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
             cur ^= 1;
-            __syncwarp();
+            __threadfence();         // this block's dibits / soft values / indices (read back through L2) before the count
+            __syncwarp();            // that announces them
+            if (lane == 0) s_prod = nsym;
         }
-        sp = shfl_d(sp, 0);
-        S.sample_point = sp;  // every lane writes the same value
+        if (lane == 0) {
+            s_sp = sp;
+            s_nsym = nsym;
+            __threadfence();
+            s_done = 1;
+        }
+        return;
     }
-    __syncwarp();
+
+    // ---- warp 0: how far the extraction is
+    int nsym = 0x7fffffff;   // the call's symbol count, known when warp 1 is done
+    bool have_n = false;
+    auto wait_for = [&](int need) {   // until `need` symbols exist or the extraction is complete
+        while (!have_n) {
+            int d = 0, pr = 0;
+            if (lane == 0) {
+                d = s_done;
+                pr = s_prod;
+            }
+            d = __shfl_sync(0xffffffffu, d, 0);
+            pr = __shfl_sync(0xffffffffu, pr, 0);
+            if (d) {
+                nsym = s_nsym;
+                have_n = true;
+            } else if (pr >= need) {
+                break;
+            } else {
+                __nanosleep(100);
+            }
+        }
+        __threadfence_block();
+    };
 
     SyncCtx c;
     c.ring = a.ring + (long long)ch * C4_RING;
@@ -556,7 +597,21 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
     c.win_n = 0;
     c.my_sync = (lane < 24) ? c_sync[lane] : 0.f;
     int fine = S.fine, since = S.since_sync, eq_init = S.eq_init, sync_count = S.sync_count, n_events = 0;
-    double sample_point = S.sample_point;
+    // The sample point after extraction is warp 1's last value. demodulate() only ever ADDS corrections to it, in event
+    // order: they are held back (s_adj) and added in that order once it is known. demodulate_discriminator() reads it at
+    // every event: that flavour waits for the extraction first.
+    double sample_point = 0.0;
+    bool sp_known = false;
+    int n_adj = 0;
+    auto resolve_sp = [&]() {
+        if (sp_known) return;
+        wait_for(0x7fffffff);
+        __syncwarp();
+        sample_point = s_sp;
+        for (int i = 0; i < n_adj; ++i) sample_point += s_adj[i];
+        sp_known = true;
+    };
+    if (DISC) resolve_sp();
 
     if (lane < 24) lagbuf[lane] = S.lag[lane];
     __syncwarp();
@@ -574,11 +629,14 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
         // batch of loads per eight steps instead of a dependent global round trip per step
         if (!win_ok || k0 + 32 > kw + C4_SOFTWIN) {
             kw = k0;
+            // everything the steps of this window touch: its symbols, and the <= 340 an event re-slices behind them
+            wait_for(kw + C4_SOFTWIN + C4_MSG_DIBITS + 32);
+            if (k0 >= nsym) break;
             for (int i = lane; i < 23 + C4_SOFTWIN; i += 32) {
                 const int t = kw - 23 + i;
                 s_soft[i] = (t < 0) ? S.det[24 + t] : ((t < nsym) ? soft[t] : 0.f);
             }
-            for (int i = lane; i < C4_SOFTWIN; i += 32) s_idx[i] = (kw + i < nsym) ? idx[kw + i] : -1;
+            for (int i = lane; i < C4_SOFTWIN; i += 32) s_idx[i] = (kw + i < nsym) ? __ldcg(idx + kw + i) : -1;
             win_ok = true;
             __syncwarp();
         }
@@ -722,7 +780,16 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
         c4_correction(c, off + adj, lane, sterm, pa, ga);
         if (sc >= C4_THRESH) {
             if (fine) adj = fmin(fmax(adj, -a.k.max_fine_adj), a.k.max_fine_adj);
-            sample_point += adj + extra;
+            {
+                const double val = adj + extra;
+                if (!sp_known && n_adj == C4_ADJ) resolve_sp();
+                if (sp_known) {
+                    sample_point += val;
+                } else {
+                    if (lane == 0) s_adj[n_adj] = val;
+                    ++n_adj;
+                }
+            }
             // _Equalizer.apply_correction (:260-272)
             if (eq_init) {
                 c.pll += pa * C4_LOOP_GAIN;
@@ -790,6 +857,7 @@ __global__ void __launch_bounds__(32) c4fm_sync_kernel(const SyncArgs a) {
 
     // ---- state epilogue
     __syncwarp();
+    resolve_sp();
     float newdet = 0.f;
     if (lane < 24) {
         const int t = nsym - 24 + lane;
@@ -1162,7 +1230,7 @@ int wc_c4fm_demod(wc_c4fm* h, const void* iq_dev, long long chan_stride, int n_s
     y.soft = soft_dev;
     y.idx = h->d_idx;
     y.n_sym = n_sym_dev;
-    c4fm_sync_kernel<false><<<C, 32, 0, s>>>(y);
+    c4fm_sync_kernel<false><<<C, C4_THREADS, 0, s>>>(y);
     WC_CUDA(cudaGetLastError());
     h->cur ^= 1;
     return 0;
@@ -1256,7 +1324,7 @@ int wc_c4fm_demod_disc(wc_c4fm* h, const float* audio_dev, long long chan_stride
     y.soft = soft_dev;
     y.idx = h->d_idx;
     y.n_sym = n_sym_dev;
-    c4fm_sync_kernel<true><<<C, 32, 0, s>>>(y);
+    c4fm_sync_kernel<true><<<C, C4_THREADS, 0, s>>>(y);
     WC_CUDA(cudaGetLastError());
     return 0;
 }
