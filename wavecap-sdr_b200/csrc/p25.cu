@@ -632,11 +632,32 @@ __global__ void __launch_bounds__(C4_THREADS) c4fm_sync_kernel(const SyncArgs a)
             // everything the steps of this window touch: its symbols, and the <= 340 an event re-slices behind them
             wait_for(kw + C4_SOFTWIN + C4_MSG_DIBITS + 32);
             if (k0 >= nsym) break;
-            for (int i = lane; i < 23 + C4_SOFTWIN; i += 32) {
-                const int t = kw - 23 + i;
-                s_soft[i] = (t < 0) ? S.det[24 + t] : ((t < nsym) ? soft[t] : 0.f);
+            {
+                // all loads first, then the stores: through `soft` (volatile) each load would wait for the one before it —
+                // nine L2 round trips per reload, a reload per sync event (23 % of the kernel in the ncu source view).
+                // ld.cg reads L2, where warp 1's values and this warp's own re-sliced ones are after their fences.
+                const float* softp = const_cast<const float*>(soft);
+                constexpr int NQ = (23 + C4_SOFTWIN + 31) / 32;
+                float tv[NQ];
+                int ti[C4_SOFTWIN / 32];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int i = lane + 32 * q;
+                    const int t = kw - 23 + i;
+                    tv[q] = 0.f;
+                    if (i < 23 + C4_SOFTWIN) tv[q] = (t < 0) ? S.det[24 + t] : ((t < nsym) ? __ldcg(softp + t) : 0.f);
+                }
+#pragma unroll
+                for (int q = 0; q < C4_SOFTWIN / 32; ++q) {
+                    const int i = lane + 32 * q;
+                    ti[q] = (kw + i < nsym) ? __ldcg(idx + kw + i) : -1;
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    if (lane + 32 * q < 23 + C4_SOFTWIN) s_soft[lane + 32 * q] = tv[q];
+#pragma unroll
+                for (int q = 0; q < C4_SOFTWIN / 32; ++q) s_idx[lane + 32 * q] = ti[q];
             }
-            for (int i = lane; i < C4_SOFTWIN; i += 32) s_idx[i] = (kw + i < nsym) ? __ldcg(idx + kw + i) : -1;
             win_ok = true;
             __syncwarp();
         }
@@ -846,7 +867,7 @@ __global__ void __launch_bounds__(C4_THREADS) c4fm_sync_kernel(const SyncArgs a)
                 }
             }
             win_ok = false;   // the staged soft window is stale from ke + 1 on
-            __threadfence_block();
+            __threadfence();
             __syncwarp();
         }
         if (since > 3600) {
