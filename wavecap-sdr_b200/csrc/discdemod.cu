@@ -26,8 +26,10 @@
 namespace wc {
 
 constexpr int DD_TAPS = 8, DD_STEPS = 128, DD_LPF = 65;
-constexpr int DD_TILE = 128;          // samples staged per step
-constexpr int DD_ROW = DD_TILE + 1;   // row pitch in floats: 32 channel rows in 32 different banks
+constexpr int DD_CH = 8;              // channels per CTA (one lane each on the walking warp): the loops are latency-bound per symbol
+                                      // whatever the lane count, and fewer lanes = fewer shared-memory bank conflicts between
+                                      // rows read at different offsets, fewer lanes to wait for at a tile end, more SMs in use
+constexpr int DD_TILE = 512;          // samples staged per step (MMSE loop)
 
 struct DDState {
     double clock_d;     // valid while clock_py
@@ -71,13 +73,13 @@ __global__ void dd_peak_kernel(const float* __restrict__ x, long long stride, in
 // walking warp they were 80 % of its instructions (ncu source view, 36 instructions per sample against 6 of arithmetic).
 constexpr int DD_HELPERS = 3;
 constexpr int DD_THREADS = 32 * (1 + DD_HELPERS);
-constexpr int DC_TILE = 124, DC_ROW = DC_TILE + 1;   // three tiles of 32 rows inside the 48 KB static limit
+constexpr int DC_TILE = 496, DC_ROW = DC_TILE + 1;   // three tiles of DD_CH rows inside the 48 KB static limit; odd pitch
 
 template <int TILE, int PITCH, int COL0>
 __device__ __forceinline__ void dd_helper_load(float (*tile)[PITCH], const float* __restrict__ x, long long stride, int c0, int C,
                                                int base, int n, int hw, int lane) {
     const int lim = min(TILE, n - base);
-    for (int r = hw; r < 32 && c0 + r < C; r += DD_HELPERS) {
+    for (int r = hw; r < DD_CH && c0 + r < C; r += DD_HELPERS) {
         const float* xr = x + (long long)(c0 + r) * stride + base;
 #pragma unroll
         for (int k = 0; k < (TILE + 31) / 32; ++k) {
@@ -91,11 +93,11 @@ __device__ __forceinline__ void dd_helper_load(float (*tile)[PITCH], const float
 __global__ void __launch_bounds__(DD_THREADS) dd_dc_kernel(const float* __restrict__ x, long long stride, int n, int C,
                                                            const float* __restrict__ peak, DDState* __restrict__ st,
                                                            float* __restrict__ y) {
-    __shared__ float tile[3][32][DC_ROW];
+    __shared__ float tile[3][DD_CH][DC_ROW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = blockIdx.x * 32;
+    const int c0 = blockIdx.x * DD_CH;
     const int c = c0 + lane;
-    const bool live = warp == 0 && c < C;
+    const bool live = warp == 0 && lane < DD_CH && c < C;
     float gain = 1.f, dc = 0.f;
     if (live) {
         gain = st[c].gain;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(DD_THREADS) dd_dc_kernel(const float* __restri
     for (int t = 0; t <= T; ++t) {
         if (warp == 0) {
             if (live && t < T) {
-                float* row = tile[t % 3][lane];
+                float* row = tile[t % 3][lane];   // live lanes only: lane < DD_CH
                 const int lim = min(DC_TILE, n - t * DC_TILE);
                 int i = 0;
                 for (; i + 4 <= lim; i += 4) {
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(DD_THREADS) dd_dc_kernel(const float* __restri
             if (t >= 1) {   // tile t-1 is finished: out, coalesced
                 const int base = (t - 1) * DC_TILE;
                 const int lim = min(DC_TILE, n - base);
-                for (int r = hw; r < 32 && c0 + r < C; r += DD_HELPERS) {
+                for (int r = hw; r < DD_CH && c0 + r < C; r += DD_HELPERS) {
                     float* yr = y + (long long)(c0 + r) * n + base;
                     const float* tr = tile[(t - 1) % 3][r];
 #pragma unroll
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(256) dd_lpf_kernel(const float* __restrict__ x
 }
 
 constexpr int DD_PAD = DD_TAPS;                 // carried history in front of every staged row
-constexpr int DD_ROWH = DD_PAD + DD_TILE + 1;   // 137 floats: odd pitch, 32 channel rows in 32 different banks
+constexpr int DD_ROWH = DD_PAD + DD_TILE + 1;   // 521 floats: odd pitch, the channel rows start in different banks
 constexpr int DD_TROW = DD_TAPS + 1;            // interpolator rows padded to 9 floats (lanes index different rows)
 
 __device__ __forceinline__ float dd_interp(const float* __restrict__ taps, const float* __restrict__ w, int imu) {
@@ -299,19 +301,20 @@ __global__ void __launch_bounds__(DD_THREADS) dd_mmse_kernel(const float* __rest
                                                              const float* __restrict__ taps_g, DDState* __restrict__ st,
                                                              unsigned char* __restrict__ dibits, float* __restrict__ soft_out,
                                                              int max_sym, int* __restrict__ n_sym) {
-    __shared__ float tile[2][32][DD_ROWH];
+    __shared__ float tile[2][DD_CH][DD_ROWH];
     __shared__ float taps[(DD_STEPS + 1) * DD_TROW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < (DD_STEPS + 1) * DD_TAPS; i += DD_THREADS) taps[(i >> 3) * DD_TROW + (i & 7)] = taps_g[i];
-    const int c0 = blockIdx.x * 32;
+    const int c0 = blockIdx.x * DD_CH;
     const int c = c0 + lane;
-    const bool live = warp == 0 && c < C;
+    const bool live = warp == 0 && lane < DD_CH && c < C;
+    const int rl = lane < DD_CH ? lane : 0;   // row of this lane (idle lanes alias row 0, read-only)
     DDState s;
     if (live) s = st[c];
     else memset(&s, 0, sizeof(s));
     const int hidx0 = s.hidx;
     // the ring, oldest first, in front of the first tile
-    if (warp == 0)
+    if (warp == 0 && lane < DD_CH)
         for (int j = 0; j < DD_PAD; ++j) tile[0][lane][j] = live ? st[c].hist[(hidx0 + j) & 7] : 0.f;
     int count = 0;
     unsigned char* dout = dibits + (long long)c * max_sym;
@@ -326,12 +329,13 @@ __global__ void __launch_bounds__(DD_THREADS) dd_mmse_kernel(const float* __rest
         const int buf = t & 1;
         if (warp == 0) {
             const int lim = min(DD_TILE, n - t * DD_TILE);
-            const float* row = tile[buf][lane];
+            const float* row = tile[buf][rl];
             if (__any_sync(0xffffffffu, live && s.clock_py)) dd_walk_tile<true>(s, k, taps, row, lim, live, dout, sout, max_sym, count);
             else dd_walk_tile<false>(s, k, taps, row, lim, live, dout, sout, max_sym, count);
             // the last 8 samples (carried ones included when the tile is shorter) lead the next tile
 #pragma unroll
-            for (int j = 0; j < DD_PAD; ++j) tile[buf ^ 1][lane][j] = row[lim + j];
+            for (int j = 0; j < DD_PAD; ++j)
+                if (lane < DD_CH) tile[buf ^ 1][lane][j] = row[lim + j];
         } else if (t + 1 < T) {
             dd_helper_load<DD_TILE, DD_ROWH, DD_PAD>(tile[buf ^ 1], x, n, c0, C, (t + 1) * DD_TILE, n, warp - 1, lane);
             cp_async_wait<0>();
@@ -551,10 +555,10 @@ int wc_discdemod_demod(wc_discdemod* h, const float* audio_dev, long long chan_s
     if (dd_ensure(&h->d_a, &h->a_cap, (size_t)C * n_samples)) return -2;
     if (dd_ensure(&h->d_b, &h->b_cap, (size_t)C * n_samples)) return -2;
     dd_peak_kernel<<<C, 256, 0, s>>>(audio_dev, chan_stride, n_samples, h->d_peak);
-    dd_dc_kernel<<<(C + 31) / 32, DD_THREADS, 0, s>>>(audio_dev, chan_stride, n_samples, C, h->d_peak, h->d_state, h->d_a);
+    dd_dc_kernel<<<(C + DD_CH - 1) / DD_CH, DD_THREADS, 0, s>>>(audio_dev, chan_stride, n_samples, C, h->d_peak, h->d_state, h->d_a);
     dim3 lg((n_samples + 255) / 256, C);
     dd_lpf_kernel<<<lg, 256, 0, s>>>(h->d_a, n_samples, h->d_lpf, h->d_b);
-    dd_mmse_kernel<<<(C + 31) / 32, DD_THREADS, 0, s>>>(h->d_b, n_samples, C, h->k, h->d_taps, h->d_state, dibits_dev, soft_dev,
+    dd_mmse_kernel<<<(C + DD_CH - 1) / DD_CH, DD_THREADS, 0, s>>>(h->d_b, n_samples, C, h->k, h->d_taps, h->d_state, dibits_dev, soft_dev,
                                                 max_sym, n_sym_dev);
     WC_CUDA(cudaGetLastError());
     return 0;
