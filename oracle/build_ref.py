@@ -28,6 +28,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference/backend"
 ARCHIVE = os.path.join(ROOT, "oracle", "_ref", "reference_backend.tar")
 _loaded_dir: str | None = None
+# reference test modules that exercise functions install() rebinds (backend/tests/...)
+REFERENCE_TESTS = (
+    "tests/unit/test_dsp_core.py",            # soft_clip, rms_normalize, quadrature_demod, resample_poly, AGC
+    "tests/unit/test_fm_demod.py",            # wbfm_demod, nbfm_demod, deemphasis_filter, lpf_audio
+    "tests/unit/test_fft_backends.py",        # FFT backends and the registry (the "cuda" slot)
+    "tests/unit/test_pack_functions.py",      # pack_iq16 / pack_pcm16 / pack_f32
+    "tests/test_p25_dsp.py",                  # C4FMDemodulator, trellis, Golay
+    "tests/test_p25_bch.py",                  # bch_decode
+    "tests/test_reference_fec.py",            # FEC known answers
+    "tests/test_tsbk_chain.py",               # TSBK encode -> trellis -> interleave -> decode -> CRC
+    "tests/test_tsbk_decoding.py",
+    "tests/test_tsbk_decoder_roundtrip.py",
+    "tests/test_p25_message_assertions.py",   # P25P1MessageFramer assertion behaviour
+)
 
 
 def staged() -> bool:
@@ -46,6 +60,12 @@ def build(verbose: bool = False) -> bool:
             if f.endswith((".py", ".json", ".yaml", ".yml")):
                 members.append(os.path.join(base, f))
     members.append(os.path.join(SRC, "benchmark_dsp.py"))
+    # the reference's own unit tests of this path (property and known-answer tests): run unmodified against
+    # install() by tests/test_reference_unit_tests_gpu.py
+    for rel in REFERENCE_TESTS + ("tests/conftest.py", "tests/unit/__init__.py"):
+        path = os.path.join(SRC, rel)
+        if os.path.isfile(path):
+            members.append(path)
     buf = io.BytesIO()
     with tarfile.open(fileobj=buf, mode="w") as tar:        # deterministic: sorted members, zeroed metadata
         for path in members:
@@ -89,6 +109,12 @@ def unpacked_dir() -> str:
 
 def benchmark_script() -> str:
     return os.path.join(unpacked_dir(), "benchmark_dsp.py")
+
+
+def reference_test_paths() -> list[str]:
+    """the packed reference test modules that exist in the archive"""
+    d = unpacked_dir()
+    return [p for p in (os.path.join(d, rel) for rel in REFERENCE_TESTS) if os.path.isfile(p)]
 
 
 def load():

@@ -1,0 +1,50 @@
+"""GPU: the reference's OWN unit tests of this path, unmodified, against wavecap_sdr_b200.install().
+
+SURVEY §4: the reference's hot-path tests are property and known-answer tests (soft-clip bounds, RMS target, quadrature of a
+tone, resampler lengths, AGC direction, wbfm/nbfm dtype / range / length, de-emphasis and MPX attenuation, FFT backend
+registry and tone peaks, wire packers, C4FMDemodulator construction / empty input / reset, BCH / trellis / TSBK chains,
+framer assertions). They travel in oracle/_ref/reference_backend.tar (packed byte for byte by oracle/build_ref.py in the
+build container, git-ignored) and run here in a subprocess whose pytest plugin (tests/ref_install_plugin.py) calls install()
+before they are imported — so `from wavecapsdr.dsp.fm import wbfm_demod` in those files resolves to the CUDA path. The same
+files are first run with the reference untouched: whatever passes there must pass here."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from conftest import parity_note
+from oracle import build_ref
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not build_ref.staged(), reason="oracle/_ref not staged")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(paths, install: bool):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests"), ROOT, env.get("PYTHONPATH", "")])
+    env["WC_REF_NO_INSTALL"] = "0" if install else "1"
+    work = os.path.dirname(os.path.dirname(paths[0]))
+    cmd = [sys.executable, "-m", "pytest", "-p", "ref_install_plugin", *paths, "-q", "-p", "no:cacheprovider", "-c", os.devnull,
+           "--rootdir", work, "-rfE", "--tb=short"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=work, timeout=900)
+    out = r.stdout + r.stderr
+    summary = [ln for ln in r.stdout.splitlines() if re.search(r"\d+ (passed|failed|error)", ln)]
+    counts = {k: int(v) for v, k in re.findall(r"(\d+) (passed|failed|errors?|skipped|xfailed|xpassed)", summary[-1] if summary else "")}
+    failed = sorted(set(re.findall(r"^(?:FAILED|ERROR) (\S+)", out, flags=re.M)))
+    return r.returncode, counts, failed, out
+
+
+def test_reference_unit_tests_pass_against_install(native):
+    paths = build_ref.reference_test_paths()
+    if not paths:
+        pytest.skip("the archive was packed without the reference tests")
+    rc0, base, failed0, out0 = _run(paths, install=False)
+    assert base.get("passed", 0) > 100, out0[-3000:]
+    rc1, got, failed1, out1 = _run(paths, install=True)
+    assert "reference names rebound" in out1, out1[-3000:]
+    new_failures = [f for f in failed1 if f not in failed0]
+    parity_note(f"reference unit tests ({len(paths)} files): untouched {base}, against install() {got}")
+    assert not new_failures, "\n".join(new_failures) + "\n" + out1[-6000:]
+    assert got.get("passed", 0) >= base.get("passed", 0), (base, got)

@@ -225,6 +225,103 @@ class P25P1MessageFramer:
         self._running = False
         self._reference_timestamp = 0
         self._ts_base_symbols = 0
+        # host-side hook of the reference's white-box tests (tests/test_p25_message_assertions.py): an assembler placed
+        # here is dispatched by _dispatch_message() / _dispatch_tsbk() / _dispatch_pdu() below with the reference's length
+        # rules. The batch path keeps its assemblers on the device (csrc/p25frame.cu) and never touches this attribute.
+        self._message_assembler = None
+        self._previous_duid = P25P1DataUnitID.PLACE_HOLDER
+        self._detected_sync_bit_errors = 0
+
+    # ---- dispatch of a host-side assembler (p25_framer.py:655-826) -----------------------------------------------
+    _TSBK = (0x7, 0x17, 0x27)
+    _PDU = (0xC, 0x1C, 0x2C, 0x3C, 0x4C, 0x5C)
+
+    def _get_timestamp(self) -> int:
+        return self._timestamp(self._bank.get_state(0)["symbols_total"])
+
+    @staticmethod
+    def _assert_message_length(bits, duid, allow_truncated: bool = False) -> None:
+        code, name = int(duid), _duid_name(int(duid))
+        if code == int(P25P1DataUnitID.PLACE_HOLDER):
+            raise AssertionError(_ERR_TEXT[1](0, 0, name))
+        have, want = int(np.asarray(bits).size), _MESSAGE_BITS.get(code, 196)
+        if allow_truncated and have < want:
+            return
+        if code in P25P1MessageFramer._TSBK or code in P25P1MessageFramer._PDU:
+            if have < want:
+                raise AssertionError(_ERR_TEXT[2](have, want, name))
+            if have % 196:
+                raise AssertionError(_ERR_TEXT[3](have, want, name))
+        elif have != want:
+            raise AssertionError(_ERR_TEXT[4](have, want, name))
+
+    def _broadcast(self, message: "P25P1Message") -> None:
+        if self._running and self._message_listener is not None:
+            try:
+                self._message_listener(message)
+            except Exception as e:
+                _log.error(f"Error in message listener: {e}")
+
+    def _emit(self, duid, bits, corrected: int) -> None:
+        a = self._message_assembler
+        self._broadcast(P25P1Message(duid=P25P1DataUnitID.from_value(int(duid)), nac=a.nac, timestamp=self._get_timestamp(),
+                                     bits=bits, corrected_bit_count=corrected))
+
+    def _dispatch_message(self) -> None:
+        a = self._message_assembler
+        if a is None:
+            return
+        self._previous_duid = a.duid
+        if not self._running or self._message_listener is None:
+            self._message_assembler = None
+            return
+        code, truncated = int(a.duid), bool(a.was_force_completed())
+        if code in self._TSBK:
+            self._dispatch_tsbk(allow_truncated=truncated)
+        elif code in self._PDU:
+            self._dispatch_pdu(allow_truncated=truncated)
+        elif code == int(P25P1DataUnitID.PLACE_HOLDER):
+            self._message_assembler = None
+        else:
+            self._dispatch_other(allow_truncated=truncated)
+
+    def _dispatch_other(self, allow_truncated: bool = False) -> None:
+        a = self._message_assembler
+        if a is None:
+            return
+        bits = a.get_message_bits()
+        self._assert_message_length(bits, a.duid, allow_truncated=allow_truncated)
+        self._emit(a.duid, bits, self._detected_sync_bit_errors)
+        self._message_assembler = None
+
+    _dispatch_pdu = _dispatch_other   # one message with every collected block (p25_framer.py:808-826)
+
+    def _dispatch_tsbk(self, allow_truncated: bool = False) -> None:
+        """Blocks 1..3 of a TSDU leave as separate 196-bit messages; the assembler is re-armed for a continuation block
+        when the next one has not arrived yet (p25_framer.py:746-806)."""
+        a = self._message_assembler
+        if a is None:
+            return
+        bits = a.get_message_bits()
+        self._assert_message_length(bits, a.duid, allow_truncated=allow_truncated)
+        block = self._TSBK.index(int(a.duid))
+        while True:
+            lo, hi = 196 * block, 196 * (block + 1)
+            if len(bits) < hi:
+                if block == 2:
+                    self._message_assembler = None
+                return
+            self._emit(self._TSBK[block], bits[lo:hi], self._detected_sync_bit_errors if block == 0 else 0)
+            if block == 2:
+                self._message_assembler = None
+                return
+            if len(bits) >= hi + 196:
+                a.set_duid(type(a.duid)(self._TSBK[block + 1]))
+                self._assert_message_length(bits, a.duid, allow_truncated=allow_truncated)
+                block += 1
+            else:
+                a.reconfigure(type(a.duid)(self._TSBK[block + 1]))
+                return
 
     def start(self) -> None:
         self._running = True

@@ -184,6 +184,11 @@ class C4FMDemodulator:
         return dib[0, :n].copy(), soft[0, :n].copy()
 
     @property
+    def _ted_phase(self) -> float:
+        """API compatibility of the reference (c4fm.py:2523-2526): fixed symbol timing, no Gardner phase."""
+        return 0.0
+
+    @property
     def _sync_count(self) -> int:
         return self._bank.state(0)["sync_count"]
 

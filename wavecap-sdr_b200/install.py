@@ -42,6 +42,7 @@ REBIND = [
 ]
 
 _saved: list[tuple[object, str, object]] = []
+_saved_backends: list[tuple[dict, str, object]] = []
 
 
 def install(device: int | None = None) -> list[str]:
@@ -59,6 +60,14 @@ def install(device: int | None = None) -> list[str]:
         reg = importlib.import_module("wavecapsdr.dsp.fft.registry")
         from .dsp.fft.cuda_backend import CudaFFTBackend
 
+        # the reference fills its table lazily and only while it is EMPTY (registry.py:139-142): registering "cuda" first
+        # would leave "scipy" (its documented always-available fallback) unregistered for good
+        ensure = getattr(reg, "_ensure_registered", None)
+        if callable(ensure):
+            ensure()
+        backends = getattr(reg, "_BACKENDS", None)
+        if isinstance(backends, dict):
+            _saved_backends.append((backends, "cuda", backends.get("cuda")))
         reg.register("cuda")(CudaFFTBackend)
         done.append("wavecapsdr.dsp.fft.registry['cuda']")
     except Exception:  # registry shape differs: leave the reference's backends alone
@@ -70,3 +79,9 @@ def uninstall() -> None:
     while _saved:
         mod, attr, val = _saved.pop()
         setattr(mod, attr, val)
+    while _saved_backends:
+        table, name, val = _saved_backends.pop()
+        if val is None:
+            table.pop(name, None)
+        else:
+            table[name] = val
