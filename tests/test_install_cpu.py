@@ -25,3 +25,31 @@ def test_rebind_table_resolves_and_signatures_match():
         for a, b in zip(rp, op):
             if a.default is not inspect.Parameter.empty:
                 assert a.default == b.default, (ref_mod, ref_attr, a.name)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refenv.available(), reason="/root/reference not present")
+def test_install_keeps_the_reference_fft_backends_registered(monkeypatch):
+    """install() adds the "cuda" slot to the reference's FFT registry WITHOUT keeping the reference's own backends out of
+    it: the registry fills itself lazily and only while empty (dsp/fft/registry.py:139-142), and `get_backend()` falls back
+    to `_BACKENDS["scipy"]` unconditionally (:121). Found by running the reference's own tests/unit/test_fft_backends.py
+    against install(). Host logic only: the device selection is stubbed out, no kernel runs."""
+    refenv.load()
+    import wavecapsdr.dsp.fft.registry as reg
+    import wavecap_sdr_b200._native as N
+    import wavecap_sdr_b200.install as b200
+
+    saved = dict(reg._BACKENDS)
+    reg._BACKENDS.clear()                      # the state of a fresh process
+    monkeypatch.setattr(N, "init", lambda device=None: None)
+    try:
+        names = b200.install(0)
+        assert "wavecapsdr.dsp.fft.registry['cuda']" in names
+        assert "scipy" in reg._BACKENDS and reg._BACKENDS["cuda"].__module__.startswith("wavecap_sdr_b200")
+        assert reg.get_backend("scipy", fft_size=1024).name == "scipy"
+        assert reg.get_backend("auto", fft_size=1024).name in ("scipy", "fftw")   # small sizes stay on the CPU (:87-104)
+    finally:
+        b200.uninstall()
+    assert "scipy" in reg._BACKENDS and "cuda" not in reg._BACKENDS      # the slot is given back (no CuPy in this image)
+    reg._BACKENDS.clear()
+    reg._BACKENDS.update(saved)

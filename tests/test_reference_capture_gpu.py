@@ -83,3 +83,46 @@ def test_capture_parallel_dsp_matches_the_reference_through_its_own_thread_pool(
             assert e < 1e-4, (label, k, mode, e)
     parity_note(f"reference Capture._process_channels_parallel, {label} (3 worker threads, {'+'.join(m for m, _ in plan)}, "
                 f"3 chunks of {n} samples): untouched vs install(), worst audio rel-RMS {worst:.1e}")
+
+
+@pytest.mark.parametrize("fft_size", [2048, 65536])
+def test_capture_calculate_fft_through_the_registry(native, fft_size):
+    """The spectrum producer of the reference's capture loop, `Capture._calculate_fft` -> `get_backend(accelerator, fft_size)`
+    -> `FFTBackend.execute` (capture.py:2353-2404), unmodified: `fft_accelerator="scipy"` on the untouched reference against
+    `"cuda"` (and `"auto"`, which picks cuda above 4096 points, registry.py:92-104) after install() registered its backend."""
+    build_ref.load()
+    import wavecapsdr.capture as rc
+    from wavecapsdr.devices.fake import FakeDriver
+    import wavecap_sdr_b200.install as b200
+
+    fs = 61_440_000
+    rng = np.random.default_rng(9)
+    n = max(8192, fft_size) * 2
+    t = np.arange(n) / fs
+    x = (0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n)) + 0.5 * np.exp(2j * np.pi * 7.3e6 * t)
+         + 0.01 * np.exp(-2j * np.pi * 19.1e6 * t)).astype(np.complex64)
+
+    def spectrum(accelerator):
+        cap = rc.Capture(cfg=rc.CaptureConfig(id="c1", device_id="fake0", center_hz=100e6, sample_rate=fs,
+                                              fft_accelerator=accelerator), driver=FakeDriver())
+        cap._calculate_fft(x, fs, fft_size)
+        return cap._fft_backend.name, np.asarray(cap._fft_power), np.asarray(cap._fft_freqs)
+
+    name0, p0, f0 = spectrum("scipy")
+    assert name0 == "scipy"
+    b200.install(0)
+    try:
+        name1, p1, f1 = spectrum("cuda")
+        name2, p2, _ = spectrum("auto")
+        import wavecapsdr.dsp.fft as rfft
+
+        assert "scipy" in rfft.available_backends() and "cuda" in rfft.available_backends()
+    finally:
+        b200.uninstall()
+    assert name1 == "cuda" and (name2 == "cuda") == (fft_size > 4096), (name1, name2)
+    assert p1.shape == p0.shape == (fft_size,) and p1.dtype == p0.dtype
+    assert np.array_equal(f1, f0)
+    e = rel_rms(p1, p0)
+    assert e < 1e-4 and rel_rms(p2, p0) < 1e-4, e
+    assert int(np.argmax(p1)) == int(np.argmax(p0))
+    parity_note(f"reference Capture._calculate_fft, {fft_size} points: scipy backend vs the installed cuda backend, dB rel-RMS {e:.1e}")
