@@ -53,3 +53,33 @@ def test_install_keeps_the_reference_fft_backends_registered(monkeypatch):
     assert "scipy" in reg._BACKENDS and "cuda" not in reg._BACKENDS      # the slot is given back (no CuPy in this image)
     reg._BACKENDS.clear()
     reg._BACKENDS.update(saved)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refenv.available(), reason="/root/reference not present")
+def test_rebound_classes_keep_the_reference_public_surface():
+    """Every public name of a rebound reference class — methods, properties, class constants, and the attributes its
+    __init__ assigns — exists on the class that replaces it, plus the private ones the reference itself reads from outside
+    the class (`demod._sync_count`, `demod._equalizer.pll/.gain` in cli.py:759-760; `_ted_phase` in its tests)."""
+    import re
+
+    refenv.load()
+    from wavecap_sdr_b200.install import REBIND
+
+    for ref_mod, ref_attr, our_mod, our_attr in REBIND:
+        r = getattr(importlib.import_module(ref_mod), ref_attr)
+        o = getattr(importlib.import_module(our_mod), our_attr)
+        if not inspect.isclass(r):
+            continue
+        want = {n for n in dir(r) if not n.startswith("_")}
+        try:
+            want |= {n for n in re.findall(r"self\.([A-Za-z][A-Za-z0-9_]*)\s*[:=][^=]", inspect.getsource(r.__init__))}
+        except (OSError, TypeError):   # a dataclass: the generated __init__ has no source, its fields are the attributes
+            want |= {f for f in getattr(r, "__dataclass_fields__", {}) if not f.startswith("_")}
+        have = set(dir(o)) | set(re.findall(r"self\.([A-Za-z_][A-Za-z0-9_]*)", inspect.getsource(o)))
+        have |= set(getattr(o, "__dataclass_fields__", {}))
+        assert not sorted(want - have), (ref_mod, ref_attr, sorted(want - have))
+    import wavecap_sdr_b200.dsp.p25.c4fm as c4
+
+    for name in ("_sync_count", "_fine_sync", "_ted_phase", "_equalizer", "_sample_point"):
+        assert hasattr(c4.C4FMDemodulator, name), name

@@ -111,8 +111,10 @@ class CQPSKDemodulator:
     BASEBAND_CUTOFF_HZ = 7250
     MMSE_NTAPS = 32
     MMSE_NSTEPS = 128
+    EQUALIZER_GAIN = 1.0   # decoders/p25.py:216
 
     def __init__(self, sample_rate: int = 19200, symbol_rate: int = 4800) -> None:
+        self.quarter_pi, self.half_pi, self.three_quarter_pi = np.pi / 4, np.pi / 2, 3 * np.pi / 4   # :232-234
         self._bank = CQPSKBank(1, sample_rate, symbol_rate)
         self.sample_rate = sample_rate
         self.symbol_rate = symbol_rate

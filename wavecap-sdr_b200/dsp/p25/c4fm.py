@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from ... import _native as N
@@ -143,8 +145,29 @@ class C4FMBank:
         return dib, soft, cnt
 
 
+class _EqualizerView:
+    """`demod._equalizer.pll` / `.gain` as the reference's CLI prints them (cli.py:759-760): read-only view of the
+    channel's equaliser state on the device (c4fm.py:199-272)."""
+
+    def __init__(self, bank, channel: int = 0):
+        self._bank, self._channel = bank, channel
+
+    @property
+    def pll(self) -> float:
+        return float(self._bank.state(self._channel)["pll"])
+
+    @property
+    def gain(self) -> float:
+        return float(self._bank.state(self._channel)["gain"])
+
+
 class C4FMDemodulator:
     """Drop-in for wavecapsdr.dsp.p25.c4fm.C4FMDemodulator (one channel)."""
+
+    # c4fm.py:2408-2410 (the kernels use the first two: csrc/p25.cu C4_THRESH)
+    SYNC_THRESHOLD_DETECTION = 100.0
+    SYNC_THRESHOLD_OPTIMIZED = 100.0
+    SYNC_THRESHOLD_EQUALIZED = 179.0
 
     def __init__(self, sample_rate: int = 19200, symbol_rate: int = 4800, wide_pulse: bool = False, **kwargs):
         self._bank = C4FMBank(1, sample_rate, symbol_rate, wide_pulse)
@@ -182,6 +205,14 @@ class C4FMDemodulator:
         dib, soft, cnt = self._bank.demodulate_discriminator(a.reshape(1, -1))
         n = int(cnt[0])
         return dib[0, :n].copy(), soft[0, :n].copy()
+
+    @property
+    def _equalizer(self) -> _EqualizerView:
+        return _EqualizerView(self._bank, 0)
+
+    @property
+    def _sample_point(self) -> float:
+        return float(self._bank.state(0)["sample_point"])
 
     @property
     def _ted_phase(self) -> float:
@@ -241,6 +272,9 @@ class _Interpolator:
 
     NTAPS = 8
     NSTEPS = 128
+    # the 129 x 8 table of the reference class (c4fm.py:907-2202), extracted by oracle/make_tables.py; the kernels carry the
+    # same numbers (csrc/interp_taps_129x8.inc)
+    TAPS = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "interp_taps_129x8.npy"))
 
     def filter_batch(self, samples, offsets, mus) -> np.ndarray:
         import torch
