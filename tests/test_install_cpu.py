@@ -83,3 +83,35 @@ def test_rebound_classes_keep_the_reference_public_surface():
 
     for name in ("_sync_count", "_fine_sync", "_ted_phase", "_equalizer", "_sample_point"):
         assert hasattr(c4.C4FMDemodulator, name), name
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refenv.available(), reason="/root/reference not present")
+def test_install_reaches_the_by_name_aliases_of_the_package(monkeypatch):
+    """The reference binds the demodulators and DSP functions by name in the modules that use them
+    (trunking/control_channel.py:28-29, decoders/p25.py:37-39, decoders/p25_frames.py:23-25, capture.py:38-45, ...): install()
+    must replace those aliases too, or the trunking control-channel monitor keeps building the CPU demodulators. Host logic
+    only (device selection stubbed)."""
+    refenv.load()
+    import wavecapsdr.capture as rcap
+    import wavecapsdr.decoders.p25 as rp25
+    import wavecapsdr.decoders.p25_frames as rfr
+    import wavecapsdr.trunking.control_channel as rcc
+    import wavecap_sdr_b200._native as N
+    import wavecap_sdr_b200.install as b200
+
+    before = (rcc.DSPC4FMDemodulator, rcc.P25CQPSKDemodulator, rp25._WorkingC4FMDemodulator, rfr.bch_decode, rfr.trellis_decode,
+              rcap.wbfm_demod, rcap.nbfm_demod, rcap.am_demod)
+    assert all(o.__module__.startswith("wavecapsdr") for o in before)
+    monkeypatch.setattr(N, "init", lambda device=None: None)
+    try:
+        names = b200.install(0)
+        after = (rcc.DSPC4FMDemodulator, rcc.P25CQPSKDemodulator, rp25._WorkingC4FMDemodulator, rfr.bch_decode, rfr.trellis_decode,
+                 rcap.wbfm_demod, rcap.nbfm_demod, rcap.am_demod)
+        assert all(o.__module__.startswith("wavecap_sdr_b200") for o in after), [o.__module__ for o in after]
+        assert "wavecapsdr.trunking.control_channel.DSPC4FMDemodulator (alias)" in names
+    finally:
+        b200.uninstall()
+    restored = (rcc.DSPC4FMDemodulator, rcc.P25CQPSKDemodulator, rp25._WorkingC4FMDemodulator, rfr.bch_decode, rfr.trellis_decode,
+                rcap.wbfm_demod, rcap.nbfm_demod, rcap.am_demod)
+    assert all(a is b for a, b in zip(before, restored))

@@ -8,6 +8,8 @@ Every right-hand side has the reference's signature and array contracts. `uninst
 from __future__ import annotations
 
 import importlib
+import inspect
+import sys
 
 from . import _native as N
 
@@ -49,12 +51,32 @@ def install(device: int | None = None) -> list[str]:
     """Returns the list of rebound names; raises NativeError when the library or a B200 is missing."""
     N.init(device)
     done = []
+    pairs = []
     for ref_mod, ref_attr, our_mod, our_attr in REBIND:
         rm = importlib.import_module(ref_mod)
         om = importlib.import_module(our_mod)
-        _saved.append((rm, ref_attr, getattr(rm, ref_attr)))
-        setattr(rm, ref_attr, getattr(om, our_attr))
+        old, new = getattr(rm, ref_attr), getattr(om, our_attr)
+        _saved.append((rm, ref_attr, old))
+        setattr(rm, ref_attr, new)
+        pairs.append((old, new))
         done.append(f"{ref_mod}.{ref_attr}")
+    # The package binds many of these objects BY NAME at import time — `from wavecapsdr.dsp.p25.c4fm import C4FMDemodulator
+    # as DSPC4FMDemodulator` (trunking/control_channel.py:29), `... as _WorkingC4FMDemodulator` (decoders/p25.py:39),
+    # `from .dsp.fm import nbfm_demod, quadrature_demod, wbfm_demod` (capture.py:42), `bch_decode` / `trellis_decode` in
+    # decoders/p25_frames.py:23-25 ... Those aliases still point at the CPU objects: every module of the package that is
+    # already loaded is swept for them (modules imported later pick the new objects up by themselves).
+    for mod_name, mod in list(sys.modules.items()):
+        if mod is None or not (mod_name == "wavecapsdr" or mod_name.startswith("wavecapsdr.")):
+            continue
+        for attr, val in list(vars(mod).items()):
+            if not (inspect.isfunction(val) or inspect.isclass(val)):
+                continue
+            for old, new in pairs:
+                if val is old:
+                    _saved.append((mod, attr, old))
+                    setattr(mod, attr, new)
+                    done.append(f"{mod_name}.{attr} (alias)")
+                    break
     # FFT registry: take the "cuda" slot (dsp/fft/registry.py:167-174)
     try:
         reg = importlib.import_module("wavecapsdr.dsp.fft.registry")
