@@ -136,3 +136,47 @@ def test_control_channel_monitor_decodes_the_same_tsbks(native, modulation, chun
     parity_note(f"reference ControlChannelMonitor.process_iq ({modulation}), chunks of {chunk}: {ref_diag['frames']} frames, {ref_diag['attempts']} TSBK "
                 f"blocks, {ref_diag['crc_pass']} CRC passes, {len(ref_results)} parsed results — identical after install() "
                 f"(counters, BCH / trellis diagnostics, raw TSBK bytes, parsed fields)")
+
+
+def test_control_channel_scanner_class_of_the_reference_after_install(native):
+    """`trunking.cc_scanner.ControlChannelScanner` (what `TrunkingSystem` builds, system.py:997, and drives with
+    `scan_all` / `log_scan_results` / `get_best_channel` / `should_roam` / `get_stats`, :1621-1708, :2767): the reference's
+    class on the box's CPU against the class install() puts in its place, same band — dB values within 2e-4 dB, sync
+    decisions, sample counts, best channel, ranking and roam decision identical."""
+    from oracle import cc_scanner as oc
+
+    build_ref.load()
+    import wavecapsdr.trunking.cc_scanner as rs
+    import wavecapsdr.trunking.system as rsys
+    import wavecap_sdr_b200.install as b200
+
+    x, center, freqs = oc.synth_band()
+
+    def run():
+        sc = rs.ControlChannelScanner(center_hz=center, sample_rate=1_200_000, control_channels=list(freqs))
+        m = sc.scan_all(x)
+        sc.log_scan_results()
+        sc._current_channel_hz = freqs[3]
+        return type(sc).__module__, m, sc.get_best_channel()[0], [f for f, _ in sc.get_channel_ranking()], sc.should_roam(freqs[3]), sc.get_stats()
+
+    mod0, m0, best0, rank0, roam0, st0 = run()
+    assert mod0.startswith("wavecapsdr")
+    names = b200.install(0)
+    try:
+        assert "wavecapsdr.trunking.system.ControlChannelScanner (alias)" in names
+        assert rsys.ControlChannelScanner.__module__.startswith("wavecap_sdr_b200")
+        mod1, m1, best1, rank1, roam1, st1 = run()
+    finally:
+        b200.uninstall()
+    assert mod1.startswith("wavecap_sdr_b200") and sorted(m1) == sorted(m0)
+    worst = 0.0
+    for f, a in m0.items():
+        b = m1[f]
+        for k in ("power_db", "peak_power_db", "noise_floor_db", "snr_db"):
+            worst = max(worst, abs(getattr(a, k) - getattr(b, k)))
+        assert a.sync_detected == b.sync_detected and a.sample_count == b.sample_count, f
+    assert worst < 2e-4 and (best1, rank1, roam1) == (best0, rank0, roam0)
+    assert st1["channels_measured"] == st0["channels_measured"] and sorted(st1["measurements"]) == sorted(st0["measurements"])
+    assert st1["current_channel_hz"] == st0["current_channel_hz"]
+    parity_note(f"reference ControlChannelScanner ({len(m0)} candidates at 1.2 MS/s): CPU class vs the installed one, worst |dB| difference "
+                f"{worst:.1e}, sync decisions / best channel / ranking / roam decision identical")

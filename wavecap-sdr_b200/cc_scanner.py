@@ -6,7 +6,9 @@ noise probes included, once per candidate on the CPU (trunking/cc_scanner.py:166
 """
 from __future__ import annotations
 
+import asyncio
 import ctypes as C
+import logging
 import time
 from dataclasses import dataclass, field
 
@@ -14,6 +16,8 @@ import numpy as np
 
 from . import _native as N
 from .dsp import _stages as S
+
+_log = logging.getLogger(__name__)
 
 
 @dataclass
@@ -73,9 +77,20 @@ class ControlChannelScanner:
     _last_scan_time: float = 0.0
     _measurements: dict = field(default_factory=dict)
     _current_channel_hz: float | None = None
+    # fields of the reference dataclass kept for its callers (trunking/system.py reads and assigns scanner attributes):
+    # the reference never fills the buffer fields either (cc_scanner.py:91-98)
+    _iq_buffer: list = field(default_factory=list)
+    _buffer_samples: int = 0
+    _measurement_in_progress: bool = False
+    _measurement_complete: asyncio.Event = field(default_factory=asyncio.Event)
+    _sync_pattern: np.ndarray | None = None
 
     def __post_init__(self) -> None:
         N.ensure_init()
+        # +3 -> dibit 1, -3 -> dibit 3 (cc_scanner.py:102-107); the kernel carries the same word (csrc/ccscan.cu)
+        self._sync_pattern = np.array([1, 1, 1, 1, 1, 3, 1, 1, 3, 3, 1, 1, 3, 3, 3, 3, 1, 3, 1, 3, 3, 3, 3, 3], dtype=np.uint8)
+        _log.info(f"ControlChannelScanner initialized: center={self.center_hz / 1e6:.4f} MHz, "
+                  f"channels={len(self.control_channels)}")
 
     def get_channel_offset(self, freq_hz: float) -> float:
         return freq_hz - self.center_hz
@@ -128,3 +143,26 @@ class ControlChannelScanner:
         if (not cur.sync_detected and best[1].sync_detected) or best[1].snr_db - cur.snr_db >= roam_threshold_db:
             return best[0]
         return None
+
+    def log_scan_results(self) -> None:
+        """cc_scanner.py:471-485"""
+        if not self._measurements:
+            _log.info("No control channel measurements available")
+            return
+        _log.info("Control Channel Scan Results:")
+        _log.info("-" * 60)
+        for i, (_freq, m) in enumerate(self.get_channel_ranking()):
+            _log.info(f"  {i + 1}. {m}{' *' if i == 0 else ''}")
+        _log.info("-" * 60)
+
+    def get_stats(self) -> dict:
+        """cc_scanner.py:487-505"""
+        return {
+            "channels_configured": len(self.control_channels),
+            "channels_measured": len(self._measurements),
+            "last_scan_time": float(self._last_scan_time),
+            "current_channel_hz": float(self._current_channel_hz) if self._current_channel_hz else None,
+            "measurements": {f"{freq / 1e6:.4f}_MHz": {"power_db": float(m.power_db), "snr_db": float(m.snr_db),
+                                                      "sync_detected": bool(m.sync_detected)}
+                             for freq, m in self._measurements.items()},
+        }

@@ -41,6 +41,9 @@ REBIND = [
     ("wavecapsdr.decoders.p25", "P25P1MessageFramer", "wavecap_sdr_b200.decoders.p25_framer", "P25P1MessageFramer"),
     # voice-channel discriminator path
     ("wavecapsdr.decoders.p25", "DiscriminatorDemodulator", "wavecap_sdr_b200.decoders.p25", "DiscriminatorDemodulator"),
+    # control-channel scanner: one library call per scan instead of one CPU chain per candidate (trunking/system.py:997)
+    ("wavecapsdr.trunking.cc_scanner", "ControlChannelScanner", "wavecap_sdr_b200.cc_scanner", "ControlChannelScanner"),
+    ("wavecapsdr.trunking.cc_scanner", "ChannelMeasurement", "wavecap_sdr_b200.cc_scanner", "ChannelMeasurement"),
 ]
 
 _saved: list[tuple[object, str, object]] = []
