@@ -126,3 +126,52 @@ def test_capture_calculate_fft_through_the_registry(native, fft_size):
     assert e < 1e-4 and rel_rms(p2, p0) < 1e-4, e
     assert int(np.argmax(p1)) == int(np.argmax(p0))
     parity_note(f"reference Capture._calculate_fft, {fft_size} points: scipy backend vs the installed cuda backend, dB rel-RMS {e:.1e}")
+
+
+@pytest.mark.parametrize("fs,mode,offset", [(2_400_000, "wbfm", 200_000.0), (2_400_000, "nbfm", -350_000.0),
+                                            (48_000, "am", 6_000.0), (48_000, "ssb", -9_000.0)])
+def test_channel_process_iq_chunk_after_install(native, fs, mode, offset):
+    """`Channel.process_iq_chunk` (capture.py:950-1200), the per-channel entry of the reference that calls `freq_shift`,
+    `wbfm_demod` / `nbfm_demod` / `am_demod` / `ssb_demod` through the names capture.py bound at import time (:38-45):
+    install() replaces those aliases, so this unmodified coroutine runs the CUDA chain. Audio handed to `_broadcast` and
+    the channel's `signal_power_db` before / after."""
+    import asyncio
+
+    build_ref.load()
+    import wavecapsdr.capture as rc
+    import wavecap_sdr_b200.install as b200
+
+    n = max(8192, fs // 20)
+    chunks = _carriers(fs, n, 2, [(mode, offset)], seed=11)
+
+    def run():
+        ch = rc.Channel(rc.ChannelConfig(id="ch0", capture_id="c1", mode=mode, offset_hz=offset))
+        ch.start()
+        got = []
+
+        async def keep(audio):
+            got.append(np.array(audio, copy=True))
+
+        ch._broadcast = keep
+
+        async def go():
+            for k in range(chunks.shape[0]):
+                await ch.process_iq_chunk(chunks[k], fs)
+
+        asyncio.run(go())
+        return got, ch.signal_power_db
+
+    ref, p0 = run()
+    assert len(ref) == 2 and rc.wbfm_demod.__module__.startswith("wavecapsdr")
+    b200.install(0)
+    try:
+        assert rc.wbfm_demod.__module__.startswith("wavecap_sdr_b200") and rc.am_demod.__module__.startswith("wavecap_sdr_b200")
+        run()
+        got, p1 = run()
+    finally:
+        b200.uninstall()
+    assert len(got) == len(ref)
+    worst = max(rel_rms(b, a) for a, b in zip(ref, got))
+    assert all(a.dtype == b.dtype and a.shape == b.shape for a, b in zip(ref, got))
+    assert worst < 1e-4 and abs(p1 - p0) < 1e-3, (mode, worst, p0, p1)
+    parity_note(f"reference Channel.process_iq_chunk ({mode}, {fs} S/s): audio before / after install() rel-RMS {worst:.1e}")
