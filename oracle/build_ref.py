@@ -28,20 +28,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference/backend"
 ARCHIVE = os.path.join(ROOT, "oracle", "_ref", "reference_backend.tar")
 _loaded_dir: str | None = None
-# reference test modules that exercise functions install() rebinds (backend/tests/...)
-REFERENCE_TESTS = (
-    "tests/unit/test_dsp_core.py",            # soft_clip, rms_normalize, quadrature_demod, resample_poly, AGC
-    "tests/unit/test_fm_demod.py",            # wbfm_demod, nbfm_demod, deemphasis_filter, lpf_audio
-    "tests/unit/test_fft_backends.py",        # FFT backends and the registry (the "cuda" slot)
-    "tests/unit/test_pack_functions.py",      # pack_iq16 / pack_pcm16 / pack_f32
-    "tests/test_p25_dsp.py",                  # C4FMDemodulator, trellis, Golay
-    "tests/test_p25_bch.py",                  # bch_decode
-    "tests/test_reference_fec.py",            # FEC known answers
-    "tests/test_tsbk_chain.py",               # TSBK encode -> trellis -> interleave -> decode -> CRC
-    "tests/test_tsbk_decoding.py",
-    "tests/test_tsbk_decoder_roundtrip.py",
-    "tests/test_p25_message_assertions.py",   # P25P1MessageFramer assertion behaviour
+# The reference's own test suite (backend/tests/test_*.py and tests/unit/test_*.py), run unmodified against
+# install() by tests/test_reference_unit_tests_gpu.py. Left out: the hardware-marked integration directory and the four
+# files that import the FastAPI app (its `slowapi` dependency is not in this image, so they cannot be collected either way).
+REFERENCE_TESTS_EXCLUDED = ("tests/test_captures_channels.py", "tests/test_config_reload.py", "tests/test_trunking_api.py",
+                            "tests/test_trunking_voice_api.py")
+# the subset that exercises functions install() rebinds directly (kept as a list for the report)
+REFERENCE_TESTS_OF_THE_PATH = (
+    "tests/unit/test_dsp_core.py", "tests/unit/test_fm_demod.py", "tests/unit/test_fft_backends.py",
+    "tests/unit/test_pack_functions.py", "tests/test_p25_dsp.py", "tests/test_p25_bch.py", "tests/test_reference_fec.py",
+    "tests/test_tsbk_chain.py", "tests/test_tsbk_decoding.py", "tests/test_tsbk_decoder_roundtrip.py",
+    "tests/test_p25_message_assertions.py",
 )
+
+
+def _reference_tests() -> tuple[str, ...]:
+    import glob
+
+    found = sorted(glob.glob(os.path.join(SRC, "tests", "test_*.py")) + glob.glob(os.path.join(SRC, "tests", "unit", "test_*.py")))
+    rel = tuple(os.path.relpath(p, SRC) for p in found)
+    return tuple(r for r in rel if r not in REFERENCE_TESTS_EXCLUDED)
 
 
 def staged() -> bool:
@@ -62,7 +68,7 @@ def build(verbose: bool = False) -> bool:
     members.append(os.path.join(SRC, "benchmark_dsp.py"))
     # the reference's own unit tests of this path (property and known-answer tests): run unmodified against
     # install() by tests/test_reference_unit_tests_gpu.py
-    for rel in REFERENCE_TESTS + ("tests/conftest.py", "tests/unit/__init__.py"):
+    for rel in _reference_tests() + ("tests/conftest.py", "tests/unit/__init__.py"):
         path = os.path.join(SRC, rel)
         if os.path.isfile(path):
             members.append(path)
@@ -111,10 +117,17 @@ def benchmark_script() -> str:
     return os.path.join(unpacked_dir(), "benchmark_dsp.py")
 
 
-def reference_test_paths() -> list[str]:
-    """the packed reference test modules that exist in the archive"""
+def reference_test_paths(only_the_path: bool = False) -> list[str]:
+    """the packed reference test modules (all of them, or the subset that calls rebound functions directly)"""
     d = unpacked_dir()
-    return [p for p in (os.path.join(d, rel) for rel in REFERENCE_TESTS) if os.path.isfile(p)]
+    if only_the_path:
+        rels = REFERENCE_TESTS_OF_THE_PATH
+    else:
+        import glob
+
+        rels = sorted(os.path.relpath(p, d) for p in glob.glob(os.path.join(d, "tests", "test_*.py")) +
+                      glob.glob(os.path.join(d, "tests", "unit", "test_*.py")))
+    return [p for p in (os.path.join(d, rel) for rel in rels) if os.path.isfile(p)]
 
 
 def load():

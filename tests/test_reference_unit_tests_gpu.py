@@ -27,7 +27,7 @@ def _run(paths, install: bool):
     env["WC_REF_NO_INSTALL"] = "0" if install else "1"
     work = os.path.dirname(os.path.dirname(paths[0]))
     cmd = [sys.executable, "-m", "pytest", "-p", "ref_install_plugin", *paths, "-q", "-p", "no:cacheprovider", "-c", os.devnull,
-           "--rootdir", work, "-rfE", "--tb=short"]
+           "--rootdir", work, "-rfE", "--tb=short", "-m", "not hardware", "-o", "addopts="]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=work, timeout=900)
     out = r.stdout + r.stderr
     summary = [ln for ln in r.stdout.splitlines() if re.search(r"\d+ (passed|failed|error)", ln)]
@@ -36,15 +36,31 @@ def _run(paths, install: bool):
     return r.returncode, counts, failed, out
 
 
-def test_reference_unit_tests_pass_against_install(native):
-    paths = build_ref.reference_test_paths()
-    if not paths:
-        pytest.skip("the archive was packed without the reference tests")
+def _check(paths, label, floor):
     rc0, base, failed0, out0 = _run(paths, install=False)
-    assert base.get("passed", 0) > 100, out0[-3000:]
+    assert base.get("passed", 0) >= floor, out0[-3000:]
     rc1, got, failed1, out1 = _run(paths, install=True)
     assert "reference names rebound" in out1, out1[-3000:]
     new_failures = [f for f in failed1 if f not in failed0]
-    parity_note(f"reference unit tests ({len(paths)} files): untouched {base}, against install() {got}")
+    parity_note(f"reference {label} ({len(paths)} files): untouched {base}, against install() {got}")
     assert not new_failures, "\n".join(new_failures) + "\n" + out1[-6000:]
     assert got.get("passed", 0) >= base.get("passed", 0), (base, got)
+
+
+def test_reference_unit_tests_pass_against_install(native):
+    """the 11 files that call rebound functions directly"""
+    paths = build_ref.reference_test_paths(only_the_path=True)
+    if not paths:
+        pytest.skip("the archive was packed without the reference tests")
+    _check(paths, "unit tests of the path", 100)
+
+
+def test_whole_reference_suite_passes_against_install(native):
+    """Every test file of backend/tests/ and backend/tests/unit/ that can be collected in this image (all but the four that
+    import the FastAPI app, whose `slowapi` dependency is absent, and the hardware-marked integration directory): trunking
+    configuration and workers, validation, decoders, FEC, packers, device detection ... — with install() active nothing that
+    passed before may fail."""
+    paths = build_ref.reference_test_paths()
+    if len(paths) < 30:
+        pytest.skip("the archive holds only the path's test files")
+    _check(paths, "test suite", 500)
