@@ -13,8 +13,9 @@
 //           rounded once instead of a float32 product.
 // Compiled with -fmad=false: every float32 operation of the reference rounds on its own.
 //
-// Kernels: peak (parallel), gain + DC tracker (sequential per channel, 32 channels per warp, tiles staged through
-// shared memory), low-pass (parallel, float64 accumulation, rounded once), MMSE loop (sequential per channel, staged).
+// Kernels: peak (parallel), gain + DC tracker (sequential per channel: DD_CH channels per CTA, one lane each on the walking
+// warp, tiles moved by helper warps), low-pass (parallel, float64 accumulation, rounded once), MMSE loop (sequential per
+// channel, same layout; profiles/r03_seq_notes.md has the measurements behind that layout).
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -67,7 +68,6 @@ __global__ void dd_peak_kernel(const float* __restrict__ x, long long stride, in
 }
 
 // auto gain (p25.py:1213-1222) and DC removal (:1224-1229); y = x*gain - dc, float32 throughout
-// one warp stages the next tile of its 32 channel rows with 4-byte LDGSTS copies while the lanes walk the current one
 // Layout of the two sequential kernels: warp 0 walks the rows (lane = channel); three helper warps move the tiles between
 // global and shared memory (4-byte LDGSTS in, coalesced stores out), one CTA barrier per tile. With the copies on the
 // walking warp they were 80 % of its instructions (ncu source view, 36 instructions per sample against 6 of arithmetic).
